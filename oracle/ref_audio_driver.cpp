@@ -1,0 +1,143 @@
+// TEST INFRASTRUCTURE ONLY (oracle). Never linked into the product library.
+//
+// extern "C" wrapper around the UNMODIFIED reference resonator bank
+// (/root/reference/src/audio/ModalAudio.{h,cpp}). The reference sources are compiled where they
+// lie by oracle/Makefile; only this driver lives in the repo. Output: oracle/_ref/libme_ref_audio.so.
+//
+// It mirrors the harness the reference's own tests use (tests/ModalBench.h:47-81 `ModalScene`):
+// AddModalObject + TuneModalObject + OutGain, InstallModalBank, one discard block, then
+// EnqueueModalEvent / RenderModal.
+#include "audio/ModalAudio.h"
+#include "audio/ModalModes.h"
+
+#include <entt/entity/entity.hpp>
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+namespace {
+struct RefScene {
+    ModalAudio Audio;
+    ModalBank Next;
+    bool Installed{false};
+};
+
+ModalModes MakeModes(uint32_t n_modes, uint32_t n_points, const float *freqs, const float *t60s, const float *shapes, const float *positions, const uint32_t *indices, uint32_t n_indices) {
+    ModalModes modes;
+    modes.Freqs.assign(freqs, freqs + n_modes);
+    modes.T60s.assign(t60s, t60s + n_modes);
+    modes.Shapes.resize(n_points);
+    modes.Positions.resize(n_points);
+    for (uint32_t p = 0; p < n_points; ++p) {
+        modes.Shapes[p].resize(n_modes);
+        for (uint32_t k = 0; k < n_modes; ++k) {
+            const float *s = shapes + (size_t(p) * n_modes + k) * 3;
+            modes.Shapes[p][k] = vec3{s[0], s[1], s[2]};
+        }
+        if (positions) modes.Positions[p] = vec3{positions[3 * p], positions[3 * p + 1], positions[3 * p + 2]};
+    }
+    if (indices) modes.Indices.assign(indices, indices + n_indices);
+    return modes;
+}
+ModalBank &BankOf(RefScene &s) { return s.Installed ? LiveBank(s.Audio) : s.Next; }
+} // namespace
+
+extern "C" {
+// Layout-identical to the reference's ModalEvent (ModalAudio.h:28-37), 48 bytes.
+struct RefEvent {
+    uint32_t Kind, Object, ExPos;
+    float Jx, Jy, Jz, PulseStep, PulseGamma, AccelAmp, ClickB0, ClickA1, ClickA2;
+};
+static_assert(sizeof(RefEvent) == sizeof(ModalEvent));
+
+void *ref_scene_create(float sample_rate, uint32_t renderers) {
+    auto *s = new RefScene;
+    s->Audio.RenderPool.SetSize(renderers);
+    s->Next.SampleRate = sample_rate;
+    return s;
+}
+void ref_scene_free(void *h) { delete static_cast<RefScene *>(h); }
+
+// shapes: [point][mode][3]; positions: [point][3]; indices: triangles over the points.
+uint32_t ref_scene_add_object(void *h, uint32_t n_modes, uint32_t n_points, const float *freqs, const float *t60s, const float *shapes, const float *positions, const uint32_t *indices, uint32_t n_indices, float out_gain, float radius_scale) {
+    auto &s = *static_cast<RefScene *>(h);
+    const auto modes = MakeModes(n_modes, n_points, freqs, t60s, shapes, positions, indices, n_indices);
+    auto &b = s.Next;
+    const auto slot = AddModalObject(b, entt::entity{uint32_t(b.Entities.size())}, modes);
+    TuneModalObject(b, slot, modes.Freqs, modes.T60s, radius_scale);
+    b.OutGain[slot] = out_gain;
+    return slot;
+}
+void ref_scene_retune(void *h, uint32_t slot, const float *freqs, const float *t60s, uint32_t n, float radius_scale) {
+    auto &s = *static_cast<RefScene *>(h);
+    TuneModalObject(BankOf(s), slot, {freqs, n}, {t60s, n}, radius_scale);
+}
+void ref_scene_set_gain(void *h, uint32_t slot, float out_gain, float listener_gain) {
+    auto &b = BankOf(*static_cast<RefScene *>(h));
+    b.OutGain[slot] = out_gain;
+    b.ListenerGain[slot] = listener_gain;
+}
+void ref_scene_set_click_gain(void *h, float g) { static_cast<RefScene *>(h)->Audio.ClickGain.store(g); }
+void ref_scene_set_max_impacts(void *h, uint32_t n) { static_cast<RefScene *>(h)->Audio.MaxImpacts.store(n); }
+
+// InstallModalBank, then one discard block as ModalScene does (tests/ModalBench.h:64-69).
+void ref_scene_install(void *h, uint32_t discard_frames) {
+    auto &s = *static_cast<RefScene *>(h);
+    InstallModalBank(s.Audio, s.Next);
+    s.Installed = true;
+    if (discard_frames) {
+        std::vector<float> discard(discard_frames, 0.f);
+        RenderModal(s.Audio, discard.data(), discard_frames);
+    }
+}
+void ref_scene_enqueue(void *h, const RefEvent *e) {
+    ModalEvent ev;
+    std::memcpy(&ev, e, sizeof ev);
+    EnqueueModalEvent(static_cast<RefScene *>(h)->Audio, ev);
+}
+// RenderModal adds into `out`.
+void ref_scene_render(void *h, float *out, uint32_t frames) { RenderModal(static_cast<RefScene *>(h)->Audio, out, frames); }
+
+uint32_t ref_scene_mode_total(void *h) { return uint32_t(BankOf(*static_cast<RefScene *>(h)).CoeffRe.size()); }
+uint32_t ref_scene_object_count(void *h) { return uint32_t(BankOf(*static_cast<RefScene *>(h)).Entities.size()); }
+uint32_t ref_scene_active_impacts(void *h) { return uint32_t(BankOf(*static_cast<RefScene *>(h)).Impacts.size()); }
+uint64_t ref_scene_events_dropped(void *h) { return static_cast<RefScene *>(h)->Audio.EventsDropped; }
+
+// Per-mode columns, concatenated over objects. which: 0 CoeffRe 1 CoeffIm 2 StateRe 3 StateIm 4 RadiationGain
+// 5 RadiationArea 6 OutPhaseIm 7 OutPhaseRe 8 DeflectionGain 9 QuadCompliance 10 QuadDriveScale
+void ref_scene_get_mode_column(void *h, uint32_t which, float *out) {
+    auto &b = BankOf(*static_cast<RefScene *>(h));
+    const std::vector<float> *cols[]{&b.CoeffRe, &b.CoeffIm, &b.StateRe, &b.StateIm, &b.RadiationGain, &b.RadiationArea, &b.OutPhaseIm, &b.OutPhaseRe, &b.DeflectionGain, &b.QuadCompliance, &b.QuadDriveScale};
+    if (which < std::size(cols)) std::memcpy(out, cols[which]->data(), cols[which]->size() * sizeof(float));
+}
+// Per-object columns. which: 0 ModeOffset 1 ModeCount 2 TunedModeCount 3 LiveModeCount 4 Ringing
+void ref_scene_get_object_column_u32(void *h, uint32_t which, uint32_t *out) {
+    auto &b = BankOf(*static_cast<RefScene *>(h));
+    const auto n = b.Entities.size();
+    for (size_t o = 0; o < n; ++o) {
+        switch (which) {
+            case 0: out[o] = b.ModeOffset[o]; break;
+            case 1: out[o] = b.ModeCount[o]; break;
+            case 2: out[o] = b.TunedModeCount[o]; break;
+            case 3: out[o] = b.LiveModeCount[o]; break;
+            case 4: out[o] = b.Ringing[o]; break;
+            default: out[o] = 0;
+        }
+    }
+}
+// which: 0 RadiantRadius 1 DeflectionScale 2 OutGain 3 ListenerGain
+void ref_scene_get_object_column_f32(void *h, uint32_t which, float *out) {
+    auto &b = BankOf(*static_cast<RefScene *>(h));
+    const std::vector<float> *cols[]{&b.RadiantRadius, &b.DeflectionScale, &b.OutGain, &b.ListenerGain};
+    if (which < std::size(cols)) std::memcpy(out, cols[which]->data(), cols[which]->size() * sizeof(float));
+}
+
+// The recoil click filter the reference's own test builds its events with (ModalAudio.h:92-99).
+void ref_click_filter(double radius, double volume, double mass, double sample_rate, float *b0_a1_a2) {
+    const auto f = RecoilClickFilter(radius, volume, mass, sample_rate);
+    b0_a1_a2[0] = f.B0;
+    b0_a1_a2[1] = f.A1;
+    b0_a1_a2[2] = f.A2;
+}
+}
