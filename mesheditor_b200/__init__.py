@@ -1,0 +1,7 @@
+"""mesheditor_b200 — B200-native linear modal analysis / synthesis (the hot path of khiner/MeshEditor).
+
+The product is libme_modal.so: hand-written sm_100a CUDA kernels behind the C ABI in include/me_modal.h.
+This package is only the ctypes face of that ABI. Importing it never imports anything under oracle/.
+"""
+from ._lib import LIB_PATH, MeError, MeModalEvent, lib  # noqa: F401
+from .audio import ModalBank, impact_event, measure_fp32_fma_rate, silence_event  # noqa: F401

@@ -1,0 +1,750 @@
+// Host side of the resonator bank. See bank.h.
+#include "bank.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <numbers>
+#include <numeric>
+#include <queue>
+
+namespace me {
+namespace {
+// ModalAudio.h:41-46.
+constexpr float AirDensity{1.204f}, SpeedOfSound{343.f}, ListenerDistance{1.f};
+constexpr float Ln1000 = 3 * std::numbers::ln10_v<float>;
+constexpr float Pi = std::numbers::pi_v<float>;
+
+constexpr size_t PartialBudgetBytes = size_t(1) << 30; // per-CTA partial mixes kept in HBM per launch window
+
+uint32_t PaddedModes(uint32_t count) { return (count + kLanes - 1) / kLanes * kLanes; }
+
+struct Vec3 {
+    float x, y, z;
+};
+Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+Vec3 Cross(Vec3 a, Vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+float Dot(Vec3 a, Vec3 b) {
+    const float px = a.x * b.x, py = a.y * b.y, pz = a.z * b.z;
+    return px + py + pz;
+}
+Vec3 At(const float *xyz, size_t i) { return {xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]}; }
+
+bool HasClick(const HostImpact &im) { return im.AccelAmp != 0.f && im.ClickB0 != 0.f; }
+
+// One sample of the contact pulse and its click filter, in the reference's float operation order (ModalAudio.cpp:518-531).
+inline void StepImpact(HostImpact &im) {
+    float cur = 0.f;
+    if (im.SamplesLeft > 0) {
+        const float re = im.PhaseRe * im.RotRe - im.PhaseIm * im.RotIm;
+        im.PhaseIm = im.PhaseRe * im.RotIm + im.PhaseIm * im.RotRe;
+        im.PhaseRe = re;
+        cur = im.Gamma * 0.5f * (1.f - im.PhaseRe);
+        --im.SamplesLeft;
+    }
+    const float u = im.AccelAmp * cur;
+    const float y = im.ClickB0 * u + im.ClickZ1;
+    im.ClickZ1 = -im.ClickA1 * y + im.ClickZ2;
+    im.ClickZ2 = -im.ClickB0 * u - im.ClickA2 * y;
+}
+} // namespace
+
+Bank::Bank(float sample_rate, int device) : SampleRate(sample_rate), Device(device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) Fail(ME_CUDA_ERROR, "no CUDA device is available (there is no CPU fallback)");
+    if (device < 0 || device >= count) Fail(ME_BAD_ARG, "device %d out of range (%d visible)", device, count);
+    ME_CUDA(cudaSetDevice(Device));
+    ME_CUDA(cudaStreamCreateWithFlags(&OwnStream, cudaStreamNonBlocking));
+    ME_CUDA(cudaEventCreate(&EvBegin));
+    ME_CUDA(cudaEventCreate(&EvEnd));
+    // Diagnostic overrides: samples advanced per state jump (1, 2 or 4) and segments of the scan along time.
+    if (const char *steps = std::getenv("ME_RESONATOR_STEPS")) Steps = std::atoi(steps);
+    if (const char *segments = std::getenv("ME_RESONATOR_SEGMENTS")) RequestedSegments = uint32_t(std::atoi(segments));
+}
+
+Bank::~Bank() {
+    cudaSetDevice(Device);
+    if (OwnStream) cudaStreamSynchronize(OwnStream), cudaStreamDestroy(OwnStream);
+    for (auto e : {EvBegin, EvEnd})
+        if (e) cudaEventDestroy(e);
+    for (auto e : EventPool) cudaEventDestroy(e);
+}
+
+void Bank::CheckSlot(uint32_t slot) const {
+    if (slot >= ObjectCount()) Fail(ME_BAD_ARG, "object slot %u out of range (%u objects)", slot, ObjectCount());
+}
+void Bank::RequireInstalled() const {
+    if (!Installed) Fail(ME_BAD_ARG, "the bank has not been installed (me_bank_install)");
+}
+
+// AddModalObject, ModalAudio.cpp:291-338.
+uint32_t Bank::AddObject(uint32_t count, uint32_t n_points, const float *shapes, const float *positions, const uint32_t *indices, uint32_t n_indices) {
+    if ((count && n_points && !shapes) || (n_indices && (!indices || !positions))) Fail(ME_BAD_ARG, "null shape/position/index array");
+    for (uint32_t t = 0; t < n_indices; ++t)
+        if (indices[t] >= n_points) Fail(ME_BAD_ARG, "triangle index %u out of range (%u points)", indices[t], n_points);
+    const auto slot = ObjectCount();
+    const size_t k0 = CoeffRe.size();
+    ModeOffset.push_back(uint32_t(k0));
+    ModeCount.push_back(count);
+    TunedModeCount.push_back(count);
+    ShapeOffset.push_back(uint32_t(ShapeX.size()));
+    ShapePoints.push_back(n_points);
+    OutGain.push_back(0.f);
+    ListenerGain.push_back(1.f);
+    DeflectionScale.push_back(1.f);
+    for (auto *col : {&CoeffRe, &CoeffIm, &RadiationGain, &DeflectionGain, &QuadCompliance, &QuadDriveScale}) col->resize(k0 + count, 0.f);
+    OutPhaseIm.resize(k0 + count, 1.f);
+    OutPhaseRe.resize(k0 + count, 0.f);
+    const size_t n_shapes = size_t(n_points) * count;
+    for (size_t i = 0; i < n_shapes; ++i) {
+        ShapeX.push_back(shapes[3 * i]);
+        ShapeY.push_back(shapes[3 * i + 1]);
+        ShapeZ.push_back(shapes[3 * i + 2]);
+    }
+    // Radiating strength: surface integral of the squared normal shape by centroid quadrature.
+    RadiationArea.resize(k0 + count, 0.f);
+    float total_area = 0.f;
+    for (size_t t = 0; t + 2 < n_indices; t += 3) {
+        const auto i = indices[t], j = indices[t + 1], l = indices[t + 2];
+        const Vec3 cr = Cross(At(positions, j) - At(positions, i), At(positions, l) - At(positions, i));
+        const float doubled = std::sqrt(Dot(cr, cr));
+        if (doubled <= 0.f) continue;
+        const Vec3 n{cr.x / doubled, cr.y / doubled, cr.z / doubled};
+        const float area = doubled / 2;
+        total_area += area;
+        for (uint32_t k = 0; k < count; ++k) {
+            const Vec3 a = At(shapes, size_t(i) * count + k), b = At(shapes, size_t(j) * count + k), c = At(shapes, size_t(l) * count + k);
+            const Vec3 shape{(a.x + b.x + c.x) / 3.f, (a.y + b.y + c.y) / 3.f, (a.z + b.z + c.z) / 3.f};
+            const float normal = Dot(shape, n);
+            RadiationArea[k0 + k] += area * normal * normal;
+        }
+    }
+    RadiantRadius.push_back(std::sqrt(total_area / (4 * Pi)));
+    return slot;
+}
+
+// TuneModalObject, ModalAudio.cpp:340-393. Runs on the host with the same libm calls as the reference, so the
+// coefficients that reach HBM are the reference's, bit for bit.
+void Bank::TuneObject(uint32_t object, const float *freqs, const float *t60s, uint32_t n, float radius_scale) {
+    CheckSlot(object);
+    if (n && (!freqs || !t60s)) Fail(ME_BAD_ARG, "null frequency/T60 array");
+    const auto k0 = ModeOffset[object];
+    const auto count = std::min(ModeCount[object], n);
+    const float sr = SampleRate;
+    const float radius = RadiantRadius[object] * radius_scale;
+    DeflectionScale[object] = 1.f / (radius_scale * radius_scale * radius_scale);
+    for (uint32_t k = 0; k < count; ++k) {
+        const float freq = freqs[k], t60 = t60s[k];
+        const size_t m = size_t(k0) + k;
+        if (!std::isfinite(freq) || !std::isfinite(t60) || freq <= 0.f || freq >= sr / 2 - 1 || t60 <= 0.f) {
+            CoeffRe[m] = CoeffIm[m] = RadiationGain[m] = DeflectionGain[m] = QuadCompliance[m] = QuadDriveScale[m] = 0.f;
+            OutPhaseIm[m] = 1.f;
+            OutPhaseRe[m] = 0.f;
+            continue;
+        }
+        const auto omega = 2 * Pi * freq / sr;
+        const float omega_si = 2 * Pi * freq;
+        const float ka = omega_si * radius / SpeedOfSound;
+        const float sigma = ka * ka / (1 + ka * ka);
+        const float area = RadiationArea[m] / radius_scale;
+        const float radiation_rate = AirDensity * SpeedOfSound * sigma * area * 0.5f;
+        const auto decay = std::exp(-(Ln1000 / t60 + radiation_rate) / sr);
+        CoeffRe[m] = decay * std::cos(omega);
+        CoeffIm[m] = decay * std::sin(omega);
+        const float gain = AirDensity * SpeedOfSound * std::sqrt(sigma * RadiationArea[m] / (4 * Pi)) / ListenerDistance;
+        RadiationGain[m] = gain;
+        const float spread = sigma * Pi * (2.f * std::fmod(0.6180339887f * float(k + 1), 1.0f) - 1.f);
+        OutPhaseIm[m] = std::cos(spread);
+        OutPhaseRe[m] = std::sin(spread);
+        DeflectionGain[m] = gain > 0.f ? 1.f / (gain * omega_si) : 0.f;
+        const float dt = 1.f / sr;
+        const float central = dt * (1 + decay * decay + 2 * decay * std::cos(omega)) / 4;
+        QuadCompliance[m] = central;
+        QuadDriveScale[m] = central * omega_si / (decay * std::sin(omega));
+    }
+    uint32_t live = ModeCount[object];
+    while (live > 0 && CoeffRe[k0 + live - 1] == 0.f && CoeffIm[k0 + live - 1] == 0.f) --live;
+    TunedModeCount[object] = live;
+    if (Installed) TuningDirty = true, RetunedObjects.push_back(object);
+}
+
+// SetModalObjectShapes, ModalAudio.cpp:395-410.
+void Bank::SetObjectShapes(uint32_t object, uint32_t n_modes, uint32_t n_points, const float *shapes) {
+    CheckSlot(object);
+    if (ModeCount[object] != n_modes || ShapePoints[object] != n_points) Fail(ME_BAD_ARG, "shape layout differs from the object's (%u modes x %u points)", ModeCount[object], ShapePoints[object]);
+    const size_t begin = ShapeOffset[object], n = size_t(n_modes) * n_points;
+    for (size_t i = 0; i < n; ++i) {
+        ShapeX[begin + i] = shapes[3 * i];
+        ShapeY[begin + i] = shapes[3 * i + 1];
+        ShapeZ[begin + i] = shapes[3 * i + 2];
+    }
+    if (Installed) TuningDirty = true;
+}
+
+void Bank::SetGain(uint32_t slot, float out_gain, float listener_gain) {
+    CheckSlot(slot);
+    OutGain[slot] = out_gain;
+    ListenerGain[slot] = listener_gain;
+}
+
+// Pads every object to whole chunks, places objects so that none of at most 256 chunks straddles a CTA, and uploads
+// the per-mode columns. Also used for live retunes.
+void Bank::UploadTuning(cudaStream_t stream) {
+    const uint32_t n_obj = ObjectCount();
+    ObjFirstChunk.assign(n_obj, 0);
+    ObjStride.assign(n_obj, 0);
+    ObjPaddedShapeOffset.assign(n_obj, 0);
+    std::vector<uint32_t> tuned_chunks(n_obj);
+    std::vector<uint8_t> obj_cull(n_obj);
+    uint64_t cursor = 0;
+    size_t shape_total = 0;
+    for (uint32_t o = 0; o < n_obj; ++o) {
+        ObjStride[o] = PaddedModes(ModeCount[o]);
+        const uint32_t chunks = ObjStride[o] / kLanes;
+        const bool fits = chunks <= kBlockThreads;
+        if (!fits || cursor % kBlockThreads + chunks > kBlockThreads) cursor = (cursor + kBlockThreads - 1) / kBlockThreads * kBlockThreads;
+        ObjFirstChunk[o] = uint32_t(cursor);
+        cursor += chunks;
+        obj_cull[o] = fits;
+        tuned_chunks[o] = (TunedModeCount[o] + kLanes - 1) / kLanes;
+        ObjPaddedShapeOffset[o] = uint32_t(shape_total);
+        shape_total += size_t(ObjStride[o]) * ShapePoints[o];
+    }
+    cursor = (cursor + kBlockThreads - 1) / kBlockThreads * kBlockThreads;
+    if (cursor * kLanes >= (uint64_t(1) << 31) || shape_total + kLanes >= (size_t(1) << 32)) Fail(ME_BAD_ARG, "bank too large for 32-bit mode indexing");
+    const uint32_t chunks = uint32_t(cursor);
+    const size_t padded = size_t(chunks) * kLanes;
+    const bool layout_changed = chunks != NChunks;
+    NChunks = chunks;
+
+    std::vector<float> cre(padded, 0.f), cim(padded, 0.f), pim(padded, 1.f), pre(padded, 0.f), rg(padded, 0.f);
+    std::vector<float> sx(shape_total, 0.f), sy(shape_total, 0.f), sz(shape_total, 0.f);
+    std::vector<uint32_t> chunk_obj(chunks, kNoObject);
+    for (uint32_t o = 0; o < n_obj; ++o) {
+        const size_t dst = size_t(ObjFirstChunk[o]) * kLanes, src = ModeOffset[o];
+        // Modes past TunedModeCount are muted (coefficient 0 already), so the whole ModeCount is copied.
+        std::copy_n(CoeffRe.begin() + src, ModeCount[o], cre.begin() + dst);
+        std::copy_n(CoeffIm.begin() + src, ModeCount[o], cim.begin() + dst);
+        std::copy_n(OutPhaseIm.begin() + src, ModeCount[o], pim.begin() + dst);
+        std::copy_n(OutPhaseRe.begin() + src, ModeCount[o], pre.begin() + dst);
+        std::copy_n(RadiationGain.begin() + src, ModeCount[o], rg.begin() + dst);
+        for (uint32_t p = 0; p < ShapePoints[o]; ++p) {
+            const size_t s_src = ShapeOffset[o] + size_t(p) * ModeCount[o], s_dst = ObjPaddedShapeOffset[o] + size_t(p) * ObjStride[o];
+            std::copy_n(ShapeX.begin() + s_src, ModeCount[o], sx.begin() + s_dst);
+            std::copy_n(ShapeY.begin() + s_src, ModeCount[o], sy.begin() + s_dst);
+            std::copy_n(ShapeZ.begin() + s_src, ModeCount[o], sz.begin() + s_dst);
+        }
+        for (uint32_t c = 0; c < ObjStride[o] / kLanes; ++c) chunk_obj[ObjFirstChunk[o] + c] = o;
+    }
+    // Polar form of every coefficient in FP64, for the powers c^m the scan along time needs.
+    std::vector<double> log_rho(padded), theta(padded);
+    for (size_t m = 0; m < padded; ++m) {
+        const double re = cre[m], im = cim[m];
+        const double rho = std::hypot(re, im);
+        log_rho[m] = rho > 0 ? std::log(rho) : -std::numeric_limits<double>::infinity();
+        theta[m] = rho > 0 ? std::atan2(im, re) : 0.0;
+    }
+    (void)layout_changed;
+    DCoeffRe.Upload(cre, stream), DCoeffIm.Upload(cim, stream), DPhaseIm.Upload(pim, stream), DPhaseRe.Upload(pre, stream), DRadiationGain.Upload(rg, stream);
+    DShapeX.Upload(sx, stream), DShapeY.Upload(sy, stream), DShapeZ.Upload(sz, stream);
+    DChunkObject.Upload(chunk_obj, stream);
+    DObjShapeOffset.Upload(ObjPaddedShapeOffset, stream), DObjStride.Upload(ObjStride, stream), DObjFirstChunk.Upload(ObjFirstChunk, stream);
+    DObjTunedChunks.Upload(tuned_chunks, stream), DObjCull.Upload(obj_cull, stream);
+    DLogRho.Upload(log_rho, stream), DTheta.Upload(theta, stream);
+    // The uploads read pageable host vectors that die at the end of this scope.
+    ME_CUDA(cudaStreamSynchronize(stream));
+    TuningDirty = false;
+}
+
+// InstallModalBank, ModalAudio.cpp:277-289: a freshly built bank starts silent, and events queued against the old
+// slot layout are dropped by the next render.
+void Bank::Install() {
+    ME_CUDA(cudaSetDevice(Device));
+    UploadTuning(OwnStream);
+    const size_t padded = std::max<size_t>(size_t(NChunks) * kLanes, 1);
+    const uint32_t n_obj = ObjectCount();
+    for (int side = 0; side < 2; ++side) {
+        DStateRe[side].Reserve(padded), DStateIm[side].Reserve(padded);
+        DChunkLive[side].Reserve(std::max<uint32_t>(NChunks, 1)), DObjRinging[side].Reserve(std::max<uint32_t>(n_obj, 1));
+    }
+    Side = 0;
+    ME_CUDA(cudaMemsetAsync(DStateRe[0].Ptr, 0, padded * sizeof(float), OwnStream));
+    ME_CUDA(cudaMemsetAsync(DStateIm[0].Ptr, 0, padded * sizeof(float), OwnStream));
+    ME_CUDA(cudaMemsetAsync(DChunkLive[0].Ptr, 1, std::max<uint32_t>(NChunks, 1), OwnStream));
+    ME_CUDA(cudaMemsetAsync(DObjRinging[0].Ptr, 0, std::max<uint32_t>(n_obj, 1), OwnStream));
+    DSpeculation.Reserve(1);
+    ME_CUDA(cudaStreamSynchronize(OwnStream));
+    Impacts.clear();
+    FlushEvents = true;
+    Installed = true;
+}
+
+// EnqueueModalEvent, ModalAudio.cpp:417-425.
+MeStatus Bank::Enqueue(const MeModalEvent &e) {
+    const auto write = EventWrite.load(std::memory_order_relaxed);
+    if (write - EventRead.load(std::memory_order_acquire) >= EventCapacity) {
+        ++EventsDropped;
+        SetLastError("event queue full (%u entries); event dropped", EventCapacity);
+        return ME_QUEUE_FULL;
+    }
+    Events[write % EventCapacity] = e;
+    EventWrite.store(write + 1, std::memory_order_release);
+    return ME_OK;
+}
+
+BankView Bank::View() const {
+    return {
+        .NChunks = NChunks,
+        .NObjects = ObjectCount(),
+        .CoeffRe = DCoeffRe.Ptr,
+        .CoeffIm = DCoeffIm.Ptr,
+        .StateRe = DStateRe[Side].Ptr,
+        .StateIm = DStateIm[Side].Ptr,
+        .StateOutRe = DStateRe[Side ^ 1].Ptr,
+        .StateOutIm = DStateIm[Side ^ 1].Ptr,
+        .PhaseIm = DPhaseIm.Ptr,
+        .PhaseRe = DPhaseRe.Ptr,
+        .RadiationGain = DRadiationGain.Ptr,
+        .LogRho = DLogRho.Ptr,
+        .Theta = DTheta.Ptr,
+        .ChunkObject = DChunkObject.Ptr,
+        .ShapeX = DShapeX.Ptr,
+        .ShapeY = DShapeY.Ptr,
+        .ShapeZ = DShapeZ.Ptr,
+        .ObjShapeOffset = DObjShapeOffset.Ptr,
+        .ObjStride = DObjStride.Ptr,
+        .ObjFirstChunk = DObjFirstChunk.Ptr,
+        .ObjTunedChunks = DObjTunedChunks.Ptr,
+        .ObjMixGain = DObjMixGain.Ptr,
+        .ObjEnergyScale = DObjEnergyScale.Ptr,
+        .ObjCull = DObjCull.Ptr,
+        .ChunkLive = DChunkLive[Side].Ptr,
+        .ObjRinging = DObjRinging[Side].Ptr,
+        .ChunkLiveOut = DChunkLive[Side ^ 1].Ptr,
+        .ObjRingingOut = DObjRinging[Side ^ 1].Ptr,
+    };
+}
+
+// The device half of SilenceObject (ModalAudio.cpp:53-64) and of TuneModalObject's LiveModeCount reset (:392).
+void Bank::ResetObjectOnDevice(uint32_t o, bool clear_state, cudaStream_t stream) {
+    const size_t first = size_t(ObjFirstChunk[o]) * kLanes, count = size_t(ObjStride[o]);
+    if (clear_state) {
+        ME_CUDA(cudaMemsetAsync(DStateRe[Side].Ptr + first, 0, count * sizeof(float), stream));
+        ME_CUDA(cudaMemsetAsync(DStateIm[Side].Ptr + first, 0, count * sizeof(float), stream));
+        ME_CUDA(cudaMemsetAsync(DObjRinging[Side].Ptr + o, 0, 1, stream));
+    }
+    if (count) ME_CUDA(cudaMemsetAsync(DChunkLive[Side].Ptr + ObjFirstChunk[o], 1, count / kLanes, stream));
+}
+
+namespace {
+// End of the render block holding `frame` (frames relative to the span, which starts on a block boundary).
+uint32_t BlockEnd(uint32_t frame, uint32_t block_frames, uint32_t span_frames) {
+    const uint64_t end = (uint64_t(frame) / block_frames + 1) * block_frames;
+    return uint32_t(std::min<uint64_t>(end, span_frames));
+}
+
+// Walks one impact from its start to its retirement or the end of the span (RenderModal :506-538, :557-561).
+// `s.AtEnd` becomes the state the next span adopts when it survives.
+void Schedule(ScheduledImpact &s, uint32_t block_frames, uint32_t span_frames) {
+    s.AtEnd = s.AtStart;
+    if (!HasClick(s.AtStart)) {
+        // The click filter stays at rest, so the impact is retired at the end of the block its pulse ends in.
+        const uint64_t pulse_end = uint64_t(s.Start) + s.AtStart.SamplesLeft;
+        if (pulse_end <= span_frames) {
+            s.End = BlockEnd(s.AtStart.SamplesLeft ? uint32_t(pulse_end - 1) : s.Start, block_frames, span_frames);
+            s.Survives = false;
+        } else {
+            for (uint32_t f = s.Start; f < span_frames; ++f) StepImpact(s.AtEnd);
+            s.End = span_frames;
+            s.Survives = true;
+        }
+        return;
+    }
+    uint32_t f = s.Start;
+    while (f < span_frames) {
+        const uint32_t end = BlockEnd(f, block_frames, span_frames);
+        for (; f < end; ++f) StepImpact(s.AtEnd);
+        if (s.AtEnd.SamplesLeft == 0 && std::abs(s.AtEnd.ClickZ1) + std::abs(s.AtEnd.ClickZ2) < 1e-12f) {
+            s.End = end;
+            s.Survives = false;
+            return;
+        }
+    }
+    s.End = span_frames;
+    s.Survives = true;
+}
+
+// ActivateImpact, ModalAudio.cpp:28-51.
+HostImpact MakeImpact(const MeModalEvent &e) {
+    const auto theta = 2 * Pi * e.pulse_step;
+    const float steps = std::ceil(1.f / e.pulse_step);
+    return {
+        .Object = e.object,
+        .ExPos = e.ex_pos,
+        .SamplesLeft = steps >= 4294967040.f ? 4294967040u : uint32_t(steps),
+        .Jx = e.jx,
+        .Jy = e.jy,
+        .Jz = e.jz,
+        .PhaseRe = 1.f,
+        .PhaseIm = 0.f,
+        .RotRe = std::cos(theta),
+        .RotIm = std::sin(theta),
+        .Gamma = e.pulse_gamma,
+        .AccelAmp = e.accel_amp,
+        .ClickB0 = e.click_b0,
+        .ClickA1 = e.click_a1,
+        .ClickA2 = e.click_a2,
+        .ClickZ1 = 0.f,
+        .ClickZ2 = 0.f,
+    };
+}
+} // namespace
+
+void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<ScheduledImpact> &scheduled, float *out_dev, cudaStream_t stream) {
+    const uint32_t n_obj = ObjectCount();
+    const uint32_t n = uint32_t(scheduled.size());
+    // Impacts sorted by (start, object): the order of the pulse rows in the mix.
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const auto &x = scheduled[a], &y = scheduled[b];
+        return x.Start != y.Start ? x.Start < y.Start : x.AtStart.Object < y.AtStart.Object;
+    });
+    CallImpacts.resize(n);
+    CallTails.resize(n);
+    CallPulseWarps.clear();
+    uint64_t force_total = 0, delta_total = 0, row_total = 0;
+    uint32_t max_len = 0;
+    bool any_click = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto &s = scheduled[order[i]];
+        const auto &im = s.AtStart;
+        const uint32_t len = uint32_t(std::min<uint64_t>(im.SamplesLeft, frames - s.Start));
+        const uint32_t chunks = ObjStride[im.Object] / kLanes;
+        const uint32_t warps = len ? (chunks + 31) / 32 : 0;
+        if (force_total + len >= (uint64_t(1) << 32) || delta_total + ObjStride[im.Object] >= (uint64_t(1) << 32) || row_total + uint64_t(warps) * len >= (uint64_t(1) << 32))
+            Fail(ME_BAD_ARG, "impact buffers exceed 2^32 entries in one span");
+        CallImpacts[i] = {.Start = s.Start, .Len = len, .ForceOff = uint32_t(force_total), .ExPos = im.ExPos, .Jx = im.Jx, .Jy = im.Jy, .Jz = im.Jz, .Object = im.Object, .PhaseRe = im.PhaseRe, .PhaseIm = im.PhaseIm, .RotRe = im.RotRe, .RotIm = im.RotIm, .End = s.End, .DeltaOff = uint32_t(delta_total), .HasClick = HasClick(im) ? 1u : 0u, .Pad = 0};
+        CallTails[i] = {.Gamma = im.Gamma, .AccelAmp = im.AccelAmp, .ClickB0 = im.ClickB0, .ClickA1 = im.ClickA1, .ClickA2 = im.ClickA2, .ClickZ1 = im.ClickZ1, .ClickZ2 = im.ClickZ2, .ClickGain = ClickGain * ListenerGain[im.Object]};
+        for (uint32_t w = 0; w < warps; ++w) {
+            CallPulseWarps.push_back({.Impact = i, .Chunk0 = w * 32, .RowOff = uint32_t(row_total), .Pad = 0});
+            row_total += len;
+        }
+        any_click |= HasClick(im);
+        max_len = std::max(max_len, len);
+        force_total += len;
+        if (len) delta_total += ObjStride[im.Object];
+    }
+    // Per object: increments in frame order, and the merged intervals during which it holds a live impact.
+    CallInjectPtr.assign(n_obj + 1, 0), CallExcitePtr.assign(n_obj + 1, 0);
+    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> inject(n_obj), excite(n_obj);
+    for (uint32_t i = 0; i < n; ++i) {
+        const auto &im = CallImpacts[i];
+        if (im.Len) inject[im.Object].push_back({im.Start + im.Len, im.DeltaOff});
+        if (im.End > im.Start) excite[im.Object].push_back({im.Start, im.End});
+    }
+    CallInjectFrame.clear(), CallInjectDelta.clear(), CallExciteBegin.clear(), CallExciteEnd.clear();
+    for (uint32_t o = 0; o < n_obj; ++o) {
+        std::stable_sort(inject[o].begin(), inject[o].end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+        for (const auto &[frame, delta] : inject[o]) CallInjectFrame.push_back(frame), CallInjectDelta.push_back(delta);
+        CallInjectPtr[o + 1] = uint32_t(CallInjectFrame.size());
+        std::sort(excite[o].begin(), excite[o].end());
+        size_t first = CallExciteBegin.size();
+        for (const auto &[begin, end] : excite[o]) {
+            if (CallExciteBegin.size() > first && begin <= CallExciteEnd.back()) CallExciteEnd.back() = std::max(CallExciteEnd.back(), end);
+            else CallExciteBegin.push_back(begin), CallExciteEnd.push_back(end);
+        }
+        CallExcitePtr[o + 1] = uint32_t(CallExciteBegin.size());
+    }
+    MixGain.resize(n_obj), EnergyScale.resize(n_obj);
+    for (uint32_t o = 0; o < n_obj; ++o) {
+        MixGain[o] = OutGain[o] * ListenerGain[o];
+        EnergyScale[o] = MixGain[o] != 0.f ? (OutGain[o] * OutGain[o]) / (MixGain[o] * MixGain[o]) : 0.f;
+    }
+
+    DImpacts.Upload(CallImpacts, stream), DTails.Upload(CallTails, stream), DPulseWarps.Upload(CallPulseWarps, stream);
+    DInjectPtr.Upload(CallInjectPtr, stream), DInjectFrame.Upload(CallInjectFrame, stream), DInjectDelta.Upload(CallInjectDelta, stream);
+    DExcitePtr.Upload(CallExcitePtr, stream), DExciteBegin.Upload(CallExciteBegin, stream), DExciteEnd.Upload(CallExciteEnd, stream);
+    DObjMixGain.Upload(MixGain, stream), DObjEnergyScale.Upload(EnergyScale, stream);
+    Stats.h2d_bytes += n * (sizeof(DevImpact) + sizeof(DevImpactTail)) + CallPulseWarps.size() * sizeof(PulseWarp) + (CallInjectPtr.size() + CallExcitePtr.size() + 2 * CallInjectFrame.size() + 2 * CallExciteBegin.size() + 2 * n_obj) * 4;
+    DForce.Reserve(std::max<uint64_t>(force_total, 1)), DDeltaRe.Reserve(std::max<uint64_t>(delta_total, 1)), DDeltaIm.Reserve(std::max<uint64_t>(delta_total, 1)), DPulseRows.Reserve(std::max<uint64_t>(row_total, 1));
+    // Slots of the delta buffers the pulse kernel does not write (chunks past the object in a warp's tail are skipped,
+    // every chunk inside the object is written) need no clearing.
+
+    LaunchForceKernel(DImpacts.Ptr, DTails.Ptr, n, DForce.Ptr, stream, Counter);
+    const PulsePlan pulses{.NPulseWarps = uint32_t(CallPulseWarps.size()), .Warps = DPulseWarps.Ptr, .Impacts = DImpacts.Ptr, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
+    BankView view = View();
+    LaunchPulseKernel(view, pulses, stream, Counter);
+
+    const uint32_t rows = ResonatorRows(NChunks);
+    Stats.time_segments = 1;
+    if (rows == 0) {
+        ME_CUDA(cudaMemsetAsync(out_dev, 0, size_t(frames) * sizeof(float), stream));
+    } else {
+        // Launch windows bound the partial-row buffer; they start on block boundaries.
+        const uint64_t blocks_in_budget = std::max<uint64_t>(1, PartialBudgetBytes / (uint64_t(rows) * sizeof(float)) / block_frames);
+        const uint32_t window = uint32_t(std::min<uint64_t>(blocks_in_budget * block_frames, frames));
+        DPartial.Reserve(size_t(rows) * window);
+        const uint32_t ctas = NChunks / kBlockThreads;
+        for (uint32_t begin = 0; begin < frames; begin += window) {
+            const uint32_t wf = std::min(window, frames - begin);
+            const uint32_t blocks = (wf + block_frames - 1) / block_frames;
+            // Segments of the block-parallel scan along time: enough (chunk-CTA x segment) units to even out the
+            // 148 SMs, each a whole number of blocks.
+            uint32_t segments = RequestedSegments;
+            if (segments == 0) segments = SpeculationFailed ? 1 : std::min<uint32_t>(64, (16 * 296 + ctas - 1) / ctas);
+            segments = std::max(1u, std::min(segments, blocks));
+            const uint32_t seg_blocks = (blocks + segments - 1) / segments;
+            segments = (blocks + seg_blocks - 1) / seg_blocks;
+            RenderPlan plan{
+                .SpanFrames = frames,
+                .BlockFrames = block_frames,
+                .FrameBegin = begin,
+                .Frames = wf,
+                .NSegments = segments,
+                .SegmentFrames = seg_blocks * block_frames,
+                .ObjInjectPtr = DInjectPtr.Ptr,
+                .InjectFrame = DInjectFrame.Ptr,
+                .InjectDelta = DInjectDelta.Ptr,
+                .ObjExcitePtr = DExcitePtr.Ptr,
+                .ExciteBegin = DExciteBegin.Ptr,
+                .ExciteEnd = DExciteEnd.Ptr,
+                .DeltaRe = DDeltaRe.Ptr,
+                .DeltaIm = DDeltaIm.Ptr,
+                .Partial = DPartial.Ptr,
+                .SegStateRe = nullptr,
+                .SegStateIm = nullptr,
+                .Speculation = DSpeculation.Ptr,
+                .Debug = std::getenv("ME_RESONATOR_DEBUG") ? 1u : 0u,
+            };
+            cudaEvent_t k0 = NextEvent(), k1 = NextEvent();
+            ME_CUDA(cudaEventRecord(k0, stream));
+            if (segments > 1) {
+                const size_t seg_floats = size_t(segments - 1) * NChunks * kLanes;
+                DSegRe.Reserve(seg_floats), DSegIm.Reserve(seg_floats);
+                plan.SegStateRe = DSegRe.Ptr, plan.SegStateIm = DSegIm.Ptr;
+                ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
+                LaunchSegmentScan(view, plan, DSegRe.Ptr, DSegIm.Ptr, stream, Counter);
+                LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+                uint32_t failed = 0;
+                ME_CUDA(cudaMemcpyAsync(&failed, DSpeculation.Ptr, sizeof failed, cudaMemcpyDeviceToHost, stream));
+                ME_CUDA(cudaStreamSynchronize(stream));
+                if (failed) {
+                    if (std::getenv("ME_RESONATOR_DEBUG")) fprintf(stderr, "[me] speculation failed: code %u (window %u+%u, %u segments)\n", failed, begin, wf, segments);
+                    // A culling decision inside the window: render it again sequentially in time (still on the GPU).
+                    SpeculationFailed = true;
+                    ++Stats.time_segments; // reported as "segments + 1 fallback" below
+                    plan.NSegments = 1;
+                    plan.SegmentFrames = blocks * block_frames;
+                    LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+                    segments = 1;
+                }
+            } else {
+                LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+            }
+            ME_CUDA(cudaEventRecord(k1, stream));
+            Stats.time_segments = std::max(Stats.time_segments, segments);
+            LaunchMixKernel(DPartial.Ptr, rows, plan, pulses, out_dev + begin, stream, Counter);
+            Side ^= 1;
+            view = View();
+        }
+    }
+    if (any_click) LaunchClickKernel(DImpacts.Ptr, DTails.Ptr, n, out_dev, frames, stream, Counter);
+    for (uint32_t o = 0; o < n_obj; ++o) Stats.mode_samples += uint64_t(TunedModeCount[o]) * frames;
+}
+
+cudaEvent_t Bank::NextEvent() {
+    if (EventsUsed == EventPool.size()) {
+        cudaEvent_t e;
+        ME_CUDA(cudaEventCreate(&e));
+        EventPool.push_back(e);
+    }
+    return EventPool[EventsUsed++];
+}
+
+void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_frames, uint32_t n_events, uint64_t total_frames, uint32_t block_frames, float *out, bool out_is_device, cudaStream_t stream, bool use_own_stream) {
+    RequireInstalled();
+    if (total_frames == 0) return;
+    if (!out) Fail(ME_BAD_ARG, "null output buffer");
+    if (block_frames == 0) Fail(ME_BAD_ARG, "block_frames must be positive");
+    if (total_frames >= (uint64_t(1) << 31)) Fail(ME_BAD_ARG, "total_frames must be below 2^31 per call");
+    if (n_events && (!events || !event_frames)) Fail(ME_BAD_ARG, "null event arrays");
+    for (uint32_t i = 0; i < n_events; ++i) {
+        if (event_frames[i] % block_frames != 0 || event_frames[i] >= total_frames) Fail(ME_BAD_ARG, "event %u: frame %llu is not a block boundary inside the timeline", i, (unsigned long long)event_frames[i]);
+        if (i && event_frames[i] < event_frames[i - 1]) Fail(ME_BAD_ARG, "event frames must be ascending");
+    }
+    ME_CUDA(cudaSetDevice(Device));
+    if (use_own_stream) stream = OwnStream;
+    if (TuningDirty) {
+        UploadTuning(stream);
+        for (const auto o : RetunedObjects) ResetObjectOnDevice(o, false, stream);
+        RetunedObjects.clear();
+    }
+    SpeculationFailed = false;
+
+    Stats = {};
+    Counter = {};
+    EventsUsed = 0;
+    StatsResolved = false;
+    float *out_dev = out;
+    if (!out_is_device) {
+        DOut.Reserve(total_frames);
+        out_dev = DOut.Ptr;
+    }
+    ME_CUDA(cudaEventRecord(EvBegin, stream));
+
+    // The callback's own prologue (RenderModal :496-499): adopt the flush flag, then drain the ring.
+    std::vector<MeModalEvent> ring;
+    if (FlushEvents) {
+        FlushEvents = false;
+        EventRead.store(EventWrite.load(std::memory_order_relaxed), std::memory_order_relaxed);
+    }
+    {
+        auto read = EventRead.load(std::memory_order_relaxed);
+        const auto write = EventWrite.load(std::memory_order_acquire);
+        for (; read != write; ++read) ring.push_back(Events[read % EventCapacity]);
+        EventRead.store(read, std::memory_order_release);
+    }
+
+    // A Silence event rewrites resonator state, so the timeline is rendered in spans cut at silences.
+    const uint32_t total = uint32_t(total_frames);
+    const uint32_t n_obj = ObjectCount();
+    uint32_t next_event = 0;
+    uint32_t span_begin = 0;
+    std::vector<ScheduledImpact> scheduled;
+    while (span_begin < total) {
+        uint32_t span_end = total;
+        for (uint32_t i = next_event; i < n_events; ++i) {
+            if (events[i].kind == 1 && event_frames[i] > span_begin) {
+                span_end = uint32_t(event_frames[i]);
+                break;
+            }
+        }
+        const uint32_t span_frames = span_end - span_begin;
+        scheduled.clear();
+        // Retirement frames of the in-flight impacts, soonest first, for the MaxImpacts cap (ActivateImpact :29).
+        std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<>> retire;
+        const auto admit = [&](const HostImpact &im, uint32_t start) {
+            ScheduledImpact s{.AtStart = im, .AtEnd = im, .Start = start, .End = 0, .Survives = false};
+            Schedule(s, block_frames, span_frames);
+            scheduled.push_back(s);
+            retire.push(s.Survives ? UINT32_MAX : s.End);
+        };
+        for (const auto &im : Impacts) admit(im, 0);
+        Impacts.clear();
+        const auto apply = [&](const MeModalEvent &e, uint32_t start) {
+            if (e.object >= n_obj) return; // DrainEvents :71
+            if (e.kind == 0) {
+                if (!(e.pulse_step > 0)) return;
+                while (!retire.empty() && retire.top() <= start) retire.pop();
+                if (retire.size() >= MaxImpacts) return;
+                admit(MakeImpact(e), start);
+            } else if (e.kind == 1) {
+                // Only ever at the first frame of a span: nothing of this span has been rendered yet.
+                const size_t before = scheduled.size();
+                std::erase_if(scheduled, [&](const ScheduledImpact &s) { return s.AtStart.Object == e.object; });
+                if (scheduled.size() != before) {
+                    retire = {};
+                    for (const auto &s : scheduled) retire.push(s.Survives ? UINT32_MAX : s.End);
+                }
+                ResetObjectOnDevice(e.object, true, stream);
+            }
+        };
+        if (span_begin == 0)
+            for (const auto &e : ring) apply(e, 0);
+        for (; next_event < n_events && event_frames[next_event] < span_end; ++next_event) apply(events[next_event], uint32_t(event_frames[next_event]) - span_begin);
+
+        RenderSpan(span_frames, block_frames, scheduled, out_dev + span_begin, stream);
+        for (const auto &s : scheduled)
+            if (s.Survives) Impacts.push_back(s.AtEnd);
+        span_begin = span_end;
+    }
+    ME_CUDA(cudaEventRecord(EvEnd, stream));
+    Stats.kernel_launches = Counter.Launches;
+
+    if (!out_is_device) {
+        POut.Reserve(total_frames);
+        ME_CUDA(cudaMemcpyAsync(POut.Ptr, out_dev, total_frames * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        ME_CUDA(cudaStreamSynchronize(stream));
+        for (uint64_t i = 0; i < total_frames; ++i) out[i] += POut.Ptr[i];
+        Stats.d2h_bytes += total_frames * sizeof(float);
+    }
+}
+
+const MeRenderStats &Bank::LastStats() {
+    if (!StatsResolved && EvEnd) {
+        cudaSetDevice(Device);
+        if (cudaEventSynchronize(EvEnd) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, EvBegin, EvEnd) == cudaSuccess) Stats.total_device_ms = ms;
+            float kernel = 0.f;
+            for (uint32_t i = 0; i + 1 < EventsUsed; i += 2) {
+                if (cudaEventElapsedTime(&ms, EventPool[i], EventPool[i + 1]) == cudaSuccess) kernel += ms;
+            }
+            Stats.resonator_kernel_ms = kernel;
+        }
+        StatsResolved = true;
+    }
+    return Stats;
+}
+
+void Bank::GetModeColumn(MeModeColumn which, float *out) {
+    if (!out) Fail(ME_BAD_ARG, "null output");
+    const std::vector<float> *host = nullptr;
+    switch (which) {
+        case ME_COL_COEFF_RE: host = &CoeffRe; break;
+        case ME_COL_COEFF_IM: host = &CoeffIm; break;
+        case ME_COL_RADIATION_GAIN: host = &RadiationGain; break;
+        case ME_COL_RADIATION_AREA: host = &RadiationArea; break;
+        case ME_COL_OUT_PHASE_IM: host = &OutPhaseIm; break;
+        case ME_COL_OUT_PHASE_RE: host = &OutPhaseRe; break;
+        case ME_COL_DEFLECTION_GAIN: host = &DeflectionGain; break;
+        case ME_COL_QUAD_COMPLIANCE: host = &QuadCompliance; break;
+        case ME_COL_QUAD_DRIVE_SCALE: host = &QuadDriveScale; break;
+        case ME_COL_STATE_RE:
+        case ME_COL_STATE_IM: break;
+        default: Fail(ME_BAD_ARG, "unknown mode column %d", int(which));
+    }
+    if (host) {
+        std::copy(host->begin(), host->end(), out);
+        return;
+    }
+    if (!Installed) {
+        std::fill_n(out, ModeTotal(), 0.f);
+        return;
+    }
+    ME_CUDA(cudaSetDevice(Device));
+    ME_CUDA(cudaStreamSynchronize(OwnStream));
+    std::vector<float> padded(size_t(NChunks) * kLanes);
+    const float *src = which == ME_COL_STATE_RE ? DStateRe[Side].Ptr : DStateIm[Side].Ptr;
+    ME_CUDA(cudaMemcpy(padded.data(), src, padded.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (uint32_t o = 0; o < ObjectCount(); ++o) std::copy_n(padded.begin() + size_t(ObjFirstChunk[o]) * kLanes, ModeCount[o], out + ModeOffset[o]);
+}
+
+void Bank::GetObjectStatus(uint32_t slot, uint32_t *live_mode_count, uint32_t *ringing) {
+    CheckSlot(slot);
+    RequireInstalled();
+    ME_CUDA(cudaSetDevice(Device));
+    ME_CUDA(cudaStreamSynchronize(OwnStream));
+    const uint32_t chunks = ObjStride[slot] / kLanes;
+    std::vector<uint8_t> live(chunks);
+    uint8_t ring = 0;
+    if (chunks) ME_CUDA(cudaMemcpy(live.data(), DChunkLive[Side].Ptr + ObjFirstChunk[slot], chunks, cudaMemcpyDeviceToHost));
+    ME_CUDA(cudaMemcpy(&ring, DObjRinging[Side].Ptr + slot, 1, cudaMemcpyDeviceToHost));
+    // The live set is a prefix of the tuned set, a whole number of chunks or the tuned count itself (:139,:146).
+    uint32_t last = 0;
+    for (uint32_t c = 0; c < chunks; ++c)
+        if (live[c]) last = c + 1;
+    if (live_mode_count) *live_mode_count = std::min(last * kLanes, TunedModeCount[slot]);
+    if (ringing) *ringing = ring;
+}
+
+void Bank::GetObjectLayout(uint32_t slot, uint32_t *mode_offset, uint32_t *mode_count, uint32_t *tuned, float *radius) const {
+    CheckSlot(slot);
+    if (mode_offset) *mode_offset = ModeOffset[slot];
+    if (mode_count) *mode_count = ModeCount[slot];
+    if (tuned) *tuned = TunedModeCount[slot];
+    if (radius) *radius = RadiantRadius[slot];
+}
+
+} // namespace me

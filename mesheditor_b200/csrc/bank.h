@@ -1,0 +1,130 @@
+// Host side of the resonator bank: the reference's ModalBank / ModalAudio bookkeeping (object slots, tuning,
+// the SPSC event ring, impact lifetimes) in C++, with the per-mode columns resident in HBM and every sample
+// computed by the kernels in resonator.cu. Reference: src/audio/ModalAudio.{h,cpp}.
+#pragma once
+
+#include "common.h"
+#include "resonator.cuh"
+
+#include <array>
+#include <atomic>
+#include <cstdint>
+#include <vector>
+
+namespace me {
+
+// ModalBank::ActiveImpact (ModalAudio.h:147-160).
+struct HostImpact {
+    uint32_t Object, ExPos, SamplesLeft;
+    float Jx, Jy, Jz;
+    float PhaseRe, PhaseIm, RotRe, RotIm;
+    float Gamma, AccelAmp;
+    float ClickB0, ClickA1, ClickA2, ClickZ1, ClickZ2;
+};
+
+// An impact as scheduled inside one span of the timeline (a stretch without Silence events inside).
+struct ScheduledImpact {
+    HostImpact AtStart; // state at Start
+    HostImpact AtEnd;   // state the next span adopts when it survives
+    uint32_t Start;     // relative to the span
+    uint32_t End;       // frame at which it is retired, or the span's end when it survives
+    bool Survives;
+};
+
+class Bank {
+public:
+    Bank(float sample_rate, int device);
+    ~Bank();
+    Bank(const Bank &) = delete;
+    Bank &operator=(const Bank &) = delete;
+
+    uint32_t AddObject(uint32_t n_modes, uint32_t n_points, const float *shapes_xyz, const float *positions_xyz, const uint32_t *indices, uint32_t n_indices);
+    void TuneObject(uint32_t slot, const float *freqs, const float *t60s, uint32_t n, float radius_scale);
+    void SetObjectShapes(uint32_t slot, uint32_t n_modes, uint32_t n_points, const float *shapes_xyz);
+    void SetGain(uint32_t slot, float out_gain, float listener_gain);
+    void SetClickGain(float g) { ClickGain = g; }
+    void SetMaxImpacts(uint32_t n) { MaxImpacts = n; }
+    void SetTimeSegments(uint32_t n) { RequestedSegments = n; }
+
+    void Install();
+    MeStatus Enqueue(const MeModalEvent &);
+    // `out` is a host buffer that is added into when `out_is_device` is false, else a device buffer that is overwritten.
+    void RenderTimeline(const MeModalEvent *events, const uint64_t *event_frames, uint32_t n_events, uint64_t total_frames, uint32_t block_frames, float *out, bool out_is_device, cudaStream_t stream, bool use_own_stream);
+
+    uint32_t ObjectCount() const { return uint32_t(ModeOffset.size()); }
+    uint32_t ModeTotal() const { return uint32_t(CoeffRe.size()); }
+    uint32_t ActiveImpacts() const { return uint32_t(Impacts.size()); }
+    uint64_t EventsDroppedCount() const { return EventsDropped; }
+    void GetModeColumn(MeModeColumn which, float *out);
+    void GetObjectLayout(uint32_t slot, uint32_t *mode_offset, uint32_t *mode_count, uint32_t *tuned, float *radius) const;
+    void GetObjectStatus(uint32_t slot, uint32_t *live_mode_count, uint32_t *ringing);
+    const MeRenderStats &LastStats();
+
+private:
+    void CheckSlot(uint32_t slot) const;
+    void RequireInstalled() const;
+    void UploadTuning(cudaStream_t);
+    void ResetObjectOnDevice(uint32_t object, bool clear_state, cudaStream_t);
+    void RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<ScheduledImpact> &, float *out_dev, cudaStream_t);
+    cudaEvent_t NextEvent();
+    BankView View() const;
+
+    float SampleRate;
+    int Device;
+    cudaStream_t OwnStream{nullptr};
+    cudaEvent_t EvBegin{nullptr}, EvEnd{nullptr};
+    std::vector<cudaEvent_t> EventPool; // begin/end pairs around every resonator kernel launch of the last call
+    uint32_t EventsUsed{0};
+    bool StatsResolved{true};
+
+    // Host columns, objects concatenated exactly like ModalBank (unpadded).
+    std::vector<float> CoeffRe, CoeffIm, RadiationGain, RadiationArea, DeflectionGain, OutPhaseIm, OutPhaseRe, QuadCompliance, QuadDriveScale;
+    std::vector<float> ShapeX, ShapeY, ShapeZ;
+    std::vector<uint32_t> ModeOffset, ModeCount, ShapeOffset, ShapePoints, TunedModeCount;
+    std::vector<float> OutGain, ListenerGain, RadiantRadius, DeflectionScale;
+
+    // ModalAudio side.
+    float ClickGain{1.f};
+    uint32_t MaxImpacts{1024};
+    static constexpr uint32_t EventCapacity{256};
+    std::array<MeModalEvent, EventCapacity> Events{};
+    std::atomic<uint32_t> EventWrite{0}, EventRead{0};
+    bool FlushEvents{false};
+    uint64_t EventsDropped{0};
+    std::vector<HostImpact> Impacts; // in flight between render calls
+
+    // Device residency.
+    bool Installed{false};
+    bool TuningDirty{false};
+    uint32_t NChunks{0};
+    std::vector<uint32_t> ObjFirstChunk, ObjStride, ObjPaddedShapeOffset; // per object, padded layout
+    std::vector<uint32_t> RetunedObjects; // LiveModeCount resets owed to the device (TuneModalObject :392)
+    int Side{0};                          // which of the ping-pong state buffers holds the current state
+    DeviceBuffer<float> DCoeffRe, DCoeffIm, DStateRe[2], DStateIm[2], DPhaseIm, DPhaseRe, DRadiationGain, DShapeX, DShapeY, DShapeZ, DObjMixGain, DObjEnergyScale;
+    DeviceBuffer<uint32_t> DChunkObject, DObjShapeOffset, DObjStride, DObjFirstChunk, DObjTunedChunks;
+    DeviceBuffer<uint8_t> DObjCull, DChunkLive[2], DObjRinging[2];
+    DeviceBuffer<uint32_t> DInjectPtr, DInjectFrame, DInjectDelta, DExcitePtr, DExciteBegin, DExciteEnd, DSpeculation;
+    DeviceBuffer<DevImpact> DImpacts;
+    DeviceBuffer<DevImpactTail> DTails;
+    DeviceBuffer<PulseWarp> DPulseWarps;
+    DeviceBuffer<float> DForce, DPartial, DOut, DSegRe, DSegIm, DDeltaRe, DDeltaIm, DPulseRows;
+    DeviceBuffer<double> DLogRho, DTheta;
+    PinnedBuffer<float> POut;
+
+    // Per-call scratch.
+    std::vector<DevImpact> CallImpacts;
+    std::vector<DevImpactTail> CallTails;
+    std::vector<PulseWarp> CallPulseWarps;
+    std::vector<uint32_t> CallInjectPtr, CallInjectFrame, CallInjectDelta, CallExcitePtr, CallExciteBegin, CallExciteEnd;
+    std::vector<float> MixGain, EnergyScale;
+
+    uint32_t RequestedSegments{0};
+    int Steps{4};
+    bool SpeculationFailed{false};
+    MeRenderStats Stats{};
+    LaunchCounter Counter;
+
+    friend struct BankAccess;
+};
+
+} // namespace me

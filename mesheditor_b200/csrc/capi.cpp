@@ -1,0 +1,122 @@
+// The C ABI (include/me_modal.h): thin extern "C" shims over me::Bank (and, later, the solver).
+#include "bank.h"
+#include "common.h"
+
+#include <new>
+
+namespace me {
+namespace {
+thread_local std::string g_last_error;
+}
+void SetLastError(const char *fmt, ...) {
+    char buffer[512];
+    va_list args;
+    va_start(args, fmt);
+    vsnprintf(buffer, sizeof buffer, fmt, args);
+    va_end(args);
+    g_last_error = buffer;
+}
+const char *LastError() { return g_last_error.c_str(); }
+} // namespace me
+
+struct MeBank {
+    me::Bank Impl;
+    MeBank(float sample_rate, int device) : Impl(sample_rate, device) {}
+};
+
+using me::Fail;
+using me::Guard;
+
+extern "C" {
+
+const char *me_last_error(void) { return me::LastError(); }
+const char *me_build_info(void) { return "libme_modal 0.1 (C ABI 1), CUDA sm_100a, no CPU fallback"; }
+int me_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+
+MeStatus me_bank_create(float sample_rate, int device, MeBank **out) {
+    return Guard([&] {
+        if (!out) Fail(ME_BAD_ARG, "null out pointer");
+        *out = nullptr;
+        if (!(sample_rate > 0)) Fail(ME_BAD_ARG, "sample_rate must be positive");
+        *out = new MeBank(sample_rate, device);
+    });
+}
+void me_bank_free(MeBank *b) { delete b; }
+
+#define ME_BANK_CALL(b, body)                          \
+    Guard([&] {                                        \
+        if (!(b)) Fail(ME_BAD_ARG, "null bank handle"); \
+        body;                                          \
+    })
+
+MeStatus me_bank_add_object(MeBank *b, uint32_t n_modes, uint32_t n_points, const float *shapes_xyz, const float *positions_xyz, const uint32_t *indices, uint32_t n_indices, uint32_t *slot_out) {
+    return ME_BANK_CALL(b, {
+        const auto slot = b->Impl.AddObject(n_modes, n_points, shapes_xyz, positions_xyz, indices, n_indices);
+        if (slot_out) *slot_out = slot;
+    });
+}
+MeStatus me_bank_tune_object(MeBank *b, uint32_t slot, const float *freqs, const float *t60s, uint32_t n, float radius_scale) {
+    return ME_BANK_CALL(b, b->Impl.TuneObject(slot, freqs, t60s, n, radius_scale));
+}
+MeStatus me_bank_set_object_shapes(MeBank *b, uint32_t slot, uint32_t n_modes, uint32_t n_points, const float *shapes_xyz) {
+    return ME_BANK_CALL(b, {
+        if (!shapes_xyz) Fail(ME_BAD_ARG, "null shapes");
+        b->Impl.SetObjectShapes(slot, n_modes, n_points, shapes_xyz);
+    });
+}
+MeStatus me_bank_set_gain(MeBank *b, uint32_t slot, float out_gain, float listener_gain) { return ME_BANK_CALL(b, b->Impl.SetGain(slot, out_gain, listener_gain)); }
+MeStatus me_bank_set_click_gain(MeBank *b, float g) { return ME_BANK_CALL(b, b->Impl.SetClickGain(g)); }
+MeStatus me_bank_set_max_impacts(MeBank *b, uint32_t n) { return ME_BANK_CALL(b, b->Impl.SetMaxImpacts(n)); }
+MeStatus me_bank_set_time_segments(MeBank *b, uint32_t n) { return ME_BANK_CALL(b, b->Impl.SetTimeSegments(n)); }
+MeStatus me_bank_install(MeBank *b) { return ME_BANK_CALL(b, b->Impl.Install()); }
+
+MeStatus me_bank_enqueue(MeBank *b, const MeModalEvent *e) {
+    MeStatus queued = ME_OK;
+    const MeStatus s = ME_BANK_CALL(b, {
+        if (!e) Fail(ME_BAD_ARG, "null event");
+        queued = b->Impl.Enqueue(*e);
+    });
+    return s != ME_OK ? s : queued;
+}
+
+MeStatus me_bank_render(MeBank *b, float *out, uint32_t frames) {
+    return ME_BANK_CALL(b, b->Impl.RenderTimeline(nullptr, nullptr, 0, frames, frames ? frames : 1, out, false, nullptr, true));
+}
+MeStatus me_bank_render_offline(MeBank *b, const MeModalEvent *events, const uint64_t *event_frames, uint32_t n_events, uint64_t total_frames, uint32_t block_frames, float *out) {
+    return ME_BANK_CALL(b, b->Impl.RenderTimeline(events, event_frames, n_events, total_frames, block_frames, out, false, nullptr, true));
+}
+MeStatus me_bank_render_offline_device(MeBank *b, const MeModalEvent *events, const uint64_t *event_frames, uint32_t n_events, uint64_t total_frames, uint32_t block_frames, float *out_device, void *cuda_stream) {
+    return ME_BANK_CALL(b, b->Impl.RenderTimeline(events, event_frames, n_events, total_frames, block_frames, out_device, true, static_cast<cudaStream_t>(cuda_stream), cuda_stream == nullptr));
+}
+
+uint32_t me_bank_object_count(const MeBank *b) { return b ? b->Impl.ObjectCount() : 0; }
+uint32_t me_bank_mode_total(const MeBank *b) { return b ? b->Impl.ModeTotal() : 0; }
+uint32_t me_bank_active_impacts(const MeBank *b) { return b ? b->Impl.ActiveImpacts() : 0; }
+uint64_t me_bank_events_dropped(const MeBank *b) { return b ? b->Impl.EventsDroppedCount() : 0; }
+MeStatus me_bank_get_mode_column(MeBank *b, MeModeColumn which, float *out) { return ME_BANK_CALL(b, b->Impl.GetModeColumn(which, out)); }
+MeStatus me_bank_get_object_layout(const MeBank *b, uint32_t slot, uint32_t *mode_offset, uint32_t *mode_count, uint32_t *tuned_mode_count, float *radiant_radius) {
+    return ME_BANK_CALL(b, b->Impl.GetObjectLayout(slot, mode_offset, mode_count, tuned_mode_count, radiant_radius));
+}
+MeStatus me_bank_get_object_status(MeBank *b, uint32_t slot, uint32_t *live_mode_count, uint32_t *ringing) {
+    return ME_BANK_CALL(b, b->Impl.GetObjectStatus(slot, live_mode_count, ringing));
+}
+MeStatus me_bank_last_render_stats(const MeBank *b, MeRenderStats *out) {
+    return ME_BANK_CALL(b, {
+        if (!out) Fail(ME_BAD_ARG, "null out");
+        *out = const_cast<MeBank *>(b)->Impl.LastStats();
+    });
+}
+
+MeStatus me_measure_fp32_fma_rate(int device, int packed, int iters, double *fma_per_second) {
+    return Guard([&] {
+        if (!fma_per_second || iters <= 0) Fail(ME_BAD_ARG, "bad arguments");
+        ME_CUDA(cudaSetDevice(device));
+        *fma_per_second = me::MeasureFmaRate(packed, iters);
+    });
+}
+
+} // extern "C"

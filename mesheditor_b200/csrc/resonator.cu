@@ -1,0 +1,662 @@
+// sm_100a kernels of the modal resonator bank.
+//
+// What is computed (reference: src/audio/ModalAudio.cpp:86-147, 486-590): every mode is a damped complex
+// one-pole  z[n] = c z[n-1] + e[n],  e[n] = sum over the object's live impacts of force[n] * gain, and the
+// object's sample is  sum_modes (pIm*Im z + pRe*Re z) * OutGain*ListenerGain.
+//
+// How it is laid out for B200 (the path is bound by FP32 issue, not by HBM: SURVEY.md F9):
+//   * ResonatorKernel: one thread owns one 8-mode chunk (the reference's Lanes) in registers for a whole time
+//     segment, so a warp covers 256 modes and reads each per-mode column as two coalesced float4 per thread.
+//   * The output rotation is folded into the state: w = z*(pIm + i pRe)*gain obeys the same recurrence and the
+//     sample is just sum Im w.
+//   * K samples are advanced at a time: the K-1 intermediate samples are read off the current state with the
+//     precomputed powers c^j (Im(c^j w), two FMAs chained into a running sum, no separate add), and the state
+//     jumps by c^K. That is (2K+3)/K FP32 lane-operations per mode-sample instead of the reference's 7
+//     (2.75 at K = 4), all issued as Blackwell packed FFMA2/FMUL2/FADD2 (fma.rn.f32x2) on mode pairs.
+//   * Modes are summed across the warp 32 samples at a time through a padded shared-memory transpose; each warp
+//     writes one coalesced 128-byte segment of its own partial row, and MixKernel sums the rows in fixed order,
+//     so the mix is deterministic (no float atomics) and no CTA barrier sits in the sample loop.
+//   * Excitation is rare (a contact pulse lasts ~1/PulseStep samples) and the system is linear, so PulseKernel
+//     renders each pulse's zero-state response on its own (samples + end-of-pulse state increment) and the main
+//     kernel only adds that increment when the pulse ends. The main loop carries no excitation term at all.
+//   * The same increments give the state at any later frame in closed form (FP64 powers of c), which is the
+//     block-parallel scan along time: SegmentScanKernel seeds segments 1.. of a window so that different threads
+//     render different time segments of the same chunk.
+//   * The reference's audibility culling (LiveModeCount prefix, SilenceObject, :139-146) is reproduced at the
+//     RenderModal block boundaries with one CTA-wide exchange per block; objects never straddle a CTA.
+#include "resonator.cuh"
+
+#include "common.h"
+
+#include <algorithm>
+#include <cstdio>
+
+namespace me {
+namespace {
+
+constexpr uint32_t kRowPad = 36; // floats per transposed row: 32 + 4 keeps float4 alignment and spreads banks
+constexpr float kSilentEnergy = 1e-12f; // ModalAudio.cpp:20
+
+__device__ __forceinline__ uint64_t AsBits(float2 v) { return reinterpret_cast<uint64_t &>(v); }
+__device__ __forceinline__ float2 Fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<uint64_t &>(d)) : "l"(AsBits(a)), "l"(AsBits(b)), "l"(AsBits(c)));
+    return d;
+}
+__device__ __forceinline__ float2 Mul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t &>(d)) : "l"(AsBits(a)), "l"(AsBits(b)));
+    return d;
+}
+__device__ __forceinline__ float2 Add2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<uint64_t &>(d)) : "l"(AsBits(a)), "l"(AsBits(b)));
+    return d;
+}
+
+// Eight complex values held as four mode pairs.
+struct Chunk {
+    float2 Re[4], Im[4];
+};
+
+__device__ __forceinline__ void Load8(const float *p, float2 (&v)[4]) {
+    const float4 a = __ldg(reinterpret_cast<const float4 *>(p)), b = __ldg(reinterpret_cast<const float4 *>(p) + 1);
+    v[0] = {a.x, a.y}, v[1] = {a.z, a.w}, v[2] = {b.x, b.y}, v[3] = {b.z, b.w};
+}
+__device__ __forceinline__ void Store8(float *p, const float2 (&v)[4]) {
+    reinterpret_cast<float4 *>(p)[0] = {v[0].x, v[0].y, v[1].x, v[1].y};
+    reinterpret_cast<float4 *>(p)[1] = {v[2].x, v[2].y, v[3].x, v[3].y};
+}
+
+// c^1 .. c^K of the chunk's eight coefficients.
+template<int K>
+struct Powers {
+    float2 Re[K][4], Im[K][4];
+    float2 NegImK[4];
+};
+
+template<int K>
+__device__ __forceinline__ void MakePowers(const float2 (&cre)[4], const float2 (&cim)[4], Powers<K> &p) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        // Powers are formed in FP64 from the float coefficient and rounded once.
+        const double ax = cre[i].x, bx = cim[i].x, ay = cre[i].y, by = cim[i].y;
+        double rx = ax, ix = bx, ry = ay, iy = by;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            p.Re[j][i] = {float(rx), float(ry)};
+            p.Im[j][i] = {float(ix), float(iy)};
+            const double nrx = rx * ax - ix * bx, nry = ry * ay - iy * by;
+            ix = rx * bx + ix * ax, iy = ry * by + iy * ay;
+            rx = nrx, ry = nry;
+        }
+        p.NegImK[i] = {-p.Im[K - 1][i].x, -p.Im[K - 1][i].y};
+    }
+}
+
+// K samples: y[j] = sum Im(c^(j+1) w) for j < K-1 straight off the state, then w <- c^K w and y[K-1] = sum Im w.
+template<int K>
+__device__ __forceinline__ void StepK(Chunk &w, const Powers<K> &p, float scale, float *column) {
+#pragma unroll
+    for (int j = 0; j + 1 < K; ++j) {
+        float2 acc = Mul2(p.Re[j][0], w.Im[0]);
+        acc = Fma2(p.Im[j][0], w.Re[0], acc);
+#pragma unroll
+        for (int i = 1; i < 4; ++i) {
+            acc = Fma2(p.Re[j][i], w.Im[i], acc);
+            acc = Fma2(p.Im[j][i], w.Re[i], acc);
+        }
+        column[j * kRowPad] = (acc.x + acc.y) * scale;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 re = Fma2(w.Im[i], p.NegImK[i], Mul2(w.Re[i], p.Re[K - 1][i]));
+        w.Im[i] = Fma2(w.Re[i], p.Im[K - 1][i], Mul2(w.Im[i], p.Re[K - 1][i]));
+        w.Re[i] = re;
+    }
+    const float2 s = Add2(Add2(w.Im[0], w.Im[1]), Add2(w.Im[2], w.Im[3]));
+    column[(K - 1) * kRowPad] = (s.x + s.y) * scale;
+}
+
+// One sample with c^1 (remainders of a tile that is not a multiple of K).
+template<int K>
+__device__ __forceinline__ void Step1(Chunk &w, const Powers<K> &p, float scale, float *column) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float rx = fmaf(-w.Im[i].x, p.Im[0][i].x, w.Re[i].x * p.Re[0][i].x);
+        const float ry = fmaf(-w.Im[i].y, p.Im[0][i].y, w.Re[i].y * p.Re[0][i].y);
+        w.Im[i].x = fmaf(w.Re[i].x, p.Im[0][i].x, w.Im[i].x * p.Re[0][i].x);
+        w.Im[i].y = fmaf(w.Re[i].y, p.Im[0][i].y, w.Im[i].y * p.Re[0][i].y);
+        w.Re[i].x = rx, w.Re[i].y = ry;
+        sum += w.Im[i].x + w.Im[i].y;
+    }
+    column[0] = sum * scale;
+}
+
+// Lane s sums sample s over the warp's 32 columns.
+__device__ __forceinline__ float SumRow(const float *rows, uint32_t lane) {
+    const float4 *r = reinterpret_cast<const float4 *>(rows + lane * kRowPad);
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const float4 x = r[j], y = r[j + 1];
+        a += (x.x + x.y) + (x.z + x.w);
+        b += (y.x + y.y) + (y.z + y.w);
+    }
+    return a + b;
+}
+
+template<int K>
+__global__ void __launch_bounds__(kBlockThreads) ResonatorKernel(const BankView b, const RenderPlan plan) {
+    __shared__ __align__(16) float transposed[kWarpsPerBlock][kTile][kRowPad];
+    __shared__ float cull_energy[kBlockThreads];
+    __shared__ uint8_t cull_audible[kBlockThreads];
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t chunk = blockIdx.x * kBlockThreads + threadIdx.x;
+    const uint32_t seg = blockIdx.y;
+    const uint32_t mode0 = chunk * kLanes;
+    const uint32_t object = chunk < b.NChunks ? b.ChunkObject[chunk] : kNoObject;
+    const bool valid = object != kNoObject;
+
+    const uint32_t seg_begin = seg * plan.SegmentFrames;                      // relative to the window
+    const uint32_t seg_end = min(plan.Frames, seg_begin + plan.SegmentFrames);
+    const bool last_segment = seg + 1 == plan.NSegments;
+
+    Powers<K> p;
+    Chunk w;
+    float gain = 1.f, out_scale = 0.f, energy_scale = 0.f;
+    uint32_t my_chunk = 0, obj_chunks = 0, obj_first_local = 0;
+    bool in_tuned = false, cull = false, live = true, ringing = true;
+    uint32_t inj = 0, inj_hi = 0, exc = 0, exc_hi = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w.Re[i] = w.Im[i] = float2{0.f, 0.f};
+    if (valid) {
+        float2 cre[4], cim[4];
+        Load8(b.CoeffRe + mode0, cre), Load8(b.CoeffIm + mode0, cim);
+        MakePowers<K>(cre, cim, p);
+        const uint32_t first = b.ObjFirstChunk[object];
+        my_chunk = chunk - first;
+        obj_chunks = b.ObjStride[object] / kLanes;
+        obj_first_local = first - blockIdx.x * kBlockThreads; // only meaningful when the object fits this CTA
+        in_tuned = my_chunk < b.ObjTunedChunks[object];
+        cull = b.ObjCull[object] != 0;
+        const float mix = b.ObjMixGain[object];
+        const bool muted = mix == 0.f;
+        gain = muted ? 1.f : mix;
+        out_scale = muted ? 0.f : 1.f;
+        energy_scale = b.ObjEnergyScale[object];
+        if (seg == 0) {
+            float2 zr[4], zi[4], qr[4], qi[4];
+            Load8(b.PhaseIm + mode0, qr), Load8(b.PhaseRe + mode0, qi);
+            Load8(b.StateRe + mode0, zr), Load8(b.StateIm + mode0, zi);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { // w = z * q * gain
+                w.Re[i] = {(zr[i].x * qr[i].x - zi[i].x * qi[i].x) * gain, (zr[i].y * qr[i].y - zi[i].y * qi[i].y) * gain};
+                w.Im[i] = {(zr[i].x * qi[i].x + zi[i].x * qr[i].x) * gain, (zr[i].y * qi[i].y + zi[i].y * qr[i].y) * gain};
+            }
+            live = b.ChunkLive[chunk] != 0;
+            ringing = b.ObjRinging[object] != 0;
+        } else {
+            const size_t off = size_t(seg - 1) * b.NChunks * kLanes + mode0;
+            Load8(plan.SegStateRe + off, w.Re), Load8(plan.SegStateIm + off, w.Im);
+        }
+        const uint32_t begin_abs = plan.FrameBegin + seg_begin;
+        inj = plan.ObjInjectPtr[object], inj_hi = plan.ObjInjectPtr[object + 1];
+        while (inj < inj_hi && plan.InjectFrame[inj] < begin_abs) ++inj;
+        exc = plan.ObjExcitePtr[object], exc_hi = plan.ObjExcitePtr[object + 1];
+    } else {
+#pragma unroll
+        for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p.Re[j][i] = p.Im[j][i] = float2{0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p.NegImK[i] = float2{0.f, 0.f};
+    }
+    uint32_t inj_frame = inj < inj_hi ? plan.InjectFrame[inj] : 0xFFFFFFFFu;
+
+    const auto inject = [&] {
+        const uint32_t off = plan.InjectDelta[inj] + my_chunk * kLanes;
+        float2 dr[4], di[4];
+        Load8(plan.DeltaRe + off, dr), Load8(plan.DeltaIm + off, di);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            w.Re[i].x += dr[i].x, w.Re[i].y += dr[i].y;
+            w.Im[i].x += di[i].x, w.Im[i].y += di[i].y;
+        }
+        ++inj;
+        inj_frame = inj < inj_hi ? plan.InjectFrame[inj] : 0xFFFFFFFFu;
+    };
+
+    float *rows = &transposed[warp][0][0];
+    float *column = rows + lane;
+    float *partial = plan.Partial + size_t(blockIdx.x * kWarpsPerBlock + warp) * plan.Frames;
+
+    uint32_t pos = seg_begin;
+    while (pos < seg_end) {
+        // One RenderModal block (or what is left of it inside this segment).
+        const uint32_t pos_abs = plan.FrameBegin + pos;
+        const uint32_t block_end_abs = min(min((pos_abs / plan.BlockFrames + 1) * plan.BlockFrames, plan.SpanFrames), plan.FrameBegin + seg_end);
+        const uint32_t block_end = block_end_abs - plan.FrameBegin;
+        // Does the object hold a live impact in this block (:90 `impacts.empty()`)?
+        while (exc < exc_hi && plan.ExciteEnd[exc] <= pos_abs) ++exc;
+        const bool excited = exc < exc_hi && plan.ExciteBegin[exc] <= pos_abs;
+        if (excited) ringing = true; // ActivateImpact :50
+        while (inj_frame < pos_abs) { // increments that landed while this chunk was not rendered are all zero
+            ++inj;
+            inj_frame = inj < inj_hi ? plan.InjectFrame[inj] : 0xFFFFFFFFu;
+        }
+        const bool rendered = valid && in_tuned && (!cull || excited || (live && ringing));
+        if (valid && in_tuned && !rendered) {
+            // A chunk that holds state but sits out the block breaks the linear evolution the scan along time assumed.
+            bool holds = false;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) holds |= w.Re[i].x != 0.f || w.Re[i].y != 0.f || w.Im[i].x != 0.f || w.Im[i].y != 0.f;
+            if (holds) {
+                if (plan.Debug && atomicOr(plan.Speculation, seg == 0 ? 1u : 2u) == 0) printf("[me] frozen chunk holds state: object %u chunk %u seg %u frame %u live %d ringing %d excited %d\n", object, my_chunk, seg, pos_abs, int(live), int(ringing), int(excited));
+                atomicOr(plan.Speculation, seg == 0 ? 1u : 2u);
+            }
+        }
+        const bool warp_renders = __ballot_sync(0xFFFFFFFFu, rendered) != 0;
+
+        for (uint32_t tile = pos; tile < block_end; tile += kTile) {
+            const uint32_t nv = min(kTile, block_end - tile);
+            if (!warp_renders) {
+                if (lane < nv) partial[tile + lane] = 0.f;
+                continue;
+            }
+            if (rendered) {
+                const uint32_t tile_abs = plan.FrameBegin + tile;
+                uint32_t s = 0;
+                while (true) {
+                    uint32_t lim = nv;
+                    if (inj_frame - tile_abs < nv) lim = inj_frame - tile_abs; // inj_frame >= tile_abs + s
+                    for (; s + K <= lim; s += K) StepK<K>(w, p, out_scale, column + s * kRowPad);
+                    for (; s < lim; ++s) Step1<K>(w, p, out_scale, column + s * kRowPad);
+                    if (s == nv) break;
+                    while (inj_frame == tile_abs + s) inject();
+                }
+            } else {
+                for (uint32_t s = 0; s < nv; ++s) column[s * kRowPad] = 0.f;
+            }
+            __syncwarp();
+            const float total = lane < nv ? SumRow(rows, lane) : 0.f;
+            if (lane < nv) partial[tile + lane] = total;
+            __syncwarp();
+        }
+
+        // End of the block: chunk energies decide the audible prefix, or silence the object (:132-146).
+        float energy = 0.f;
+        if (rendered) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) energy += (w.Re[i].x * w.Re[i].x + w.Im[i].x * w.Im[i].x) + (w.Re[i].y * w.Re[i].y + w.Im[i].y * w.Im[i].y);
+        }
+        cull_energy[threadIdx.x] = energy;
+        cull_audible[threadIdx.x] = rendered && energy * energy_scale >= kSilentEnergy;
+        __syncthreads();
+        if (valid && cull) {
+            float total = 0.f;
+            int last = -1;
+            for (uint32_t k = 0; k < obj_chunks; ++k) {
+                total += cull_energy[obj_first_local + k];
+                if (cull_audible[obj_first_local + k]) last = int(k);
+            }
+            // A decision that removes state from the linear evolution invalidates the scan along time for every later
+            // segment; the window's very last block only feeds the next window, which starts from the real flags.
+            const bool feeds_scan = !(last_segment && block_end == seg_end);
+            if (!excited && total * energy_scale < kSilentEnergy) { // SilenceObject :53-64
+                if (total > 0.f && feeds_scan) atomicOr(plan.Speculation, 4u);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w.Re[i] = w.Im[i] = float2{0.f, 0.f};
+                live = true;
+                ringing = false;
+            } else {
+                ringing = true;
+                live = excited || int(my_chunk) <= last;
+                if (!live && in_tuned && energy > 0.f && feeds_scan) {
+                    if (plan.Debug && atomicOr(plan.Speculation, 2u) == 0) printf("[me] chunk frozen with state: object %u chunk %u seg %u frame %u last %d total %g energy %g scale %g\n", object, my_chunk, seg, block_end_abs, last, total, energy, energy_scale);
+                    atomicOr(plan.Speculation, 2u);
+                }
+            }
+        }
+        __syncthreads();
+        pos = block_end;
+    }
+
+    if (valid && last_segment) {
+        // Increments of pulses that end exactly with the span belong to the state the next call adopts.
+        if (plan.FrameBegin + seg_end == plan.SpanFrames && in_tuned)
+            while (inj_frame == plan.SpanFrames) inject();
+        float2 zr[4], zi[4], qr[4], qi[4];
+        Load8(b.PhaseIm + mode0, qr), Load8(b.PhaseRe + mode0, qi);
+        const float inv_gain = 1.f / gain;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { // z = w * conj(q) / gain
+            zr[i] = {(w.Re[i].x * qr[i].x + w.Im[i].x * qi[i].x) * inv_gain, (w.Re[i].y * qr[i].y + w.Im[i].y * qi[i].y) * inv_gain};
+            zi[i] = {(w.Im[i].x * qr[i].x - w.Re[i].x * qi[i].x) * inv_gain, (w.Im[i].y * qr[i].y - w.Re[i].y * qi[i].y) * inv_gain};
+        }
+        Store8(b.StateOutRe + mode0, zr), Store8(b.StateOutIm + mode0, zi);
+        b.ChunkLiveOut[chunk] = live;
+        if (my_chunk == 0) b.ObjRingingOut[object] = ringing;
+    }
+}
+
+// The impulse of an impact projected onto the chunk's 8 mode shapes (ImpactGainRow, ModalAudio.h:182-188), in the
+// reference's operation order, then rotated by the output phase and scaled by the mix gain.
+__device__ __forceinline__ void ImpactGain(const BankView &b, const DevImpact &im, uint32_t mode0, uint32_t first_mode, const float2 (&qr)[4], const float2 (&qi)[4], float scale, Chunk &g) {
+    const uint32_t base = b.ObjShapeOffset[im.Object] + im.ExPos * b.ObjStride[im.Object] + first_mode;
+    float2 sx[4], sy[4], sz[4], rg[4];
+    Load8(b.ShapeX + base, sx), Load8(b.ShapeY + base, sy), Load8(b.ShapeZ + base, sz), Load8(b.RadiationGain + mode0, rg);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float gx = __fmul_rn(rg[i].x, __fadd_rn(__fadd_rn(__fmul_rn(sx[i].x, im.Jx), __fmul_rn(sy[i].x, im.Jy)), __fmul_rn(sz[i].x, im.Jz)));
+        const float gy = __fmul_rn(rg[i].y, __fadd_rn(__fadd_rn(__fmul_rn(sx[i].y, im.Jx), __fmul_rn(sy[i].y, im.Jy)), __fmul_rn(sz[i].y, im.Jz)));
+        g.Re[i] = {gx * qr[i].x * scale, gy * qr[i].y * scale};
+        g.Im[i] = {gx * qi[i].x * scale, gy * qi[i].y * scale};
+    }
+}
+
+// One warp per (impact, 32 chunks of its object): the zero-state response to the force pulse, v <- c v + f g.
+constexpr uint32_t kPulseWarps = 4;
+__global__ void __launch_bounds__(kPulseWarps * 32) PulseKernel(const BankView b, const PulsePlan plan) {
+    __shared__ __align__(16) float transposed[kPulseWarps][kTile][kRowPad];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t pw = blockIdx.x * kPulseWarps + warp;
+    if (pw >= plan.NPulseWarps) return;
+    const PulseWarp job = plan.Warps[pw];
+    const DevImpact im = plan.Impacts[job.Impact];
+    const uint32_t my_chunk = job.Chunk0 + lane;
+    const bool valid = my_chunk < b.ObjStride[im.Object] / kLanes;
+    const uint32_t mode0 = (b.ObjFirstChunk[im.Object] + my_chunk) * kLanes;
+
+    float2 cre[4], cim[4];
+    Chunk g, v;
+    float out_scale = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cre[i] = cim[i] = g.Re[i] = g.Im[i] = v.Re[i] = v.Im[i] = float2{0.f, 0.f};
+    if (valid) {
+        float2 qr[4], qi[4];
+        Load8(b.CoeffRe + mode0, cre), Load8(b.CoeffIm + mode0, cim);
+        Load8(b.PhaseIm + mode0, qr), Load8(b.PhaseRe + mode0, qi);
+        const float mix = b.ObjMixGain[im.Object];
+        out_scale = mix == 0.f ? 0.f : 1.f;
+        ImpactGain(b, im, mode0, my_chunk * kLanes, qr, qi, mix == 0.f ? 1.f : mix, g);
+    }
+    float *rows = &transposed[warp][0][0];
+    const float *force = plan.Force + im.ForceOff;
+    for (uint32_t tile = 0; tile < im.Len; tile += kTile) {
+        const uint32_t nv = min(kTile, im.Len - tile);
+        for (uint32_t s = 0; s < nv; ++s) {
+            const float f = __ldg(force + tile + s);
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float rx = fmaf(-v.Im[i].x, cim[i].x, fmaf(v.Re[i].x, cre[i].x, f * g.Re[i].x));
+                const float ry = fmaf(-v.Im[i].y, cim[i].y, fmaf(v.Re[i].y, cre[i].y, f * g.Re[i].y));
+                v.Im[i].x = fmaf(v.Re[i].x, cim[i].x, fmaf(v.Im[i].x, cre[i].x, f * g.Im[i].x));
+                v.Im[i].y = fmaf(v.Re[i].y, cim[i].y, fmaf(v.Im[i].y, cre[i].y, f * g.Im[i].y));
+                v.Re[i].x = rx, v.Re[i].y = ry;
+                sum += v.Im[i].x + v.Im[i].y;
+            }
+            rows[s * kRowPad + lane] = sum * out_scale;
+        }
+        __syncwarp();
+        if (lane < nv) plan.Rows[job.RowOff + tile + lane] = SumRow(rows, lane);
+        __syncwarp();
+    }
+    if (valid) {
+        const uint32_t off = im.DeltaOff + my_chunk * kLanes;
+        Store8(plan.DeltaRe + off, v.Re), Store8(plan.DeltaIm + off, v.Im);
+    }
+}
+
+// Block-parallel scan along time: one thread per chunk walks the window's segment boundaries, carrying the rotated
+// state in FP64 and jumping between events with c^m = exp(m ln|c|) (cos m*arg c + i sin m*arg c).
+__global__ void __launch_bounds__(128) SegmentScanKernel(const BankView b, const RenderPlan plan, float *__restrict__ seg_re, float *__restrict__ seg_im) {
+    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chunk >= b.NChunks) return;
+    const uint32_t object = b.ChunkObject[chunk];
+    const uint32_t mode0 = chunk * kLanes;
+    if (object == kNoObject) {
+        for (uint32_t s = 1; s < plan.NSegments; ++s)
+            for (uint32_t l = 0; l < kLanes; ++l) seg_re[size_t(s - 1) * b.NChunks * kLanes + mode0 + l] = seg_im[size_t(s - 1) * b.NChunks * kLanes + mode0 + l] = 0.f;
+        return;
+    }
+    const uint32_t my_chunk = chunk - b.ObjFirstChunk[object];
+    const float mix = b.ObjMixGain[object];
+    const double gain = mix == 0.f ? 1.0 : double(mix);
+    double wr[kLanes], wi[kLanes], log_rho[kLanes], theta[kLanes];
+    for (uint32_t l = 0; l < kLanes; ++l) {
+        const double zr = b.StateRe[mode0 + l], zi = b.StateIm[mode0 + l], qr = b.PhaseIm[mode0 + l], qi = b.PhaseRe[mode0 + l];
+        wr[l] = (zr * qr - zi * qi) * gain, wi[l] = (zr * qi + zi * qr) * gain;
+        log_rho[l] = b.LogRho[mode0 + l], theta[l] = b.Theta[mode0 + l];
+    }
+    const auto jump = [&](uint32_t m) {
+        if (m == 0) return;
+        for (uint32_t l = 0; l < kLanes; ++l) {
+            const double mag = exp(double(m) * log_rho[l]); // ln 0 = -inf -> 0
+            double sn, cs;
+            sincos(double(m) * theta[l], &sn, &cs);
+            const double re = (wr[l] * cs - wi[l] * sn) * mag, im = (wr[l] * sn + wi[l] * cs) * mag;
+            wr[l] = re, wi[l] = im;
+        }
+    };
+    uint32_t inj = plan.ObjInjectPtr[object];
+    const uint32_t inj_hi = plan.ObjInjectPtr[object + 1];
+    while (inj < inj_hi && plan.InjectFrame[inj] < plan.FrameBegin) ++inj;
+    uint32_t cursor = plan.FrameBegin;
+    for (uint32_t s = 1; s < plan.NSegments; ++s) {
+        const uint32_t boundary = plan.FrameBegin + s * plan.SegmentFrames;
+        // Increments landing strictly before the boundary; one landing on it is added by the segment's own thread.
+        for (; inj < inj_hi && plan.InjectFrame[inj] < boundary; ++inj) {
+            jump(plan.InjectFrame[inj] - cursor);
+            cursor = plan.InjectFrame[inj];
+            const uint32_t off = plan.InjectDelta[inj] + my_chunk * kLanes;
+            for (uint32_t l = 0; l < kLanes; ++l) wr[l] += double(plan.DeltaRe[off + l]), wi[l] += double(plan.DeltaIm[off + l]);
+        }
+        jump(boundary - cursor);
+        cursor = boundary;
+        const size_t out = size_t(s - 1) * b.NChunks * kLanes + mode0;
+        for (uint32_t l = 0; l < kLanes; ++l) seg_re[out + l] = float(wr[l]), seg_im[out + l] = float(wi[l]);
+    }
+}
+
+// out[n] = sum of the warp rows in fixed order + the pulse rows overlapping n (sorted by start, so also fixed order).
+__global__ void MixKernel(const float *__restrict__ partial, uint32_t rows, const RenderPlan plan, const PulsePlan pulses, float *__restrict__ out) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= plan.Frames) return;
+    float a = 0.f, b2 = 0.f, c = 0.f, d = 0.f;
+    uint32_t r = 0;
+    for (; r + 4 <= rows; r += 4) {
+        a += partial[size_t(r) * plan.Frames + n];
+        b2 += partial[size_t(r + 1) * plan.Frames + n];
+        c += partial[size_t(r + 2) * plan.Frames + n];
+        d += partial[size_t(r + 3) * plan.Frames + n];
+    }
+    for (; r < rows; ++r) a += partial[size_t(r) * plan.Frames + n];
+    float sum = (a + b2) + (c + d);
+    if (pulses.NPulseWarps) {
+        const uint32_t n_abs = plan.FrameBegin + n;
+        // First pulse-warp whose start could still cover n_abs.
+        const uint32_t earliest = n_abs >= pulses.MaxLen ? n_abs - pulses.MaxLen + 1 : 0;
+        uint32_t lo = 0, hi = pulses.NPulseWarps;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (pulses.Impacts[pulses.Warps[mid].Impact].Start < earliest) lo = mid + 1;
+            else hi = mid;
+        }
+        float extra = 0.f;
+        for (uint32_t i = lo; i < pulses.NPulseWarps; ++i) {
+            const PulseWarp pw = pulses.Warps[i];
+            const uint32_t start = pulses.Impacts[pw.Impact].Start;
+            if (start > n_abs) break;
+            if (n_abs - start < pulses.Impacts[pw.Impact].Len) extra += pulses.Rows[pw.RowOff + (n_abs - start)];
+        }
+        sum += extra;
+    }
+    out[n] = sum;
+}
+
+// One thread per impact: the raised-cosine force curve from a unit-circle rotor, with the reference's own float
+// operation order and no FMA contraction (ModalAudio.cpp:517-526), so the curve is bit-identical.
+__global__ void ForceKernel(const DevImpact *__restrict__ impacts, const DevImpactTail *__restrict__ tails, uint32_t n, float *__restrict__ force) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevImpact im = impacts[i];
+    const float half_gamma = __fmul_rn(tails[i].Gamma, 0.5f);
+    float pr = im.PhaseRe, pi = im.PhaseIm;
+    float *f = force + im.ForceOff;
+    for (uint32_t s = 0; s < im.Len; ++s) {
+        const float re = __fsub_rn(__fmul_rn(pr, im.RotRe), __fmul_rn(pi, im.RotIm));
+        pi = __fadd_rn(__fmul_rn(pr, im.RotIm), __fmul_rn(pi, im.RotRe));
+        pr = re;
+        f[s] = __fmul_rn(half_gamma, __fsub_rn(1.f, pr));
+    }
+}
+
+// One thread per click-carrying impact: the coupled recoil biquad driven by the force pulse (ModalAudio.cpp:527-531).
+__global__ void ClickKernel(const DevImpact *__restrict__ impacts, const DevImpactTail *__restrict__ tails, uint32_t n, float *__restrict__ out, uint32_t frames) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const DevImpact im = impacts[i];
+    if (!im.HasClick) return;
+    const DevImpactTail t = tails[i];
+    const float half_gamma = __fmul_rn(t.Gamma, 0.5f);
+    float pr = im.PhaseRe, pi = im.PhaseIm, z1 = t.ClickZ1, z2 = t.ClickZ2;
+    const uint32_t end = min(im.End, frames);
+    for (uint32_t s = im.Start; s < end; ++s) {
+        float cur = 0.f;
+        if (s - im.Start < im.Len) {
+            const float re = __fsub_rn(__fmul_rn(pr, im.RotRe), __fmul_rn(pi, im.RotIm));
+            pi = __fadd_rn(__fmul_rn(pr, im.RotIm), __fmul_rn(pi, im.RotRe));
+            pr = re;
+            cur = __fmul_rn(half_gamma, __fsub_rn(1.f, pr));
+        }
+        const float u = __fmul_rn(t.AccelAmp, cur);
+        const float y = __fadd_rn(__fmul_rn(t.ClickB0, u), z1);
+        z1 = __fadd_rn(__fmul_rn(-t.ClickA1, y), z2);
+        z2 = __fsub_rn(__fmul_rn(-t.ClickB0, u), __fmul_rn(t.ClickA2, y));
+        atomicAdd(out + s, __fmul_rn(y, t.ClickGain));
+    }
+}
+
+// ---- FP32 issue-rate micro-benchmark --------------------------------------------------------------------------
+
+// Mode 0: scalar FFMA. 1: packed FFMA2. 2: FFMA2 and FFMA interleaved 1:1 (instructions). 3: FFMA2:FFMA 1:2. 4: scalar FADD.
+template<int Mode>
+__global__ void __launch_bounds__(256) FmaRateKernel(float *sink, int inner) {
+    float2 a[8], b = {1.0000001f, 0.9999999f}, c = {1e-9f, -1e-9f};
+    float d[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = {float(threadIdx.x + i), float(i)}, d[i] = float(i) * 0.5f;
+    for (int it = 0; it < inner; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if constexpr (Mode == 1) {
+                a[i] = Fma2(a[i], b, c);
+            } else if constexpr (Mode == 0) {
+                a[i].x = fmaf(a[i].x, b.x, c.x);
+                a[i].y = fmaf(a[i].y, b.y, c.y);
+            } else if constexpr (Mode == 2) {
+                if (i < 4) a[i] = Fma2(a[i], b, c);
+                else d[i] = fmaf(d[i], b.x, c.x);
+            } else if constexpr (Mode == 3) {
+                if (i < 4) a[i] = Fma2(a[i], b, c);
+                else d[i] = fmaf(d[i], b.x, c.x), d[i - 4] = fmaf(d[i - 4], b.y, c.y);
+            } else {
+                a[i].x = a[i].x + c.x;
+                a[i].y = a[i].y + c.y;
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i].x + a[i].y + d[i];
+    if (s == 123.456f) sink[0] = s;
+}
+
+} // namespace
+
+uint32_t ResonatorRows(uint32_t n_chunks) { return (n_chunks + kBlockThreads - 1) / kBlockThreads * kWarpsPerBlock; }
+
+void LaunchForceKernel(const DevImpact *impacts, const DevImpactTail *tails, uint32_t n, float *force, cudaStream_t stream, LaunchCounter &counter) {
+    if (n == 0) return;
+    ForceKernel<<<(n + 127) / 128, 128, 0, stream>>>(impacts, tails, n, force);
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+void LaunchPulseKernel(const BankView &bank, const PulsePlan &plan, cudaStream_t stream, LaunchCounter &counter) {
+    if (plan.NPulseWarps == 0) return;
+    PulseKernel<<<(plan.NPulseWarps + kPulseWarps - 1) / kPulseWarps, kPulseWarps * 32, 0, stream>>>(bank, plan);
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+void LaunchSegmentScan(const BankView &bank, const RenderPlan &plan, float *seg_re, float *seg_im, cudaStream_t stream, LaunchCounter &counter) {
+    if (plan.NSegments <= 1 || bank.NChunks == 0) return;
+    SegmentScanKernel<<<(bank.NChunks + 127) / 128, 128, 0, stream>>>(bank, plan, seg_re, seg_im);
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int steps, cudaStream_t stream, LaunchCounter &counter) {
+    if (bank.NChunks == 0 || plan.Frames == 0) return;
+    const dim3 grid((bank.NChunks + kBlockThreads - 1) / kBlockThreads, plan.NSegments);
+    switch (steps) {
+        case 1: ResonatorKernel<1><<<grid, kBlockThreads, 0, stream>>>(bank, plan); break;
+        case 2: ResonatorKernel<2><<<grid, kBlockThreads, 0, stream>>>(bank, plan); break;
+        default: ResonatorKernel<4><<<grid, kBlockThreads, 0, stream>>>(bank, plan); break;
+    }
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+void LaunchMixKernel(const float *partial, uint32_t rows, const RenderPlan &plan, const PulsePlan &pulses, float *out, cudaStream_t stream, LaunchCounter &counter) {
+    if (plan.Frames == 0) return;
+    MixKernel<<<(plan.Frames + 255) / 256, 256, 0, stream>>>(partial, rows, plan, pulses, out);
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+void LaunchClickKernel(const DevImpact *impacts, const DevImpactTail *tails, uint32_t n, float *out, uint32_t frames, cudaStream_t stream, LaunchCounter &counter) {
+    if (n == 0) return;
+    ClickKernel<<<(n + 127) / 128, 128, 0, stream>>>(impacts, tails, n, out, frames);
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+double MeasureFmaRate(int mode, int iters) {
+    int device = 0, sms = 0;
+    ME_CUDA(cudaGetDevice(&device));
+    ME_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    float *sink = nullptr;
+    ME_CUDA(cudaMalloc(&sink, sizeof(float)));
+    const int inner = 4096, blocks = sms * 8, threads = 256;
+    cudaEvent_t start, stop;
+    ME_CUDA(cudaEventCreate(&start));
+    ME_CUDA(cudaEventCreate(&stop));
+    auto launch = [&] {
+        switch (mode) {
+            case 0: FmaRateKernel<0><<<blocks, threads>>>(sink, inner); break;
+            case 1: FmaRateKernel<1><<<blocks, threads>>>(sink, inner); break;
+            case 2: FmaRateKernel<2><<<blocks, threads>>>(sink, inner); break;
+            case 3: FmaRateKernel<3><<<blocks, threads>>>(sink, inner); break;
+            default: FmaRateKernel<4><<<blocks, threads>>>(sink, inner); break;
+        }
+    };
+    for (int i = 0; i < 3; ++i) launch();
+    ME_CUDA(cudaEventRecord(start));
+    for (int i = 0; i < iters; ++i) launch();
+    ME_CUDA(cudaEventRecord(stop));
+    ME_CUDA(cudaEventSynchronize(stop));
+    float ms = 0.f;
+    ME_CUDA(cudaEventElapsedTime(&ms, start, stop));
+    cudaEventDestroy(start), cudaEventDestroy(stop), cudaFree(sink);
+    // Lane-operations per thread per inner iteration.
+    const double per_iter = mode == 2 ? 12.0 : 16.0;
+    return double(iters) * blocks * threads * double(inner) * per_iter / (double(ms) * 1e-3);
+}
+
+} // namespace me
