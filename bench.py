@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the modal hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[4], the polyphonic resonator bank — 1024 voices x 500 modes x 10 s at
+48 kHz, one strike per voice at frame 0 plus Poisson re-strikes — the one metric BASELINE.json quotes at 1/2/4/8 B200.
+A "step" is one offline render of the whole 10 s timeline. Voices are sharded over the ranks (strong scaling: the total
+stays 1024 voices) and the per-rank mono mixes are summed with one NCCL all-reduce over NVLink.
+
+`value`  = mode-samples/s with the bank resident in HBM, timed on the device (CUDA events, max over ranks).
+`e2e`    = the same metric through the C ABI with the strike timeline in HOST memory and the mix read back to HOST.
+`roofline` = FP32 issue ceiling (the resonator is FP32-ALU bound); `roofline_hbm` = mandatory bytes.
+`cpu_baseline` = the UNMODIFIED reference RenderModal (oracle/_ref) on the host cores, on a bounded sample.
+`--impl reference` runs only that CPU arm and prints it in the same format.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOICES, MODES, SECONDS, RATE, BLOCK = 1024, 500, 10.0, 48000.0, 512
+METRIC, UNIT = "resonator mode-samples/s", "mode-samples/s"
+OPS_PER_MODE_SAMPLE = 2.75  # FP32 lane-operations per mode-sample of the K=4 kernel: (2K+3)/K
+REF_OPS_PER_MODE_SAMPLE = 7.0  # the reference's loop, SURVEY.md §8(d)
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """One `nvidia-smi -lms` process sampling clocks and throttle reasons while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.rows = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.3)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            self.rows = [[x.strip() for x in line.split(",")] for line in out.splitlines() if line.count(",") >= 6]
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        # "Under load" = samples drawing more than the idle floor; the median SM clock over those.
+        power = [float(r[2]) for r in self.rows]
+        loaded = [r for r, p in zip(self.rows, power) if p >= 0.5 * max(power)] or self.rows
+        sm = sorted(float(r[0]) for r in loaded)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(power), "samples": len(self.rows), "samples_under_load": len(loaded), "reasons": reasons}
+
+
+def cpu_reference(steps, warmup, voices=256, seconds=1.0, quiet=False):
+    """The reference's own RenderModal (oracle/_ref/libme_ref_audio.so, built from /root/reference sources) on the host
+    cores, RenderThreads = min(16, cores) (its cap, src/audio/AudioSystem.cpp:60), 512-frame blocks."""
+    from mesheditor_b200 import workloads as wl
+    from oracle import resonator as orc
+
+    kind = "reference" if orc.have_ref() else "port"
+    cores = os.cpu_count() or 1
+    threads = min(16, cores) if kind == "reference" else 1
+    modes = wl.c5_modes(MODES)
+    blocks = int(seconds * RATE) // BLOCK
+    events, ev_frames, _ = wl.c5_timeline(voices, blocks * BLOCK)
+    times, live = [], None
+    for it in range(warmup + steps):
+        scene = (orc.RefScene if kind == "reference" else orc.PortBank)(RATE, threads)
+        for _ in range(voices):
+            scene.add_modes(modes)
+        scene.install()
+        out = np.zeros(blocks * BLOCK, np.float32)
+        k = 0
+        t0 = time.perf_counter()
+        for b in range(blocks):
+            while k < len(events) and ev_frames[k] == b * BLOCK:
+                v, impulse, ex = events[k]
+                scene.enqueue(orc.impact_event(v, impulse, ex))
+                k += 1
+            scene.render(out[b * BLOCK:(b + 1) * BLOCK])
+        dt = time.perf_counter() - t0
+        live = scene.object_column("LiveModeCount")
+        if it >= warmup:
+            times.append(dt)
+    mode_samples = voices * MODES * blocks * BLOCK
+    ms = 1e3 * sum(times) / len(times)
+    return {
+        "value": mode_samples / (ms * 1e-3), "unit": UNIT, "cores": threads, "kind": kind, "ms_per_step": ms,
+        "sample": f"{voices} voices x {MODES} modes x {blocks * BLOCK} frames ({blocks} blocks of {BLOCK}), same strike recipe; LiveModeCount {int(live.min())}..{int(live.max())} of {MODES} (no culling)",
+    }
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    base = cpu_reference(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus), "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": f"BASELINE.json configs[4]: polyphonic resonator bank {VOICES} voices x {MODES} modes x {SECONDS:g} s at {RATE:g} Hz, strike per voice at frame 0 + 2 Hz Poisson re-strikes (MT19937 12345), 512-frame blocks",
+        "voices": VOICES, "modes_per_voice": MODES, "frames": int(SECONDS * RATE), "sample_rate": RATE, "block_frames": BLOCK,
+        "parallelism": f"voices sharded over {n_gpus} GPU(s), NCCL all-reduce of the mono mix" if n_gpus > 1 else "single GPU",
+        "l2_policy": "working set > L2: per-warp partial mixes of one step exceed 126 MB, nothing is reused across steps",
+    }
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from mesheditor_b200 import ModalBank, build, measure_fp32_fma_rate
+    from mesheditor_b200 import workloads as wl
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    frames = int(SECONDS * RATE)
+    lo, hi = wl.shard_voices(VOICES, world, rank)
+    modes = wl.c5_modes(MODES)
+    all_events, all_frames, all_voice = wl.c5_timeline(VOICES, frames)
+    mine = (all_voice >= lo) & (all_voice < hi)
+    events = [wl.impact(v - lo, impulse, ex) for (v, impulse, ex), keep in zip(all_events, mine) if keep]
+    ev_frames = all_frames[mine]
+    events = ModalBank.pack_events(events, ev_frames)  # contiguous MeModalEvent[] + frames, built once
+
+    bank = ModalBank(RATE, local)
+    for _ in range(hi - lo):
+        bank.add_modes(modes)
+    bank.install(0)
+
+    out = torch.zeros(frames, dtype=torch.float32, device="cuda")
+    host_out = torch.zeros(frames, dtype=torch.float32).pin_memory()
+    # One explicit stream carries the library's kernels, the NCCL all-reduce and the timing events.
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    launches = [0]
+
+    def step_device():
+        bank.render_offline_device(events, ev_frames, frames, BLOCK, out.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(out)
+
+    def step_e2e():
+        # Strike timeline from host memory in, final mix back in host memory (rank 0 keeps it).
+        bank.render_offline_device(events, ev_frames, frames, BLOCK, out.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            dist.all_reduce(out)
+        host_out.copy_(out, non_blocking=True)
+        stream.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # Each step re-renders the same 10 s from a silent bank, so every step does identical work.
+    def reset():
+        bank.install(0)
+
+    for _ in range(max(args.warmup, 3)):
+        reset()
+        step_device()
+    barrier()
+
+    kernel_ms, stats = [], None
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    elapsed_ms = 0.0
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            reset()
+            barrier()
+            start.record(stream)
+            step_device()
+            stop.record(stream)
+            barrier()
+            elapsed_ms += start.elapsed_time(stop)
+            stats = bank.stats()
+            kernel_ms.append(stats["resonator_kernel_ms"])
+            launches[0] += stats["kernel_launches"]
+    # e2e: wall clock around the host-buffer path.
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        reset()
+        barrier()
+        t0 = time.perf_counter()
+        step_e2e()
+        e2e_s += time.perf_counter() - t0
+        launches[0] += bank.stats()["kernel_launches"]
+    barrier()
+
+    live = [bank.object_status(v)["LiveModeCount"] for v in range(hi - lo)]
+    fallbacks = stats["scan_fallbacks"]
+    t = torch.tensor([elapsed_ms, e2e_s, float(launches[0]), float(min(live)) - 1e6 * fallbacks], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmin = t.clone()
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        elapsed_ms, e2e_s, total_launches, min_live = float(tmax[0]), float(tmax[1]), int(tsum[2]), int(tmin[3])
+    else:
+        total_launches, min_live = launches[0], int(min(live))
+
+    if rank == 0:
+        total_mode_samples = VOICES * MODES * frames
+        ms_per_step = elapsed_ms / args.steps
+        value = total_mode_samples / (ms_per_step * 1e-3)
+        e2e_value = total_mode_samples / (e2e_s / args.steps)
+        pk, pk_kind = peaks()
+        fma_peak = measure_fp32_fma_rate(local, 0, 10)       # scalar FFMA, the nominal FP32 issue ceiling
+        fma_peak_fresh = measure_fp32_fma_rate(local, 5, 10)  # FFMA2 with three fresh register pairs (register-file bound)
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        rank_mode_samples = (hi - lo) * MODES * frames
+        achieved = OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "resonator_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        # Mandatory bytes of one launch on this rank: 32 B per mode of state/coefficients + the per-warp
+        # partial rows written once (4 B per warp-sample) — the latter is this design's own traffic, counted as such.
+        mandatory = (hi - lo) * (32 * MODES) + 4 * frames
+        base = cpu_reference(1, 0) if not args.no_cpu_baseline else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(world), live_mode_count_min=min_live, culling_triggered=min_live < MODES, time_segments=stats["time_segments"]),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": frames * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": total_launches,
+            "roofline": {
+                "bound": "fp32_fma", "kernel": "ResonatorKernel<4,2>", "achieved": achieved / 1e12, "peak": fma_peak / 1e12, "unit": "TFMA-lane-op/s",
+                "frac": achieved / fma_peak, "traffic": traffic, "kernel_ms_per_launch": k_ms,
+                "ops_per_mode_sample": OPS_PER_MODE_SAMPLE, "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
+                "peak_three_fresh_operands": fma_peak_fresh / 1e12, "frac_of_register_file_bound": achieved / fma_peak_fresh,
+                "reference_op_equivalent_frac": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3) / fma_peak,
+            },
+            "roofline_hbm": {"bound": "hbm", "achieved": mandatory / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": mandatory / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_kind,
+                             "note": "mandatory bytes only; the path is FP32-issue bound by >100x (SURVEY.md F9)"},
+            "clocks": clocks.summary(),
+        }
+        if base:
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -133,6 +133,7 @@ typedef struct MeRenderStats {
     uint64_t mode_samples;          /* sum over objects of TunedModeCount x frames */
     uint64_t h2d_bytes, d2h_bytes;  /* host<->device bytes moved by the call */
     uint32_t time_segments;         /* segments of the block-parallel scan along time (1 = sequential in time) */
+    uint32_t scan_fallbacks;        /* windows re-rendered sequentially because culling fell inside them */
 } MeRenderStats;
 MeStatus me_bank_last_render_stats(const MeBank *, MeRenderStats *out);
 /* Scheduling knobs of the offline renderer: time_segments 0 = automatic. */

@@ -105,12 +105,17 @@ class ModalBank:
         return out
 
     @staticmethod
-    def _pack_events(events, frames):
+    def pack_events(events, frames):
+        """Timeline as the C ABI takes it: a contiguous MeModalEvent array and ascending frame numbers."""
+        if isinstance(events, tuple) and len(events) == 3:
+            return events
         n = len(events)
         arr = (MeModalEvent * max(n, 1))(*events)
         fr = np.ascontiguousarray(frames, np.uint64)
         assert fr.size == n
         return arr, fr, n
+
+    _pack_events = pack_events
 
     def render_offline(self, events, frames, total_frames, block_frames=512, out=None):
         arr, fr, n = self._pack_events(events, frames)

@@ -15,7 +15,7 @@ constexpr float AirDensity{1.204f}, SpeedOfSound{343.f}, ListenerDistance{1.f};
 constexpr float Ln1000 = 3 * std::numbers::ln10_v<float>;
 constexpr float Pi = std::numbers::pi_v<float>;
 
-constexpr size_t PartialBudgetBytes = size_t(1) << 30; // per-CTA partial mixes kept in HBM per launch window
+constexpr size_t PartialBudgetBytes = size_t(8) << 30; // per-warp partial mixes kept in HBM per launch window (of 180 GB)
 
 uint32_t PaddedModes(uint32_t count) { return (count + kLanes - 1) / kLanes * kLanes; }
 
@@ -533,7 +533,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                     if (std::getenv("ME_RESONATOR_DEBUG")) fprintf(stderr, "[me] speculation failed: code %u (window %u+%u, %u segments)\n", failed, begin, wf, segments);
                     // A culling decision inside the window: render it again sequentially in time (still on the GPU).
                     SpeculationFailed = true;
-                    ++Stats.time_segments; // reported as "segments + 1 fallback" below
+                    ++Stats.scan_fallbacks;
                     plan.NSegments = 1;
                     plan.SegmentFrames = blocks * block_frames;
                     LaunchResonatorKernel(view, plan, Steps, stream, Counter);

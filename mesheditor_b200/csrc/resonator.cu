@@ -30,11 +30,12 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 namespace me {
 namespace {
 
-constexpr uint32_t kRowPad = 36; // floats per transposed row: 32 + 4 keeps float4 alignment and spreads banks
+constexpr uint32_t kRowPad = 68; // floats per transposed row: 32 float2 partial sums + 4 keeps float4 alignment and spreads banks
 constexpr float kSilentEnergy = 1e-12f; // ModalAudio.cpp:20
 
 __device__ __forceinline__ uint64_t AsBits(float2 v) { return reinterpret_cast<uint64_t &>(v); }
@@ -95,32 +96,35 @@ __device__ __forceinline__ void MakePowers(const float2 (&cre)[4], const float2 
 }
 
 // K samples: y[j] = sum Im(c^(j+1) w) for j < K-1 straight off the state, then w <- c^K w and y[K-1] = sum Im w.
+// Each sample is left as a float2 of two partial sums (the row sum adds them). Instructions that share a state
+// operand are kept adjacent so the operand-reuse cache can serve it: FFMA2 with three fresh register pairs is
+// bound by register-file bandwidth, not by the FMA pipe.
 template<int K>
-__device__ __forceinline__ void StepK(Chunk &w, const Powers<K> &p, float scale, float *column) {
-#pragma unroll
-    for (int j = 0; j + 1 < K; ++j) {
-        float2 acc = Mul2(p.Re[j][0], w.Im[0]);
-        acc = Fma2(p.Im[j][0], w.Re[0], acc);
-#pragma unroll
-        for (int i = 1; i < 4; ++i) {
-            acc = Fma2(p.Re[j][i], w.Im[i], acc);
-            acc = Fma2(p.Im[j][i], w.Re[i], acc);
-        }
-        column[j * kRowPad] = (acc.x + acc.y) * scale;
-    }
+__device__ __forceinline__ void StepK(Chunk &w, const Powers<K> &p, float2 *column) {
+    float2 acc[K > 1 ? K - 1 : 1];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float2 re = Fma2(w.Im[i], p.NegImK[i], Mul2(w.Re[i], p.Re[K - 1][i]));
-        w.Im[i] = Fma2(w.Re[i], p.Im[K - 1][i], Mul2(w.Im[i], p.Re[K - 1][i]));
-        w.Re[i] = re;
+#pragma unroll
+        for (int j = 0; j + 1 < K; ++j) acc[j] = i == 0 ? Mul2(p.Re[j][0], w.Im[0]) : Fma2(p.Re[j][i], w.Im[i], acc[j]);
+#pragma unroll
+        for (int j = 0; j + 1 < K; ++j) acc[j] = Fma2(p.Im[j][i], w.Re[i], acc[j]);
     }
-    const float2 s = Add2(Add2(w.Im[0], w.Im[1]), Add2(w.Im[2], w.Im[3]));
-    column[(K - 1) * kRowPad] = (s.x + s.y) * scale;
+#pragma unroll
+    for (int j = 0; j + 1 < K; ++j) column[j * (kRowPad / 2)] = acc[j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 t2 = Mul2(w.Im[i], p.Re[K - 1][i]);
+        const float2 t1 = Mul2(w.Re[i], p.Re[K - 1][i]);
+        const float2 im = Fma2(w.Re[i], p.Im[K - 1][i], t2);
+        w.Re[i] = Fma2(w.Im[i], p.NegImK[i], t1);
+        w.Im[i] = im;
+    }
+    column[(K - 1) * (kRowPad / 2)] = Add2(Add2(w.Im[0], w.Im[1]), Add2(w.Im[2], w.Im[3]));
 }
 
 // One sample with c^1 (remainders of a tile that is not a multiple of K).
 template<int K>
-__device__ __forceinline__ void Step1(Chunk &w, const Powers<K> &p, float scale, float *column) {
+__device__ __forceinline__ void Step1(Chunk &w, const Powers<K> &p, float2 *column) {
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -131,15 +135,15 @@ __device__ __forceinline__ void Step1(Chunk &w, const Powers<K> &p, float scale,
         w.Re[i].x = rx, w.Re[i].y = ry;
         sum += w.Im[i].x + w.Im[i].y;
     }
-    column[0] = sum * scale;
+    column[0] = float2{sum, 0.f};
 }
 
-// Lane s sums sample s over the warp's 32 columns.
+// Lane s sums sample s over the warp's 32 columns (64 partial sums).
 __device__ __forceinline__ float SumRow(const float *rows, uint32_t lane) {
     const float4 *r = reinterpret_cast<const float4 *>(rows + lane * kRowPad);
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
+    for (int j = 0; j < 16; j += 2) {
         const float4 x = r[j], y = r[j + 1];
         a += (x.x + x.y) + (x.z + x.w);
         b += (y.x + y.y) + (y.z + y.w);
@@ -147,9 +151,10 @@ __device__ __forceinline__ float SumRow(const float *rows, uint32_t lane) {
     return a + b;
 }
 
-template<int K>
-__global__ void __launch_bounds__(kBlockThreads) ResonatorKernel(const BankView b, const RenderPlan plan) {
-    __shared__ __align__(16) float transposed[kWarpsPerBlock][kTile][kRowPad];
+template<int K, int MinBlocks>
+__global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(const BankView b, const RenderPlan plan) {
+    extern __shared__ __align__(16) float transposed_storage[];
+    float (*transposed)[kTile][kRowPad] = reinterpret_cast<float (*)[kTile][kRowPad]>(transposed_storage);
     __shared__ float cull_energy[kBlockThreads];
     __shared__ uint8_t cull_audible[kBlockThreads];
 
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kBlockThreads) ResonatorKernel(const BankView 
     };
 
     float *rows = &transposed[warp][0][0];
-    float *column = rows + lane;
+    float2 *column = reinterpret_cast<float2 *>(rows) + lane;
     float *partial = plan.Partial + size_t(blockIdx.x * kWarpsPerBlock + warp) * plan.Frames;
 
     uint32_t pos = seg_begin;
@@ -272,14 +277,15 @@ __global__ void __launch_bounds__(kBlockThreads) ResonatorKernel(const BankView 
                 while (true) {
                     uint32_t lim = nv;
                     if (inj_frame - tile_abs < nv) lim = inj_frame - tile_abs; // inj_frame >= tile_abs + s
-                    for (; s + K <= lim; s += K) StepK<K>(w, p, out_scale, column + s * kRowPad);
-                    for (; s < lim; ++s) Step1<K>(w, p, out_scale, column + s * kRowPad);
+                    for (; s + K <= lim; s += K) StepK<K>(w, p, column + s * (kRowPad / 2));
+                    for (; s < lim; ++s) Step1<K>(w, p, column + s * (kRowPad / 2));
                     if (s == nv) break;
                     while (inj_frame == tile_abs + s) inject();
                 }
-            } else {
-                for (uint32_t s = 0; s < nv; ++s) column[s * kRowPad] = 0.f;
             }
+            // A chunk sitting the block out adds nothing; a muted object (mix gain 0) evolves but its samples are discarded.
+            if (!rendered || out_scale == 0.f)
+                for (uint32_t s = 0; s < nv; ++s) column[s * (kRowPad / 2)] = float2{0.f, 0.f};
             __syncwarp();
             const float total = lane < nv ? SumRow(rows, lane) : 0.f;
             if (lane < nv) partial[tile + lane] = total;
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(kPulseWarps * 32) PulseKernel(const BankView b
                 v.Re[i].x = rx, v.Re[i].y = ry;
                 sum += v.Im[i].x + v.Im[i].y;
             }
-            rows[s * kRowPad + lane] = sum * out_scale;
+            reinterpret_cast<float2 *>(rows)[s * (kRowPad / 2) + lane] = float2{sum * out_scale, 0.f};
         }
         __syncwarp();
         if (lane < nv) plan.Rows[job.RowOff + tile + lane] = SumRow(rows, lane);
@@ -463,19 +469,31 @@ __global__ void __launch_bounds__(128) SegmentScanKernel(const BankView b, const
 }
 
 // out[n] = sum of the warp rows in fixed order + the pulse rows overlapping n (sorted by start, so also fixed order).
-__global__ void MixKernel(const float *__restrict__ partial, uint32_t rows, const RenderPlan plan, const PulsePlan pulses, float *__restrict__ out) {
-    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= plan.Frames) return;
+// A CTA owns 32 consecutive frames; its 8 warps each sum a fixed residue class of the rows, coalesced along n, and
+// the eight partial sums are combined in warp order.
+constexpr uint32_t kMixWarps = 8;
+__global__ void __launch_bounds__(kMixWarps * 32) MixKernel(const float *__restrict__ partial, uint32_t rows, const RenderPlan plan, const PulsePlan pulses, float *__restrict__ out) {
+    __shared__ float sums[kMixWarps][32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = blockIdx.x * 32 + lane;
+    const bool in_range = n < plan.Frames;
     float a = 0.f, b2 = 0.f, c = 0.f, d = 0.f;
-    uint32_t r = 0;
-    for (; r + 4 <= rows; r += 4) {
-        a += partial[size_t(r) * plan.Frames + n];
-        b2 += partial[size_t(r + 1) * plan.Frames + n];
-        c += partial[size_t(r + 2) * plan.Frames + n];
-        d += partial[size_t(r + 3) * plan.Frames + n];
+    if (in_range) {
+        uint32_t r = warp;
+        for (; r + 3 * kMixWarps < rows; r += 4 * kMixWarps) {
+            a += partial[size_t(r) * plan.Frames + n];
+            b2 += partial[size_t(r + kMixWarps) * plan.Frames + n];
+            c += partial[size_t(r + 2 * kMixWarps) * plan.Frames + n];
+            d += partial[size_t(r + 3 * kMixWarps) * plan.Frames + n];
+        }
+        for (; r < rows; r += kMixWarps) a += partial[size_t(r) * plan.Frames + n];
     }
-    for (; r < rows; ++r) a += partial[size_t(r) * plan.Frames + n];
-    float sum = (a + b2) + (c + d);
+    sums[warp][lane] = (a + b2) + (c + d);
+    __syncthreads();
+    if (warp != 0 || !in_range) return;
+    float sum = 0.f;
+#pragma unroll
+    for (uint32_t k = 0; k < kMixWarps; ++k) sum += sums[k][lane];
     if (pulses.NPulseWarps) {
         const uint32_t n_abs = plan.FrameBegin + n;
         // First pulse-warp whose start could still cover n_abs.
@@ -549,7 +567,7 @@ __global__ void __launch_bounds__(256) FmaRateKernel(float *sink, int inner) {
     float2 a[8], b = {1.0000001f, 0.9999999f}, c = {1e-9f, -1e-9f};
     float d[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = {float(threadIdx.x + i), float(i)}, d[i] = float(i) * 0.5f;
+    for (int i = 0; i < 8; ++i) a[i] = {Mode >= 5 ? 1e-3f * float(threadIdx.x + i) : float(threadIdx.x + i), Mode >= 5 ? 1e-3f * float(i) : float(i)}, d[i] = float(i) * 0.5f;
     for (int it = 0; it < inner; ++it) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -564,9 +582,16 @@ __global__ void __launch_bounds__(256) FmaRateKernel(float *sink, int inner) {
             } else if constexpr (Mode == 3) {
                 if (i < 4) a[i] = Fma2(a[i], b, c);
                 else d[i] = fmaf(d[i], b.x, c.x), d[i - 4] = fmaf(d[i - 4], b.y, c.y);
-            } else {
+            } else if constexpr (Mode == 4) {
                 a[i].x = a[i].x + c.x;
                 a[i].y = a[i].y + c.y;
+            } else if constexpr (Mode == 5) { // three fresh register pairs per FFMA2, no operand reuse possible
+                a[i] = Fma2(a[(i + 3) & 7], a[(i + 5) & 7], a[i]);
+            } else if constexpr (Mode == 6) { // two fresh pairs, one shared with the previous instruction's slot
+                a[i] = Fma2(b, a[(i + 5) & 7], a[i]);
+            } else { // scalar FFMA with three fresh registers
+                a[i].x = fmaf(a[(i + 3) & 7].x, a[(i + 5) & 7].y, a[i].x);
+                a[i].y = fmaf(a[(i + 3) & 7].y, a[(i + 5) & 7].x, a[i].y);
             }
         }
     }
@@ -604,10 +629,26 @@ void LaunchSegmentScan(const BankView &bank, const RenderPlan &plan, float *seg_
 void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int steps, cudaStream_t stream, LaunchCounter &counter) {
     if (bank.NChunks == 0 || plan.Frames == 0) return;
     const dim3 grid((bank.NChunks + kBlockThreads - 1) / kBlockThreads, plan.NSegments);
+    constexpr size_t smem = sizeof(float) * kWarpsPerBlock * kTile * kRowPad;
+    static const bool wide = [] {
+        const char *occ = std::getenv("ME_RESONATOR_OCC");
+        return occ && occ[0] == '1';
+    }();
+    static bool configured = false;
+    if (!configured) {
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = true;
+    }
     switch (steps) {
-        case 1: ResonatorKernel<1><<<grid, kBlockThreads, 0, stream>>>(bank, plan); break;
-        case 2: ResonatorKernel<2><<<grid, kBlockThreads, 0, stream>>>(bank, plan); break;
-        default: ResonatorKernel<4><<<grid, kBlockThreads, 0, stream>>>(bank, plan); break;
+        case 1: ResonatorKernel<1, 2><<<grid, kBlockThreads, smem, stream>>>(bank, plan); break;
+        case 2: ResonatorKernel<2, 2><<<grid, kBlockThreads, smem, stream>>>(bank, plan); break;
+        default:
+            if (wide) ResonatorKernel<4, 1><<<grid, kBlockThreads, smem, stream>>>(bank, plan);
+            else ResonatorKernel<4, 2><<<grid, kBlockThreads, smem, stream>>>(bank, plan);
+            break;
     }
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
@@ -615,7 +656,7 @@ void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int ste
 
 void LaunchMixKernel(const float *partial, uint32_t rows, const RenderPlan &plan, const PulsePlan &pulses, float *out, cudaStream_t stream, LaunchCounter &counter) {
     if (plan.Frames == 0) return;
-    MixKernel<<<(plan.Frames + 255) / 256, 256, 0, stream>>>(partial, rows, plan, pulses, out);
+    MixKernel<<<(plan.Frames + 31) / 32, kMixWarps * 32, 0, stream>>>(partial, rows, plan, pulses, out);
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
 }
@@ -643,7 +684,10 @@ double MeasureFmaRate(int mode, int iters) {
             case 1: FmaRateKernel<1><<<blocks, threads>>>(sink, inner); break;
             case 2: FmaRateKernel<2><<<blocks, threads>>>(sink, inner); break;
             case 3: FmaRateKernel<3><<<blocks, threads>>>(sink, inner); break;
-            default: FmaRateKernel<4><<<blocks, threads>>>(sink, inner); break;
+            case 4: FmaRateKernel<4><<<blocks, threads>>>(sink, inner); break;
+            case 5: FmaRateKernel<5><<<blocks, threads>>>(sink, inner); break;
+            case 6: FmaRateKernel<6><<<blocks, threads>>>(sink, inner); break;
+            default: FmaRateKernel<7><<<blocks, threads>>>(sink, inner); break;
         }
     };
     for (int i = 0; i < 3; ++i) launch();
