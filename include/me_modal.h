@@ -139,6 +139,138 @@ MeStatus me_bank_last_render_stats(const MeBank *, MeRenderStats *out);
 /* Scheduling knobs of the offline renderer: time_segments 0 = automatic. */
 MeStatus me_bank_set_time_segments(MeBank *, uint32_t time_segments);
 
+/* ------------------------------------------------------------------------------------------------
+ * Analysis: tet mesh + material -> modal model (reference: src/audio/mesh2modes.{h,cpp}).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* AcousticMaterialProperties (src/audio/AcousticMaterialProperties.h:6-16). */
+typedef struct MeMaterial {
+    double density, young_modulus, poisson_ratio, alpha, beta;
+} MeMaterial;
+
+/* modal::SolverConfig (src/audio/mesh2modes.h:17-26) plus the two knobs this library adds. */
+typedef struct MeSolverConfig {
+    float min_mode_freq, max_mode_freq;   /* 20, 16000 */
+    uint32_t num_modes, num_fem_modes;    /* 30, 45 */
+    double tolerance, warm_tolerance;     /* 1e-8, 1e-4 */
+    uint32_t max_restarts;                /* 100 */
+    int32_t has_fundamental_freq;         /* std::optional<float> FundamentalFreq */
+    float fundamental_freq;
+    uint32_t element_order;               /* 2 = the reference's 10-node tets (parity mode); 1 = 4-node tets */
+    int32_t device;                       /* CUDA ordinal the solve runs on */
+} MeSolverConfig;
+void me_solver_config_default(MeSolverConfig *);
+
+/* JobMonitor (src/Job.h:13-19): progress written by the solve, cancelled polled between stages and restarts. */
+typedef struct MeJobMonitor {
+    volatile float progress;
+    volatile int32_t cancelled;
+} MeJobMonitor;
+
+/* modal::SolveProfile (src/audio/mesh2modes.h:30-50): the same fields (seconds, counters), then device-side detail. */
+typedef struct MeSolveProfile {
+    double mass_props, quad_mesh, assemble, sample_excite, factorize, iterate, op_solve, extract;
+    uint32_t dofs, stiffness_nonzeros, op_applications, restarts;
+    double analyse;                 /* host symbolic analysis (ordering + structure), part of `factorize` */
+    double factor_flops;            /* flops of the numeric factorisation, from the symbolic analysis */
+    uint64_t factor_nonzeros;       /* scalars in the supernodal factor */
+    float assemble_kernel_ms, factor_device_ms;
+    uint32_t supernodes, levels, kernel_launches, tets_kept;
+} MeSolveProfile;
+
+/* MassProperties (src/audio/ContactModel.h:16-23). Orientation is a unit quaternion (w, x, y, z) of the principal axes. */
+typedef struct MeMassProperties {
+    double mass;
+    float center_of_mass[3];
+    float inertia_diagonal[3];
+    float inertia_orientation[4];
+} MeMassProperties;
+
+typedef struct MeModalResult MeModalResult; /* modal::ModalResult (mesh2modes.h:52-62) */
+
+/* modal::mesh2modes (src/audio/mesh2modes.h:77, mesh2modes.cpp:605-658).
+ *   points_xyz [n_points][3] doubles, tets [n_tets][4] positively oriented (TetMesh, src/mesh/TetMesh.h:10-13);
+ *   excite_xyz [n_excite][3] floats (SI), each sampled at its nearest tet point; baked_scale[3];
+ *   seed_basis: a prior solve's eigenvector basis (seed_rows x seed_cols floats, column-major) or NULL. The warm
+ *   re-solve (SubspaceIterate, mesh2modes.cpp:339-428) is not built yet: a seed is accepted and the cold path runs,
+ *   which returns the same eigenpairs to the solver tolerance;
+ *   keep_basis: fill the result's basis (SolveReuse::KeepBasis).
+ * Status mirrors the reference's failure modes: ME_CANCELLED / ME_NOT_CONVERGED / ME_NO_MODES leave *out holding an
+ * EMPTY result (the reference returns an empty ModalResult); ME_FACTOR_FAILED is the reference's std::runtime_error. */
+MeStatus me_modal_solve(const double *points_xyz, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const MeMaterial *material,
+                        const float *excite_xyz, uint32_t n_excite, const float baked_scale[3], const MeSolverConfig *config,
+                        const float *seed_basis, uint32_t seed_rows, uint32_t seed_cols, int keep_basis, MeJobMonitor *monitor,
+                        MeModalResult **out);
+void me_modal_result_free(MeModalResult *);
+
+/* ModalModes (src/audio/ModalModes.h:7-20). Arrays are owned by the result. */
+uint32_t me_modal_result_mode_count(const MeModalResult *);        /* Freqs.size() */
+uint32_t me_modal_result_point_count(const MeModalResult *);       /* Positions.size() == Shapes.size() */
+const float *me_modal_result_freqs(const MeModalResult *);
+const float *me_modal_result_t60s(const MeModalResult *);
+const float *me_modal_result_shapes(const MeModalResult *);        /* [point][mode][3] */
+const float *me_modal_result_positions(const MeModalResult *);     /* [point][3], node-local */
+float me_modal_result_original_fundamental(const MeModalResult *); /* OriginalFundamentalFreq */
+/* ModalResult::SamplePointOfExcitation: [n_excite] indices into positions. */
+const uint32_t *me_modal_result_sample_point_of_excitation(const MeModalResult *, uint32_t *count);
+/* ModalEigenSummary (src/audio/ModalEigenSummary.h:12-23): raw eigenpairs at the sample points. */
+uint32_t me_modal_result_eigenpair_count(const MeModalResult *);
+const double *me_modal_result_eigenvalues(const MeModalResult *);
+const float *me_modal_result_summary_shapes(const MeModalResult *); /* [point][eigenpair][3] */
+MeStatus me_modal_result_mass_properties(const MeModalResult *, MeMassProperties *out);
+MeStatus me_modal_result_profile(const MeModalResult *, MeSolveProfile *out);
+/* ModalResult::Basis (n x eigenpairs floats, column-major) when keep_basis was set, else NULL. */
+const float *me_modal_result_basis(const MeModalResult *, uint32_t *rows, uint32_t *cols);
+
+/* modal::PostprocessModes (mesh2modes.h:82, mesh2modes.cpp:515-588), host-only: eigenvalues[n_eigen] ascending,
+ * shapes [n_points][n_eigen][3], positions [n_points][3]. Returns a result holding only the ModalModes part. */
+MeStatus me_postprocess_modes(const double *eigenvalues, uint32_t n_eigen, const float *shapes, uint32_t n_points, float shape_scale,
+                              const MeMaterial *material, const MeSolverConfig *config, const float *positions, MeModalResult **out);
+/* modal::RescaleModes (mesh2modes.h:88, mesh2modes.cpp:590-603), host-only: re-derives the modes of `solved` (solved with
+ * `solved_material`) under `material`. ME_BAD_ARG when the edit is not exactly scalable (the reference returns nullopt). */
+MeStatus me_rescale_modes(const MeModalResult *solved, const MeMaterial *solved_material, const MeMaterial *material,
+                          const MeSolverConfig *config, MeModalResult **out);
+
+/* --- Stages of the solve, exported for the parity tests and the roofline bench (inner operator concept of
+ *     src/audio/CholeskyShiftInvert.h:18-23 and lib/spectra/.../SparseSymMatProd.h:83). ------------------------------ */
+typedef struct MeFemSystem MeFemSystem;
+typedef struct MeFemInfo {
+    uint32_t tets_kept, node_count, dofs, nodes_per_element;
+    uint64_t nnz_stiffness, nnz_mass;   /* stored lower-triangular scalars, Eigen layout */
+    uint64_t node_blocks_lower, node_blocks_full;
+    float assemble_kernel_ms;
+    uint32_t kernel_launches;
+} MeFemInfo;
+/* FilterDegenerate + BuildQuadMesh + AssembleQuadratic on the device (mesh2modes.cpp:42-60, 246-264, 273-327). */
+MeStatus me_fem_assemble(const double *points_xyz, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const MeMaterial *material,
+                         uint32_t element_order, int device, MeFemSystem **out);
+void me_fem_free(MeFemSystem *);
+MeStatus me_fem_info(const MeFemSystem *, MeFemInfo *out);
+MeStatus me_fem_get_element_nodes(MeFemSystem *, uint32_t *out /* [tets_kept][nodes_per_element] */);
+/* The lower-triangular CSC the reference's Eigen matrices hold: which = 0 stiffness, 1 mass. */
+MeStatus me_fem_get_csc(MeFemSystem *, int which, uint64_t *colptr /* [dofs+1] */, uint32_t *rowidx, double *values);
+/* First-fit element colouring in element order (defined by oracle/modal.py greedy_colouring). */
+MeStatus me_fem_colour_elements(MeFemSystem *, uint32_t *colours /* [tets_kept] */, uint32_t *n_colours);
+/* y = A x (which = 0: K, 1: M), host vectors; `repeats` products are timed on the device (ms per product). */
+MeStatus me_fem_spmv(MeFemSystem *, int which, const double *x, double *y, uint32_t repeats, float *ms_per_product);
+
+typedef struct MeFactor MeFactor;
+typedef struct MeFactorInfo {
+    double analyse_seconds, factor_flops;
+    float factor_device_ms, last_solve_device_ms;
+    uint64_t factor_nonzeros;
+    uint32_t supernodes, levels, dofs, kernel_launches;
+} MeFactorInfo;
+/* CholeskyShiftInvert::set_shift (CholeskyShiftInvert.cpp:26-46): analyse and factor K - sigma*M on the device. */
+MeStatus me_factor_create(MeFemSystem *, double sigma, MeFactor **out);
+void me_factor_free(MeFactor *);
+/* perform_op / solve_panel (CholeskyShiftInvert.cpp:48-62): x = (K - sigma M)^-1 b, `width` column-major right-hand sides (host). */
+MeStatus me_factor_solve(MeFactor *, const double *b, double *x, uint32_t width);
+MeStatus me_factor_info(MeFactor *, MeFactorInfo *out);
+
+/* FP64 issue-rate micro-benchmark (flop/s): mode 0 DFMA, 1 DMMA (mma.sync.m8n8k4.f64). */
+MeStatus me_measure_fp64_rate(int device, int mode, int iters, double *flops_per_second);
+
 /* FP32 FMA issue-rate micro-benchmark (the ceiling the resonator is bound by).
  * Returns FP32 lane-operations per second on `device`, measured with CUDA events over `iters` launches.
  * packed: 0 scalar FFMA; 1 Blackwell packed FFMA2 (fma.rn.f32x2); 2 / 3 FFMA2 and FFMA interleaved 1:1 / 1:2

@@ -36,6 +36,49 @@ class MeRenderStats(C.Structure):
     ]
 
 
+class MeMaterial(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("density", "young_modulus", "poisson_ratio", "alpha", "beta")]
+
+
+class MeSolverConfig(C.Structure):
+    _fields_ = [("min_mode_freq", C.c_float), ("max_mode_freq", C.c_float), ("num_modes", C.c_uint32), ("num_fem_modes", C.c_uint32), ("tolerance", C.c_double),
+                ("warm_tolerance", C.c_double), ("max_restarts", C.c_uint32), ("has_fundamental_freq", C.c_int32), ("fundamental_freq", C.c_float),
+                ("element_order", C.c_uint32), ("device", C.c_int32)]
+
+
+class MeJobMonitor(C.Structure):
+    _fields_ = [("progress", C.c_float), ("cancelled", C.c_int32)]
+
+
+class MeSolveProfile(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("mass_props", "quad_mesh", "assemble", "sample_excite", "factorize", "iterate", "op_solve", "extract")] + [
+        (n, C.c_uint32) for n in ("dofs", "stiffness_nonzeros", "op_applications", "restarts")] + [("analyse", C.c_double), ("factor_flops", C.c_double),
+        ("factor_nonzeros", C.c_uint64), ("assemble_kernel_ms", C.c_float), ("factor_device_ms", C.c_float)] + [
+        (n, C.c_uint32) for n in ("supernodes", "levels", "kernel_launches", "tets_kept")]
+
+
+class MeMassProperties(C.Structure):
+    _fields_ = [("mass", C.c_double), ("center_of_mass", C.c_float * 3), ("inertia_diagonal", C.c_float * 3), ("inertia_orientation", C.c_float * 4)]
+
+
+class MeFemInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("tets_kept", "node_count", "dofs", "nodes_per_element")] + [
+        (n, C.c_uint64) for n in ("nnz_stiffness", "nnz_mass", "node_blocks_lower", "node_blocks_full")] + [("assemble_kernel_ms", C.c_float), ("kernel_launches", C.c_uint32)]
+
+
+class MeFactorInfo(C.Structure):
+    _fields_ = [("analyse_seconds", C.c_double), ("factor_flops", C.c_double), ("factor_device_ms", C.c_float), ("last_solve_device_ms", C.c_float),
+                ("factor_nonzeros", C.c_uint64)] + [(n, C.c_uint32) for n in ("supernodes", "levels", "dofs", "kernel_launches")]
+
+
+def struct_dict(s):
+    out = {}
+    for name, _ in s._fields_:
+        v = getattr(s, name)
+        out[name] = list(v) if hasattr(v, "__len__") else v
+    return out
+
+
 _lib = None
 
 
@@ -69,13 +112,45 @@ def lib():
         "me_bank_get_object_status": [vp, u32, C.POINTER(u32), C.POINTER(u32)],
         "me_bank_last_render_stats": [vp, C.POINTER(MeRenderStats)],
         "me_measure_fp32_fma_rate": [i32, i32, i32, C.POINTER(C.c_double)],
+        "me_measure_fp64_rate": [i32, i32, i32, C.POINTER(C.c_double)],
+        "me_modal_solve": [vp, u32, vp, u32, C.POINTER(MeMaterial), vp, u32, vp, C.POINTER(MeSolverConfig), vp, u32, u32, i32, C.POINTER(MeJobMonitor), C.POINTER(vp)],
+        "me_modal_result_mass_properties": [vp, C.POINTER(MeMassProperties)],
+        "me_modal_result_profile": [vp, C.POINTER(MeSolveProfile)],
+        "me_postprocess_modes": [vp, u32, vp, u32, f32, C.POINTER(MeMaterial), C.POINTER(MeSolverConfig), vp, C.POINTER(vp)],
+        "me_rescale_modes": [vp, C.POINTER(MeMaterial), C.POINTER(MeMaterial), C.POINTER(MeSolverConfig), C.POINTER(vp)],
+        "me_fem_assemble": [vp, u32, vp, u32, C.POINTER(MeMaterial), u32, i32, C.POINTER(vp)],
+        "me_fem_info": [vp, C.POINTER(MeFemInfo)],
+        "me_fem_get_element_nodes": [vp, vp],
+        "me_fem_get_csc": [vp, i32, vp, vp, vp],
+        "me_fem_colour_elements": [vp, vp, C.POINTER(u32)],
+        "me_fem_spmv": [vp, i32, vp, vp, u32, C.POINTER(f32)],
+        "me_factor_create": [vp, C.c_double, C.POINTER(vp)],
+        "me_factor_solve": [vp, vp, vp, u32],
+        "me_factor_info": [vp, C.POINTER(MeFactorInfo)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = i32
-    L.me_bank_free.argtypes = [vp]
-    L.me_bank_free.restype = None
+    for name in ("me_bank_free", "me_modal_result_free", "me_fem_free", "me_factor_free"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = None
+    L.me_solver_config_default.argtypes = [C.POINTER(MeSolverConfig)]
+    L.me_solver_config_default.restype = None
+    for name in ("me_modal_result_mode_count", "me_modal_result_point_count", "me_modal_result_eigenpair_count"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = u32
+    for name in ("me_modal_result_freqs", "me_modal_result_t60s", "me_modal_result_shapes", "me_modal_result_positions", "me_modal_result_summary_shapes"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = C.POINTER(f32)
+    L.me_modal_result_eigenvalues.argtypes = [vp]
+    L.me_modal_result_eigenvalues.restype = C.POINTER(C.c_double)
+    L.me_modal_result_original_fundamental.argtypes = [vp]
+    L.me_modal_result_original_fundamental.restype = f32
+    L.me_modal_result_sample_point_of_excitation.argtypes = [vp, C.POINTER(u32)]
+    L.me_modal_result_sample_point_of_excitation.restype = C.POINTER(u32)
+    L.me_modal_result_basis.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    L.me_modal_result_basis.restype = C.POINTER(f32)
     for name in ("me_bank_object_count", "me_bank_mode_total", "me_bank_active_impacts"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = u32

@@ -1,0 +1,507 @@
+// sm_100a kernels of the supernodal sparse Cholesky and its triangular solves. See cholesky.h / symbolic.h.
+//
+// Storage: every supernode S (k columns, m below-diagonal rows, both multiples of 3) owns a dense column-major panel
+// of (k + m) x k doubles in HBM: the k x k diagonal block on top, the m x k rectangle below. The factorisation is
+// right-looking and level-scheduled on the supernodal tree (levels = height above the leaves):
+//   level l:  FactorDiagKernel   one CTA per supernode: Cholesky of the diagonal block in shared memory, fused with the
+//                                inverse of the triangular factor (kept for the panel solve and the triangular solves);
+//             PanelTrsmKernel    one CTA per 64-row tile: panel <- panel * Linv^T, a GEMM on the FP64 tensor cores;
+//             SyrkScatterKernel  one CTA per 64x64 tile of the trailing update panel * panel^T (FP64 DMMA, accumulators
+//                                in registers), subtracted straight into the ancestors' panels with FP64 atomics:
+//                                no frontal/update matrices are ever materialised in HBM.
+// The dense contractions are genuine GEMMs, so they run on the tensor cores: mma.sync.m8n8k4.f64 (DMMA) is the only
+// FP64 tensor instruction sm_100a has (tcgen05.mma has no f64 kind; the m16n8k* f64 shapes lower to the same DMMA.8x8x4).
+#include "cholesky.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+
+namespace me {
+namespace {
+
+struct FactorView {
+    const uint32_t *SuperFirst, *Rows, *NodeSuper;
+    const uint64_t *RowPtr, *PanelOffset, *InvOffset;
+    const uint32_t *SegTarget, *SegBegin, *SegEnd;
+    double *L, *Linv;
+    int *Fail;
+};
+
+__device__ __forceinline__ uint32_t PanelColumns(const FactorView &v, uint32_t s) { return 3 * (v.SuperFirst[s + 1] - v.SuperFirst[s]); }
+__device__ __forceinline__ uint32_t PanelRows(const FactorView &v, uint32_t s) { return 3 * uint32_t(v.RowPtr[s + 1] - v.RowPtr[s]); }
+
+// Position of `node` in the below-diagonal node list of supernode s, or 0xFFFFFFFF.
+__device__ __forceinline__ uint32_t FindRow(const FactorView &v, uint32_t s, uint32_t node) {
+    const uint32_t *rows = v.Rows + v.RowPtr[s];
+    uint32_t lo = 0, hi = uint32_t(v.RowPtr[s + 1] - v.RowPtr[s]);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (rows[mid] < node) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < uint32_t(v.RowPtr[s + 1] - v.RowPtr[s]) && rows[lo] == node) ? lo : 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ void Dmma(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// A = K - sigma*M scattered into the (zeroed) panels under the fill-reducing permutation. One thread per stored block.
+__global__ void ScatterMatrixKernel(FactorView v, const uint32_t *__restrict__ blk_row, const uint32_t *__restrict__ blk_col, const double *__restrict__ kblk,
+                                    const double *__restrict__ mblk, const uint32_t *__restrict__ inv_perm, uint32_t n_blocks, double sigma) {
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_blocks) return;
+    const uint32_t pr = inv_perm[blk_row[u]], pc = inv_perm[blk_col[u]];
+    const bool tr = pr < pc;
+    const uint32_t R = tr ? pc : pr, C = tr ? pr : pc;
+    const uint32_t s = v.NodeSuper[C], k = PanelColumns(v, s), ld = k + PanelRows(v, s);
+    const uint32_t lc = 3 * (C - v.SuperFirst[s]);
+    uint32_t lr;
+    if (R < v.SuperFirst[s + 1]) lr = 3 * (R - v.SuperFirst[s]);
+    else {
+        const uint32_t pos = FindRow(v, s, R);
+        if (pos == 0xFFFFFFFFu) {
+            atomicExch(v.Fail, 2);
+            return;
+        }
+        lr = k + 3 * pos;
+    }
+    double *panel = v.L + v.PanelOffset[s];
+    const double shift = sigma * mblk[u];
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double a = kblk[size_t(9) * u + 3 * p + q] - (p == q ? shift : 0.0);
+            panel[(lr + (tr ? q : p)) + size_t(lc + (tr ? p : q)) * ld] = a;
+        }
+}
+
+// Cholesky of one diagonal block (k <= 128) in shared memory, fused with the inverse of its factor.
+// 512 threads: four per matrix row. The lower triangle of the k x LDS array holds A (then L); the strict upper
+// triangle holds E^T, where E (unit lower) accumulates the same row operations applied to the identity, so that
+// L^-1 = diag(L)^-1 E.
+constexpr int kFactorThreads = 512;
+__global__ void __launch_bounds__(kFactorThreads) FactorDiagKernel(FactorView v, const uint32_t *__restrict__ level_supers) {
+    extern __shared__ double sm[];
+    const uint32_t s = level_supers[blockIdx.x];
+    const uint32_t k = PanelColumns(v, s), ld = k + PanelRows(v, s), lds = k | 1;
+    double *panel = v.L + v.PanelOffset[s];
+    const uint32_t t = threadIdx.x, i = t & 127, h = t >> 7;
+    for (uint32_t idx = t; idx < k * k; idx += kFactorThreads) {
+        const uint32_t r = idx % k, c = idx / k;
+        sm[r + c * lds] = r >= c ? panel[r + size_t(c) * ld] : 0.0;
+    }
+    double pending = 0;
+    bool bad = false;
+    for (uint32_t j = 0; j < k; ++j) {
+        __syncthreads();
+        if (h == 0 && j > 0 && i >= j - 1 && i < k) sm[i + (j - 1) * lds] = pending;
+        double d = sm[j + j * lds];
+        if (!(d > 0.0) || !isfinite(d)) {
+            bad = true;
+            d = 1.0;
+        }
+        const double sq = sqrt(d), inv = 1.0 / sq;
+        if (i == j) pending = sq;
+        if (i > j && i < k) {
+            const double l = sm[i + j * lds] * inv, f = l * inv;
+            for (uint32_t c = j + 1 + h; c <= i; c += 4) sm[i + c * lds] -= l * (sm[c + j * lds] * inv);
+            for (uint32_t c = h; c < j; c += 4) sm[c + i * lds] -= f * sm[c + j * lds];
+            if (h == (j & 3)) sm[j + i * lds] = -f;
+            pending = l;
+        }
+    }
+    __syncthreads();
+    if (h == 0 && i >= k - 1 && i < k) sm[i + (k - 1) * lds] = pending;
+    __syncthreads();
+    if (bad && t == 0) atomicExch(v.Fail, 1);
+    double *linv = v.Linv + v.InvOffset[s];
+    for (uint32_t idx = t; idx < k * k; idx += kFactorThreads) {
+        const uint32_t r = idx % k, c = idx / k;
+        if (r >= c) panel[r + size_t(c) * ld] = sm[r + c * lds];
+        const double dr = sm[r + r * lds];
+        linv[r + size_t(c) * k] = r == c ? 1.0 / dr : (r > c ? sm[c + r * lds] / dr : 0.0);
+    }
+}
+
+// Tile geometry of the DMMA kernels: operands are staged in shared memory K-major, [kk][row] with a row stride of
+// 4 (mod 16) doubles, which makes the m8n8k4 fragment loads (lane -> row lane/4, k lane%4) bank-conflict free.
+constexpr int kChunk = 16;          // K columns staged per step
+constexpr int kLdA = 64 + 4;        // 64-row operand tiles
+constexpr int kLdB128 = 128 + 4;    // 128-row operand tile (the inverse factor in the panel solve)
+
+// panel <- panel * Linv^T for one 64-row tile of the below-diagonal rectangle (TRSM as GEMM, C[64 x k]).
+constexpr int kTrsmThreads = 256;
+__global__ void __launch_bounds__(kTrsmThreads) PanelTrsmKernel(FactorView v, const PanelTile *__restrict__ tiles) {
+    extern __shared__ double sm[];
+    double *As = sm;                 // [128][kLdA]: the whole 64 x k tile, K-major
+    double *Bs = sm + 128 * kLdA;    // [kChunk][kLdB128]
+    const PanelTile tile = tiles[blockIdx.x];
+    const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
+    double *p0 = v.L + v.PanelOffset[s] + k;
+    const double *linv = v.Linv + v.InvOffset[s];
+    const uint32_t row0 = tile.RowTile * kTile, nrows = min(kTile, m - row0);
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, wm = w & 1, wn = w >> 1;
+    for (uint32_t idx = t; idx < 128 * 64; idx += kTrsmThreads) {
+        const uint32_t r = idx & 63, c = idx >> 6;
+        As[c * kLdA + r] = (r < nrows && c < k) ? p0[row0 + r + size_t(c) * ld] : 0.0;
+    }
+    double acc[4][4][2]{};
+    for (uint32_t kc = 0; kc < k; kc += kChunk) {
+        __syncthreads();
+        for (uint32_t idx = t; idx < kChunk * 128; idx += kTrsmThreads) {
+            const uint32_t j = idx & 127, c = idx >> 7;
+            Bs[c * kLdB128 + j] = (j < k && kc + c < k) ? linv[j + size_t(kc + c) * k] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < kChunk / 4; ++ks) {
+            double a[4], b[4];
+            const uint32_t kk = 4 * ks + (lane & 3);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[(kc + kk) * kLdA + 32 * wm + 8 * mi + (lane >> 2)];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[kk * kLdB128 + 32 * wn + 8 * ni + (lane >> 2)];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) Dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t r = 32 * wm + 8 * mi + (lane >> 2), c = 32 * wn + 8 * ni + 2 * (lane & 3) + e;
+                if (r < nrows && c < k) p0[row0 + r + size_t(c) * ld] = acc[mi][ni][e];
+            }
+}
+
+// One 64 x 64 tile of the trailing update of supernode S restricted to one target segment:
+//   U = P[rowsA, :] * P[rowsB, :]^T   (rowsB are rows of S that are columns of the ancestor T)
+// subtracted into T's panel at the rows/columns the global indices select.
+constexpr int kSyrkThreads = 128;
+__global__ void __launch_bounds__(kSyrkThreads) SyrkScatterKernel(FactorView v, const UpdateTile *__restrict__ tiles) {
+    __shared__ double As[kChunk * kLdA], Bs[kChunk * kLdA];
+    __shared__ uint32_t row_dest[kTile], col_dest[kTile];
+    const UpdateTile tile = tiles[blockIdx.x];
+    const uint32_t s = tile.Super, g = tile.Segment;
+    const uint32_t k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
+    const double *p0 = v.L + v.PanelOffset[s] + k;
+    const uint32_t c0 = 3 * v.SegBegin[g], c1 = 3 * v.SegEnd[g];
+    const uint32_t row_a = c0 + tile.RowTile * kTile, row_b = c0 + tile.ColTile * kTile;
+    const uint32_t na = min(kTile, m - row_a), nb = min(kTile, c1 - row_b);
+    const uint32_t target = v.SegTarget[g], kt = PanelColumns(v, target), ldt = kt + PanelRows(v, target);
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, wm = w & 1, wn = w >> 1;
+    {
+        const uint32_t *rows = v.Rows + v.RowPtr[s];
+        if (t < kTile) {
+            if (t < na) {
+                const uint32_t br = row_a + t, node = rows[br / 3], comp = br % 3;
+                uint32_t lr;
+                if (node < v.SuperFirst[target + 1]) lr = 3 * (node - v.SuperFirst[target]) + comp;
+                else {
+                    const uint32_t pos = FindRow(v, target, node);
+                    if (pos == 0xFFFFFFFFu) atomicExch(v.Fail, 3);
+                    lr = pos == 0xFFFFFFFFu ? 0 : kt + 3 * pos + comp;
+                }
+                row_dest[t] = lr;
+            }
+        } else {
+            const uint32_t j = t - kTile;
+            if (j < nb) {
+                const uint32_t bc = row_b + j, node = rows[bc / 3], comp = bc % 3;
+                col_dest[j] = (3 * (node - v.SuperFirst[target]) + comp) * ldt;
+            }
+        }
+    }
+    double acc[4][4][2]{};
+    for (uint32_t kc = 0; kc < k; kc += kChunk) {
+        __syncthreads();
+        for (uint32_t idx = t; idx < kChunk * kTile; idx += kSyrkThreads) {
+            const uint32_t r = idx & 63, c = idx >> 6;
+            const bool kin = kc + c < k;
+            As[c * kLdA + r] = (kin && r < na) ? p0[row_a + r + size_t(kc + c) * ld] : 0.0;
+            Bs[c * kLdA + r] = (kin && r < nb) ? p0[row_b + r + size_t(kc + c) * ld] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < kChunk / 4; ++ks) {
+            double a[4], b[4];
+            const uint32_t kk = 4 * ks + (lane & 3);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[kk * kLdA + 32 * wm + 8 * mi + (lane >> 2)];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[kk * kLdA + 32 * wn + 8 * ni + (lane >> 2)];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) Dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+    double *lt = v.L + v.PanelOffset[target];
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const uint32_t r = 32 * wm + 8 * mi + (lane >> 2), c = 32 * wn + 8 * ni + 2 * (lane & 3) + e;
+                if (r < na && c < nb && row_a + r >= row_b + c) atomicAdd(lt + row_dest[r] + size_t(col_dest[c]), -acc[mi][ni][e]);
+            }
+}
+
+// ------------------------------------------------------------------------------------------------ triangular solves
+__global__ void PermuteInKernel(const double *__restrict__ b, const uint32_t *__restrict__ inv_perm, uint32_t n_nodes, double *__restrict__ w) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n_nodes) w[3 * inv_perm[i / 3] + i % 3] = b[i];
+}
+__global__ void PermuteOutKernel(const double *__restrict__ w, const uint32_t *__restrict__ inv_perm, uint32_t n_nodes, double *__restrict__ x) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n_nodes) x[i] = w[3 * inv_perm[i / 3] + i % 3];
+}
+
+// w_S <- Linv_S w_S (forward) or Linv_S^T w_S (backward) for every supernode of one level. 128 threads per supernode.
+template<bool Transposed>
+__global__ void __launch_bounds__(128) DiagSolveKernel(FactorView v, const uint32_t *__restrict__ level_supers, double *__restrict__ w) {
+    __shared__ double vs[128];
+    const uint32_t s = level_supers[blockIdx.x], k = PanelColumns(v, s);
+    double *ws = w + size_t(3) * v.SuperFirst[s];
+    const double *linv = v.Linv + v.InvOffset[s];
+    const uint32_t t = threadIdx.x;
+    if (t < k) vs[t] = ws[t];
+    __syncthreads();
+    if constexpr (!Transposed) {
+        if (t < k) {
+            double sum = 0;
+            for (uint32_t c = 0; c <= t; ++c) sum += linv[t + size_t(c) * k] * vs[c];
+            ws[t] = sum;
+        }
+    } else {
+        const uint32_t lane = t & 31, warp = t >> 5;
+        for (uint32_t i = warp; i < k; i += 4) {
+            double sum = 0;
+            for (uint32_t c = i + lane; c < k; c += 32) sum += linv[c + size_t(i) * k] * vs[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) ws[i] = sum;
+        }
+    }
+}
+// Forward: w[rows of the tile] -= P_tile * y_S. One thread per row, 64 rows per CTA.
+__global__ void __launch_bounds__(64) PanelForwardKernel(FactorView v, const PanelTile *__restrict__ tiles, double *__restrict__ w) {
+    __shared__ double ys[128];
+    const PanelTile tile = tiles[blockIdx.x];
+    const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
+    const double *p0 = v.L + v.PanelOffset[s] + k;
+    const uint32_t t = threadIdx.x;
+    for (uint32_t c = t; c < k; c += 64) ys[c] = w[size_t(3) * v.SuperFirst[s] + c];
+    __syncthreads();
+    const uint32_t r = tile.RowTile * kTile + t;
+    if (r >= m) return;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    uint32_t c = 0;
+    for (; c + 4 <= k; c += 4) {
+        s0 += p0[r + size_t(c) * ld] * ys[c];
+        s1 += p0[r + size_t(c + 1) * ld] * ys[c + 1];
+        s2 += p0[r + size_t(c + 2) * ld] * ys[c + 2];
+        s3 += p0[r + size_t(c + 3) * ld] * ys[c + 3];
+    }
+    for (; c < k; ++c) s0 += p0[r + size_t(c) * ld] * ys[c];
+    const uint32_t node = v.Rows[v.RowPtr[s] + r / 3];
+    atomicAdd(w + size_t(3) * node + r % 3, -((s0 + s1) + (s2 + s3)));
+}
+// Backward: w_S -= P_tile^T x[rows of the tile]. Four warps stride over the panel's columns.
+__global__ void __launch_bounds__(128) PanelBackwardKernel(FactorView v, const PanelTile *__restrict__ tiles, double *__restrict__ w) {
+    __shared__ double xs[kTile];
+    const PanelTile tile = tiles[blockIdx.x];
+    const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
+    const double *p0 = v.L + v.PanelOffset[s] + k;
+    const uint32_t t = threadIdx.x, row0 = tile.RowTile * kTile, nrows = min(kTile, m - row0);
+    if (t < kTile) {
+        const uint32_t r = row0 + t;
+        xs[t] = t < nrows ? w[size_t(3) * v.Rows[v.RowPtr[s] + r / 3] + r % 3] : 0.0;
+    }
+    __syncthreads();
+    const uint32_t lane = t & 31, warp = t >> 5;
+    double *ws = w + size_t(3) * v.SuperFirst[s];
+    for (uint32_t c = warp; c < k; c += 4) {
+        const double *col = p0 + row0 + size_t(c) * ld;
+        double sum = (lane < nrows ? col[lane] * xs[lane] : 0.0) + (lane + 32 < nrows ? col[lane + 32] * xs[lane + 32] : 0.0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) atomicAdd(ws + c, -sum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ FP64 rate probes
+template<int Mode>
+__global__ void Fp64RateKernel(double *out, int iters) {
+    double a = 1.0 + threadIdx.x * 1e-9, b = 0.999999, c[8][2]{};
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if constexpr (Mode == 0) {
+                c[u][0] = fma(a, b, c[u][0]);
+                c[u][1] = fma(b, a, c[u][1]);
+            } else {
+                Dmma(c[u][0], c[u][1], a, b);
+            }
+        }
+    }
+    double sum = 0;
+    for (int u = 0; u < 8; ++u) sum += c[u][0] + c[u][1];
+    if (sum == 123.456) out[0] = sum;
+}
+
+double Seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+inline uint32_t Blocks(uint64_t n, int threads) { return uint32_t((n + threads - 1) / threads); }
+} // namespace
+
+double MeasureFp64Rate(int mode, int iters) {
+    double *out = nullptr;
+    ME_CUDA(cudaMalloc(&out, 8));
+    cudaEvent_t e0, e1;
+    ME_CUDA(cudaEventCreate(&e0));
+    ME_CUDA(cudaEventCreate(&e1));
+    const int grid = 148 * 8, threads = 256, inner = 4096;
+    auto launch = [&] {
+        if (mode == 0) Fp64RateKernel<0><<<grid, threads>>>(out, inner);
+        else Fp64RateKernel<1><<<grid, threads>>>(out, inner);
+    };
+    launch();
+    ME_CUDA(cudaEventRecord(e0));
+    for (int i = 0; i < iters; ++i) launch();
+    ME_CUDA(cudaEventRecord(e1));
+    ME_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    ME_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    // Per thread per inner iteration: mode 0 = 16 DFMA = 32 flop; mode 1 = 8 DMMA per warp = 8 * 512 flop per 32 threads = 128 flop per thread.
+    const double flop_per_thread = double(inner) * (mode == 0 ? 32.0 : 128.0);
+    return flop_per_thread * grid * threads * iters / (ms * 1e-3);
+}
+
+SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem(fem) {
+    const double t0 = Seconds();
+    ME_CUDA(cudaSetDevice(fem.Device));
+    std::vector<uint32_t> rowptr, col;
+    std::vector<float> xyz;
+    fem.CopyFullPattern(rowptr, col);
+    fem.CopyNodeCoords(xyz);
+    Sym = Analyse(fem.NodeCount, rowptr.data(), col.data(), xyz.data(), opt);
+    if (Sym.MaxPanelColumns > 128) Fail(ME_BAD_ARG, "internal: panel of %u columns", Sym.MaxPanelColumns);
+    auto s = fem.Stream;
+    DSuperFirst.Upload(Sym.SuperFirst, s);
+    DRows.Upload(Sym.Rows, s);
+    DNodeSuper.Upload(Sym.NodeSuper, s);
+    DInvPerm.Upload(Sym.InvPerm, s);
+    DPerm.Upload(Sym.Perm, s);
+    DSegTarget.Upload(Sym.SegTarget, s);
+    DSegBegin.Upload(Sym.SegBegin, s);
+    DSegEnd.Upload(Sym.SegEnd, s);
+    DLevelOrder.Upload(Sym.LevelOrder, s);
+    DRowPtr.Upload(Sym.RowPtr, s);
+    DPanelOffset.Upload(Sym.PanelOffset, s);
+    DInvOffset.Upload(Sym.InvOffset, s);
+    DPanelTiles.Upload(Sym.PanelTiles, s);
+    DUpdateTiles.Upload(Sym.UpdateTiles, s);
+    L.Reserve(Sym.FactorNonZeros);
+    Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
+    Work.Reserve(fem.N);
+    DFail.Reserve(1);
+    for (auto &e : Ev) ME_CUDA(cudaEventCreate(&e));
+    ME_CUDA(cudaFuncSetAttribute(FactorDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
+    ME_CUDA(cudaFuncSetAttribute(PanelTrsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * kLdA + kChunk * kLdB128) * 8));
+    ME_CUDA(cudaStreamSynchronize(s));
+    Stats.AnalyseSeconds = Seconds() - t0;
+    Stats.FactorNonZeros = Sym.FactorNonZeros;
+    Stats.FactorFlops = Sym.FactorFlops;
+    Stats.Supernodes = Sym.NumSuper;
+    Stats.Levels = Sym.NumLevels;
+}
+
+SparseCholesky::~SparseCholesky() {
+    cudaSetDevice(Fem.Device);
+    for (auto &e : Ev)
+        if (e) cudaEventDestroy(e);
+}
+
+void SparseCholesky::Factorize(double sigma) {
+    ME_CUDA(cudaSetDevice(Fem.Device));
+    auto s = Fem.Stream;
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, DFail.Ptr};
+    ME_CUDA(cudaEventRecord(Ev[0], s));
+    ME_CUDA(cudaMemsetAsync(DFail.Ptr, 0, sizeof(int), s));
+    ME_CUDA(cudaMemsetAsync(L.Ptr, 0, Sym.FactorNonZeros * sizeof(double), s));
+    ScatterMatrixKernel<<<Blocks(Fem.NumBlocks, 256), 256, 0, s>>>(v, Fem.BlkRow.Ptr, Fem.BlkCol.Ptr, Fem.KBlk.Ptr, Fem.MBlk.Ptr, DInvPerm.Ptr, Fem.NumBlocks, sigma);
+    uint32_t launches = 1;
+    const uint32_t kmax = Sym.MaxPanelColumns;
+    const size_t diag_smem = size_t(kmax) * (kmax | 1) * 8;
+    const size_t trsm_smem = (128 * kLdA + kChunk * kLdB128) * 8;
+    for (uint32_t l = 0; l < Sym.NumLevels; ++l) {
+        const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
+        FactorDiagKernel<<<n_super, kFactorThreads, diag_smem, s>>>(v, DLevelOrder.Ptr + Sym.LevelPtr[l]);
+        ++launches;
+        const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
+        if (n_panel) {
+            PanelTrsmKernel<<<uint32_t(n_panel), kTrsmThreads, trsm_smem, s>>>(v, DPanelTiles.Ptr + Sym.PanelTilePtr[l]);
+            ++launches;
+        }
+        const uint64_t n_update = Sym.UpdateTilePtr[l + 1] - Sym.UpdateTilePtr[l];
+        if (n_update) {
+            SyrkScatterKernel<<<uint32_t(n_update), kSyrkThreads, 0, s>>>(v, DUpdateTiles.Ptr + Sym.UpdateTilePtr[l]);
+            ++launches;
+        }
+    }
+    ME_CUDA(cudaEventRecord(Ev[1], s));
+    int fail = 0;
+    ME_CUDA(cudaMemcpyAsync(&fail, DFail.Ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
+    ME_CUDA(cudaStreamSynchronize(s));
+    ME_CUDA(cudaGetLastError());
+    ME_CUDA(cudaEventElapsedTime(&Stats.FactorMs, Ev[0], Ev[1]));
+    Stats.KernelLaunches += launches;
+    if (fail == 1) Fail(ME_FACTOR_FAILED, "Cholesky factorization of K - sigma*M failed: non-positive pivot (sigma = %g)", sigma);
+    if (fail) Fail(ME_CUDA_ERROR, "internal: symbolic structure does not cover the matrix (code %d)", fail);
+    Factored = true;
+}
+
+void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
+    if (!Factored) Fail(ME_BAD_ARG, "Solve before Factorize");
+    ME_CUDA(cudaSetDevice(Fem.Device));
+    auto s = Fem.Stream;
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, DFail.Ptr};
+    const uint32_t n = Fem.N;
+    uint32_t launches = 0;
+    ME_CUDA(cudaEventRecord(Ev[2], s));
+    for (uint32_t rhs = 0; rhs < width; ++rhs) {
+        double *w = Work.Ptr;
+        PermuteInKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, w);
+        for (uint32_t l = 0; l < Sym.NumLevels; ++l) {
+            const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
+            DiagSolveKernel<false><<<n_super, 128, 0, s>>>(v, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
+            const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
+            if (n_panel) PanelForwardKernel<<<uint32_t(n_panel), 64, 0, s>>>(v, DPanelTiles.Ptr + Sym.PanelTilePtr[l], w);
+            launches += 1 + (n_panel != 0);
+        }
+        for (uint32_t l = Sym.NumLevels; l-- > 0;) {
+            const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
+            const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
+            if (n_panel) PanelBackwardKernel<<<uint32_t(n_panel), 128, 0, s>>>(v, DPanelTiles.Ptr + Sym.PanelTilePtr[l], w);
+            DiagSolveKernel<true><<<n_super, 128, 0, s>>>(v, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
+            launches += 1 + (n_panel != 0);
+        }
+        PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(w, DInvPerm.Ptr, Fem.NodeCount, x + size_t(rhs) * n);
+        launches += 2;
+    }
+    ME_CUDA(cudaEventRecord(Ev[3], s));
+    Stats.KernelLaunches += launches;
+}
+
+} // namespace me

@@ -1,0 +1,45 @@
+// Shift-invert Lanczos for the lowest eigenpairs of K x = lambda M x, basis and all vector work on the device.
+// Replaces Spectra::SymGEigsShiftSolver<CholeskyShiftInvert, SparseSymMatProd, ShiftInvert> as configured by the
+// reference (src/audio/mesh2modes.cpp:485-487; lib/spectra/include/Spectra/HermEigsBase.h:105-390, LinAlg/Lanczos.h:62-187).
+#pragma once
+
+#include "cholesky.h"
+#include "dense.h"
+#include "fem.h"
+
+#include <atomic>
+#include <vector>
+
+namespace me {
+
+struct LanczosOutcome {
+    std::vector<double> Eigenvalues; // ascending, nev of them when converged
+    uint32_t OpApplications{0}, Restarts{0};
+    bool Converged{false}, Cancelled{false};
+    double OpSolveMs{0};             // device time inside the shift-invert operator (M x + two triangular solves)
+    uint32_t KernelLaunches{0};
+};
+
+// Dense symmetric eigen-decomposition on the host (Householder tridiagonalisation + implicit QL), for the projected
+// matrix H (at most ncv x ncv). a: row-major n x n, overwritten with the eigenvectors (columns); d: eigenvalues, unsorted.
+bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d);
+
+class ShiftInvertLanczos {
+public:
+    ShiftInvertLanczos(FemSystem &fem, SparseCholesky &factor, double sigma) : Fem(fem), Factor(factor), Sigma(sigma) {}
+    // On success Vectors holds the n x nev M-orthonormal eigenvectors (column-major, device).
+    LanczosOutcome Compute(uint32_t nev, uint32_t ncv, double tol, uint32_t max_restarts, const volatile int *cancelled);
+    DeviceBuffer<double> Vectors;
+
+private:
+    void Op(const double *x, double *y); // y = (K - sigma M)^-1 M x
+    FemSystem &Fem;
+    SparseCholesky &Factor;
+    double Sigma;
+    DenseWorkspace Ws;
+    DeviceBuffer<double> Tmp;
+    std::vector<cudaEvent_t> OpEvents;
+    uint32_t Ops{0};
+};
+
+} // namespace me

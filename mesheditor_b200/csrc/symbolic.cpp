@@ -1,0 +1,251 @@
+// Geometric nested dissection + supernodal symbolic factorisation (host). See symbolic.h.
+//
+// Ordering: recursive coordinate bisection of the node graph. A subdomain is cut by the plane through its median
+// coordinate along its longest axis; the side of the cut that touches the other side through fewer nodes gives the
+// vertex separator. Tet meshes carry their embedding, and a planar cut of a 3-D mesh is within a small factor of the
+// best separator, so no graph partitioner is needed (none exists in this image anyway).
+// Supernodes are read straight off the dissection tree: each leaf subdomain is one supernode, each separator is a
+// chain of panels of at most PanelNodes nodes. Their diagonal blocks are treated as dense (a separator is a clique
+// once both sides are eliminated), the below-diagonal structure is the union of the graph adjacency and of the
+// children's structures (a superset of the true fill; the few explicit zeros buy dense kernels).
+#include "symbolic.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <numeric>
+
+namespace me {
+namespace {
+double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct Dissector {
+    uint32_t N;
+    const uint32_t *RowPtr, *Col;
+    const float *Xyz;
+    SymbolicOptions Opt;
+    std::vector<uint32_t> Dom;  // current subdomain stamp of each node
+    uint32_t NextStamp{1};
+    // Output, in elimination order.
+    std::vector<uint32_t> Perm;       // new -> old
+    std::vector<uint32_t> SuperFirst; // first new index of each supernode
+    std::vector<uint32_t> Parent;
+    std::vector<uint32_t> Chain;      // panels of one separator (or one leaf) share a chain id
+    uint32_t NextChain{0};
+
+    // Emits `nodes` as a chain of panels; `children` are the tops of the subtrees below. Returns the chain's top.
+    uint32_t EmitChain(const std::vector<uint32_t> &nodes, uint32_t panel, const std::vector<uint32_t> &children) {
+        uint32_t first_panel = uint32_t(SuperFirst.size());
+        for (size_t at = 0; at < nodes.size(); at += panel) {
+            const size_t end = std::min(nodes.size(), at + panel);
+            const uint32_t id = uint32_t(SuperFirst.size());
+            SuperFirst.push_back(uint32_t(Perm.size()));
+            Parent.push_back(UINT32_MAX);
+            Chain.push_back(NextChain);
+            if (id > first_panel) Parent[id - 1] = id;
+            Perm.insert(Perm.end(), nodes.begin() + at, nodes.begin() + end);
+        }
+        ++NextChain;
+        for (uint32_t c : children) Parent[c] = first_panel;
+        return uint32_t(SuperFirst.size()) - 1;
+    }
+
+    // Orders the subdomain `nodes`; appends the tops of the emitted subtrees to `tops`.
+    void Dissect(std::vector<uint32_t> &nodes, std::vector<uint32_t> &tops) {
+        if (nodes.empty()) return;
+        if (nodes.size() <= Opt.LeafNodes) {
+            tops.push_back(EmitChain(nodes, std::max(Opt.LeafNodes, Opt.PanelNodes), {}));
+            return;
+        }
+        float lo[3]{1e30f, 1e30f, 1e30f}, hi[3]{-1e30f, -1e30f, -1e30f};
+        for (uint32_t v : nodes)
+            for (int a = 0; a < 3; ++a) {
+                lo[a] = std::min(lo[a], Xyz[3 * v + a]);
+                hi[a] = std::max(hi[a], Xyz[3 * v + a]);
+            }
+        int axis = 0;
+        for (int a = 1; a < 3; ++a)
+            if (hi[a] - lo[a] > hi[axis] - lo[axis]) axis = a;
+        // Median coordinate, then split by VALUE so that a grid plane stays on one side.
+        std::vector<float> coord(nodes.size());
+        for (size_t i = 0; i < nodes.size(); ++i) coord[i] = Xyz[3 * nodes[i] + axis];
+        std::vector<float> sorted = coord;
+        std::nth_element(sorted.begin(), sorted.begin() + sorted.size() / 2, sorted.end());
+        const float t = sorted[sorted.size() / 2];
+        std::vector<uint32_t> left, right;
+        for (size_t i = 0; i < nodes.size(); ++i) (coord[i] < t ? left : right).push_back(nodes[i]);
+        if (left.empty() || right.empty()) {
+            left.clear(), right.clear();
+            for (size_t i = 0; i < nodes.size(); ++i) (coord[i] <= t ? left : right).push_back(nodes[i]);
+        }
+        if (left.empty() || right.empty()) { // every node on one plane along the longest axis: split by position in the list
+            left.assign(nodes.begin(), nodes.begin() + nodes.size() / 2);
+            right.assign(nodes.begin() + nodes.size() / 2, nodes.end());
+        }
+        const uint32_t stamp_l = NextStamp++, stamp_r = NextStamp++;
+        for (uint32_t v : left) Dom[v] = stamp_l;
+        for (uint32_t v : right) Dom[v] = stamp_r;
+        auto boundary = [&](const std::vector<uint32_t> &side, uint32_t other) {
+            std::vector<uint32_t> out;
+            for (uint32_t v : side)
+                for (uint32_t j = RowPtr[v]; j < RowPtr[v + 1]; ++j)
+                    if (Dom[Col[j]] == other) {
+                        out.push_back(v);
+                        break;
+                    }
+            return out;
+        };
+        std::vector<uint32_t> sep_l = boundary(left, stamp_r), sep_r = boundary(right, stamp_l);
+        const bool take_left = sep_l.size() < sep_r.size();
+        std::vector<uint32_t> &sep = take_left ? sep_l : sep_r;
+        std::vector<uint32_t> &cut_side = take_left ? left : right;
+        const uint32_t stamp_s = NextStamp++;
+        for (uint32_t v : sep) Dom[v] = stamp_s;
+        std::vector<uint32_t> rest;
+        rest.reserve(cut_side.size() - sep.size());
+        for (uint32_t v : cut_side)
+            if (Dom[v] != stamp_s) rest.push_back(v);
+        cut_side.swap(rest);
+        nodes.clear();
+        nodes.shrink_to_fit();
+        std::vector<uint32_t> children;
+        Dissect(left, children);
+        Dissect(right, children);
+        if (sep.empty()) {
+            tops.insert(tops.end(), children.begin(), children.end());
+            return;
+        }
+        tops.push_back(EmitChain(sep, Opt.PanelNodes, children));
+    }
+};
+} // namespace
+
+Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const float *xyz, const SymbolicOptions &opt) {
+    Symbolic sym;
+    sym.NodeCount = n;
+    const double t0 = Now();
+    Dissector d{n, rowptr, col, xyz, opt};
+    d.Dom.assign(n, 0);
+    d.Perm.reserve(n);
+    {
+        std::vector<uint32_t> all(n), tops;
+        std::iota(all.begin(), all.end(), 0u);
+        d.Dissect(all, tops);
+    }
+    sym.Perm = std::move(d.Perm);
+    sym.InvPerm.assign(n, 0);
+    for (uint32_t i = 0; i < n; ++i) sym.InvPerm[sym.Perm[i]] = i;
+    const uint32_t ns = uint32_t(d.SuperFirst.size());
+    sym.NumSuper = ns;
+    sym.SuperFirst = std::move(d.SuperFirst);
+    sym.SuperFirst.push_back(n);
+    sym.Parent = std::move(d.Parent);
+    const std::vector<uint32_t> chain = std::move(d.Chain);
+    for (auto &p : sym.Parent)
+        if (p == UINT32_MAX) p = ns;
+    sym.NodeSuper.assign(n, 0);
+    for (uint32_t s = 0; s < ns; ++s)
+        for (uint32_t v = sym.SuperFirst[s]; v < sym.SuperFirst[s + 1]; ++v) sym.NodeSuper[v] = s;
+    const double t1 = Now();
+    sym.OrderingSeconds = t1 - t0;
+
+    // Structures, children before parents (supernode ids are in elimination order, so ascending works).
+    std::vector<std::vector<uint32_t>> children(ns);
+    for (uint32_t s = 0; s < ns; ++s)
+        if (sym.Parent[s] < ns) children[sym.Parent[s]].push_back(s);
+    std::vector<uint32_t> mark(n, UINT32_MAX);
+    sym.RowPtr.assign(size_t(ns) + 1, 0);
+    {
+        for (uint32_t s = 0; s < ns; ++s) {
+            const uint32_t first = sym.SuperFirst[s], last = sym.SuperFirst[s + 1];
+            std::vector<uint32_t> r;
+            for (uint32_t v = first; v < last; ++v) {
+                const uint32_t old = sym.Perm[v];
+                for (uint32_t j = rowptr[old]; j < rowptr[old + 1]; ++j) {
+                    const uint32_t u = sym.InvPerm[col[j]];
+                    if (u >= last && mark[u] != s) {
+                        mark[u] = s;
+                        r.push_back(u);
+                    }
+                }
+            }
+            for (uint32_t c : children[s])
+                for (uint64_t j = sym.RowPtr[c]; j < sym.RowPtr[c + 1]; ++j) {
+                    const uint32_t u = sym.Rows[j];
+                    if (u >= last && mark[u] != s) {
+                        mark[u] = s;
+                        r.push_back(u);
+                    }
+                }
+            // A panel of a chain is coupled to the rest of its separator: the separator is a clique after elimination.
+            for (uint32_t e = s + 1; e < ns && chain[e] == chain[s]; ++e)
+                for (uint32_t u = sym.SuperFirst[e]; u < sym.SuperFirst[e + 1]; ++u)
+                    if (mark[u] != s) {
+                        mark[u] = s;
+                        r.push_back(u);
+                    }
+            std::sort(r.begin(), r.end());
+            sym.Rows.insert(sym.Rows.end(), r.begin(), r.end());
+            sym.RowPtr[s + 1] = sym.Rows.size();
+        }
+    }
+
+    // Levels (height above the leaves), panel offsets, segments, work lists.
+    sym.Level.assign(ns, 0);
+    for (uint32_t s = 0; s < ns; ++s)
+        if (sym.Parent[s] < ns) sym.Level[sym.Parent[s]] = std::max(sym.Level[sym.Parent[s]], sym.Level[s] + 1);
+    sym.NumLevels = ns ? *std::max_element(sym.Level.begin(), sym.Level.end()) + 1 : 0;
+    sym.LevelPtr.assign(size_t(sym.NumLevels) + 1, 0);
+    for (uint32_t s = 0; s < ns; ++s) ++sym.LevelPtr[sym.Level[s] + 1];
+    for (uint32_t l = 0; l < sym.NumLevels; ++l) sym.LevelPtr[l + 1] += sym.LevelPtr[l];
+    sym.LevelOrder.assign(ns, 0);
+    {
+        std::vector<uint32_t> at(sym.LevelPtr.begin(), sym.LevelPtr.end() - 1);
+        for (uint32_t s = 0; s < ns; ++s) sym.LevelOrder[at[sym.Level[s]]++] = s;
+    }
+    sym.PanelOffset.assign(size_t(ns) + 1, 0);
+    sym.InvOffset.assign(size_t(ns) + 1, 0);
+    sym.SegPtr.assign(size_t(ns) + 1, 0);
+    for (uint32_t s = 0; s < ns; ++s) {
+        const uint64_t k = 3ull * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]), m = 3ull * (sym.RowPtr[s + 1] - sym.RowPtr[s]);
+        sym.PanelOffset[s + 1] = sym.PanelOffset[s] + (k + m) * k;
+        sym.InvOffset[s + 1] = sym.InvOffset[s] + k * k;
+        sym.FactorFlops += double(k) * k * k / 3.0 + double(m) * k * k + double(m) * m * k;
+        sym.MaxPanelColumns = std::max<uint32_t>(sym.MaxPanelColumns, uint32_t(k));
+        sym.MaxPanelRows = std::max<uint32_t>(sym.MaxPanelRows, uint32_t(m));
+        const uint64_t r0 = sym.RowPtr[s], r1 = sym.RowPtr[s + 1];
+        for (uint64_t j = r0; j < r1;) {
+            const uint32_t target = sym.NodeSuper[sym.Rows[j]];
+            uint64_t e = j + 1;
+            while (e < r1 && sym.NodeSuper[sym.Rows[e]] == target) ++e;
+            sym.SegTarget.push_back(target);
+            sym.SegBegin.push_back(uint32_t(j - r0));
+            sym.SegEnd.push_back(uint32_t(e - r0));
+            j = e;
+        }
+        sym.SegPtr[s + 1] = sym.SegTarget.size();
+    }
+    sym.FactorNonZeros = sym.PanelOffset[ns];
+
+    sym.PanelTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
+    sym.UpdateTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
+    for (uint32_t l = 0; l < sym.NumLevels; ++l) {
+        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
+            const uint32_t s = sym.LevelOrder[i];
+            const uint32_t m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
+            for (uint32_t t = 0; t * kTile < m; ++t) sym.PanelTiles.push_back({s, t});
+            for (uint64_t g = sym.SegPtr[s]; g < sym.SegPtr[s + 1]; ++g) {
+                const uint32_t c0 = 3 * sym.SegBegin[g], c1 = 3 * sym.SegEnd[g];
+                const uint32_t col_tiles = (c1 - c0 + kTile - 1) / kTile, row_tiles = (m - c0 + kTile - 1) / kTile;
+                for (uint32_t ct = 0; ct < col_tiles; ++ct)
+                    for (uint32_t rt = ct; rt < row_tiles; ++rt) sym.UpdateTiles.push_back({s, uint32_t(g), uint16_t(rt), uint16_t(ct)});
+            }
+        }
+        sym.PanelTilePtr[l + 1] = sym.PanelTiles.size();
+        sym.UpdateTilePtr[l + 1] = sym.UpdateTiles.size();
+    }
+    sym.StructureSeconds = Now() - t1;
+    return sym;
+}
+
+} // namespace me
