@@ -268,6 +268,18 @@ void me_factor_free(MeFactor *);
 MeStatus me_factor_solve(MeFactor *, const double *b, double *x, uint32_t width);
 MeStatus me_factor_info(MeFactor *, MeFactorInfo *out);
 
+/* Host-only: the symbolic analysis behind me_factor_create (geometric nested dissection + supernodes) on a node graph
+ * given as full symmetric CSR (rowptr[node_count+1], col) with node coordinates xyz[node_count][3]. perm_out (may be NULL)
+ * receives the elimination order (perm[new] = old). `violations` counts structural inconsistencies found by the
+ * self-check (entries of the permuted matrix not covered by the supernodal structure, child structures not contained
+ * in their parent's): 0 for a valid analysis. Needs no CUDA device. */
+typedef struct MeSymbolicInfo {
+    uint32_t supernodes, levels, max_panel_columns, max_panel_rows;
+    uint64_t factor_nonzeros, update_tiles, panel_tiles, violations;
+    double factor_flops, ordering_seconds, structure_seconds;
+} MeSymbolicInfo;
+MeStatus me_symbolic_analyse(uint32_t node_count, const uint32_t *rowptr, const uint32_t *col, const float *xyz, uint32_t *perm_out, MeSymbolicInfo *out);
+
 /* FP64 issue-rate micro-benchmark (flop/s): mode 0 DFMA, 1 DMMA (mma.sync.m8n8k4.f64). */
 MeStatus me_measure_fp64_rate(int device, int mode, int iters, double *flops_per_second);
 

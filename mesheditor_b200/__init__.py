@@ -5,4 +5,4 @@ This package is only the ctypes face of that ABI. Importing it never imports any
 """
 from ._lib import LIB_PATH, MeError, MeModalEvent, lib  # noqa: F401
 from .audio import ModalBank, impact_event, measure_fp32_fma_rate, silence_event  # noqa: F401
-from .modal import Factor, FemSystem, ModalResult, material, measure_fp64_rate, mesh2modes, postprocess_modes, solver_config  # noqa: F401,E402
+from .modal import symbolic_analyse, Factor, FemSystem, ModalResult, material, measure_fp64_rate, mesh2modes, postprocess_modes, solver_config  # noqa: F401,E402

@@ -71,6 +71,11 @@ class MeFactorInfo(C.Structure):
                 ("factor_nonzeros", C.c_uint64)] + [(n, C.c_uint32) for n in ("supernodes", "levels", "dofs", "kernel_launches")]
 
 
+class MeSymbolicInfo(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("supernodes", "levels", "max_panel_columns", "max_panel_rows")] + [
+        (n, C.c_uint64) for n in ("factor_nonzeros", "update_tiles", "panel_tiles", "violations")] + [(n, C.c_double) for n in ("factor_flops", "ordering_seconds", "structure_seconds")]
+
+
 def struct_dict(s):
     out = {}
     for name, _ in s._fields_:
@@ -127,6 +132,7 @@ def lib():
         "me_factor_create": [vp, C.c_double, C.POINTER(vp)],
         "me_factor_solve": [vp, vp, vp, u32],
         "me_factor_info": [vp, C.POINTER(MeFactorInfo)],
+        "me_symbolic_analyse": [u32, vp, vp, vp, vp, C.POINTER(MeSymbolicInfo)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

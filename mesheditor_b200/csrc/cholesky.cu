@@ -24,7 +24,7 @@ struct FactorView {
     const uint32_t *SuperFirst, *Rows, *NodeSuper;
     const uint64_t *RowPtr, *PanelOffset, *InvOffset;
     const uint32_t *SegTarget, *SegBegin, *SegEnd;
-    double *L, *Linv;
+    double *L, *Linv, *LinvT;
     int *Fail;
 };
 
@@ -117,12 +117,14 @@ __global__ void __launch_bounds__(kFactorThreads) FactorDiagKernel(FactorView v,
     if (h == 0 && i >= k - 1 && i < k) sm[i + (k - 1) * lds] = pending;
     __syncthreads();
     if (bad && t == 0) atomicExch(v.Fail, 1);
-    double *linv = v.Linv + v.InvOffset[s];
+    double *linv = v.Linv + v.InvOffset[s], *linvt = v.LinvT + v.InvOffset[s];
     for (uint32_t idx = t; idx < k * k; idx += kFactorThreads) {
         const uint32_t r = idx % k, c = idx / k;
         if (r >= c) panel[r + size_t(c) * ld] = sm[r + c * lds];
         const double dr = sm[r + r * lds];
-        linv[r + size_t(c) * k] = r == c ? 1.0 / dr : (r > c ? sm[c + r * lds] / dr : 0.0);
+        const double value = r == c ? 1.0 / dr : (r > c ? sm[c + r * lds] / dr : 0.0);
+        linv[r + size_t(c) * k] = value;
+        linvt[c + size_t(r) * k] = value;
     }
 }
 
@@ -265,77 +267,109 @@ __global__ void PermuteOutKernel(const double *__restrict__ w, const uint32_t *_
     if (i < 3 * n_nodes) x[i] = w[3 * inv_perm[i / 3] + i % 3];
 }
 
-// w_S <- Linv_S w_S (forward) or Linv_S^T w_S (backward) for every supernode of one level. 128 threads per supernode.
-template<bool Transposed>
-__global__ void __launch_bounds__(128) DiagSolveKernel(FactorView v, const uint32_t *__restrict__ level_supers, double *__restrict__ w) {
-    __shared__ double vs[128];
+// The three solve kernels share one load shape: a 64-row x k-column slab (k <= 128) is covered by 256 threads, thread t
+// owning row t & 63 and the 32 columns (t >> 6) + 4 j. All 32 loads of a thread are independent and issued together,
+// so a kernel costs about one L2/HBM round trip instead of k dependent ones: the solves are a chain of ~4 small
+// launches per level, and their latency, not bandwidth, is what the low levels of the tree pay.
+constexpr int kSolveThreads = 256;
+
+// w_S <- T_S w_S for every supernode of one level, T = Linv (forward, lower triangular) or the stored transpose
+// Linv^T (backward, upper triangular). One CTA per supernode.
+template<bool Upper>
+__global__ void __launch_bounds__(kSolveThreads) DiagSolveKernel(FactorView v, const double *__restrict__ tri, const uint32_t *__restrict__ level_supers, double *__restrict__ w) {
+    __shared__ double vs[128], part[4][64];
     const uint32_t s = level_supers[blockIdx.x], k = PanelColumns(v, s);
     double *ws = w + size_t(3) * v.SuperFirst[s];
-    const double *linv = v.Linv + v.InvOffset[s];
-    const uint32_t t = threadIdx.x;
-    if (t < k) vs[t] = ws[t];
+    const double *mat = tri + v.InvOffset[s];
+    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6;
+    if (t < 128) vs[t] = t < k ? ws[t] : 0.0;
     __syncthreads();
-    if constexpr (!Transposed) {
-        if (t < k) {
-            double sum = 0;
-            for (uint32_t c = 0; c <= t; ++c) sum += linv[t + size_t(c) * k] * vs[c];
-            ws[t] = sum;
-        }
-    } else {
-        const uint32_t lane = t & 31, warp = t >> 5;
-        for (uint32_t i = warp; i < k; i += 4) {
-            double sum = 0;
-            for (uint32_t c = i + lane; c < k; c += 32) sum += linv[c + size_t(i) * k] * vs[c];
+    for (uint32_t pass = 0; pass * 64 < k; ++pass) {
+        const uint32_t row = pass * 64 + r;
+        double val[32];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) ws[i] = sum;
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t c = q + 4 * j;
+            const bool in = row < k && c < k && (Upper ? c >= row : c <= row);
+            val[j] = in ? mat[row + size_t(c) * k] : 0.0;
         }
+        double sum = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sum += val[j] * vs[q + 4 * j];
+        part[q][r] = sum;
+        __syncthreads();
+        if (t < 64 && row < k) ws[row] = (part[0][t] + part[1][t]) + (part[2][t] + part[3][t]);
+        __syncthreads();
     }
 }
-// Forward: w[rows of the tile] -= P_tile * y_S. One thread per row, 64 rows per CTA.
-__global__ void __launch_bounds__(64) PanelForwardKernel(FactorView v, const PanelTile *__restrict__ tiles, double *__restrict__ w) {
-    __shared__ double ys[128];
+// Forward: w[rows of the tile] -= P_tile * y_S.
+__global__ void __launch_bounds__(kSolveThreads) PanelForwardKernel(FactorView v, const PanelTile *__restrict__ tiles, double *__restrict__ w) {
+    __shared__ double ys[128], part[4][64];
     const PanelTile tile = tiles[blockIdx.x];
     const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
     const double *p0 = v.L + v.PanelOffset[s] + k;
-    const uint32_t t = threadIdx.x;
-    for (uint32_t c = t; c < k; c += 64) ys[c] = w[size_t(3) * v.SuperFirst[s] + c];
+    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6;
+    if (t < 128) ys[t] = t < k ? w[size_t(3) * v.SuperFirst[s] + t] : 0.0;
     __syncthreads();
-    const uint32_t r = tile.RowTile * kTile + t;
-    if (r >= m) return;
-    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-    uint32_t c = 0;
-    for (; c + 4 <= k; c += 4) {
-        s0 += p0[r + size_t(c) * ld] * ys[c];
-        s1 += p0[r + size_t(c + 1) * ld] * ys[c + 1];
-        s2 += p0[r + size_t(c + 2) * ld] * ys[c + 2];
-        s3 += p0[r + size_t(c + 3) * ld] * ys[c + 3];
-    }
-    for (; c < k; ++c) s0 += p0[r + size_t(c) * ld] * ys[c];
-    const uint32_t node = v.Rows[v.RowPtr[s] + r / 3];
-    atomicAdd(w + size_t(3) * node + r % 3, -((s0 + s1) + (s2 + s3)));
-}
-// Backward: w_S -= P_tile^T x[rows of the tile]. Four warps stride over the panel's columns.
-__global__ void __launch_bounds__(128) PanelBackwardKernel(FactorView v, const PanelTile *__restrict__ tiles, double *__restrict__ w) {
-    __shared__ double xs[kTile];
-    const PanelTile tile = tiles[blockIdx.x];
-    const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
-    const double *p0 = v.L + v.PanelOffset[s] + k;
-    const uint32_t t = threadIdx.x, row0 = tile.RowTile * kTile, nrows = min(kTile, m - row0);
-    if (t < kTile) {
-        const uint32_t r = row0 + t;
-        xs[t] = t < nrows ? w[size_t(3) * v.Rows[v.RowPtr[s] + r / 3] + r % 3] : 0.0;
-    }
-    __syncthreads();
-    const uint32_t lane = t & 31, warp = t >> 5;
-    double *ws = w + size_t(3) * v.SuperFirst[s];
-    for (uint32_t c = warp; c < k; c += 4) {
-        const double *col = p0 + row0 + size_t(c) * ld;
-        double sum = (lane < nrows ? col[lane] * xs[lane] : 0.0) + (lane + 32 < nrows ? col[lane + 32] * xs[lane + 32] : 0.0);
+    const uint32_t row = tile.RowTile * kTile + r;
+    double val[32];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) atomicAdd(ws + c, -sum);
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t c = q + 4 * j;
+        val[j] = (row < m && c < k) ? p0[row + size_t(c) * ld] : 0.0;
     }
+    double sum = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) sum += val[j] * ys[q + 4 * j];
+    part[q][r] = sum;
+    __syncthreads();
+    if (t < 64 && row < m) {
+        const uint32_t node = v.Rows[v.RowPtr[s] + row / 3];
+        atomicAdd(w + size_t(3) * node + row % 3, -((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])));
+    }
+}
+// Backward: w_S -= P_rows^T x[rows] over a run of up to 8 row tiles of one panel. Each warp accumulates 32 rows x 32
+// columns of products per tile and reduces them once at the end with a transposing butterfly (31 shuffles), after which
+// lane L holds the column sum of its L-th column: two atomics per column and CTA instead of two per column and tile.
+__global__ void __launch_bounds__(kSolveThreads) PanelBackwardKernel(FactorView v, const PanelGroup *__restrict__ groups, double *__restrict__ w) {
+    __shared__ double xs[kGroupTiles * kTile];
+    const PanelGroup group = groups[blockIdx.x];
+    const uint32_t s = group.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
+    const double *p0 = v.L + v.PanelOffset[s] + k;
+    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6, lane = t & 31;
+    const uint32_t row0 = group.FirstTile * kTile, n_rows = min(group.Tiles * kTile, m - row0);
+    for (uint32_t i = t; i < group.Tiles * kTile; i += kSolveThreads) {
+        const uint32_t row = row0 + i;
+        xs[i] = i < n_rows ? w[size_t(3) * v.Rows[v.RowPtr[s] + row / 3] + row % 3] : 0.0;
+    }
+    __syncthreads();
+    double val[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) val[j] = 0.0;
+    for (uint32_t tile = 0; tile < group.Tiles; ++tile) {
+        const uint32_t local = tile * kTile + r, row = row0 + local;
+        const double x = xs[local];
+        double a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const uint32_t c = q + 4 * j;
+            a[j] = (local < n_rows && c < k) ? p0[row + size_t(c) * ld] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) val[j] += a[j] * x;
+    }
+#pragma unroll
+    for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const double send = upper ? val[i] : val[i + n / 2];
+            const double keep = upper ? val[i + n / 2] : val[i];
+            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+    }
+    const uint32_t c = q + 4 * lane;
+    if (c < k) atomicAdd(w + size_t(3) * v.SuperFirst[s] + c, -val[0]);
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 rate probes
@@ -411,9 +445,11 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     DPanelOffset.Upload(Sym.PanelOffset, s);
     DInvOffset.Upload(Sym.InvOffset, s);
     DPanelTiles.Upload(Sym.PanelTiles, s);
+    DPanelGroups.Upload(Sym.PanelGroups, s);
     DUpdateTiles.Upload(Sym.UpdateTiles, s);
     L.Reserve(Sym.FactorNonZeros);
     Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
+    LinvT.Reserve(Sym.InvOffset[Sym.NumSuper]);
     Work.Reserve(fem.N);
     DFail.Reserve(1);
     for (auto &e : Ev) ME_CUDA(cudaEventCreate(&e));
@@ -431,12 +467,13 @@ SparseCholesky::~SparseCholesky() {
     cudaSetDevice(Fem.Device);
     for (auto &e : Ev)
         if (e) cudaEventDestroy(e);
+    if (SolveGraph) cudaGraphExecDestroy(SolveGraph);
 }
 
 void SparseCholesky::Factorize(double sigma) {
     ME_CUDA(cudaSetDevice(Fem.Device));
     auto s = Fem.Stream;
-    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, DFail.Ptr};
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, DFail.Ptr};
     ME_CUDA(cudaEventRecord(Ev[0], s));
     ME_CUDA(cudaMemsetAsync(DFail.Ptr, 0, sizeof(int), s));
     ME_CUDA(cudaMemsetAsync(L.Ptr, 0, Sym.FactorNonZeros * sizeof(double), s));
@@ -472,36 +509,47 @@ void SparseCholesky::Factorize(double sigma) {
     Factored = true;
 }
 
+void SparseCholesky::RecordSolveLevels(cudaStream_t s, uint32_t &launches) {
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, DFail.Ptr};
+    double *w = Work.Ptr;
+    for (uint32_t l = 0; l < Sym.NumLevels; ++l) {
+        const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
+        DiagSolveKernel<false><<<n_super, kSolveThreads, 0, s>>>(v, Linv.Ptr, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
+        const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
+        if (n_panel) PanelForwardKernel<<<uint32_t(n_panel), kSolveThreads, 0, s>>>(v, DPanelTiles.Ptr + Sym.PanelTilePtr[l], w);
+        launches += 1 + (n_panel != 0);
+    }
+    for (uint32_t l = Sym.NumLevels; l-- > 0;) {
+        const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
+        const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
+        const uint64_t n_group = Sym.PanelGroupPtr[l + 1] - Sym.PanelGroupPtr[l];
+        if (n_group) PanelBackwardKernel<<<uint32_t(n_group), kSolveThreads, 0, s>>>(v, DPanelGroups.Ptr + Sym.PanelGroupPtr[l], w);
+        DiagSolveKernel<true><<<n_super, kSolveThreads, 0, s>>>(v, LinvT.Ptr, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
+        launches += 1 + (n_panel != 0);
+    }
+}
+
 void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     if (!Factored) Fail(ME_BAD_ARG, "Solve before Factorize");
     ME_CUDA(cudaSetDevice(Fem.Device));
     auto s = Fem.Stream;
-    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, DFail.Ptr};
     const uint32_t n = Fem.N;
-    uint32_t launches = 0;
-    ME_CUDA(cudaEventRecord(Ev[2], s));
-    for (uint32_t rhs = 0; rhs < width; ++rhs) {
-        double *w = Work.Ptr;
-        PermuteInKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, w);
-        for (uint32_t l = 0; l < Sym.NumLevels; ++l) {
-            const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
-            DiagSolveKernel<false><<<n_super, 128, 0, s>>>(v, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
-            const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
-            if (n_panel) PanelForwardKernel<<<uint32_t(n_panel), 64, 0, s>>>(v, DPanelTiles.Ptr + Sym.PanelTilePtr[l], w);
-            launches += 1 + (n_panel != 0);
-        }
-        for (uint32_t l = Sym.NumLevels; l-- > 0;) {
-            const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
-            const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
-            if (n_panel) PanelBackwardKernel<<<uint32_t(n_panel), 128, 0, s>>>(v, DPanelTiles.Ptr + Sym.PanelTilePtr[l], w);
-            DiagSolveKernel<true><<<n_super, 128, 0, s>>>(v, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
-            launches += 1 + (n_panel != 0);
-        }
-        PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(w, DInvPerm.Ptr, Fem.NodeCount, x + size_t(rhs) * n);
-        launches += 2;
+    if (!SolveGraph) {
+        // The level sweep is the same ~4 launches per level for every right-hand side: capture it once, replay it.
+        cudaGraph_t graph = nullptr;
+        GraphLaunches = 0;
+        ME_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        RecordSolveLevels(s, GraphLaunches);
+        ME_CUDA(cudaStreamEndCapture(s, &graph));
+        ME_CUDA(cudaGraphInstantiate(&SolveGraph, graph, 0));
+        cudaGraphDestroy(graph);
     }
-    ME_CUDA(cudaEventRecord(Ev[3], s));
-    Stats.KernelLaunches += launches;
+    for (uint32_t rhs = 0; rhs < width; ++rhs) {
+        PermuteInKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr);
+        ME_CUDA(cudaGraphLaunch(SolveGraph, s));
+        PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, DInvPerm.Ptr, Fem.NodeCount, x + size_t(rhs) * n);
+        Stats.KernelLaunches += GraphLaunches + 2;
+    }
 }
 
 } // namespace me

@@ -45,8 +45,12 @@ private:
     DeviceBuffer<uint32_t> DSuperFirst, DRows, DNodeSuper, DInvPerm, DPerm, DSegTarget, DSegBegin, DSegEnd, DLevelOrder;
     DeviceBuffer<uint64_t> DRowPtr, DPanelOffset, DInvOffset;
     DeviceBuffer<PanelTile> DPanelTiles;
+    DeviceBuffer<PanelGroup> DPanelGroups;
     DeviceBuffer<UpdateTile> DUpdateTiles;
-    DeviceBuffer<double> L, Linv, Work;
+    void RecordSolveLevels(cudaStream_t, uint32_t &launches);
+    DeviceBuffer<double> L, Linv, LinvT, Work;
+    cudaGraphExec_t SolveGraph{nullptr};
+    uint32_t GraphLaunches{0};
     DeviceBuffer<int> DFail;
     cudaEvent_t Ev[4]{};
     bool Factored{false};

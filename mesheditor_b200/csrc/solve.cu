@@ -625,6 +625,42 @@ MeStatus me_factor_info(MeFactor *f, MeFactorInfo *out) {
     });
 }
 
+MeStatus me_symbolic_analyse(uint32_t node_count, const uint32_t *rowptr, const uint32_t *col, const float *xyz, uint32_t *perm_out, MeSymbolicInfo *out) {
+    return Guard([&] {
+        if (!rowptr || !col || !xyz || !out || node_count == 0) Fail(ME_BAD_ARG, "bad argument");
+        const me::Symbolic sym = me::Analyse(node_count, rowptr, col, xyz);
+        uint64_t violations = 0;
+        std::vector<uint8_t> seen(node_count, 0);
+        for (uint32_t v : sym.Perm) {
+            if (v >= node_count || seen[v]) ++violations;
+            else seen[v] = 1;
+        }
+        auto in_rows = [&](uint32_t s, uint32_t node) {
+            const auto b = sym.Rows.begin() + sym.RowPtr[s], e = sym.Rows.begin() + sym.RowPtr[s + 1];
+            return std::binary_search(b, e, node);
+        };
+        for (uint32_t v = 0; v < node_count; ++v)
+            for (uint32_t j = rowptr[v]; j < rowptr[v + 1]; ++j) {
+                const uint32_t a = sym.InvPerm[v], b = sym.InvPerm[col[j]], r = std::max(a, b), c = std::min(a, b), s = sym.NodeSuper[c];
+                if (r >= sym.SuperFirst[s + 1] && !in_rows(s, r)) ++violations;
+            }
+        for (uint32_t s = 0; s < sym.NumSuper; ++s) {
+            const uint32_t p = sym.Parent[s];
+            if (sym.RowPtr[s + 1] > sym.RowPtr[s] && !std::is_sorted(sym.Rows.begin() + sym.RowPtr[s], sym.Rows.begin() + sym.RowPtr[s + 1])) ++violations;
+            for (uint64_t j = sym.RowPtr[s]; j < sym.RowPtr[s + 1]; ++j) {
+                const uint32_t u = sym.Rows[j];
+                if (u < sym.SuperFirst[s + 1]) ++violations;
+                if (p >= sym.NumSuper) ++violations; // a root has no below-diagonal structure
+                else if (!(u >= sym.SuperFirst[p] && u < sym.SuperFirst[p + 1]) && !in_rows(p, u)) ++violations;
+            }
+            if (p < sym.NumSuper && sym.Level[p] <= sym.Level[s]) ++violations;
+        }
+        if (perm_out) std::copy(sym.Perm.begin(), sym.Perm.end(), perm_out);
+        *out = MeSymbolicInfo{sym.NumSuper, sym.NumLevels, sym.MaxPanelColumns, sym.MaxPanelRows, sym.FactorNonZeros, sym.UpdateTiles.size(), sym.PanelTiles.size(), violations,
+                              sym.FactorFlops, sym.OrderingSeconds, sym.StructureSeconds};
+    });
+}
+
 MeStatus me_measure_fp64_rate(int device, int mode, int iters, double *flops_per_second) {
     return Guard([&] {
         if (!flops_per_second || mode < 0 || mode > 1 || iters < 1) Fail(ME_BAD_ARG, "bad argument");

@@ -229,11 +229,14 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
 
     sym.PanelTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
     sym.UpdateTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
+    sym.PanelGroupPtr.assign(size_t(sym.NumLevels) + 1, 0);
     for (uint32_t l = 0; l < sym.NumLevels; ++l) {
         for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
             const uint32_t s = sym.LevelOrder[i];
             const uint32_t m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
             for (uint32_t t = 0; t * kTile < m; ++t) sym.PanelTiles.push_back({s, t});
+            const uint32_t n_tiles = (m + kTile - 1) / kTile;
+            for (uint32_t t = 0; t < n_tiles; t += kGroupTiles) sym.PanelGroups.push_back({s, t, std::min(kGroupTiles, n_tiles - t)});
             for (uint64_t g = sym.SegPtr[s]; g < sym.SegPtr[s + 1]; ++g) {
                 const uint32_t c0 = 3 * sym.SegBegin[g], c1 = 3 * sym.SegEnd[g];
                 const uint32_t col_tiles = (c1 - c0 + kTile - 1) / kTile, row_tiles = (m - c0 + kTile - 1) / kTile;
@@ -242,6 +245,7 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
             }
         }
         sym.PanelTilePtr[l + 1] = sym.PanelTiles.size();
+        sym.PanelGroupPtr[l + 1] = sym.PanelGroups.size();
         sym.UpdateTilePtr[l + 1] = sym.UpdateTiles.size();
     }
     sym.StructureSeconds = Now() - t1;

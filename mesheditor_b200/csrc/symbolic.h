@@ -23,6 +23,11 @@ struct UpdateTile {
 struct PanelTile {
     uint32_t Super, RowTile;
 };
+// A run of consecutive 64-row tiles of one panel handled by one CTA of the backward solve (fewer atomics per column).
+struct PanelGroup {
+    uint32_t Super, FirstTile, Tiles;
+};
+constexpr uint32_t kGroupTiles = 8;
 
 struct Symbolic {
     uint32_t NodeCount{0}, NumSuper{0}, NumLevels{0};
@@ -40,6 +45,8 @@ struct Symbolic {
     // Work lists per level.
     std::vector<uint64_t> PanelTilePtr, UpdateTilePtr; // [NumLevels+1]
     std::vector<PanelTile> PanelTiles;        // 64-row tiles of the below-diagonal panels (TRSM, solves)
+    std::vector<uint64_t> PanelGroupPtr;      // [NumLevels+1]
+    std::vector<PanelGroup> PanelGroups;
     std::vector<UpdateTile> UpdateTiles;
     uint64_t FactorNonZeros{0};               // scalars stored in the panels
     double FactorFlops{0};

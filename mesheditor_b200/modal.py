@@ -9,7 +9,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-from ._lib import (ME_CANCELLED, ME_NO_MODES, ME_NOT_CONVERGED, ME_OK, MeError, MeFactorInfo, MeFemInfo, MeJobMonitor, MeMassProperties, MeMaterial, MeSolveProfile,
+from ._lib import (MeSymbolicInfo, ME_CANCELLED, ME_NO_MODES, ME_NOT_CONVERGED, ME_OK, MeError, MeFactorInfo, MeFemInfo, MeJobMonitor, MeMassProperties, MeMaterial, MeSolveProfile,
                    MeSolverConfig, check, lib, struct_dict)
 
 # materials::acoustic (src/audio/AcousticMaterial.h:33-40): density, Young, Poisson, alpha, beta
@@ -205,3 +205,12 @@ def measure_fp64_rate(device=0, mode=1, iters=5):
     out = C.c_double()
     check(lib().me_measure_fp64_rate(device, mode, iters, C.byref(out)))
     return out.value
+
+
+def symbolic_analyse(rowptr, col, xyz):
+    """The host-side ordering + supernodal structure of the sparse Cholesky (no device needed): (perm, info dict)."""
+    rowptr, col, xyz = np.ascontiguousarray(rowptr, np.uint32), np.ascontiguousarray(col, np.uint32), np.ascontiguousarray(xyz, np.float32)
+    n = len(rowptr) - 1
+    perm, info = np.zeros(n, np.uint32), MeSymbolicInfo()
+    check(lib().me_symbolic_analyse(n, rowptr.ctypes.data, col.ctypes.data, xyz.ctypes.data, perm.ctypes.data, C.byref(info)))
+    return perm, struct_dict(info)

@@ -90,7 +90,48 @@ def golden_model(path, name):
     )
 
 
+def icosphere(radius, recursion_level):
+    """IcoSphere primitive restated from src/mesh/Primitives.h:60-110 in float32 (positions, triangle indices)."""
+    f32 = np.float32
+    t = f32((1 + 5 ** 0.5) / 2)
+    verts = [np.array(v, f32) for v in [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]]
+
+    def normalize(v):
+        return (v * (f32(1) / np.sqrt(f32(np.dot(v, v))))).astype(f32)
+
+    verts = [normalize(v) for v in verts]
+    tris = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+            (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    cache = {}
+
+    def mid(a, b):
+        key = (min(a, b), max(a, b))
+        if key not in cache:
+            verts.append(normalize(((verts[a] + verts[b]) / f32(2)).astype(f32)))
+            cache[key] = len(verts) - 1
+        return cache[key]
+
+    for _ in range(recursion_level):
+        new = []
+        for a, b, c in tris:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            new += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        tris = new
+    return (np.asarray(verts, f32) * f32(radius)).astype(f32), np.asarray(tris, np.uint32).ravel()
+
+
+def make_config1():
+    """BASELINE.json configs[0]: IcoSphere radius 0.1 m, 4 subdivisions, reference tetrahedralizer with
+    Quality on. Mesh only (no golden answer exists for it); the parity tests solve it with the oracle."""
+    surf, tri = icosphere(0.1, 4)
+    points, tets = tetrahedralize(surf, tri, quality=True)
+    np.savez_compressed(os.path.join(HERE, "..", "meshes", "icosphere_c1.npz"), points=points, tets=tets, surface=surf, triangles=tri)
+    print(f"icosphere_c1: {len(surf)} surface verts, {len(points)} points, {len(tets)} tets")
+
+
 def main():
+    os.makedirs(os.path.join(HERE, "..", "meshes"), exist_ok=True)
+    make_config1()
     gen = load_generator()
     sphere = lambda r: (lambda p, n, u, idx: (p, [tuple(idx[t:t + 3]) for t in range(0, len(idx), 3)]))(*gen.sphere(r))
     cases = [
