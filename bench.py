@@ -300,6 +300,200 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ analysis workloads
+SOLVE_METRIC, SOLVE_UNIT = "modal solve seconds per mesh", "s/mesh"
+C3_EDGE, C3_MODES, C3_ORDER = 55, 200, 1  # BASELINE.json configs[2]: 55^3 Kuhn block = 998,250 tets, lowest 200 modes, P1
+CPU_SAMPLE_EDGE = 16                       # the CPU arm's bounded sample: 16^3 cells = 24,576 tets (~20-30 s of host work), same material / modes / element order
+
+
+def solve_config():
+    return {
+        "workload": f"BASELINE.json configs[2]: synthetic {C3_EDGE}^3-cell Kuhn block = {6 * C3_EDGE ** 3:,} tets (0.3 m steel cube), linear (P1) elements (the reference's P2 does not fit one GPU at this size, SURVEY.md F1), "
+                    f"lowest {C3_MODES} modes (NumFemModes {C3_MODES + 15}, ncv {C3_MODES + 35}), FP64 shift-invert Lanczos, 10 excitation points",
+        "tets": 6 * C3_EDGE ** 3, "element_order": C3_ORDER, "num_modes": C3_MODES,
+        "l2_policy": "working set > L2: the factor is 7.3 GB and the Lanczos basis 1 GB, both streamed from HBM every step",
+    }
+
+
+def cpu_solve_reference(edge=CPU_SAMPLE_EDGE, modes=C3_MODES, order=C3_ORDER):
+    """The oracle's restatement of the reference path (numpy assembly + ARPACK shift-invert over SuperLU; the reference binary
+    itself needs Eigen + Apple Accelerate and cannot be built here) on a bounded sample of the workload."""
+    from mesheditor_b200 import workloads as wl
+    from oracle import modal as om
+
+    points, tets = wl.kuhn_block(edge, edge, edge, (0.3, 0.3, 0.3))
+    cfg = om.SolverConfig(num_modes=modes, num_fem_modes=modes + 15, max_mode_freq=1e9)
+    t0 = time.perf_counter()
+    r = om.mesh2modes(points, tets, om.MATERIALS["Steel"], wl.bench_excitations(points), config=cfg, order=order, tol=1e-8)
+    dt = time.perf_counter() - t0
+    return {"value": dt, "unit": SOLVE_UNIT, "cores": os.cpu_count() or 1, "kind": "port", "tets": len(tets), "dofs": r["dofs"],
+            "sample": f"{edge}^3-cell Kuhn block = {len(tets):,} tets ({len(tets) / (6 * C3_EDGE ** 3):.1%} of the workload's tets), P{order}, {modes} modes, oracle/modal.py (numpy assembly + scipy ARPACK/SuperLU, BLAS threads on all host cores): "
+                      f"{dt:.1f} s for this sample; the full 998,250-tet mesh does not finish on the host in the bench's time budget"}
+
+
+def solve_once(points, tets, ex, cfg):
+    from mesheditor_b200 import mesh2modes
+
+    t0 = time.perf_counter()
+    r = mesh2modes(points, tets, "Steel", ex, config=cfg)
+    return time.perf_counter() - t0, r
+
+
+def run_solve(args):
+    """`--workload solve`: one 1M-tet mesh on one GPU (a single eigensolve does not shard: with --gpus N every rank solves a
+    replica and the slowest is reported)."""
+    import torch
+    import torch.distributed as dist
+
+    from mesheditor_b200 import Factor, FemSystem, build, measure_fp64_rate, solver_config
+    from mesheditor_b200 import workloads as wl
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    points, tets = wl.kuhn_block(C3_EDGE, C3_EDGE, C3_EDGE, (0.3, 0.3, 0.3))
+    ex = wl.bench_excitations(points)
+    cfg = solver_config(num_modes=C3_MODES, element_order=C3_ORDER, max_mode_freq=1e9, device=local)
+    for _ in range(max(1, min(args.warmup, 3))):
+        solve_once(points, tets, ex, cfg)
+    times, profiles = [], []
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            torch.cuda.synchronize()
+            dt, r = solve_once(points, tets, ex, cfg)  # host mesh in, host modal model out: this IS the end-to-end call
+            assert r.status == 0 and len(r.freqs) == C3_MODES
+            times.append(dt)
+            profiles.append(r.profile)
+    t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        sec = float(t[0])
+        prof = {k: (sum(p[k] for p in profiles) / len(profiles) if isinstance(profiles[0][k], float) else profiles[-1][k]) for k in profiles[0]}
+        device_s = sec - prof["mass_props"]  # everything but the (host) lumped mass properties runs on, or waits for, the device
+        pk, pk_kind = peaks()
+        # Stage rooflines, measured in this run through the stage entry points of the C ABI.
+        fem = FemSystem(points, tets, "Steel", C3_ORDER, local)
+        i = fem.info
+        x = np.random.default_rng(0).standard_normal(i["dofs"])
+        fem.spmv("K", x, 50)
+        spmv_bytes = 12 * 9 * i["node_blocks_full"] + 20 * i["dofs"] + 4
+        spmv = {"kernel": "SpmvBsr3Kernel (y = K x)", "bound": "hbm", "achieved": spmv_bytes / (fem.last_spmv_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "ms": fem.last_spmv_ms, "algorithmic_bytes": spmv_bytes}
+        spmv["frac"] = spmv["achieved"] / spmv["peak"]
+        asm_bytes = 16 * len(tets) + 24 * len(points) + 12 * (i["nnz_stiffness"] + i["nnz_mass"]) + 8 * (i["dofs"] + 1)
+        asm = {"kernel": "AssembleKernel", "bound": "hbm", "achieved": asm_bytes / (i["assemble_kernel_ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "ms": i["assemble_kernel_ms"], "algorithmic_bytes": asm_bytes}
+        asm["frac"] = asm["achieved"] / asm["peak"]
+        f = Factor(fem, -((2 * np.pi * 20.0) ** 2))
+        fi = f.info
+        dmma = measure_fp64_rate(local, 1, 3)
+        factor = {"kernel": "SyrkScatterKernel + PanelTrsmKernel + FactorDiagKernel (numeric Cholesky)", "bound": "tensor", "achieved": fi["factor_flops"] / (fi["factor_device_ms"] * 1e-3) / 1e12, "peak": dmma / 1e12,
+                  "unit": "TFLOP/s", "ms": fi["factor_device_ms"], "flops": fi["factor_flops"], "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) issue-rate probe measured in this run; MEASURED_PEAKS.json has no FP64 figure"}
+        factor["frac"] = factor["achieved"] / factor["peak"]
+        b = np.random.default_rng(1).standard_normal(i["dofs"])
+        for _ in range(3):
+            f.solve(b)
+        solve_ms = f.info["last_solve_device_ms"]
+        sweep_bytes = 16 * fi["factor_nonzeros"] + 16 * i["dofs"]
+        ops = prof["op_applications"]
+        line = {
+            "metric": SOLVE_METRIC, "value": sec, "unit": SOLVE_UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 * sec, "higher_is_better": False,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(solve_config(), parallelism="replicas only: one mesh's eigensolve runs on one GPU" if world > 1 else "single GPU"),
+            "e2e": {"value": sec, "unit": SOLVE_UNIT, "h2d_bytes_per_step": int(points.nbytes + tets.nbytes + ex.nbytes), "d2h_bytes_per_step": int(8 * (C3_MODES + 15) + 4 * 3 * 10 * (C3_MODES + 15) + 4 * 3 * 10),
+                    "note": "me_modal_solve takes the mesh from HOST memory and returns the modal model to HOST memory; value and e2e are the same call"},
+            "device_seconds": device_s, "gpu_launches": int(sum(p["kernel_launches"] for p in profiles)),
+            "profile": {k: prof[k] for k in ("mass_props", "assemble", "sample_excite", "factorize", "analyse", "iterate", "op_solve", "extract", "dofs", "stiffness_nonzeros", "op_applications", "restarts", "factor_nonzeros", "supernodes", "levels")},
+            "roofline": {"bound": "hbm", "kernel": "triangular-solve sweep of the shift-invert operator (DiagSolve/PanelForward/PanelBackward, one CUDA-graph replay per operator application)",
+                         "achieved": sweep_bytes / (solve_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": sweep_bytes / (solve_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                         "ms_per_launch": solve_ms, "algorithmic_bytes": sweep_bytes, "share_of_step": prof["op_solve"] / sec, "applications_per_step": ops, "peak_source": pk_kind},
+            "roofline_spmv": spmv, "roofline_assembly": asm, "roofline_factor": factor,
+            "clocks": clocks.summary(),
+        }
+        if not args.no_cpu_baseline:
+            base = cpu_solve_reference()
+            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_batch(args):
+    """`--workload batch`: BASELINE.json configs[3], 64 Kuhn blocks of 10k..500k tets, dealt biggest-first to the least-loaded
+    rank (the reference bench's biggest-file-first rule, tests/ModalSolverBench.cpp:475-478); no collective on the data path."""
+    import torch
+    import torch.distributed as dist
+
+    from mesheditor_b200 import build, solver_config
+    from mesheditor_b200 import workloads as wl
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    build.build()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dims = wl.config4_dims()
+    owner = wl.lpt_assign([(6.0 * d ** 3) ** (4.0 / 3.0) for d in dims], world)
+    mine = [d for d, o in zip(dims, owner) if o == rank]
+    cfg = solver_config(num_modes=30, element_order=1, max_mode_freq=1e9, device=local)
+    meshes = [wl.kuhn_block(d, d, d, (0.3, 0.3, 0.3)) for d in mine]
+
+    def step():
+        n = 0
+        for points, tets in meshes:
+            _, r = solve_once(points, tets, wl.bench_excitations(points), cfg)
+            assert r.status == 0
+            n += r.profile["kernel_launches"]
+        return n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(1, min(args.warmup, 3)) if args.warmup else 0):
+        step()
+    launches, total = 0, 0.0
+    with ClockSampler(local) as clocks:
+        for _ in range(args.steps):
+            barrier()
+            t0 = time.perf_counter()
+            launches += step()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            total += float(dt[0])
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(lt)
+    if rank == 0:
+        sec = total / args.steps
+        print(json.dumps({
+            "metric": "batch modal solve meshes/s", "value": len(dims) / sec, "unit": "meshes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE.json configs[3]: 64 Kuhn-block meshes, {6 * dims[0] ** 3:,}..{6 * dims[-1] ** 3:,} tets (log-spaced), P1, lowest 30 modes each", "parallelism": f"meshes dealt biggest-first over {world} GPU(s), no collective"},
+            "e2e": {"value": len(dims) / sec, "unit": "meshes/s", "h2d_bytes_per_step": int(sum(p.nbytes + t.nbytes for p, t in meshes)), "d2h_bytes_per_step": 0}, "gpu_launches": int(lt[0]), "clocks": clocks.summary()}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_solve_reference(args):
+    if env_int("RANK", 0) != 0:
+        return
+    base = cpu_solve_reference()
+    print(json.dumps({
+        "impl": "reference", "metric": SOLVE_METRIC, "value": base["value"], "unit": SOLVE_UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": 1e3 * base["value"], "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": solve_config(), "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": SOLVE_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+        "note": "value is the time of the bounded SAMPLE (see cpu_baseline.sample), not of the full 998,250-tet mesh"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -307,8 +501,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="resonator", choices=["resonator", "solve", "batch"],
+                    help="resonator: configs[4] (default, the metric quoted at 1/2/4/8 GPUs); solve: configs[2], one 1M-tet mesh; batch: configs[3], 64 meshes sharded")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "solve":
+        if args.steps == 5:
+            args.steps = 2
+        run_solve_reference(args) if args.impl == "reference" else run_solve(args)
+    elif args.workload == "batch":
+        if args.steps == 5:
+            args.steps = 1
+        if args.impl == "reference":
+            run_solve_reference(args)
+        else:
+            run_batch(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
