@@ -2,6 +2,7 @@
 #include "bank.h"
 #include "common.h"
 
+#include <mutex>
 #include <new>
 
 namespace me {
@@ -17,6 +18,61 @@ void SetLastError(const char *fmt, ...) {
     g_last_error = buffer;
 }
 const char *LastError() { return g_last_error.c_str(); }
+
+namespace {
+// One pool stream per device, created on first use; the pool keeps freed memory (release threshold = max).
+cudaStream_t PoolStream() {
+    static thread_local int cached_device = -1;
+    static thread_local cudaStream_t cached_stream = nullptr;
+    static cudaStream_t streams[64]{};
+    static std::mutex mutex;
+    int device = 0;
+    ME_CUDA(cudaGetDevice(&device));
+    if (device == cached_device) return cached_stream;
+    std::lock_guard<std::mutex> lock(mutex);
+    if (device < 0 || device >= 64) Fail(ME_BAD_ARG, "device ordinal %d out of range", device);
+    if (!streams[device]) {
+        cudaMemPool_t pool;
+        ME_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t threshold = UINT64_MAX;
+        ME_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+        ME_CUDA(cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking));
+    }
+    cached_device = device;
+    cached_stream = streams[device];
+    return cached_stream;
+}
+} // namespace
+
+void *PoolAllocate(size_t bytes) {
+    void *ptr = nullptr;
+    const cudaStream_t s = PoolStream();
+    const cudaError_t err = cudaMallocAsync(&ptr, bytes ? bytes : 1, s);
+    if (err != cudaSuccess) Fail(err == cudaErrorMemoryAllocation ? ME_OUT_OF_MEMORY : ME_CUDA_ERROR, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(err));
+    ME_CUDA(cudaStreamSynchronize(s)); // usable from any stream from here on
+    return ptr;
+}
+void PoolFree(void *ptr) {
+    // Called from destructors: never throws. The device-wide wait is what cudaFree did implicitly.
+    cudaDeviceSynchronize();
+    int device = 0;
+    if (cudaGetDevice(&device) != cudaSuccess) return;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.device != device) {
+        cudaSetDevice(attr.device);
+        cudaDeviceSynchronize();
+        try {
+            cudaFreeAsync(ptr, PoolStream());
+        } catch (...) {
+        }
+        cudaSetDevice(device);
+        return;
+    }
+    try {
+        cudaFreeAsync(ptr, PoolStream());
+    } catch (...) {
+    }
+}
 } // namespace me
 
 struct MeBank {

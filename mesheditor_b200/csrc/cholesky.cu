@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 
 namespace me {
 namespace {
@@ -24,7 +25,7 @@ struct FactorView {
     const uint32_t *SuperFirst, *Rows, *NodeSuper;
     const uint64_t *RowPtr, *PanelOffset, *InvOffset;
     const uint32_t *SegTarget, *SegBegin, *SegEnd;
-    double *L, *Linv, *LinvT;
+    double *L, *Linv, *LinvT, *LT; // LT: the below-diagonal rectangles again, transposed ([row][column]), for the backward sweep
     int *Fail;
 };
 
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kTrsmThreads) PanelTrsmKernel(FactorView v, co
     const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
     double *p0 = v.L + v.PanelOffset[s] + k;
     const double *linv = v.Linv + v.InvOffset[s];
+    double *pt = v.LT + (v.PanelOffset[s] - v.InvOffset[s]);
     const uint32_t row0 = tile.RowTile * kTile, nrows = min(kTile, m - row0);
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, wm = w & 1, wn = w >> 1;
     for (uint32_t idx = t; idx < 128 * 64; idx += kTrsmThreads) {
@@ -179,7 +181,10 @@ __global__ void __launch_bounds__(kTrsmThreads) PanelTrsmKernel(FactorView v, co
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const uint32_t r = 32 * wm + 8 * mi + (lane >> 2), c = 32 * wn + 8 * ni + 2 * (lane & 3) + e;
-                if (r < nrows && c < k) p0[row0 + r + size_t(c) * ld] = acc[mi][ni][e];
+                if (r < nrows && c < k) {
+                    p0[row0 + r + size_t(c) * ld] = acc[mi][ni][e];
+                    pt[size_t(row0 + r) * k + c] = acc[mi][ni][e];
+                }
             }
 }
 
@@ -267,109 +272,180 @@ __global__ void PermuteOutKernel(const double *__restrict__ w, const uint32_t *_
     if (i < 3 * n_nodes) x[i] = w[3 * inv_perm[i / 3] + i % 3];
 }
 
-// The three solve kernels share one load shape: a 64-row x k-column slab (k <= 128) is covered by 256 threads, thread t
-// owning row t & 63 and the 32 columns (t >> 6) + 4 j. All 32 loads of a thread are independent and issued together,
-// so a kernel costs about one L2/HBM round trip instead of k dependent ones: the solves are a chain of ~4 small
-// launches per level, and their latency, not bandwidth, is what the low levels of the tree pay.
+// Load shape shared by the solve tasks: a 64-row x k-column slab (k <= 128) is covered by 256 threads, and every thread
+// issues its 32 loads before using any, so a task costs about one L2/HBM round trip instead of k dependent ones.
 constexpr int kSolveThreads = 256;
 
-// w_S <- T_S w_S for every supernode of one level, T = Linv (forward, lower triangular) or the stored transpose
-// Linv^T (backward, upper triangular). One CTA per supernode.
-template<bool Upper>
-__global__ void __launch_bounds__(kSolveThreads) DiagSolveKernel(FactorView v, const double *__restrict__ tri, const uint32_t *__restrict__ level_supers, double *__restrict__ w) {
-    __shared__ double vs[128], part[4][64];
-    const uint32_t s = level_supers[blockIdx.x], k = PanelColumns(v, s);
-    double *ws = w + size_t(3) * v.SuperFirst[s];
-    const double *mat = tri + v.InvOffset[s];
-    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6;
-    if (t < 128) vs[t] = t < k ? ws[t] : 0.0;
-    __syncthreads();
-    for (uint32_t pass = 0; pass * 64 < k; ++pass) {
-        const uint32_t row = pass * 64 + r;
-        double val[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t c = q + 4 * j;
-            const bool in = row < k && c < k && (Upper ? c >= row : c <= row);
-            val[j] = in ? mat[row + size_t(c) * k] : 0.0;
-        }
-        double sum = 0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum += val[j] * vs[q + 4 * j];
-        part[q][r] = sum;
-        __syncthreads();
-        if (t < 64 && row < k) ws[row] = (part[0][t] + part[1][t]) + (part[2][t] + part[3][t]);
-        __syncthreads();
-    }
-}
-// Forward: w[rows of the tile] -= P_tile * y_S.
-__global__ void __launch_bounds__(kSolveThreads) PanelForwardKernel(FactorView v, const PanelTile *__restrict__ tiles, double *__restrict__ w) {
+// ------------------------------------------------------------------------------------------------ dataflow sweeps
+// A level-synchronous sweep (one or two launches per level of the tree) pays a launch gap and a ramp-up/tail per kernel,
+// ~360 times per sweep on the 1M-tet mesh, and makes every supernode of a level wait for the slowest one: measured
+// 8.2 ms per solve against 2.2 ms of HBM time. The two kernels below run a whole sweep in ONE launch: persistent CTAs
+// take tasks (a diagonal solve, or one panel tile / tile group) from a ticket counter in a topological order and wait
+// only for their own inputs through per-supernode counters. A task's inputs always hold smaller tickets, every ticket
+// holder is resident, so the spin-waits cannot deadlock. Values other CTAs produced are read with ld.global.cg (L2),
+// after the flag that publishes them (written behind a __threadfence).
+__device__ __forceinline__ uint32_t Peek(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+
+struct SweepCounters {
+    uint32_t *Ticket, *Arrived, *Done;
+};
+
+__global__ void __launch_bounds__(kSolveThreads) ForwardSweepKernel(FactorView v, const PanelTile *__restrict__ tasks, uint32_t n_tasks, const uint32_t *__restrict__ target_ptr,
+                                                                    const uint32_t *__restrict__ targets, const uint32_t *__restrict__ expected, SweepCounters c, double *w) {
     __shared__ double ys[128], part[4][64];
-    const PanelTile tile = tiles[blockIdx.x];
-    const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
-    const double *p0 = v.L + v.PanelOffset[s] + k;
+    __shared__ uint32_t s_ticket;
     const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6;
-    if (t < 128) ys[t] = t < k ? w[size_t(3) * v.SuperFirst[s] + t] : 0.0;
-    __syncthreads();
-    const uint32_t row = tile.RowTile * kTile + r;
-    double val[32];
+    for (;;) {
+        __syncthreads();
+        if (t == 0) s_ticket = atomicAdd(c.Ticket, 1u);
+        __syncthreads();
+        const uint32_t id = s_ticket;
+        if (id >= n_tasks) return;
+        const PanelTile task = tasks[id];
+        const uint32_t s = task.Super, k = PanelColumns(v, s);
+        double *ws = w + size_t(3) * v.SuperFirst[s];
+        if (task.RowTile == kDiagTask) {
+            if (t == 0) {
+                const uint32_t need = expected[s];
+                while (Peek(c.Arrived + s) < need) __nanosleep(40);
+                __threadfence();
+            }
+            __syncthreads();
+            if (t < 128) ys[t] = t < k ? __ldcg(ws + t) : 0.0;
+            __syncthreads();
+            const double *mat = v.Linv + v.InvOffset[s];
+            for (uint32_t pass = 0; pass * 64 < k; ++pass) {
+                const uint32_t row = pass * 64 + r;
+                double val[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const uint32_t c = q + 4 * j;
-        val[j] = (row < m && c < k) ? p0[row + size_t(c) * ld] : 0.0;
-    }
-    double sum = 0;
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t col = q + 4 * j;
+                    val[j] = (row < k && col <= row) ? mat[row + size_t(col) * k] : 0.0;
+                }
+                double sum = 0;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) sum += val[j] * ys[q + 4 * j];
-    part[q][r] = sum;
-    __syncthreads();
-    if (t < 64 && row < m) {
-        const uint32_t node = v.Rows[v.RowPtr[s] + row / 3];
-        atomicAdd(w + size_t(3) * node + row % 3, -((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])));
+                for (int j = 0; j < 32; ++j) sum += val[j] * ys[q + 4 * j];
+                part[q][r] = sum;
+                __syncthreads();
+                if (t < 64 && row < k) ws[row] = (part[0][t] + part[1][t]) + (part[2][t] + part[3][t]);
+                __syncthreads();
+            }
+            __threadfence();
+            __syncthreads();
+            if (t == 0) atomicExch(c.Done + s, 1u);
+        } else {
+            if (t == 0) {
+                while (Peek(c.Done + s) == 0) __nanosleep(40);
+                __threadfence();
+            }
+            __syncthreads();
+            const uint32_t m = PanelRows(v, s), ld = k + m;
+            const double *p0 = v.L + v.PanelOffset[s] + k;
+            if (t < 128) ys[t] = t < k ? __ldcg(ws + t) : 0.0;
+            __syncthreads();
+            const uint32_t row = task.RowTile * kTile + r;
+            double val[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t col = q + 4 * j;
+                val[j] = (row < m && col < k) ? p0[row + size_t(col) * ld] : 0.0;
+            }
+            double sum = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += val[j] * ys[q + 4 * j];
+            part[q][r] = sum;
+            __syncthreads();
+            if (t < 64 && row < m) {
+                const uint32_t node = v.Rows[v.RowPtr[s] + row / 3];
+                atomicAdd(w + size_t(3) * node + row % 3, -((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])));
+            }
+            __threadfence();
+            __syncthreads();
+            const uint32_t t0 = target_ptr[id], n_targets = target_ptr[id + 1] - t0;
+            if (t < n_targets) atomicAdd(c.Arrived + targets[t0 + t], 1u);
+        }
     }
 }
-// Backward: w_S -= P_rows^T x[rows] over a run of up to 8 row tiles of one panel. Each warp accumulates 32 rows x 32
-// columns of products per tile and reduces them once at the end with a transposing butterfly (31 shuffles), after which
-// lane L holds the column sum of its L-th column: two atomics per column and CTA instead of two per column and tile.
-__global__ void __launch_bounds__(kSolveThreads) PanelBackwardKernel(FactorView v, const PanelGroup *__restrict__ groups, double *__restrict__ w) {
-    __shared__ double xs[kGroupTiles * kTile];
-    const PanelGroup group = groups[blockIdx.x];
-    const uint32_t s = group.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
-    const double *p0 = v.L + v.PanelOffset[s] + k;
-    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6, lane = t & 31;
-    const uint32_t row0 = group.FirstTile * kTile, n_rows = min(group.Tiles * kTile, m - row0);
-    for (uint32_t i = t; i < group.Tiles * kTile; i += kSolveThreads) {
-        const uint32_t row = row0 + i;
-        xs[i] = i < n_rows ? w[size_t(3) * v.Rows[v.RowPtr[s] + row / 3] + row % 3] : 0.0;
-    }
-    __syncthreads();
-    double val[32];
+
+__global__ void __launch_bounds__(kSolveThreads) BackwardSweepKernel(FactorView v, const PanelGroup *__restrict__ tasks, uint32_t n_tasks, const uint32_t *__restrict__ dep_ptr,
+                                                                     const uint32_t *__restrict__ deps, const uint32_t *__restrict__ expected, SweepCounters c, double *w) {
+    __shared__ double xs[kGroupTiles * kTile], part[4][64];
+    __shared__ uint32_t s_ticket;
+    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6;
+    for (;;) {
+        __syncthreads();
+        if (t == 0) s_ticket = atomicAdd(c.Ticket, 1u);
+        __syncthreads();
+        const uint32_t id = s_ticket;
+        if (id >= n_tasks) return;
+        const PanelGroup task = tasks[id];
+        const uint32_t s = task.Super, k = PanelColumns(v, s);
+        double *ws = w + size_t(3) * v.SuperFirst[s];
+        if (task.Tiles == 0) {
+            if (t == 0) {
+                const uint32_t need = expected[s];
+                while (Peek(c.Arrived + s) < need) __nanosleep(40);
+                __threadfence();
+            }
+            __syncthreads();
+            if (t < 128) xs[t] = t < k ? __ldcg(ws + t) : 0.0;
+            __syncthreads();
+            const double *mat = v.LinvT + v.InvOffset[s];
+            for (uint32_t pass = 0; pass * 64 < k; ++pass) {
+                const uint32_t row = pass * 64 + r;
+                double val[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) val[j] = 0.0;
-    for (uint32_t tile = 0; tile < group.Tiles; ++tile) {
-        const uint32_t local = tile * kTile + r, row = row0 + local;
-        const double x = xs[local];
-        double a[32];
+                for (int j = 0; j < 32; ++j) {
+                    const uint32_t col = q + 4 * j;
+                    val[j] = (row < k && col < k && col >= row) ? mat[row + size_t(col) * k] : 0.0;
+                }
+                double sum = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const uint32_t c = q + 4 * j;
-            a[j] = (local < n_rows && c < k) ? p0[row + size_t(c) * ld] : 0.0;
+                for (int j = 0; j < 32; ++j) sum += val[j] * xs[q + 4 * j];
+                part[q][r] = sum;
+                __syncthreads();
+                if (t < 64 && row < k) ws[row] = (part[0][t] + part[1][t]) + (part[2][t] + part[3][t]);
+                __syncthreads();
+            }
+            __threadfence();
+            __syncthreads();
+            if (t == 0) atomicExch(c.Done + s, 1u);
+        } else {
+            const uint32_t d0 = dep_ptr[id], n_deps = dep_ptr[id + 1] - d0;
+            if (t < n_deps) {
+                const uint32_t *flag = c.Done + deps[d0 + t];
+                while (Peek(flag) == 0) __nanosleep(40);
+                __threadfence();
+            }
+            __syncthreads();
+            // w_S -= P^T x over the group's rows, read from the TRANSPOSED copy of the panel ([row][column]): thread =
+            // column (two row halves per tile), so the sum over rows stays in one register and the loads are coalesced.
+            const uint32_t m = PanelRows(v, s);
+            const double *pt = v.LT + (v.PanelOffset[s] - v.InvOffset[s]);
+            const uint32_t row0 = task.FirstTile * kTile, n_rows = min(task.Tiles * kTile, m - row0);
+            for (uint32_t i = t; i < task.Tiles * kTile; i += kSolveThreads) {
+                const uint32_t row = row0 + i;
+                xs[i] = i < n_rows ? __ldcg(w + size_t(3) * v.Rows[v.RowPtr[s] + row / 3] + row % 3) : 0.0;
+            }
+            __syncthreads();
+            const uint32_t col = t & 127, half = t >> 7;
+            double sum = 0;
+            for (uint32_t tile = 0; tile < task.Tiles; ++tile) {
+                const uint32_t local0 = tile * kTile + half * 32;
+                double a[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) a[j] = (local0 + j < n_rows && col < k) ? pt[size_t(row0 + local0 + j) * k + col] : 0.0;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum += a[j] * xs[local0 + j];
+            }
+            reinterpret_cast<double *>(part)[half * 128 + col] = sum;
+            __syncthreads();
+            if (t < 128 && t < k) atomicAdd(ws + t, -(reinterpret_cast<double *>(part)[t] + reinterpret_cast<double *>(part)[128 + t]));
+            __threadfence();
+            __syncthreads();
+            if (t == 0) atomicAdd(c.Arrived + s, 1u);
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) val[j] += a[j] * x;
     }
-#pragma unroll
-    for (int o = 16, n = 32; o >= 1; o >>= 1, n >>= 1) {
-        const bool upper = (lane & o) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const double send = upper ? val[i] : val[i + n / 2];
-            const double keep = upper ? val[i + n / 2] : val[i];
-            val[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-        }
-    }
-    const uint32_t c = q + 4 * lane;
-    if (c < k) atomicAdd(w + size_t(3) * v.SuperFirst[s] + c, -val[0]);
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 rate probes
@@ -445,11 +521,29 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     DPanelOffset.Upload(Sym.PanelOffset, s);
     DInvOffset.Upload(Sym.InvOffset, s);
     DPanelTiles.Upload(Sym.PanelTiles, s);
-    DPanelGroups.Upload(Sym.PanelGroups, s);
+    DFwdTasks.Upload(Sym.FwdTasks, s);
+    DFwdTargetPtr.Upload(Sym.FwdTargetPtr, s);
+    DFwdTargets.Upload(Sym.FwdTargets, s);
+    DFwdExpected.Upload(Sym.FwdExpected, s);
+    DBwdTasks.Upload(Sym.BwdTasks, s);
+    DBwdDepPtr.Upload(Sym.BwdDepPtr, s);
+    DBwdDeps.Upload(Sym.BwdDeps, s);
+    DBwdExpected.Upload(Sym.BwdExpected, s);
+    DCounters.Reserve(size_t(4) * Sym.NumSuper + 2);
+    {
+        int device = 0, sms = 0, fwd = 0, bwd = 0;
+        ME_CUDA(cudaGetDevice(&device));
+        ME_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd, ForwardSweepKernel, kSolveThreads, 0));
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, BackwardSweepKernel, kSolveThreads, 0));
+        if (fwd < 1 || bwd < 1) Fail(ME_CUDA_ERROR, "sweep kernels do not fit an SM");
+        FwdGrid = uint32_t(sms * fwd), BwdGrid = uint32_t(sms * bwd); // every CTA resident: the spin-waits rely on it
+    }
     DUpdateTiles.Upload(Sym.UpdateTiles, s);
     L.Reserve(Sym.FactorNonZeros);
     Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
     LinvT.Reserve(Sym.InvOffset[Sym.NumSuper]);
+    LT.Reserve(Sym.FactorNonZeros - Sym.InvOffset[Sym.NumSuper] + 1);
     Work.Reserve(fem.N);
     DFail.Reserve(1);
     for (auto &e : Ev) ME_CUDA(cudaEventCreate(&e));
@@ -467,13 +561,12 @@ SparseCholesky::~SparseCholesky() {
     cudaSetDevice(Fem.Device);
     for (auto &e : Ev)
         if (e) cudaEventDestroy(e);
-    if (SolveGraph) cudaGraphExecDestroy(SolveGraph);
 }
 
 void SparseCholesky::Factorize(double sigma) {
     ME_CUDA(cudaSetDevice(Fem.Device));
     auto s = Fem.Stream;
-    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, DFail.Ptr};
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};
     ME_CUDA(cudaEventRecord(Ev[0], s));
     ME_CUDA(cudaMemsetAsync(DFail.Ptr, 0, sizeof(int), s));
     ME_CUDA(cudaMemsetAsync(L.Ptr, 0, Sym.FactorNonZeros * sizeof(double), s));
@@ -509,46 +602,22 @@ void SparseCholesky::Factorize(double sigma) {
     Factored = true;
 }
 
-void SparseCholesky::RecordSolveLevels(cudaStream_t s, uint32_t &launches) {
-    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, DFail.Ptr};
-    double *w = Work.Ptr;
-    for (uint32_t l = 0; l < Sym.NumLevels; ++l) {
-        const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
-        DiagSolveKernel<false><<<n_super, kSolveThreads, 0, s>>>(v, Linv.Ptr, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
-        const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
-        if (n_panel) PanelForwardKernel<<<uint32_t(n_panel), kSolveThreads, 0, s>>>(v, DPanelTiles.Ptr + Sym.PanelTilePtr[l], w);
-        launches += 1 + (n_panel != 0);
-    }
-    for (uint32_t l = Sym.NumLevels; l-- > 0;) {
-        const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
-        const uint64_t n_panel = Sym.PanelTilePtr[l + 1] - Sym.PanelTilePtr[l];
-        const uint64_t n_group = Sym.PanelGroupPtr[l + 1] - Sym.PanelGroupPtr[l];
-        if (n_group) PanelBackwardKernel<<<uint32_t(n_group), kSolveThreads, 0, s>>>(v, DPanelGroups.Ptr + Sym.PanelGroupPtr[l], w);
-        DiagSolveKernel<true><<<n_super, kSolveThreads, 0, s>>>(v, LinvT.Ptr, DLevelOrder.Ptr + Sym.LevelPtr[l], w);
-        launches += 1 + (n_panel != 0);
-    }
-}
-
 void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     if (!Factored) Fail(ME_BAD_ARG, "Solve before Factorize");
     ME_CUDA(cudaSetDevice(Fem.Device));
     auto s = Fem.Stream;
-    const uint32_t n = Fem.N;
-    if (!SolveGraph) {
-        // The level sweep is the same ~4 launches per level for every right-hand side: capture it once, replay it.
-        cudaGraph_t graph = nullptr;
-        GraphLaunches = 0;
-        ME_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        RecordSolveLevels(s, GraphLaunches);
-        ME_CUDA(cudaStreamEndCapture(s, &graph));
-        ME_CUDA(cudaGraphInstantiate(&SolveGraph, graph, 0));
-        cudaGraphDestroy(graph);
-    }
+    const uint32_t n = Fem.N, ns = Sym.NumSuper;
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};
+    uint32_t *counters = DCounters.Ptr;
+    const SweepCounters fwd{counters + 4 * size_t(ns), counters, counters + ns}, bwd{counters + 4 * size_t(ns) + 1, counters + 2 * size_t(ns), counters + 3 * size_t(ns)};
     for (uint32_t rhs = 0; rhs < width; ++rhs) {
         PermuteInKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr);
-        ME_CUDA(cudaGraphLaunch(SolveGraph, s));
+        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
+        ForwardSweepKernel<<<FwdGrid, kSolveThreads, 0, s>>>(v, DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdTargetPtr.Ptr, DFwdTargets.Ptr, DFwdExpected.Ptr, fwd, Work.Ptr);
+        BackwardSweepKernel<<<BwdGrid, kSolveThreads, 0, s>>>(v, DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), DBwdDepPtr.Ptr, DBwdDeps.Ptr, DBwdExpected.Ptr, bwd, Work.Ptr);
+        Stats.KernelLaunches += 2;
         PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, DInvPerm.Ptr, Fem.NodeCount, x + size_t(rhs) * n);
-        Stats.KernelLaunches += GraphLaunches + 2;
+        Stats.KernelLaunches += 2;
     }
 }
 

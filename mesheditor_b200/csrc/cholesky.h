@@ -45,12 +45,12 @@ private:
     DeviceBuffer<uint32_t> DSuperFirst, DRows, DNodeSuper, DInvPerm, DPerm, DSegTarget, DSegBegin, DSegEnd, DLevelOrder;
     DeviceBuffer<uint64_t> DRowPtr, DPanelOffset, DInvOffset;
     DeviceBuffer<PanelTile> DPanelTiles;
-    DeviceBuffer<PanelGroup> DPanelGroups;
+    DeviceBuffer<PanelGroup> DBwdTasks;
+    DeviceBuffer<PanelTile> DFwdTasks;
+    DeviceBuffer<uint32_t> DFwdTargetPtr, DFwdTargets, DFwdExpected, DBwdDepPtr, DBwdDeps, DBwdExpected, DCounters;
+    uint32_t FwdGrid{0}, BwdGrid{0};
     DeviceBuffer<UpdateTile> DUpdateTiles;
-    void RecordSolveLevels(cudaStream_t, uint32_t &launches);
-    DeviceBuffer<double> L, Linv, LinvT, Work;
-    cudaGraphExec_t SolveGraph{nullptr};
-    uint32_t GraphLaunches{0};
+    DeviceBuffer<double> L, Linv, LinvT, LT, Work;
     DeviceBuffer<int> DFail;
     cudaEvent_t Ev[4]{};
     bool Factored{false};

@@ -56,6 +56,13 @@ MeStatus Guard(Body &&body) {
     }
 }
 
+// Device allocations come from the device's stream-ordered memory pool with an unbounded release threshold: a solve
+// frees ~10 GB of panels and basis vectors when it returns, and handing those pages back to the driver (cudaFree) and
+// mapping them again on the next call (cudaMalloc) costs far more than the assembly they bracket. Release() first waits
+// for the device, which keeps the old cudaFree semantics (no kernel can still be using the block).
+void *PoolAllocate(size_t bytes);
+void PoolFree(void *ptr);
+
 // Device buffer that only ever grows; contents are not preserved across a growth unless asked.
 template<typename T>
 struct DeviceBuffer {
@@ -68,14 +75,14 @@ struct DeviceBuffer {
     ~DeviceBuffer() { Release(); }
 
     void Release() {
-        if (Ptr) cudaFree(Ptr);
+        if (Ptr) PoolFree(Ptr);
         Ptr = nullptr;
         Capacity = 0;
     }
     void Reserve(size_t count) {
         if (count <= Capacity) return;
         Release();
-        ME_CUDA(cudaMalloc(reinterpret_cast<void **>(&Ptr), count * sizeof(T)));
+        Ptr = static_cast<T *>(PoolAllocate(count * sizeof(T)));
         Capacity = count;
     }
     void Upload(const T *host, size_t count, cudaStream_t stream) {

@@ -20,7 +20,7 @@ namespace me {
 bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) {
     d.assign(n, 0.0);
     if (n == 0) return true;
-    std::vector<double> e(n, 0.0);
+    std::vector<double> e(n, 0.0), scratch(n, 0.0);
     auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
     // Householder reduction to tridiagonal form, accumulating the transformation.
     for (uint32_t i = n - 1; i >= 1; --i) {
@@ -40,12 +40,22 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
                 h -= f * g;
                 A(i, l) = f - g;
                 f = 0;
+                // e = A u / h with A symmetric and only its lower triangle stored: both sweeps run along contiguous rows.
+                for (uint32_t j = 0; j <= l; ++j) e[j] = 0;
+                const double *u = &a[size_t(i) * n];
+                for (uint32_t j = 0; j <= l; ++j) {
+                    const double *row = &a[size_t(j) * n];
+                    const double uj = u[j];
+                    double dot = 0;
+                    for (uint32_t k = 0; k < j; ++k) {
+                        dot += row[k] * u[k];
+                        e[k] += row[k] * uj;
+                    }
+                    e[j] += dot + row[j] * uj;
+                }
                 for (uint32_t j = 0; j <= l; ++j) {
                     A(j, i) = A(i, j) / h;
-                    g = 0;
-                    for (uint32_t k = 0; k <= j; ++k) g += A(j, k) * A(i, k);
-                    for (uint32_t k = j + 1; k <= l; ++k) g += A(k, j) * A(i, k);
-                    e[j] = g / h;
+                    e[j] /= h;
                     f += e[j] * A(i, j);
                 }
                 const double hh = f / (h + h);
@@ -62,17 +72,28 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
     e[0] = 0;
     for (uint32_t i = 0; i < n; ++i) {
         if (d[i] != 0.0 && i > 0) {
-            for (uint32_t j = 0; j < i; ++j) {
-                double g = 0;
-                for (uint32_t k = 0; k < i; ++k) g += A(i, k) * A(k, j);
-                for (uint32_t k = 0; k < i; ++k) A(k, j) -= g * A(k, i);
+            // g = row_i * Q[0..i, 0..i), then Q[0..i, 0..i) -= Q[0..i, i] * g: contiguous row sweeps.
+            std::vector<double> &g = scratch;
+            std::fill(g.begin(), g.begin() + i, 0.0);
+            for (uint32_t k = 0; k < i; ++k) {
+                const double aik = A(i, k);
+                const double *row = &a[size_t(k) * n];
+                for (uint32_t j = 0; j < i; ++j) g[j] += aik * row[j];
+            }
+            for (uint32_t k = 0; k < i; ++k) {
+                const double aki = A(k, i);
+                double *row = &a[size_t(k) * n];
+                for (uint32_t j = 0; j < i; ++j) row[j] -= g[j] * aki;
             }
         }
         d[i] = A(i, i);
         A(i, i) = 1;
         for (uint32_t j = 0; j < i; ++j) A(j, i) = A(i, j) = 0;
     }
-    // Implicit QL on the tridiagonal matrix.
+    // Implicit QL on the tridiagonal matrix. The rotations mix two eigenvector columns at a time: work on the transpose
+    // so that they are contiguous rows (this loop is ~3 n^3 flops and sits between every two restarts).
+    for (uint32_t r = 0; r < n; ++r)
+        for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
     for (uint32_t i = 1; i < n; ++i) e[i - 1] = e[i];
     e[n - 1] = 0;
     const double eps = std::numeric_limits<double>::epsilon();
@@ -105,10 +126,11 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
                     r = (d[i] - g) * s + 2.0 * c * b;
                     d[i + 1] = g + (p = s * r);
                     g = c * r - b;
+                    double *zi = &a[size_t(i) * n], *zi1 = &a[size_t(i + 1) * n];
                     for (uint32_t k = 0; k < n; ++k) {
-                        f = A(k, uint32_t(i) + 1);
-                        A(k, uint32_t(i) + 1) = s * A(k, uint32_t(i)) + c * f;
-                        A(k, uint32_t(i)) = c * A(k, uint32_t(i)) - s * f;
+                        const double fk = zi1[k];
+                        zi1[k] = s * zi[k] + c * fk;
+                        zi[k] = c * zi[k] - s * fk;
                     }
                 }
                 if (r == 0.0 && i >= int64_t(l)) continue;
@@ -118,6 +140,8 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
             }
         } while (m != l);
     }
+    for (uint32_t r = 0; r < n; ++r)
+        for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
     return true;
 }
 

@@ -248,6 +248,57 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
         sym.PanelGroupPtr[l + 1] = sym.PanelGroups.size();
         sym.UpdateTilePtr[l + 1] = sym.UpdateTiles.size();
     }
+    // Dataflow schedules of the solves. Ticket order = level order (height above the leaves), NOT elimination order:
+    // both are topological, but the post-order would walk one subtree's separator chains at a time, while the level
+    // order keeps the chains of all subtrees of the same height in flight together.
+    sym.FwdExpected.assign(ns, 0);
+    sym.BwdExpected.assign(ns, 0);
+    auto targets_of = [&](uint32_t s, uint32_t first_tile, uint32_t tiles, std::vector<uint32_t> &out) {
+        const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0;
+        const uint64_t first = (uint64_t(first_tile) * kTile) / 3, last = std::min<uint64_t>(nodes, (uint64_t(first_tile + tiles) * kTile + 2) / 3);
+        uint32_t prev = UINT32_MAX;
+        for (uint64_t j = first; j < last; ++j) {
+            const uint32_t target = sym.NodeSuper[sym.Rows[r0 + j]];
+            if (target != prev) {
+                out.push_back(target);
+                prev = target;
+            }
+        }
+    };
+    sym.FwdTargetPtr.push_back(0);
+    for (uint32_t l = 0; l < sym.NumLevels; ++l) {
+        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
+            sym.FwdTasks.push_back({sym.LevelOrder[i], kDiagTask});
+            sym.FwdTargetPtr.push_back(uint32_t(sym.FwdTargets.size()));
+        }
+        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
+            const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
+            for (uint32_t t = 0; t * kTile < m; ++t) {
+                sym.FwdTasks.push_back({s, t});
+                const size_t before = sym.FwdTargets.size();
+                targets_of(s, t, 1, sym.FwdTargets);
+                for (size_t j = before; j < sym.FwdTargets.size(); ++j) ++sym.FwdExpected[sym.FwdTargets[j]];
+                sym.FwdTargetPtr.push_back(uint32_t(sym.FwdTargets.size()));
+            }
+        }
+    }
+    sym.BwdDepPtr.push_back(0);
+    for (uint32_t l = sym.NumLevels; l-- > 0;) {
+        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
+            const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]), n_tiles = (m + kTile - 1) / kTile;
+            for (uint32_t t = 0; t < n_tiles; t += kGroupTiles) {
+                const uint32_t tiles = std::min(kGroupTiles, n_tiles - t);
+                sym.BwdTasks.push_back({s, t, tiles});
+                ++sym.BwdExpected[s];
+                targets_of(s, t, tiles, sym.BwdDeps);
+                sym.BwdDepPtr.push_back(uint32_t(sym.BwdDeps.size()));
+            }
+        }
+        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
+            sym.BwdTasks.push_back({sym.LevelOrder[i], 0, 0});
+            sym.BwdDepPtr.push_back(uint32_t(sym.BwdDeps.size()));
+        }
+    }
     sym.StructureSeconds = Now() - t1;
     return sym;
 }

@@ -28,6 +28,7 @@ struct PanelGroup {
     uint32_t Super, FirstTile, Tiles;
 };
 constexpr uint32_t kGroupTiles = 8;
+constexpr uint32_t kDiagTask = 0xFFFFFFFFu;
 
 struct Symbolic {
     uint32_t NodeCount{0}, NumSuper{0}, NumLevels{0};
@@ -48,6 +49,14 @@ struct Symbolic {
     std::vector<uint64_t> PanelGroupPtr;      // [NumLevels+1]
     std::vector<PanelGroup> PanelGroups;
     std::vector<UpdateTile> UpdateTiles;
+    // Dataflow schedules of the triangular solves (cholesky.cu SweepKernel): tasks in a topological order, taken by
+    // persistent CTAs through a ticket counter and gated by per-supernode arrival counters instead of level barriers.
+    std::vector<PanelTile> FwdTasks;          // per supernode ascending: {s, kDiagTask} then its row tiles
+    std::vector<uint32_t> FwdTargetPtr, FwdTargets; // per task: ancestors whose right-hand side the tile updates
+    std::vector<uint32_t> FwdExpected;        // [NumSuper] tiles that must arrive before the supernode's diagonal solve
+    std::vector<PanelGroup> BwdTasks;         // per supernode descending: its tile groups, then {s, 0, 0} = diagonal solve
+    std::vector<uint32_t> BwdDepPtr, BwdDeps; // per task: ancestors whose solution the group reads
+    std::vector<uint32_t> BwdExpected;        // [NumSuper] groups that must arrive before the supernode's diagonal solve
     uint64_t FactorNonZeros{0};               // scalars stored in the panels
     double FactorFlops{0};
     uint32_t MaxPanelColumns{0}, MaxPanelRows{0};
