@@ -278,172 +278,143 @@ constexpr int kSolveThreads = 256;
 
 // ------------------------------------------------------------------------------------------------ dataflow sweeps
 // A level-synchronous sweep (one or two launches per level of the tree) pays a launch gap and a ramp-up/tail per kernel,
-// ~360 times per sweep on the 1M-tet mesh, and makes every supernode of a level wait for the slowest one: measured
-// 8.2 ms per solve against 2.2 ms of HBM time. The two kernels below run a whole sweep in ONE launch: persistent CTAs
-// take tasks (a diagonal solve, or one panel tile / tile group) from a ticket counter in a topological order and wait
-// only for their own inputs through per-supernode counters. A task's inputs always hold smaller tickets, every ticket
-// holder is resident, so the spin-waits cannot deadlock. Values other CTAs produced are read with ld.global.cg (L2),
-// after the flag that publishes them (written behind a __threadfence).
+// ~360 times per sweep on the 1M-tet mesh, and makes every supernode of a level wait for the slowest one. Here a whole
+// sweep is ONE launch of persistent CTAs:
+//   * work is cut into uniform slabs of 32 rows x k columns (of a diagonal block's inverse, or of a panel) listed in a
+//     topological order (level by level); CTAs take them from a ticket counter;
+//   * a task waits only for its own inputs, through per-supernode counters: a panel slab for its supernode's diagonal
+//     solve, a diagonal solve for every slab that updates it. A task's inputs always hold smaller tickets and every CTA
+//     is resident, so the spin-waits cannot deadlock;
+//   * a task is a short chain of dependent round trips (ticket, flag, vector, 32 KB of matrix, atomics, fence), so what
+//     keeps HBM busy is the number of chains in flight: the CTAs are small (128 threads, every thread issues its 32 loads
+//     before using any) and five of them share an SM;
+//   * values produced by other CTAs are read with ld.global.cg after the counter that publishes them (written behind
+//     a __threadfence).
+// Forward: `acc` holds the right-hand side that panel slabs update, diagonal slabs write y into `out`.
+// Backward: `acc` holds y, panel slabs subtract P^T x from it, diagonal slabs write x into `out`.
 __device__ __forceinline__ uint32_t Peek(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 
-struct SweepCounters {
+struct SweepArgs {
+    const SweepTask *Tasks;
+    uint32_t NumTasks;
+    const uint32_t *Links, *LinkNeed; // ancestors updated (forward) / read (backward, with their diagonal-slab counts)
     uint32_t *Ticket, *Arrived, *Done;
+    const uint32_t *Rows;             // below-diagonal node lists of all supernodes
+    const double *Diag, *Panel;       // Linv + L (forward) or Linv^T + LT (backward)
+    double *Acc, *Out;
 };
+constexpr int kSweepThreads = 128;
+constexpr int kSweepCtasPerSm = 5;
 
-__global__ void __launch_bounds__(kSolveThreads) ForwardSweepKernel(FactorView v, const PanelTile *__restrict__ tasks, uint32_t n_tasks, const uint32_t *__restrict__ target_ptr,
-                                                                    const uint32_t *__restrict__ targets, const uint32_t *__restrict__ expected, SweepCounters c, double *w) {
-    __shared__ double ys[128], part[4][64];
-    __shared__ uint32_t s_ticket;
-    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6;
+template<bool Backward>
+__global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(SweepArgs a) {
+    __shared__ double vec[128], part[kSweepThreads];
+    __shared__ SweepTask s_task;
+    __shared__ uint32_t s_id;
+    const uint32_t t = threadIdx.x, r = t & 31, q = t >> 5;
+    // Warp 0 keeps the NEXT ticket and its 64-byte descriptor (8 lanes x 8 bytes) in registers, fetched while the
+    // current task runs, so that neither the ticket atomic nor the descriptor load sits on the per-task chain.
+    uint32_t next_id = 0;
+    uint64_t next_word = 0;
+    auto prefetch_next = [&] {
+        if (t < 32) {
+            if (t == 0) next_id = atomicAdd(a.Ticket, 1u);
+            next_id = __shfl_sync(0xffffffffu, next_id, 0);
+            if (t < 8 && next_id < a.NumTasks) next_word = reinterpret_cast<const uint64_t *>(a.Tasks + next_id)[t];
+        }
+    };
+    prefetch_next();
     for (;;) {
         __syncthreads();
-        if (t == 0) s_ticket = atomicAdd(c.Ticket, 1u);
+        if (t < 8) reinterpret_cast<uint64_t *>(&s_task)[t] = next_word;
+        if (t == 0) s_id = next_id;
         __syncthreads();
-        const uint32_t id = s_ticket;
-        if (id >= n_tasks) return;
-        const PanelTile task = tasks[id];
-        const uint32_t s = task.Super, k = PanelColumns(v, s);
-        double *ws = w + size_t(3) * v.SuperFirst[s];
-        if (task.RowTile == kDiagTask) {
-            if (t == 0) {
-                const uint32_t need = expected[s];
-                while (Peek(c.Arrived + s) < need) __nanosleep(40);
-                __threadfence();
-            }
-            __syncthreads();
-            if (t < 128) ys[t] = t < k ? __ldcg(ws + t) : 0.0;
-            __syncthreads();
-            const double *mat = v.Linv + v.InvOffset[s];
-            for (uint32_t pass = 0; pass * 64 < k; ++pass) {
-                const uint32_t row = pass * 64 + r;
-                double val[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t col = q + 4 * j;
-                    val[j] = (row < k && col <= row) ? mat[row + size_t(col) * k] : 0.0;
-                }
-                double sum = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum += val[j] * ys[q + 4 * j];
-                part[q][r] = sum;
-                __syncthreads();
-                if (t < 64 && row < k) ws[row] = (part[0][t] + part[1][t]) + (part[2][t] + part[3][t]);
-                __syncthreads();
-            }
-            __threadfence();
-            __syncthreads();
-            if (t == 0) atomicExch(c.Done + s, 1u);
-        } else {
-            if (t == 0) {
-                while (Peek(c.Done + s) == 0) __nanosleep(40);
-                __threadfence();
-            }
-            __syncthreads();
-            const uint32_t m = PanelRows(v, s), ld = k + m;
-            const double *p0 = v.L + v.PanelOffset[s] + k;
-            if (t < 128) ys[t] = t < k ? __ldcg(ws + t) : 0.0;
-            __syncthreads();
-            const uint32_t row = task.RowTile * kTile + r;
-            double val[32];
+        const uint32_t id = s_id;
+        if (id >= a.NumTasks) return;
+        const SweepTask task = s_task;
+        const uint32_t k = task.K;
+        double val[32];
+        if (task.Kind == 0) {
+            // out_S[slab rows] = T_S[slab rows, :] acc_S once every contribution to acc_S has arrived. The matrix slab
+            // does not depend on anything: it is requested before the wait.
+            const double *mat = a.Diag + task.Base;
+            const uint32_t row = task.Row0 + r;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const uint32_t col = q + 4 * j;
-                val[j] = (row < m && col < k) ? p0[row + size_t(col) * ld] : 0.0;
+                const bool in = row < k && col < k && (Backward ? col >= row : col <= row);
+                val[j] = in ? mat[row + size_t(col) * k] : 0.0;
             }
-            double sum = 0;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum += val[j] * ys[q + 4 * j];
-            part[q][r] = sum;
-            __syncthreads();
-            if (t < 64 && row < m) {
-                const uint32_t node = v.Rows[v.RowPtr[s] + row / 3];
-                atomicAdd(w + size_t(3) * node + row % 3, -((part[0][t] + part[1][t]) + (part[2][t] + part[3][t])));
-            }
-            __threadfence();
-            __syncthreads();
-            const uint32_t t0 = target_ptr[id], n_targets = target_ptr[id + 1] - t0;
-            if (t < n_targets) atomicAdd(c.Arrived + targets[t0 + t], 1u);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(kSolveThreads) BackwardSweepKernel(FactorView v, const PanelGroup *__restrict__ tasks, uint32_t n_tasks, const uint32_t *__restrict__ dep_ptr,
-                                                                     const uint32_t *__restrict__ deps, const uint32_t *__restrict__ expected, SweepCounters c, double *w) {
-    __shared__ double xs[kGroupTiles * kTile], part[4][64];
-    __shared__ uint32_t s_ticket;
-    const uint32_t t = threadIdx.x, r = t & 63, q = t >> 6;
-    for (;;) {
-        __syncthreads();
-        if (t == 0) s_ticket = atomicAdd(c.Ticket, 1u);
-        __syncthreads();
-        const uint32_t id = s_ticket;
-        if (id >= n_tasks) return;
-        const PanelGroup task = tasks[id];
-        const uint32_t s = task.Super, k = PanelColumns(v, s);
-        double *ws = w + size_t(3) * v.SuperFirst[s];
-        if (task.Tiles == 0) {
+            prefetch_next();
             if (t == 0) {
-                const uint32_t need = expected[s];
-                while (Peek(c.Arrived + s) < need) __nanosleep(40);
+                while (Peek(a.Arrived + task.Super) < task.Need) __nanosleep(32);
                 __threadfence();
             }
             __syncthreads();
-            if (t < 128) xs[t] = t < k ? __ldcg(ws + t) : 0.0;
+            vec[t] = t < k ? __ldcg(a.Acc + task.VecOffset + t) : 0.0;
             __syncthreads();
-            const double *mat = v.LinvT + v.InvOffset[s];
-            for (uint32_t pass = 0; pass * 64 < k; ++pass) {
-                const uint32_t row = pass * 64 + r;
-                double val[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const uint32_t col = q + 4 * j;
-                    val[j] = (row < k && col < k && col >= row) ? mat[row + size_t(col) * k] : 0.0;
-                }
-                double sum = 0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum += val[j] * xs[q + 4 * j];
-                part[q][r] = sum;
-                __syncthreads();
-                if (t < 64 && row < k) ws[row] = (part[0][t] + part[1][t]) + (part[2][t] + part[3][t]);
-                __syncthreads();
-            }
-            __threadfence();
-            __syncthreads();
-            if (t == 0) atomicExch(c.Done + s, 1u);
-        } else {
-            const uint32_t d0 = dep_ptr[id], n_deps = dep_ptr[id + 1] - d0;
-            if (t < n_deps) {
-                const uint32_t *flag = c.Done + deps[d0 + t];
-                while (Peek(flag) == 0) __nanosleep(40);
-                __threadfence();
-            }
-            __syncthreads();
-            // w_S -= P^T x over the group's rows, read from the TRANSPOSED copy of the panel ([row][column]): thread =
-            // column (two row halves per tile), so the sum over rows stays in one register and the loads are coalesced.
-            const uint32_t m = PanelRows(v, s);
-            const double *pt = v.LT + (v.PanelOffset[s] - v.InvOffset[s]);
-            const uint32_t row0 = task.FirstTile * kTile, n_rows = min(task.Tiles * kTile, m - row0);
-            for (uint32_t i = t; i < task.Tiles * kTile; i += kSolveThreads) {
-                const uint32_t row = row0 + i;
-                xs[i] = i < n_rows ? __ldcg(w + size_t(3) * v.Rows[v.RowPtr[s] + row / 3] + row % 3) : 0.0;
-            }
-            __syncthreads();
-            const uint32_t col = t & 127, half = t >> 7;
             double sum = 0;
-            for (uint32_t tile = 0; tile < task.Tiles; ++tile) {
-                const uint32_t local0 = tile * kTile + half * 32;
-                double a[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) a[j] = (local0 + j < n_rows && col < k) ? pt[size_t(row0 + local0 + j) * k + col] : 0.0;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) sum += a[j] * xs[local0 + j];
-            }
-            reinterpret_cast<double *>(part)[half * 128 + col] = sum;
+            for (int j = 0; j < 32; ++j) sum += val[j] * vec[q + 4 * j];
+            part[t] = sum;
             __syncthreads();
-            if (t < 128 && t < k) atomicAdd(ws + t, -(reinterpret_cast<double *>(part)[t] + reinterpret_cast<double *>(part)[128 + t]));
+            if (t < 32 && row < k) a.Out[task.VecOffset + row] = (part[t] + part[32 + t]) + (part[64 + t] + part[96 + t]);
             __threadfence();
             __syncthreads();
-            if (t == 0) atomicAdd(c.Arrived + s, 1u);
+            if (t == 0) atomicAdd(a.Done + task.Super, 1u);
+        } else if constexpr (!Backward) {
+            // acc[slab rows] -= P_slab out_S once out_S is complete. Panel: column-major, leading dimension k + m.
+            const uint32_t row = task.Row0 + r;
+            const double *p0 = a.Panel + task.Base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t col = q + 4 * j;
+                val[j] = (row < task.Limit && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
+            }
+            uint32_t node = 0, link = 0;
+            if (t < 32 && row < task.Limit) node = a.Rows[task.RowsBase + row / 3];
+            if (t < task.LinkCount) link = a.Links[task.LinkBegin + t];
+            prefetch_next();
+            if (t == 0) {
+                while (Peek(a.Done + task.Super) < task.Need) __nanosleep(32);
+                __threadfence();
+            }
+            __syncthreads();
+            vec[t] = t < k ? __ldcg(a.Out + task.VecOffset + t) : 0.0;
+            __syncthreads();
+            double sum = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += val[j] * vec[q + 4 * j];
+            part[t] = sum;
+            __syncthreads();
+            if (t < 32 && row < task.Limit) atomicAdd(a.Acc + size_t(3) * node + row % 3, -((part[t] + part[32 + t]) + (part[64 + t] + part[96 + t])));
+            __threadfence();
+            __syncthreads();
+            if (t < task.LinkCount) atomicAdd(a.Arrived + link, 1u);
+        } else {
+            // acc_S -= P_slab^T out[slab rows] once the ancestors owning those rows are solved. Read from the transposed
+            // panel copy ([row][column]): thread = column, so the sum over the slab's rows stays in one register.
+            const double *pt = a.Panel + task.Base;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) val[j] = (task.Row0 + j < task.Limit && t < k) ? pt[size_t(task.Row0 + j) * k + t] : 0.0;
+            uint32_t node = 0;
+            if (t < kSolveRows && task.Row0 + t < task.Limit) node = a.Rows[task.RowsBase + (task.Row0 + t) / 3];
+            prefetch_next();
+            if (t < task.LinkCount) {
+                const uint32_t target = a.Links[task.LinkBegin + t], need = a.LinkNeed[task.LinkBegin + t];
+                while (Peek(a.Done + target) < need) __nanosleep(32);
+                __threadfence();
+            }
+            __syncthreads();
+            if (t < kSolveRows) vec[t] = task.Row0 + t < task.Limit ? __ldcg(a.Out + size_t(3) * node + (task.Row0 + t) % 3) : 0.0;
+            __syncthreads();
+            double sum = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += val[j] * vec[j];
+            if (t < k) atomicAdd(a.Acc + task.VecOffset + t, -sum);
+            __threadfence();
+            __syncthreads();
+            if (t == 0) atomicAdd(a.Arrived + task.Super, 1u);
         }
     }
 }
@@ -521,31 +492,30 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     DPanelOffset.Upload(Sym.PanelOffset, s);
     DInvOffset.Upload(Sym.InvOffset, s);
     DPanelTiles.Upload(Sym.PanelTiles, s);
-    DFwdTasks.Upload(Sym.FwdTasks, s);
-    DFwdTargetPtr.Upload(Sym.FwdTargetPtr, s);
-    DFwdTargets.Upload(Sym.FwdTargets, s);
-    DFwdExpected.Upload(Sym.FwdExpected, s);
-    DBwdTasks.Upload(Sym.BwdTasks, s);
-    DBwdDepPtr.Upload(Sym.BwdDepPtr, s);
-    DBwdDeps.Upload(Sym.BwdDeps, s);
-    DBwdExpected.Upload(Sym.BwdExpected, s);
-    DCounters.Reserve(size_t(4) * Sym.NumSuper + 2);
-    {
-        int device = 0, sms = 0, fwd = 0, bwd = 0;
-        ME_CUDA(cudaGetDevice(&device));
-        ME_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd, ForwardSweepKernel, kSolveThreads, 0));
-        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, BackwardSweepKernel, kSolveThreads, 0));
-        if (fwd < 1 || bwd < 1) Fail(ME_CUDA_ERROR, "sweep kernels do not fit an SM");
-        FwdGrid = uint32_t(sms * fwd), BwdGrid = uint32_t(sms * bwd); // every CTA resident: the spin-waits rely on it
-    }
     DUpdateTiles.Upload(Sym.UpdateTiles, s);
+    DFwdTasks.Upload(Sym.FwdTasks, s);
+    DFwdLinks.Upload(Sym.FwdLinks, s);
+    DBwdTasks.Upload(Sym.BwdTasks, s);
+    DBwdLinks.Upload(Sym.BwdLinks, s);
+    DBwdLinkNeed.Upload(Sym.BwdLinkNeed, s);
+    if (Sym.Rows.size() >= (uint64_t(1) << 32)) Fail(ME_BAD_ARG, "mesh too large: supernodal row lists exceed 32-bit indexing");
     L.Reserve(Sym.FactorNonZeros);
     Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
     LinvT.Reserve(Sym.InvOffset[Sym.NumSuper]);
     LT.Reserve(Sym.FactorNonZeros - Sym.InvOffset[Sym.NumSuper] + 1);
     Work.Reserve(fem.N);
+    Work2.Reserve(fem.N);
     DFail.Reserve(1);
+    DCounters.Reserve(size_t(4) * Sym.NumSuper + 2);
+    {
+        int device = 0, sms = 0, fwd = 0, bwd = 0;
+        ME_CUDA(cudaGetDevice(&device));
+        ME_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd, SweepKernel<false>, kSweepThreads, 0));
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, SweepKernel<true>, kSweepThreads, 0));
+        if (fwd < 1 || bwd < 1) Fail(ME_CUDA_ERROR, "sweep kernels do not fit an SM");
+        FwdGrid = uint32_t(sms * fwd), BwdGrid = uint32_t(sms * bwd); // every CTA resident: the spin-waits rely on it
+    }
     for (auto &e : Ev) ME_CUDA(cudaEventCreate(&e));
     ME_CUDA(cudaFuncSetAttribute(FactorDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
     ME_CUDA(cudaFuncSetAttribute(PanelTrsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * kLdA + kChunk * kLdB128) * 8));
@@ -609,12 +579,14 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     const uint32_t n = Fem.N, ns = Sym.NumSuper;
     FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};
     uint32_t *counters = DCounters.Ptr;
-    const SweepCounters fwd{counters + 4 * size_t(ns), counters, counters + ns}, bwd{counters + 4 * size_t(ns) + 1, counters + 2 * size_t(ns), counters + 3 * size_t(ns)};
+    // Forward: Work accumulates the right-hand side, Work2 receives y. Backward: Work2 accumulates, Work receives x.
+    const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, nullptr, counters + 4 * size_t(ns), counters, counters + ns, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr};
+    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), DBwdLinks.Ptr, DBwdLinkNeed.Ptr, counters + 4 * size_t(ns) + 1, counters + 2 * size_t(ns), counters + 3 * size_t(ns), DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr};
     for (uint32_t rhs = 0; rhs < width; ++rhs) {
         PermuteInKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr);
         ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
-        ForwardSweepKernel<<<FwdGrid, kSolveThreads, 0, s>>>(v, DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdTargetPtr.Ptr, DFwdTargets.Ptr, DFwdExpected.Ptr, fwd, Work.Ptr);
-        BackwardSweepKernel<<<BwdGrid, kSolveThreads, 0, s>>>(v, DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), DBwdDepPtr.Ptr, DBwdDeps.Ptr, DBwdExpected.Ptr, bwd, Work.Ptr);
+        SweepKernel<false><<<FwdGrid, kSweepThreads, 0, s>>>(fwd);
+        SweepKernel<true><<<BwdGrid, kSweepThreads, 0, s>>>(bwd);
         Stats.KernelLaunches += 2;
         PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, DInvPerm.Ptr, Fem.NodeCount, x + size_t(rhs) * n);
         Stats.KernelLaunches += 2;

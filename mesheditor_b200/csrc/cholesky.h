@@ -45,12 +45,11 @@ private:
     DeviceBuffer<uint32_t> DSuperFirst, DRows, DNodeSuper, DInvPerm, DPerm, DSegTarget, DSegBegin, DSegEnd, DLevelOrder;
     DeviceBuffer<uint64_t> DRowPtr, DPanelOffset, DInvOffset;
     DeviceBuffer<PanelTile> DPanelTiles;
-    DeviceBuffer<PanelGroup> DBwdTasks;
-    DeviceBuffer<PanelTile> DFwdTasks;
-    DeviceBuffer<uint32_t> DFwdTargetPtr, DFwdTargets, DFwdExpected, DBwdDepPtr, DBwdDeps, DBwdExpected, DCounters;
+    DeviceBuffer<SweepTask> DFwdTasks, DBwdTasks;
+    DeviceBuffer<uint32_t> DFwdLinks, DBwdLinks, DBwdLinkNeed, DCounters;
     uint32_t FwdGrid{0}, BwdGrid{0};
     DeviceBuffer<UpdateTile> DUpdateTiles;
-    DeviceBuffer<double> L, Linv, LinvT, LT, Work;
+    DeviceBuffer<double> L, Linv, LinvT, LT, Work, Work2;
     DeviceBuffer<int> DFail;
     cudaEvent_t Ev[4]{};
     bool Factored{false};

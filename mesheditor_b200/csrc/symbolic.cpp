@@ -229,14 +229,11 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
 
     sym.PanelTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
     sym.UpdateTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
-    sym.PanelGroupPtr.assign(size_t(sym.NumLevels) + 1, 0);
     for (uint32_t l = 0; l < sym.NumLevels; ++l) {
         for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
             const uint32_t s = sym.LevelOrder[i];
             const uint32_t m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
             for (uint32_t t = 0; t * kTile < m; ++t) sym.PanelTiles.push_back({s, t});
-            const uint32_t n_tiles = (m + kTile - 1) / kTile;
-            for (uint32_t t = 0; t < n_tiles; t += kGroupTiles) sym.PanelGroups.push_back({s, t, std::min(kGroupTiles, n_tiles - t)});
             for (uint64_t g = sym.SegPtr[s]; g < sym.SegPtr[s + 1]; ++g) {
                 const uint32_t c0 = 3 * sym.SegBegin[g], c1 = 3 * sym.SegEnd[g];
                 const uint32_t col_tiles = (c1 - c0 + kTile - 1) / kTile, row_tiles = (m - c0 + kTile - 1) / kTile;
@@ -245,17 +242,15 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
             }
         }
         sym.PanelTilePtr[l + 1] = sym.PanelTiles.size();
-        sym.PanelGroupPtr[l + 1] = sym.PanelGroups.size();
         sym.UpdateTilePtr[l + 1] = sym.UpdateTiles.size();
     }
     // Dataflow schedules of the solves. Ticket order = level order (height above the leaves), NOT elimination order:
     // both are topological, but the post-order would walk one subtree's separator chains at a time, while the level
     // order keeps the chains of all subtrees of the same height in flight together.
-    sym.FwdExpected.assign(ns, 0);
-    sym.BwdExpected.assign(ns, 0);
-    auto targets_of = [&](uint32_t s, uint32_t first_tile, uint32_t tiles, std::vector<uint32_t> &out) {
+    std::vector<uint32_t> fwd_expected(ns, 0), bwd_expected(ns, 0);
+    auto targets_of = [&](uint32_t s, uint32_t slab, std::vector<uint32_t> &out) {
         const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0;
-        const uint64_t first = (uint64_t(first_tile) * kTile) / 3, last = std::min<uint64_t>(nodes, (uint64_t(first_tile + tiles) * kTile + 2) / 3);
+        const uint64_t first = (uint64_t(slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, (uint64_t(slab + 1) * kSolveRows + 2) / 3);
         uint32_t prev = UINT32_MAX;
         for (uint64_t j = first; j < last; ++j) {
             const uint32_t target = sym.NodeSuper[sym.Rows[r0 + j]];
@@ -265,39 +260,59 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
             }
         }
     };
-    sym.FwdTargetPtr.push_back(0);
+    auto columns = [&](uint32_t s) { return 3 * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]); };
+    auto diag_slabs = [&](uint32_t s) { return (columns(s) + kSolveRows - 1) / kSolveRows; };
+    auto base_task = [&](uint32_t s) {
+        SweepTask t{};
+        t.Super = s;
+        t.K = columns(s);
+        t.VecOffset = 3 * sym.SuperFirst[s];
+        t.RowsBase = uint32_t(sym.RowPtr[s]);
+        return t;
+    };
+    auto diag_task = [&](uint32_t s, uint32_t h) {
+        SweepTask t = base_task(s);
+        t.Kind = 0, t.Base = sym.InvOffset[s], t.Limit = t.K, t.Ld = t.K, t.Row0 = h * kSolveRows;
+        return t;
+    };
     for (uint32_t l = 0; l < sym.NumLevels; ++l) {
-        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-            sym.FwdTasks.push_back({sym.LevelOrder[i], kDiagTask});
-            sym.FwdTargetPtr.push_back(uint32_t(sym.FwdTargets.size()));
-        }
+        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
+            for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) sym.FwdTasks.push_back(diag_task(sym.LevelOrder[i], h));
         for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
             const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
-            for (uint32_t t = 0; t * kTile < m; ++t) {
-                sym.FwdTasks.push_back({s, t});
-                const size_t before = sym.FwdTargets.size();
-                targets_of(s, t, 1, sym.FwdTargets);
-                for (size_t j = before; j < sym.FwdTargets.size(); ++j) ++sym.FwdExpected[sym.FwdTargets[j]];
-                sym.FwdTargetPtr.push_back(uint32_t(sym.FwdTargets.size()));
+            for (uint32_t h = 0; h * kSolveRows < m; ++h) {
+                SweepTask t = base_task(s);
+                t.Kind = 1, t.Base = sym.PanelOffset[s] + t.K, t.Limit = m, t.Ld = t.K + m, t.Row0 = h * kSolveRows, t.Need = diag_slabs(s);
+                t.LinkBegin = uint32_t(sym.FwdLinks.size());
+                targets_of(s, h, sym.FwdLinks);
+                t.LinkCount = uint32_t(sym.FwdLinks.size()) - t.LinkBegin;
+                for (uint32_t j = 0; j < t.LinkCount; ++j) ++fwd_expected[sym.FwdLinks[t.LinkBegin + j]];
+                sym.FwdTasks.push_back(t);
             }
         }
     }
-    sym.BwdDepPtr.push_back(0);
+    for (auto &t : sym.FwdTasks)
+        if (t.Kind == 0) t.Need = fwd_expected[t.Super];
     for (uint32_t l = sym.NumLevels; l-- > 0;) {
         for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-            const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]), n_tiles = (m + kTile - 1) / kTile;
-            for (uint32_t t = 0; t < n_tiles; t += kGroupTiles) {
-                const uint32_t tiles = std::min(kGroupTiles, n_tiles - t);
-                sym.BwdTasks.push_back({s, t, tiles});
-                ++sym.BwdExpected[s];
-                targets_of(s, t, tiles, sym.BwdDeps);
-                sym.BwdDepPtr.push_back(uint32_t(sym.BwdDeps.size()));
+            const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
+            for (uint32_t h = 0; h * kSolveRows < m; ++h) {
+                SweepTask t = base_task(s);
+                t.Kind = 1, t.Base = sym.PanelOffset[s] - sym.InvOffset[s], t.Limit = m, t.Ld = t.K, t.Row0 = h * kSolveRows;
+                t.LinkBegin = uint32_t(sym.BwdLinks.size());
+                targets_of(s, h, sym.BwdLinks);
+                t.LinkCount = uint32_t(sym.BwdLinks.size()) - t.LinkBegin;
+                for (uint32_t j = 0; j < t.LinkCount; ++j) sym.BwdLinkNeed.push_back(diag_slabs(sym.BwdLinks[t.LinkBegin + j]));
+                ++bwd_expected[s];
+                sym.BwdTasks.push_back(t);
             }
         }
-        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-            sym.BwdTasks.push_back({sym.LevelOrder[i], 0, 0});
-            sym.BwdDepPtr.push_back(uint32_t(sym.BwdDeps.size()));
-        }
+        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
+            for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) {
+                SweepTask t = diag_task(sym.LevelOrder[i], h);
+                t.Need = bwd_expected[t.Super];
+                sym.BwdTasks.push_back(t);
+            }
     }
     sym.StructureSeconds = Now() - t1;
     return sym;

@@ -23,12 +23,22 @@ struct UpdateTile {
 struct PanelTile {
     uint32_t Super, RowTile;
 };
-// A run of consecutive 64-row tiles of one panel handled by one CTA of the backward solve (fewer atomics per column).
-struct PanelGroup {
-    uint32_t Super, FirstTile, Tiles;
+// One task of a triangular-solve sweep: a slab of kSolveRows rows of a diagonal block's inverse (Kind 0) or of a panel
+// (Kind 1), with everything the kernel needs in one 64-byte record so that a task costs a single descriptor fetch.
+constexpr uint32_t kSolveRows = 32;
+struct alignas(64) SweepTask {
+    uint64_t Base;       // offset in doubles of the matrix block: into Linv / Linv^T (diag), L (forward panel), LT (backward panel)
+    uint32_t Kind;       // 0 diagonal slab, 1 panel slab
+    uint32_t Super;
+    uint32_t K, Limit;   // columns of the supernode; row limit (k for diagonal slabs, m for panel slabs)
+    uint32_t Ld;         // leading dimension of the block
+    uint32_t Row0;       // first row of the slab
+    uint32_t VecOffset;  // 3 * SuperFirst[s]: where the supernode's own entries sit in the permuted vectors
+    uint32_t RowsBase;   // RowPtr[s]: the supernode's below-diagonal node list
+    uint32_t LinkBegin, LinkCount; // ancestors updated (forward panel) / read (backward panel)
+    uint32_t Need;       // arrivals to wait for: diagonal slab = contributions to the supernode; forward panel = its diagonal slabs
+    uint32_t Pad[3];
 };
-constexpr uint32_t kGroupTiles = 8;
-constexpr uint32_t kDiagTask = 0xFFFFFFFFu;
 
 struct Symbolic {
     uint32_t NodeCount{0}, NumSuper{0}, NumLevels{0};
@@ -46,17 +56,14 @@ struct Symbolic {
     // Work lists per level.
     std::vector<uint64_t> PanelTilePtr, UpdateTilePtr; // [NumLevels+1]
     std::vector<PanelTile> PanelTiles;        // 64-row tiles of the below-diagonal panels (TRSM, solves)
-    std::vector<uint64_t> PanelGroupPtr;      // [NumLevels+1]
-    std::vector<PanelGroup> PanelGroups;
     std::vector<UpdateTile> UpdateTiles;
     // Dataflow schedules of the triangular solves (cholesky.cu SweepKernel): tasks in a topological order, taken by
     // persistent CTAs through a ticket counter and gated by per-supernode arrival counters instead of level barriers.
-    std::vector<PanelTile> FwdTasks;          // per supernode ascending: {s, kDiagTask} then its row tiles
-    std::vector<uint32_t> FwdTargetPtr, FwdTargets; // per task: ancestors whose right-hand side the tile updates
-    std::vector<uint32_t> FwdExpected;        // [NumSuper] tiles that must arrive before the supernode's diagonal solve
-    std::vector<PanelGroup> BwdTasks;         // per supernode descending: its tile groups, then {s, 0, 0} = diagonal solve
-    std::vector<uint32_t> BwdDepPtr, BwdDeps; // per task: ancestors whose solution the group reads
-    std::vector<uint32_t> BwdExpected;        // [NumSuper] groups that must arrive before the supernode's diagonal solve
+    // Every task is one kSolveRows-row slab: a slab of a diagonal block's inverse, or of a panel.
+    std::vector<SweepTask> FwdTasks;          // levels ascending: the level's diagonal slabs, then its panel slabs
+    std::vector<SweepTask> BwdTasks;          // levels descending: the level's panel slabs, then its diagonal slabs
+    std::vector<uint32_t> FwdLinks;           // forward panel slabs: the ancestors they update
+    std::vector<uint32_t> BwdLinks, BwdLinkNeed; // backward panel slabs: the ancestors they read, and how many diagonal slabs each has
     uint64_t FactorNonZeros{0};               // scalars stored in the panels
     double FactorFlops{0};
     uint32_t MaxPanelColumns{0}, MaxPanelRows{0};
