@@ -263,10 +263,6 @@ __global__ void __launch_bounds__(kSyrkThreads) SyrkScatterKernel(FactorView v, 
 }
 
 // ------------------------------------------------------------------------------------------------ triangular solves
-__global__ void PermuteInKernel(const double *__restrict__ b, const uint32_t *__restrict__ inv_perm, uint32_t n_nodes, double *__restrict__ w) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 3 * n_nodes) w[3 * inv_perm[i / 3] + i % 3] = b[i];
-}
 __global__ void PermuteOutKernel(const double *__restrict__ w, const uint32_t *__restrict__ inv_perm, uint32_t n_nodes, double *__restrict__ x) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 3 * n_nodes) x[i] = w[3 * inv_perm[i / 3] + i % 3];
@@ -282,26 +278,61 @@ constexpr int kSolveThreads = 256;
 // sweep is ONE launch of persistent CTAs:
 //   * work is cut into uniform slabs of 32 rows x k columns (of a diagonal block's inverse, or of a panel) listed in a
 //     topological order (level by level); CTAs take them from a ticket counter;
-//   * a task waits only for its own inputs, through per-supernode counters: a panel slab for its supernode's diagonal
-//     solve, a diagonal solve for every slab that updates it. A task's inputs always hold smaller tickets and every CTA
-//     is resident, so the spin-waits cannot deadlock;
-//   * a task is a short chain of dependent round trips (ticket, flag, vector, 32 KB of matrix, atomics, fence), so what
-//     keeps HBM busy is the number of chains in flight: the CTAs are small (128 threads, every thread issues its 32 loads
-//     before using any) and five of them share an SM;
-//   * values produced by other CTAs are read with ld.global.cg after the counter that publishes them (written behind
-//     a __threadfence).
+//   * a task waits only for its own inputs. A task's inputs always hold smaller tickets and every CTA is resident, so the
+//     spin-waits cannot deadlock (they are bounded all the same: a sweep that stalls raises Fail instead of hanging);
+//   * a task is a short chain of dependent L2 round trips, so what keeps HBM busy is the number of chains in flight and
+//     how much of each chain overlaps the 32 KB matrix load: the CTAs are small (128 threads, every thread issues its 32
+//     loads before using any), five share an SM, and the chain is kept short:
+//       - solved entries are SELF-VALIDATING: `out` is pre-filled with a NaN sentinel, a diagonal slab just stores its
+//         results, and a consumer polls the entries it needs until none is the sentinel — no fence, no flag, and the
+//         poll is the load;
+//       - only the many-to-one direction (panel slabs accumulating into a supernode's entries with FP64 atomics) keeps a
+//         counter, and its publication (fence + increment) is deferred until the NEXT task's matrix loads are in
+//         flight, so the fence's round trip overlaps them.
 // Forward: `acc` holds the right-hand side that panel slabs update, diagonal slabs write y into `out`.
 // Backward: `acc` holds y, panel slabs subtract P^T x from it, diagonal slabs write x into `out`.
 __device__ __forceinline__ uint32_t Peek(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
 
+constexpr unsigned long long kUnsolved = 0xFFFBADC0FFEE0DD5ull; // quiet NaN with a payload arithmetic never produces
+constexpr uint32_t kSpinLimit = 1u << 19;                        // ~0.3 s of polling: far beyond any legitimate wait
+
+__device__ __forceinline__ unsigned long long LoadL2(const double *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void StoreL2(double *p, double v) {
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(__double_as_longlong(v)) : "memory");
+}
+// A wait gives up when it has spun past the limit, or (checked now and then) once any other wait has: a stalled sweep
+// drains quickly instead of timing out task by task.
+__device__ __forceinline__ bool GiveUp(uint32_t spin, int *fail) {
+    if (spin > kSpinLimit) {
+        atomicExch(fail, 4);
+        return true;
+    }
+    return (spin & 1023u) == 1023u && *reinterpret_cast<volatile int *>(fail) != 0;
+}
+// Polls one solved entry until it is published. Returns 0.0 (and raises Fail) if it never is.
+__device__ __forceinline__ double AwaitSolved(const double *p, int *fail) {
+    unsigned long long v = LoadL2(p);
+    for (uint32_t spin = 0; v == kUnsolved; ++spin) {
+        if (GiveUp(spin, fail)) return 0.0;
+        __nanosleep(20);
+        v = LoadL2(p);
+    }
+    return __longlong_as_double((long long)v);
+}
+
 struct SweepArgs {
     const SweepTask *Tasks;
     uint32_t NumTasks;
-    const uint32_t *Links, *LinkNeed; // ancestors updated (forward) / read (backward, with their diagonal-slab counts)
-    uint32_t *Ticket, *Arrived, *Done;
+    const uint32_t *Links;            // forward panel slabs: the ancestors they update
+    uint32_t *Ticket, *Arrived;
     const uint32_t *Rows;             // below-diagonal node lists of all supernodes
     const double *Diag, *Panel;       // Linv + L (forward) or Linv^T + LT (backward)
     double *Acc, *Out;
+    int *Fail;
 };
 constexpr int kSweepThreads = 128;
 constexpr int kSweepCtasPerSm = 5;
@@ -323,6 +354,29 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
             if (t < 8 && next_id < a.NumTasks) next_word = reinterpret_cast<const uint64_t *>(a.Tasks + next_id)[t];
         }
     };
+    // Deferred publication of the previous panel slab's contributions: tail_any is CTA-uniform, tail_mine marks the
+    // threads that own one counter increment each.
+    bool tail_any = false, tail_mine = false;
+    uint32_t tail_target = 0;
+    auto publish_tail = [&] {
+        if (tail_any) {
+            __threadfence();
+            __syncthreads();
+            if (tail_mine) atomicAdd(a.Arrived + tail_target, 1u);
+            tail_any = tail_mine = false;
+        }
+    };
+    // Waits (thread 0) until every contribution to the supernode's entries of `acc` has been published.
+    auto await_arrivals = [&](uint32_t super, uint32_t need) {
+        if (t == 0) {
+            for (uint32_t spin = 0; Peek(a.Arrived + super) < need; ++spin) {
+                if (GiveUp(spin, a.Fail)) break;
+                __nanosleep(20);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    };
     prefetch_next();
     for (;;) {
         __syncthreads();
@@ -330,7 +384,10 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
         if (t == 0) s_id = next_id;
         __syncthreads();
         const uint32_t id = s_id;
-        if (id >= a.NumTasks) return;
+        if (id >= a.NumTasks) {
+            publish_tail();
+            return;
+        }
         const SweepTask task = s_task;
         const uint32_t k = task.K;
         double val[32];
@@ -346,11 +403,8 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
                 val[j] = in ? mat[row + size_t(col) * k] : 0.0;
             }
             prefetch_next();
-            if (t == 0) {
-                while (Peek(a.Arrived + task.Super) < task.Need) __nanosleep(32);
-                __threadfence();
-            }
-            __syncthreads();
+            publish_tail();
+            await_arrivals(task.Super, task.Need);
             vec[t] = t < k ? __ldcg(a.Acc + task.VecOffset + t) : 0.0;
             __syncthreads();
             double sum = 0;
@@ -358,10 +412,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
             for (int j = 0; j < 32; ++j) sum += val[j] * vec[q + 4 * j];
             part[t] = sum;
             __syncthreads();
-            if (t < 32 && row < k) a.Out[task.VecOffset + row] = (part[t] + part[32 + t]) + (part[64 + t] + part[96 + t]);
-            __threadfence();
-            __syncthreads();
-            if (t == 0) atomicAdd(a.Done + task.Super, 1u);
+            if (t < 32 && row < k) StoreL2(a.Out + task.VecOffset + row, (part[t] + part[32 + t]) + (part[64 + t] + part[96 + t]));
         } else if constexpr (!Backward) {
             // acc[slab rows] -= P_slab out_S once out_S is complete. Panel: column-major, leading dimension k + m.
             const uint32_t row = task.Row0 + r;
@@ -375,12 +426,8 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
             if (t < 32 && row < task.Limit) node = a.Rows[task.RowsBase + row / 3];
             if (t < task.LinkCount) link = a.Links[task.LinkBegin + t];
             prefetch_next();
-            if (t == 0) {
-                while (Peek(a.Done + task.Super) < task.Need) __nanosleep(32);
-                __threadfence();
-            }
-            __syncthreads();
-            vec[t] = t < k ? __ldcg(a.Out + task.VecOffset + t) : 0.0;
+            publish_tail();
+            vec[t] = t < k ? AwaitSolved(a.Out + task.VecOffset + t, a.Fail) : 0.0;
             __syncthreads();
             double sum = 0;
 #pragma unroll
@@ -388,9 +435,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
             part[t] = sum;
             __syncthreads();
             if (t < 32 && row < task.Limit) atomicAdd(a.Acc + size_t(3) * node + row % 3, -((part[t] + part[32 + t]) + (part[64 + t] + part[96 + t])));
-            __threadfence();
-            __syncthreads();
-            if (t < task.LinkCount) atomicAdd(a.Arrived + link, 1u);
+            tail_any = true, tail_mine = t < task.LinkCount, tail_target = link;
         } else {
             // acc_S -= P_slab^T out[slab rows] once the ancestors owning those rows are solved. Read from the transposed
             // panel copy ([row][column]): thread = column, so the sum over the slab's rows stays in one register.
@@ -400,23 +445,29 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
             uint32_t node = 0;
             if (t < kSolveRows && task.Row0 + t < task.Limit) node = a.Rows[task.RowsBase + (task.Row0 + t) / 3];
             prefetch_next();
-            if (t < task.LinkCount) {
-                const uint32_t target = a.Links[task.LinkBegin + t], need = a.LinkNeed[task.LinkBegin + t];
-                while (Peek(a.Done + target) < need) __nanosleep(32);
-                __threadfence();
-            }
-            __syncthreads();
-            if (t < kSolveRows) vec[t] = task.Row0 + t < task.Limit ? __ldcg(a.Out + size_t(3) * node + (task.Row0 + t) % 3) : 0.0;
+            publish_tail();
+            if (t < kSolveRows) vec[t] = task.Row0 + t < task.Limit ? AwaitSolved(a.Out + size_t(3) * node + (task.Row0 + t) % 3, a.Fail) : 0.0;
             __syncthreads();
             double sum = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum += val[j] * vec[j];
             if (t < k) atomicAdd(a.Acc + task.VecOffset + t, -sum);
-            __threadfence();
-            __syncthreads();
-            if (t == 0) atomicAdd(a.Arrived + task.Super, 1u);
+            tail_any = true, tail_mine = t == 0, tail_target = task.Super;
         }
     }
+}
+
+// b (natural DOF order) -> acc under the fill-reducing permutation; `out` is marked unsolved.
+__global__ void SweepBeginKernel(const double *__restrict__ b, const uint32_t *__restrict__ inv_perm, uint32_t n_nodes, double *__restrict__ acc, double *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3 * n_nodes) {
+        acc[3 * inv_perm[i / 3] + i % 3] = b[i];
+        out[i] = __longlong_as_double((long long)kUnsolved);
+    }
+}
+__global__ void MarkUnsolvedKernel(double *__restrict__ out, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __longlong_as_double((long long)kUnsolved);
 }
 
 // ------------------------------------------------------------------------------------------------ FP64 rate probes
@@ -496,8 +547,6 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     DFwdTasks.Upload(Sym.FwdTasks, s);
     DFwdLinks.Upload(Sym.FwdLinks, s);
     DBwdTasks.Upload(Sym.BwdTasks, s);
-    DBwdLinks.Upload(Sym.BwdLinks, s);
-    DBwdLinkNeed.Upload(Sym.BwdLinkNeed, s);
     if (Sym.Rows.size() >= (uint64_t(1) << 32)) Fail(ME_BAD_ARG, "mesh too large: supernodal row lists exceed 32-bit indexing");
     L.Reserve(Sym.FactorNonZeros);
     Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
@@ -506,7 +555,7 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     Work.Reserve(fem.N);
     Work2.Reserve(fem.N);
     DFail.Reserve(1);
-    DCounters.Reserve(size_t(4) * Sym.NumSuper + 2);
+    DCounters.Reserve(size_t(2) * Sym.NumSuper + 2);
     {
         int device = 0, sms = 0, fwd = 0, bwd = 0;
         ME_CUDA(cudaGetDevice(&device));
@@ -578,19 +627,29 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     auto s = Fem.Stream;
     const uint32_t n = Fem.N, ns = Sym.NumSuper;
     FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};
-    uint32_t *counters = DCounters.Ptr;
+    uint32_t *counters = DCounters.Ptr; // [0, ns) forward arrivals, [ns, 2 ns) backward arrivals, then the two ticket counters
     // Forward: Work accumulates the right-hand side, Work2 receives y. Backward: Work2 accumulates, Work receives x.
-    const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, nullptr, counters + 4 * size_t(ns), counters, counters + ns, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr};
-    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), DBwdLinks.Ptr, DBwdLinkNeed.Ptr, counters + 4 * size_t(ns) + 1, counters + 2 * size_t(ns), counters + 3 * size_t(ns), DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr};
+    const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, counters + 2 * size_t(ns), counters, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr, DFail.Ptr};
+    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), nullptr, counters + 2 * size_t(ns) + 1, counters + ns, DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
     for (uint32_t rhs = 0; rhs < width; ++rhs) {
-        PermuteInKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr);
-        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
+        SweepBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr, Work2.Ptr);
+        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(2) * ns + 2) * sizeof(uint32_t), s));
         SweepKernel<false><<<FwdGrid, kSweepThreads, 0, s>>>(fwd);
+        MarkUnsolvedKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n);
         SweepKernel<true><<<BwdGrid, kSweepThreads, 0, s>>>(bwd);
-        Stats.KernelLaunches += 2;
         PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, DInvPerm.Ptr, Fem.NodeCount, x + size_t(rhs) * n);
-        Stats.KernelLaunches += 2;
+        Stats.KernelLaunches += 5;
     }
+    SolvesSinceCheck += width;
+}
+
+void SparseCholesky::CheckSolves() {
+    if (!SolvesSinceCheck) return;
+    int fail = 0;
+    ME_CUDA(cudaMemcpyAsync(&fail, DFail.Ptr, sizeof(int), cudaMemcpyDeviceToHost, Fem.Stream));
+    ME_CUDA(cudaStreamSynchronize(Fem.Stream));
+    SolvesSinceCheck = 0;
+    if (fail) Fail(ME_CUDA_ERROR, "internal: a triangular-solve sweep stalled (code %d)", fail);
 }
 
 } // namespace me

@@ -33,6 +33,8 @@ public:
     // x = A^-1 b for `width` right-hand sides stored column-major (n x width), device pointers, natural DOF order
     // (perform_op for width 1, solve_panel otherwise). b and x may alias.
     void Solve(const double *b, double *x, uint32_t width = 1);
+    // Synchronises and throws if a sweep since the last check raised the stall flag (a sweep never hangs: its waits are bounded).
+    void CheckSolves();
 
     uint32_t Rows() const { return Fem.N; }
     const Symbolic &Analysis() const { return Sym; }
@@ -46,13 +48,14 @@ private:
     DeviceBuffer<uint64_t> DRowPtr, DPanelOffset, DInvOffset;
     DeviceBuffer<PanelTile> DPanelTiles;
     DeviceBuffer<SweepTask> DFwdTasks, DBwdTasks;
-    DeviceBuffer<uint32_t> DFwdLinks, DBwdLinks, DBwdLinkNeed, DCounters;
+    DeviceBuffer<uint32_t> DFwdLinks, DCounters;
     uint32_t FwdGrid{0}, BwdGrid{0};
     DeviceBuffer<UpdateTile> DUpdateTiles;
     DeviceBuffer<double> L, Linv, LinvT, LT, Work, Work2;
     DeviceBuffer<int> DFail;
     cudaEvent_t Ev[4]{};
     bool Factored{false};
+    uint32_t SolvesSinceCheck{0};
 };
 
 // FP64 issue-rate micro-benchmark: mode 0 = DFMA, 1 = DMMA m8n8k4. Returns flop/s.

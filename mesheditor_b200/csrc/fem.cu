@@ -343,30 +343,59 @@ __global__ void GatherFullKernel(const uint32_t *__restrict__ full_src, const do
     if (e == 0) mfull[d] = mblk[u];
 }
 
-// y = K x, K in full block-CSR with 3x3 blocks. One warp per block row; lanes stride over the row's scalars so the
-// value stream (72 of the 76 bytes per block) is read fully coalesced.
+// y = K x, K in full block-CSR with 3x3 blocks. A CTA owns kSpmvRows consecutive block rows and STREAMS their blocks:
+// the value array of those rows is one contiguous range, so 256 threads read it scalar by scalar, fully coalesced and
+// with every load of a pass issued before the first is used (a row has only ~130 scalars for P1: a warp per row would
+// sit on three dependent round trips — row pointer, value + column, x — with a single load per lane in flight).
+// Products go to shared memory; 3 * kSpmvRows threads then sum their own output component.
+constexpr int kSpmvRows = 32;   // block rows per CTA
+constexpr int kSpmvCap = 512;   // blocks staged per pass: 9 * 512 products = 36 KB of shared memory
+constexpr int kSpmvUnroll = 6;
 __global__ void __launch_bounds__(kThreads) SpmvBsr3Kernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, const double *__restrict__ val,
                                                            const double *__restrict__ x, double *__restrict__ y, uint32_t n_rows) {
-    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (row >= n_rows) return;
-    const uint32_t b0 = row_ptr[row], count = (row_ptr[row + 1] - b0) * 9;
-    const double *v = val + size_t(9) * b0;
-    const uint32_t *cb = col + b0;
-    double acc0 = 0, acc1 = 0, acc2 = 0;
-    for (uint32_t s = lane; s < count; s += 32) {
-        const uint32_t blk = s / 9, rem = s - 9 * blk, p = rem / 3, q = rem - 3 * p;
-        const double t = v[s] * x[3 * cb[blk] + q];
-        acc0 += p == 0 ? t : 0.0;
-        acc1 += p == 1 ? t : 0.0;
-        acc2 += p == 2 ? t : 0.0;
-    }
+    __shared__ double prod[9 * kSpmvCap];
+    __shared__ uint32_t rp[kSpmvRows + 1];
+    const uint32_t t = threadIdx.x, row0 = blockIdx.x * kSpmvRows, rows = min(uint32_t(kSpmvRows), n_rows - row0);
+    if (t <= rows) rp[t] = row_ptr[row0 + t];
+    __syncthreads();
+    const uint32_t b_end = rp[rows];
+    const uint32_t my_row = t / 3, my_p = t - 3 * my_row;
+    double acc = 0;
+    for (uint32_t base = rp[0]; base < b_end; base += kSpmvCap) {
+        const uint32_t nb = min(uint32_t(kSpmvCap), b_end - base), ns = 9 * nb;
+        const double *v = val + size_t(9) * base;
+        const uint32_t *cb = col + base;
+        for (uint32_t s0 = t; s0 < ns; s0 += kSpmvUnroll * kThreads) {
+            double vv[kSpmvUnroll], xx[kSpmvUnroll];
+            uint32_t cc[kSpmvUnroll];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
-        acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
-        acc2 += __shfl_xor_sync(0xffffffffu, acc2, o);
+            for (int u = 0; u < kSpmvUnroll; ++u) {
+                const uint32_t s = s0 + u * kThreads;
+                vv[u] = s < ns ? __ldcs(v + s) : 0.0;
+                cc[u] = s < ns ? __ldg(cb + s / 9) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kSpmvUnroll; ++u) {
+                const uint32_t s = s0 + u * kThreads;
+                xx[u] = s < ns ? __ldg(x + 3 * cc[u] + (s % 9) % 3) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kSpmvUnroll; ++u) {
+                const uint32_t s = s0 + u * kThreads;
+                if (s < ns) prod[s] = vv[u] * xx[u];
+            }
+        }
+        __syncthreads();
+        if (my_row < rows) {
+            const uint32_t lo = max(rp[my_row], base) - base, hi = min(rp[my_row + 1], base + nb);
+            for (uint32_t b = lo; base + b < hi; ++b) {
+                const double *pb = prod + 9 * b + 3 * my_p;
+                acc += (pb[0] + pb[1]) + pb[2];
+            }
+        }
+        __syncthreads();
     }
-    if (lane < 3) y[3 * row + lane] = lane == 0 ? acc0 : lane == 1 ? acc1 : acc2;
+    if (my_row < rows) y[size_t(3) * row0 + t] = acc;
 }
 
 // y = M x, M = (node mass matrix) (x) I3 in full node CSR: 12 bytes per stored scalar serve three output components.
@@ -680,7 +709,7 @@ void FemSystem::Build(const double *points_xyz, uint32_t n_points, const uint32_
 }
 
 void FemSystem::SpmvK(const double *x, double *y) {
-    SpmvBsr3Kernel<<<Blocks(uint64_t(NodeCount) * 32), kThreads, 0, Stream>>>(FullRowPtr.Ptr, FullCol.Ptr, KFull.Ptr, x, y, NodeCount);
+    SpmvBsr3Kernel<<<Blocks(NodeCount, kSpmvRows), kThreads, 0, Stream>>>(FullRowPtr.Ptr, FullCol.Ptr, KFull.Ptr, x, y, NodeCount);
     ++KernelLaunches;
 }
 void FemSystem::SpmvM(const double *x, double *y) {

@@ -370,6 +370,7 @@ LanczosOutcome ShiftInvertLanczos::Compute(uint32_t nev, uint32_t ncv, double to
         TallGemm(Ws, V, n, m, DSmall.Ptr, m, nev, Vectors.Ptr, s);
     }
     ME_CUDA(cudaStreamSynchronize(s));
+    Factor.CheckSolves();
     for (uint32_t i = 0; i < Ops; ++i) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, OpEvents[2 * i], OpEvents[2 * i + 1]) == cudaSuccess) out.OpSolveMs += ms;

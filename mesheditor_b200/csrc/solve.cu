@@ -615,6 +615,7 @@ MeStatus me_factor_solve(MeFactor *f, const double *b, double *x, uint32_t width
         ME_CUDA(cudaEventElapsedTime(&c.Stats.LastSolveMs, e0, e1));
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+        c.CheckSolves();
     });
 }
 MeStatus me_factor_info(MeFactor *f, MeFactorInfo *out) {
