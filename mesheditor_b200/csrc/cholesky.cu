@@ -457,6 +457,223 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
     }
 }
 
+// ------------------------------------------------------------------------------------------------ panel sweeps
+// The same dataflow sweep for a PANEL of kWide right-hand sides (solve_panel, CholeskyShiftInvert.cpp:55-62): one pass
+// over the factor serves all of them, so the bytes per right-hand side drop by kWide while the sweep stays HBM-bound.
+// Vectors are stored [permuted DOF][kWide] (one 64-byte row per DOF: a gathered/scattered row is one full sector pair).
+// Every slab product is a small dense contraction (32 x k times k x 8, or k x 32 times 32 x 8) and runs on the FP64
+// tensor cores: each warp owns a quarter of the contraction (forward/diagonal: a quarter of k, reduced across warps in
+// shared memory; backward: a quarter of the output columns), loads its 32 A-fragments straight from global memory in
+// the m8n8k4 fragment layout (all 32 loads in flight before anything waits), and takes B from the shared k x 8 panel.
+constexpr int kWide = 8;
+
+__device__ __forceinline__ void LoadL2x2(const double *p, unsigned long long &a, unsigned long long &b) {
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// Polls a pair of adjacent solved entries (16-byte aligned) until both are published.
+__device__ __forceinline__ void AwaitSolved2(const double *p, int *fail, double &x, double &y) {
+    unsigned long long a, b;
+    LoadL2x2(p, a, b);
+    for (uint32_t spin = 0; a == kUnsolved || b == kUnsolved; ++spin) {
+        if (GiveUp(spin, fail)) {
+            a = b = 0;
+            break;
+        }
+        __nanosleep(20);
+        LoadL2x2(p, a, b);
+    }
+    x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b);
+}
+
+template<bool Backward>
+__global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKernel(SweepArgs a) {
+    __shared__ __align__(16) double vec[128 * kWide];      // the k x 8 (or 32 x 8) right-hand operand
+    __shared__ __align__(16) double part[4 * 32 * kWide];  // per-warp partial products of one slab
+    __shared__ SweepTask s_task;
+    __shared__ uint32_t s_id, s_node[kSolveRows];
+    const uint32_t t = threadIdx.x, lane = t & 31, q = t >> 5, fr = lane >> 2, fk = lane & 3;
+    uint32_t next_id = 0;
+    uint64_t next_word = 0;
+    auto prefetch_next = [&] {
+        if (t < 32) {
+            if (t == 0) next_id = atomicAdd(a.Ticket, 1u);
+            next_id = __shfl_sync(0xffffffffu, next_id, 0);
+            if (t < 8 && next_id < a.NumTasks) next_word = reinterpret_cast<const uint64_t *>(a.Tasks + next_id)[t];
+        }
+    };
+    bool tail_any = false, tail_mine = false;
+    uint32_t tail_target = 0;
+    auto publish_tail = [&] {
+        if (tail_any) {
+            __threadfence();
+            __syncthreads();
+            if (tail_mine) atomicAdd(a.Arrived + tail_target, 1u);
+            tail_any = tail_mine = false;
+        }
+    };
+    auto await_arrivals = [&](uint32_t super, uint32_t need) {
+        if (t == 0) {
+            for (uint32_t spin = 0; Peek(a.Arrived + super) < need; ++spin) {
+                if (GiveUp(spin, a.Fail)) break;
+                __nanosleep(20);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    };
+    // C[32 x 8] partial of this warp = A-fragments val[mi*8+ks] (rows 8mi.., k-steps of the warp's quarter) times vec.
+    auto contract_quarter = [&](const double (&val)[32], double (&c)[4][2]) {
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const double b = vec[(32 * q + 4 * ks + fk) * kWide + fr];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b);
+        }
+    };
+    auto store_partials = [&](const double (&c)[4][2]) {
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+            *reinterpret_cast<double2 *>(&part[(q * 32 + 8 * mi + fr) * kWide + 2 * fk]) = make_double2(c[mi][0], c[mi][1]);
+    };
+    auto reduced = [&](uint32_t idx) { return (part[idx] + part[256 + idx]) + (part[512 + idx] + part[768 + idx]); };
+    prefetch_next();
+    for (;;) {
+        __syncthreads();
+        if (t < 8) reinterpret_cast<uint64_t *>(&s_task)[t] = next_word;
+        if (t == 0) s_id = next_id;
+        __syncthreads();
+        const uint32_t id = s_id;
+        if (id >= a.NumTasks) {
+            publish_tail();
+            return;
+        }
+        const SweepTask task = s_task;
+        const uint32_t k = task.K;
+        double val[32];
+        if (task.Kind == 0) {
+            const double *mat = a.Diag + task.Base;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t row = task.Row0 + 8 * mi + fr, col = 32 * q + 4 * ks + fk;
+                    const bool in = row < k && col < k && (Backward ? col >= row : col <= row);
+                    val[mi * 8 + ks] = in ? mat[row + size_t(col) * k] : 0.0;
+                }
+            prefetch_next();
+            publish_tail();
+            await_arrivals(task.Super, task.Need);
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(a.Acc + (size_t(task.VecOffset) + t) * kWide);
+                double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
+#pragma unroll
+                for (int j = 0; j < kWide / 2; ++j) dst[j] = t < k ? __ldcg(src + j) : make_double2(0.0, 0.0);
+            }
+            __syncthreads();
+            double c[4][2]{};
+            contract_quarter(val, c);
+            store_partials(c);
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t idx = t + 128 * h, row = task.Row0 + idx / kWide;
+                if (row < k) StoreL2(a.Out + (size_t(task.VecOffset) + row) * kWide + idx % kWide, reduced(idx));
+            }
+        } else if constexpr (!Backward) {
+            const double *p0 = a.Panel + task.Base;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t row = task.Row0 + 8 * mi + fr, col = 32 * q + 4 * ks + fk;
+                    val[mi * 8 + ks] = (row < task.Limit && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
+                }
+            uint32_t link = 0;
+            if (t < kSolveRows) s_node[t] = task.Row0 + t < task.Limit ? a.Rows[task.RowsBase + (task.Row0 + t) / 3] : 0;
+            if (t < task.LinkCount) link = a.Links[task.LinkBegin + t];
+            prefetch_next();
+            publish_tail();
+            {
+                const double *src = a.Out + (size_t(task.VecOffset) + t) * kWide;
+                double *dst = vec + t * kWide;
+#pragma unroll
+                for (int j = 0; j < kWide / 2; ++j) {
+                    double x = 0, y = 0;
+                    if (t < k) AwaitSolved2(src + 2 * j, a.Fail, x, y);
+                    dst[2 * j] = x, dst[2 * j + 1] = y;
+                }
+            }
+            __syncthreads();
+            double c[4][2]{};
+            contract_quarter(val, c);
+            store_partials(c);
+            __syncthreads();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t idx = t + 128 * h, lr = idx / kWide, row = task.Row0 + lr;
+                if (row < task.Limit) atomicAdd(a.Acc + (size_t(3) * s_node[lr] + row % 3) * kWide + idx % kWide, -reduced(idx));
+            }
+            tail_any = true, tail_mine = t < task.LinkCount, tail_target = link;
+        } else {
+            // acc_S[k x 8] -= P_slab^T [k x 32] out[slab rows x 8]: warp q owns output columns 32q .. 32q+31 of the supernode.
+            const double *pt = a.Panel + task.Base;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t col = 32 * q + 8 * mi + fr, row = task.Row0 + 4 * ks + fk;
+                    val[mi * 8 + ks] = (row < task.Limit && col < k) ? pt[size_t(row) * k + col] : 0.0;
+                }
+            uint32_t node = 0;
+            const uint32_t vr = t >> 2, row = task.Row0 + vr;
+            if (row < task.Limit) node = a.Rows[task.RowsBase + row / 3];
+            prefetch_next();
+            publish_tail();
+            {
+                double x = 0, y = 0;
+                if (row < task.Limit) AwaitSolved2(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3), a.Fail, x, y);
+                vec[vr * kWide + 2 * (t & 3)] = x, vec[vr * kWide + 2 * (t & 3) + 1] = y;
+            }
+            __syncthreads();
+            double c[4][2]{};
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double b = vec[(4 * ks + fk) * kWide + fr];
+#pragma unroll
+                for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const uint32_t col = 32 * q + 8 * mi + fr;
+                if (col < k) {
+                    double *dst = a.Acc + (size_t(task.VecOffset) + col) * kWide + 2 * fk;
+                    atomicAdd(dst, -c[mi][0]);
+                    atomicAdd(dst + 1, -c[mi][1]);
+                }
+            }
+            tail_any = true, tail_mine = t == 0, tail_target = task.Super;
+        }
+    }
+}
+
+// Panel of up to kWide right-hand sides, column-major n x width in natural DOF order -> acc[permuted DOF][kWide]
+// (missing columns are zero); `out` is marked unsolved.
+__global__ void WideBeginKernel(const double *__restrict__ b, size_t n, uint32_t width, const uint32_t *__restrict__ inv_perm, double *__restrict__ acc, double *__restrict__ out) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; // natural DOF
+    if (i >= n) return;
+    const size_t dst = (size_t(3) * inv_perm[i / 3] + i % 3) * kWide;
+#pragma unroll
+    for (int w = 0; w < kWide; ++w) acc[dst + w] = uint32_t(w) < width ? b[i + size_t(w) * n] : 0.0;
+#pragma unroll
+    for (int w = 0; w < kWide; ++w) out[i * kWide + w] = __longlong_as_double((long long)kUnsolved);
+}
+__global__ void WidePermuteOutKernel(const double *__restrict__ work, size_t n, uint32_t width, const uint32_t *__restrict__ inv_perm, double *__restrict__ x) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t src = (size_t(3) * inv_perm[i / 3] + i % 3) * kWide;
+    for (uint32_t w = 0; w < width; ++w) x[i + size_t(w) * n] = work[src + w];
+}
+
 // b (natural DOF order) -> acc under the fill-reducing permutation; `out` is marked unsolved.
 __global__ void SweepBeginKernel(const double *__restrict__ b, const uint32_t *__restrict__ inv_perm, uint32_t n_nodes, double *__restrict__ acc, double *__restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -465,8 +682,8 @@ __global__ void SweepBeginKernel(const double *__restrict__ b, const uint32_t *_
         out[i] = __longlong_as_double((long long)kUnsolved);
     }
 }
-__global__ void MarkUnsolvedKernel(double *__restrict__ out, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void MarkUnsolvedKernel(double *__restrict__ out, size_t n) {
+    const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __longlong_as_double((long long)kUnsolved);
 }
 
@@ -564,6 +781,10 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
         ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, SweepKernel<true>, kSweepThreads, 0));
         if (fwd < 1 || bwd < 1) Fail(ME_CUDA_ERROR, "sweep kernels do not fit an SM");
         FwdGrid = uint32_t(sms * fwd), BwdGrid = uint32_t(sms * bwd); // every CTA resident: the spin-waits rely on it
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd, WideSweepKernel<false>, kSweepThreads, 0));
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, WideSweepKernel<true>, kSweepThreads, 0));
+        if (fwd < 1 || bwd < 1) Fail(ME_CUDA_ERROR, "panel sweep kernels do not fit an SM");
+        WideFwdGrid = uint32_t(sms * fwd), WideBwdGrid = uint32_t(sms * bwd);
     }
     for (auto &e : Ev) ME_CUDA(cudaEventCreate(&e));
     ME_CUDA(cudaFuncSetAttribute(FactorDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
@@ -627,18 +848,43 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     auto s = Fem.Stream;
     const uint32_t n = Fem.N, ns = Sym.NumSuper;
     FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};
+    if (width > 2 && Work.Capacity < size_t(n) * kWide) {
+        ME_CUDA(cudaStreamSynchronize(s)); // growing a buffer releases the old block
+        Work.Reserve(size_t(n) * kWide);
+        Work2.Reserve(size_t(n) * kWide);
+    }
     uint32_t *counters = DCounters.Ptr; // [0, ns) forward arrivals, [ns, 2 ns) backward arrivals, then the two ticket counters
     // Forward: Work accumulates the right-hand side, Work2 receives y. Backward: Work2 accumulates, Work receives x.
     const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, counters + 2 * size_t(ns), counters, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr, DFail.Ptr};
     const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), nullptr, counters + 2 * size_t(ns) + 1, counters + ns, DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
-    for (uint32_t rhs = 0; rhs < width; ++rhs) {
-        SweepBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr, Work2.Ptr);
+    auto single = [&](const double *bi, double *xi) {
+        SweepBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(bi, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr, Work2.Ptr);
         ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(2) * ns + 2) * sizeof(uint32_t), s));
         SweepKernel<false><<<FwdGrid, kSweepThreads, 0, s>>>(fwd);
         MarkUnsolvedKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n);
         SweepKernel<true><<<BwdGrid, kSweepThreads, 0, s>>>(bwd);
-        PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, DInvPerm.Ptr, Fem.NodeCount, x + size_t(rhs) * n);
+        PermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, DInvPerm.Ptr, Fem.NodeCount, xi);
         Stats.KernelLaunches += 5;
+    };
+    // Panels go through the factor kWide columns per pass (WideSweepKernel); a remainder of one or two columns is
+    // cheaper as single sweeps than as a mostly empty panel.
+    uint32_t rhs = 0;
+    while (rhs < width) {
+        const uint32_t left = width - rhs;
+        if (left <= 2) {
+            single(b + size_t(rhs) * n, x + size_t(rhs) * n);
+            ++rhs;
+            continue;
+        }
+        const uint32_t w = std::min<uint32_t>(left, kWide);
+        WideBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, n, w, DInvPerm.Ptr, Work.Ptr, Work2.Ptr);
+        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(2) * ns + 2) * sizeof(uint32_t), s));
+        WideSweepKernel<false><<<WideFwdGrid, kSweepThreads, 0, s>>>(fwd);
+        MarkUnsolvedKernel<<<Blocks(size_t(n) * kWide, 256), 256, 0, s>>>(Work.Ptr, n * kWide);
+        WideSweepKernel<true><<<WideBwdGrid, kSweepThreads, 0, s>>>(bwd);
+        WidePermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n, w, DInvPerm.Ptr, x + size_t(rhs) * n);
+        Stats.KernelLaunches += 5;
+        rhs += w;
     }
     SolvesSinceCheck += width;
 }

@@ -49,7 +49,7 @@ private:
     DeviceBuffer<PanelTile> DPanelTiles;
     DeviceBuffer<SweepTask> DFwdTasks, DBwdTasks;
     DeviceBuffer<uint32_t> DFwdLinks, DCounters;
-    uint32_t FwdGrid{0}, BwdGrid{0};
+    uint32_t FwdGrid{0}, BwdGrid{0}, WideFwdGrid{0}, WideBwdGrid{0};
     DeviceBuffer<UpdateTile> DUpdateTiles;
     DeviceBuffer<double> L, Linv, LinvT, LT, Work, Work2;
     DeviceBuffer<int> DFail;

@@ -41,6 +41,13 @@ si = f.info
 out["solve_ms"] = si["last_solve_device_ms"]
 out["solve_alg_bytes"] = 16 * fi["factor_nonzeros"] + 16 * i["dofs"]
 out["solve_GBs"] = out["solve_alg_bytes"] / (si["last_solve_device_ms"] * 1e-3) / 1e9
+B = np.random.default_rng(2).standard_normal((i["dofs"], 8))
+for _ in range(solves):
+    X = f.solve(B)
+out["solve8_ms"] = f.info["last_solve_device_ms"]
+out["solve8_GBs"] = out["solve_alg_bytes"] / (out["solve8_ms"] * 1e-3) / 1e9
+x1 = f.solve(B[:, 3].copy())
+out["solve8_vs_single_relerr"] = float(np.linalg.norm(X[:, 3] - x1) / np.linalg.norm(x1))
 out["dfma_TFLOPs"] = measure_fp64_rate(0, 0, 3) / 1e12
 out["dmma_TFLOPs"] = measure_fp64_rate(0, 1, 3) / 1e12
 print(json.dumps(out))
