@@ -68,7 +68,7 @@ __device__ __forceinline__ void Dmma(double &c0, double &c1, double a, double b)
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 constexpr int kChunk = 16, kLd = 68;
-__global__ void __launch_bounds__(128) TallGemmKernel(const double *__restrict__ V, size_t n, uint32_t m, const double *__restrict__ Q, uint32_t ldq, uint32_t cols_out, double *__restrict__ C) {
+__global__ void __launch_bounds__(128) TallGemmKernel(const double *__restrict__ V, size_t n, uint32_t m, const double *__restrict__ Q, uint32_t ldq, uint32_t cols_out, double *__restrict__ C, double alpha, double beta) {
     __shared__ double As[kChunk * kLd], Bs[kChunk * kLd];
     const size_t row0 = size_t(blockIdx.x) * 64;
     const uint32_t col0 = blockIdx.y * 64;
@@ -105,8 +105,105 @@ __global__ void __launch_bounds__(128) TallGemmKernel(const double *__restrict__
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const uint32_t r = 32 * wm + 8 * mi + (lane >> 2), c = 32 * wn + 8 * ni + 2 * (lane & 3) + e;
-                if (r < na && c < nb) C[row0 + r + size_t(col0 + c) * n] = acc[mi][ni][e];
+                if (r < na && c < nb) {
+                    double *dst = C + row0 + r + size_t(col0 + c) * n;
+                    *dst = beta != 0.0 ? alpha * acc[mi][ni][e] + beta * *dst : alpha * acc[mi][ni][e];
+                }
             }
+}
+
+// Narrow forms (at most 8 columns on the short side): the long operand streams from HBM exactly once, straight into
+// m8n8k4 A-fragments (32 loads in flight per thread, no shared-memory staging, no barriers in the main loop).
+constexpr int kNarrow = 8;
+
+// C[n x 8] = alpha * V[n x m] * Q[m x cols (<= 8)] + beta * C. One warp per 32 rows.
+__global__ void __launch_bounds__(128) TallGemmNarrowKernel(const double *__restrict__ V, size_t n, uint32_t m, const double *__restrict__ Q, uint32_t ldq, uint32_t cols, double *__restrict__ C, double alpha, double beta) {
+    extern __shared__ double qs[]; // [m rounded up to 32][8]
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, fr = lane >> 2, fk = lane & 3;
+    const uint32_t mpad = (m + 31) & ~31u;
+    for (uint32_t idx = t; idx < mpad * kNarrow; idx += 128) {
+        const uint32_t k = idx / kNarrow, c = idx % kNarrow;
+        qs[idx] = (k < m && c < cols) ? Q[k + size_t(c) * ldq] : 0.0;
+    }
+    __syncthreads();
+    const size_t row0 = size_t(blockIdx.x) * 128 + 32 * w;
+    if (row0 >= n) return;
+    double acc[4][2]{};
+    for (uint32_t kc = 0; kc < m; kc += 32) {
+        double val[32];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const size_t r = row0 + 8 * mi + fr;
+                const uint32_t k = kc + 4 * ks + fk;
+                val[ks * 4 + mi] = (r < n && k < m) ? V[r + size_t(k) * n] : 0.0;
+            }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const double b = qs[(kc + 4 * ks + fk) * kNarrow + fr];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) Dmma(acc[mi][0], acc[mi][1], val[ks * 4 + mi], b);
+        }
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const size_t r = row0 + 8 * mi + fr;
+            const uint32_t c = 2 * fk + e;
+            if (r < n && c < cols) {
+                double *dst = C + r + size_t(c) * n;
+                *dst = beta != 0.0 ? alpha * acc[mi][e] + beta * *dst : alpha * acc[mi][e];
+            }
+        }
+}
+
+// partial[split][a_pad x 8] of X[:, :a]^T Y[:, :c (<= 8)]: CTA = 32 columns of X x one row range; its 4 warps take
+// alternate 4-row steps and are reduced in shared memory.
+constexpr uint32_t kGramSplits = 64;
+__global__ void __launch_bounds__(128) GramNarrowPartialKernel(const double *__restrict__ X, size_t n, uint32_t a, const double *__restrict__ Y, uint32_t c, double *__restrict__ partial, uint32_t a_pad) {
+    __shared__ double part[4 * 32 * kNarrow];
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, fr = lane >> 2, fk = lane & 3;
+    const uint32_t col0 = blockIdx.x * 32, split = blockIdx.y;
+    size_t chunk = (n + kGramSplits - 1) / kGramSplits;
+    chunk = (chunk + 127) & ~size_t(127); // whole CTA iterations (4 warps x 8 steps x 4 rows)
+    const size_t begin = split * chunk, end = min(n, begin + chunk);
+    double acc[4][2]{};
+    for (size_t r0 = begin + 32 * w; r0 < end; r0 += 128) {
+        double val[32], b[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const size_t r = r0 + 4 * ks + fk;
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const uint32_t col = col0 + 8 * mi + fr;
+                val[ks * 4 + mi] = (r < end && col < a) ? X[r + size_t(col) * n] : 0.0;
+            }
+            b[ks] = (r < end && fr < c) ? Y[r + size_t(fr) * n] : 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) Dmma(acc[mi][0], acc[mi][1], val[ks * 4 + mi], b[ks]);
+    }
+#pragma unroll
+    for (int mi = 0; mi < 4; ++mi) {
+        part[(w * 32 + 8 * mi + fr) * kNarrow + 2 * fk] = acc[mi][0];
+        part[(w * 32 + 8 * mi + fr) * kNarrow + 2 * fk + 1] = acc[mi][1];
+    }
+    __syncthreads();
+    for (uint32_t idx = t; idx < 32 * kNarrow; idx += 128)
+        partial[(size_t(split) * a_pad + col0) * kNarrow + idx] = (part[idx] + part[256 + idx]) + (part[512 + idx] + part[768 + idx]);
+}
+__global__ void GramNarrowFinalKernel(const double *__restrict__ partial, uint32_t a, uint32_t c, uint32_t a_pad, double *__restrict__ out, uint32_t ldo) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a * kNarrow) return;
+    const uint32_t col = idx / kNarrow, w = idx % kNarrow;
+    if (w >= c) return;
+    double v = 0;
+    for (uint32_t s = 0; s < kGramSplits; ++s) v += partial[(size_t(s) * a_pad + col) * kNarrow + w];
+    out[col + size_t(w) * ldo] = v;
 }
 } // namespace
 
@@ -126,10 +223,26 @@ void Axpby(DenseWorkspace &ws, size_t n, double a, const double *x, double b, co
     AxpbyKernel<<<uint32_t((n + kThreads - 1) / kThreads), kThreads, 0, s>>>(n, a, x, b, y, out);
     ws.Launches += 1;
 }
-void TallGemm(DenseWorkspace &ws, const double *V, size_t n, uint32_t m, const double *Q, uint32_t ldq, uint32_t cols_out, double *C, cudaStream_t s) {
+void TallGemm(DenseWorkspace &ws, const double *V, size_t n, uint32_t m, const double *Q, uint32_t ldq, uint32_t cols_out, double *C, cudaStream_t s, double alpha, double beta) {
     if (cols_out == 0) return;
-    TallGemmKernel<<<dim3(uint32_t((n + 63) / 64), (cols_out + 63) / 64), 128, 0, s>>>(V, n, m, Q, ldq, cols_out, C);
+    if (cols_out <= kNarrow && m <= 736) { // Q (m x 8) fits the default 48 KB of shared memory
+        const uint32_t mpad = (m + 31) & ~31u;
+        TallGemmNarrowKernel<<<uint32_t((n + 127) / 128), 128, size_t(mpad) * kNarrow * sizeof(double), s>>>(V, n, m, Q, ldq, cols_out, C, alpha, beta);
+    } else {
+        TallGemmKernel<<<dim3(uint32_t((n + 63) / 64), (cols_out + 63) / 64), 128, 0, s>>>(V, n, m, Q, ldq, cols_out, C, alpha, beta);
+    }
     ws.Launches += 1;
+}
+void Gram(DenseWorkspace &ws, const double *X, size_t n, uint32_t a, const double *Y, uint32_t c, double *out, uint32_t ldo, cudaStream_t s) {
+    if (a == 0 || c == 0) return;
+    const uint32_t a_pad = (a + 31) & ~31u;
+    ws.GramPartial.Reserve(size_t(kGramSplits) * a_pad * kNarrow);
+    for (uint32_t c0 = 0; c0 < c; c0 += kNarrow) {
+        const uint32_t cw = c - c0 < uint32_t(kNarrow) ? c - c0 : uint32_t(kNarrow);
+        GramNarrowPartialKernel<<<dim3(a_pad / 32, kGramSplits), 128, 0, s>>>(X, n, a, Y + size_t(c0) * n, cw, ws.GramPartial.Ptr, a_pad);
+        GramNarrowFinalKernel<<<(a * kNarrow + 255) / 256, 256, 0, s>>>(ws.GramPartial.Ptr, a, cw, a_pad, out + size_t(c0) * ldo, ldo);
+        ws.Launches += 2;
+    }
 }
 
 } // namespace me

@@ -12,6 +12,7 @@ namespace me {
 struct DenseWorkspace {
     DeviceBuffer<double> Partial; // per-split partial sums of the two-stage (deterministic) reductions
     DeviceBuffer<double> Coeff;   // small coefficient vectors uploaded per call
+    DeviceBuffer<double> GramPartial; // per-split partial Gram blocks
     uint32_t Launches{0};
 };
 
@@ -21,7 +22,12 @@ void GemvT(DenseWorkspace &, const double *V, size_t n, uint32_t cols, const dou
 void GemvNSub(DenseWorkspace &, const double *V, size_t n, uint32_t cols, const double *c, double *y, cudaStream_t);
 // y = a*x + b*y ; when y_out != nullptr writes there instead of y
 void Axpby(DenseWorkspace &, size_t n, double a, const double *x, double b, const double *y, double *out, cudaStream_t);
-// C[n x cols_out] = V[n x m] * Q[m x cols_out] (Q: device column-major, leading dimension ldq). FP64 DMMA.
-void TallGemm(DenseWorkspace &, const double *V, size_t n, uint32_t m, const double *Q, uint32_t ldq, uint32_t cols_out, double *C, cudaStream_t);
+// C[n x cols_out] = alpha * V[n x m] * Q[m x cols_out] + beta * C (Q: device column-major, leading dimension ldq; C must
+// not alias V). FP64 DMMA; at most 8 output columns take the streaming form that reads V exactly once.
+void TallGemm(DenseWorkspace &, const double *V, size_t n, uint32_t m, const double *Q, uint32_t ldq, uint32_t cols_out, double *C, cudaStream_t, double alpha = 1.0, double beta = 0.0);
+// out[a x c] (column-major, leading dimension ldo, device) = X[:, :a]^T Y[:, :c]: the projections of the block methods
+// (mesh2modes.cpp:379-388 Kr/Mr/C; the block form of Lanczos.h:139-182). Deterministic: fixed-order two-stage reduction.
+// X is read once per 8 columns of Y.
+void Gram(DenseWorkspace &, const double *X, size_t n, uint32_t a, const double *Y, uint32_t c, double *out, uint32_t ldo, cudaStream_t);
 
 } // namespace me

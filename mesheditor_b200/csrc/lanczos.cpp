@@ -11,7 +11,9 @@
 #include "lanczos.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <numeric>
 
@@ -147,17 +149,18 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
 
 void ShiftInvertLanczos::Op(const double *x, double *y) {
     auto s = Fem.Stream;
-    if (OpEvents.size() < size_t(2) * (Ops + 1)) {
+    if (OpEvents.size() < size_t(2) * (OpCalls + 1)) {
         cudaEvent_t a, b;
         ME_CUDA(cudaEventCreate(&a));
         ME_CUDA(cudaEventCreate(&b));
         OpEvents.push_back(a);
         OpEvents.push_back(b);
     }
-    ME_CUDA(cudaEventRecord(OpEvents[2 * Ops], s));
+    ME_CUDA(cudaEventRecord(OpEvents[2 * OpCalls], s));
     Fem.SpmvM(x, Tmp.Ptr);
     Factor.Solve(Tmp.Ptr, y, 1);
-    ME_CUDA(cudaEventRecord(OpEvents[2 * Ops + 1], s));
+    ME_CUDA(cudaEventRecord(OpEvents[2 * OpCalls + 1], s));
+    ++OpCalls;
     ++Ops;
 }
 
@@ -371,12 +374,293 @@ LanczosOutcome ShiftInvertLanczos::Compute(uint32_t nev, uint32_t ncv, double to
     }
     ME_CUDA(cudaStreamSynchronize(s));
     Factor.CheckSolves();
-    for (uint32_t i = 0; i < Ops; ++i) {
+    for (uint32_t i = 0; i < OpCalls; ++i) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, OpEvents[2 * i], OpEvents[2 * i + 1]) == cudaSuccess) out.OpSolveMs += ms;
     }
     for (auto e : OpEvents) cudaEventDestroy(e);
     OpEvents.clear();
+    OpCalls = 0;
+    out.KernelLaunches = (Fem.KernelLaunches - launches0) + (Factor.Stats.KernelLaunches - f_launches0) + Ws.Launches;
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------ block form
+// The same shift-invert Krylov iteration carried kLanczosBlock vectors at a time. One operator application is then a
+// PANEL solve (SparseCholesky::Solve with width 8: one pass over the factor for the 8 columns), which is what makes it
+// worth it on the device: the triangular solves are HBM-bound, so the bytes per Krylov vector drop ~5x. The structure is
+// the block counterpart of what Compute does: M-inner product, full re-orthogonalisation of every new block against the
+// whole basis (two classical Gram-Schmidt passes, as tall GEMMs), block M-orthonormalisation by Cholesky-QR applied
+// twice, Rayleigh-Ritz on the projected matrix T = V^T M Op V (host, <= mcap x mcap), the reference's convergence test
+// with the block residual ||R S_last|| in place of beta |s_last| (HermEigsBase.h:158-175), thick restart keeping the
+// wanted Ritz vectors plus the residual block, theta -> 1/theta + sigma (SymGEigsShiftSolver.h:170-176).
+namespace {
+// In-place Cholesky G = L L^T of a b x b matrix (row-major, lower triangle used). False when not positive definite.
+bool SmallCholesky(uint32_t b, std::vector<double> &g) {
+    for (uint32_t j = 0; j < b; ++j) {
+        double d = g[size_t(j) * b + j];
+        for (uint32_t k = 0; k < j; ++k) d -= g[size_t(j) * b + k] * g[size_t(j) * b + k];
+        if (!(d > 0.0) || !std::isfinite(d)) return false;
+        const double l = std::sqrt(d);
+        g[size_t(j) * b + j] = l;
+        for (uint32_t i = j + 1; i < b; ++i) {
+            double v = g[size_t(i) * b + j];
+            for (uint32_t k = 0; k < j; ++k) v -= g[size_t(i) * b + k] * g[size_t(j) * b + k];
+            g[size_t(i) * b + j] = v / l;
+        }
+        for (uint32_t c = j + 1; c < b; ++c) g[size_t(j) * b + c] = 0.0;
+    }
+    return true;
+}
+// X = L^-1 (row-major, lower) of a lower-triangular L.
+std::vector<double> LowerInverse(uint32_t b, const std::vector<double> &l) {
+    std::vector<double> x(size_t(b) * b, 0.0);
+    for (uint32_t c = 0; c < b; ++c) {
+        x[size_t(c) * b + c] = 1.0 / l[size_t(c) * b + c];
+        for (uint32_t r = c + 1; r < b; ++r) {
+            double v = 0;
+            for (uint32_t k = c; k < r; ++k) v -= l[size_t(r) * b + k] * x[size_t(k) * b + c];
+            x[size_t(r) * b + c] = v / l[size_t(r) * b + r];
+        }
+    }
+    return x;
+}
+} // namespace
+
+uint32_t ShiftInvertLanczos::BlockBasisSize(uint32_t nev) {
+    const uint32_t extra = std::max(96u, nev / 2); // a deeper basis than the reference's nev + 20: restarts (host eigensolves) halve, the extra columns cost HBM only
+    return (nev + extra + kLanczosBlock - 1) / kLanczosBlock * kLanczosBlock;
+}
+
+void ShiftInvertLanczos::OpPanel(const double *x, double *y, uint32_t width) {
+    auto s = Fem.Stream;
+    const size_t n = Fem.N;
+    if (OpEvents.size() < size_t(2) * (OpCalls + 1)) {
+        cudaEvent_t a, b;
+        ME_CUDA(cudaEventCreate(&a));
+        ME_CUDA(cudaEventCreate(&b));
+        OpEvents.push_back(a);
+        OpEvents.push_back(b);
+    }
+    Tmp.Reserve(n * width);
+    ME_CUDA(cudaEventRecord(OpEvents[2 * OpCalls], s));
+    for (uint32_t j = 0; j < width; ++j) Fem.SpmvM(x + size_t(j) * n, Tmp.Ptr + size_t(j) * n);
+    Factor.Solve(Tmp.Ptr, y, width);
+    ME_CUDA(cudaEventRecord(OpEvents[2 * OpCalls + 1], s));
+    ++OpCalls;
+    Ops += width;
+}
+
+LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32_t max_restarts, const volatile int *cancelled) {
+    LanczosOutcome out;
+    const size_t n = Fem.N;
+    constexpr uint32_t b = kLanczosBlock;
+    const uint32_t mcap = BlockBasisSize(nev);
+    if (nev < 1 || size_t(mcap) + b > n) Fail(ME_BAD_ARG, "block Lanczos: basis of %u + %u columns does not fit n = %zu", mcap, b, n);
+    ME_CUDA(cudaSetDevice(Fem.Device));
+    auto s = Fem.Stream;
+    const double eps = std::numeric_limits<double>::epsilon(), eps23 = std::pow(eps, 2.0 / 3.0);
+    const uint32_t launches0 = Fem.KernelLaunches, f_launches0 = Factor.Stats.KernelLaunches;
+    const uint32_t tcap = mcap + b;
+
+    DeviceBuffer<double> Va, Vb, W, Wb, MW, H1, H2, Small;
+    Va.Reserve(n * tcap), Vb.Reserve(n * tcap), W.Reserve(n * b), Wb.Reserve(n * b), MW.Reserve(n * b);
+    H1.Reserve(size_t(tcap) * b), H2.Reserve(size_t(tcap) * b), Small.Reserve(std::max<size_t>(size_t(tcap) * tcap, 4 * b * b));
+    double *V = Va.Ptr, *V2 = Vb.Ptr;
+    auto col = [&](double *base, uint32_t j) { return base + size_t(j) * n; };
+    std::vector<double> T(size_t(tcap) * tcap, 0.0), h1(size_t(tcap) * b), h2(size_t(tcap) * b), g(size_t(b) * b), small(size_t(b) * b);
+    auto Tm = [&](uint32_t r, uint32_t c) -> double & { return T[size_t(r) * tcap + c]; };
+    auto mass_product = [&](const double *x, double *y) {
+        for (uint32_t j = 0; j < b; ++j) Fem.SpmvM(x + size_t(j) * n, y + size_t(j) * n);
+    };
+    // One Cholesky-QR pass in the M inner product: dst = src * L^-T with src^T M src = L L^T. r (row-major b x b)
+    // receives L^T. False when the block has lost rank.
+    auto cholqr_pass = [&](const double *src, double *dst, std::vector<double> &r) {
+        mass_product(src, MW.Ptr);
+        Gram(Ws, src, n, b, MW.Ptr, b, Small.Ptr, b, s);
+        ME_CUDA(cudaMemcpyAsync(small.data(), Small.Ptr, size_t(b) * b * sizeof(double), cudaMemcpyDeviceToHost, s));
+        ME_CUDA(cudaStreamSynchronize(s));
+        for (uint32_t i = 0; i < b; ++i)
+            for (uint32_t j = 0; j < b; ++j) g[size_t(i) * b + j] = 0.5 * (small[i + size_t(j) * b] + small[j + size_t(i) * b]);
+        if (!SmallCholesky(b, g)) return false;
+        const std::vector<double> linv = LowerInverse(b, g);
+        // Q = L^-T, column-major b x b: Q[i + j b] = Linv[j][i]
+        for (uint32_t i = 0; i < b; ++i)
+            for (uint32_t j = 0; j < b; ++j) small[i + size_t(j) * b] = linv[size_t(j) * b + i];
+        ME_CUDA(cudaMemcpyAsync(Small.Ptr + size_t(2) * b * b, small.data(), size_t(b) * b * sizeof(double), cudaMemcpyHostToDevice, s));
+        TallGemm(Ws, src, n, b, Small.Ptr + size_t(2) * b * b, b, b, dst, s);
+        r.assign(size_t(b) * b, 0.0);
+        for (uint32_t i = 0; i < b; ++i)
+            for (uint32_t j = i; j < b; ++j) r[size_t(i) * b + j] = g[size_t(j) * b + i];
+        return true;
+    };
+    // dst = M-orthonormal basis of span(src) (src is overwritten), R (row-major b x b upper) with src = dst R.
+    std::vector<double> r1, r2, R(size_t(b) * b);
+    auto orthonormalize = [&](double *src, double *scratch, double *dst) {
+        if (!cholqr_pass(src, scratch, r1) || !cholqr_pass(scratch, dst, r2)) return false;
+        for (uint32_t i = 0; i < b; ++i)
+            for (uint32_t j = 0; j < b; ++j) {
+                double v = 0;
+                for (uint32_t k = 0; k < b; ++k) v += r2[size_t(i) * b + k] * r1[size_t(k) * b + j];
+                R[size_t(i) * b + j] = v;
+            }
+        return true;
+    };
+
+    // Start block: Op applied to the reference's pseudo-random residual (SimpleRandom, seed 0 -> 1), b columns of it.
+    {
+        std::vector<double> r0(n * b);
+        uint64_t x = 1;
+        for (auto &v : r0) {
+            x = (x * 16807ull) % 2147483647ull;
+            v = double(x) / 2147483647.0 - 0.5;
+        }
+        ME_CUDA(cudaMemcpyAsync(Wb.Ptr, r0.data(), r0.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        ME_CUDA(cudaStreamSynchronize(s));
+    }
+    OpPanel(Wb.Ptr, W.Ptr, b);
+    if (!orthonormalize(W.Ptr, Wb.Ptr, col(V, 0))) Fail(ME_NOT_CONVERGED, "block Lanczos: the start block is rank deficient");
+
+    // ME_PROFILE=1: synchronising section timers printed to stderr (diagnostics only; perturbs the overlap of host and device).
+    const bool prof = std::getenv("ME_PROFILE") != nullptr;
+    double sec[5]{};
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double mark_t = now();
+    auto mark = [&](int which) {
+        if (!prof) return;
+        cudaStreamSynchronize(s);
+        const double t = now();
+        sec[which] += t - mark_t;
+        mark_t = t;
+    };
+    uint32_t m = 0; // expanded columns: T is m x m, the residual block sits in columns [m, m + b)
+    std::vector<double> evec, theta, ritz_val, est;
+    std::vector<uint32_t> order;
+    uint32_t iter = 0, nconv = 0;
+    bool broke = false;
+    for (;; ++iter) {
+        while (m < mcap) {
+            if (cancelled && *cancelled) {
+                out.Cancelled = true;
+                break;
+            }
+            const uint32_t cur = m + b;
+            mark(4);
+            OpPanel(col(V, m), W.Ptr, b);
+            mark(0);
+            // Two Gram-Schmidt passes against the whole basis; the coefficients are the block column of T.
+            mass_product(W.Ptr, MW.Ptr);
+            Gram(Ws, V, n, cur, MW.Ptr, b, H1.Ptr, cur, s);
+            TallGemm(Ws, V, n, cur, H1.Ptr, cur, b, W.Ptr, s, -1.0, 1.0);
+            mass_product(W.Ptr, MW.Ptr);
+            Gram(Ws, V, n, cur, MW.Ptr, b, H2.Ptr, cur, s);
+            TallGemm(Ws, V, n, cur, H2.Ptr, cur, b, W.Ptr, s, -1.0, 1.0);
+            ME_CUDA(cudaMemcpyAsync(h1.data(), H1.Ptr, size_t(cur) * b * sizeof(double), cudaMemcpyDeviceToHost, s));
+            ME_CUDA(cudaMemcpyAsync(h2.data(), H2.Ptr, size_t(cur) * b * sizeof(double), cudaMemcpyDeviceToHost, s));
+            mark(1);
+            if (!orthonormalize(W.Ptr, Wb.Ptr, col(V, cur))) { // (synchronises: h1, h2 are on the host now)
+                broke = true;
+                break;
+            }
+            mark(2);
+            for (uint32_t j = 0; j < b; ++j)
+                for (uint32_t i = 0; i < cur; ++i) {
+                    const double v = h1[i + size_t(j) * cur] + h2[i + size_t(j) * cur];
+                    Tm(i, m + j) = v;
+                    Tm(m + j, i) = v;
+                }
+            for (uint32_t i = 0; i < b; ++i) // the diagonal block was written twice above: make it exactly symmetric
+                for (uint32_t j = i + 1; j < b; ++j) Tm(m + i, m + j) = Tm(m + j, m + i) = 0.5 * (Tm(m + i, m + j) + Tm(m + j, m + i));
+            for (uint32_t i = 0; i < b; ++i)
+                for (uint32_t j = 0; j < b; ++j) Tm(cur + i, m + j) = Tm(m + j, cur + i) = R[size_t(i) * b + j];
+            m += b;
+        }
+        if (out.Cancelled || broke) break;
+        // Rayleigh-Ritz on T[0:m, 0:m].
+        mark(4);
+        evec.assign(size_t(m) * m, 0.0);
+        for (uint32_t i = 0; i < m; ++i)
+            for (uint32_t j = 0; j < m; ++j) evec[size_t(i) * m + j] = 0.5 * (Tm(i, j) + Tm(j, i));
+        if (!SymmetricEigen(m, evec, theta)) Fail(ME_NOT_CONVERGED, "block Lanczos: projected eigenproblem did not converge");
+        order.resize(m);
+        std::iota(order.begin(), order.end(), 0u);
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return std::abs(theta[a]) > std::abs(theta[c]); });
+        ritz_val.resize(m), est.resize(m);
+        for (uint32_t i = 0; i < m; ++i) {
+            ritz_val[i] = theta[order[i]];
+            double sq = 0;
+            for (uint32_t r = 0; r < b; ++r) {
+                double v = 0;
+                for (uint32_t c = 0; c < b; ++c) v += Tm(m + r, m - b + c) * evec[size_t(m - b + c) * m + order[i]];
+                sq += v * v;
+            }
+            est[i] = std::sqrt(sq);
+        }
+        nconv = 0;
+        for (uint32_t i = 0; i < nev; ++i)
+            if (est[i] < tol * std::max(eps23, std::abs(ritz_val[i]))) ++nconv;
+        mark(3);
+        if (nconv >= nev || iter >= max_restarts) break;
+        // Thick restart: keep k Ritz vectors (the reference's rule, HermEigsBase.h:178-202, rounded so that whole
+        // blocks fill the basis again) and the residual block.
+        uint32_t k = nev + std::min(nconv, (m - nev) / 2);
+        k = std::min(k, m - b);
+        k = mcap - (mcap - k) / b * b;
+        std::vector<double> q(size_t(m) * k);
+        for (uint32_t j = 0; j < k; ++j)
+            for (uint32_t r = 0; r < m; ++r) q[r + size_t(j) * m] = evec[size_t(r) * m + order[j]];
+        Small.Reserve(q.size());
+        ME_CUDA(cudaMemcpyAsync(Small.Ptr, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        TallGemm(Ws, V, n, m, Small.Ptr, m, k, V2, s);
+        ME_CUDA(cudaMemcpyAsync(col(V2, k), col(V, m), n * b * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        ME_CUDA(cudaStreamSynchronize(s));
+        std::swap(V, V2);
+        std::vector<double> border(size_t(b) * k);
+        for (uint32_t r = 0; r < b; ++r)
+            for (uint32_t j = 0; j < k; ++j) {
+                double v = 0;
+                for (uint32_t c = 0; c < b; ++c) v += Tm(m + r, m - b + c) * evec[size_t(m - b + c) * m + order[j]];
+                border[size_t(r) * k + j] = v;
+            }
+        std::fill(T.begin(), T.end(), 0.0);
+        for (uint32_t j = 0; j < k; ++j) {
+            Tm(j, j) = ritz_val[j];
+            for (uint32_t r = 0; r < b; ++r) Tm(k + r, j) = Tm(j, k + r) = border[size_t(r) * k + j];
+        }
+        m = k;
+    }
+    mark(4);
+    if (prof) fprintf(stderr, "[block lanczos] op %.3f s, reorth %.3f s, cholqr %.3f s, ritz (host) %.3f s, restart+other %.3f s, %u panel ops, %u restarts\n", sec[0], sec[1], sec[2], sec[3], sec[4], OpCalls, iter);
+    out.Restarts = iter + 1;
+    out.OpApplications = Ops;
+    out.Converged = !out.Cancelled && !broke && nconv >= nev;
+    if (out.Converged) {
+        std::vector<uint32_t> pick(nev);
+        std::iota(pick.begin(), pick.end(), 0u);
+        std::vector<double> lambda(nev);
+        for (uint32_t i = 0; i < nev; ++i) lambda[i] = 1.0 / ritz_val[i] + Sigma;
+        std::stable_sort(pick.begin(), pick.end(), [&](uint32_t a, uint32_t c) { return lambda[a] < lambda[c]; });
+        out.Eigenvalues.resize(nev);
+        std::vector<double> q(size_t(m) * nev);
+        for (uint32_t j = 0; j < nev; ++j) {
+            out.Eigenvalues[j] = lambda[pick[j]];
+            for (uint32_t r = 0; r < m; ++r) q[r + size_t(j) * m] = evec[size_t(r) * m + order[pick[j]]];
+        }
+        Small.Reserve(q.size());
+        ME_CUDA(cudaMemcpyAsync(Small.Ptr, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        Vectors.Reserve(n * nev);
+        TallGemm(Ws, V, n, m, Small.Ptr, m, nev, Vectors.Ptr, s);
+    }
+    ME_CUDA(cudaStreamSynchronize(s));
+    Factor.CheckSolves();
+    for (uint32_t i = 0; i < OpCalls; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, OpEvents[2 * i], OpEvents[2 * i + 1]) == cudaSuccess) out.OpSolveMs += ms;
+    }
+    for (auto e : OpEvents) cudaEventDestroy(e);
+    OpEvents.clear();
+    OpCalls = 0;
+    out.RankLost = broke;
     out.KernelLaunches = (Fem.KernelLaunches - launches0) + (Factor.Stats.KernelLaunches - f_launches0) + Ws.Launches;
     return out;
 }

@@ -12,10 +12,13 @@
 
 namespace me {
 
+constexpr uint32_t kLanczosBlock = 8; // columns per operator application of the block form = width of one panel sweep
+
 struct LanczosOutcome {
     std::vector<double> Eigenvalues; // ascending, nev of them when converged
     uint32_t OpApplications{0}, Restarts{0};
     bool Converged{false}, Cancelled{false};
+    bool RankLost{false};            // block form only: a new block lost rank (the caller falls back to the single-vector form)
     double OpSolveMs{0};             // device time inside the shift-invert operator (M x + two triangular solves)
     uint32_t KernelLaunches{0};
 };
@@ -29,17 +32,22 @@ public:
     ShiftInvertLanczos(FemSystem &fem, SparseCholesky &factor, double sigma) : Fem(fem), Factor(factor), Sigma(sigma) {}
     // On success Vectors holds the n x nev M-orthonormal eigenvectors (column-major, device).
     LanczosOutcome Compute(uint32_t nev, uint32_t ncv, double tol, uint32_t max_restarts, const volatile int *cancelled);
+    // The block form (kLanczosBlock vectors per operator application, panel solves). Basis size BlockBasisSize(nev);
+    // needs BlockBasisSize(nev) + kLanczosBlock <= n.
+    LanczosOutcome ComputeBlock(uint32_t nev, double tol, uint32_t max_restarts, const volatile int *cancelled);
+    static uint32_t BlockBasisSize(uint32_t nev);
     DeviceBuffer<double> Vectors;
 
 private:
     void Op(const double *x, double *y); // y = (K - sigma M)^-1 M x
+    void OpPanel(const double *x, double *y, uint32_t width); // the same for `width` columns (one panel solve)
     FemSystem &Fem;
     SparseCholesky &Factor;
     double Sigma;
     DenseWorkspace Ws;
     DeviceBuffer<double> Tmp;
     std::vector<cudaEvent_t> OpEvents;
-    uint32_t Ops{0};
+    uint32_t Ops{0}, OpCalls{0};
 };
 
 } // namespace me

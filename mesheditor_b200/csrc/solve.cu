@@ -9,6 +9,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <unordered_map>
 
@@ -381,7 +383,18 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
 
     t0 = Seconds();
     ShiftInvertLanczos lanczos(fem, factor, sigma);
-    const LanczosOutcome outcome = lanczos.Compute(nev, ncv, config.Tolerance, config.MaxRestarts, monitor ? &monitor->cancelled : nullptr);
+    // Block form (panel solves, 8 Krylov vectors per pass over the factor) whenever its larger basis is a small part of
+    // the problem; the single-vector form otherwise (tiny meshes) and as the fallback if a block ever loses rank.
+    // ME_LANCZOS=single|block overrides the choice (A/B measurements).
+    const volatile int *cancel_flag = monitor ? &monitor->cancelled : nullptr;
+    bool use_block = size_t(4) * (ShiftInvertLanczos::BlockBasisSize(nev) + kLanczosBlock) <= n;
+    if (const char *env = std::getenv("ME_LANCZOS")) {
+        if (!std::strcmp(env, "single")) use_block = false;
+        else if (!std::strcmp(env, "block")) use_block = size_t(ShiftInvertLanczos::BlockBasisSize(nev)) + kLanczosBlock <= n;
+    }
+    LanczosOutcome outcome;
+    if (use_block) outcome = lanczos.ComputeBlock(nev, config.Tolerance, config.MaxRestarts, cancel_flag);
+    if (!use_block || outcome.RankLost) outcome = lanczos.Compute(nev, ncv, config.Tolerance, config.MaxRestarts, cancel_flag);
     profile.iterate = Seconds() - t0;
     profile.op_solve = outcome.OpSolveMs * 1e-3;
     profile.op_applications = outcome.OpApplications;

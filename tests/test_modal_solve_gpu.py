@@ -35,9 +35,14 @@ def test_golden_models(name):
     assert p["dofs"] > 0 and p["op_applications"] >= 65 and p["restarts"] >= 1 and p["kernel_launches"] > 0
 
 
+@pytest.mark.parametrize("form", ["block", "single"])
 @pytest.mark.parametrize("order,dims,modes", [(2, (8, 3, 2), 20), (1, (14, 9, 7), 40)])
-def test_eigenpairs_match_oracle_fp64(order, dims, modes):
+def test_eigenpairs_match_oracle_fp64(order, dims, modes, form, monkeypatch):
+    """Both forms of the shift-invert iteration (block: 8 Krylov vectors per panel solve; single: the reference's
+    vector-at-a-time recurrence) against the oracle in FP64."""
     from mesheditor_b200 import mesh2modes, solver_config
+
+    monkeypatch.setenv("ME_LANCZOS", form)
 
     points, tets = om.kuhn_block(*dims, size=(0.4, 0.15, 0.1))
     mat = om.MATERIALS["Ceramic"]
