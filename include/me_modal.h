@@ -191,9 +191,10 @@ typedef struct MeModalResult MeModalResult; /* modal::ModalResult (mesh2modes.h:
 /* modal::mesh2modes (src/audio/mesh2modes.h:77, mesh2modes.cpp:605-658).
  *   points_xyz [n_points][3] doubles, tets [n_tets][4] positively oriented (TetMesh, src/mesh/TetMesh.h:10-13);
  *   excite_xyz [n_excite][3] floats (SI), each sampled at its nearest tet point; baked_scale[3];
- *   seed_basis: a prior solve's eigenvector basis (seed_rows x seed_cols floats, column-major) or NULL. The warm
- *   re-solve (SubspaceIterate, mesh2modes.cpp:339-428) is not built yet: a seed is accepted and the cold path runs,
- *   which returns the same eigenpairs to the solver tolerance;
+ *   seed_basis: a prior solve's eigenvector basis (seed_rows x seed_cols floats, column-major; SolveReuse::SeedBasis,
+ *   mesh2modes.h:28-36) or NULL. When seed_rows equals this mesh's DOF count and seed_cols >= min(NumFemModes, n-1) the
+ *   warm path runs: subspace iteration over NumFemModes + 15 columns to config->warm_tolerance
+ *   (SubspaceIterate, mesh2modes.cpp:339-428, selected at :459-472); any other seed falls back to the cold solve;
  *   keep_basis: fill the result's basis (SolveReuse::KeepBasis).
  * Status mirrors the reference's failure modes: ME_CANCELLED / ME_NOT_CONVERGED / ME_NO_MODES leave *out holding an
  * EMPTY result (the reference returns an empty ModalResult); ME_FACTOR_FAILED is the reference's std::runtime_error. */

@@ -50,4 +50,29 @@ private:
     uint32_t Ops{0}, OpCalls{0};
 };
 
+// Warm re-solve (SubspaceIterate, src/audio/mesh2modes.cpp:339-428): block subspace iteration with Rayleigh-Ritz,
+// prefix locking at relative eigenvalue change < tol, and deflation against the locked pairs.
+struct SubspaceOutcome {
+    std::vector<double> Eigenvalues; // ascending, nev of them; empty when not converged (the reference's failure convention)
+    uint32_t Iterations{0}, OpApplications{0};
+    bool Converged{false}, Cancelled{false};
+    double OpSolveMs{0};
+    uint32_t KernelLaunches{0};
+};
+
+class SubspaceIteration {
+public:
+    SubspaceIteration(FemSystem &fem, SparseCholesky &factor, double sigma) : Fem(fem), Factor(factor), Sigma(sigma) {}
+    // seed: host floats, n x seed_cols column-major (the previous solve's basis); the leading min(seed_cols, p) panel
+    // columns start from it, the rest from Gaussian noise. On success Vectors holds the n x nev M-orthonormal Ritz vectors.
+    SubspaceOutcome Compute(uint32_t nev, uint32_t p, double tol, uint32_t max_iters, const float *seed, uint32_t seed_cols, const volatile int *cancelled);
+    DeviceBuffer<double> Vectors;
+
+private:
+    FemSystem &Fem;
+    SparseCholesky &Factor;
+    double Sigma;
+    DenseWorkspace Ws;
+};
+
 } // namespace me

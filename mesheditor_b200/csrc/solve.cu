@@ -284,7 +284,8 @@ struct MeFactor {
 namespace me {
 namespace {
 MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const MeMaterial *c_material, const float *excite, uint32_t n_excite,
-                   const float baked_scale[3], const MeSolverConfig *c_config, int keep_basis, MeJobMonitor *monitor, MeModalResult &res) {
+                   const float baked_scale[3], const MeSolverConfig *c_config, const float *seed_basis, uint32_t seed_rows, uint32_t seed_cols, int keep_basis, MeJobMonitor *monitor,
+                   MeModalResult &res) {
     const Config config = FromC(c_config);
     const Material material = FromC(c_material);
     const float unit_scale[3]{1, 1, 1};
@@ -362,7 +363,7 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
     profile.sample_excite = Seconds() - t0;
     res.PointCount = uint32_t(sample_points.size());
 
-    // ComputeModes, cold path (mesh2modes.cpp:441-512).
+    // ComputeModes (mesh2modes.cpp:441-512).
     const uint32_t n = fem.N;
     const uint32_t nev = std::min(config.NumFemModes, n - 1);
     const uint32_t ncv = std::min(std::max(nev + 20, 20u), n);
@@ -382,34 +383,56 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
     if (cancelled()) return ME_CANCELLED;
 
     t0 = Seconds();
-    ShiftInvertLanczos lanczos(fem, factor, sigma);
-    // Block form (panel solves, 8 Krylov vectors per pass over the factor) whenever its larger basis is a small part of
-    // the problem; the single-vector form otherwise (tiny meshes) and as the fallback if a block ever loses rank.
-    // ME_LANCZOS=single|block overrides the choice (A/B measurements).
     const volatile int *cancel_flag = monitor ? &monitor->cancelled : nullptr;
-    bool use_block = size_t(4) * (ShiftInvertLanczos::BlockBasisSize(nev) + kLanczosBlock) <= n;
-    if (const char *env = std::getenv("ME_LANCZOS")) {
-        if (!std::strcmp(env, "single")) use_block = false;
-        else if (!std::strcmp(env, "block")) use_block = size_t(ShiftInvertLanczos::BlockBasisSize(nev)) + kLanczosBlock <= n;
-    }
-    LanczosOutcome outcome;
-    if (use_block) outcome = lanczos.ComputeBlock(nev, config.Tolerance, config.MaxRestarts, cancel_flag);
-    if (!use_block || outcome.RankLost) outcome = lanczos.Compute(nev, ncv, config.Tolerance, config.MaxRestarts, cancel_flag);
-    profile.iterate = Seconds() - t0;
-    profile.op_solve = outcome.OpSolveMs * 1e-3;
-    profile.op_applications = outcome.OpApplications;
-    profile.restarts = outcome.Restarts;
-    profile.kernel_launches = fem.KernelLaunches + factor.Stats.KernelLaunches + outcome.KernelLaunches;
-    if (outcome.Cancelled) return ME_CANCELLED;
-    if (!outcome.Converged) {
-        SetLastError("eigensolver did not converge in %u restarts", config.MaxRestarts);
-        return ME_NOT_CONVERGED;
+    // A basis solved over a different mesh cannot seed this solve: it falls back to the cold path (mesh2modes.cpp:459-464).
+    const bool use_subspace = seed_basis != nullptr && seed_rows == n && seed_cols >= nev;
+    ShiftInvertLanczos lanczos(fem, factor, sigma);
+    SubspaceIteration subspace(fem, factor, sigma);
+    const double *eigenvectors = nullptr; // device, n x nev column-major, M-orthonormal
+    if (use_subspace) {
+        // Warm path: subspace iteration re-converges the seed in a few block iterations (:466-472).
+        const SubspaceOutcome warm = subspace.Compute(nev, std::min(nev + 15, n), config.WarmTolerance, config.MaxRestarts, seed_basis, seed_cols, cancel_flag);
+        profile.iterate = Seconds() - t0;
+        profile.op_solve = warm.OpSolveMs * 1e-3;
+        profile.op_applications = warm.OpApplications;
+        profile.restarts = warm.Iterations;
+        profile.kernel_launches = fem.KernelLaunches + factor.Stats.KernelLaunches + warm.KernelLaunches;
+        if (warm.Cancelled) return ME_CANCELLED;
+        if (!warm.Converged) {
+            SetLastError("warm subspace iteration did not converge in %u iterations", config.MaxRestarts);
+            return ME_NOT_CONVERGED;
+        }
+        res.Eigenvalues = warm.Eigenvalues;
+        eigenvectors = subspace.Vectors.Ptr;
+    } else {
+        // Block form (panel solves, 8 Krylov vectors per pass over the factor) whenever its larger basis is a small part of
+        // the problem; the single-vector form otherwise (tiny meshes) and as the fallback if a block ever loses rank.
+        // ME_LANCZOS=single|block overrides the choice (A/B measurements).
+        bool use_block = size_t(4) * (ShiftInvertLanczos::BlockBasisSize(nev) + kLanczosBlock) <= n;
+        if (const char *env = std::getenv("ME_LANCZOS")) {
+            if (!std::strcmp(env, "single")) use_block = false;
+            else if (!std::strcmp(env, "block")) use_block = size_t(ShiftInvertLanczos::BlockBasisSize(nev)) + kLanczosBlock <= n;
+        }
+        LanczosOutcome outcome;
+        if (use_block) outcome = lanczos.ComputeBlock(nev, config.Tolerance, config.MaxRestarts, cancel_flag);
+        if (!use_block || outcome.RankLost) outcome = lanczos.Compute(nev, ncv, config.Tolerance, config.MaxRestarts, cancel_flag);
+        profile.iterate = Seconds() - t0;
+        profile.op_solve = outcome.OpSolveMs * 1e-3;
+        profile.op_applications = outcome.OpApplications;
+        profile.restarts = outcome.Restarts;
+        profile.kernel_launches = fem.KernelLaunches + factor.Stats.KernelLaunches + outcome.KernelLaunches;
+        if (outcome.Cancelled) return ME_CANCELLED;
+        if (!outcome.Converged) {
+            SetLastError("eigensolver did not converge in %u restarts", config.MaxRestarts);
+            return ME_NOT_CONVERGED;
+        }
+        res.Eigenvalues = outcome.Eigenvalues;
+        eigenvectors = lanczos.Vectors.Ptr;
     }
     progress(0.95f);
 
     // Extract: shapes at the sample points, optional basis, post-processing.
     t0 = Seconds();
-    res.Eigenvalues = outcome.Eigenvalues;
     res.SummaryShapes.assign(size_t(res.PointCount) * nev * 3, 0.f);
     if (res.PointCount) {
         DeviceBuffer<uint32_t> d_pts;
@@ -417,7 +440,7 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
         d_pts.Upload(sample_points, s);
         d_shapes.Reserve(res.SummaryShapes.size());
         const uint32_t count = res.PointCount * nev * 3;
-        GatherShapesKernel<<<(count + 255) / 256, 256, 0, s>>>(lanczos.Vectors.Ptr, n, nev, d_pts.Ptr, res.PointCount, d_shapes.Ptr);
+        GatherShapesKernel<<<(count + 255) / 256, 256, 0, s>>>(eigenvectors, n, nev, d_pts.Ptr, res.PointCount, d_shapes.Ptr);
         ME_CUDA(cudaMemcpyAsync(res.SummaryShapes.data(), d_shapes.Ptr, res.SummaryShapes.size() * 4, cudaMemcpyDeviceToHost, s));
         ME_CUDA(cudaStreamSynchronize(s));
     }
@@ -425,7 +448,7 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
         DeviceBuffer<float> d_basis;
         const size_t count = size_t(n) * nev;
         d_basis.Reserve(count);
-        CastBasisKernel<<<uint32_t((count + 255) / 256), 256, 0, s>>>(lanczos.Vectors.Ptr, count, d_basis.Ptr);
+        CastBasisKernel<<<uint32_t((count + 255) / 256), 256, 0, s>>>(eigenvectors, count, d_basis.Ptr);
         res.Basis.resize(count);
         ME_CUDA(cudaMemcpyAsync(res.Basis.data(), d_basis.Ptr, count * 4, cudaMemcpyDeviceToHost, s));
         ME_CUDA(cudaStreamSynchronize(s));
@@ -456,13 +479,12 @@ void me_solver_config_default(MeSolverConfig *c) {
 MeStatus me_modal_solve(const double *points_xyz, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const MeMaterial *material, const float *excite_xyz, uint32_t n_excite,
                         const float baked_scale[3], const MeSolverConfig *config, const float *seed_basis, uint32_t seed_rows, uint32_t seed_cols, int keep_basis,
                         MeJobMonitor *monitor, MeModalResult **out) {
-    (void)seed_basis, (void)seed_rows, (void)seed_cols; // warm re-solve: next; the cold path serves it
     MeStatus inner = ME_OK;
     const MeStatus outer = Guard([&] {
         if (!out) Fail(ME_BAD_ARG, "null out pointer");
         *out = nullptr;
         auto res = std::make_unique<MeModalResult>();
-        inner = me::SolveImpl(points_xyz, n_points, tets, n_tets, material, excite_xyz, n_excite, baked_scale, config, keep_basis, monitor, *res);
+        inner = me::SolveImpl(points_xyz, n_points, tets, n_tets, material, excite_xyz, n_excite, baked_scale, config, seed_basis, seed_rows, seed_cols, keep_basis, monitor, *res);
         if (inner == ME_CANCELLED || inner == ME_NOT_CONVERGED) {
             // The reference returns a default-constructed (empty) ModalResult here (mesh2modes.cpp:462,479,490,616).
             const MeSolveProfile profile = res->Profile;

@@ -90,8 +90,9 @@ def _read_result(h, status):
     return r
 
 
-def mesh2modes(points, tets, mat, excite_positions, baked_scale=(1.0, 1.0, 1.0), config=None, keep_basis=False, monitor=None):
-    """modal::mesh2modes (mesh2modes.h:77). Like the reference, a cancelled / non-converged / no-mode solve returns an EMPTY
+def mesh2modes(points, tets, mat, excite_positions, baked_scale=(1.0, 1.0, 1.0), config=None, keep_basis=False, monitor=None, seed_basis=None):
+    """modal::mesh2modes (mesh2modes.h:77). seed_basis (n x cols, a prior result's `basis`) selects the warm re-solve
+    (SolveReuse::SeedBasis). Like the reference, a cancelled / non-converged / no-mode solve returns an EMPTY
     result (status says which); a failed factorisation raises (the reference throws std::runtime_error)."""
     L = lib()
     pts = np.ascontiguousarray(points, np.float64)
@@ -101,7 +102,11 @@ def mesh2modes(points, tets, mat, excite_positions, baked_scale=(1.0, 1.0, 1.0),
     cfg = config or solver_config()
     m = material(mat)
     h = C.c_void_p()
-    status = L.me_modal_solve(pts.ctypes.data, len(pts), tt.ctypes.data, len(tt), C.byref(m), ex.ctypes.data, len(ex), scale, C.byref(cfg), None, 0, 0, int(keep_basis),
+    seed, seed_rows, seed_cols = None, 0, 0
+    if seed_basis is not None:
+        seed_arr = np.asfortranarray(seed_basis, np.float32)  # column-major n x cols
+        seed, (seed_rows, seed_cols) = seed_arr.ctypes.data, seed_arr.shape
+    status = L.me_modal_solve(pts.ctypes.data, len(pts), tt.ctypes.data, len(tt), C.byref(m), ex.ctypes.data, len(ex), scale, C.byref(cfg), seed, seed_rows, seed_cols, int(keep_basis),
                               C.byref(monitor) if monitor is not None else None, C.byref(h))
     if status not in (ME_OK, ME_CANCELLED, ME_NOT_CONVERGED, ME_NO_MODES):
         raise MeError(status, L.me_last_error().decode())

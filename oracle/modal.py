@@ -58,6 +58,7 @@ class SolverConfig:
     num_modes: int = 30
     num_fem_modes: int = 45
     tolerance: float = 1e-8
+    warm_tolerance: float = 1e-4
     max_restarts: int = 100
     fundamental_freq: float | None = None
 
@@ -311,6 +312,65 @@ def eigensolve(M, K, config, tol=1e-12):
     return vals[idx], vecs[:, idx]
 
 
+
+def subspace_iterate(M, K, nev, p, sigma, tol, max_iters, x0, rng_seed=20260710):
+    """SubspaceIterate (mesh2modes.cpp:339-428): the warm path of ComputeModes. x0 (n x cols, float32) seeds the leading
+    panel columns, Gaussian columns fill the rest (the reference draws them from std::mt19937_64{20260710} through
+    libc++'s normal_distribution; numpy's generator stands in, converged results do not depend on the draw). Returns
+    (eigenvalues ascending [nev] or empty, eigenvectors n x nev M-orthonormal, iterations, op_applications)."""
+    import scipy.linalg as sla
+    import scipy.sparse.linalg as spla
+
+    Mf, Kf = M.to_scipy_full().tocsc(), K.to_scipy_full().tocsc()
+    n = Mf.shape[0]
+    lu = spla.splu((Kf - sigma * Mf).tocsc())
+    X = np.zeros((n, p))
+    seeded = min(x0.shape[1], p)
+    X[:, :seeded] = np.asarray(x0, np.float32)[:, :seeded].astype(np.float64)
+    X[:, seeded:] = np.random.default_rng(rng_seed).standard_normal((n, p - seeded))
+    MX = Mf @ X
+    XL, MXL, theta_locked = np.zeros((n, nev)), np.zeros((n, nev)), np.zeros(nev)
+    prev = np.full(nev, np.finfo(np.float64).max)
+    c = iterations = ops = 0
+    for it in range(max_iters):
+        w = p - c
+        Xbar = lu.solve(MX)
+        ops += w
+        Kr = Xbar.T @ MX
+        MXbar = Mf @ Xbar
+        if c > 0:
+            C = XL[:, :c].T @ MXbar
+            Xbar = Xbar - XL[:, :c] @ C
+            MXbar = MXbar - MXL[:, :c] @ C
+            Kr = Kr - C.T @ (theta_locked[:c, None] * C)
+        Mr = Xbar.T @ MXbar
+        Kr, Mr = 0.5 * (Kr + Kr.T), 0.5 * (Mr + Mr.T)
+        d = 1.0 / np.sqrt(np.diag(Mr))
+        Kr, Mr = d[:, None] * Kr * d[None, :], d[:, None] * Mr * d[None, :]
+        try:
+            theta, y = sla.eigh(Kr, Mr)
+        except np.linalg.LinAlgError:
+            return np.zeros(0), np.zeros((n, 0)), iterations, ops
+        q = d[:, None] * y
+        newly = 0
+        for i in range(min(w, nev - c)):
+            lam = theta[i] + sigma
+            rel = abs(lam - prev[c + i]) / max(abs(lam), abs(sigma))
+            prev[c + i] = lam
+            if newly == i and rel < tol:
+                newly += 1
+        if newly:
+            XL[:, c:c + newly] = Xbar @ q[:, :newly]
+            MXL[:, c:c + newly] = MXbar @ q[:, :newly]
+            theta_locked[c:c + newly] = theta[:newly]
+            c += newly
+        iterations = it + 1
+        if c >= nev:
+            return prev.copy(), XL, iterations, ops
+        MX = MXbar @ q[:, newly:]
+    return np.zeros(0), np.zeros((n, 0)), iterations, ops
+
+
 def postprocess_modes(eigenvalues, shapes, shape_scale, material, config, positions):
     """modal::PostprocessModes (mesh2modes.cpp:515-588). shapes: [point][eigenpair][3] float32."""
     f32 = np.float32
@@ -379,8 +439,9 @@ def sample_excitations(points, excite_positions, baked_scale=(1.0, 1.0, 1.0)):
     return np.asarray(pts, np.uint32), np.asarray(local, np.float32).reshape(-1, 3), remap
 
 
-def mesh2modes(points, tets, material, excite_positions, baked_scale=(1.0, 1.0, 1.0), config=None, order=2, tol=1e-12):
-    """modal::mesh2modes (mesh2modes.cpp:605-658), cold path. Returns a dict mirroring ModalResult."""
+def mesh2modes(points, tets, material, excite_positions, baked_scale=(1.0, 1.0, 1.0), config=None, order=2, tol=1e-12, seed_basis=None):
+    """modal::mesh2modes (mesh2modes.cpp:605-658): cold path, or the warm path when seed_basis (n x >=nev float32) fits
+    (:459-472). Returns a dict mirroring ModalResult; eigenvalues empty when the warm path fails to converge."""
     config = config or SolverConfig()
     points = np.asarray(points, np.float64)
     tets = filter_degenerate(points, np.asarray(tets, np.uint32))
@@ -388,10 +449,17 @@ def mesh2modes(points, tets, material, excite_positions, baked_scale=(1.0, 1.0, 
     props = mass_properties(points, tets, material.density, baked_scale, length_to_si)
     M, K, nodes, node_count = assemble(points, tets, material, order)
     ex_points, positions, remap = sample_excitations(points, excite_positions, baked_scale)
-    vals, vecs = eigensolve(M, K, config, tol)
+    nev, _, sigma = solver_sizes(config, M.n)
+    iterations = ops = None
+    if seed_basis is not None and seed_basis.shape[0] == M.n and seed_basis.shape[1] >= nev:
+        vals, vecs, iterations, ops = subspace_iterate(M, K, nev, min(nev + 15, M.n), sigma, config.warm_tolerance, config.max_restarts, seed_basis)
+        if len(vals) == 0:
+            return dict(modes=Modes(), eigenvalues=vals, eigenvectors=vecs, iterations=iterations, op_applications=ops)
+    else:
+        vals, vecs = eigensolve(M, K, config, tol)
     shapes = np.stack([vecs[3 * p:3 * p + 3, :].T for p in ex_points.tolist()]).astype(np.float32) if len(ex_points) else np.zeros((0, len(vals), 3), np.float32)
     modes = postprocess_modes(vals, shapes, 1.0, material, config, positions)
-    return dict(modes=modes, mass_props=props, eigenvalues=vals, eigenvectors=vecs, shapes=shapes, sample_point_of_excitation=remap, dofs=3 * node_count, stiffness_nonzeros=len(K.values), M=M, K=K, nodes=nodes)
+    return dict(modes=modes, mass_props=props, eigenvalues=vals, eigenvectors=vecs, shapes=shapes, sample_point_of_excitation=remap, dofs=3 * node_count, stiffness_nonzeros=len(K.values), M=M, K=K, nodes=nodes, iterations=iterations, op_applications=ops)
 
 
 # ------------------------------------------------------------------------------------------------ synthetic meshes

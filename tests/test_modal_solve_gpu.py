@@ -91,3 +91,74 @@ def test_excitations_sharing_a_point_merge():
     np.testing.assert_array_equal(r.sample_point_of_excitation, ref_map)
     np.testing.assert_array_equal(r.positions, ref_pos)
     assert r.shapes.shape[0] == len(ref_pts) == 2
+
+
+def _nu_edit(mat):
+    """The reference's Poisson-ratio edit (tests/ModalSolverBench.cpp:388-389)."""
+    return om.Material(mat.density, mat.young, min(mat.poisson + 0.02, 0.49), mat.alpha, mat.beta)
+
+
+@pytest.mark.parametrize("order,dims,modes", [(2, (8, 3, 2), 20), (1, (14, 9, 7), 40)])
+def test_warm_resolve_matches_cold_and_oracle(order, dims, modes):
+    """SolveReuse::SeedBasis -> SubspaceIterate (mesh2modes.cpp:339-428, :459-472): the edit loop of
+    tests/ModalSolverBench.cpp:346-411. Solve cold keeping the basis, edit the Poisson ratio, re-solve warm; the bench's
+    acceptance is equal mode counts and |f1 warm - f1 cold| < 0.05 Hz (:384). Beyond that: eigenvalues against the cold
+    FP64 oracle at the warm tolerance (pairs lock when their relative change drops under WarmTolerance = 1e-4, which is
+    the reference's accuracy on this path, not 1e-6), against the oracle's own restatement of the iteration, and
+    M-orthonormal Ritz vectors."""
+    from mesheditor_b200 import mesh2modes, solver_config
+
+    points, tets = om.kuhn_block(*dims, size=(0.4, 0.15, 0.1))
+    mat = om.MATERIALS["Ceramic"]
+    edited = _nu_edit(mat)
+    ex = points[:8].astype(np.float32)
+    cfg = solver_config(num_modes=modes, max_mode_freq=1e9, element_order=order)
+    initial = mesh2modes(points, tets, mat, ex, config=cfg, keep_basis=True)
+    assert initial.status == 0 and initial.basis.shape[1] == modes + 15
+    cold = mesh2modes(points, tets, edited, ex, config=cfg)
+    warm = mesh2modes(points, tets, edited, ex, config=cfg, seed_basis=initial.basis, keep_basis=True)
+    assert warm.status == 0 and cold.status == 0
+    assert len(warm.freqs) == len(cold.freqs) and abs(float(warm.freqs[0]) - float(cold.freqs[0])) < 0.05
+    p = warm.profile
+    assert p["restarts"] >= 2 and p["op_applications"] >= 2 * (modes + 15) - modes - 15  # block iterations x active widths
+    assert p["op_applications"] <= p["restarts"] * (modes + 30)
+    ocfg = om.SolverConfig(num_modes=modes, num_fem_modes=modes + 15, max_mode_freq=1e9)
+    ref = om.mesh2modes(points, tets, edited, ex, config=ocfg, order=order)
+    ref_warm = om.mesh2modes(points, tets, edited, ex, config=ocfg, order=order, seed_basis=initial.basis)
+    ref_lam = ref["eigenvalues"]
+    elastic = ref_lam > 1e-3 * ref_lam[-1]
+    for lam in (warm.eigenvalues, ref_warm["eigenvalues"]):
+        assert len(lam) == modes + 15
+        # the pairs that survive into the model (lowest `modes` elastic ones) sit far inside the locked prefix
+        keep = np.flatnonzero(elastic)[:modes]
+        assert np.abs(lam[keep] / ref_lam[keep] - 1).max() <= 1e-4
+        assert np.abs(lam[elastic] / ref_lam[elastic] - 1).max() <= 1e-3  # the trailing pairs converge slowest
+    assert np.abs(warm.eigenvalues[keep] / ref_warm["eigenvalues"][keep] - 1).max() <= 1e-4  # device vs restated iteration
+    np.testing.assert_allclose(warm.freqs, cold.freqs, rtol=1e-4)
+    # same iteration, same seed: the device run and the oracle's restatement take the same number of block iterations (+-1)
+    assert abs(int(p["restarts"]) - int(ref_warm["iterations"])) <= 2  # (the Gaussian filler columns differ: libstdc++ vs numpy)
+    Mfull = ref["M"].to_scipy_full()
+    basis = warm.basis.astype(np.float64)
+    gram = basis.T @ (Mfull @ basis)
+    assert np.abs(gram - np.eye(gram.shape[0])).max() <= 1e-5
+    n_rigid = int((~elastic).sum())
+    groups = [(0, n_rigid)] + [(n_rigid + lo, n_rigid + hi) for lo, hi in clusters(ref_lam[elastic], rel=1e-5)]
+    for lo, hi in groups:
+        if hi > modes or hi == lo:
+            continue
+        assert subspace_sine(basis[:, lo:hi], ref["eigenvectors"][:, lo:hi]) <= 2e-2  # vectors converge as the sqrt of the values
+
+
+def test_mismatched_seed_falls_back_to_the_cold_path():
+    """A basis solved over a different mesh cannot seed this solve (mesh2modes.cpp:459-464)."""
+    from mesheditor_b200 import mesh2modes, solver_config
+
+    points, tets = om.kuhn_block(5, 3, 2, size=(0.4, 0.3, 0.2))
+    cfg = solver_config(num_modes=10, max_mode_freq=1e9)
+    cold = mesh2modes(points, tets, "Steel", points[:4].astype(np.float32), config=cfg)
+    wrong_rows = np.zeros((cold.profile["dofs"] + 3, 25), np.float32)
+    too_few_cols = np.zeros((cold.profile["dofs"], 24), np.float32)
+    for seed in (wrong_rows, too_few_cols):
+        r = mesh2modes(points, tets, "Steel", points[:4].astype(np.float32), config=cfg, seed_basis=seed)
+        assert r.status == 0 and r.profile["op_applications"] == cold.profile["op_applications"]
+        np.testing.assert_array_equal(r.freqs, cold.freqs)

@@ -49,3 +49,30 @@ def test_bar_closed_forms():
     freqs = r["modes"].freqs.astype(np.float64)
     f_long = np.sqrt(mat.young / mat.density) / (2 * L)  # 50 Hz
     assert np.min(np.abs(freqs - f_long)) < 0.01 * f_long
+
+
+def test_oracle_warm_path_reconverges_an_edited_material():
+    """oracle.subspace_iterate (SubspaceIterate, mesh2modes.cpp:339-428) seeded by the basis of a cold solve re-converges
+    a Poisson-ratio edit to the cold answer: the reference's own acceptance is |delta f1| < 0.05 Hz and equal mode
+    counts (tests/ModalSolverBench.cpp:384)."""
+    points, tets = om.kuhn_block(6, 3, 2, size=(0.4, 0.15, 0.1))
+    mat = om.MATERIALS["Ceramic"]
+    edited = om.Material(mat.density, mat.young, mat.poisson + 0.02, mat.alpha, mat.beta)
+    cfg = om.SolverConfig(num_modes=12, num_fem_modes=27, max_mode_freq=1e9)
+    ex = points[:4].astype(np.float32)
+    initial = om.mesh2modes(points, tets, mat, ex, config=cfg)
+    cold = om.mesh2modes(points, tets, edited, ex, config=cfg)
+    warm = om.mesh2modes(points, tets, edited, ex, config=cfg, seed_basis=initial["eigenvectors"].astype(np.float32))
+    assert len(warm["eigenvalues"]) == 27 and 2 <= warm["iterations"] <= 30
+    assert len(warm["modes"].freqs) == len(cold["modes"].freqs)
+    assert abs(float(warm["modes"].freqs[0]) - float(cold["modes"].freqs[0])) < 0.05
+    elastic = cold["eigenvalues"] > 1e-3 * cold["eigenvalues"][-1]
+    keep = np.flatnonzero(elastic)[:12]
+    # pairs lock when their relative change drops under WarmTolerance = 1e-4: that, not 1e-6, is the reference's warm accuracy
+    assert np.abs(warm["eigenvalues"][keep] / cold["eigenvalues"][keep] - 1).max() <= 1e-4
+    V = warm["eigenvectors"]
+    gram = V.T @ (cold["M"].to_scipy_full() @ V)
+    assert np.abs(gram - np.eye(27)).max() <= 1e-8
+    # a seed of the wrong height is ignored (cold path)
+    again = om.mesh2modes(points, tets, edited, ex, config=cfg, seed_basis=np.zeros((5, 27), np.float32))
+    assert again["iterations"] is None

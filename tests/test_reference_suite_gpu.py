@@ -1,0 +1,136 @@
+"""The reference's own solver tests (tests/ModalSolverTest.cpp:228-261) run through me_modal_solve: free-free bars whose
+mode families have closed forms, with the reference's shape classifier (Classify, :83-116), tolerances (1 % longitudinal,
+5 % torsional / thin bending, 10 % Euler-Bernoulli bending) and default SolverConfig. Plus size-independent properties at
+BASELINE.json's full analysis size (configs[2], 998,250 tets), where the CPU oracle cannot follow."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import modal as om
+
+pytestmark = pytest.mark.gpu
+
+BENDING_BL = (4.73004074, 7.85320462, 10.9956078)  # ModalSolverTest.cpp:34
+
+
+def classify(modes, mode, length, width, thickness, nx):
+    """Classify (ModalSolverTest.cpp:83-116): kinetic-energy fractions; torsion = energy of the per-slice best-fit rotation."""
+    u = modes.shapes[:, mode, :].astype(np.float64)
+    p = modes.positions.astype(np.float64)
+    ry, rz = p[:, 1] - width / 2, p[:, 2] - thickness / 2
+    axial, lat_y, lat_z = (u[:, 0] ** 2).sum(), (u[:, 1] ** 2).sum(), (u[:, 2] ** 2).sum()
+    total = axial + lat_y + lat_z
+    if total <= 0:
+        return "other"
+    slices = np.rint(p[:, 0] * nx / length).astype(np.int64)
+    rotation = 0.0
+    for s in np.unique(slices):
+        sel = slices == s
+        circulation, r2 = (ry[sel] * u[sel, 2] - rz[sel] * u[sel, 1]).sum(), (ry[sel] ** 2 + rz[sel] ** 2).sum()
+        if r2 > 0:
+            rotation += circulation * circulation / r2
+    if axial / total > 0.85:
+        return "longitudinal"
+    if rotation / total > 0.85:
+        return "torsional"
+    lateral = lat_y + lat_z
+    if lateral / total > 0.6 and rotation / total < 0.5:
+        if lat_y / lateral > 0.8:
+            return "bending_y"
+        if lat_z / lateral > 0.8:
+            return "bending_z"
+        return "bending"
+    return "other"
+
+
+def solve_bar(length, width, thickness, mat, nx, ny, nz):
+    """SolveBar (ModalSolverTest.cpp:119-128): every mesh point is an excitation position, default SolverConfig."""
+    from mesheditor_b200 import mesh2modes
+
+    points, tets = om.kuhn_block(nx, ny, nz, (length, width, thickness))
+    r = mesh2modes(points, tets, mat, points.astype(np.float32))
+    assert r.status == 0 and len(r.freqs) > 0
+    fem = {}
+    for mode in range(len(r.freqs)):
+        fem.setdefault(classify(r, mode, length, width, thickness, nx), []).append(float(r.freqs[mode]))
+    return fem
+
+
+def bending_theory(length, mat, thickness, per_root):
+    base = math.sqrt(mat.young / mat.density) * (thickness / math.sqrt(12.0)) / (2 * math.pi * length * length)
+    return [bl * bl * base for bl in BENDING_BL for _ in range(per_root)]
+
+
+def check_family(fem, theory, tolerance, min_count=2):
+    count = min(len(fem), len(theory))
+    assert count >= min_count
+    for f, t in zip(fem[:count], theory[:count]):
+        assert abs(f / t - 1.0) < tolerance, (f, t)
+
+
+def test_square_bar_modes_match_closed_forms():
+    length, a = 0.3, 0.05
+    mat = om.Material(1000.0, 1e7, 0.0, 0.0, 0.0)
+    speed = math.sqrt(mat.young / mat.density)
+    torsion_f1 = math.sqrt(mat.mu / mat.density * 0.140577 * 6) / (2 * length)
+    fem = solve_bar(length, a, a, mat, 20, 4, 4)
+    bending = sorted(fem.get("bending", []) + fem.get("bending_y", []) + fem.get("bending_z", []))[:2]
+    check_family(fem.get("longitudinal", []), [n * speed / (2 * length) for n in (1, 2, 3)], 0.01)
+    check_family(fem.get("torsional", []), [n * torsion_f1 for n in (1, 2, 3)], 0.05)
+    check_family(bending, bending_theory(length, mat, a, 2), 0.10)
+
+
+def test_thin_bar_bending_matches_closed_forms():
+    length, width, thickness = 0.3, 0.05, 0.01
+    mat = om.Material(1000.0, 1e9, 0.0, 0.0, 0.0)
+    speed = math.sqrt(mat.young / mat.density)
+    fem = solve_bar(length, width, thickness, mat, 30, 5, 1)
+    check_family(fem.get("longitudinal", []), [n * speed / (2 * length) for n in (1, 2, 3)], 0.01)
+    check_family(fem.get("bending_y", []), bending_theory(length, mat, width, 1)[:1], 0.10, 1)
+    check_family(fem.get("bending_z", []), bending_theory(length, mat, thickness, 1), 0.05)
+
+
+def test_full_size_solve_properties():
+    """BASELINE.json configs[2] (55^3-cell block, 998,250 tets, P1, 200 modes) is beyond the CPU oracle; what can be checked
+    at that size without one, through independent device operators (me_fem_spmv, me_factor_solve):
+    (1) the six rigid-body modes are there (|lambda| tiny), the model starts above them, eigenvalues ascend;
+    (2) Rayleigh quotients x^T K x / x^T M x of the returned (float32) basis reproduce the eigenvalues;
+    (3) shift-invert residual ||A^-1 (K - lambda M) x||_2 / ||x||_2 with A = K - sigma M: the quantity the iteration
+        converges, and one that float32 rounding of the basis does not amplify (a plain ||K x - lambda M x|| would be
+        dominated by lambda_max times the rounding noise);
+    (4) the basis is M-orthonormal;
+    (5) a warm re-solve seeded by that basis reproduces the eigenvalues to the warm tolerance in a few block iterations."""
+    from mesheditor_b200 import Factor, FemSystem, mesh2modes, solver_config
+    from mesheditor_b200 import workloads as wl
+
+    points, tets = wl.kuhn_block(55, 55, 55, (0.3, 0.3, 0.3))
+    ex = wl.bench_excitations(points)
+    cfg = solver_config(num_modes=200, element_order=1, max_mode_freq=1e9)
+    r = mesh2modes(points, tets, "Steel", ex, config=cfg, keep_basis=True)
+    assert r.status == 0 and len(r.freqs) == 200 and r.profile["dofs"] == 526848
+    lam = r.eigenvalues
+    assert len(lam) == 215 and np.all(np.diff(lam) >= -1e-9 * lam[-1])
+    assert np.abs(lam[:6]).max() < 1e-6 * lam[6] and lam[6] > 0  # rigid-body modes
+    assert abs(float(r.freqs[0]) - math.sqrt(lam[6]) / (2 * math.pi)) < 1e-3 * float(r.freqs[0])  # steel's damping shifts f by ~1e-9
+    fem = FemSystem(points, tets, "Steel", 1)
+    sigma = -((2 * math.pi * 20.0) ** 2)
+    factor = Factor(fem, sigma)
+    cols = [6, 7, 8, 20, 57, 111, 180, 214]
+    Mx = {}
+    for j in cols:
+        x = r.basis[:, j].astype(np.float64)
+        kx, mx = fem.spmv("K", x), fem.spmv("M", x)
+        Mx[j] = mx
+        assert abs(float(x @ kx) / float(x @ mx) / lam[j] - 1) < 1e-5, j
+        z = factor.solve(kx - lam[j] * mx)
+        assert np.linalg.norm(z) / np.linalg.norm(x) < 1e-5, (j, np.linalg.norm(z) / np.linalg.norm(x))
+    for i in cols:
+        for j in cols:
+            assert abs(float(r.basis[:, i].astype(np.float64) @ Mx[j]) - (1.0 if i == j else 0.0)) < 1e-5, (i, j)
+    del factor
+    warm = mesh2modes(points, tets, "Steel", ex, config=cfg, seed_basis=r.basis)
+    assert warm.status == 0 and len(warm.freqs) == 200
+    assert np.abs(warm.eigenvalues[6:206] / lam[6:206] - 1).max() < 1e-4
+    assert abs(float(warm.freqs[0]) - float(r.freqs[0])) < 0.05
+    assert warm.profile["restarts"] <= 5  # an exact seed re-locks in a few block iterations
