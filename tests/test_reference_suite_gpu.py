@@ -97,8 +97,10 @@ def test_full_size_solve_properties():
     (1) the six rigid-body modes are there (|lambda| tiny), the model starts above them, eigenvalues ascend;
     (2) Rayleigh quotients x^T K x / x^T M x of the returned (float32) basis reproduce the eigenvalues;
     (3) shift-invert residual ||A^-1 (K - lambda M) x||_2 / ||x||_2 with A = K - sigma M: the quantity the iteration
-        converges, and one that float32 rounding of the basis does not amplify (a plain ||K x - lambda M x|| would be
-        dominated by lambda_max times the rounding noise);
+        converges (a plain ||K x - lambda M x|| would be dominated by lambda_max times the float32 rounding noise of the
+        returned basis). A^-1 (K - lambda M) still amplifies the part of that noise lying in the six rigid-body modes by
+        (lambda - sigma) / |sigma| ~ 1e6, so x is first M-orthogonalised against the ANALYTIC rigid-body modes
+        (translations, e_a x p) in FP64; what remains is the float32 rounding itself, ~2.5e-8;
     (4) the basis is M-orthonormal;
     (5) a warm re-solve seeded by that basis reproduces the eigenvalues to the warm tolerance in a few block iterations."""
     from mesheditor_b200 import Factor, FemSystem, mesh2modes, solver_config
@@ -117,14 +119,22 @@ def test_full_size_solve_properties():
     sigma = -((2 * math.pi * 20.0) ** 2)
     factor = Factor(fem, sigma)
     cols = [6, 7, 8, 20, 57, 111, 180, 214]
+    rigid = np.zeros((3 * len(points), 6))
+    for a in range(3):
+        rigid[a::3, a] = 1.0
+        rigid[:, 3 + a] = np.cross(np.eye(3)[a], points - points.mean(axis=0)).reshape(-1)
+    m_rigid = np.stack([fem.spmv("M", rigid[:, i]) for i in range(6)], axis=1)
+    gram = rigid.T @ m_rigid
     Mx = {}
     for j in cols:
         x = r.basis[:, j].astype(np.float64)
         kx, mx = fem.spmv("K", x), fem.spmv("M", x)
         Mx[j] = mx
         assert abs(float(x @ kx) / float(x @ mx) / lam[j] - 1) < 1e-5, j
-        z = factor.solve(kx - lam[j] * mx)
-        assert np.linalg.norm(z) / np.linalg.norm(x) < 1e-5, (j, np.linalg.norm(z) / np.linalg.norm(x))
+        xd = x - rigid @ np.linalg.solve(gram, m_rigid.T @ x)
+        assert np.linalg.norm(xd - x) < 1e-9 * np.linalg.norm(x), j  # the elastic modes hold no rigid-body motion
+        z = factor.solve(fem.spmv("K", xd) - lam[j] * fem.spmv("M", xd))
+        assert np.linalg.norm(z) / np.linalg.norm(xd) < 1e-6, (j, np.linalg.norm(z) / np.linalg.norm(xd))
     for i in cols:
         for j in cols:
             assert abs(float(r.basis[:, i].astype(np.float64) @ Mx[j]) - (1.0 if i == j else 0.0)) < 1e-5, (i, j)
