@@ -290,6 +290,14 @@ MeStatus me_measure_fp64_rate(int device, int mode, int iters, double *flops_per
  * (instructions), probing whether both FMA pipes run concurrently; 4 scalar FADD. */
 MeStatus me_measure_fp32_fma_rate(int device, int packed, int iters, double *fma_per_second);
 
+/* Unit-test entry of the tensor-core mix (tensor_mix.cuh): out[group][frame] = sum over the group's 4096 reduction
+ * elements of power * state, operands given as host images of the stage layout documented in tensor_mix.cuh
+ * (powers: groups*128 stages of 2*128*32 floats; states: tiles*groups*128 stages of 2*blocks_per_tile*32 floats).
+ * blocks_per_tile is 128 or 256; frames <= tiles*blocks_per_tile*128. `milliseconds` (may be NULL) receives the
+ * kernel time of the last of `repeats` launches. */
+MeStatus me_debug_tensor_mix(int device, const float *powers, const float *states, uint32_t groups, uint32_t tiles, uint32_t blocks_per_tile, uint32_t frames, uint32_t repeats,
+                             float *out, float *milliseconds);
+
 #ifdef __cplusplus
 }
 #endif

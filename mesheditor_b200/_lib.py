@@ -118,6 +118,7 @@ def lib():
         "me_bank_last_render_stats": [vp, C.POINTER(MeRenderStats)],
         "me_measure_fp32_fma_rate": [i32, i32, i32, C.POINTER(C.c_double)],
         "me_measure_fp64_rate": [i32, i32, i32, C.POINTER(C.c_double)],
+        "me_debug_tensor_mix": [i32, vp, vp, u32, u32, u32, u32, u32, vp, C.POINTER(f32)],
         "me_modal_solve": [vp, u32, vp, u32, C.POINTER(MeMaterial), vp, u32, vp, C.POINTER(MeSolverConfig), vp, u32, u32, i32, C.POINTER(MeJobMonitor), C.POINTER(vp)],
         "me_modal_result_mass_properties": [vp, C.POINTER(MeMassProperties)],
         "me_modal_result_profile": [vp, C.POINTER(MeSolveProfile)],

@@ -1,5 +1,6 @@
 // The C ABI (include/me_modal.h): thin extern "C" shims over me::Bank (and, later, the solver).
 #include "bank.h"
+#include "tensor_mix.cuh"
 #include "common.h"
 
 #include <mutex>
@@ -172,6 +173,34 @@ MeStatus me_measure_fp32_fma_rate(int device, int packed, int iters, double *fma
         if (!fma_per_second || iters <= 0) Fail(ME_BAD_ARG, "bad arguments");
         ME_CUDA(cudaSetDevice(device));
         *fma_per_second = me::MeasureFmaRate(packed, iters);
+    });
+}
+
+MeStatus me_debug_tensor_mix(int device, const float *powers, const float *states, uint32_t groups, uint32_t tiles, uint32_t blocks_per_tile, uint32_t frames, uint32_t repeats,
+                             float *out, float *milliseconds) {
+    return Guard([&] {
+        if (!powers || !states || !out || groups == 0 || tiles == 0 || repeats == 0) Fail(ME_BAD_ARG, "bad arguments");
+        if (frames > uint64_t(tiles) * blocks_per_tile * me::kTmBlock) Fail(ME_BAD_ARG, "frames exceed the tiles");
+        ME_CUDA(cudaSetDevice(device));
+        const size_t np = size_t(groups) * me::kTmStagesPerGroup * me::TmPowerStageFloats();
+        const size_t ns = size_t(tiles) * groups * me::kTmStagesPerGroup * me::TmStateStageFloats(blocks_per_tile);
+        me::DeviceBuffer<float> dp, ds, dout;
+        dp.Upload(powers, np, nullptr), ds.Upload(states, ns, nullptr), dout.Reserve(size_t(groups) * frames);
+        const me::TensorMixPlan plan{.Groups = groups, .Tiles = tiles, .BlocksPerTile = blocks_per_tile, .Frames = frames, .Powers = dp.Ptr, .States = ds.Ptr, .Partial = dout.Ptr};
+        cudaEvent_t a, b;
+        ME_CUDA(cudaEventCreate(&a));
+        ME_CUDA(cudaEventCreate(&b));
+        for (uint32_t r = 0; r < repeats; ++r) {
+            if (r + 1 == repeats) ME_CUDA(cudaEventRecord(a, nullptr));
+            me::LaunchTensorMixKernel(plan, nullptr);
+        }
+        ME_CUDA(cudaEventRecord(b, nullptr));
+        ME_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        ME_CUDA(cudaEventElapsedTime(&ms, a, b));
+        cudaEventDestroy(a), cudaEventDestroy(b);
+        if (milliseconds) *milliseconds = ms;
+        ME_CUDA(cudaMemcpy(out, dout.Ptr, size_t(groups) * frames * sizeof(float), cudaMemcpyDeviceToHost));
     });
 }
 

@@ -1,0 +1,214 @@
+// sm_100a tcgen05 kernel of the resonator bank's tensor-core form; see tensor_mix.cuh for the algebra.
+//
+// One CTA renders one time tile (BlocksPerTile x 128 frames) of one chunk group: a 128 x N accumulator in tensor
+// memory, fed stage by stage (32 reduction elements = 16 modes) through a ring of shared-memory buffers.
+//   warp 0 (one lane): producer. Per stage two bulk copies HBM -> shared memory (power stage, state stage), completion
+//                      counted on the stage's "full" mbarrier.
+//   warp 1 (one lane): issues tcgen05.mma kind::tf32, three per 8-wide reduction step (head*head, head*tail,
+//                      tail*head), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
+//   warps 2-5:         epilogue. tcgen05.ld of the accumulator (lane = frame inside the block, column = block) and
+//                      coalesced stores of the group's partial mix row.
+// Operand images in HBM are already in the canonical K-major no-swizzle UMMA layout, so no tensor map is needed.
+#include "tensor_mix.cuh"
+
+#include "common.h"
+
+namespace me {
+namespace {
+
+constexpr uint32_t kThreads = 192;
+constexpr uint32_t kPowerHalfBytes = kTmBlock * kTmKChunk * 4; // 16 KB
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void BarrierInit(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void BarrierExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void BarrierWait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = SmemAddr(bar);
+    for (uint32_t spin = 0;; ++spin) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spin > kSpinLimit) __trap(); // a lost arrival must surface as an error, never as a hung device
+    }
+}
+__device__ __forceinline__ void BulkCopy(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(SmemAddr(dst)), "l"(src), "r"(bytes), "r"(SmemAddr(bar))
+                 : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): 8-row core matrices of 128
+// contiguous bytes; `lbo` = byte step between the two 16-byte K halves of one MMA, `sbo` = byte step between 8-row groups.
+__device__ __forceinline__ uint64_t MatrixDescriptor(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (uint64_t(1) << 46);
+}
+// Instruction descriptor of kind::tf32 (cute::UMMA::InstrDescriptor): FP32 accumulate, TF32 A and B, both K-major.
+__host__ __device__ constexpr uint32_t InstructionDescriptor(uint32_t m, uint32_t n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24); }
+
+__device__ __forceinline__ void MmaTf32(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void MmaCommit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
+        "%28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+          "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]),
+          "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Tensor-core accumulation rounds toward zero: n MMAs chained on one accumulator lose up to n * 2^-24 of its
+// magnitude, always in the same direction (measured: 1e-4 after the 1536 MMAs of a group). So a chain is cut after
+// kFoldStages stages (24 MMAs, <= 1.5e-6) and folded into FP32 registers by the epilogue warps with round-to-nearest
+// adds; two accumulators alternate so the fold of one overlaps the MMAs into the other.
+constexpr uint32_t kFoldStages = 2;
+constexpr uint32_t kFolds = kTmStagesPerGroup / kFoldStages;
+
+template<uint32_t N, uint32_t Stages>
+__global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPlan plan) {
+    static_assert(N == 128, "the epilogue keeps one accumulator row of N columns in registers");
+    constexpr uint32_t kStateHalfBytes = N * kTmKChunk * 4;
+    constexpr uint32_t kPowerBytes = 2 * kPowerHalfBytes, kStateBytes = 2 * kStateHalfBytes;
+    constexpr uint32_t kStageBytes = kPowerBytes + kStateBytes;
+    constexpr uint32_t kSteps = kTmKChunk / 8; // MMAs of K = 8 per stage and operand pair
+    extern __shared__ __align__(1024) uint8_t stage_storage[];
+    __shared__ __align__(8) uint64_t full_bar[Stages], empty_bar[Stages], accum_full[2], accum_empty[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // Tiles of one group are adjacent in launch order, so the CTAs streaming the same power stages run together and
+    // share them through L2.
+    const uint32_t tile = blockIdx.x % plan.Tiles, group = blockIdx.x / plan.Tiles;
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < Stages; ++s) BarrierInit(&full_bar[s], 1), BarrierInit(&empty_bar[s], 1);
+        for (uint32_t b = 0; b < 2; ++b) BarrierInit(&accum_full[b], 1), BarrierInit(&accum_empty[b], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(&tmem_base_slot)), "r"(2 * N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint8_t *powers = reinterpret_cast<const uint8_t *>(plan.Powers) + size_t(group) * kTmStagesPerGroup * kPowerBytes;
+            const uint8_t *states = reinterpret_cast<const uint8_t *>(plan.States) + (size_t(tile) * plan.Groups + group) * kTmStagesPerGroup * kStateBytes;
+            for (uint32_t k = 0; k < kTmStagesPerGroup; ++k) {
+                const uint32_t s = k % Stages, round = k / Stages;
+                if (round) BarrierWait(&empty_bar[s], (round - 1) & 1);
+                uint8_t *stage = stage_storage + size_t(s) * kStageBytes;
+                BarrierExpectTx(&full_bar[s], kStageBytes);
+                BulkCopy(stage, powers + size_t(k) * kPowerBytes, kPowerBytes, &full_bar[s]);
+                BulkCopy(stage + kPowerBytes, states + size_t(k) * kStateBytes, kStateBytes, &full_bar[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = InstructionDescriptor(kTmBlock, N);
+            // Inside a half the 16-byte K pieces are (rows*16) bytes apart and the 8-row groups 128 bytes.
+            constexpr uint32_t lbo_p = kTmBlock * 16, lbo_w = N * 16, sbo = 128;
+            for (uint32_t k = 0; k < kTmStagesPerGroup; ++k) {
+                const uint32_t s = k % Stages, round = k / Stages;
+                const uint32_t fold = k / kFoldStages, buffer = fold & 1;
+                const bool opens = k % kFoldStages == 0;
+                if (opens && fold >= 2) {
+                    BarrierWait(&accum_empty[buffer], ((fold >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                BarrierWait(&full_bar[s], round & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t stage = SmemAddr(stage_storage + size_t(s) * kStageBytes);
+                const uint32_t tmem_d = tmem_base + buffer * N;
+#pragma unroll
+                for (uint32_t kk = 0; kk < kSteps; ++kk) {
+                    const uint64_t p_head = MatrixDescriptor(stage + kk * 2 * lbo_p, lbo_p, sbo);
+                    const uint64_t p_tail = MatrixDescriptor(stage + kPowerHalfBytes + kk * 2 * lbo_p, lbo_p, sbo);
+                    const uint64_t w_head = MatrixDescriptor(stage + kPowerBytes + kk * 2 * lbo_w, lbo_w, sbo);
+                    const uint64_t w_tail = MatrixDescriptor(stage + kPowerBytes + kStateHalfBytes + kk * 2 * lbo_w, lbo_w, sbo);
+                    MmaTf32(tmem_d, p_tail, w_head, idesc, !(opens && kk == 0));
+                    MmaTf32(tmem_d, p_head, w_tail, idesc, 1);
+                    MmaTf32(tmem_d, p_head, w_head, idesc, 1);
+                }
+                MmaCommit(&empty_bar[s]); // arrives when the MMAs above have read the stage
+                if (k % kFoldStages == kFoldStages - 1) MmaCommit(&accum_full[buffer]);
+            }
+        }
+    } else {
+        // TMEM lanes are reachable from the warp whose index mod 4 matches the lane quarter.
+        const uint32_t quarter = warp & 3;
+        const uint32_t row = quarter * 32 + lane; // frame inside the time block
+        float acc[N];
+#pragma unroll
+        for (uint32_t c = 0; c < N; ++c) acc[c] = 0.f;
+#pragma unroll 1
+        for (uint32_t fold = 0; fold < kFolds; ++fold) {
+            const uint32_t buffer = fold & 1;
+            BarrierWait(&accum_full[buffer], (fold >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (uint32_t c0 = 0; c0 < N; c0 += 32) {
+                uint32_t v[32];
+                TmemLoad32(tmem_base + ((quarter * 32) << 16) + buffer * N + c0, v);
+#pragma unroll
+                for (uint32_t c = 0; c < 32; ++c) acc[c0 + c] += __uint_as_float(v[c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(&accum_empty[buffer])) : "memory");
+        }
+        float *out = plan.Partial + size_t(group) * plan.Frames;
+        const uint32_t tile_frame = tile * N * kTmBlock;
+#pragma unroll
+        for (uint32_t c = 0; c < N; ++c) {
+            const uint32_t frame = tile_frame + c * kTmBlock + row;
+            if (frame < plan.Frames) out[frame] = acc[c];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N) : "memory");
+}
+
+template<uint32_t N, uint32_t Stages>
+void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
+    constexpr uint32_t bytes = Stages * (2 * kPowerHalfBytes + 2 * N * kTmKChunk * 4);
+    ME_CUDA(cudaFuncSetAttribute(TensorMixKernel<N, Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); // per device, cheap
+    TensorMixKernel<N, Stages><<<plan.Groups * plan.Tiles, kThreads, bytes, stream>>>(plan);
+    ME_CUDA(cudaGetLastError());
+}
+
+} // namespace
+
+void LaunchTensorMixKernel(const TensorMixPlan &plan, cudaStream_t stream) {
+    if (plan.Groups == 0 || plan.Tiles == 0) return;
+    if (plan.BlocksPerTile == 128) Launch<128, 3>(plan, stream);
+    else Fail(ME_BAD_ARG, "tensor mix: blocks per tile must be 128");
+}
+
+} // namespace me

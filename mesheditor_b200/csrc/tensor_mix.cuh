@@ -1,0 +1,44 @@
+// Tensor-core form of the free-running resonator bank (tensor_mix.cu).
+//
+// Between excitations every mode is z[n] = c z[n-1], so the samples of one 128-frame time block are a linear map of the
+// state at the block's start:  y[b*128 + j] = sum_modes Im(c^(j+1) w_b) = sum_modes Re(c^(j+1)) Im w_b + Im(c^(j+1)) Re w_b.
+// Over many blocks that is a GEMM  Y[128 x blocks] = P[128 x 2*modes] * W[2*modes x blocks]  whose reduction runs over
+// the modes of every object in a chunk group: the mode sum AND the object mix of RenderModal (ModalAudio.cpp:125-128,
+// 553-555) happen in the tensor-core accumulator. P (powers of the coefficients) is fixed by the tuning; W (block-start
+// states) costs 4 FMAs per mode per 128 samples.  FP32 accuracy comes from the 3xTF32 split: both operands are stored
+// as a TF32 head and an FP32 tail, and head*head + head*tail + tail*head accumulate in FP32 (the dropped tail*tail
+// term is 2^-22 relative).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace me {
+
+constexpr uint32_t kTmBlock = 128;     // frames per time block: the M extent of one tcgen05.mma
+constexpr uint32_t kTmKChunk = 32;     // reduction elements per pipeline stage = 16 modes = two 8-mode chunks
+constexpr uint32_t kTmGroupChunks = 256; // chunk slots per reduction group (== kBlockThreads: one resonator CTA)
+constexpr uint32_t kTmStagesPerGroup = kTmGroupChunks * 8 * 2 / kTmKChunk; // 128
+
+// Operand images in HBM are exactly what a pipeline stage holds in shared memory (the canonical K-major, no-swizzle
+// UMMA layout), so a stage is filled by two plain bulk copies:
+//   element (row r, reduction index k) of a [rows x 32] half lives at byte (k/4)*rows*16 + (r/8)*128 + (r%8)*16 + (k%4)*4
+// and a stage is [head half][tail half]. Reduction index 2*m holds Re(c^(j+1)) in P and Im w in W; 2*m+1 holds
+// Im(c^(j+1)) and Re w, m = mode inside the stage (0..15).
+inline size_t TmPowerStageFloats() { return size_t(2) * kTmBlock * kTmKChunk; }
+inline size_t TmStateStageFloats(uint32_t blocks_per_tile) { return size_t(2) * blocks_per_tile * kTmKChunk; }
+
+struct TensorMixPlan {
+    uint32_t Groups;          // chunk groups (reduction ranges of 256 chunk slots)
+    uint32_t Tiles;           // time tiles in the window
+    uint32_t BlocksPerTile;   // 128 or 256 time blocks (the N extent)
+    uint32_t Frames;          // valid frames of the window (the last tile may be ragged)
+    const float *Powers;      // [Groups][128 stages] power stages
+    const float *States;      // [Tiles][Groups][128 stages] state stages
+    float *Partial;           // [Groups][Frames] per-group mixes
+};
+
+void LaunchTensorMixKernel(const TensorMixPlan &, cudaStream_t);
+
+} // namespace me

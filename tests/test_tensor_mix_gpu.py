@@ -1,0 +1,58 @@
+"""The tcgen05 mix kernel (mesheditor_b200/csrc/tensor_mix.cu) against a float64 matrix product.
+
+out[group][tile*N*128 + n*128 + r] = sum_k P_group[r, k] * W_tile,group[n, k] over the group's 4096 reduction elements,
+operands split into a TF32 head and an FP32 tail (3xTF32). Tolerance: 5e-6 of the row scale (measured 2.1e-6, FP32-level; a plain TF32
+product would miss it by 1e-3).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+STAGES = 128  # per group
+KC = 32
+
+
+def split_tf32(x):
+    bits = x.astype(np.float32).view(np.uint32)
+    head = ((bits + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+    return head, (x.astype(np.float32) - head).astype(np.float32)
+
+
+def pack(mat):
+    """[rows, 4096] -> [128 stages][2 halves][rows*32] in the stage layout of tensor_mix.cuh."""
+    rows = mat.shape[0]
+    head, tail = split_tf32(mat)
+    out = np.empty((STAGES, 2, rows * KC), np.float32)
+    r = np.arange(rows)[:, None]
+    k = np.arange(KC)[None, :]
+    idx = (k // 4) * rows * 4 + (r // 8) * 32 + (r % 8) * 4 + (k % 4)
+    for s in range(STAGES):
+        out[s, 0, idx] = head[:, s * KC:(s + 1) * KC]
+        out[s, 1, idx] = tail[:, s * KC:(s + 1) * KC]
+    return out
+
+
+@pytest.mark.parametrize("n_blocks,groups,tiles,ragged", [(128, 2, 2, 0), (128, 1, 2, 777), (128, 3, 1, 5000)])
+def test_tensor_mix_matches_float64_product(n_blocks, groups, tiles, ragged):
+    from mesheditor_b200 import lib
+    from mesheditor_b200._lib import check
+
+    rng = np.random.default_rng(7)
+    K = STAGES * KC
+    P = rng.standard_normal((groups, 128, K)).astype(np.float32) * np.exp(rng.uniform(-6, 0, (groups, 1, K))).astype(np.float32)
+    W = rng.standard_normal((tiles, groups, n_blocks, K)).astype(np.float32)
+    powers = np.stack([pack(P[g]) for g in range(groups)])
+    states = np.stack([np.stack([pack(W[t, g]) for g in range(groups)]) for t in range(tiles)])
+    frames = tiles * n_blocks * 128 - ragged
+    out = np.full((groups, frames), np.nan, np.float32)
+    ms = C.c_float(0)
+    check(lib().me_debug_tensor_mix(0, powers.ctypes.data, states.ctypes.data, groups, tiles, n_blocks, frames, 1, out.ctypes.data, C.byref(ms)))
+    for g in range(groups):
+        want = np.concatenate([(W[t, g].astype(np.float64) @ P[g].astype(np.float64).T).reshape(-1) for t in range(tiles)])[:frames]
+        scale = np.sqrt((P[g].astype(np.float64) ** 2).sum(axis=1).max())
+        err = np.abs(out[g] - want).max()
+        assert np.isfinite(out[g]).all()
+        assert err <= 5e-6 * scale, f"group {g}: max error {err:.3e} vs scale {scale:.3e}"
