@@ -33,6 +33,7 @@ class MeRenderStats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint32), ("resonator_kernel_ms", C.c_float), ("total_device_ms", C.c_float),
         ("mode_samples", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("time_segments", C.c_uint32), ("scan_fallbacks", C.c_uint32),
+        ("tensor_windows", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -107,6 +108,7 @@ def lib():
         "me_bank_set_click_gain": [vp, f32],
         "me_bank_set_max_impacts": [vp, u32],
         "me_bank_set_time_segments": [vp, u32],
+        "me_bank_set_render_path": [vp, u32],
         "me_bank_install": [vp],
         "me_bank_enqueue": [vp, C.POINTER(MeModalEvent)],
         "me_bank_render": [vp, vp, u32],
@@ -118,7 +120,7 @@ def lib():
         "me_bank_last_render_stats": [vp, C.POINTER(MeRenderStats)],
         "me_measure_fp32_fma_rate": [i32, i32, i32, C.POINTER(C.c_double)],
         "me_measure_fp64_rate": [i32, i32, i32, C.POINTER(C.c_double)],
-        "me_debug_tensor_mix": [i32, vp, vp, u32, u32, u32, u32, u32, vp, C.POINTER(f32)],
+        "me_debug_tensor_mix": [i32, vp, vp, u32, u32, u32, u32, u32, u32, vp, C.POINTER(f32)],
         "me_modal_solve": [vp, u32, vp, u32, C.POINTER(MeMaterial), vp, u32, vp, C.POINTER(MeSolverConfig), vp, u32, u32, i32, C.POINTER(MeJobMonitor), C.POINTER(vp)],
         "me_modal_result_mass_properties": [vp, C.POINTER(MeMassProperties)],
         "me_modal_result_profile": [vp, C.POINTER(MeSolveProfile)],

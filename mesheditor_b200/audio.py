@@ -79,6 +79,10 @@ class ModalBank:
     def set_time_segments(self, n):
         check(lib().me_bank_set_time_segments(self._h, n))
 
+    def set_render_path(self, path):
+        """0 automatic, 1 FP32 sample loop, 2 tensor-core form wherever the span allows it."""
+        check(lib().me_bank_set_render_path(self._h, path))
+
     def install(self, discard_frames=512):
         """InstallModalBank, then the one discard block ModalScene renders (tests/ModalBench.h:64-69)."""
         check(lib().me_bank_install(self._h))

@@ -16,6 +16,10 @@ constexpr float Ln1000 = 3 * std::numbers::ln10_v<float>;
 constexpr float Pi = std::numbers::pi_v<float>;
 
 constexpr size_t PartialBudgetBytes = size_t(8) << 30; // per-warp partial mixes kept in HBM per launch window (of 180 GB)
+// Tensor-core form: a tile is 128 time blocks of 128 frames; the state stages of a launch window stay under this budget.
+constexpr uint32_t TensorBlocksPerTile = 128;
+constexpr uint32_t TensorTileFrames = TensorBlocksPerTile * kTmBlock;
+constexpr size_t TensorStateBudgetBytes = size_t(40) << 30; // 10 s of 1024 x 500 modes is 31.5 GB: one window (of 180 GB)
 
 uint32_t PaddedModes(uint32_t count) { return (count + kLanes - 1) / kLanes * kLanes; }
 
@@ -84,6 +88,7 @@ uint32_t Bank::AddObject(uint32_t count, uint32_t n_points, const float *shapes,
         if (indices[t] >= n_points) Fail(ME_BAD_ARG, "triangle index %u out of range (%u points)", indices[t], n_points);
     const auto slot = ObjectCount();
     const size_t k0 = CoeffRe.size();
+    ++TuningVersion;
     ModeOffset.push_back(uint32_t(k0));
     ModeCount.push_back(count);
     TunedModeCount.push_back(count);
@@ -128,6 +133,7 @@ uint32_t Bank::AddObject(uint32_t count, uint32_t n_points, const float *shapes,
 void Bank::TuneObject(uint32_t object, const float *freqs, const float *t60s, uint32_t n, float radius_scale) {
     CheckSlot(object);
     if (n && (!freqs || !t60s)) Fail(ME_BAD_ARG, "null frequency/T60 array");
+    ++TuningVersion;
     const auto k0 = ModeOffset[object];
     const auto count = std::min(ModeCount[object], n);
     const float sr = SampleRate;
@@ -413,6 +419,12 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     CallImpacts.resize(n);
     CallTails.resize(n);
     CallPulseWarps.clear();
+    // The tensor-core form needs RenderModal blocks made of whole 128-frame time blocks and tiles made of whole
+    // RenderModal blocks, and pays off once (chunk groups x tiles) fills the SMs.
+    const uint32_t groups = NChunks / kTmGroupChunks;
+    const bool tensor_possible = groups > 0 && block_frames % kTmBlock == 0 && TensorTileFrames % block_frames == 0 && !SpeculationFailed;
+    const uint64_t tensor_units = uint64_t(groups) * ((frames + TensorTileFrames - 1) / TensorTileFrames);
+    const bool tensor_span = tensor_possible && (RenderPath == 2 || (RenderPath == 0 && tensor_units >= 128 && frames >= 2 * TensorTileFrames));
     uint64_t force_total = 0, delta_total = 0, row_total = 0;
     uint32_t max_len = 0;
     bool any_click = false;
@@ -420,18 +432,22 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         const auto &s = scheduled[order[i]];
         const auto &im = s.AtStart;
         const uint32_t len = uint32_t(std::min<uint64_t>(im.SamplesLeft, frames - s.Start));
+        // In a tensor span the pulse kernel keeps rendering the pulse's free ringing up to the next time-block boundary,
+        // where its state increment joins the bank (increments must land on block-start states).
+        uint32_t render_len = len;
+        if (tensor_span && len) render_len = uint32_t(std::min<uint64_t>((uint64_t(s.Start) + len + kTmBlock - 1) / kTmBlock * kTmBlock, frames)) - s.Start;
         const uint32_t chunks = ObjStride[im.Object] / kLanes;
         const uint32_t warps = len ? (chunks + 31) / 32 : 0;
-        if (force_total + len >= (uint64_t(1) << 32) || delta_total + ObjStride[im.Object] >= (uint64_t(1) << 32) || row_total + uint64_t(warps) * len >= (uint64_t(1) << 32))
+        if (force_total + len >= (uint64_t(1) << 32) || delta_total + ObjStride[im.Object] >= (uint64_t(1) << 32) || row_total + uint64_t(warps) * render_len >= (uint64_t(1) << 32))
             Fail(ME_BAD_ARG, "impact buffers exceed 2^32 entries in one span");
-        CallImpacts[i] = {.Start = s.Start, .Len = len, .ForceOff = uint32_t(force_total), .ExPos = im.ExPos, .Jx = im.Jx, .Jy = im.Jy, .Jz = im.Jz, .Object = im.Object, .PhaseRe = im.PhaseRe, .PhaseIm = im.PhaseIm, .RotRe = im.RotRe, .RotIm = im.RotIm, .End = s.End, .DeltaOff = uint32_t(delta_total), .HasClick = HasClick(im) ? 1u : 0u, .Pad = 0};
+        CallImpacts[i] = {.Start = s.Start, .Len = len, .ForceOff = uint32_t(force_total), .ExPos = im.ExPos, .Jx = im.Jx, .Jy = im.Jy, .Jz = im.Jz, .Object = im.Object, .PhaseRe = im.PhaseRe, .PhaseIm = im.PhaseIm, .RotRe = im.RotRe, .RotIm = im.RotIm, .End = s.End, .DeltaOff = uint32_t(delta_total), .HasClick = HasClick(im) ? 1u : 0u, .RenderLen = render_len};
         CallTails[i] = {.Gamma = im.Gamma, .AccelAmp = im.AccelAmp, .ClickB0 = im.ClickB0, .ClickA1 = im.ClickA1, .ClickA2 = im.ClickA2, .ClickZ1 = im.ClickZ1, .ClickZ2 = im.ClickZ2, .ClickGain = ClickGain * ListenerGain[im.Object]};
         for (uint32_t w = 0; w < warps; ++w) {
             CallPulseWarps.push_back({.Impact = i, .Chunk0 = w * 32, .RowOff = uint32_t(row_total), .Pad = 0});
-            row_total += len;
+            row_total += render_len;
         }
         any_click |= HasClick(im);
-        max_len = std::max(max_len, len);
+        max_len = std::max(max_len, render_len);
         force_total += len;
         if (len) delta_total += ObjStride[im.Object];
     }
@@ -440,7 +456,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     std::vector<std::vector<std::pair<uint32_t, uint32_t>>> inject(n_obj), excite(n_obj);
     for (uint32_t i = 0; i < n; ++i) {
         const auto &im = CallImpacts[i];
-        if (im.Len) inject[im.Object].push_back({im.Start + im.Len, im.DeltaOff});
+        if (im.Len) inject[im.Object].push_back({im.Start + im.RenderLen, im.DeltaOff});
         if (im.End > im.Start) excite[im.Object].push_back({im.Start, im.End});
     }
     CallInjectFrame.clear(), CallInjectDelta.clear(), CallExciteBegin.clear(), CallExciteEnd.clear();
@@ -481,28 +497,43 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     if (rows == 0) {
         ME_CUDA(cudaMemsetAsync(out_dev, 0, size_t(frames) * sizeof(float), stream));
     } else {
-        // Launch windows bound the partial-row buffer; they start on block boundaries.
+        // Launch windows bound the partial-row buffer (or the state stages); they start on block boundaries.
         const uint64_t blocks_in_budget = std::max<uint64_t>(1, PartialBudgetBytes / (uint64_t(rows) * sizeof(float)) / block_frames);
-        const uint32_t window = uint32_t(std::min<uint64_t>(blocks_in_budget * block_frames, frames));
-        DPartial.Reserve(size_t(rows) * window);
+        uint32_t window = uint32_t(std::min<uint64_t>(blocks_in_budget * block_frames, frames));
+        if (tensor_span) {
+            const uint64_t tile_bytes = uint64_t(groups) * TmStateTileFloats(TensorBlocksPerTile) * sizeof(float);
+            size_t free_bytes = 0, total_bytes = 0;
+            ME_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
+            // What the pool already holds for this buffer is reusable; beyond that stay within half of the free memory.
+            const uint64_t budget = std::min<uint64_t>(TensorStateBudgetBytes, std::max<uint64_t>(DWalkStates.Capacity * sizeof(float), free_bytes / 2));
+            const uint64_t tiles_in_budget = std::max<uint64_t>(1, budget / tile_bytes);
+            window = uint32_t(std::min<uint64_t>(tiles_in_budget * TensorTileFrames, (uint64_t(frames) + TensorTileFrames - 1) / TensorTileFrames * TensorTileFrames));
+            if (PowersDirty || PowersVersion != TuningVersion) {
+                DPowers.Reserve(size_t(groups) * kTmStagesPerGroup * TmPowerStageFloats());
+                LaunchPowerTableKernel(view, DPowers.Ptr, stream, Counter);
+                PowersDirty = false;
+                PowersVersion = TuningVersion;
+            }
+        }
+        // Chunk groups reduced in one CTA of the tensor-core kernel (one partial mix row each): as many as keeps the
+        // grid at eight waves or more (a CTA runs for tens of microseconds, so few waves leave a long tail).
+        uint32_t groups_per_row = 1;
+        if (tensor_span) {
+            const uint32_t tiles_in_window = (std::min(window, frames) + TensorTileFrames - 1) / TensorTileFrames;
+            while (groups_per_row < 16 && groups % (groups_per_row * 2) == 0 && uint64_t(groups / (groups_per_row * 2)) * tiles_in_window >= 8 * 148) groups_per_row *= 2;
+        }
+        const uint32_t mix_rows = groups ? groups / groups_per_row : 0;
         const uint32_t ctas = NChunks / kBlockThreads;
         for (uint32_t begin = 0; begin < frames; begin += window) {
             const uint32_t wf = std::min(window, frames - begin);
             const uint32_t blocks = (wf + block_frames - 1) / block_frames;
-            // Segments of the block-parallel scan along time: enough (chunk-CTA x segment) units to even out the
-            // 148 SMs, each a whole number of blocks.
-            uint32_t segments = RequestedSegments;
-            if (segments == 0) segments = SpeculationFailed ? 1 : std::min<uint32_t>(64, (16 * 296 + ctas - 1) / ctas);
-            segments = std::max(1u, std::min(segments, blocks));
-            const uint32_t seg_blocks = (blocks + segments - 1) / segments;
-            segments = (blocks + seg_blocks - 1) / seg_blocks;
             RenderPlan plan{
                 .SpanFrames = frames,
                 .BlockFrames = block_frames,
                 .FrameBegin = begin,
                 .Frames = wf,
-                .NSegments = segments,
-                .SegmentFrames = seg_blocks * block_frames,
+                .NSegments = 1,
+                .SegmentFrames = blocks * block_frames,
                 .ObjInjectPtr = DInjectPtr.Ptr,
                 .InjectFrame = DInjectFrame.Ptr,
                 .InjectDelta = DInjectDelta.Ptr,
@@ -511,40 +542,90 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 .ExciteEnd = DExciteEnd.Ptr,
                 .DeltaRe = DDeltaRe.Ptr,
                 .DeltaIm = DDeltaIm.Ptr,
-                .Partial = DPartial.Ptr,
+                .Partial = nullptr,
                 .SegStateRe = nullptr,
                 .SegStateIm = nullptr,
                 .Speculation = DSpeculation.Ptr,
                 .Debug = std::getenv("ME_RESONATOR_DEBUG") ? 1u : 0u,
+                .WalkStates = nullptr,
+                .WalkBlocksPerTile = TensorBlocksPerTile,
             };
-            cudaEvent_t k0 = NextEvent(), k1 = NextEvent();
-            ME_CUDA(cudaEventRecord(k0, stream));
-            if (segments > 1) {
+            const auto seed_segments = [&](uint32_t segments) {
+                if (segments <= 1) return;
                 const size_t seg_floats = size_t(segments - 1) * NChunks * kLanes;
                 DSegRe.Reserve(seg_floats), DSegIm.Reserve(seg_floats);
                 plan.SegStateRe = DSegRe.Ptr, plan.SegStateIm = DSegIm.Ptr;
-                ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
                 LaunchSegmentScan(view, plan, DSegRe.Ptr, DSegIm.Ptr, stream, Counter);
-                LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+            };
+            const auto speculation_failed = [&]() -> uint32_t {
                 uint32_t failed = 0;
                 ME_CUDA(cudaMemcpyAsync(&failed, DSpeculation.Ptr, sizeof failed, cudaMemcpyDeviceToHost, stream));
                 ME_CUDA(cudaStreamSynchronize(stream));
-                if (failed) {
-                    if (std::getenv("ME_RESONATOR_DEBUG")) fprintf(stderr, "[me] speculation failed: code %u (window %u+%u, %u segments)\n", failed, begin, wf, segments);
-                    // A culling decision inside the window: render it again sequentially in time (still on the GPU).
-                    SpeculationFailed = true;
-                    ++Stats.scan_fallbacks;
-                    plan.NSegments = 1;
-                    plan.SegmentFrames = blocks * block_frames;
-                    LaunchResonatorKernel(view, plan, Steps, stream, Counter);
-                    segments = 1;
+                if (failed && std::getenv("ME_RESONATOR_DEBUG")) fprintf(stderr, "[me] speculation failed: code %u (window %u+%u, %u segments)\n", failed, begin, wf, plan.NSegments);
+                return failed;
+            };
+            // A culling decision inside the window (or an increment off the time-block grid): the window is rendered
+            // again sequentially in time by the sample loop (still on the GPU).
+            const auto render_sequentially = [&] {
+                SpeculationFailed = true;
+                ++Stats.scan_fallbacks;
+                DPartial.Reserve(size_t(rows) * wf);
+                plan.Partial = DPartial.Ptr;
+                plan.NSegments = 1;
+                plan.SegmentFrames = blocks * block_frames;
+                plan.SegStateRe = plan.SegStateIm = nullptr;
+                LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+            };
+            cudaEvent_t k0 = NextEvent(), k1 = NextEvent();
+            ME_CUDA(cudaEventRecord(k0, stream));
+            bool tensor_window = tensor_span && !SpeculationFailed;
+            uint32_t segments = 1;
+            if (tensor_window) {
+                // The walk kernel steps every chunk through the window 128 frames at a time (culling applied exactly as
+                // it goes) and writes the block-start states; the tcgen05 kernel turns them into per-group-set mixes.
+                const uint32_t tiles = (wf + TensorTileFrames - 1) / TensorTileFrames;
+                DWalkStates.Reserve(size_t(tiles) * groups * TmStateTileFloats(TensorBlocksPerTile));
+                DGroupMix.Reserve(size_t(mix_rows) * wf);
+                plan.WalkStates = DWalkStates.Ptr;
+                ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
+                LaunchStateWalkKernel(view, plan, stream, Counter);
+                LaunchTensorMixKernel({.Groups = groups, .GroupsPerRow = groups_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
+                ++Counter.Launches;
+                // Only code 8 (an increment off the time-block grid) can invalidate a sequential walk.
+                if (speculation_failed() & 8u) {
+                    tensor_window = false;
+                    render_sequentially();
+                } else {
+                    ++Stats.tensor_windows;
                 }
             } else {
-                LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+                // Segments of the block-parallel scan along time: enough (chunk-CTA x segment) units to even out the
+                // 148 SMs, each a whole number of blocks.
+                segments = RequestedSegments;
+                if (segments == 0) segments = SpeculationFailed ? 1 : std::min<uint32_t>(64, (16 * 296 + ctas - 1) / ctas);
+                segments = std::max(1u, std::min(segments, blocks));
+                const uint32_t seg_blocks = (blocks + segments - 1) / segments;
+                segments = (blocks + seg_blocks - 1) / seg_blocks;
+                DPartial.Reserve(size_t(rows) * wf);
+                plan.Partial = DPartial.Ptr;
+                plan.NSegments = segments;
+                plan.SegmentFrames = seg_blocks * block_frames;
+                if (segments > 1) {
+                    ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
+                    seed_segments(segments);
+                    LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+                    if (speculation_failed()) {
+                        render_sequentially();
+                        segments = 1;
+                    }
+                } else {
+                    LaunchResonatorKernel(view, plan, Steps, stream, Counter);
+                }
             }
             ME_CUDA(cudaEventRecord(k1, stream));
             Stats.time_segments = std::max(Stats.time_segments, segments);
-            LaunchMixKernel(DPartial.Ptr, rows, plan, pulses, out_dev + begin, stream, Counter);
+            if (tensor_window) LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, pulses, out_dev + begin, stream, Counter);
+            else LaunchMixKernel(DPartial.Ptr, rows, plan, pulses, out_dev + begin, stream, Counter);
             Side ^= 1;
             view = View();
         }

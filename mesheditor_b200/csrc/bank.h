@@ -5,6 +5,7 @@
 
 #include "common.h"
 #include "resonator.cuh"
+#include "tensor_mix.cuh"
 
 #include <array>
 #include <atomic>
@@ -45,6 +46,7 @@ public:
     void SetClickGain(float g) { ClickGain = g; }
     void SetMaxImpacts(uint32_t n) { MaxImpacts = n; }
     void SetTimeSegments(uint32_t n) { RequestedSegments = n; }
+    void SetRenderPath(uint32_t path) { RenderPath = path; }
 
     void Install();
     MeStatus Enqueue(const MeModalEvent &);
@@ -117,6 +119,12 @@ private:
     std::vector<PulseWarp> CallPulseWarps;
     std::vector<uint32_t> CallInjectPtr, CallInjectFrame, CallInjectDelta, CallExcitePtr, CallExciteBegin, CallExciteEnd;
     std::vector<float> MixGain, EnergyScale;
+
+    // Tensor-core form (tensor_mix.cuh): power stages of the installed tuning, state stages and group mixes of a window.
+    DeviceBuffer<float> DPowers, DWalkStates, DGroupMix;
+    bool PowersDirty{true};
+    uint64_t TuningVersion{1}, PowersVersion{0}; // the power stages follow the coefficients, not the install
+    uint32_t RenderPath{0}; // 0 automatic, 1 sample loop (FP32 pipe), 2 tensor-core form wherever the span allows it
 
     uint32_t RequestedSegments{0};
     int Steps{4};

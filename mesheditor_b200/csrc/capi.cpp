@@ -129,6 +129,12 @@ MeStatus me_bank_set_gain(MeBank *b, uint32_t slot, float out_gain, float listen
 MeStatus me_bank_set_click_gain(MeBank *b, float g) { return ME_BANK_CALL(b, b->Impl.SetClickGain(g)); }
 MeStatus me_bank_set_max_impacts(MeBank *b, uint32_t n) { return ME_BANK_CALL(b, b->Impl.SetMaxImpacts(n)); }
 MeStatus me_bank_set_time_segments(MeBank *b, uint32_t n) { return ME_BANK_CALL(b, b->Impl.SetTimeSegments(n)); }
+MeStatus me_bank_set_render_path(MeBank *b, uint32_t path) {
+    return ME_BANK_CALL(b, {
+        if (path > 2) Fail(ME_BAD_ARG, "render path must be 0, 1 or 2");
+        b->Impl.SetRenderPath(path);
+    });
+}
 MeStatus me_bank_install(MeBank *b) { return ME_BANK_CALL(b, b->Impl.Install()); }
 
 MeStatus me_bank_enqueue(MeBank *b, const MeModalEvent *e) {
@@ -176,17 +182,17 @@ MeStatus me_measure_fp32_fma_rate(int device, int packed, int iters, double *fma
     });
 }
 
-MeStatus me_debug_tensor_mix(int device, const float *powers, const float *states, uint32_t groups, uint32_t tiles, uint32_t blocks_per_tile, uint32_t frames, uint32_t repeats,
+MeStatus me_debug_tensor_mix(int device, const float *powers, const float *states, uint32_t groups, uint32_t groups_per_row, uint32_t tiles, uint32_t blocks_per_tile, uint32_t frames, uint32_t repeats,
                              float *out, float *milliseconds) {
     return Guard([&] {
-        if (!powers || !states || !out || groups == 0 || tiles == 0 || repeats == 0) Fail(ME_BAD_ARG, "bad arguments");
+        if (!powers || !states || !out || groups == 0 || tiles == 0 || repeats == 0 || groups_per_row == 0 || groups % groups_per_row) Fail(ME_BAD_ARG, "bad arguments");
         if (frames > uint64_t(tiles) * blocks_per_tile * me::kTmBlock) Fail(ME_BAD_ARG, "frames exceed the tiles");
         ME_CUDA(cudaSetDevice(device));
         const size_t np = size_t(groups) * me::kTmStagesPerGroup * me::TmPowerStageFloats();
-        const size_t ns = size_t(tiles) * groups * me::kTmStagesPerGroup * me::TmStateStageFloats(blocks_per_tile);
+        const size_t ns = size_t(tiles) * groups * me::TmStateTileFloats(blocks_per_tile);
         me::DeviceBuffer<float> dp, ds, dout;
-        dp.Upload(powers, np, nullptr), ds.Upload(states, ns, nullptr), dout.Reserve(size_t(groups) * frames);
-        const me::TensorMixPlan plan{.Groups = groups, .Tiles = tiles, .BlocksPerTile = blocks_per_tile, .Frames = frames, .Powers = dp.Ptr, .States = ds.Ptr, .Partial = dout.Ptr};
+        dp.Upload(powers, np, nullptr), ds.Upload(states, ns, nullptr), dout.Reserve(size_t(groups / groups_per_row) * frames);
+        const me::TensorMixPlan plan{.Groups = groups, .GroupsPerRow = groups_per_row, .Tiles = tiles, .BlocksPerTile = blocks_per_tile, .Frames = frames, .Powers = dp.Ptr, .States = ds.Ptr, .Partial = dout.Ptr};
         cudaEvent_t a, b;
         ME_CUDA(cudaEventCreate(&a));
         ME_CUDA(cudaEventCreate(&b));
@@ -200,7 +206,7 @@ MeStatus me_debug_tensor_mix(int device, const float *powers, const float *state
         ME_CUDA(cudaEventElapsedTime(&ms, a, b));
         cudaEventDestroy(a), cudaEventDestroy(b);
         if (milliseconds) *milliseconds = ms;
-        ME_CUDA(cudaMemcpy(out, dout.Ptr, size_t(groups) * frames * sizeof(float), cudaMemcpyDeviceToHost));
+        ME_CUDA(cudaMemcpy(out, dout.Ptr, size_t(groups / groups_per_row) * frames * sizeof(float), cudaMemcpyDeviceToHost));
     });
 }
 

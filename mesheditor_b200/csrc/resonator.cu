@@ -25,6 +25,7 @@
 //   * The reference's audibility culling (LiveModeCount prefix, SilenceObject, :139-146) is reproduced at the
 //     RenderModal block boundaries with one CTA-wide exchange per block; objects never straddle a CTA.
 #include "resonator.cuh"
+#include "tensor_mix.cuh"
 
 #include "common.h"
 
@@ -151,7 +152,33 @@ __device__ __forceinline__ float SumRow(const float *rows, uint32_t lane) {
     return a + b;
 }
 
-template<int K, int MinBlocks>
+// TF32 head of x (round to nearest) and the FP32 tail x - head: the two pieces of a 3xTF32 operand.
+__device__ __forceinline__ float Tf32Head(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+
+// c^m for the chunk's eight modes from the FP64 polar form.
+__device__ __forceinline__ void PolarPower(const BankView &b, uint32_t mode0, uint32_t m, float2 (&re)[4], float2 (&im)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float r[2], q[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double mag = exp(double(m) * b.LogRho[mode0 + 2 * i + h]); // ln 0 = -inf -> 0
+            double sn, cs;
+            sincos(double(m) * b.Theta[mode0 + 2 * i + h], &sn, &cs);
+            r[h] = float(mag * cs), q[h] = float(mag * sn);
+        }
+        re[i] = {r[0], r[1]}, im[i] = {q[0], q[1]};
+    }
+}
+
+// Walk == false: the sample loop (K samples per step). Walk == true: the producer of the tensor-core form, which
+// advances one 128-frame time block per step and writes the block-start states as state stages (tensor_mix.cuh).
+// Everything around the inner loop (RenderModal blocks, culling, increments, final state) is shared.
+template<int K, int MinBlocks, bool Walk>
 __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(const BankView b, const RenderPlan plan) {
     extern __shared__ __align__(16) float transposed_storage[];
     float (*transposed)[kTile][kRowPad] = reinterpret_cast<float (*)[kTile][kRowPad]>(transposed_storage);
@@ -171,6 +198,9 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
 
     Powers<K> p;
     Chunk w;
+    float2 jump_re[4], jump_im[4]; // Walk: c^128
+#pragma unroll
+    for (int i = 0; i < 4; ++i) jump_re[i] = jump_im[i] = float2{0.f, 0.f};
     float gain = 1.f, out_scale = 0.f, energy_scale = 0.f;
     uint32_t my_chunk = 0, obj_chunks = 0, obj_first_local = 0;
     bool in_tuned = false, cull = false, live = true, ringing = true;
@@ -181,6 +211,19 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         float2 cre[4], cim[4];
         Load8(b.CoeffRe + mode0, cre), Load8(b.CoeffIm + mode0, cim);
         MakePowers<K>(cre, cim, p);
+        if constexpr (Walk) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { // c^128 by seven FP64 squarings of the float coefficient, rounded once
+                double rx = cre[i].x, ix = cim[i].x, ry = cre[i].y, iy = cim[i].y;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    const double nrx = rx * rx - ix * ix, nry = ry * ry - iy * iy;
+                    ix = 2.0 * rx * ix, iy = 2.0 * ry * iy;
+                    rx = nrx, ry = nry;
+                }
+                jump_re[i] = {float(rx), float(ry)}, jump_im[i] = {float(ix), float(iy)};
+            }
+        }
         const uint32_t first = b.ObjFirstChunk[object];
         my_chunk = chunk - first;
         obj_chunks = b.ObjStride[object] / kLanes;
@@ -265,31 +308,92 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         }
         const bool warp_renders = __ballot_sync(0xFFFFFFFFu, rendered) != 0;
 
-        for (uint32_t tile = pos; tile < block_end; tile += kTile) {
-            const uint32_t nv = min(kTile, block_end - tile);
-            if (!warp_renders) {
-                if (lane < nv) partial[tile + lane] = 0.f;
-                continue;
-            }
-            if (rendered) {
-                const uint32_t tile_abs = plan.FrameBegin + tile;
-                uint32_t s = 0;
-                while (true) {
-                    uint32_t lim = nv;
-                    if (inj_frame - tile_abs < nv) lim = inj_frame - tile_abs; // inj_frame >= tile_abs + s
-                    for (; s + K <= lim; s += K) StepK<K>(w, p, column + s * (kRowPad / 2));
-                    for (; s < lim; ++s) Step1<K>(w, p, column + s * (kRowPad / 2));
-                    if (s == nv) break;
-                    while (inj_frame == tile_abs + s) inject();
+        if constexpr (Walk) {
+            // Row-major states (tensor_mix.cuh): this chunk owns 16 consecutive reduction elements of every time-block row,
+            // so the CTA's 256 chunk-threads fill one 16 KB row per step, coalesced.
+            // The walk is sequential in time over the whole window (one segment), so culling needs no speculation.
+            // A warp's 32 chunks own 2 KB of the row; they pass through a swizzled shared-memory transpose so that every
+            // store instruction covers 512 contiguous bytes.
+            const uint32_t nb = plan.WalkBlocksPerTile;
+            float4 *rows = reinterpret_cast<float4 *>(plan.WalkStates + size_t(blockIdx.x) * TmStateTileFloats(nb)) + warp * 128 + lane;
+            const size_t tile_stride = size_t(gridDim.x) * TmStateTileFloats(nb) / 4, half_stride = size_t(nb) * kTmGroupK / 4;
+            float4 *exchange = reinterpret_cast<float4 *>(transposed_storage) + warp * 256;
+            const uint32_t put = lane * 4, put_swizzle = (lane >> 1) & 3;
+            const bool audible = rendered && out_scale != 0.f;
+            for (uint32_t t = pos; t < block_end;) {
+                const uint32_t t_abs = plan.FrameBegin + t;
+                const uint32_t step = min(kTmBlock, block_end - t);
+                if (rendered) {
+                    while (inj_frame == t_abs) inject();
+                    // Increments land on time-block boundaries in a span planned for this form (DevImpact::RenderLen).
+                    if (inj_frame - t_abs < step) atomicOr(plan.Speculation, 8u);
                 }
+                const uint32_t block_index = t / kTmBlock;
+                float4 *at = rows + size_t(block_index / nb) * tile_stride + size_t(block_index % nb) * (kTmGroupK / 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 head = {0.f, 0.f, 0.f, 0.f}, tail = head;
+                    if (audible) {
+                        head = {Tf32Head(w.Im[i].x), Tf32Head(w.Re[i].x), Tf32Head(w.Im[i].y), Tf32Head(w.Re[i].y)};
+                        tail = {w.Im[i].x - head.x, w.Re[i].x - head.y, w.Im[i].y - head.z, w.Re[i].y - head.w};
+                    }
+                    exchange[put + (i ^ put_swizzle)] = head;
+                    exchange[128 + put + (i ^ put_swizzle)] = tail;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t from = 8 * j + (lane >> 2); // the chunk-lane whose piece lands at position 32*j + lane
+                    const uint32_t get = from * 4 + ((lane & 3) ^ ((from >> 1) & 3));
+                    at[32 * j] = exchange[get];
+                    at[half_stride + 32 * j] = exchange[128 + get];
+                }
+                __syncwarp();
+                if (rendered) {
+                    float2 sr[4], si[4];
+                    if (step == kTmBlock) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) sr[i] = jump_re[i], si[i] = jump_im[i];
+                    } else {
+                        PolarPower(b, mode0, step, sr, si); // ragged end of the span
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 re = {fmaf(-w.Im[i].x, si[i].x, w.Re[i].x * sr[i].x), fmaf(-w.Im[i].y, si[i].y, w.Re[i].y * sr[i].y)};
+                        w.Im[i] = {fmaf(w.Re[i].x, si[i].x, w.Im[i].x * sr[i].x), fmaf(w.Re[i].y, si[i].y, w.Im[i].y * sr[i].y)};
+                        w.Re[i] = re;
+                    }
+                }
+                t += step;
             }
-            // A chunk sitting the block out adds nothing; a muted object (mix gain 0) evolves but its samples are discarded.
-            if (!rendered || out_scale == 0.f)
-                for (uint32_t s = 0; s < nv; ++s) column[s * (kRowPad / 2)] = float2{0.f, 0.f};
-            __syncwarp();
-            const float total = lane < nv ? SumRow(rows, lane) : 0.f;
-            if (lane < nv) partial[tile + lane] = total;
-            __syncwarp();
+        } else {
+            for (uint32_t tile = pos; tile < block_end; tile += kTile) {
+                const uint32_t nv = min(kTile, block_end - tile);
+                if (!warp_renders) {
+                    if (lane < nv) partial[tile + lane] = 0.f;
+                    continue;
+                }
+                if (rendered) {
+                    const uint32_t tile_abs = plan.FrameBegin + tile;
+                    uint32_t s = 0;
+                    while (true) {
+                        uint32_t lim = nv;
+                        if (inj_frame - tile_abs < nv) lim = inj_frame - tile_abs; // inj_frame >= tile_abs + s
+                        for (; s + K <= lim; s += K) StepK<K>(w, p, column + s * (kRowPad / 2));
+                        for (; s < lim; ++s) Step1<K>(w, p, column + s * (kRowPad / 2));
+                        if (s == nv) break;
+                        while (inj_frame == tile_abs + s) inject();
+                    }
+                }
+                // A chunk sitting the block out adds nothing; a muted object (mix gain 0) evolves but its samples are discarded.
+                if (!rendered || out_scale == 0.f)
+                    for (uint32_t s = 0; s < nv; ++s) column[s * (kRowPad / 2)] = float2{0.f, 0.f};
+                __syncwarp();
+                const float total = lane < nv ? SumRow(rows, lane) : 0.f;
+                if (lane < nv) partial[tile + lane] = total;
+                __syncwarp();
+            }
+
         }
 
         // End of the block: chunk energies decide the audible prefix, or silence the object (:132-146).
@@ -391,10 +495,10 @@ __global__ void __launch_bounds__(kPulseWarps * 32) PulseKernel(const BankView b
     }
     float *rows = &transposed[warp][0][0];
     const float *force = plan.Force + im.ForceOff;
-    for (uint32_t tile = 0; tile < im.Len; tile += kTile) {
-        const uint32_t nv = min(kTile, im.Len - tile);
+    for (uint32_t tile = 0; tile < im.RenderLen; tile += kTile) {
+        const uint32_t nv = min(kTile, im.RenderLen - tile);
         for (uint32_t s = 0; s < nv; ++s) {
-            const float f = __ldg(force + tile + s);
+            const float f = tile + s < im.Len ? __ldg(force + tile + s) : 0.f; // past the pulse: free ringing up to the injection frame
             float sum = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -509,7 +613,7 @@ __global__ void __launch_bounds__(kMixWarps * 32) MixKernel(const float *__restr
             const PulseWarp pw = pulses.Warps[i];
             const uint32_t start = pulses.Impacts[pw.Impact].Start;
             if (start > n_abs) break;
-            if (n_abs - start < pulses.Impacts[pw.Impact].Len) extra += pulses.Rows[pw.RowOff + (n_abs - start)];
+            if (n_abs - start < pulses.Impacts[pw.Impact].RenderLen) extra += pulses.Rows[pw.RowOff + (n_abs - start)];
         }
         sum += extra;
     }
@@ -556,6 +660,30 @@ __global__ void ClickKernel(const DevImpact *__restrict__ impacts, const DevImpa
         z1 = __fadd_rn(__fmul_rn(-t.ClickA1, y), z2);
         z2 = __fsub_rn(__fmul_rn(-t.ClickB0, u), __fmul_rn(t.ClickA2, y));
         atomicAdd(out + s, __fmul_rn(y, t.ClickGain));
+    }
+}
+
+// One thread per mode pair: rows j = 1..128 of the power stages, c^j by FP64 products of the float coefficient
+// (the same arithmetic as MakePowers), each value split into its TF32 head and FP32 tail.
+__global__ void __launch_bounds__(128) PowerTableKernel(const BankView b, float *__restrict__ powers) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; // chunk * 4 + pair
+    if (idx >= b.NChunks * 4) return;
+    const uint32_t chunk = idx >> 2, pair = idx & 3;
+    const uint32_t group = chunk / kTmGroupChunks, lc = chunk % kTmGroupChunks;
+    const uint32_t mode = chunk * kLanes + pair * 2;
+    const double ax = b.CoeffRe[mode], bx = b.CoeffIm[mode], ay = b.CoeffRe[mode + 1], by = b.CoeffIm[mode + 1];
+    float *stage = powers + (size_t(group) * kTmStagesPerGroup + (lc >> 1)) * TmPowerStageFloats() + size_t((lc & 1) * 4 + pair) * kTmBlock * 4;
+    double rx = ax, ix = bx, ry = ay, iy = by;
+    for (uint32_t j = 0; j < kTmBlock; ++j) {
+        const float4 v = {float(rx), float(ix), float(ry), float(iy)};
+        const float4 head = {Tf32Head(v.x), Tf32Head(v.y), Tf32Head(v.z), Tf32Head(v.w)};
+        const float4 tail = {v.x - head.x, v.y - head.y, v.z - head.z, v.w - head.w};
+        float *at = stage + (j >> 3) * 32 + (j & 7) * 4;
+        *reinterpret_cast<float4 *>(at) = head;
+        *reinterpret_cast<float4 *>(at + kTmBlock * kTmKChunk) = tail;
+        const double nrx = rx * ax - ix * bx, nry = ry * ay - iy * by;
+        ix = rx * bx + ix * ax, iy = ry * by + iy * ay;
+        rx = nrx, ry = nry;
     }
 }
 
@@ -636,20 +764,35 @@ void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int ste
     }();
     static bool configured = false;
     if (!configured) {
-        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<1, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = true;
     }
     switch (steps) {
-        case 1: ResonatorKernel<1, 2><<<grid, kBlockThreads, smem, stream>>>(bank, plan); break;
-        case 2: ResonatorKernel<2, 2><<<grid, kBlockThreads, smem, stream>>>(bank, plan); break;
+        case 1: ResonatorKernel<1, 2, false><<<grid, kBlockThreads, smem, stream>>>(bank, plan); break;
+        case 2: ResonatorKernel<2, 2, false><<<grid, kBlockThreads, smem, stream>>>(bank, plan); break;
         default:
-            if (wide) ResonatorKernel<4, 1><<<grid, kBlockThreads, smem, stream>>>(bank, plan);
-            else ResonatorKernel<4, 2><<<grid, kBlockThreads, smem, stream>>>(bank, plan);
+            if (wide) ResonatorKernel<4, 1, false><<<grid, kBlockThreads, smem, stream>>>(bank, plan);
+            else ResonatorKernel<4, 2, false><<<grid, kBlockThreads, smem, stream>>>(bank, plan);
             break;
     }
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+void LaunchStateWalkKernel(const BankView &bank, const RenderPlan &plan, cudaStream_t stream, LaunchCounter &counter) {
+    if (bank.NChunks == 0 || plan.Frames == 0) return;
+    if (plan.NSegments != 1) Fail(ME_BAD_ARG, "the state walk is sequential in time");
+    ResonatorKernel<1, 2, true><<<bank.NChunks / kBlockThreads, kBlockThreads, kWarpsPerBlock * 256 * sizeof(float4), stream>>>(bank, plan);
+    ME_CUDA(cudaGetLastError());
+    ++counter.Launches;
+}
+
+void LaunchPowerTableKernel(const BankView &bank, float *powers, cudaStream_t stream, LaunchCounter &counter) {
+    if (bank.NChunks == 0) return;
+    PowerTableKernel<<<(bank.NChunks * 4 + 127) / 128, 128, 0, stream>>>(bank, powers);
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
 }

@@ -51,7 +51,8 @@ struct alignas(16) DevImpact {
     float PhaseRe, PhaseIm, RotRe, RotIm; // rotor state at Start and its per-sample rotation
     uint32_t End;        // frame at which the impact is retired, or the span's end
     uint32_t DeltaOff;   // offset of its end-of-pulse state increment in the delta buffers
-    uint32_t HasClick, Pad;
+    uint32_t HasClick;
+    uint32_t RenderLen;  // samples the pulse kernel renders on its own (>= Len): up to the frame its increment is injected at
 };
 struct alignas(16) DevImpactTail {
     float Gamma, AccelAmp, ClickB0, ClickA1;
@@ -86,6 +87,10 @@ struct RenderPlan {
     // silenced object with state left): the window is then rendered again sequentially in time.
     uint32_t *Speculation;
     uint32_t Debug;
+    // Tensor-core form (tensor_mix.cuh): the walk kernel (one segment: sequential in time, so culling is exact) writes
+    // the block-start state of every 128-frame time block as rows of States[tile][chunk group][head,tail][block][4096].
+    float *WalkStates;
+    uint32_t WalkBlocksPerTile;
 };
 
 struct PulsePlan {
@@ -111,6 +116,12 @@ void LaunchSegmentScan(const BankView &, const RenderPlan &, float *seg_re, floa
 // The free-running resonator bank over the window: one thread per 8-mode chunk and time segment.
 void LaunchResonatorKernel(const BankView &, const RenderPlan &, int steps, cudaStream_t, LaunchCounter &);
 uint32_t ResonatorRows(uint32_t n_chunks);
+// Tensor-core form, producer side: the same per-chunk walk over RenderModal blocks (culling, increments, final state)
+// as the resonator kernel, but advancing 128 frames per step with c^128 and writing the state stages instead of samples.
+void LaunchStateWalkKernel(const BankView &, const RenderPlan &, cudaStream_t, LaunchCounter &);
+// Power stages of the installed tuning: c^1..c^128 of every mode (FP64 products of the float coefficient), split into
+// TF32 head + FP32 tail, in the stage layout of tensor_mix.cuh. powers: [NChunks/256][128 stages][2][128*32] floats.
+void LaunchPowerTableKernel(const BankView &, float *powers, cudaStream_t, LaunchCounter &);
 // out[n] = sum of the partial rows in fixed order (the reference sums renderer buffers in a fixed order, :553-555)
 // plus the pulse rows overlapping n.
 void LaunchMixKernel(const float *partial, uint32_t rows, const RenderPlan &, const PulsePlan &, float *out, cudaStream_t, LaunchCounter &);

@@ -2,16 +2,19 @@
 //
 // One CTA renders one time tile (BlocksPerTile x 128 frames) of one chunk group: a 128 x N accumulator in tensor
 // memory, fed stage by stage (32 reduction elements = 16 modes) through a ring of shared-memory buffers.
-//   warp 0 (one lane): producer. Per stage two bulk copies HBM -> shared memory (power stage, state stage), completion
-//                      counted on the stage's "full" mbarrier.
+//   warp 0 (one lane): producer. Per stage a bulk copy (power stage, already a shared-memory image) and a 4-D TMA tile
+//                      copy (32 reduction elements x all time blocks x head/tail of the row-major states, 128-byte
+//                      swizzle), completion counted on the stage's "full" mbarrier.
 //   warp 1 (one lane): issues tcgen05.mma kind::tf32, three per 8-wide reduction step (head*head, head*tail,
 //                      tail*head), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
 //   warps 2-5:         epilogue. tcgen05.ld of the accumulator (lane = frame inside the block, column = block) and
 //                      coalesced stores of the group's partial mix row.
-// Operand images in HBM are already in the canonical K-major no-swizzle UMMA layout, so no tensor map is needed.
 #include "tensor_mix.cuh"
 
 #include "common.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 namespace me {
 namespace {
@@ -46,6 +49,17 @@ __device__ __forceinline__ void BarrierWait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void BulkCopy(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(SmemAddr(dst)), "l"(src), "r"(bytes), "r"(SmemAddr(bar))
                  : "memory");
+}
+
+__device__ __forceinline__ void TensorCopy4(void *dst, const CUtensorMap *map, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(SmemAddr(dst)), "l"(reinterpret_cast<uint64_t>(map)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(SmemAddr(bar))
+                 : "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 bytes (32 TF32), 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t SwizzledDescriptor(uint32_t smem_addr) {
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
 }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): 8-row core matrices of 128
@@ -83,23 +97,26 @@ __device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&v)[32]) {
 // kFoldStages stages (24 MMAs, <= 1.5e-6) and folded into FP32 registers by the epilogue warps with round-to-nearest
 // adds; two accumulators alternate so the fold of one overlaps the MMAs into the other.
 constexpr uint32_t kFoldStages = 2;
-constexpr uint32_t kFolds = kTmStagesPerGroup / kFoldStages;
 
 template<uint32_t N, uint32_t Stages>
-__global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPlan plan) {
+__global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPlan plan, const __grid_constant__ CUtensorMap states_map) {
     static_assert(N == 128, "the epilogue keeps one accumulator row of N columns in registers");
     constexpr uint32_t kStateHalfBytes = N * kTmKChunk * 4;
     constexpr uint32_t kPowerBytes = 2 * kPowerHalfBytes, kStateBytes = 2 * kStateHalfBytes;
     constexpr uint32_t kStageBytes = kPowerBytes + kStateBytes;
     constexpr uint32_t kSteps = kTmKChunk / 8; // MMAs of K = 8 per stage and operand pair
-    extern __shared__ __align__(1024) uint8_t stage_storage[];
+    extern __shared__ __align__(1024) uint8_t stage_storage_raw[];
+    // The 128-byte swizzle is a function of the shared-memory address: the ring starts on a 1024-byte boundary.
+    uint8_t *stage_storage = stage_storage_raw + ((1024u - (SmemAddr(stage_storage_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full_bar[Stages], empty_bar[Stages], accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // Tiles of one group are adjacent in launch order, so the CTAs streaming the same power stages run together and
     // share them through L2.
-    const uint32_t tile = blockIdx.x % plan.Tiles, group = blockIdx.x / plan.Tiles;
+    const uint32_t tile = blockIdx.x % plan.Tiles, row_index = blockIdx.x / plan.Tiles;
+    const uint32_t first_group = row_index * plan.GroupsPerRow;
+    const uint32_t n_stages = plan.GroupsPerRow * kTmStagesPerGroup;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < Stages; ++s) BarrierInit(&full_bar[s], 1), BarrierInit(&empty_bar[s], 1);
@@ -117,23 +134,23 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint8_t *powers = reinterpret_cast<const uint8_t *>(plan.Powers) + size_t(group) * kTmStagesPerGroup * kPowerBytes;
-            const uint8_t *states = reinterpret_cast<const uint8_t *>(plan.States) + (size_t(tile) * plan.Groups + group) * kTmStagesPerGroup * kStateBytes;
-            for (uint32_t k = 0; k < kTmStagesPerGroup; ++k) {
+            const uint8_t *powers = reinterpret_cast<const uint8_t *>(plan.Powers) + size_t(first_group) * kTmStagesPerGroup * kPowerBytes;
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&states_map)) : "memory");
+            for (uint32_t k = 0; k < n_stages; ++k) {
                 const uint32_t s = k % Stages, round = k / Stages;
                 if (round) BarrierWait(&empty_bar[s], (round - 1) & 1);
                 uint8_t *stage = stage_storage + size_t(s) * kStageBytes;
                 BarrierExpectTx(&full_bar[s], kStageBytes);
-                BulkCopy(stage, powers + size_t(k) * kPowerBytes, kPowerBytes, &full_bar[s]);
-                BulkCopy(stage + kPowerBytes, states + size_t(k) * kStateBytes, kStateBytes, &full_bar[s]);
+                TensorCopy4(stage, &states_map, (k % kTmStagesPerGroup) * kTmKChunk, 0, 0, tile * plan.Groups + first_group + k / kTmStagesPerGroup, &full_bar[s]);
+                BulkCopy(stage + kStateBytes, powers + size_t(k) * kPowerBytes, kPowerBytes, &full_bar[s]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc = InstructionDescriptor(kTmBlock, N);
-            // Inside a half the 16-byte K pieces are (rows*16) bytes apart and the 8-row groups 128 bytes.
-            constexpr uint32_t lbo_p = kTmBlock * 16, lbo_w = N * 16, sbo = 128;
-            for (uint32_t k = 0; k < kTmStagesPerGroup; ++k) {
+            // Power halves: the 16-byte K pieces are 2048 bytes apart and the 8-row groups 128 bytes.
+            constexpr uint32_t lbo_p = kTmBlock * 16, sbo = 128;
+            for (uint32_t k = 0; k < n_stages; ++k) {
                 const uint32_t s = k % Stages, round = k / Stages;
                 const uint32_t fold = k / kFoldStages, buffer = fold & 1;
                 const bool opens = k % kFoldStages == 0;
@@ -147,10 +164,11 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
                 const uint32_t tmem_d = tmem_base + buffer * N;
 #pragma unroll
                 for (uint32_t kk = 0; kk < kSteps; ++kk) {
-                    const uint64_t p_head = MatrixDescriptor(stage + kk * 2 * lbo_p, lbo_p, sbo);
-                    const uint64_t p_tail = MatrixDescriptor(stage + kPowerHalfBytes + kk * 2 * lbo_p, lbo_p, sbo);
-                    const uint64_t w_head = MatrixDescriptor(stage + kPowerBytes + kk * 2 * lbo_w, lbo_w, sbo);
-                    const uint64_t w_tail = MatrixDescriptor(stage + kPowerBytes + kStateHalfBytes + kk * 2 * lbo_w, lbo_w, sbo);
+                    const uint64_t p_head = MatrixDescriptor(stage + kStateBytes + kk * 2 * lbo_p, lbo_p, sbo);
+                    const uint64_t p_tail = MatrixDescriptor(stage + kStateBytes + kPowerHalfBytes + kk * 2 * lbo_p, lbo_p, sbo);
+                    // Inside the swizzle atom a K step of 8 TF32 is 32 bytes further along the row.
+                    const uint64_t w_head = SwizzledDescriptor(stage + kk * 32);
+                    const uint64_t w_tail = SwizzledDescriptor(stage + kStateHalfBytes + kk * 32);
                     MmaTf32(tmem_d, p_tail, w_head, idesc, !(opens && kk == 0));
                     MmaTf32(tmem_d, p_head, w_tail, idesc, 1);
                     MmaTf32(tmem_d, p_head, w_head, idesc, 1);
@@ -167,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
 #pragma unroll
         for (uint32_t c = 0; c < N; ++c) acc[c] = 0.f;
 #pragma unroll 1
-        for (uint32_t fold = 0; fold < kFolds; ++fold) {
+        for (uint32_t fold = 0; fold < n_stages / kFoldStages; ++fold) {
             const uint32_t buffer = fold & 1;
             BarrierWait(&accum_full[buffer], (fold >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -182,7 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(&accum_empty[buffer])) : "memory");
         }
-        float *out = plan.Partial + size_t(group) * plan.Frames;
+        float *out = plan.Partial + size_t(row_index) * plan.Frames;
         const uint32_t tile_frame = tile * N * kTmBlock;
 #pragma unroll
         for (uint32_t c = 0; c < N; ++c) {
@@ -195,11 +213,30 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N) : "memory");
 }
 
+PFN_cuTensorMapEncodeTiled EncodeTiled() {
+    static PFN_cuTensorMapEncodeTiled fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &status) != cudaSuccess || status != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(p);
+    }();
+    if (!fn) Fail(ME_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+    return fn;
+}
+
 template<uint32_t N, uint32_t Stages>
 void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
-    constexpr uint32_t bytes = Stages * (2 * kPowerHalfBytes + 2 * N * kTmKChunk * 4);
+    constexpr uint32_t bytes = Stages * (2 * kPowerHalfBytes + 2 * N * kTmKChunk * 4) + 1024; // + slack to align the ring to the swizzle period
+    // States[tile*group][half][block][4096] as a 4-D tensor, innermost first; one box = one stage.
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {kTmGroupK, N, 2, cuuint64_t(plan.Tiles) * plan.Groups};
+    const cuuint64_t strides[3] = {cuuint64_t(kTmGroupK) * 4, cuuint64_t(N) * kTmGroupK * 4, cuuint64_t(2) * N * kTmGroupK * 4};
+    const cuuint32_t box[4] = {kTmKChunk, N, 2, 1}, unit[4] = {1, 1, 1, 1};
+    const CUresult r = EncodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(plan.States), dims, strides, box, unit, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) Fail(ME_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", int(r));
     ME_CUDA(cudaFuncSetAttribute(TensorMixKernel<N, Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); // per device, cheap
-    TensorMixKernel<N, Stages><<<plan.Groups * plan.Tiles, kThreads, bytes, stream>>>(plan);
+    TensorMixKernel<N, Stages><<<plan.Groups / plan.GroupsPerRow * plan.Tiles, kThreads, bytes, stream>>>(plan, map);
     ME_CUDA(cudaGetLastError());
 }
 
@@ -207,6 +244,7 @@ void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
 
 void LaunchTensorMixKernel(const TensorMixPlan &plan, cudaStream_t stream) {
     if (plan.Groups == 0 || plan.Tiles == 0) return;
+    if (plan.GroupsPerRow == 0 || plan.Groups % plan.GroupsPerRow != 0) Fail(ME_BAD_ARG, "tensor mix: groups per row must divide the groups");
     if (plan.BlocksPerTile == 128) Launch<128, 3>(plan, stream);
     else Fail(ME_BAD_ARG, "tensor mix: blocks per tile must be 128");
 }

@@ -21,22 +21,29 @@ constexpr uint32_t kTmKChunk = 32;     // reduction elements per pipeline stage 
 constexpr uint32_t kTmGroupChunks = 256; // chunk slots per reduction group (== kBlockThreads: one resonator CTA)
 constexpr uint32_t kTmStagesPerGroup = kTmGroupChunks * 8 * 2 / kTmKChunk; // 128
 
-// Operand images in HBM are exactly what a pipeline stage holds in shared memory (the canonical K-major, no-swizzle
-// UMMA layout), so a stage is filled by two plain bulk copies:
-//   element (row r, reduction index k) of a [rows x 32] half lives at byte (k/4)*rows*16 + (r/8)*128 + (r%8)*16 + (k%4)*4
+// Power stages in HBM are exactly what a pipeline stage holds in shared memory (the canonical K-major, no-swizzle UMMA
+// layout), so one plain bulk copy fills them:
+//   element (row r, reduction index k) of a [128 x 32] half lives at byte (k/4)*2048 + (r/8)*128 + (r%8)*16 + (k%4)*4
 // and a stage is [head half][tail half]. Reduction index 2*m holds Re(c^(j+1)) in P and Im w in W; 2*m+1 holds
-// Im(c^(j+1)) and Re w, m = mode inside the stage (0..15).
-inline size_t TmPowerStageFloats() { return size_t(2) * kTmBlock * kTmKChunk; }
-inline size_t TmStateStageFloats(uint32_t blocks_per_tile) { return size_t(2) * blocks_per_tile * kTmKChunk; }
+// Im(c^(j+1)) and Re w, m = mode inside the group (0..2047).
+// States are written by the walk kernel as plain row-major matrices, one row of the group's 4096 reduction elements
+// per time block, so a warp of chunk-threads stores 2 KB contiguous per step:
+//   States[tile][group][half (0 head, 1 tail)][time block][4096]
+// and a stage (32 reduction elements of all blocks, both halves) reaches shared memory by one 4-D TMA tile copy that
+// applies the 128-byte swizzle the UMMA descriptor expects.
+__host__ __device__ constexpr size_t TmPowerStageFloats() { return size_t(2) * kTmBlock * kTmKChunk; }
+constexpr uint32_t kTmGroupK = kTmGroupChunks * 8 * 2; // 4096 reduction elements per group
+__host__ __device__ constexpr size_t TmStateTileFloats(uint32_t blocks_per_tile) { return size_t(2) * blocks_per_tile * kTmGroupK; }
 
 struct TensorMixPlan {
     uint32_t Groups;          // chunk groups (reduction ranges of 256 chunk slots)
+    uint32_t GroupsPerRow;    // consecutive groups reduced by one CTA into one partial row (divides Groups)
     uint32_t Tiles;           // time tiles in the window
-    uint32_t BlocksPerTile;   // 128 or 256 time blocks (the N extent)
+    uint32_t BlocksPerTile;   // 128 time blocks (the N extent)
     uint32_t Frames;          // valid frames of the window (the last tile may be ragged)
     const float *Powers;      // [Groups][128 stages] power stages
-    const float *States;      // [Tiles][Groups][128 stages] state stages
-    float *Partial;           // [Groups][Frames] per-group mixes
+    const float *States;      // [Tiles][Groups][2][BlocksPerTile][4096]
+    float *Partial;           // [Groups / GroupsPerRow][Frames] partial mixes
 };
 
 void LaunchTensorMixKernel(const TensorMixPlan &, cudaStream_t);

@@ -1,7 +1,7 @@
 """The tcgen05 mix kernel (mesheditor_b200/csrc/tensor_mix.cu) against a float64 matrix product.
 
 out[group][tile*N*128 + n*128 + r] = sum_k P_group[r, k] * W_tile,group[n, k] over the group's 4096 reduction elements,
-operands split into a TF32 head and an FP32 tail (3xTF32). Tolerance: 5e-6 of the row scale (measured 2.1e-6, FP32-level; a plain TF32
+operands split into a TF32 head and an FP32 tail (3xTF32); powers in the shared-memory stage layout, states row-major. Tolerance: 5e-6 of the row scale (measured 2.1e-6, FP32-level; a plain TF32
 product would miss it by 1e-3).
 """
 import ctypes as C
@@ -35,8 +35,8 @@ def pack(mat):
     return out
 
 
-@pytest.mark.parametrize("n_blocks,groups,tiles,ragged", [(128, 2, 2, 0), (128, 1, 2, 777), (128, 3, 1, 5000)])
-def test_tensor_mix_matches_float64_product(n_blocks, groups, tiles, ragged):
+@pytest.mark.parametrize("n_blocks,groups,per_row,tiles,ragged", [(128, 2, 1, 2, 0), (128, 1, 1, 2, 777), (128, 4, 2, 1, 5000)])
+def test_tensor_mix_matches_float64_product(n_blocks, groups, per_row, tiles, ragged):
     from mesheditor_b200 import lib
     from mesheditor_b200._lib import check
 
@@ -45,14 +45,18 @@ def test_tensor_mix_matches_float64_product(n_blocks, groups, tiles, ragged):
     P = rng.standard_normal((groups, 128, K)).astype(np.float32) * np.exp(rng.uniform(-6, 0, (groups, 1, K))).astype(np.float32)
     W = rng.standard_normal((tiles, groups, n_blocks, K)).astype(np.float32)
     powers = np.stack([pack(P[g]) for g in range(groups)])
-    states = np.stack([np.stack([pack(W[t, g]) for g in range(groups)]) for t in range(tiles)])
+    states = np.ascontiguousarray(np.stack(split_tf32(W), axis=2))  # [tiles][groups][head, tail][blocks][4096], row-major
     frames = tiles * n_blocks * 128 - ragged
-    out = np.full((groups, frames), np.nan, np.float32)
+    rows = groups // per_row
+    out = np.full((rows, frames), np.nan, np.float32)
     ms = C.c_float(0)
-    check(lib().me_debug_tensor_mix(0, powers.ctypes.data, states.ctypes.data, groups, tiles, n_blocks, frames, 1, out.ctypes.data, C.byref(ms)))
-    for g in range(groups):
-        want = np.concatenate([(W[t, g].astype(np.float64) @ P[g].astype(np.float64).T).reshape(-1) for t in range(tiles)])[:frames]
-        scale = np.sqrt((P[g].astype(np.float64) ** 2).sum(axis=1).max())
-        err = np.abs(out[g] - want).max()
-        assert np.isfinite(out[g]).all()
-        assert err <= 5e-6 * scale, f"group {g}: max error {err:.3e} vs scale {scale:.3e}"
+    check(lib().me_debug_tensor_mix(0, powers.ctypes.data, states.ctypes.data, groups, per_row, tiles, n_blocks, frames, 1, out.ctypes.data, C.byref(ms)))
+    for r in range(rows):
+        want, scale = 0.0, 0.0
+        for g in range(r * per_row, (r + 1) * per_row):
+            want = want + np.concatenate([(W[t, g].astype(np.float64) @ P[g].astype(np.float64).T).reshape(-1) for t in range(tiles)])[:frames]
+            scale += (P[g].astype(np.float64) ** 2).sum(axis=1).max()
+        scale = np.sqrt(scale)
+        err = np.abs(out[r] - want).max()
+        assert np.isfinite(out[r]).all()
+        assert err <= 5e-6 * scale, f"row {r}: max error {err:.3e} vs scale {scale:.3e}"
