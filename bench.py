@@ -39,6 +39,15 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
+def tensor_traffic(which):
+    """DRAM bytes per launch of the tensor-form kernels from the committed ncu --set full capture, when there is one."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "resonator_traffic.json")) as f:
+            return json.load(f).get(f"{which}_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -143,7 +152,7 @@ def workload_config(n_gpus):
         "workload": f"BASELINE.json configs[4]: polyphonic resonator bank {VOICES} voices x {MODES} modes x {SECONDS:g} s at {RATE:g} Hz, strike per voice at frame 0 + 2 Hz Poisson re-strikes (MT19937 12345), 512-frame blocks",
         "voices": VOICES, "modes_per_voice": MODES, "frames": int(SECONDS * RATE), "sample_rate": RATE, "block_frames": BLOCK,
         "parallelism": f"voices sharded over {n_gpus} GPU(s), NCCL all-reduce of the mono mix" if n_gpus > 1 else "single GPU",
-        "l2_policy": "working set > L2: per-warp partial mixes of one step exceed 126 MB, nothing is reused across steps",
+        "l2_policy": "working set > L2: one step writes and reads 31 GB of block-start states (tensor-core form) or 3.9 GB of per-warp partial mixes (sample loop); nothing is reused across steps",
     }
 
 
@@ -178,6 +187,7 @@ def run_ours(args):
     for _ in range(hi - lo):
         bank.add_modes(modes)
     bank.install(0)
+    bank.set_render_path({"auto": 0, "loop": 1, "tensor": 2}[args.render_path])
 
     out = torch.zeros(frames, dtype=torch.float32, device="cuda")
     host_out = torch.zeros(frames, dtype=torch.float32).pin_memory()
@@ -214,7 +224,7 @@ def run_ours(args):
         step_device()
     barrier()
 
-    kernel_ms, stats = [], None
+    kernel_ms, walk_ms, mix_ms, stats = [], [], [], None
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     elapsed_ms = 0.0
     with ClockSampler(local) as clocks:
@@ -227,7 +237,11 @@ def run_ours(args):
             barrier()
             elapsed_ms += start.elapsed_time(stop)
             stats = bank.stats()
+            if os.environ.get("ME_BENCH_DEBUG"):
+                print(f"[bench] step {start.elapsed_time(stop):.2f} ms, library total {stats['total_device_ms']:.2f} ms, walk {stats['walk_kernel_ms']:.2f}, mix {stats['tensor_mix_kernel_ms']:.2f}, host plan {stats['host_plan_ms']:.2f}", file=sys.stderr)
             kernel_ms.append(stats["resonator_kernel_ms"])
+            walk_ms.append(stats["walk_kernel_ms"])
+            mix_ms.append(stats["tensor_mix_kernel_ms"])
             launches[0] += stats["kernel_launches"]
     # e2e: wall clock around the host-buffer path.
     e2e_s = 0.0
@@ -275,21 +289,52 @@ def run_ours(args):
         # partial rows written once (4 B per warp-sample) — the latter is this design's own traffic, counted as such.
         mandatory = (hi - lo) * (32 * MODES) + 4 * frames
         base = cpu_reference(1, 0) if not args.no_cpu_baseline else None
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), live_mode_count_min=min_live, culling_triggered=min_live < MODES, time_segments=stats["time_segments"]),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": frames * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
-            "gpu_launches": total_launches,
-            "roofline": {
+        tensor_form = stats["tensor_windows"] > 0
+        if tensor_form:
+            # Tensor-core form. Dominant kernels: the tcgen05 mix (3xTF32 GEMM) and the state walk that
+            # feeds it. Issued flops and written bytes follow from the padded layout: 4 voices of 63 chunks per 256-chunk
+            # group, 4096 reduction elements per group, 128 x 128 frames per tile.
+            chunks = -(-MODES // 8)
+            groups = -(-(hi - lo) // (256 // chunks))
+            tiles = -(-frames // 16384)
+            issued_flops = 3 * 2.0 * 128 * 128 * 4096 * groups * tiles
+            walk_bytes = 2.0 * 128 * 4096 * 4 * groups * tiles
+            m_ms, w_ms = sum(mix_ms) / len(mix_ms), sum(walk_ms) / len(walk_ms)
+            tf32_peak = pk.get("bf16_tflops", 2250.0) / 2
+            roofline = {
+                "bound": "tensor", "kernel": "TensorMixKernel<128,3> (tcgen05.mma kind::tf32, 3xTF32 split, FP32 register folds)", "achieved": issued_flops / (m_ms * 1e-3) / 1e12, "peak": tf32_peak,
+                "unit": "TFLOP/s", "frac": issued_flops / (m_ms * 1e-3) / 1e12 / tf32_peak, "traffic": tensor_traffic("mix"), "kernel_ms_per_launch": m_ms, "launches_per_step": stats["tensor_windows"],
+                "issued_flops_per_step": issued_flops, "share_of_step": m_ms / ms_per_step,
+                "peak_source": ("half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate; nominal 1125)" if "bf16_tflops" in pk else "nominal dense TF32 1125 TFLOP/s"),
+                "reference_fma_equivalent": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (m_ms * 1e-3) / 1e12,
+                "note": "the kernel streams 2 operand images (power stages from L2, state stages from HBM) at %.1f TB/s into shared memory; that ingest, not the MMA rate, bounds it" % ((issued_flops / (3 * 2.0 * 128 * 128 * 32)) * 65536 / (m_ms * 1e-3) / 1e12),
+            }
+            roofline_extra = {
+                "roofline_walk": {"bound": "hbm", "kernel": "ResonatorKernel<1,2,true> (state walk: c^128 steps, TF32 head/tail rows)", "achieved": walk_bytes / (w_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                  "frac": walk_bytes / (w_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": tensor_traffic("walk"), "kernel_ms_per_launch": w_ms, "algorithmic_bytes": walk_bytes, "share_of_step": w_ms / ms_per_step, "peak_source": pk_kind},
+                "fp32_pipe_equivalent": {"note": "the same mode-samples per second on the FP32 pipe would need this multiple of the measured scalar-FFMA ceiling (reference loop: 7 lane-ops per mode-sample; this repo's sample loop: 2.75)",
+                                         "reference_loop": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3) / fma_peak, "sample_loop": achieved / fma_peak, "ffma_peak_tlane_ops": fma_peak / 1e12},
+            }
+        else:
+            roofline = {
                 "bound": "fp32_fma", "kernel": "ResonatorKernel<4,2>", "achieved": achieved / 1e12, "peak": fma_peak / 1e12, "unit": "TFMA-lane-op/s",
                 "frac": achieved / fma_peak, "traffic": traffic, "kernel_ms_per_launch": k_ms,
                 "ops_per_mode_sample": OPS_PER_MODE_SAMPLE, "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                 "peak_three_fresh_operands": fma_peak_fresh / 1e12, "frac_of_register_file_bound": achieved / fma_peak_fresh,
                 "reference_op_equivalent_frac": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3) / fma_peak,
-            },
+            }
+            roofline_extra = {}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (3xTF32 products, FP32 accumulation)" if tensor_form else "f32", "data": "synthetic",
+            "config": dict(workload_config(world), live_mode_count_min=min_live, culling_triggered=min_live < MODES, time_segments=stats["time_segments"],
+                           render_path="tensor-core form: state walk + tcgen05 mix" if tensor_form else "FP32 sample loop", partial_rows=stats["partial_rows"]),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": frames * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": total_launches,
+            "roofline": roofline,
+            **roofline_extra,
             "roofline_hbm": {"bound": "hbm", "achieved": mandatory / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": mandatory / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_kind,
-                             "note": "mandatory bytes only; the path is FP32-issue bound by >100x (SURVEY.md F9)"},
+                             "note": "mandatory bytes of the reference formulation only (SURVEY.md F9)"},
             "clocks": clocks.summary(),
         }
         if base:
@@ -501,6 +546,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--render-path", default="auto", choices=["auto", "loop", "tensor"], help="resonator: kernels of the free-running bank (auto = tensor-core form for this workload)")
     ap.add_argument("--workload", default="resonator", choices=["resonator", "solve", "batch"],
                     help="resonator: configs[4] (default, the metric quoted at 1/2/4/8 GPUs); solve: configs[2], one 1M-tet mesh; batch: configs[3], 64 meshes sharded")
     args = ap.parse_args()

@@ -135,6 +135,10 @@ typedef struct MeRenderStats {
     uint32_t time_segments;         /* segments of the block-parallel scan along time (1 = sequential in time) */
     uint32_t scan_fallbacks;        /* windows re-rendered sequentially because culling fell inside them */
     uint32_t tensor_windows;        /* launch windows rendered in the tensor-core form (tcgen05 mix kernel) */
+    uint32_t partial_rows;          /* partial mix rows the last window left for the mix kernel */
+    float walk_kernel_ms;           /* tensor-core form: device time of the state walk kernel(s) */
+    float tensor_mix_kernel_ms;     /* tensor-core form: device time of the tcgen05 mix kernel(s) */
+    float host_plan_ms;             /* host time spent planning the spans (impact schedule, uploads) before their first launch */
     uint32_t reserved;
 } MeRenderStats;
 MeStatus me_bank_last_render_stats(const MeBank *, MeRenderStats *out);

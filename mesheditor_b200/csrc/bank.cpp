@@ -2,6 +2,7 @@
 #include "bank.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <numbers>
@@ -407,6 +408,7 @@ HostImpact MakeImpact(const MeModalEvent &e) {
 } // namespace
 
 void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<ScheduledImpact> &scheduled, float *out_dev, cudaStream_t stream) {
+    const auto plan_begin = std::chrono::steady_clock::now();
     const uint32_t n_obj = ObjectCount();
     const uint32_t n = uint32_t(scheduled.size());
     // Impacts sorted by (start, object): the order of the pulse rows in the mix.
@@ -443,7 +445,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         CallImpacts[i] = {.Start = s.Start, .Len = len, .ForceOff = uint32_t(force_total), .ExPos = im.ExPos, .Jx = im.Jx, .Jy = im.Jy, .Jz = im.Jz, .Object = im.Object, .PhaseRe = im.PhaseRe, .PhaseIm = im.PhaseIm, .RotRe = im.RotRe, .RotIm = im.RotIm, .End = s.End, .DeltaOff = uint32_t(delta_total), .HasClick = HasClick(im) ? 1u : 0u, .RenderLen = render_len};
         CallTails[i] = {.Gamma = im.Gamma, .AccelAmp = im.AccelAmp, .ClickB0 = im.ClickB0, .ClickA1 = im.ClickA1, .ClickA2 = im.ClickA2, .ClickZ1 = im.ClickZ1, .ClickZ2 = im.ClickZ2, .ClickGain = ClickGain * ListenerGain[im.Object]};
         for (uint32_t w = 0; w < warps; ++w) {
-            CallPulseWarps.push_back({.Impact = i, .Chunk0 = w * 32, .RowOff = uint32_t(row_total), .Pad = 0});
+            CallPulseWarps.push_back({.Impact = i, .Chunk0 = w * 32, .RowOff = uint32_t(row_total), .Start = s.Start, .RenderLen = render_len, .Pad = 0});
             row_total += render_len;
         }
         any_click |= HasClick(im);
@@ -487,6 +489,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     // Slots of the delta buffers the pulse kernel does not write (chunks past the object in a warp's tail are skipped,
     // every chunk inside the object is written) need no clearing.
 
+    Stats.host_plan_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - plan_begin).count();
     LaunchForceKernel(DImpacts.Ptr, DTails.Ptr, n, DForce.Ptr, stream, Counter);
     const PulsePlan pulses{.NPulseWarps = uint32_t(CallPulseWarps.size()), .Warps = DPulseWarps.Ptr, .Impacts = DImpacts.Ptr, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
     BankView view = View();
@@ -502,10 +505,13 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         uint32_t window = uint32_t(std::min<uint64_t>(blocks_in_budget * block_frames, frames));
         if (tensor_span) {
             const uint64_t tile_bytes = uint64_t(groups) * TmStateTileFloats(TensorBlocksPerTile) * sizeof(float);
-            size_t free_bytes = 0, total_bytes = 0;
-            ME_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
-            // What the pool already holds for this buffer is reusable; beyond that stay within half of the free memory.
-            const uint64_t budget = std::min<uint64_t>(TensorStateBudgetBytes, std::max<uint64_t>(DWalkStates.Capacity * sizeof(float), free_bytes / 2));
+            // Asked once: the query takes a driver lock that monitoring tools (nvidia-smi) contend for.
+            if (StateBudgetBytes == 0) {
+                size_t free_bytes = 0, total_bytes = 0;
+                ME_CUDA(cudaMemGetInfo(&free_bytes, &total_bytes));
+                StateBudgetBytes = std::min<uint64_t>(TensorStateBudgetBytes, free_bytes / 2);
+            }
+            const uint64_t budget = std::max<uint64_t>(StateBudgetBytes, DWalkStates.Capacity * sizeof(float));
             const uint64_t tiles_in_budget = std::max<uint64_t>(1, budget / tile_bytes);
             window = uint32_t(std::min<uint64_t>(tiles_in_budget * TensorTileFrames, (uint64_t(frames) + TensorTileFrames - 1) / TensorTileFrames * TensorTileFrames));
             if (PowersDirty || PowersVersion != TuningVersion) {
@@ -577,6 +583,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 LaunchResonatorKernel(view, plan, Steps, stream, Counter);
             };
             cudaEvent_t k0 = NextEvent(), k1 = NextEvent();
+            EventKind.push_back(0);
             ME_CUDA(cudaEventRecord(k0, stream));
             bool tensor_window = tensor_span && !SpeculationFailed;
             uint32_t segments = 1;
@@ -588,8 +595,10 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 DGroupMix.Reserve(size_t(mix_rows) * wf);
                 plan.WalkStates = DWalkStates.Ptr;
                 ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
-                LaunchStateWalkKernel(view, plan, stream, Counter);
-                LaunchTensorMixKernel({.Groups = groups, .GroupsPerRow = groups_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
+                Timed(1, stream, [&] { LaunchStateWalkKernel(view, plan, stream, Counter); });
+                Timed(2, stream, [&] {
+                    LaunchTensorMixKernel({.Groups = groups, .GroupsPerRow = groups_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
+                });
                 ++Counter.Launches;
                 // Only code 8 (an increment off the time-block grid) can invalidate a sequential walk.
                 if (speculation_failed() & 8u) {
@@ -624,6 +633,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
             }
             ME_CUDA(cudaEventRecord(k1, stream));
             Stats.time_segments = std::max(Stats.time_segments, segments);
+            Stats.partial_rows = tensor_window ? mix_rows : rows;
             if (tensor_window) LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, pulses, out_dev + begin, stream, Counter);
             else LaunchMixKernel(DPartial.Ptr, rows, plan, pulses, out_dev + begin, stream, Counter);
             Side ^= 1;
@@ -666,6 +676,7 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
     Stats = {};
     Counter = {};
     EventsUsed = 0;
+    EventKind.clear();
     StatsResolved = false;
     float *out_dev = out;
     if (!out_is_device) {
@@ -758,11 +769,13 @@ const MeRenderStats &Bank::LastStats() {
         if (cudaEventSynchronize(EvEnd) == cudaSuccess) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, EvBegin, EvEnd) == cudaSuccess) Stats.total_device_ms = ms;
-            float kernel = 0.f;
+            float kernel[3] = {0.f, 0.f, 0.f};
             for (uint32_t i = 0; i + 1 < EventsUsed; i += 2) {
-                if (cudaEventElapsedTime(&ms, EventPool[i], EventPool[i + 1]) == cudaSuccess) kernel += ms;
+                if (cudaEventElapsedTime(&ms, EventPool[i], EventPool[i + 1]) == cudaSuccess) kernel[EventKind[i / 2]] += ms;
             }
-            Stats.resonator_kernel_ms = kernel;
+            Stats.resonator_kernel_ms = kernel[0];
+            Stats.walk_kernel_ms = kernel[1];
+            Stats.tensor_mix_kernel_ms = kernel[2];
         }
         StatsResolved = true;
     }

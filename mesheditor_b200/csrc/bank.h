@@ -69,6 +69,15 @@ private:
     void ResetObjectOnDevice(uint32_t object, bool clear_state, cudaStream_t);
     void RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<ScheduledImpact> &, float *out_dev, cudaStream_t);
     cudaEvent_t NextEvent();
+    // Brackets `launch` with an event pair of the given kind.
+    template<typename F>
+    void Timed(uint8_t kind, cudaStream_t stream, F &&launch) {
+        cudaEvent_t a = NextEvent(), b = NextEvent();
+        EventKind.push_back(kind);
+        ME_CUDA(cudaEventRecord(a, stream));
+        launch();
+        ME_CUDA(cudaEventRecord(b, stream));
+    }
     BankView View() const;
 
     float SampleRate;
@@ -76,6 +85,7 @@ private:
     cudaStream_t OwnStream{nullptr};
     cudaEvent_t EvBegin{nullptr}, EvEnd{nullptr};
     std::vector<cudaEvent_t> EventPool; // begin/end pairs around every resonator kernel launch of the last call
+    std::vector<uint8_t> EventKind;     // per pair: 0 the whole resonator stage of a window, 1 the walk kernel, 2 the tcgen05 mix kernel
     uint32_t EventsUsed{0};
     bool StatsResolved{true};
 
@@ -122,6 +132,7 @@ private:
 
     // Tensor-core form (tensor_mix.cuh): power stages of the installed tuning, state stages and group mixes of a window.
     DeviceBuffer<float> DPowers, DWalkStates, DGroupMix;
+    uint64_t StateBudgetBytes{0}; // HBM the state stages of one launch window may take (half of what was free at first use, at most 40 GB)
     bool PowersDirty{true};
     uint64_t TuningVersion{1}, PowersVersion{0}; // the power stages follow the coefficients, not the install
     uint32_t RenderPath{0}; // 0 automatic, 1 sample loop (FP32 pipe), 2 tensor-core form wherever the span allows it

@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(128) SegmentScanKernel(const BankView b, const
 // the eight partial sums are combined in warp order.
 constexpr uint32_t kMixWarps = 8;
 __global__ void __launch_bounds__(kMixWarps * 32) MixKernel(const float *__restrict__ partial, uint32_t rows, const RenderPlan plan, const PulsePlan pulses, float *__restrict__ out) {
-    __shared__ float sums[kMixWarps][32];
+    __shared__ float sums[kMixWarps][32], pulse_sums[kMixWarps][32];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n = blockIdx.x * 32 + lane;
     const bool in_range = n < plan.Frames;
@@ -592,32 +592,32 @@ __global__ void __launch_bounds__(kMixWarps * 32) MixKernel(const float *__restr
         }
         for (; r < rows; r += kMixWarps) a += partial[size_t(r) * plan.Frames + n];
     }
-    sums[warp][lane] = (a + b2) + (c + d);
-    __syncthreads();
-    if (warp != 0 || !in_range) return;
-    float sum = 0.f;
-#pragma unroll
-    for (uint32_t k = 0; k < kMixWarps; ++k) sum += sums[k][lane];
-    if (pulses.NPulseWarps) {
+    // The pulse rows overlapping n, sorted by start: warp k adds every eighth one, again a fixed order.
+    float extra = 0.f;
+    if (in_range && pulses.NPulseWarps) {
         const uint32_t n_abs = plan.FrameBegin + n;
         // First pulse-warp whose start could still cover n_abs.
         const uint32_t earliest = n_abs >= pulses.MaxLen ? n_abs - pulses.MaxLen + 1 : 0;
         uint32_t lo = 0, hi = pulses.NPulseWarps;
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (pulses.Impacts[pulses.Warps[mid].Impact].Start < earliest) lo = mid + 1;
+            if (pulses.Warps[mid].Start < earliest) lo = mid + 1;
             else hi = mid;
         }
-        float extra = 0.f;
-        for (uint32_t i = lo; i < pulses.NPulseWarps; ++i) {
+        for (uint32_t i = lo + warp; i < pulses.NPulseWarps; i += kMixWarps) {
             const PulseWarp pw = pulses.Warps[i];
-            const uint32_t start = pulses.Impacts[pw.Impact].Start;
-            if (start > n_abs) break;
-            if (n_abs - start < pulses.Impacts[pw.Impact].RenderLen) extra += pulses.Rows[pw.RowOff + (n_abs - start)];
+            if (pw.Start > n_abs) break;
+            if (n_abs - pw.Start < pw.RenderLen) extra += pulses.Rows[pw.RowOff + (n_abs - pw.Start)];
         }
-        sum += extra;
     }
-    out[n] = sum;
+    sums[warp][lane] = (a + b2) + (c + d);
+    pulse_sums[warp][lane] = extra;
+    __syncthreads();
+    if (warp != 0 || !in_range) return;
+    float sum = 0.f, pulse_sum = 0.f;
+#pragma unroll
+    for (uint32_t k = 0; k < kMixWarps; ++k) sum += sums[k][lane], pulse_sum += pulse_sums[k][lane];
+    out[n] = sum + pulse_sum;
 }
 
 // One thread per impact: the raised-cosine force curve from a unit-circle rotor, with the reference's own float

@@ -62,7 +62,9 @@ struct alignas(16) DevImpactTail {
 struct PulseWarp {
     uint32_t Impact;     // index into the DevImpact array
     uint32_t Chunk0;     // first chunk (inside the object) this warp covers
-    uint32_t RowOff;     // offset of its Len output samples in the pulse rows
+    uint32_t RowOff;     // offset of its RenderLen output samples in the pulse rows
+    uint32_t Start;      // == Impacts[Impact].Start and .RenderLen, so the mix kernel reads one record per pulse-warp
+    uint32_t RenderLen;
     uint32_t Pad;
 };
 
