@@ -146,7 +146,7 @@ MeStatus me_bank_last_render_stats(const MeBank *, MeRenderStats *out);
 MeStatus me_bank_set_time_segments(MeBank *, uint32_t time_segments);
 /* Which kernels render the free-running bank: 0 = automatic (tensor-core form for long offline spans, sample loop
  * otherwise), 1 = always the FP32 sample loop, 2 = the tensor-core form wherever the span allows it (block_frames a
- * multiple of 128 that divides 16384). Both forms implement RenderObjectFast (ModalAudio.cpp:86-147) to the same
+ * multiple of 256 that divides 32768). Both forms implement RenderObjectFast (ModalAudio.cpp:86-147) to the same
  * 1e-5-of-peak bar. */
 MeStatus me_bank_set_render_path(MeBank *, uint32_t path);
 
@@ -303,8 +303,8 @@ MeStatus me_measure_fp32_fma_rate(int device, int packed, int iters, double *fma
 
 /* Unit-test entry of the tensor-core mix (tensor_mix.cuh): out[row][frame] = sum over the 4096 reduction elements of
  * each of the row's groups_per_row consecutive groups of power * state, operands given as host images of the stage layout documented in tensor_mix.cuh
- * (powers: groups*128 stages of 2*128*32 floats, stage layout; states: [tiles][groups][head,tail][blocks_per_tile][4096] floats).
- * blocks_per_tile is 128; frames <= tiles*blocks_per_tile*128. `milliseconds` (may be NULL) receives the
+ * (powers: groups*256 stages of 2*256*16 floats, stage layout; states: [tiles][groups][head,tail][blocks_per_tile][4096] floats).
+ * blocks_per_tile is 128; frames <= tiles*blocks_per_tile*256. `milliseconds` (may be NULL) receives the
  * kernel time of the last of `repeats` launches. */
 MeStatus me_debug_tensor_mix(int device, const float *powers, const float *states, uint32_t groups, uint32_t groups_per_row, uint32_t tiles, uint32_t blocks_per_tile, uint32_t frames,
                              uint32_t repeats,

@@ -414,10 +414,11 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     // Impacts sorted by (start, object): the order of the pulse rows in the mix.
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    const auto by_start_then_object = [&](uint32_t a, uint32_t b) {
         const auto &x = scheduled[a], &y = scheduled[b];
         return x.Start != y.Start ? x.Start < y.Start : x.AtStart.Object < y.AtStart.Object;
-    });
+    };
+    if (!std::is_sorted(order.begin(), order.end(), by_start_then_object)) std::stable_sort(order.begin(), order.end(), by_start_then_object);
     CallImpacts.resize(n);
     CallTails.resize(n);
     CallPulseWarps.clear();
@@ -454,26 +455,51 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         if (len) delta_total += ObjStride[im.Object];
     }
     // Per object: increments in frame order, and the merged intervals during which it holds a live impact.
+    // (impacts are in start order, so a counting sort by object leaves each object's lists in start order too)
     CallInjectPtr.assign(n_obj + 1, 0), CallExcitePtr.assign(n_obj + 1, 0);
-    std::vector<std::vector<std::pair<uint32_t, uint32_t>>> inject(n_obj), excite(n_obj);
     for (uint32_t i = 0; i < n; ++i) {
         const auto &im = CallImpacts[i];
-        if (im.Len) inject[im.Object].push_back({im.Start + im.RenderLen, im.DeltaOff});
-        if (im.End > im.Start) excite[im.Object].push_back({im.Start, im.End});
+        if (im.Len) ++CallInjectPtr[im.Object + 1];
+        if (im.End > im.Start) ++CallExcitePtr[im.Object + 1];
     }
-    CallInjectFrame.clear(), CallInjectDelta.clear(), CallExciteBegin.clear(), CallExciteEnd.clear();
-    for (uint32_t o = 0; o < n_obj; ++o) {
-        std::stable_sort(inject[o].begin(), inject[o].end(), [](const auto &a, const auto &b) { return a.first < b.first; });
-        for (const auto &[frame, delta] : inject[o]) CallInjectFrame.push_back(frame), CallInjectDelta.push_back(delta);
-        CallInjectPtr[o + 1] = uint32_t(CallInjectFrame.size());
-        std::sort(excite[o].begin(), excite[o].end());
-        size_t first = CallExciteBegin.size();
-        for (const auto &[begin, end] : excite[o]) {
-            if (CallExciteBegin.size() > first && begin <= CallExciteEnd.back()) CallExciteEnd.back() = std::max(CallExciteEnd.back(), end);
-            else CallExciteBegin.push_back(begin), CallExciteEnd.push_back(end);
+    for (uint32_t o = 0; o < n_obj; ++o) CallInjectPtr[o + 1] += CallInjectPtr[o], CallExcitePtr[o + 1] += CallExcitePtr[o];
+    CallInjectFrame.resize(CallInjectPtr[n_obj]), CallInjectDelta.resize(CallInjectPtr[n_obj]);
+    std::vector<std::pair<uint32_t, uint32_t>> excite(CallExcitePtr[n_obj]);
+    {
+        std::vector<uint32_t> inject_at(CallInjectPtr.begin(), CallInjectPtr.end() - 1), excite_at(CallExcitePtr.begin(), CallExcitePtr.end() - 1);
+        for (uint32_t i = 0; i < n; ++i) {
+            const auto &im = CallImpacts[i];
+            if (im.Len) {
+                const uint32_t at = inject_at[im.Object]++;
+                CallInjectFrame[at] = im.Start + im.RenderLen, CallInjectDelta[at] = im.DeltaOff;
+            }
+            if (im.End > im.Start) excite[excite_at[im.Object]++] = {im.Start, im.End};
         }
-        CallExcitePtr[o + 1] = uint32_t(CallExciteBegin.size());
     }
+    CallExciteBegin.clear(), CallExciteEnd.clear();
+    std::vector<uint32_t> merged_ptr(n_obj + 1, 0);
+    for (uint32_t o = 0; o < n_obj; ++o) {
+        // Increments sorted by the frame they land on (pulse lengths differ, so start order is not landing order).
+        const uint32_t i0 = CallInjectPtr[o], i1 = CallInjectPtr[o + 1];
+        bool sorted = true;
+        for (uint32_t i = i0 + 1; i < i1 && sorted; ++i) sorted = CallInjectFrame[i - 1] <= CallInjectFrame[i];
+        if (!sorted) {
+            std::vector<std::pair<uint32_t, uint32_t>> tmp(i1 - i0);
+            for (uint32_t i = i0; i < i1; ++i) tmp[i - i0] = {CallInjectFrame[i], CallInjectDelta[i]};
+            std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+            for (uint32_t i = i0; i < i1; ++i) CallInjectFrame[i] = tmp[i - i0].first, CallInjectDelta[i] = tmp[i - i0].second;
+        }
+        // Merged intervals during which the object holds a live impact.
+        const auto e0 = excite.begin() + CallExcitePtr[o], e1 = excite.begin() + CallExcitePtr[o + 1];
+        if (!std::is_sorted(e0, e1)) std::sort(e0, e1);
+        const size_t first = CallExciteBegin.size();
+        for (auto it = e0; it != e1; ++it) {
+            if (CallExciteBegin.size() > first && it->first <= CallExciteEnd.back()) CallExciteEnd.back() = std::max(CallExciteEnd.back(), it->second);
+            else CallExciteBegin.push_back(it->first), CallExciteEnd.push_back(it->second);
+        }
+        merged_ptr[o + 1] = uint32_t(CallExciteBegin.size());
+    }
+    CallExcitePtr = merged_ptr;
     MixGain.resize(n_obj), EnergyScale.resize(n_obj);
     for (uint32_t o = 0; o < n_obj; ++o) {
         MixGain[o] = OutGain[o] * ListenerGain[o];

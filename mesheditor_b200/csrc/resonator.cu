@@ -176,7 +176,7 @@ __device__ __forceinline__ void PolarPower(const BankView &b, uint32_t mode0, ui
 }
 
 // Walk == false: the sample loop (K samples per step). Walk == true: the producer of the tensor-core form, which
-// advances one 128-frame time block per step and writes the block-start states as state stages (tensor_mix.cuh).
+// advances one kTmBlock-frame time block per step and writes the block-start states as state stages (tensor_mix.cuh).
 // Everything around the inner loop (RenderModal blocks, culling, increments, final state) is shared.
 template<int K, int MinBlocks, bool Walk>
 __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(const BankView b, const RenderPlan plan) {
@@ -198,11 +198,11 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
 
     Powers<K> p;
     Chunk w;
-    float2 jump_re[4], jump_im[4]; // Walk: c^128
+    float2 jump_re[4], jump_im[4]; // Walk: c^kTmBlock
 #pragma unroll
     for (int i = 0; i < 4; ++i) jump_re[i] = jump_im[i] = float2{0.f, 0.f};
     float gain = 1.f, out_scale = 0.f, energy_scale = 0.f;
-    uint32_t my_chunk = 0, obj_chunks = 0, obj_first_local = 0;
+    uint32_t my_chunk = 0, obj_chunks = 0, obj_first_local = 0, obj_tuned = 0;
     bool in_tuned = false, cull = false, live = true, ringing = true;
     uint32_t inj = 0, inj_hi = 0, exc = 0, exc_hi = 0;
 #pragma unroll
@@ -213,10 +213,10 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         MakePowers<K>(cre, cim, p);
         if constexpr (Walk) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { // c^128 by seven FP64 squarings of the float coefficient, rounded once
+            for (int i = 0; i < 4; ++i) { // c^kTmBlock by FP64 squarings of the float coefficient, rounded once
                 double rx = cre[i].x, ix = cim[i].x, ry = cre[i].y, iy = cim[i].y;
 #pragma unroll
-                for (int q = 0; q < 7; ++q) {
+                for (uint32_t q = 1; q < kTmBlock; q <<= 1) {
                     const double nrx = rx * rx - ix * ix, nry = ry * ry - iy * iy;
                     ix = 2.0 * rx * ix, iy = 2.0 * ry * iy;
                     rx = nrx, ry = nry;
@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         my_chunk = chunk - first;
         obj_chunks = b.ObjStride[object] / kLanes;
         obj_first_local = first - blockIdx.x * kBlockThreads; // only meaningful when the object fits this CTA
-        in_tuned = my_chunk < b.ObjTunedChunks[object];
+        obj_tuned = b.ObjTunedChunks[object];
+        in_tuned = my_chunk < obj_tuned;
         cull = b.ObjCull[object] != 0;
         const float mix = b.ObjMixGain[object];
         const bool muted = mix == 0.f;
@@ -402,10 +403,18 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
 #pragma unroll
             for (int i = 0; i < 4; ++i) energy += (w.Re[i].x * w.Re[i].x + w.Im[i].x * w.Im[i].x) + (w.Re[i].y * w.Re[i].y + w.Im[i].y * w.Im[i].y);
         }
+        const bool audible_chunk = rendered && energy * energy_scale >= kSilentEnergy;
         cull_energy[threadIdx.x] = energy;
-        cull_audible[threadIdx.x] = rendered && energy * energy_scale >= kSilentEnergy;
-        __syncthreads();
-        if (valid && cull) {
+        cull_audible[threadIdx.x] = audible_chunk;
+        // Common case: every tuned chunk of every culled object in the CTA is audible. Then each object's audible prefix
+        // is its whole tuned set and its total energy is above the threshold, so the per-object scan below is skipped.
+        const bool settled = !(valid && cull) || (in_tuned ? audible_chunk : obj_tuned != 0);
+        if (__syncthreads_and(settled)) {
+            if (valid && cull) {
+                ringing = true;
+                live = excited || in_tuned;
+            }
+        } else if (valid && cull) {
             float total = 0.f;
             int last = -1;
             for (uint32_t k = 0; k < obj_chunks; ++k) {
@@ -663,7 +672,7 @@ __global__ void ClickKernel(const DevImpact *__restrict__ impacts, const DevImpa
     }
 }
 
-// One thread per mode pair: rows j = 1..128 of the power stages, c^j by FP64 products of the float coefficient
+// One thread per mode pair: rows j = 1..kTmBlock of the power stages, c^j by FP64 products of the float coefficient
 // (the same arithmetic as MakePowers), each value split into its TF32 head and FP32 tail.
 __global__ void __launch_bounds__(128) PowerTableKernel(const BankView b, float *__restrict__ powers) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; // chunk * 4 + pair
@@ -672,7 +681,8 @@ __global__ void __launch_bounds__(128) PowerTableKernel(const BankView b, float 
     const uint32_t group = chunk / kTmGroupChunks, lc = chunk % kTmGroupChunks;
     const uint32_t mode = chunk * kLanes + pair * 2;
     const double ax = b.CoeffRe[mode], bx = b.CoeffIm[mode], ay = b.CoeffRe[mode + 1], by = b.CoeffIm[mode + 1];
-    float *stage = powers + (size_t(group) * kTmStagesPerGroup + (lc >> 1)) * TmPowerStageFloats() + size_t((lc & 1) * 4 + pair) * kTmBlock * 4;
+    constexpr uint32_t chunks_per_stage = kTmKChunk / 16;
+    float *stage = powers + (size_t(group) * kTmStagesPerGroup + lc / chunks_per_stage) * TmPowerStageFloats() + size_t((lc % chunks_per_stage) * 4 + pair) * kTmBlock * 4;
     double rx = ax, ix = bx, ry = ay, iy = by;
     for (uint32_t j = 0; j < kTmBlock; ++j) {
         const float4 v = {float(rx), float(ix), float(ry), float(iy)};

@@ -1,14 +1,16 @@
 // sm_100a tcgen05 kernel of the resonator bank's tensor-core form; see tensor_mix.cuh for the algebra.
 //
-// One CTA renders one time tile (BlocksPerTile x 128 frames) of one chunk group: a 128 x N accumulator in tensor
-// memory, fed stage by stage (32 reduction elements = 16 modes) through a ring of shared-memory buffers.
+// One CTA renders one time tile (BlocksPerTile x 256 frames) of a few chunk groups: two 128 x N accumulators (frames
+// 0-127 and 128-255 of every block) in tensor memory, fed stage by stage (16 reduction elements = 8 modes) through a
+// ring of shared-memory buffers.
 //   warp 0 (one lane): producer. Per stage a bulk copy (power stage, already a shared-memory image) and a 4-D TMA tile
-//                      copy (32 reduction elements x all time blocks x head/tail of the row-major states, 128-byte
+//                      copy (16 reduction elements x all time blocks x head/tail of the row-major states, 64-byte
 //                      swizzle), completion counted on the stage's "full" mbarrier.
-//   warp 1 (one lane): issues tcgen05.mma kind::tf32, three per 8-wide reduction step (head*head, head*tail,
-//                      tail*head), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
-//   warps 2-5:         epilogue. tcgen05.ld of the accumulator (lane = frame inside the block, column = block) and
-//                      coalesced stores of the group's partial mix row.
+//   warp 1 (one lane): issues tcgen05.mma kind::tf32, three per 8-wide reduction step and accumulator (head*head,
+//                      head*tail, tail*head), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
+//   warps 2-9:         epilogue, one warp per (TMEM lane quarter, block half). tcgen05.ld of the accumulator (lane =
+//                      frame inside the half block, column = block) folded into FP32 registers, then coalesced stores
+//                      of the partial mix row.
 #include "tensor_mix.cuh"
 
 #include "common.h"
@@ -19,7 +21,7 @@
 namespace me {
 namespace {
 
-constexpr uint32_t kThreads = 192;
+constexpr uint32_t kThreads = 320;
 constexpr uint32_t kPowerHalfBytes = kTmBlock * kTmKChunk * 4; // 16 KB
 constexpr uint32_t kSpinLimit = 1u << 24;
 
@@ -57,9 +59,9 @@ __device__ __forceinline__ void TensorCopy4(void *dst, const CUtensorMap *map, u
                  : "memory");
 }
 
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle: rows of 128 bytes (32 TF32), 8-row groups 1024 bytes apart.
+// Shared-memory matrix descriptor, K-major, 64-byte swizzle: rows of 64 bytes (16 TF32), 8-row groups 512 bytes apart.
 __device__ __forceinline__ uint64_t SwizzledDescriptor(uint32_t smem_addr) {
-    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1) << 16) | (uint64_t(512 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(4) << 61);
 }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): 8-row core matrices of 128
@@ -81,7 +83,14 @@ __device__ __forceinline__ void MmaTf32(uint32_t tmem_d, uint64_t a, uint64_t b,
 __device__ __forceinline__ void MmaCommit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemAddr(bar)) : "memory");
 }
-__device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void TmemLoad16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                   "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+[[maybe_unused]] __device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, "
         "%28, %29, %30, %31}, [%32];"
@@ -94,9 +103,9 @@ __device__ __forceinline__ void TmemLoad32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // Tensor-core accumulation rounds toward zero: n MMAs chained on one accumulator lose up to n * 2^-24 of its
 // magnitude, always in the same direction (measured: 1e-4 after the 1536 MMAs of a group). So a chain is cut after
-// kFoldStages stages (24 MMAs, <= 1.5e-6) and folded into FP32 registers by the epilogue warps with round-to-nearest
-// adds; two accumulators alternate so the fold of one overlaps the MMAs into the other.
-constexpr uint32_t kFoldStages = 2;
+// kFoldStages stages (24 MMAs per accumulator, <= 1.5e-6) and folded into FP32 registers by the epilogue warps with
+// round-to-nearest adds; two accumulator pairs alternate so the fold of one overlaps the MMAs into the other.
+constexpr uint32_t kFoldStages = 4;
 
 template<uint32_t N, uint32_t Stages>
 __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPlan plan, const __grid_constant__ CUtensorMap states_map) {
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
     constexpr uint32_t kStageBytes = kPowerBytes + kStateBytes;
     constexpr uint32_t kSteps = kTmKChunk / 8; // MMAs of K = 8 per stage and operand pair
     extern __shared__ __align__(1024) uint8_t stage_storage_raw[];
-    // The 128-byte swizzle is a function of the shared-memory address: the ring starts on a 1024-byte boundary.
+    // The swizzle is a function of the shared-memory address: the ring starts on a 1024-byte boundary.
     uint8_t *stage_storage = stage_storage_raw + ((1024u - (SmemAddr(stage_storage_raw) & 1023u)) & 1023u);
     __shared__ __align__(8) uint64_t full_bar[Stages], empty_bar[Stages], accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_slot;
@@ -120,11 +129,11 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < Stages; ++s) BarrierInit(&full_bar[s], 1), BarrierInit(&empty_bar[s], 1);
-        for (uint32_t b = 0; b < 2; ++b) BarrierInit(&accum_full[b], 1), BarrierInit(&accum_empty[b], 4);
+        for (uint32_t b = 0; b < 2; ++b) BarrierInit(&accum_full[b], 1), BarrierInit(&accum_empty[b], 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(&tmem_base_slot)), "r"(2 * N) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(SmemAddr(&tmem_base_slot)), "r"(4 * N) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -147,9 +156,10 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = InstructionDescriptor(kTmBlock, N);
-            // Power halves: the 16-byte K pieces are 2048 bytes apart and the 8-row groups 128 bytes.
-            constexpr uint32_t lbo_p = kTmBlock * 16, sbo = 128;
+            constexpr uint32_t idesc = InstructionDescriptor(128, N);
+            // Power halves: the 16-byte K pieces are 4096 bytes apart and the 8-row groups 128 bytes; frames 128-255
+            // of the block start 16 row groups further.
+            constexpr uint32_t lbo_p = kTmBlock * 16, sbo = 128, upper_rows = 16 * 128;
             for (uint32_t k = 0; k < n_stages; ++k) {
                 const uint32_t s = k % Stages, round = k / Stages;
                 const uint32_t fold = k / kFoldStages, buffer = fold & 1;
@@ -161,26 +171,30 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
                 BarrierWait(&full_bar[s], round & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t stage = SmemAddr(stage_storage + size_t(s) * kStageBytes);
-                const uint32_t tmem_d = tmem_base + buffer * N;
+                const uint32_t tmem_d = tmem_base + buffer * 2 * N;
 #pragma unroll
                 for (uint32_t kk = 0; kk < kSteps; ++kk) {
-                    const uint64_t p_head = MatrixDescriptor(stage + kStateBytes + kk * 2 * lbo_p, lbo_p, sbo);
-                    const uint64_t p_tail = MatrixDescriptor(stage + kStateBytes + kPowerHalfBytes + kk * 2 * lbo_p, lbo_p, sbo);
                     // Inside the swizzle atom a K step of 8 TF32 is 32 bytes further along the row.
                     const uint64_t w_head = SwizzledDescriptor(stage + kk * 32);
                     const uint64_t w_tail = SwizzledDescriptor(stage + kStateHalfBytes + kk * 32);
-                    MmaTf32(tmem_d, p_tail, w_head, idesc, !(opens && kk == 0));
-                    MmaTf32(tmem_d, p_head, w_tail, idesc, 1);
-                    MmaTf32(tmem_d, p_head, w_head, idesc, 1);
+#pragma unroll
+                    for (uint32_t half = 0; half < 2; ++half) {
+                        const uint64_t p_head = MatrixDescriptor(stage + kStateBytes + kk * 2 * lbo_p + half * upper_rows, lbo_p, sbo);
+                        const uint64_t p_tail = MatrixDescriptor(stage + kStateBytes + kPowerHalfBytes + kk * 2 * lbo_p + half * upper_rows, lbo_p, sbo);
+                        MmaTf32(tmem_d + half * N, p_tail, w_head, idesc, !(opens && kk == 0));
+                        MmaTf32(tmem_d + half * N, p_head, w_tail, idesc, 1);
+                        MmaTf32(tmem_d + half * N, p_head, w_head, idesc, 1);
+                    }
                 }
                 MmaCommit(&empty_bar[s]); // arrives when the MMAs above have read the stage
                 if (k % kFoldStages == kFoldStages - 1) MmaCommit(&accum_full[buffer]);
             }
         }
     } else {
-        // TMEM lanes are reachable from the warp whose index mod 4 matches the lane quarter.
-        const uint32_t quarter = warp & 3;
-        const uint32_t row = quarter * 32 + lane; // frame inside the time block
+        // TMEM lanes are reachable from the warp whose index mod 4 matches the lane quarter; warps 2-5 take frames
+        // 0-127 of every block, warps 6-9 frames 128-255.
+        const uint32_t quarter = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t row = half * 128 + quarter * 32 + lane; // frame inside the time block
         float acc[N];
 #pragma unroll
         for (uint32_t c = 0; c < N; ++c) acc[c] = 0.f;
@@ -190,11 +204,11 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
             BarrierWait(&accum_full[buffer], (fold >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (uint32_t c0 = 0; c0 < N; c0 += 32) {
-                uint32_t v[32];
-                TmemLoad32(tmem_base + ((quarter * 32) << 16) + buffer * N + c0, v);
+            for (uint32_t c0 = 0; c0 < N; c0 += 16) {
+                uint32_t v[16];
+                TmemLoad16(tmem_base + ((quarter * 32) << 16) + (buffer * 2 + half) * N + c0, v);
 #pragma unroll
-                for (uint32_t c = 0; c < 32; ++c) acc[c0 + c] += __uint_as_float(v[c]);
+                for (uint32_t c = 0; c < 16; ++c) acc[c0 + c] += __uint_as_float(v[c]);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -210,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * N) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(4 * N) : "memory");
 }
 
 PFN_cuTensorMapEncodeTiled EncodeTiled() {
@@ -232,7 +246,7 @@ void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
     const cuuint64_t dims[4] = {kTmGroupK, N, 2, cuuint64_t(plan.Tiles) * plan.Groups};
     const cuuint64_t strides[3] = {cuuint64_t(kTmGroupK) * 4, cuuint64_t(N) * kTmGroupK * 4, cuuint64_t(2) * N * kTmGroupK * 4};
     const cuuint32_t box[4] = {kTmKChunk, N, 2, 1}, unit[4] = {1, 1, 1, 1};
-    const CUresult r = EncodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(plan.States), dims, strides, box, unit, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    const CUresult r = EncodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(plan.States), dims, strides, box, unit, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) Fail(ME_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", int(r));
     ME_CUDA(cudaFuncSetAttribute(TensorMixKernel<N, Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); // per device, cheap
@@ -245,7 +259,7 @@ void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
 void LaunchTensorMixKernel(const TensorMixPlan &plan, cudaStream_t stream) {
     if (plan.Groups == 0 || plan.Tiles == 0) return;
     if (plan.GroupsPerRow == 0 || plan.Groups % plan.GroupsPerRow != 0) Fail(ME_BAD_ARG, "tensor mix: groups per row must divide the groups");
-    if (plan.BlocksPerTile == 128) Launch<128, 3>(plan, stream);
+    if (plan.BlocksPerTile == 128) Launch<128, 4>(plan, stream);
     else Fail(ME_BAD_ARG, "tensor mix: blocks per tile must be 128");
 }
 

@@ -1,11 +1,12 @@
 // Tensor-core form of the free-running resonator bank (tensor_mix.cu).
 //
-// Between excitations every mode is z[n] = c z[n-1], so the samples of one 128-frame time block are a linear map of the
-// state at the block's start:  y[b*128 + j] = sum_modes Im(c^(j+1) w_b) = sum_modes Re(c^(j+1)) Im w_b + Im(c^(j+1)) Re w_b.
-// Over many blocks that is a GEMM  Y[128 x blocks] = P[128 x 2*modes] * W[2*modes x blocks]  whose reduction runs over
+// Between excitations every mode is z[n] = c z[n-1], so the samples of one 256-frame time block are a linear map of the
+// state at the block's start:  y[b*256 + j] = sum_modes Im(c^(j+1) w_b) = sum_modes Re(c^(j+1)) Im w_b + Im(c^(j+1)) Re w_b.
+// Over many blocks that is a GEMM  Y[256 x blocks] = P[256 x 2*modes] * W[2*modes x blocks]  whose reduction runs over
 // the modes of every object in a chunk group: the mode sum AND the object mix of RenderModal (ModalAudio.cpp:125-128,
 // 553-555) happen in the tensor-core accumulator. P (powers of the coefficients) is fixed by the tuning; W (block-start
-// states) costs 4 FMAs per mode per 128 samples.  FP32 accuracy comes from the 3xTF32 split: both operands are stored
+// states) costs 4 FMAs and 16 bytes of HBM per mode per 256 samples: the block length trades the size of P (L2-resident)
+// against the HBM traffic of W, which is what bounds both kernels.  FP32 accuracy comes from the 3xTF32 split: both operands are stored
 // as a TF32 head and an FP32 tail, and head*head + head*tail + tail*head accumulate in FP32 (the dropped tail*tail
 // term is 2^-22 relative).
 #pragma once
@@ -16,21 +17,21 @@
 
 namespace me {
 
-constexpr uint32_t kTmBlock = 128;     // frames per time block: the M extent of one tcgen05.mma
-constexpr uint32_t kTmKChunk = 32;     // reduction elements per pipeline stage = 16 modes = two 8-mode chunks
+constexpr uint32_t kTmBlock = 256;     // frames per time block: two M = 128 tcgen05.mma halves
+constexpr uint32_t kTmKChunk = 16;     // reduction elements per pipeline stage = 8 modes = one chunk
 constexpr uint32_t kTmGroupChunks = 256; // chunk slots per reduction group (== kBlockThreads: one resonator CTA)
-constexpr uint32_t kTmStagesPerGroup = kTmGroupChunks * 8 * 2 / kTmKChunk; // 128
+constexpr uint32_t kTmStagesPerGroup = kTmGroupChunks * 8 * 2 / kTmKChunk; // 256
 
 // Power stages in HBM are exactly what a pipeline stage holds in shared memory (the canonical K-major, no-swizzle UMMA
 // layout), so one plain bulk copy fills them:
-//   element (row r, reduction index k) of a [128 x 32] half lives at byte (k/4)*2048 + (r/8)*128 + (r%8)*16 + (k%4)*4
+//   element (row r, reduction index k) of a [256 x 16] half lives at byte (k/4)*4096 + (r/8)*128 + (r%8)*16 + (k%4)*4
 // and a stage is [head half][tail half]. Reduction index 2*m holds Re(c^(j+1)) in P and Im w in W; 2*m+1 holds
 // Im(c^(j+1)) and Re w, m = mode inside the group (0..2047).
 // States are written by the walk kernel as plain row-major matrices, one row of the group's 4096 reduction elements
 // per time block, so a warp of chunk-threads stores 2 KB contiguous per step:
 //   States[tile][group][half (0 head, 1 tail)][time block][4096]
-// and a stage (32 reduction elements of all blocks, both halves) reaches shared memory by one 4-D TMA tile copy that
-// applies the 128-byte swizzle the UMMA descriptor expects.
+// and a stage (16 reduction elements of all blocks, both halves) reaches shared memory by one 4-D TMA tile copy that
+// applies the 64-byte swizzle the UMMA descriptor expects.
 __host__ __device__ constexpr size_t TmPowerStageFloats() { return size_t(2) * kTmBlock * kTmKChunk; }
 constexpr uint32_t kTmGroupK = kTmGroupChunks * 8 * 2; // 4096 reduction elements per group
 __host__ __device__ constexpr size_t TmStateTileFloats(uint32_t blocks_per_tile) { return size_t(2) * blocks_per_tile * kTmGroupK; }
@@ -41,7 +42,7 @@ struct TensorMixPlan {
     uint32_t Tiles;           // time tiles in the window
     uint32_t BlocksPerTile;   // 128 time blocks (the N extent)
     uint32_t Frames;          // valid frames of the window (the last tile may be ragged)
-    const float *Powers;      // [Groups][128 stages] power stages
+    const float *Powers;      // [Groups][256 stages] power stages
     const float *States;      // [Tiles][Groups][2][BlocksPerTile][4096]
     float *Partial;           // [Groups / GroupsPerRow][Frames] partial mixes
 };

@@ -1,6 +1,7 @@
 """The tcgen05 mix kernel (mesheditor_b200/csrc/tensor_mix.cu) against a float64 matrix product.
 
-out[group][tile*N*128 + n*128 + r] = sum_k P_group[r, k] * W_tile,group[n, k] over the group's 4096 reduction elements,
+out[row][tile*N*256 + n*256 + r] = sum_k P_group[r, k] * W_tile,group[n, k] over the 4096 reduction elements of each of the
+row's groups (r = frame inside the 256-frame time block, n = time block inside the tile),
 operands split into a TF32 head and an FP32 tail (3xTF32); powers in the shared-memory stage layout, states row-major. Tolerance: 5e-6 of the row scale (measured 2.1e-6, FP32-level; a plain TF32
 product would miss it by 1e-3).
 """
@@ -11,8 +12,9 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-STAGES = 128  # per group
-KC = 32
+STAGES = 256  # per group
+KC = 16
+BLOCK = 256  # frames per time block
 
 
 def split_tf32(x):
@@ -22,7 +24,7 @@ def split_tf32(x):
 
 
 def pack(mat):
-    """[rows, 4096] -> [128 stages][2 halves][rows*32] in the stage layout of tensor_mix.cuh."""
+    """[rows, 4096] -> [stages][2 halves][rows*KC] in the stage layout of tensor_mix.cuh."""
     rows = mat.shape[0]
     head, tail = split_tf32(mat)
     out = np.empty((STAGES, 2, rows * KC), np.float32)
@@ -42,11 +44,11 @@ def test_tensor_mix_matches_float64_product(n_blocks, groups, per_row, tiles, ra
 
     rng = np.random.default_rng(7)
     K = STAGES * KC
-    P = rng.standard_normal((groups, 128, K)).astype(np.float32) * np.exp(rng.uniform(-6, 0, (groups, 1, K))).astype(np.float32)
+    P = rng.standard_normal((groups, BLOCK, K)).astype(np.float32) * np.exp(rng.uniform(-6, 0, (groups, 1, K))).astype(np.float32)
     W = rng.standard_normal((tiles, groups, n_blocks, K)).astype(np.float32)
     powers = np.stack([pack(P[g]) for g in range(groups)])
     states = np.ascontiguousarray(np.stack(split_tf32(W), axis=2))  # [tiles][groups][head, tail][blocks][4096], row-major
-    frames = tiles * n_blocks * 128 - ragged
+    frames = tiles * n_blocks * BLOCK - ragged
     rows = groups // per_row
     out = np.full((rows, frames), np.nan, np.float32)
     ms = C.c_float(0)
