@@ -301,6 +301,73 @@ MeStatus me_measure_fp64_rate(int device, int mode, int iters, double *flops_per
  * (instructions), probing whether both FMA pipes run concurrently; 4 scalar FADD. */
 MeStatus me_measure_fp32_fma_rate(int device, int packed, int iters, double *fma_per_second);
 
+/* ------------------------------------------------------------------------------------------------
+ * Strike front-end: contact dynamics -> the ModalEvent a strike enqueues.
+ * Reference: src/audio/ContactModel.{h,cpp}, RecoilClickFilter (src/audio/ModalAudio.h:92-99) and the arithmetic of
+ * TriggerModalStrike (src/audio/AudioSystem.cpp:400-465). Host-only, needs no CUDA device.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Striker (ContactModel.h:36-40): a capsule mallet; defaults steel, 0.01 m tip radius, 0.19 m long. */
+typedef struct MeStriker {
+    MeMaterial material;
+    float tip_radius, length;
+} MeStriker;
+/* Impactor (ContactModel.h:44-48): the striking side of a Hertz contact. inv_mass 0 = immovable. */
+typedef struct MeImpactor {
+    MeMaterial material;
+    double curvature; /* 1/m */
+    double inv_mass;  /* 1/kg */
+} MeImpactor;
+/* ContactDynamics (ContactModel.h:28-32): mass, inverse inertia about the centre of mass (glm::mat3, column-major) and
+ * the contact arm of every excitable vertex (borrowed for the call). */
+typedef struct MeContactDynamics {
+    double mass;
+    float inverse_inertia[9];
+    const float *contact_arm_xyz;
+    uint32_t arm_count;
+} MeContactDynamics;
+
+double me_striker_mass(const MeStriker *);                              /* StrikerMass, ContactModel.cpp:10-13 */
+MeStatus me_striker_impactor(const MeStriker *, MeImpactor *out);       /* StrikerImpactor, :15 */
+MeStatus me_inverse_inertia_tensor(const MeMassProperties *, float out[9]); /* InverseInertiaTensor, :17-24 */
+/* ReducedContactMass (:27-38); 0 when the index is out of range or the object has no mass. */
+double me_reduced_contact_mass(const MeContactDynamics *, uint32_t excitable_index, const float impact_direction[3], const MeImpactor *);
+/* EstimateContactTime (:76-114): seconds, clamped to [2e-5, 5e-2]; MinContactTime on degenerate input. */
+double me_estimate_contact_time(const MeContactDynamics *, uint32_t excitable_index, const float impact_direction[3], double contact_speed, const MeMaterial *object_material,
+                                double object_curvature, double nominal_area, const MeImpactor *, double scale_ratio, double combined_roughness);
+/* Hertz contact constants (ContactModel.cpp:40-66). Arguments by constant:
+ *   INV_EFFECTIVE_MODULUS(a, b); COMBINED_CURVATURE(x = k1, y = k2); STIFFNESS(x = 1/E*, y = 1/R*);
+ *   PATCH_RADIUS(x = N, y = 1/E*, z = 1/R*); STATIC_PENETRATION(x = N, y = k); SATURATION_PENETRATION(x = 1/R*, y = A0);
+ *   PUNCH_STIFFNESS(x = 1/E*, y = A0). */
+typedef enum MeContactConstant {
+    ME_CONTACT_INV_EFFECTIVE_MODULUS = 0, ME_CONTACT_COMBINED_CURVATURE = 1, ME_CONTACT_STIFFNESS = 2, ME_CONTACT_PATCH_RADIUS = 3,
+    ME_CONTACT_STATIC_PENETRATION = 4, ME_CONTACT_SATURATION_PENETRATION = 5, ME_CONTACT_PUNCH_STIFFNESS = 6
+} MeContactConstant;
+double me_contact_constant(MeContactConstant which, const MeMaterial *a, const MeMaterial *b, double x, double y, double z);
+/* RecoilClickFilter (ModalAudio.h:92-99): {B0, A1, A2}; zeros when radius or mass is not positive. */
+void me_recoil_click_filter(double radius, double volume, double mass, double sample_rate, float b0_a1_a2[3]);
+
+/* One strike as TriggerModalStrike sees it once the scene lookups are done (AudioSystem.cpp:400-465). */
+typedef struct MeStrike {
+    uint32_t object;              /* bank slot (FindModalObject) */
+    uint32_t excitable_index;     /* excitation position; also where a mallet's contact time is evaluated */
+    float force, contact_speed;
+    float direction[3];           /* node-local; normalised here when is_collision (physics->Direction), else taken as is */
+    int32_t is_collision;         /* PhysicsStrike present: force is the true contact impulse */
+    uint32_t resultant_index;     /* collision: sample point nearest the manifold's load-weighted centre */
+    const MeContactDynamics *dynamics; /* NULL (or elastic NULL): 1e-4 s contact, no click */
+    const MeMaterial *elastic;    /* material of the struck surface */
+    MeImpactor impactor;          /* StrikerImpactor(...) for a mallet, the colliding body's for a collision */
+    double curvature;             /* struck surface's contribution to 1/R* where the strike lands */
+    double nominal_area;          /* collision only: area the two faces share, m^2 */
+    double scale_ratio;           /* UniformScaleRatio */
+    double roughness;             /* combined rms asperity height, m */
+    double displaced_volume;      /* DisplacedVolume (:247-254); 0 = none, the click corner then uses radiant_radius */
+    float radiant_radius;         /* bank.RadiantRadius[slot] */
+    float sample_rate;            /* bank.SampleRate */
+} MeStrike;
+MeStatus me_make_strike_event(const MeStrike *, MeModalEvent *out);
+
 /* Unit-test entry of the tensor-core mix (tensor_mix.cuh): out[row][frame] = sum over the 4096 reduction elements of
  * each of the row's groups_per_row consecutive groups of power * state, operands given as host images of the stage layout documented in tensor_mix.cuh
  * (powers: groups*256 stages of 2*256*16 floats, stage layout; states: [tiles][groups][head,tail][blocks_per_tile][4096] floats).

@@ -41,6 +41,24 @@ class MeMaterial(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("density", "young_modulus", "poisson_ratio", "alpha", "beta")]
 
 
+class MeStriker(C.Structure):
+    _fields_ = [("material", MeMaterial), ("tip_radius", C.c_float), ("length", C.c_float)]
+
+
+class MeImpactor(C.Structure):
+    _fields_ = [("material", MeMaterial), ("curvature", C.c_double), ("inv_mass", C.c_double)]
+
+
+class MeContactDynamics(C.Structure):
+    _fields_ = [("mass", C.c_double), ("inverse_inertia", C.c_float * 9), ("contact_arm_xyz", C.c_void_p), ("arm_count", C.c_uint32)]
+
+
+class MeStrike(C.Structure):
+    _fields_ = [("object", C.c_uint32), ("excitable_index", C.c_uint32), ("force", C.c_float), ("contact_speed", C.c_float), ("direction", C.c_float * 3), ("is_collision", C.c_int32),
+                ("resultant_index", C.c_uint32), ("dynamics", C.POINTER(MeContactDynamics)), ("elastic", C.POINTER(MeMaterial)), ("impactor", MeImpactor), ("curvature", C.c_double),
+                ("nominal_area", C.c_double), ("scale_ratio", C.c_double), ("roughness", C.c_double), ("displaced_volume", C.c_double), ("radiant_radius", C.c_float), ("sample_rate", C.c_float)]
+
+
 class MeSolverConfig(C.Structure):
     _fields_ = [("min_mode_freq", C.c_float), ("max_mode_freq", C.c_float), ("num_modes", C.c_uint32), ("num_fem_modes", C.c_uint32), ("tolerance", C.c_double),
                 ("warm_tolerance", C.c_double), ("max_restarts", C.c_uint32), ("has_fundamental_freq", C.c_int32), ("fundamental_freq", C.c_float),
@@ -137,10 +155,26 @@ def lib():
         "me_factor_info": [vp, C.POINTER(MeFactorInfo)],
         "me_symbolic_analyse": [u32, vp, vp, vp, vp, C.POINTER(MeSymbolicInfo)],
     }
+    sig.update({
+        "me_striker_impactor": [C.POINTER(MeStriker), C.POINTER(MeImpactor)],
+        "me_inverse_inertia_tensor": [C.POINTER(MeMassProperties), vp],
+        "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
+    })
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
         fn.restype = i32
+    f64 = C.c_double
+    for name, args in {
+        "me_striker_mass": [C.POINTER(MeStriker)],
+        "me_reduced_contact_mass": [C.POINTER(MeContactDynamics), u32, vp, C.POINTER(MeImpactor)],
+        "me_estimate_contact_time": [C.POINTER(MeContactDynamics), u32, vp, f64, C.POINTER(MeMaterial), f64, f64, C.POINTER(MeImpactor), f64, f64],
+        "me_contact_constant": [i32, C.POINTER(MeMaterial), C.POINTER(MeMaterial), f64, f64, f64],
+    }.items():
+        getattr(L, name).argtypes = args
+        getattr(L, name).restype = f64
+    L.me_recoil_click_filter.argtypes = [f64, f64, f64, f64, vp]
+    L.me_recoil_click_filter.restype = None
     for name in ("me_bank_free", "me_modal_result_free", "me_fem_free", "me_factor_free"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = None

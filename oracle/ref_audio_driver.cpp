@@ -7,6 +7,7 @@
 // It mirrors the harness the reference's own tests use (tests/ModalBench.h:47-81 `ModalScene`):
 // AddModalObject + TuneModalObject + OutGain, InstallModalBank, one discard block, then
 // EnqueueModalEvent / RenderModal.
+#include "audio/ContactModel.h"
 #include "audio/ModalAudio.h"
 #include "audio/ModalModes.h"
 
@@ -139,5 +140,60 @@ void ref_click_filter(double radius, double volume, double mass, double sample_r
     b0_a1_a2[0] = f.B0;
     b0_a1_a2[1] = f.A1;
     b0_a1_a2[2] = f.A2;
+}
+
+// ---- Strike front-end (src/audio/ContactModel.{h,cpp}): the unmodified reference functions behind plain arguments. ----
+// material: {Density, YoungModulus, PoissonRatio, Alpha, Beta}; mass_props: {Mass} + com[3], inertia_diagonal[3], quat wxyz.
+static AcousticMaterialProperties RefMaterial(const double *m) { return {m[0], m[1], m[2], m[3], m[4]}; }
+static Striker RefStriker(const double *material, float tip_radius, float length) {
+    Striker s;
+    s.Material.Properties = RefMaterial(material);
+    s.TipRadius = tip_radius;
+    s.Length = length;
+    return s;
+}
+static ContactDynamics RefDynamics(double mass, const float *inverse_inertia, const float *arms, uint32_t n_arms) {
+    ContactDynamics d;
+    d.Mass = mass;
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) d.InverseInertia[c][r] = inverse_inertia[3 * c + r];
+    for (uint32_t i = 0; i < n_arms; ++i) d.ContactArm.push_back(vec3{arms[3 * i], arms[3 * i + 1], arms[3 * i + 2]});
+    return d;
+}
+double ref_striker_mass(const double *material, float tip_radius, float length) { return StrikerMass(RefStriker(material, tip_radius, length)); }
+void ref_striker_impactor(const double *material, float tip_radius, float length, double *curvature_invmass) {
+    const auto imp = StrikerImpactor(RefStriker(material, tip_radius, length));
+    curvature_invmass[0] = imp.Curvature, curvature_invmass[1] = imp.InvMass;
+}
+void ref_inverse_inertia(double mass, const float *inertia_diagonal, const float *quat_wxyz, float *out9) {
+    MassProperties mp;
+    mp.Mass = mass;
+    mp.InertiaDiagonal = vec3{inertia_diagonal[0], inertia_diagonal[1], inertia_diagonal[2]};
+    mp.InertiaOrientation = glm::quat{quat_wxyz[0], quat_wxyz[1], quat_wxyz[2], quat_wxyz[3]};
+    const glm::mat3 m = InverseInertiaTensor(mp);
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) out9[3 * c + r] = m[c][r];
+}
+double ref_reduced_contact_mass(double mass, const float *inverse_inertia, const float *arms, uint32_t n_arms, uint32_t i, const float *dir, const double *imp_material, double imp_curvature, double imp_inv_mass) {
+    const Impactor imp{RefMaterial(imp_material), imp_curvature, imp_inv_mass};
+    return ReducedContactMass(RefDynamics(mass, inverse_inertia, arms, n_arms), i, vec3{dir[0], dir[1], dir[2]}, imp);
+}
+double ref_estimate_contact_time(double mass, const float *inverse_inertia, const float *arms, uint32_t n_arms, uint32_t i, const float *dir, double contact_speed, const double *object_material,
+                                 double object_curvature, double nominal_area, const double *imp_material, double imp_curvature, double imp_inv_mass, double scale_ratio, double combined_roughness) {
+    const Impactor imp{RefMaterial(imp_material), imp_curvature, imp_inv_mass};
+    return EstimateContactTime(RefDynamics(mass, inverse_inertia, arms, n_arms), i, vec3{dir[0], dir[1], dir[2]}, contact_speed, RefMaterial(object_material), object_curvature, nominal_area, imp, scale_ratio,
+                               combined_roughness);
+}
+// Hertz constants (ContactModel.cpp:40-66): which = 0 InvEffectiveModulus(a,b as materials), else scalar helpers.
+double ref_inv_effective_modulus(const double *a, const double *b) { return InvEffectiveModulus(RefMaterial(a), RefMaterial(b)); }
+double ref_contact_scalar(int which, double x, double y, double z) {
+    switch (which) {
+        case 0: return CombinedCurvature(x, y);
+        case 1: return ContactStiffness(x, y);
+        case 2: return ContactPatchRadius(x, y, z);
+        case 3: return StaticPenetration(x, y);
+        case 4: return SaturationPenetration(x, y);
+        default: return PunchStiffness(x, y);
+    }
 }
 }
