@@ -424,6 +424,48 @@ __global__ void __launch_bounds__(kThreads) SpmvMassKernel(const uint32_t *__res
     if (live && sub < 3) y[size_t(3) * row + sub] = sub == 0 ? a0 : sub == 1 ? a1 : a2;
 }
 
+// Y = M X for a column-major panel of W right-hand sides: the matrix (12 bytes per stored scalar) is read once for all
+// W columns instead of once per column.
+template<int W>
+__global__ void __launch_bounds__(kThreads) SpmvMassPanelKernel(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, const double *__restrict__ val, const double *__restrict__ x,
+                                                                double *__restrict__ y, uint32_t n_rows, size_t ld) {
+    const uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x, row = gid >> 3, sub = gid & 7;
+    const bool live = row < n_rows;
+    double a[W][3];
+#pragma unroll
+    for (int w = 0; w < W; ++w) a[w][0] = a[w][1] = a[w][2] = 0;
+    if (live) {
+        const uint32_t end = row_ptr[row + 1];
+        for (uint32_t j = row_ptr[row] + sub; j < end; j += 8) {
+            const double m = val[j];
+            const double *xc = x + size_t(3) * col[j];
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                a[w][0] += m * xc[w * ld];
+                a[w][1] += m * xc[w * ld + 1];
+                a[w][2] += m * xc[w * ld + 2];
+            }
+        }
+    }
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a[w][0] += __shfl_xor_sync(0xffffffffu, a[w][0], o);
+            a[w][1] += __shfl_xor_sync(0xffffffffu, a[w][1], o);
+            a[w][2] += __shfl_xor_sync(0xffffffffu, a[w][2], o);
+        }
+    // Lane `sub` writes column `sub` (three consecutive doubles): with W = 8 every lane of the row group stores.
+    if (live) {
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+            if (int(sub) == w) {
+                double *out = y + w * ld + size_t(3) * row;
+                out[0] = a[w][0], out[1] = a[w][1], out[2] = a[w][2];
+            }
+    }
+}
+
 // Scalar lower-triangular CSC exactly as Eigen lays it out after setFromTriplets (mesh2modes.cpp:322-325).
 __global__ void ExportCscKernel(int which, const uint32_t *__restrict__ blk_row, const uint32_t *__restrict__ blk_col, const uint32_t *__restrict__ blk_col_ptr, const double *__restrict__ kblk,
                                 const double *__restrict__ mblk, uint32_t n_blocks, uint64_t *__restrict__ colptr, uint32_t *__restrict__ rowidx, double *__restrict__ values) {
@@ -715,6 +757,15 @@ void FemSystem::SpmvK(const double *x, double *y) {
 void FemSystem::SpmvM(const double *x, double *y) {
     SpmvMassKernel<<<Blocks(uint64_t(NodeCount) * 8), kThreads, 0, Stream>>>(FullRowPtr.Ptr, FullCol.Ptr, MFull.Ptr, x, y, NodeCount);
     ++KernelLaunches;
+}
+void FemSystem::SpmvMPanel(const double *x, double *y, uint32_t width) {
+    const uint32_t blocks = Blocks(uint64_t(NodeCount) * 8);
+    uint32_t j = 0;
+    for (; j + 8 <= width; j += 8, ++KernelLaunches)
+        SpmvMassPanelKernel<8><<<blocks, kThreads, 0, Stream>>>(FullRowPtr.Ptr, FullCol.Ptr, MFull.Ptr, x + size_t(j) * N, y + size_t(j) * N, NodeCount, N);
+    for (; j + 4 <= width; j += 4, ++KernelLaunches)
+        SpmvMassPanelKernel<4><<<blocks, kThreads, 0, Stream>>>(FullRowPtr.Ptr, FullCol.Ptr, MFull.Ptr, x + size_t(j) * N, y + size_t(j) * N, NodeCount, N);
+    for (; j < width; ++j) SpmvM(x + size_t(j) * N, y + size_t(j) * N);
 }
 
 void FemSystem::ExportCsc(int which, uint64_t *colptr, uint32_t *rowidx, double *values) {

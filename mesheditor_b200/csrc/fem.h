@@ -46,6 +46,8 @@ public:
     // y = K x / y = M x over N = 3*NodeCount scalars (device pointers, on Stream).
     void SpmvK(const double *x, double *y);
     void SpmvM(const double *x, double *y);
+    // Y = M X for `width` column-major right-hand sides (leading dimension N): one pass over M per 8 columns.
+    void SpmvMPanel(const double *x, double *y, uint32_t width);
 
     // Host copies for parity checks and for the host-side symbolic analysis.
     uint64_t ScalarNonZerosK() const { return uint64_t(9) * NumBlocks - uint64_t(3) * NodeCount; }

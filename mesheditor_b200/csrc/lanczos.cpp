@@ -444,7 +444,7 @@ void ShiftInvertLanczos::OpPanel(const double *x, double *y, uint32_t width) {
     }
     Tmp.Reserve(n * width);
     ME_CUDA(cudaEventRecord(OpEvents[2 * OpCalls], s));
-    for (uint32_t j = 0; j < width; ++j) Fem.SpmvM(x + size_t(j) * n, Tmp.Ptr + size_t(j) * n);
+    Fem.SpmvMPanel(x, Tmp.Ptr, width);
     Factor.Solve(Tmp.Ptr, y, width);
     ME_CUDA(cudaEventRecord(OpEvents[2 * OpCalls + 1], s));
     ++OpCalls;
@@ -471,7 +471,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
     std::vector<double> T(size_t(tcap) * tcap, 0.0), h1(size_t(tcap) * b), h2(size_t(tcap) * b), g(size_t(b) * b), small(size_t(b) * b);
     auto Tm = [&](uint32_t r, uint32_t c) -> double & { return T[size_t(r) * tcap + c]; };
     auto mass_product = [&](const double *x, double *y) {
-        for (uint32_t j = 0; j < b; ++j) Fem.SpmvM(x + size_t(j) * n, y + size_t(j) * n);
+        Fem.SpmvMPanel(x, y, b);
     };
     // One Cholesky-QR pass in the M inner product: dst = src * L^-T with src^T M src = L L^T. r (row-major b x b)
     // receives L^T. False when the block has lost rank.

@@ -504,21 +504,25 @@ __global__ void __launch_bounds__(kPulseWarps * 32) PulseKernel(const BankView b
     }
     float *rows = &transposed[warp][0][0];
     const float *force = plan.Force + im.ForceOff;
+    // v <- c v + f g on mode pairs (packed FFMA2): three packed operations per component pair and sample.
+    float2 ncim[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ncim[i] = {-cim[i].x, -cim[i].y};
+    const float2 scale2 = {out_scale, out_scale};
     for (uint32_t tile = 0; tile < im.RenderLen; tile += kTile) {
         const uint32_t nv = min(kTile, im.RenderLen - tile);
         for (uint32_t s = 0; s < nv; ++s) {
             const float f = tile + s < im.Len ? __ldg(force + tile + s) : 0.f; // past the pulse: free ringing up to the injection frame
-            float sum = 0.f;
+            const float2 f2 = {f, f};
+            float2 sum = {0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float rx = fmaf(-v.Im[i].x, cim[i].x, fmaf(v.Re[i].x, cre[i].x, f * g.Re[i].x));
-                const float ry = fmaf(-v.Im[i].y, cim[i].y, fmaf(v.Re[i].y, cre[i].y, f * g.Re[i].y));
-                v.Im[i].x = fmaf(v.Re[i].x, cim[i].x, fmaf(v.Im[i].x, cre[i].x, f * g.Im[i].x));
-                v.Im[i].y = fmaf(v.Re[i].y, cim[i].y, fmaf(v.Im[i].y, cre[i].y, f * g.Im[i].y));
-                v.Re[i].x = rx, v.Re[i].y = ry;
-                sum += v.Im[i].x + v.Im[i].y;
+                const float2 re = Fma2(f2, g.Re[i], Fma2(v.Re[i], cre[i], Mul2(v.Im[i], ncim[i])));
+                v.Im[i] = Fma2(f2, g.Im[i], Fma2(v.Re[i], cim[i], Mul2(v.Im[i], cre[i])));
+                v.Re[i] = re;
+                sum = Add2(sum, v.Im[i]);
             }
-            reinterpret_cast<float2 *>(rows)[s * (kRowPad / 2) + lane] = float2{sum * out_scale, 0.f};
+            reinterpret_cast<float2 *>(rows)[s * (kRowPad / 2) + lane] = Mul2(sum, scale2);
         }
         __syncwarp();
         if (lane < nv) plan.Rows[job.RowOff + tile + lane] = SumRow(rows, lane);

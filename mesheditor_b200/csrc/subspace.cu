@@ -81,7 +81,7 @@ SubspaceOutcome SubspaceIteration::Compute(uint32_t nev, uint32_t p, double tol,
     const uint32_t launches0 = Fem.KernelLaunches, f_launches0 = Factor.Stats.KernelLaunches;
     auto col = [&](double *base, uint32_t j) { return base + size_t(j) * n; };
     auto mass_product = [&](const double *x, double *y, uint32_t cols) {
-        for (uint32_t j = 0; j < cols; ++j) Fem.SpmvM(x + size_t(j) * n, y + size_t(j) * n);
+        Fem.SpmvMPanel(x, y, cols);
     };
 
     DeviceBuffer<double> MX, Xbar, MXbar, XL, MXL, DKr, DMr, DC, DQ;

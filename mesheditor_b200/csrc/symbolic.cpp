@@ -12,11 +12,29 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <numeric>
+#include <thread>
 
 namespace me {
 namespace {
+// Runs body(begin, end, worker) over [0, count) split into contiguous chunks on up to 16 host threads.
+template<typename Body>
+void ParallelChunks(size_t count, size_t min_per_thread, Body &&body) {
+    const size_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    const size_t workers = std::max<size_t>(1, std::min(hw, count / std::max<size_t>(1, min_per_thread)));
+    if (workers <= 1) {
+        body(size_t(0), count, size_t(0));
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (size_t w = 0; w < workers; ++w) pool.emplace_back([&, w] { body(count * w / workers, count * (w + 1) / workers, w); });
+    for (auto &t : pool) t.join();
+}
+
 double Now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct Dissector {
@@ -153,44 +171,8 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
     std::vector<std::vector<uint32_t>> children(ns);
     for (uint32_t s = 0; s < ns; ++s)
         if (sym.Parent[s] < ns) children[sym.Parent[s]].push_back(s);
-    std::vector<uint32_t> mark(n, UINT32_MAX);
-    sym.RowPtr.assign(size_t(ns) + 1, 0);
-    {
-        for (uint32_t s = 0; s < ns; ++s) {
-            const uint32_t first = sym.SuperFirst[s], last = sym.SuperFirst[s + 1];
-            std::vector<uint32_t> r;
-            for (uint32_t v = first; v < last; ++v) {
-                const uint32_t old = sym.Perm[v];
-                for (uint32_t j = rowptr[old]; j < rowptr[old + 1]; ++j) {
-                    const uint32_t u = sym.InvPerm[col[j]];
-                    if (u >= last && mark[u] != s) {
-                        mark[u] = s;
-                        r.push_back(u);
-                    }
-                }
-            }
-            for (uint32_t c : children[s])
-                for (uint64_t j = sym.RowPtr[c]; j < sym.RowPtr[c + 1]; ++j) {
-                    const uint32_t u = sym.Rows[j];
-                    if (u >= last && mark[u] != s) {
-                        mark[u] = s;
-                        r.push_back(u);
-                    }
-                }
-            // A panel of a chain is coupled to the rest of its separator: the separator is a clique after elimination.
-            for (uint32_t e = s + 1; e < ns && chain[e] == chain[s]; ++e)
-                for (uint32_t u = sym.SuperFirst[e]; u < sym.SuperFirst[e + 1]; ++u)
-                    if (mark[u] != s) {
-                        mark[u] = s;
-                        r.push_back(u);
-                    }
-            std::sort(r.begin(), r.end());
-            sym.Rows.insert(sym.Rows.end(), r.begin(), r.end());
-            sym.RowPtr[s + 1] = sym.Rows.size();
-        }
-    }
-
-    // Levels (height above the leaves), panel offsets, segments, work lists.
+    // Levels (height above the leaves) first: the supernodes of one level only read the structures of lower levels, so
+    // a level is processed by several host threads at once, each with its own marker array.
     sym.Level.assign(ns, 0);
     for (uint32_t s = 0; s < ns; ++s)
         if (sym.Parent[s] < ns) sym.Level[sym.Parent[s]] = std::max(sym.Level[sym.Parent[s]], sym.Level[s] + 1);
@@ -203,6 +185,92 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
         std::vector<uint32_t> at(sym.LevelPtr.begin(), sym.LevelPtr.end() - 1);
         for (uint32_t s = 0; s < ns; ++s) sym.LevelOrder[at[sym.Level[s]]++] = s;
     }
+    std::vector<std::vector<uint32_t>> rows_of(ns);
+    {
+        std::vector<std::vector<uint32_t>> marks(16);
+        const auto structure = [&](uint32_t s, std::vector<uint32_t> &mark) {
+            const uint32_t first = sym.SuperFirst[s], last = sym.SuperFirst[s + 1];
+            std::vector<uint32_t> &r = rows_of[s];
+            for (uint32_t v = first; v < last; ++v) {
+                const uint32_t old = sym.Perm[v];
+                for (uint32_t j = rowptr[old]; j < rowptr[old + 1]; ++j) {
+                    const uint32_t u = sym.InvPerm[col[j]];
+                    if (u >= last && mark[u] != s) {
+                        mark[u] = s;
+                        r.push_back(u);
+                    }
+                }
+            }
+            for (uint32_t c : children[s])
+                for (const uint32_t u : rows_of[c])
+                    if (u >= last && mark[u] != s) {
+                        mark[u] = s;
+                        r.push_back(u);
+                    }
+            // A panel of a chain is coupled to the rest of its separator: the separator is a clique after elimination.
+            for (uint32_t e = s + 1; e < ns && chain[e] == chain[s]; ++e)
+                for (uint32_t u = sym.SuperFirst[e]; u < sym.SuperFirst[e + 1]; ++u)
+                    if (mark[u] != s) {
+                        mark[u] = s;
+                        r.push_back(u);
+                    }
+            std::sort(r.begin(), r.end());
+        };
+        // Supernode ids are in post-order, so a subtree is a contiguous id range processed in ascending order. The tree is
+        // cut below its top separators into a few dozen subtrees that host threads take from a shared counter; the top
+        // supernodes follow sequentially.
+        std::vector<uint32_t> subtree(ns, 1);
+        for (uint32_t s = 0; s < ns; ++s)
+            if (sym.Parent[s] < ns) subtree[sym.Parent[s]] += subtree[s];
+        std::vector<uint32_t> cut, top;
+        for (uint32_t s = 0; s < ns; ++s)
+            if (sym.Parent[s] >= ns) cut.push_back(s);
+        while (cut.size() < 48) {
+            size_t big = cut.size();
+            for (size_t i = 0; i < cut.size(); ++i)
+                if (subtree[cut[i]] > 128 && !children[cut[i]].empty() && (big == cut.size() || subtree[cut[i]] > subtree[cut[big]])) big = i;
+            if (big == cut.size()) break;
+            const uint32_t root = cut[big];
+            cut.erase(cut.begin() + big);
+            top.push_back(root);
+            cut.insert(cut.end(), children[root].begin(), children[root].end());
+        }
+        std::sort(cut.begin(), cut.end(), [&](uint32_t a, uint32_t b) { return subtree[a] > subtree[b]; });
+        std::sort(top.begin(), top.end());
+        std::atomic<size_t> next{0};
+        const size_t workers = std::max<size_t>(1, std::min<size_t>({16, std::thread::hardware_concurrency(), cut.size()}));
+        const auto work = [&](size_t worker) {
+            std::vector<uint32_t> &mark = marks[worker];
+            mark.assign(n, UINT32_MAX);
+            for (size_t i = next++; i < cut.size(); i = next++)
+                for (uint32_t s = cut[i] + 1 - subtree[cut[i]]; s <= cut[i]; ++s) structure(s, mark);
+        };
+        if (workers <= 1 || ns < 512) {
+            work(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (size_t w = 0; w < workers; ++w) pool.emplace_back(work, w);
+            for (auto &t : pool) t.join();
+        }
+        if (marks[0].empty()) marks[0].assign(n, UINT32_MAX);
+        for (const uint32_t s : top) structure(s, marks[0]);
+    }
+    sym.RowPtr.assign(size_t(ns) + 1, 0);
+    for (uint32_t s = 0; s < ns; ++s) sym.RowPtr[s + 1] = sym.RowPtr[s] + rows_of[s].size();
+    sym.Rows.resize(sym.RowPtr[ns]);
+    ParallelChunks(ns, 256, [&](size_t a, size_t b, size_t) {
+        for (size_t s = a; s < b; ++s) std::copy(rows_of[s].begin(), rows_of[s].end(), sym.Rows.begin() + sym.RowPtr[s]);
+    });
+    rows_of.clear();
+
+    const bool timing = std::getenv("ME_SYMBOLIC_TIMING") != nullptr;
+    double tm = Now();
+    const auto lap = [&](const char *what) {
+        if (timing) fprintf(stderr, "[me] symbolic %-12s %.1f ms\n", what, 1e3 * (Now() - tm));
+        tm = Now();
+    };
+    if (timing) fprintf(stderr, "[me] symbolic %-12s %.1f ms\n", "rows", 1e3 * (tm - t1));
+    // Panel offsets, segments, work lists.
     sym.PanelOffset.assign(size_t(ns) + 1, 0);
     sym.InvOffset.assign(size_t(ns) + 1, 0);
     sym.SegPtr.assign(size_t(ns) + 1, 0);
@@ -226,28 +294,50 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
         sym.SegPtr[s + 1] = sym.SegTarget.size();
     }
     sym.FactorNonZeros = sym.PanelOffset[ns];
+    lap("segments");
 
+    // Tile lists in (level, order inside the level) sequence: count per supernode, prefix, then fill on several threads.
     sym.PanelTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
     sym.UpdateTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
-    for (uint32_t l = 0; l < sym.NumLevels; ++l) {
-        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-            const uint32_t s = sym.LevelOrder[i];
+    {
+        std::vector<uint64_t> panel_at(size_t(ns) + 1, 0), update_at(size_t(ns) + 1, 0);
+        const auto tiles_of = [&](uint32_t s, PanelTile *panel_out, UpdateTile *update_out, uint64_t &panels, uint64_t &updates) {
             const uint32_t m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
-            for (uint32_t t = 0; t * kTile < m; ++t) sym.PanelTiles.push_back({s, t});
+            panels = updates = 0;
+            for (uint32_t t = 0; t * kTile < m; ++t, ++panels)
+                if (panel_out) panel_out[panels] = {s, t};
             for (uint64_t g = sym.SegPtr[s]; g < sym.SegPtr[s + 1]; ++g) {
                 const uint32_t c0 = 3 * sym.SegBegin[g], c1 = 3 * sym.SegEnd[g];
                 const uint32_t col_tiles = (c1 - c0 + kTile - 1) / kTile, row_tiles = (m - c0 + kTile - 1) / kTile;
                 for (uint32_t ct = 0; ct < col_tiles; ++ct)
-                    for (uint32_t rt = ct; rt < row_tiles; ++rt) sym.UpdateTiles.push_back({s, uint32_t(g), uint16_t(rt), uint16_t(ct)});
+                    for (uint32_t rt = ct; rt < row_tiles; ++rt, ++updates)
+                        if (update_out) update_out[updates] = {s, uint32_t(g), uint16_t(rt), uint16_t(ct)};
             }
-        }
-        sym.PanelTilePtr[l + 1] = sym.PanelTiles.size();
-        sym.UpdateTilePtr[l + 1] = sym.UpdateTiles.size();
+        };
+        ParallelChunks(ns, 256, [&](size_t a, size_t b, size_t) {
+            for (size_t i = a; i < b; ++i) tiles_of(sym.LevelOrder[i], nullptr, nullptr, panel_at[i + 1], update_at[i + 1]);
+        });
+        for (uint32_t i = 0; i < ns; ++i) panel_at[i + 1] += panel_at[i], update_at[i + 1] += update_at[i];
+        sym.PanelTiles.resize(panel_at[ns]);
+        sym.UpdateTiles.resize(update_at[ns]);
+        ParallelChunks(ns, 256, [&](size_t a, size_t b, size_t) {
+            uint64_t panels, updates;
+            for (size_t i = a; i < b; ++i) tiles_of(sym.LevelOrder[i], sym.PanelTiles.data() + panel_at[i], sym.UpdateTiles.data() + update_at[i], panels, updates);
+        });
+        for (uint32_t l = 0; l < sym.NumLevels; ++l) sym.PanelTilePtr[l + 1] = panel_at[sym.LevelPtr[l + 1]], sym.UpdateTilePtr[l + 1] = update_at[sym.LevelPtr[l + 1]];
     }
+    lap("tiles");
     // Dataflow schedules of the solves. Ticket order = level order (height above the leaves), NOT elimination order:
     // both are topological, but the post-order would walk one subtree's separator chains at a time, while the level
     // order keeps the chains of all subtrees of the same height in flight together.
     std::vector<uint32_t> fwd_expected(ns, 0), bwd_expected(ns, 0);
+    {
+        size_t tasks = 0;
+        for (uint32_t s = 0; s < ns; ++s)
+            tasks += (3 * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]) + kSolveRows - 1) / kSolveRows + (3 * size_t(sym.RowPtr[s + 1] - sym.RowPtr[s]) + kSolveRows - 1) / kSolveRows;
+        sym.FwdTasks.reserve(tasks), sym.BwdTasks.reserve(tasks);
+        sym.FwdLinks.reserve(sym.Rows.size() / 2), sym.BwdLinks.reserve(sym.Rows.size() / 2), sym.BwdLinkNeed.reserve(sym.Rows.size() / 2);
+    }
     auto targets_of = [&](uint32_t s, uint32_t slab, std::vector<uint32_t> &out) {
         const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0;
         const uint64_t first = (uint64_t(slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, (uint64_t(slab + 1) * kSolveRows + 2) / 3);
@@ -314,6 +404,7 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
                 sym.BwdTasks.push_back(t);
             }
     }
+    lap("sweep tasks");
     sym.StructureSeconds = Now() - t1;
     return sym;
 }
