@@ -160,6 +160,10 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    global VOICES
+    if args.voices:
+        VOICES = args.voices
+
     from mesheditor_b200 import ModalBank, build, measure_fp32_fma_rate
     from mesheditor_b200 import workloads as wl
 
@@ -546,6 +550,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--voices", type=int, default=0, help="resonator: experiment with another voice count (the bench line then names it; default = BASELINE.json configs[4])")
     ap.add_argument("--render-path", default="auto", choices=["auto", "loop", "tensor"], help="resonator: kernels of the free-running bank (auto = tensor-core form for this workload)")
     ap.add_argument("--workload", default="resonator", choices=["resonator", "solve", "batch"],
                     help="resonator: configs[4] (default, the metric quoted at 1/2/4/8 GPUs); solve: configs[2], one 1M-tet mesh; batch: configs[3], 64 meshes sharded")

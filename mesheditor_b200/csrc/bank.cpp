@@ -620,8 +620,27 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 DWalkStates.Reserve(size_t(tiles) * groups * TmStateTileFloats(TensorBlocksPerTile));
                 DGroupMix.Reserve(size_t(mix_rows) * wf);
                 plan.WalkStates = DWalkStates.Ptr;
+                // A bank of few chunk groups cannot fill the SMs with one CTA per group: its walk is split into seeded
+                // segments along time (the scan of the sample loop). A culling decision inside the window invalidates
+                // the seeds; the walk is then repeated sequentially (it is cheap next to the mix).
+                segments = RequestedSegments ? RequestedSegments : (SeededWalkFailed || groups >= 148 ? 1u : std::min<uint32_t>(16, (296 + groups - 1) / groups));
+                segments = std::max(1u, std::min(segments, blocks));
+                const uint32_t seg_blocks = (blocks + segments - 1) / segments;
+                segments = (blocks + seg_blocks - 1) / seg_blocks;
+                plan.NSegments = segments;
+                plan.SegmentFrames = seg_blocks * block_frames;
                 ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
+                seed_segments(segments);
                 Timed(1, stream, [&] { LaunchStateWalkKernel(view, plan, stream, Counter); });
+                if (segments > 1 && (speculation_failed() & 7u)) {
+                    SeededWalkFailed = true;
+                    ++Stats.scan_fallbacks;
+                    segments = plan.NSegments = 1;
+                    plan.SegmentFrames = blocks * block_frames;
+                    plan.SegStateRe = plan.SegStateIm = nullptr;
+                    ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
+                    Timed(1, stream, [&] { LaunchStateWalkKernel(view, plan, stream, Counter); });
+                }
                 Timed(2, stream, [&] {
                     LaunchTensorMixKernel({.Groups = groups, .GroupsPerRow = groups_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
                 });
@@ -698,6 +717,7 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
         RetunedObjects.clear();
     }
     SpeculationFailed = false;
+    SeededWalkFailed = false;
 
     Stats = {};
     Counter = {};

@@ -140,6 +140,7 @@ private:
     uint32_t RequestedSegments{0};
     int Steps{4};
     bool SpeculationFailed{false};
+    bool SeededWalkFailed{false}; // tensor-core form: a culling decision fell inside a seeded walk; later windows walk sequentially
     MeRenderStats Stats{};
     LaunchCounter Counter;
 

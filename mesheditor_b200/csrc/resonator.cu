@@ -312,8 +312,8 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         if constexpr (Walk) {
             // Row-major states (tensor_mix.cuh): this chunk owns 16 consecutive reduction elements of every time-block row,
             // so the CTA's 256 chunk-threads fill one 16 KB row per step, coalesced.
-            // The walk is sequential in time over the whole window (one segment), so culling needs no speculation.
-            // A warp's 32 chunks own 2 KB of the row; they pass through a swizzled shared-memory transpose so that every
+            // With one segment the walk is sequential in time over the whole window and culling needs no speculation; small
+            // banks (few chunk groups) are walked in several seeded segments like the sample loop. A warp's 32 chunks own 2 KB of the row; they pass through a swizzled shared-memory transpose so that every
             // store instruction covers 512 contiguous bytes.
             const uint32_t nb = plan.WalkBlocksPerTile;
             float4 *rows = reinterpret_cast<float4 *>(plan.WalkStates + size_t(blockIdx.x) * TmStateTileFloats(nb)) + warp * 128 + lane;
@@ -798,8 +798,8 @@ void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int ste
 
 void LaunchStateWalkKernel(const BankView &bank, const RenderPlan &plan, cudaStream_t stream, LaunchCounter &counter) {
     if (bank.NChunks == 0 || plan.Frames == 0) return;
-    if (plan.NSegments != 1) Fail(ME_BAD_ARG, "the state walk is sequential in time");
-    ResonatorKernel<1, 2, true><<<bank.NChunks / kBlockThreads, kBlockThreads, kWarpsPerBlock * 256 * sizeof(float4), stream>>>(bank, plan);
+    const dim3 grid(bank.NChunks / kBlockThreads, plan.NSegments);
+    ResonatorKernel<1, 2, true><<<grid, kBlockThreads, kWarpsPerBlock * 256 * sizeof(float4), stream>>>(bank, plan);
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
 }
