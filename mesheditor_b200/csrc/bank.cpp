@@ -547,14 +547,18 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 PowersVersion = TuningVersion;
             }
         }
-        // Chunk groups reduced in one CTA of the tensor-core kernel (one partial mix row each): as many as keeps the
-        // grid at eight waves or more (a CTA runs for tens of microseconds, so few waves leave a long tail).
-        uint32_t groups_per_row = 1;
+        // Stages reduced in one CTA of the tensor-core kernel (one partial mix row each): whole groups for large banks,
+        // fractions of a group for small ones, aiming at six waves or more (a CTA runs for tens of microseconds, so a
+        // short grid leaves a long tail).
+        uint32_t stages_per_row = kTmStagesPerGroup;
         if (tensor_span) {
-            const uint32_t tiles_in_window = (std::min(window, frames) + TensorTileFrames - 1) / TensorTileFrames;
-            while (groups_per_row < 16 && groups % (groups_per_row * 2) == 0 && uint64_t(groups / (groups_per_row * 2)) * tiles_in_window >= 8 * 148) groups_per_row *= 2;
+            const uint64_t tiles_in_window = (std::min(window, frames) + TensorTileFrames - 1) / TensorTileFrames;
+            const uint64_t total_stages = uint64_t(groups) * kTmStagesPerGroup;
+            // coarser rows (fewer partial rows to mix) only while twelve waves remain; finer ones until there are six
+            while (stages_per_row < 16 * kTmStagesPerGroup && total_stages % (stages_per_row * 2) == 0 && total_stages / (stages_per_row * 2) * tiles_in_window >= 12 * 148) stages_per_row *= 2;
+            while (stages_per_row > 64 && total_stages / stages_per_row * tiles_in_window < 6 * 148) stages_per_row /= 2;
         }
-        const uint32_t mix_rows = groups ? groups / groups_per_row : 0;
+        const uint32_t mix_rows = groups ? uint32_t(uint64_t(groups) * kTmStagesPerGroup / stages_per_row) : 0;
         const uint32_t ctas = NChunks / kBlockThreads;
         for (uint32_t begin = 0; begin < frames; begin += window) {
             const uint32_t wf = std::min(window, frames - begin);
@@ -623,7 +627,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 // A bank of few chunk groups cannot fill the SMs with one CTA per group: its walk is split into seeded
                 // segments along time (the scan of the sample loop). A culling decision inside the window invalidates
                 // the seeds; the walk is then repeated sequentially (it is cheap next to the mix).
-                segments = RequestedSegments ? RequestedSegments : (SeededWalkFailed || groups >= 148 ? 1u : std::min<uint32_t>(16, (296 + groups - 1) / groups));
+                segments = RequestedSegments ? RequestedSegments : (SeededWalkFailed || groups >= 148 ? 1u : std::min<uint32_t>(16, 296 / groups)); // two walk CTAs fit an SM: one wave
                 segments = std::max(1u, std::min(segments, blocks));
                 const uint32_t seg_blocks = (blocks + segments - 1) / segments;
                 segments = (blocks + seg_blocks - 1) / seg_blocks;
@@ -642,7 +646,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                     Timed(1, stream, [&] { LaunchStateWalkKernel(view, plan, stream, Counter); });
                 }
                 Timed(2, stream, [&] {
-                    LaunchTensorMixKernel({.Groups = groups, .GroupsPerRow = groups_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
+                    LaunchTensorMixKernel({.Groups = groups, .StagesPerRow = stages_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
                 });
                 ++Counter.Launches;
                 // Only code 8 (an increment off the time-block grid) can invalidate a sequential walk.

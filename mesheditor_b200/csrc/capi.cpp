@@ -192,7 +192,7 @@ MeStatus me_debug_tensor_mix(int device, const float *powers, const float *state
         const size_t ns = size_t(tiles) * groups * me::TmStateTileFloats(blocks_per_tile);
         me::DeviceBuffer<float> dp, ds, dout;
         dp.Upload(powers, np, nullptr), ds.Upload(states, ns, nullptr), dout.Reserve(size_t(groups / groups_per_row) * frames);
-        const me::TensorMixPlan plan{.Groups = groups, .GroupsPerRow = groups_per_row, .Tiles = tiles, .BlocksPerTile = blocks_per_tile, .Frames = frames, .Powers = dp.Ptr, .States = ds.Ptr, .Partial = dout.Ptr};
+        const me::TensorMixPlan plan{.Groups = groups, .StagesPerRow = groups_per_row * me::kTmStagesPerGroup, .Tiles = tiles, .BlocksPerTile = blocks_per_tile, .Frames = frames, .Powers = dp.Ptr, .States = ds.Ptr, .Partial = dout.Ptr};
         cudaEvent_t a, b;
         ME_CUDA(cudaEventCreate(&a));
         ME_CUDA(cudaEventCreate(&b));

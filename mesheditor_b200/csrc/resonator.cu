@@ -534,36 +534,31 @@ __global__ void __launch_bounds__(kPulseWarps * 32) PulseKernel(const BankView b
     }
 }
 
-// Block-parallel scan along time: one thread per chunk walks the window's segment boundaries, carrying the rotated
+// Block-parallel scan along time: one thread per mode walks the window's segment boundaries, carrying the rotated
 // state in FP64 and jumping between events with c^m = exp(m ln|c|) (cos m*arg c + i sin m*arg c).
 __global__ void __launch_bounds__(128) SegmentScanKernel(const BankView b, const RenderPlan plan, float *__restrict__ seg_re, float *__restrict__ seg_im) {
-    const uint32_t chunk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (chunk >= b.NChunks) return;
+    const uint32_t mode = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mode >= b.NChunks * kLanes) return;
+    const uint32_t chunk = mode / kLanes, lane_in_chunk = mode % kLanes;
     const uint32_t object = b.ChunkObject[chunk];
-    const uint32_t mode0 = chunk * kLanes;
+    const size_t stride = size_t(b.NChunks) * kLanes;
     if (object == kNoObject) {
-        for (uint32_t s = 1; s < plan.NSegments; ++s)
-            for (uint32_t l = 0; l < kLanes; ++l) seg_re[size_t(s - 1) * b.NChunks * kLanes + mode0 + l] = seg_im[size_t(s - 1) * b.NChunks * kLanes + mode0 + l] = 0.f;
+        for (uint32_t s = 1; s < plan.NSegments; ++s) seg_re[size_t(s - 1) * stride + mode] = seg_im[size_t(s - 1) * stride + mode] = 0.f;
         return;
     }
     const uint32_t my_chunk = chunk - b.ObjFirstChunk[object];
     const float mix = b.ObjMixGain[object];
     const double gain = mix == 0.f ? 1.0 : double(mix);
-    double wr[kLanes], wi[kLanes], log_rho[kLanes], theta[kLanes];
-    for (uint32_t l = 0; l < kLanes; ++l) {
-        const double zr = b.StateRe[mode0 + l], zi = b.StateIm[mode0 + l], qr = b.PhaseIm[mode0 + l], qi = b.PhaseRe[mode0 + l];
-        wr[l] = (zr * qr - zi * qi) * gain, wi[l] = (zr * qi + zi * qr) * gain;
-        log_rho[l] = b.LogRho[mode0 + l], theta[l] = b.Theta[mode0 + l];
-    }
+    const double zr = b.StateRe[mode], zi = b.StateIm[mode], qr = b.PhaseIm[mode], qi = b.PhaseRe[mode];
+    double wr = (zr * qr - zi * qi) * gain, wi = (zr * qi + zi * qr) * gain;
+    const double log_rho = b.LogRho[mode], theta = b.Theta[mode];
     const auto jump = [&](uint32_t m) {
         if (m == 0) return;
-        for (uint32_t l = 0; l < kLanes; ++l) {
-            const double mag = exp(double(m) * log_rho[l]); // ln 0 = -inf -> 0
-            double sn, cs;
-            sincos(double(m) * theta[l], &sn, &cs);
-            const double re = (wr[l] * cs - wi[l] * sn) * mag, im = (wr[l] * sn + wi[l] * cs) * mag;
-            wr[l] = re, wi[l] = im;
-        }
+        const double mag = exp(double(m) * log_rho); // ln 0 = -inf -> 0
+        double sn, cs;
+        sincos(double(m) * theta, &sn, &cs);
+        const double re = (wr * cs - wi * sn) * mag, im = (wr * sn + wi * cs) * mag;
+        wr = re, wi = im;
     };
     uint32_t inj = plan.ObjInjectPtr[object];
     const uint32_t inj_hi = plan.ObjInjectPtr[object + 1];
@@ -575,13 +570,12 @@ __global__ void __launch_bounds__(128) SegmentScanKernel(const BankView b, const
         for (; inj < inj_hi && plan.InjectFrame[inj] < boundary; ++inj) {
             jump(plan.InjectFrame[inj] - cursor);
             cursor = plan.InjectFrame[inj];
-            const uint32_t off = plan.InjectDelta[inj] + my_chunk * kLanes;
-            for (uint32_t l = 0; l < kLanes; ++l) wr[l] += double(plan.DeltaRe[off + l]), wi[l] += double(plan.DeltaIm[off + l]);
+            const uint32_t off = plan.InjectDelta[inj] + my_chunk * kLanes + lane_in_chunk;
+            wr += double(plan.DeltaRe[off]), wi += double(plan.DeltaIm[off]);
         }
         jump(boundary - cursor);
         cursor = boundary;
-        const size_t out = size_t(s - 1) * b.NChunks * kLanes + mode0;
-        for (uint32_t l = 0; l < kLanes; ++l) seg_re[out + l] = float(wr[l]), seg_im[out + l] = float(wi[l]);
+        seg_re[size_t(s - 1) * stride + mode] = float(wr), seg_im[size_t(s - 1) * stride + mode] = float(wi);
     }
 }
 
@@ -763,7 +757,7 @@ void LaunchPulseKernel(const BankView &bank, const PulsePlan &plan, cudaStream_t
 
 void LaunchSegmentScan(const BankView &bank, const RenderPlan &plan, float *seg_re, float *seg_im, cudaStream_t stream, LaunchCounter &counter) {
     if (plan.NSegments <= 1 || bank.NChunks == 0) return;
-    SegmentScanKernel<<<(bank.NChunks + 127) / 128, 128, 0, stream>>>(bank, plan, seg_re, seg_im);
+    SegmentScanKernel<<<(bank.NChunks * kLanes + 127) / 128, 128, 0, stream>>>(bank, plan, seg_re, seg_im);
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
 }

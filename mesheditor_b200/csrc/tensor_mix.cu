@@ -106,6 +106,7 @@ __device__ __forceinline__ void TmemLoad16(uint32_t taddr, uint32_t (&v)[16]) {
 // kFoldStages stages (24 MMAs per accumulator, <= 1.5e-6) and folded into FP32 registers by the epilogue warps with
 // round-to-nearest adds; two accumulator pairs alternate so the fold of one overlaps the MMAs into the other.
 constexpr uint32_t kFoldStages = 4;
+constexpr uint32_t kFoldStagesHost = kFoldStages;
 
 template<uint32_t N, uint32_t Stages>
 __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPlan plan, const __grid_constant__ CUtensorMap states_map) {
@@ -124,8 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
     // Tiles of one group are adjacent in launch order, so the CTAs streaming the same power stages run together and
     // share them through L2.
     const uint32_t tile = blockIdx.x % plan.Tiles, row_index = blockIdx.x / plan.Tiles;
-    const uint32_t first_group = row_index * plan.GroupsPerRow;
-    const uint32_t n_stages = plan.GroupsPerRow * kTmStagesPerGroup;
+    const uint32_t n_stages = plan.StagesPerRow, first_stage = row_index * plan.StagesPerRow; // in the group-major stage sequence
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < Stages; ++s) BarrierInit(&full_bar[s], 1), BarrierInit(&empty_bar[s], 1);
@@ -143,14 +143,14 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint8_t *powers = reinterpret_cast<const uint8_t *>(plan.Powers) + size_t(first_group) * kTmStagesPerGroup * kPowerBytes;
+            const uint8_t *powers = reinterpret_cast<const uint8_t *>(plan.Powers) + size_t(first_stage) * kPowerBytes;
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&states_map)) : "memory");
             for (uint32_t k = 0; k < n_stages; ++k) {
                 const uint32_t s = k % Stages, round = k / Stages;
                 if (round) BarrierWait(&empty_bar[s], (round - 1) & 1);
                 uint8_t *stage = stage_storage + size_t(s) * kStageBytes;
                 BarrierExpectTx(&full_bar[s], kStageBytes);
-                TensorCopy4(stage, &states_map, (k % kTmStagesPerGroup) * kTmKChunk, 0, 0, tile * plan.Groups + first_group + k / kTmStagesPerGroup, &full_bar[s]);
+                TensorCopy4(stage, &states_map, ((first_stage + k) % kTmStagesPerGroup) * kTmKChunk, 0, 0, tile * plan.Groups + (first_stage + k) / kTmStagesPerGroup, &full_bar[s]);
                 BulkCopy(stage + kStateBytes, powers + size_t(k) * kPowerBytes, kPowerBytes, &full_bar[s]);
             }
         }
@@ -250,7 +250,7 @@ void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) Fail(ME_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", int(r));
     ME_CUDA(cudaFuncSetAttribute(TensorMixKernel<N, Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); // per device, cheap
-    TensorMixKernel<N, Stages><<<plan.Groups / plan.GroupsPerRow * plan.Tiles, kThreads, bytes, stream>>>(plan, map);
+    TensorMixKernel<N, Stages><<<plan.Groups * kTmStagesPerGroup / plan.StagesPerRow * plan.Tiles, kThreads, bytes, stream>>>(plan, map);
     ME_CUDA(cudaGetLastError());
 }
 
@@ -258,7 +258,8 @@ void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
 
 void LaunchTensorMixKernel(const TensorMixPlan &plan, cudaStream_t stream) {
     if (plan.Groups == 0 || plan.Tiles == 0) return;
-    if (plan.GroupsPerRow == 0 || plan.Groups % plan.GroupsPerRow != 0) Fail(ME_BAD_ARG, "tensor mix: groups per row must divide the groups");
+    if (plan.StagesPerRow == 0 || plan.StagesPerRow % kFoldStagesHost != 0 || (uint64_t(plan.Groups) * kTmStagesPerGroup) % plan.StagesPerRow != 0)
+        Fail(ME_BAD_ARG, "tensor mix: stages per row must be a multiple of %u that divides the stage count", kFoldStagesHost);
     if (plan.BlocksPerTile == 128) Launch<128, 4>(plan, stream);
     else Fail(ME_BAD_ARG, "tensor mix: blocks per tile must be 128");
 }

@@ -38,13 +38,14 @@ __host__ __device__ constexpr size_t TmStateTileFloats(uint32_t blocks_per_tile)
 
 struct TensorMixPlan {
     uint32_t Groups;          // chunk groups (reduction ranges of 256 chunk slots)
-    uint32_t GroupsPerRow;    // consecutive groups reduced by one CTA into one partial row (divides Groups)
+    uint32_t StagesPerRow;    // consecutive stages (of the group-major sequence, 256 per group) reduced by one CTA into one
+                              // partial row: a multiple of 4 that divides Groups * 256
     uint32_t Tiles;           // time tiles in the window
     uint32_t BlocksPerTile;   // 128 time blocks (the N extent)
     uint32_t Frames;          // valid frames of the window (the last tile may be ragged)
     const float *Powers;      // [Groups][256 stages] power stages
     const float *States;      // [Tiles][Groups][2][BlocksPerTile][4096]
-    float *Partial;           // [Groups / GroupsPerRow][Frames] partial mixes
+    float *Partial;           // [Groups * 256 / StagesPerRow][Frames] partial mixes
 };
 
 void LaunchTensorMixKernel(const TensorMixPlan &, cudaStream_t);
