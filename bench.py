@@ -242,7 +242,7 @@ def run_ours(args):
             elapsed_ms += start.elapsed_time(stop)
             stats = bank.stats()
             if os.environ.get("ME_BENCH_DEBUG"):
-                print(f"[bench] step {start.elapsed_time(stop):.2f} ms, library total {stats['total_device_ms']:.2f} ms, walk {stats['walk_kernel_ms']:.2f}, mix {stats['tensor_mix_kernel_ms']:.2f}, host plan {stats['host_plan_ms']:.2f}", file=sys.stderr)
+                print(f"[bench] step {start.elapsed_time(stop):.2f} ms, library total {stats['total_device_ms']:.2f} ms, walk {stats['walk_kernel_ms']:.2f}, mix {stats['tensor_mix_kernel_ms']:.2f}, host plan {stats['host_plan_ms']:.2f}, pulses {stats['pulse_kernels_ms']:.2f}, stage {stats['resonator_kernel_ms']:.2f}", file=sys.stderr)
             kernel_ms.append(stats["resonator_kernel_ms"])
             walk_ms.append(stats["walk_kernel_ms"])
             mix_ms.append(stats["tensor_mix_kernel_ms"])

@@ -139,7 +139,7 @@ typedef struct MeRenderStats {
     float walk_kernel_ms;           /* tensor-core form: device time of the state walk kernel(s) */
     float tensor_mix_kernel_ms;     /* tensor-core form: device time of the tcgen05 mix kernel(s) */
     float host_plan_ms;             /* host time spent planning the spans (impact schedule, uploads) before their first launch */
-    uint32_t reserved;
+    float pulse_kernels_ms;         /* device time of the force + pulse kernels */
 } MeRenderStats;
 MeStatus me_bank_last_render_stats(const MeBank *, MeRenderStats *out);
 /* Scheduling knobs of the offline renderer: time_segments 0 = automatic. */

@@ -33,7 +33,7 @@ class MeRenderStats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint32), ("resonator_kernel_ms", C.c_float), ("total_device_ms", C.c_float),
         ("mode_samples", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("time_segments", C.c_uint32), ("scan_fallbacks", C.c_uint32),
-        ("tensor_windows", C.c_uint32), ("partial_rows", C.c_uint32), ("walk_kernel_ms", C.c_float), ("tensor_mix_kernel_ms", C.c_float), ("host_plan_ms", C.c_float), ("reserved", C.c_uint32),
+        ("tensor_windows", C.c_uint32), ("partial_rows", C.c_uint32), ("walk_kernel_ms", C.c_float), ("tensor_mix_kernel_ms", C.c_float), ("host_plan_ms", C.c_float), ("pulse_kernels_ms", C.c_float),
     ]
 
 

@@ -454,6 +454,31 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         force_total += len;
         if (len) delta_total += ObjStride[im.Object];
     }
+    // The force and pulse kernels only need the impacts: they start now, and the per-object lists below are planned on the
+    // host while they run.
+    DImpacts.Upload(CallImpacts, stream), DTails.Upload(CallTails, stream), DPulseWarps.Upload(CallPulseWarps, stream);
+    DForce.Reserve(std::max<uint64_t>(force_total, 1)), DDeltaRe.Reserve(std::max<uint64_t>(delta_total, 1)), DDeltaIm.Reserve(std::max<uint64_t>(delta_total, 1)), DPulseRows.Reserve(std::max<uint64_t>(row_total, 1));
+    // Slots of the delta buffers the pulse kernel does not write (chunks past the object in a warp's tail are skipped,
+    // every chunk inside the object is written) need no clearing.
+    Stats.host_plan_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - plan_begin).count();
+    cudaEvent_t pulse_begin = NextEvent(), pulse_end = NextEvent();
+    EventKind.push_back(3);
+    ME_CUDA(cudaEventRecord(pulse_begin, stream));
+    LaunchForceKernel(DImpacts.Ptr, DTails.Ptr, n, DForce.Ptr, stream, Counter);
+    const PulsePlan pulses{.NPulseWarps = uint32_t(CallPulseWarps.size()), .Warps = DPulseWarps.Ptr, .Impacts = DImpacts.Ptr, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
+    {
+        // The mix gains are read by the pulse kernel too (and the view below must see their final addresses).
+        MixGain.resize(n_obj), EnergyScale.resize(n_obj);
+        for (uint32_t o = 0; o < n_obj; ++o) {
+            MixGain[o] = OutGain[o] * ListenerGain[o];
+            EnergyScale[o] = MixGain[o] != 0.f ? (OutGain[o] * OutGain[o]) / (MixGain[o] * MixGain[o]) : 0.f;
+        }
+        DObjMixGain.Upload(MixGain, stream), DObjEnergyScale.Upload(EnergyScale, stream);
+    }
+    BankView view = View();
+    LaunchPulseKernel(view, pulses, stream, Counter);
+    ME_CUDA(cudaEventRecord(pulse_end, stream));
+
     // Per object: increments in frame order, and the merged intervals during which it holds a live impact.
     // (impacts are in start order, so a counting sort by object leaves each object's lists in start order too)
     CallInjectPtr.assign(n_obj + 1, 0), CallExcitePtr.assign(n_obj + 1, 0);
@@ -500,26 +525,9 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         merged_ptr[o + 1] = uint32_t(CallExciteBegin.size());
     }
     CallExcitePtr = merged_ptr;
-    MixGain.resize(n_obj), EnergyScale.resize(n_obj);
-    for (uint32_t o = 0; o < n_obj; ++o) {
-        MixGain[o] = OutGain[o] * ListenerGain[o];
-        EnergyScale[o] = MixGain[o] != 0.f ? (OutGain[o] * OutGain[o]) / (MixGain[o] * MixGain[o]) : 0.f;
-    }
-
-    DImpacts.Upload(CallImpacts, stream), DTails.Upload(CallTails, stream), DPulseWarps.Upload(CallPulseWarps, stream);
     DInjectPtr.Upload(CallInjectPtr, stream), DInjectFrame.Upload(CallInjectFrame, stream), DInjectDelta.Upload(CallInjectDelta, stream);
     DExcitePtr.Upload(CallExcitePtr, stream), DExciteBegin.Upload(CallExciteBegin, stream), DExciteEnd.Upload(CallExciteEnd, stream);
-    DObjMixGain.Upload(MixGain, stream), DObjEnergyScale.Upload(EnergyScale, stream);
     Stats.h2d_bytes += n * (sizeof(DevImpact) + sizeof(DevImpactTail)) + CallPulseWarps.size() * sizeof(PulseWarp) + (CallInjectPtr.size() + CallExcitePtr.size() + 2 * CallInjectFrame.size() + 2 * CallExciteBegin.size() + 2 * n_obj) * 4;
-    DForce.Reserve(std::max<uint64_t>(force_total, 1)), DDeltaRe.Reserve(std::max<uint64_t>(delta_total, 1)), DDeltaIm.Reserve(std::max<uint64_t>(delta_total, 1)), DPulseRows.Reserve(std::max<uint64_t>(row_total, 1));
-    // Slots of the delta buffers the pulse kernel does not write (chunks past the object in a warp's tail are skipped,
-    // every chunk inside the object is written) need no clearing.
-
-    Stats.host_plan_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - plan_begin).count();
-    LaunchForceKernel(DImpacts.Ptr, DTails.Ptr, n, DForce.Ptr, stream, Counter);
-    const PulsePlan pulses{.NPulseWarps = uint32_t(CallPulseWarps.size()), .Warps = DPulseWarps.Ptr, .Impacts = DImpacts.Ptr, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
-    BankView view = View();
-    LaunchPulseKernel(view, pulses, stream, Counter);
 
     const uint32_t rows = ResonatorRows(NChunks);
     Stats.time_segments = 1;
@@ -819,13 +827,14 @@ const MeRenderStats &Bank::LastStats() {
         if (cudaEventSynchronize(EvEnd) == cudaSuccess) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, EvBegin, EvEnd) == cudaSuccess) Stats.total_device_ms = ms;
-            float kernel[3] = {0.f, 0.f, 0.f};
+            float kernel[4] = {0.f, 0.f, 0.f, 0.f};
             for (uint32_t i = 0; i + 1 < EventsUsed; i += 2) {
                 if (cudaEventElapsedTime(&ms, EventPool[i], EventPool[i + 1]) == cudaSuccess) kernel[EventKind[i / 2]] += ms;
             }
             Stats.resonator_kernel_ms = kernel[0];
             Stats.walk_kernel_ms = kernel[1];
             Stats.tensor_mix_kernel_ms = kernel[2];
+            Stats.pulse_kernels_ms = kernel[3];
         }
         StatsResolved = true;
     }

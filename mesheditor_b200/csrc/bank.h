@@ -85,7 +85,7 @@ private:
     cudaStream_t OwnStream{nullptr};
     cudaEvent_t EvBegin{nullptr}, EvEnd{nullptr};
     std::vector<cudaEvent_t> EventPool; // begin/end pairs around every resonator kernel launch of the last call
-    std::vector<uint8_t> EventKind;     // per pair: 0 the whole resonator stage of a window, 1 the walk kernel, 2 the tcgen05 mix kernel
+    std::vector<uint8_t> EventKind;     // per pair: 0 the whole resonator stage of a window, 1 the walk kernel, 2 the tcgen05 mix kernel, 3 force + pulse kernels
     uint32_t EventsUsed{0};
     bool StatsResolved{true};
 
