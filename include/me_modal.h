@@ -368,6 +368,42 @@ typedef struct MeStrike {
 } MeStrike;
 MeStatus me_make_strike_event(const MeStrike *, MeModalEvent *out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Model interchange: the data formats either side of a modal solve. Host-only.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* What ModalModelData (src/audio/ModalModelFile.h:13-20) holds beyond a solve's result: ModalModes::Vertices / Indices /
+ * BakedScale, the display TetMeshData, and the rest of ModalEigenSummary. Arrays are borrowed for a serialize call and owned
+ * by the MeModalFile handle after a parse. */
+typedef struct MeModalFileExtras {
+    const uint32_t *vertices;          uint32_t n_vertices;         /* ModalModes::Vertices */
+    const uint32_t *indices;           uint32_t n_indices;          /* ModalModes::Indices */
+    float baked_scale[3];                                           /* ModalModes::BakedScale */
+    const float *tet_positions_xyz;    uint32_t n_tet_positions;    /* TetMeshData::Positions */
+    const uint32_t *tet_edge_indices;  uint32_t n_tet_edge_indices; /* TetMeshData::EdgeIndices */
+    MeMaterial solved_material;                                     /* ModalEigenSummary::SolvedMaterial ... */
+    float solved_min_mode_freq, solved_max_mode_freq;
+    uint32_t solved_num_modes;
+    uint64_t tet_inputs_hash;
+    const uint32_t *solved_vertices;   uint32_t n_solved_vertices;
+} MeModalFileExtras;
+typedef struct MeModalFile MeModalFile;
+
+/* The bytes SaveModalModelFile writes (ModalModelFile.cpp:15-22: zpp::bits archive of ModalModelData{Modes, Mass, Tets,
+ * Summary}), byte for byte. *bytes is malloc'ed: release with me_bytes_free. */
+MeStatus me_modal_file_serialize(const MeModalResult *, const MeModalFileExtras *, uint8_t **bytes, uint64_t *size);
+/* LoadModalModelFile (ModalModelFile.cpp:52-58): ME_BAD_ARG on truncated or inconsistent data. The result answers the
+ * me_modal_result_* accessors (modes, mass properties, eigenvalues, summary shapes); the rest through me_modal_file_extras. */
+MeStatus me_modal_file_parse(const uint8_t *bytes, uint64_t size, MeModalResult **result, MeModalFile **file);
+MeStatus me_modal_file_extras(const MeModalFile *, MeModalFileExtras *out);
+void me_modal_file_free(MeModalFile *);
+void me_bytes_free(void *);
+/* The JSON MeshEditorModalSolve prints (tests/ModalSolveTool.cpp:84-123), which glTF_PhysicalAudio embeds as a
+ * KHR_audio_rigid_bodies modal model: frequencies, decayRates (= ln 1000 / T60), positions, mode-major shapes, the mesh
+ * triangles relabelled onto the sample points (merged corners drop the triangle), mass, centerOfMass, inertiaDiagonal.
+ * Numbers are the shortest text that round-trips (std::format "{}"). *json is malloc'ed: release with me_bytes_free. */
+MeStatus me_modal_solve_json(const MeModalResult *, const uint32_t *triangle_indices, uint32_t n_triangle_indices, char **json);
+
 /* Unit-test entry of the tensor-core mix (tensor_mix.cuh): out[row][frame] = sum over the 4096 reduction elements of
  * each of the row's groups_per_row consecutive groups of power * state, operands given as host images of the stage layout documented in tensor_mix.cuh
  * (powers: groups*256 stages of 2*256*16 floats, stage layout; states: [tiles][groups][head,tail][blocks_per_tile][4096] floats).

@@ -41,6 +41,13 @@ class MeMaterial(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("density", "young_modulus", "poisson_ratio", "alpha", "beta")]
 
 
+class MeModalFileExtras(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("n_vertices", C.c_uint32), ("indices", C.c_void_p), ("n_indices", C.c_uint32), ("baked_scale", C.c_float * 3),
+                ("tet_positions_xyz", C.c_void_p), ("n_tet_positions", C.c_uint32), ("tet_edge_indices", C.c_void_p), ("n_tet_edge_indices", C.c_uint32), ("solved_material", MeMaterial),
+                ("solved_min_mode_freq", C.c_float), ("solved_max_mode_freq", C.c_float), ("solved_num_modes", C.c_uint32), ("tet_inputs_hash", C.c_uint64),
+                ("solved_vertices", C.c_void_p), ("n_solved_vertices", C.c_uint32)]
+
+
 class MeStriker(C.Structure):
     _fields_ = [("material", MeMaterial), ("tip_radius", C.c_float), ("length", C.c_float)]
 
@@ -156,6 +163,10 @@ def lib():
         "me_symbolic_analyse": [u32, vp, vp, vp, vp, C.POINTER(MeSymbolicInfo)],
     }
     sig.update({
+        "me_modal_file_serialize": [vp, C.POINTER(MeModalFileExtras), C.POINTER(vp), C.POINTER(u64)],
+        "me_modal_file_parse": [vp, u64, C.POINTER(vp), C.POINTER(vp)],
+        "me_modal_file_extras": [vp, C.POINTER(MeModalFileExtras)],
+        "me_modal_solve_json": [vp, vp, u32, C.POINTER(vp)],
         "me_striker_impactor": [C.POINTER(MeStriker), C.POINTER(MeImpactor)],
         "me_inverse_inertia_tensor": [C.POINTER(MeMassProperties), vp],
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
@@ -173,6 +184,9 @@ def lib():
     }.items():
         getattr(L, name).argtypes = args
         getattr(L, name).restype = f64
+    for name in ("me_modal_file_free", "me_bytes_free"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = None
     L.me_recoil_click_filter.argtypes = [f64, f64, f64, f64, vp]
     L.me_recoil_click_filter.restype = None
     for name in ("me_bank_free", "me_modal_result_free", "me_fem_free", "me_factor_free"):

@@ -3,6 +3,7 @@
 // Reference: src/audio/mesh2modes.cpp:605-658 (mesh2modes), :441-512 (ComputeModes), :515-603, :73-126.
 #include "cholesky.h"
 #include "common.h"
+#include "result.h"
 #include "fem.h"
 #include "lanczos.h"
 
@@ -45,13 +46,6 @@ Material FromC(const MeMaterial *m) {
     return {m->density, m->young_modulus, m->poisson_ratio, m->alpha, m->beta};
 }
 
-// ModalModes (src/audio/ModalModes.h:7-20).
-struct Modes {
-    std::vector<float> Freqs, T60s;
-    std::vector<float> Shapes;    // [point][mode][3]
-    std::vector<float> Positions; // [point][3]
-    float OriginalFundamentalFreq{0};
-};
 
 // modal::PostprocessModes (mesh2modes.cpp:515-588). shapes: [point][eigenpair][3].
 Modes Postprocess(const std::vector<double> &eigenvalues, const std::vector<float> &shapes, uint32_t n_points, float shape_scale, const Material &material, const Config &config,
@@ -261,17 +255,6 @@ __global__ void CastBasisKernel(const double *__restrict__ X, size_t count, floa
 } // namespace
 } // namespace me
 
-struct MeModalResult {
-    me::Modes Modes;
-    MeMassProperties MassProps{};
-    MeSolveProfile Profile{};
-    std::vector<double> Eigenvalues;
-    std::vector<float> SummaryShapes; // [point][eigenpair][3]
-    std::vector<uint32_t> SamplePointOfExcitation;
-    std::vector<float> Basis;
-    uint32_t BasisRows{0}, BasisCols{0};
-    uint32_t PointCount{0};
-};
 struct MeFemSystem {
     me::FemSystem Impl;
     explicit MeFemSystem(int device) : Impl(device) {}

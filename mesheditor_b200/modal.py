@@ -94,6 +94,15 @@ def mesh2modes(points, tets, mat, excite_positions, baked_scale=(1.0, 1.0, 1.0),
     """modal::mesh2modes (mesh2modes.h:77). seed_basis (n x cols, a prior result's `basis`) selects the warm re-solve
     (SolveReuse::SeedBasis). Like the reference, a cancelled / non-converged / no-mode solve returns an EMPTY
     result (status says which); a failed factorisation raises (the reference throws std::runtime_error)."""
+    h, status = solve_handle(points, tets, mat, excite_positions, baked_scale, config, keep_basis, monitor, seed_basis)
+    try:
+        return _read_result(h, status)
+    finally:
+        lib().me_modal_result_free(h)
+
+
+def solve_handle(points, tets, mat, excite_positions, baked_scale=(1.0, 1.0, 1.0), config=None, keep_basis=False, monitor=None, seed_basis=None):
+    """me_modal_solve, returning the library-owned MeModalResult handle and the status (interchange.py keeps the handle)."""
     L = lib()
     pts = np.ascontiguousarray(points, np.float64)
     tt = np.ascontiguousarray(tets, np.uint32)
@@ -110,10 +119,7 @@ def mesh2modes(points, tets, mat, excite_positions, baked_scale=(1.0, 1.0, 1.0),
                               C.byref(monitor) if monitor is not None else None, C.byref(h))
     if status not in (ME_OK, ME_CANCELLED, ME_NOT_CONVERGED, ME_NO_MODES):
         raise MeError(status, L.me_last_error().decode())
-    try:
-        return _read_result(h, status)
-    finally:
-        L.me_modal_result_free(h)
+    return h, status
 
 
 def postprocess_modes(eigenvalues, shapes, shape_scale, mat, config, positions):

@@ -7,7 +7,9 @@
 // It mirrors the harness the reference's own tests use (tests/ModalBench.h:47-81 `ModalScene`):
 // AddModalObject + TuneModalObject + OutGain, InstallModalBank, one discard block, then
 // EnqueueModalEvent / RenderModal.
+#include "action/SerializeGlm.h"
 #include "audio/ContactModel.h"
+#include "audio/ModalModelFile.h"
 #include "audio/ModalAudio.h"
 #include "audio/ModalModes.h"
 
@@ -195,5 +197,71 @@ double ref_contact_scalar(int which, double x, double y, double z) {
         case 4: return SaturationPenetration(x, y);
         default: return PunchStiffness(x, y);
     }
+}
+
+// ---- Model interchange: the reference's .modal bytes (src/audio/ModalModelFile.cpp:15-22 Serialize, :52-58 load) ----
+// Flat arguments -> ModalModelData -> zpp::bits (the reference's own struct definitions and ADL hooks). Returns the byte
+// count (0 on failure); `out` may be NULL to query the size.
+struct RefModalFlat {
+    uint32_t n_modes, n_points, n_vertices, n_indices, n_tet_positions, n_tet_edges, n_eigen, n_solved_vertices;
+    const float *freqs, *t60s, *shapes /*[point][mode][3]*/, *positions;
+    const uint32_t *vertices, *indices;
+    float original_fundamental, baked_scale[3];
+    double mass;
+    float com[3], inertia[3], quat_wxyz[4];
+    const float *tet_positions;
+    const uint32_t *tet_edges;
+    const double *eigenvalues;
+    const float *summary_shapes /*[point][eigenpair][3]*/;
+    double material[5];
+    float min_freq, max_freq;
+    uint32_t num_modes;
+    uint64_t tet_hash;
+    const uint32_t *solved_vertices;
+};
+static ModalModelData RefModalData(const RefModalFlat &f) {
+    ModalModelData d;
+    d.Modes.Freqs.assign(f.freqs, f.freqs + f.n_modes);
+    d.Modes.T60s.assign(f.t60s, f.t60s + f.n_modes);
+    d.Modes.Shapes.resize(f.n_points);
+    d.Summary.Shapes.resize(f.n_points);
+    for (uint32_t p = 0; p < f.n_points; ++p) {
+        for (uint32_t k = 0; k < f.n_modes; ++k) d.Modes.Shapes[p].push_back(vec3{f.shapes[(size_t(p) * f.n_modes + k) * 3], f.shapes[(size_t(p) * f.n_modes + k) * 3 + 1], f.shapes[(size_t(p) * f.n_modes + k) * 3 + 2]});
+        for (uint32_t k = 0; k < f.n_eigen; ++k)
+            d.Summary.Shapes[p].push_back(vec3{f.summary_shapes[(size_t(p) * f.n_eigen + k) * 3], f.summary_shapes[(size_t(p) * f.n_eigen + k) * 3 + 1], f.summary_shapes[(size_t(p) * f.n_eigen + k) * 3 + 2]});
+        d.Modes.Positions.push_back(vec3{f.positions[3 * p], f.positions[3 * p + 1], f.positions[3 * p + 2]});
+    }
+    d.Modes.Vertices.assign(f.vertices, f.vertices + f.n_vertices);
+    d.Modes.Indices.assign(f.indices, f.indices + f.n_indices);
+    d.Modes.OriginalFundamentalFreq = f.original_fundamental;
+    d.Modes.BakedScale = vec3{f.baked_scale[0], f.baked_scale[1], f.baked_scale[2]};
+    d.Mass.Mass = f.mass;
+    d.Mass.CenterOfMass = vec3{f.com[0], f.com[1], f.com[2]};
+    d.Mass.InertiaDiagonal = vec3{f.inertia[0], f.inertia[1], f.inertia[2]};
+    d.Mass.InertiaOrientation = glm::quat{f.quat_wxyz[0], f.quat_wxyz[1], f.quat_wxyz[2], f.quat_wxyz[3]};
+    for (uint32_t i = 0; i < f.n_tet_positions; ++i) d.Tets.Positions.push_back(vec3{f.tet_positions[3 * i], f.tet_positions[3 * i + 1], f.tet_positions[3 * i + 2]});
+    d.Tets.EdgeIndices.assign(f.tet_edges, f.tet_edges + f.n_tet_edges);
+    d.Summary.Eigenvalues.assign(f.eigenvalues, f.eigenvalues + f.n_eigen);
+    d.Summary.SolvedMaterial = RefMaterial(f.material);
+    d.Summary.SolvedMinModeFreq = f.min_freq, d.Summary.SolvedMaxModeFreq = f.max_freq;
+    d.Summary.SolvedNumModes = f.num_modes;
+    d.Summary.TetInputsHash = size_t(f.tet_hash);
+    d.Summary.SolvedVertices.assign(f.solved_vertices, f.solved_vertices + f.n_solved_vertices);
+    return d;
+}
+uint64_t ref_modal_file_serialize(const RefModalFlat *flat, uint8_t *out, uint64_t capacity) {
+    ModalModelData d = RefModalData(*flat);
+    std::vector<std::byte> bytes;
+    zpp::bits::out archive{bytes};
+    if (zpp::bits::failure(archive(d))) return 0;
+    if (out && capacity >= bytes.size()) std::memcpy(out, bytes.data(), bytes.size());
+    return bytes.size();
+}
+// Parses bytes with the reference's loader arithmetic and reports whether they decode to exactly `flat`'s content.
+int ref_modal_file_roundtrip_equal(const RefModalFlat *flat, const uint8_t *bytes, uint64_t size) {
+    std::vector<std::byte> in(reinterpret_cast<const std::byte *>(bytes), reinterpret_cast<const std::byte *>(bytes) + size);
+    ModalModelData parsed;
+    if (zpp::bits::failure(zpp::bits::in{in}(parsed))) return -1;
+    return parsed == RefModalData(*flat) ? 1 : 0;
 }
 }

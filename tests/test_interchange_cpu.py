@@ -1,0 +1,91 @@
+"""Model interchange through the C ABI: `.modal` bytes against the reference's own zpp::bits archive
+(committed blobs tests/golden/interchange/*.modal written by oracle/_ref, and oracle/_ref live where it is built), and the
+MeshEditorModalSolve JSON against a restatement of tests/ModalSolveTool.cpp:84-123. Host-only. Bar: byte-exact."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_interchange_golden import SEEDS  # noqa: E402
+
+from mesheditor_b200 import MeError  # noqa: E402
+from mesheditor_b200.interchange import LN1000, ModalModel, bank_modes, khr_modal_model  # noqa: E402
+from oracle import interchange as oi  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "interchange")
+
+
+def check_fields(model: ModalModel, m):
+    r = model.result
+    np.testing.assert_array_equal(r.freqs, m["freqs"]), np.testing.assert_array_equal(r.t60s, m["t60s"])
+    np.testing.assert_array_equal(r.shapes, m["shapes"]), np.testing.assert_array_equal(r.positions, m["positions"])
+    np.testing.assert_array_equal(r.eigenvalues, m["eigenvalues"]), np.testing.assert_array_equal(r.summary_shapes, m["summary_shapes"])
+    assert r.original_fundamental == float(m["original_fundamental"]) and r.mass_props["mass"] == m["mass"]
+    np.testing.assert_array_equal(np.array(r.mass_props["center_of_mass"], np.float32), m["com"])
+    np.testing.assert_array_equal(np.array(r.mass_props["inertia_diagonal"], np.float32), m["inertia"])
+    np.testing.assert_array_equal(np.array(r.mass_props["inertia_orientation"], np.float32), m["quat_wxyz"])
+    for ours, theirs in ((model.vertices, "vertices"), (model.indices, "indices"), (model.tet_edge_indices, "tet_edges"), (model.solved_vertices, "solved_vertices"), (model.tet_positions, "tet_positions")):
+        np.testing.assert_array_equal(ours, m[theirs])
+    np.testing.assert_array_equal(np.array(model.baked_scale, np.float32), m["baked_scale"])
+    sm = model.solved_material
+    assert (sm.density, sm.young_modulus, sm.poisson_ratio, sm.alpha, sm.beta) == tuple(m["material"])
+    assert (model.solved_min_mode_freq, model.solved_max_mode_freq, model.solved_num_modes, model.tet_inputs_hash) == (float(m["min_freq"]), float(m["max_freq"]), m["num_modes"], m["tet_hash"])
+
+
+@pytest.mark.parametrize("seed", sorted(SEEDS))
+def test_golden_modal_files_parse_and_reserialise_byte_exact(seed):
+    with open(os.path.join(GOLDEN, f"model_{seed}.modal"), "rb") as f:
+        data = f.read()
+    model = ModalModel.from_bytes(data)
+    check_fields(model, oi.random_model(seed, **SEEDS[seed]))
+    assert model.to_bytes() == data
+
+
+@pytest.mark.skipif(not oi.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", [101, 102, 103])
+def test_against_the_reference_archive_live(seed):
+    rng = np.random.default_rng(seed)
+    m = oi.random_model(seed, n_modes=int(rng.integers(1, 40)), n_points=int(rng.integers(1, 20)), n_eigen=int(rng.integers(1, 60)))
+    data = oi.serialize(m)
+    model = ModalModel.from_bytes(data)
+    check_fields(model, m)
+    ours = model.to_bytes()
+    assert ours == data
+    assert oi.parses_to(m, ours) == 1  # the reference's loader reads our bytes back to the same ModalModelData
+
+
+def test_bad_modal_data_is_rejected():
+    with open(os.path.join(GOLDEN, "model_3.modal"), "rb") as f:
+        data = f.read()
+    for bad in (data[:-3], data + b"\0", data[:40]):
+        with pytest.raises(MeError):
+            ModalModel.from_bytes(bad)
+
+
+def test_modal_solve_json_matches_the_tool():
+    """tests/ModalSolveTool.cpp:84-123 restated: key order, decayRates in float, mode-major shapes, relabelled triangles."""
+    with open(os.path.join(GOLDEN, "model_21.modal"), "rb") as f:
+        model = ModalModel.from_bytes(f.read())
+    r = model.result
+    n_points = len(r.positions)
+    # a parsed file carries no SamplePointOfExcitation: triangles cannot be relabelled, so an index is an error ...
+    with pytest.raises(MeError):
+        model.solve_json([0, 1, 2])
+    text = model.solve_json()
+    d = json.loads(text)
+    assert list(d) == ["frequencies", "decayRates", "positions", "shapes", "indices", "mass", "centerOfMass", "inertiaDiagonal"]
+    f32 = np.float32
+    np.testing.assert_array_equal(np.asarray(d["frequencies"], f32), r.freqs)  # shortest round-trip text: exact float32 back
+    want_rates = np.where(r.t60s > 0, f32(LN1000) / r.t60s, f32(0)).astype(f32)
+    np.testing.assert_array_equal(np.asarray(d["decayRates"], f32), want_rates)
+    np.testing.assert_array_equal(np.asarray(d["positions"], f32), r.positions)
+    np.testing.assert_array_equal(np.asarray(d["shapes"], f32).reshape(len(r.freqs), n_points, 3), np.transpose(r.shapes, (1, 0, 2)))
+    assert d["indices"] == [] and d["mass"] == r.mass_props["mass"]
+    np.testing.assert_array_equal(np.asarray(d["centerOfMass"], f32), np.array(r.mass_props["center_of_mass"], f32))
+    # ... and the KHR_audio_rigid_bodies view of it feeds the synthesis bank with the model's own T60s back (to rounding)
+    bank = bank_modes(khr_modal_model(text))
+    np.testing.assert_allclose(bank["t60s"], r.t60s, rtol=2e-7)
+    np.testing.assert_array_equal(bank["shapes"], r.shapes)

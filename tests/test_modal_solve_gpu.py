@@ -162,3 +162,35 @@ def test_mismatched_seed_falls_back_to_the_cold_path():
         r = mesh2modes(points, tets, "Steel", points[:4].astype(np.float32), config=cfg, seed_basis=seed)
         assert r.status == 0 and r.profile["op_applications"] == cold.profile["op_applications"]
         np.testing.assert_array_equal(r.freqs, cold.freqs)
+
+
+def test_solved_model_round_trips_through_the_interchange_formats():
+    """A fresh solve -> `.modal` bytes -> parse gives the same model back; the MeshEditorModalSolve JSON relabels the mesh's
+    triangles onto the sample points (tests/ModalSolveTool.cpp:84-96). Byte parity of the format itself: test_interchange_cpu.py."""
+    import json
+
+    from mesheditor_b200 import solver_config
+    from mesheditor_b200.interchange import ModalModel
+
+    points, tets = om.kuhn_block(6, 3, 2, (0.3, 0.15, 0.1))
+    excite = np.vstack([points[:12], points[3:5]]).astype(np.float32)  # the last two repeat earlier points: they merge
+    model = ModalModel.solve(points, tets, "Steel", excite, config=solver_config(num_modes=12, num_fem_modes=20, element_order=2), vertices=np.arange(12), solved_num_modes=12,
+                             tet_positions=points[:5], tet_edge_indices=[0, 1, 1, 2], solved_vertices=np.arange(14), tet_inputs_hash=12345)
+    r = model.result
+    assert not r.empty and len(r.sample_point_of_excitation) == 14 and len(r.positions) == 12
+    back = ModalModel.from_bytes(model.to_bytes())
+    for a, b in ((back.result.freqs, r.freqs), (back.result.t60s, r.t60s), (back.result.shapes, r.shapes), (back.result.positions, r.positions), (back.result.eigenvalues, r.eigenvalues),
+                 (back.result.summary_shapes, r.summary_shapes), (back.vertices, model.vertices), (back.solved_vertices, model.solved_vertices), (back.tet_positions, model.tet_positions)):
+        np.testing.assert_array_equal(a, b)
+    assert back.result.mass_props == r.mass_props and back.tet_inputs_hash == 12345 and back.solved_num_modes == 12
+    assert back.to_bytes() == model.to_bytes()
+    triangles = [0, 1, 2, 3, 12, 4, 5, 6, 13]  # excitation 12 is point 3 (degenerate with corner 3), 13 is point 4
+    d = json.loads(model.solve_json(triangles))
+    sp = r.sample_point_of_excitation
+    want = []
+    for t in range(0, len(triangles), 3):
+        a, b, c = (int(sp[i]) for i in triangles[t:t + 3])
+        if len({a, b, c}) == 3:
+            want += [a, b, c]
+    assert d["indices"] == want and len(want) == 6
+    np.testing.assert_array_equal(np.asarray(d["frequencies"], np.float32), r.freqs)
