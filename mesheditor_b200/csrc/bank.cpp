@@ -772,13 +772,20 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
         }
         const uint32_t span_frames = span_end - span_begin;
         scheduled.clear();
-        // Retirement frames of the in-flight impacts, soonest first, for the MaxImpacts cap (ActivateImpact :29).
-        std::priority_queue<uint32_t, std::vector<uint32_t>, std::greater<>> retire;
+        // In-flight impacts for the MaxImpacts cap (ActivateImpact :29). Impacts retire on block boundaries and events arrive
+        // in frame order, so a count per retirement block and a cursor replace a heap of retirement frames.
+        std::vector<uint32_t> retire_in_block(size_t(span_frames) / block_frames + 2, 0);
+        uint32_t retire_cursor = 0, in_flight = 0;
+        scheduled.reserve(Impacts.size() + (n_events - next_event) + ring.size());
+        const auto note_retirement = [&](const ScheduledImpact &s) {
+            ++in_flight;
+            if (!s.Survives) ++retire_in_block[(uint64_t(s.End) + block_frames - 1) / block_frames];
+        };
         const auto admit = [&](const HostImpact &im, uint32_t start) {
             ScheduledImpact s{.AtStart = im, .AtEnd = im, .Start = start, .End = 0, .Survives = false};
             Schedule(s, block_frames, span_frames);
             scheduled.push_back(s);
-            retire.push(s.Survives ? UINT32_MAX : s.End);
+            note_retirement(s);
         };
         for (const auto &im : Impacts) admit(im, 0);
         Impacts.clear();
@@ -786,16 +793,17 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
             if (e.object >= n_obj) return; // DrainEvents :71
             if (e.kind == 0) {
                 if (!(e.pulse_step > 0)) return;
-                while (!retire.empty() && retire.top() <= start) retire.pop();
-                if (retire.size() >= MaxImpacts) return;
+                for (; retire_cursor <= start / block_frames; ++retire_cursor) in_flight -= retire_in_block[retire_cursor]; // retired at or before `start`
+                if (in_flight >= MaxImpacts) return;
                 admit(MakeImpact(e), start);
             } else if (e.kind == 1) {
                 // Only ever at the first frame of a span: nothing of this span has been rendered yet.
                 const size_t before = scheduled.size();
                 std::erase_if(scheduled, [&](const ScheduledImpact &s) { return s.AtStart.Object == e.object; });
                 if (scheduled.size() != before) {
-                    retire = {};
-                    for (const auto &s : scheduled) retire.push(s.Survives ? UINT32_MAX : s.End);
+                    std::fill(retire_in_block.begin(), retire_in_block.end(), 0u);
+                    retire_cursor = 0, in_flight = 0;
+                    for (const auto &s : scheduled) note_retirement(s);
                 }
                 ResetObjectOnDevice(e.object, true, stream);
             }
