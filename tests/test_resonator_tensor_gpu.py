@@ -146,3 +146,65 @@ def test_seeded_walk_of_a_small_bank(oracle_cls, t60, shape_scale, expect_fallba
     assert stats["time_segments"] == (1 if expect_fallback else 5)
     assert rel_err(out, ref) <= TOL
     assert_same_status(o, g, n_obj)
+
+
+@pytest.mark.parametrize("oracle_cls", oracles())
+@pytest.mark.parametrize("rate,block", [(96000.0, 256), (48000.0, 1024), (44100.0, 2048)])
+def test_clicks_silence_and_other_block_sizes(oracle_cls, rate, block):
+    """Click-carrying impacts (they survive across blocks until their filter rings out), a Silence event in the middle
+    of the timeline (it cuts the timeline into two spans and clears one object), other sample rates and block lengths."""
+    from mesheditor_b200 import silence_event
+
+    rng = np.random.default_rng(23)
+    n_obj, blocks = 6, 48
+    modes = orc.make_modes(80, 2000.0, 50.0)
+    o, g = build_pair(oracle_cls, n_obj, modes, rate)
+    g.set_render_path(2)
+    click = orc.RefScene(rate, 1).click_filter(0.05, 4.0 / 3.0 * np.pi * 0.05**3, 1.0, rate) if orc.have_ref() else (0.0001865190570242703, -1.716620683670044, 0.7520560026168823)
+    events, frames = [], []
+    for b in range(blocks):
+        for obj in range(n_obj):
+            if b == 0 or rng.random() < 0.06:
+                step = np.float32(1.0 / rng.integers(40, 900))
+                events.append(orc.Event(0, obj, int(rng.integers(0, 4)), float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1)), float(rng.uniform(0.2, 1)), step, 2 * step, 0.5 * rate, *click))
+                frames.append(b * block)
+        if b == blocks // 2:
+            events.append(orc.Event(1, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0))
+            frames.append(b * block)
+    total = blocks * block
+    ref = oracle_timeline(o, events, frames, total, block)
+    me_events = [silence_event(e.Object) if e.Kind == 1 else to_me(e) for e in events]
+    out = g.render_offline(me_events, frames, total, block)
+    assert g.stats()["tensor_windows"] >= 1
+    assert rel_err(out, ref) <= TOL
+    assert o.active_impacts() == g.active_impacts()
+    assert_same_status(o, g, n_obj)
+
+
+def test_object_larger_than_a_chunk_group():
+    """2100 modes = 263 chunks: the object straddles chunk groups (no culling applies to it, as in the sample loop)."""
+    modes = orc.make_modes(2100, 9000.0, 20.0)
+    o, g = build_pair(orc.PortBank, 2, modes)
+    g.set_render_path(2)
+    rng = np.random.default_rng(4)
+    events, frames = timeline(rng, 2, 70, 0.03)
+    ref = oracle_timeline(o, events, frames, 70 * 512)
+    out = g.render_offline([to_me(e) for e in events], frames, 70 * 512, 512)
+    assert g.stats()["tensor_windows"] >= 1
+    assert rel_err(out, ref) <= TOL
+
+
+def test_automatic_path_choice():
+    """Long spans of a large bank go to the tensor-core form, block-sized real-time calls stay on the sample loop."""
+    modes = orc.make_modes(500, 10000.0, 100.0)
+    g = gpu_bank()
+    for _ in range(40):
+        g.add_modes(modes)
+    g.install()
+    ev = [to_me(orc.impact_event(v, 1.0, v % 4)) for v in range(40)]
+    g.render_offline(ev, [0] * 40, 64 * 32768, 512)  # 10 groups x 64 tiles
+    assert g.stats()["tensor_windows"] >= 1
+    g.render_blocks(2)
+    assert g.stats()["tensor_windows"] == 0
+    g.render_offline(ev, [0] * 40, 20 * 512, 512)  # too short to fill the SMs
+    assert g.stats()["tensor_windows"] == 0
