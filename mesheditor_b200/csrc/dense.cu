@@ -1,6 +1,8 @@
 // Tall-skinny dense kernels for the Lanczos basis. See dense.h. All are HBM-bound streams over V except TallGemm.
 #include "dense.h"
 
+#include <algorithm>
+
 namespace me {
 namespace {
 constexpr int kThreads = 256;
@@ -161,12 +163,13 @@ __global__ void __launch_bounds__(128) TallGemmNarrowKernel(const double *__rest
 
 // partial[split][a_pad x 8] of X[:, :a]^T Y[:, :c (<= 8)]: CTA = 32 columns of X x one row range; its 4 warps take
 // alternate 4-row steps and are reduced in shared memory.
-constexpr uint32_t kGramSplits = 64;
-__global__ void __launch_bounds__(128) GramNarrowPartialKernel(const double *__restrict__ X, size_t n, uint32_t a, const double *__restrict__ Y, uint32_t c, double *__restrict__ partial, uint32_t a_pad) {
+// The row range is split so that (column groups x splits) fills the SMs several times over even when X is narrow.
+constexpr uint32_t kGramMinSplits = 64, kGramMaxSplits = 512;
+__global__ void __launch_bounds__(128) GramNarrowPartialKernel(const double *__restrict__ X, size_t n, uint32_t a, const double *__restrict__ Y, uint32_t c, double *__restrict__ partial, uint32_t a_pad, uint32_t splits) {
     __shared__ double part[4 * 32 * kNarrow];
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, fr = lane >> 2, fk = lane & 3;
     const uint32_t col0 = blockIdx.x * 32, split = blockIdx.y;
-    size_t chunk = (n + kGramSplits - 1) / kGramSplits;
+    size_t chunk = (n + splits - 1) / splits;
     chunk = (chunk + 127) & ~size_t(127); // whole CTA iterations (4 warps x 8 steps x 4 rows)
     const size_t begin = split * chunk, end = min(n, begin + chunk);
     double acc[4][2]{};
@@ -196,14 +199,17 @@ __global__ void __launch_bounds__(128) GramNarrowPartialKernel(const double *__r
     for (uint32_t idx = t; idx < 32 * kNarrow; idx += 128)
         partial[(size_t(split) * a_pad + col0) * kNarrow + idx] = (part[idx] + part[256 + idx]) + (part[512 + idx] + part[768 + idx]);
 }
-__global__ void GramNarrowFinalKernel(const double *__restrict__ partial, uint32_t a, uint32_t c, uint32_t a_pad, double *__restrict__ out, uint32_t ldo) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per output entry: lanes sum every 32nd split, then a shuffle tree (fixed order, so still deterministic).
+__global__ void GramNarrowFinalKernel(const double *__restrict__ partial, uint32_t a, uint32_t c, uint32_t a_pad, double *__restrict__ out, uint32_t ldo, uint32_t splits) {
+    const uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (idx >= a * kNarrow) return;
     const uint32_t col = idx / kNarrow, w = idx % kNarrow;
     if (w >= c) return;
     double v = 0;
-    for (uint32_t s = 0; s < kGramSplits; ++s) v += partial[(size_t(s) * a_pad + col) * kNarrow + w];
-    out[col + size_t(w) * ldo] = v;
+    for (uint32_t s = lane; s < splits; s += 32) v += partial[(size_t(s) * a_pad + col) * kNarrow + w];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[col + size_t(w) * ldo] = v;
 }
 } // namespace
 
@@ -236,11 +242,13 @@ void TallGemm(DenseWorkspace &ws, const double *V, size_t n, uint32_t m, const d
 void Gram(DenseWorkspace &ws, const double *X, size_t n, uint32_t a, const double *Y, uint32_t c, double *out, uint32_t ldo, cudaStream_t s) {
     if (a == 0 || c == 0) return;
     const uint32_t a_pad = (a + 31) & ~31u;
-    ws.GramPartial.Reserve(size_t(kGramSplits) * a_pad * kNarrow);
+    const uint32_t groups = a_pad / 32;
+    const uint32_t splits = std::min(kGramMaxSplits, std::max(kGramMinSplits, (6 * 148 + groups - 1) / groups));
+    ws.GramPartial.Reserve(size_t(splits) * a_pad * kNarrow);
     for (uint32_t c0 = 0; c0 < c; c0 += kNarrow) {
         const uint32_t cw = c - c0 < uint32_t(kNarrow) ? c - c0 : uint32_t(kNarrow);
-        GramNarrowPartialKernel<<<dim3(a_pad / 32, kGramSplits), 128, 0, s>>>(X, n, a, Y + size_t(c0) * n, cw, ws.GramPartial.Ptr, a_pad);
-        GramNarrowFinalKernel<<<(a * kNarrow + 255) / 256, 256, 0, s>>>(ws.GramPartial.Ptr, a, cw, a_pad, out + size_t(c0) * ldo, ldo);
+        GramNarrowPartialKernel<<<dim3(groups, splits), 128, 0, s>>>(X, n, a, Y + size_t(c0) * n, cw, ws.GramPartial.Ptr, a_pad, splits);
+        GramNarrowFinalKernel<<<(a * kNarrow * 32 + 255) / 256, 256, 0, s>>>(ws.GramPartial.Ptr, a, cw, a_pad, out + size_t(c0) * ldo, ldo, splits);
         ws.Launches += 2;
     }
 }
