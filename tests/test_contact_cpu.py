@@ -14,6 +14,8 @@ from make_contact_golden import cases  # noqa: E402
 from mesheditor_b200 import contact as mc  # noqa: E402
 from oracle import contact as oc  # noqa: E402
 
+pytestmark = pytest.mark.usefixtures("built_lib")  # builds libme_modal.so on demand (tests/conftest.py)
+
 GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "strike", "contact.npz"))
 FIELDS = ("jx", "jy", "jz", "pulse_step", "pulse_gamma", "accel_amp", "click_b0", "click_a1", "click_a2")
 

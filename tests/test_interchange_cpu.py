@@ -15,6 +15,8 @@ from mesheditor_b200 import MeError  # noqa: E402
 from mesheditor_b200.interchange import LN1000, ModalModel, bank_modes, khr_modal_model  # noqa: E402
 from oracle import interchange as oi  # noqa: E402
 
+pytestmark = pytest.mark.usefixtures("built_lib")  # builds libme_modal.so on demand (tests/conftest.py)
+
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "interchange")
 
 
