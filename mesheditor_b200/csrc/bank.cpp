@@ -17,7 +17,7 @@ constexpr float Ln1000 = 3 * std::numbers::ln10_v<float>;
 constexpr float Pi = std::numbers::pi_v<float>;
 
 constexpr size_t PartialBudgetBytes = size_t(8) << 30; // per-warp partial mixes kept in HBM per launch window (of 180 GB)
-// Tensor-core form: a tile is 128 time blocks of 128 frames; the state stages of a launch window stay under this budget.
+// Tensor-core form: a tile is 128 time blocks of 256 frames; the state stages of a launch window stay under this budget.
 constexpr uint32_t TensorBlocksPerTile = 128;
 constexpr uint32_t TensorTileFrames = TensorBlocksPerTile * kTmBlock;
 constexpr size_t TensorStateBudgetBytes = size_t(40) << 30; // 10 s of 1024 x 500 modes is 31.5 GB: one window (of 180 GB)
@@ -422,7 +422,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     CallImpacts.resize(n);
     CallTails.resize(n);
     CallPulseWarps.clear();
-    // The tensor-core form needs RenderModal blocks made of whole 128-frame time blocks and tiles made of whole
+    // The tensor-core form needs RenderModal blocks made of whole 256-frame time blocks and tiles made of whole
     // RenderModal blocks, and pays off once (chunk groups x tiles) fills the SMs.
     const uint32_t groups = NChunks / kTmGroupChunks;
     const bool tensor_possible = groups > 0 && block_frames % kTmBlock == 0 && TensorTileFrames % block_frames == 0 && !SpeculationFailed;
@@ -626,7 +626,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
             bool tensor_window = tensor_span && !SpeculationFailed;
             uint32_t segments = 1;
             if (tensor_window) {
-                // The walk kernel steps every chunk through the window 128 frames at a time (culling applied exactly as
+                // The walk kernel steps every chunk through the window one 256-frame time block at a time (culling applied exactly as
                 // it goes) and writes the block-start states; the tcgen05 kernel turns them into per-group-set mixes.
                 const uint32_t tiles = (wf + TensorTileFrames - 1) / TensorTileFrames;
                 DWalkStates.Reserve(size_t(tiles) * groups * TmStateTileFloats(TensorBlocksPerTile));

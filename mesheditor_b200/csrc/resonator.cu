@@ -4,7 +4,11 @@
 // one-pole  z[n] = c z[n-1] + e[n],  e[n] = sum over the object's live impacts of force[n] * gain, and the
 // object's sample is  sum_modes (pIm*Im z + pRe*Re z) * OutGain*ListenerGain.
 //
-// How it is laid out for B200 (the path is bound by FP32 issue, not by HBM: SURVEY.md F9):
+// Two forms share this file's kernels: the FP32 sample loop below, and the tensor-core form, in which
+// the same ResonatorKernel (template parameter Walk) advances a whole 256-frame time block per step and only writes
+// the block-start states that tensor_mix.cu turns into samples (plus PowerTableKernel for its constant operand).
+//
+// How the sample loop is laid out for B200 (this form is bound by FP32 issue, not by HBM: SURVEY.md F9):
 //   * ResonatorKernel: one thread owns one 8-mode chunk (the reference's Lanes) in registers for a whole time
 //     segment, so a warp covers 256 modes and reads each per-mode column as two coalesced float4 per thread.
 //   * The output rotation is folded into the state: w = z*(pIm + i pRe)*gain obeys the same recurrence and the

@@ -90,7 +90,7 @@ struct RenderPlan {
     uint32_t *Speculation;
     uint32_t Debug;
     // Tensor-core form (tensor_mix.cuh): the walk kernel (one segment: sequential in time, so culling is exact) writes
-    // the block-start state of every 128-frame time block as rows of States[tile][chunk group][head,tail][block][4096].
+    // the block-start state of every 256-frame time block (kTmBlock) as rows of States[tile][chunk group][head,tail][block][4096].
     float *WalkStates;
     uint32_t WalkBlocksPerTile;
 };
@@ -119,10 +119,10 @@ void LaunchSegmentScan(const BankView &, const RenderPlan &, float *seg_re, floa
 void LaunchResonatorKernel(const BankView &, const RenderPlan &, int steps, cudaStream_t, LaunchCounter &);
 uint32_t ResonatorRows(uint32_t n_chunks);
 // Tensor-core form, producer side: the same per-chunk walk over RenderModal blocks (culling, increments, final state)
-// as the resonator kernel, but advancing 128 frames per step with c^128 and writing the state stages instead of samples.
+// as the resonator kernel, but advancing one 256-frame time block per step with c^256 and writing the state stages instead of samples.
 void LaunchStateWalkKernel(const BankView &, const RenderPlan &, cudaStream_t, LaunchCounter &);
-// Power stages of the installed tuning: c^1..c^128 of every mode (FP64 products of the float coefficient), split into
-// TF32 head + FP32 tail, in the stage layout of tensor_mix.cuh. powers: [NChunks/256][128 stages][2][128*32] floats.
+// Power stages of the installed tuning: c^1..c^256 of every mode (FP64 products of the float coefficient), split into
+// TF32 head + FP32 tail, in the stage layout of tensor_mix.cuh. powers: [NChunks/256][256 stages][2][256*16] floats.
 void LaunchPowerTableKernel(const BankView &, float *powers, cudaStream_t, LaunchCounter &);
 // out[n] = sum of the partial rows in fixed order (the reference sums renderer buffers in a fixed order, :553-555)
 // plus the pulse rows overlapping n.
