@@ -152,7 +152,7 @@ def workload_config(n_gpus):
         "workload": f"BASELINE.json configs[4]: polyphonic resonator bank {VOICES} voices x {MODES} modes x {SECONDS:g} s at {RATE:g} Hz, strike per voice at frame 0 + 2 Hz Poisson re-strikes (MT19937 12345), 512-frame blocks",
         "voices": VOICES, "modes_per_voice": MODES, "frames": int(SECONDS * RATE), "sample_rate": RATE, "block_frames": BLOCK,
         "parallelism": f"voices sharded over {n_gpus} GPU(s), NCCL all-reduce of the mono mix" if n_gpus > 1 else "single GPU",
-        "l2_policy": "working set > L2: one step writes and reads 16 GB of block-start states (tensor-core form) or 3.9 GB of per-warp partial mixes (sample loop); nothing is reused across steps",
+        "l2_policy": "working set > L2: one step writes and reads 8 GB of block-start states (tensor-core form) or 3.9 GB of per-warp partial mixes (sample loop); nothing is reused across steps",
     }
 
 
@@ -302,19 +302,19 @@ def run_ours(args):
             groups = -(-(hi - lo) // (256 // chunks))
             tiles = -(-frames // 32768)
             issued_flops = 3 * 2.0 * 256 * 128 * 4096 * groups * tiles
-            walk_bytes = 2.0 * 4096 * 4 * groups * -(-frames // 256)
+            walk_bytes = 4096 * 4.0 * groups * -(-frames // 256)
             m_ms, w_ms = sum(mix_ms) / len(mix_ms), sum(walk_ms) / len(walk_ms)
             tf32_peak = pk.get("bf16_tflops", 2250.0) / 2
             roofline = {
-                "bound": "tensor", "kernel": "TensorMixKernel<128,4> (tcgen05.mma kind::tf32, 3xTF32 split, FP32 register folds)", "achieved": issued_flops / (m_ms * 1e-3) / 1e12, "peak": tf32_peak,
+                "bound": "tensor", "kernel": "TensorMixKernel<128,4> (tcgen05.mma kind::tf32, 3xTF32 split in the kernel, FP32 register folds)", "achieved": issued_flops / (m_ms * 1e-3) / 1e12, "peak": tf32_peak,
                 "unit": "TFLOP/s", "frac": issued_flops / (m_ms * 1e-3) / 1e12 / tf32_peak, "traffic": tensor_traffic("mix"), "kernel_ms_per_launch": m_ms, "launches_per_step": stats["tensor_windows"],
                 "issued_flops_per_step": issued_flops, "share_of_step": m_ms / ms_per_step,
                 "peak_source": ("half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate; nominal 1125)" if "bf16_tflops" in pk else "nominal dense TF32 1125 TFLOP/s"),
                 "reference_fma_equivalent": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (m_ms * 1e-3) / 1e12,
-                "note": "the kernel streams 2 operand images (power stages from L2, state stages from HBM) at %.1f TB/s into shared memory; that ingest, not the MMA rate, bounds it" % ((issued_flops / (3 * 2.0 * 256 * 128 * 16)) * 49152 / (m_ms * 1e-3) / 1e12),
+                "note": "the kernel streams 2 operand images (power stages from L2, state stages from HBM) at %.1f TB/s into shared memory; that ingest, not the MMA rate, bounds it" % ((issued_flops / (3 * 2.0 * 256 * 128 * 16)) * 40960 / (m_ms * 1e-3) / 1e12),
             }
             roofline_extra = {
-                "roofline_walk": {"bound": "hbm", "kernel": "ResonatorKernel<1,2,true> (state walk: c^256 steps, TF32 head/tail rows)", "achieved": walk_bytes / (w_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "roofline_walk": {"bound": "hbm", "kernel": "ResonatorKernel<1,2,true> (state walk: c^256 steps, FP32 state rows)", "achieved": walk_bytes / (w_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                   "frac": walk_bytes / (w_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": tensor_traffic("walk"), "kernel_ms_per_launch": w_ms, "algorithmic_bytes": walk_bytes, "share_of_step": w_ms / ms_per_step, "peak_source": pk_kind},
                 "fp32_pipe_equivalent": {"note": "the same mode-samples per second on the FP32 pipe would need this multiple of the measured scalar-FFMA ceiling (reference loop: 7 lane-ops per mode-sample; this repo's sample loop: 2.75)",
                                          "reference_loop": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3) / fma_peak, "sample_loop": achieved / fma_peak, "ffma_peak_tlane_ops": fma_peak / 1e12},

@@ -156,7 +156,7 @@ __device__ __forceinline__ float SumRow(const float *rows, uint32_t lane) {
     return a + b;
 }
 
-// TF32 head of x (round to nearest) and the FP32 tail x - head: the two pieces of a 3xTF32 operand.
+// TF32 head of x (round to nearest); x - head is the FP32 tail: the two pieces of a 3xTF32 operand.
 __device__ __forceinline__ float Tf32Head(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -321,8 +321,8 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
             // store instruction covers 512 contiguous bytes.
             const uint32_t nb = plan.WalkBlocksPerTile;
             float4 *rows = reinterpret_cast<float4 *>(plan.WalkStates + size_t(blockIdx.x) * TmStateTileFloats(nb)) + warp * 128 + lane;
-            const size_t tile_stride = size_t(gridDim.x) * TmStateTileFloats(nb) / 4, half_stride = size_t(nb) * kTmGroupK / 4;
-            float4 *exchange = reinterpret_cast<float4 *>(transposed_storage) + warp * 256;
+            const size_t tile_stride = size_t(gridDim.x) * TmStateTileFloats(nb) / 4;
+            float4 *exchange = reinterpret_cast<float4 *>(transposed_storage) + warp * 128;
             const uint32_t put = lane * 4, put_swizzle = (lane >> 1) & 3;
             const bool audible = rendered && out_scale != 0.f;
             for (uint32_t t = pos; t < block_end;) {
@@ -336,22 +336,13 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                 const uint32_t block_index = t / kTmBlock;
                 float4 *at = rows + size_t(block_index / nb) * tile_stride + size_t(block_index % nb) * (kTmGroupK / 4);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 head = {0.f, 0.f, 0.f, 0.f}, tail = head;
-                    if (audible) {
-                        head = {Tf32Head(w.Im[i].x), Tf32Head(w.Re[i].x), Tf32Head(w.Im[i].y), Tf32Head(w.Re[i].y)};
-                        tail = {w.Im[i].x - head.x, w.Re[i].x - head.y, w.Im[i].y - head.z, w.Re[i].y - head.w};
-                    }
-                    exchange[put + (i ^ put_swizzle)] = head;
-                    exchange[128 + put + (i ^ put_swizzle)] = tail;
-                }
+                for (int i = 0; i < 4; ++i) // (Im, Re) of the chunk's mode pairs: reduction elements 2m, 2m+1 (tensor_mix.cuh)
+                    exchange[put + (i ^ put_swizzle)] = audible ? float4{w.Im[i].x, w.Re[i].x, w.Im[i].y, w.Re[i].y} : float4{0.f, 0.f, 0.f, 0.f};
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t from = 8 * j + (lane >> 2); // the chunk-lane whose piece lands at position 32*j + lane
-                    const uint32_t get = from * 4 + ((lane & 3) ^ ((from >> 1) & 3));
-                    at[32 * j] = exchange[get];
-                    at[half_stride + 32 * j] = exchange[128 + get];
+                    at[32 * j] = exchange[from * 4 + ((lane & 3) ^ ((from >> 1) & 3))];
                 }
                 __syncwarp();
                 if (rendered) {
@@ -797,7 +788,7 @@ void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int ste
 void LaunchStateWalkKernel(const BankView &bank, const RenderPlan &plan, cudaStream_t stream, LaunchCounter &counter) {
     if (bank.NChunks == 0 || plan.Frames == 0) return;
     const dim3 grid(bank.NChunks / kBlockThreads, plan.NSegments);
-    ResonatorKernel<1, 2, true><<<grid, kBlockThreads, kWarpsPerBlock * 256 * sizeof(float4), stream>>>(bank, plan);
+    ResonatorKernel<1, 2, true><<<grid, kBlockThreads, kWarpsPerBlock * 128 * sizeof(float4), stream>>>(bank, plan);
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
 }

@@ -7,8 +7,8 @@
 // 553-555) happen in the tensor-core accumulator. P (powers of the coefficients) is fixed by the tuning; W (block-start
 // states) costs 4 FMAs and 16 bytes of HBM per mode per 256 samples: the block length trades the size of P (L2-resident)
 // against the HBM traffic of W, which is what bounds both kernels.  FP32 accuracy comes from the 3xTF32 split: both operands are stored
-// as a TF32 head and an FP32 tail, and head*head + head*tail + tail*head accumulate in FP32 (the dropped tail*tail
-// term is 2^-22 relative).
+// as a TF32 head and an FP32 tail (P once per tuning, W inside the mix kernel), and head*head + head*tail + tail*head
+// accumulate in FP32 (the dropped tail*tail term is 2^-22 relative).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -27,14 +27,15 @@ constexpr uint32_t kTmStagesPerGroup = kTmGroupChunks * 8 * 2 / kTmKChunk; // 25
 //   element (row r, reduction index k) of a [256 x 16] half lives at byte (k/4)*4096 + (r/8)*128 + (r%8)*16 + (k%4)*4
 // and a stage is [head half][tail half]. Reduction index 2*m holds Re(c^(j+1)) in P and Im w in W; 2*m+1 holds
 // Im(c^(j+1)) and Re w, m = mode inside the group (0..2047).
-// States are written by the walk kernel as plain row-major matrices, one row of the group's 4096 reduction elements
+// States are written by the walk kernel as plain FP32 row-major matrices, one row of the group's 4096 reduction elements
 // per time block, so a warp of chunk-threads stores 2 KB contiguous per step:
-//   States[tile][group][half (0 head, 1 tail)][time block][4096]
-// and a stage (16 reduction elements of all blocks, both halves) reaches shared memory by one 4-D TMA tile copy that
-// applies the 64-byte swizzle the UMMA descriptor expects.
+//   States[tile][group][time block][4096]
+// A stage (16 reduction elements of all blocks) reaches shared memory raw by one 3-D TMA tile copy; two splitter warps of
+// the mix kernel turn it into the TF32 head and FP32 tail halves in the 64-byte-swizzled layout the UMMA descriptor
+// expects. Splitting in the kernel instead of in the walk halves the HBM traffic of the states (8 B per mode per block).
 __host__ __device__ constexpr size_t TmPowerStageFloats() { return size_t(2) * kTmBlock * kTmKChunk; }
 constexpr uint32_t kTmGroupK = kTmGroupChunks * 8 * 2; // 4096 reduction elements per group
-__host__ __device__ constexpr size_t TmStateTileFloats(uint32_t blocks_per_tile) { return size_t(2) * blocks_per_tile * kTmGroupK; }
+__host__ __device__ constexpr size_t TmStateTileFloats(uint32_t blocks_per_tile) { return size_t(blocks_per_tile) * kTmGroupK; }
 
 struct TensorMixPlan {
     uint32_t Groups;          // chunk groups (reduction ranges of 256 chunk slots)
@@ -44,7 +45,7 @@ struct TensorMixPlan {
     uint32_t BlocksPerTile;   // 128 time blocks (the N extent)
     uint32_t Frames;          // valid frames of the window (the last tile may be ragged)
     const float *Powers;      // [Groups][256 stages] power stages
-    const float *States;      // [Tiles][Groups][2][BlocksPerTile][4096]
+    const float *States;      // [Tiles][Groups][BlocksPerTile][4096]
     float *Partial;           // [Groups * 256 / StagesPerRow][Frames] partial mixes
 };
 

@@ -12,7 +12,7 @@ from mesheditor_b200._lib import check
 groups, tiles, n = int(sys.argv[1]) if len(sys.argv) > 1 else 8, int(sys.argv[2]) if len(sys.argv) > 2 else 37, 128
 rng = np.random.default_rng(1)
 powers = rng.standard_normal(groups * 256 * 2 * 256 * 16, dtype=np.float32)
-states = rng.standard_normal(tiles * groups * 2 * n * 4096, dtype=np.float32)
+states = rng.standard_normal(tiles * groups * n * 4096, dtype=np.float32)
 frames = tiles * n * 256
 gpr = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 out = np.zeros((groups // gpr, frames), np.float32)
