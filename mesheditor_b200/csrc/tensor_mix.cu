@@ -4,9 +4,10 @@
 // 0-127 and 128-255 of every block) in tensor memory, fed stage by stage (16 reduction elements = 8 modes) through a
 // ring of shared-memory buffers.
 //   warp 0 (one lane): producer. Per stage a bulk copy (power stage, already a shared-memory image) and a 3-D TMA tile
-//                      copy (16 reduction elements x all time blocks of the row-major FP32 states) into a raw ring.
-//   warps 2-3:         splitters. Raw state rows -> TF32 head + FP32 tail in the 64-byte-swizzled K-major layout of the
-//                      stage; they and the power copy complete the stage's "full" mbarrier.
+//                      copy (16 reduction elements x all time blocks of the row-major FP32 states, 64-byte swizzle)
+//                      straight into the stage's head half: kind::tf32 reads the top 19 bits, so FP32 rows are the head.
+//   warps 2-3:         splitters. tail = x - truncated(x) into the tail half; they and the power copy complete the
+//                      stage's "full" mbarrier.
 //   warp 1 (one lane): issues tcgen05.mma kind::tf32, three per 8-wide reduction step and accumulator (head*head,
 //                      head*tail, tail*head), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
 //   warps 4-11:        epilogue, one warp per (TMEM lane quarter, block half). tcgen05.ld of the accumulator (lane =
@@ -59,11 +60,7 @@ __device__ __forceinline__ void TensorCopy3(void *dst, const CUtensorMap *map, u
                  "r"(c1), "r"(c2), "r"(SmemAddr(bar))
                  : "memory");
 }
-__device__ __forceinline__ float Tf32HeadOf(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
+__device__ __forceinline__ float Tf32Truncated(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); } // what kind::tf32 reads of x
 
 // Shared-memory matrix descriptor, K-major, 64-byte swizzle: rows of 64 bytes (16 TF32), 8-row groups 512 bytes apart.
 __device__ __forceinline__ uint64_t SwizzledDescriptor(uint32_t smem_addr) {
@@ -120,13 +117,12 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
     constexpr uint32_t kStateHalfBytes = N * kTmKChunk * 4;
     constexpr uint32_t kPowerBytes = 2 * kPowerHalfBytes, kStateBytes = 2 * kStateHalfBytes;
     constexpr uint32_t kStageBytes = kPowerBytes + kStateBytes;
-    constexpr uint32_t kRawBytes = N * kTmKChunk * 4; // a stage's FP32 state rows before the split
+    constexpr uint32_t kRawBytes = N * kTmKChunk * 4; // a stage's FP32 state rows: they ARE the head operand (the tensor core ignores the low 13 mantissa bits)
     constexpr uint32_t kSteps = kTmKChunk / 8; // MMAs of K = 8 per stage and operand pair
     static_assert(kTmKChunk == 16, "a state row is one 64-byte swizzle atom");
     extern __shared__ __align__(1024) uint8_t stage_storage_raw[];
     // The swizzle is a function of the shared-memory address: the ring starts on a 1024-byte boundary.
     uint8_t *stage_storage = stage_storage_raw + ((1024u - (SmemAddr(stage_storage_raw) & 1023u)) & 1023u);
-    uint8_t *raw_storage = stage_storage + size_t(Stages) * kStageBytes;
     __shared__ __align__(8) uint64_t full_bar[Stages], raw_bar[Stages], empty_bar[Stages], accum_full[2], accum_empty[2];
     __shared__ uint32_t tmem_base_slot;
 
@@ -159,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
                 if (round) BarrierWait(&empty_bar[s], (round - 1) & 1);
                 uint8_t *stage = stage_storage + size_t(s) * kStageBytes;
                 BarrierExpectTx(&raw_bar[s], kRawBytes);
-                TensorCopy3(raw_storage + size_t(s) * kRawBytes, &states_map, ((first_stage + k) % kTmStagesPerGroup) * kTmKChunk, 0, tile * plan.Groups + (first_stage + k) / kTmStagesPerGroup, &raw_bar[s]);
+                TensorCopy3(stage, &states_map, ((first_stage + k) % kTmStagesPerGroup) * kTmKChunk, 0, tile * plan.Groups + (first_stage + k) / kTmStagesPerGroup, &raw_bar[s]);
                 BarrierExpectTx(&full_bar[s], kPowerBytes);
                 BulkCopy(stage + kStateBytes, powers + size_t(k) * kPowerBytes, kPowerBytes, &full_bar[s]);
             }
@@ -201,28 +197,24 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
             }
         }
     } else if (warp < 4) {
-        // Splitters: thread wt owns time blocks (rows) wt and wt + 64 of every stage. A raw row is 64 bytes = four 16-byte
-        // pieces; piece order and the swizzled destination are chosen so that neither the loads nor the stores of a
-        // quarter-warp meet in a bank.
+        // Splitters: the TMA copy lands the FP32 state rows in the head half of the stage, already in the swizzled K-major
+        // layout. kind::tf32 reads only the top 19 bits of each element, i.e. the head is the TRUNCATED value, so the tail is
+        // x - trunc(x), written at the same offsets of the tail half. Thread wt owns rows wt and wt + 64; the piece order
+        // keeps the loads and stores of a quarter-warp in different banks.
         static_assert(N == 128, "two rows per splitter thread");
         const uint32_t wt = (warp - 2) * 32 + lane;
         for (uint32_t k = 0; k < n_stages; ++k) {
             const uint32_t s = k % Stages, round = k / Stages;
             BarrierWait(&raw_bar[s], round & 1); // (the producer refilled this slot only after the MMAs of its last use)
-            const uint8_t *raw = raw_storage + size_t(s) * kRawBytes;
             uint8_t *stage = stage_storage + size_t(s) * kStageBytes;
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const uint32_t n = wt + 64 * r, q = (n >> 1) & 3;
-                const uint32_t sigma = (0x1320u >> (4 * q)) & 3; // the permutation (0, 2, 3, 1): sigma(q) and sigma(q) ^ q both run over 0..3
 #pragma unroll
                 for (uint32_t j = 0; j < 4; ++j) {
-                    const uint32_t piece = j ^ sigma;
-                    const float4 v = *reinterpret_cast<const float4 *>(raw + n * 64 + piece * 16);
-                    const float4 head = {Tf32HeadOf(v.x), Tf32HeadOf(v.y), Tf32HeadOf(v.z), Tf32HeadOf(v.w)};
-                    const float4 tail = {v.x - head.x, v.y - head.y, v.z - head.z, v.w - head.w};
-                    const uint32_t at = n * 64 + ((piece ^ q) << 4); // 64-byte swizzle: piece index ^ bits 7-8 of the row offset
-                    *reinterpret_cast<float4 *>(stage + at) = head;
+                    const uint32_t at = n * 64 + ((j ^ q) << 4);
+                    const float4 v = *reinterpret_cast<const float4 *>(stage + at);
+                    const float4 tail = {v.x - Tf32Truncated(v.x), v.y - Tf32Truncated(v.y), v.z - Tf32Truncated(v.z), v.w - Tf32Truncated(v.w)};
                     *reinterpret_cast<float4 *>(stage + kStateHalfBytes + at) = tail;
                 }
             }
@@ -280,13 +272,13 @@ PFN_cuTensorMapEncodeTiled EncodeTiled() {
 
 template<uint32_t N, uint32_t Stages>
 void Launch(const TensorMixPlan &plan, cudaStream_t stream) {
-    constexpr uint32_t bytes = Stages * (2 * kPowerHalfBytes + 2 * N * kTmKChunk * 4 + N * kTmKChunk * 4) + 1024; // stage ring + raw ring + alignment slack
+    constexpr uint32_t bytes = Stages * (2 * kPowerHalfBytes + 2 * N * kTmKChunk * 4) + 1024; // stage ring + alignment slack
     // States[tile*group][block][4096] as a 3-D tensor, innermost first; one box = the raw rows of one stage.
     CUtensorMap map;
     const cuuint64_t dims[3] = {kTmGroupK, N, cuuint64_t(plan.Tiles) * plan.Groups};
     const cuuint64_t strides[2] = {cuuint64_t(kTmGroupK) * 4, cuuint64_t(N) * kTmGroupK * 4};
     const cuuint32_t box[3] = {kTmKChunk, N, 1}, unit[3] = {1, 1, 1};
-    const CUresult r = EncodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(plan.States), dims, strides, box, unit, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    const CUresult r = EncodeTiled()(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(plan.States), dims, strides, box, unit, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) Fail(ME_CUDA_ERROR, "cuTensorMapEncodeTiled failed (%d)", int(r));
     ME_CUDA(cudaFuncSetAttribute(TensorMixKernel<N, Stages>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes))); // per device, cheap

@@ -30,9 +30,10 @@ constexpr uint32_t kTmStagesPerGroup = kTmGroupChunks * 8 * 2 / kTmKChunk; // 25
 // States are written by the walk kernel as plain FP32 row-major matrices, one row of the group's 4096 reduction elements
 // per time block, so a warp of chunk-threads stores 2 KB contiguous per step:
 //   States[tile][group][time block][4096]
-// A stage (16 reduction elements of all blocks) reaches shared memory raw by one 3-D TMA tile copy; two splitter warps of
-// the mix kernel turn it into the TF32 head and FP32 tail halves in the 64-byte-swizzled layout the UMMA descriptor
-// expects. Splitting in the kernel instead of in the walk halves the HBM traffic of the states (8 B per mode per block).
+// A stage (16 reduction elements of all blocks) reaches shared memory by one 3-D TMA tile copy with the 64-byte swizzle the
+// UMMA descriptor expects; the FP32 rows serve as the head operand as they are (kind::tf32 ignores the low 13 mantissa bits)
+// and two splitter warps of the mix kernel write the tail x - truncated(x) next to them. Splitting in the kernel instead of
+// in the walk halves the HBM traffic of the states (8 B per mode per block).
 __host__ __device__ constexpr size_t TmPowerStageFloats() { return size_t(2) * kTmBlock * kTmKChunk; }
 constexpr uint32_t kTmGroupK = kTmGroupChunks * 8 * 2; // 4096 reduction elements per group
 __host__ __device__ constexpr size_t TmStateTileFloats(uint32_t blocks_per_tile) { return size_t(blocks_per_tile) * kTmGroupK; }
