@@ -33,6 +33,8 @@
 
 #include "common.h"
 
+#include <cuda_bf16.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -161,6 +163,11 @@ __device__ __forceinline__ float Tf32Head(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
     return __uint_as_float(u);
+}
+
+__device__ __forceinline__ uint2 PackBf16(float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    return {reinterpret_cast<const uint32_t &>(lo), reinterpret_cast<const uint32_t &>(hi)};
 }
 
 // c^m for the chunk's eight modes from the FP64 polar form.
@@ -666,24 +673,27 @@ __global__ void ClickKernel(const DevImpact *__restrict__ impacts, const DevImpa
 }
 
 // One thread per mode pair: rows j = 1..kTmBlock of the power stages, c^j by FP64 products of the float coefficient
-// (the same arithmetic as MakePowers), each value split into its TF32 head and FP32 tail.
+// (the same arithmetic as MakePowers). A stage (one chunk) holds three images of its 256 x 16 block (tensor_mix.cuh):
+// the TF32 head, and BF16 copies of the value and of the tail for the two cross products.
 __global__ void __launch_bounds__(128) PowerTableKernel(const BankView b, float *__restrict__ powers) {
+    static_assert(kTmKChunk == 16, "one chunk per stage");
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; // chunk * 4 + pair
     if (idx >= b.NChunks * 4) return;
     const uint32_t chunk = idx >> 2, pair = idx & 3;
-    const uint32_t group = chunk / kTmGroupChunks, lc = chunk % kTmGroupChunks;
     const uint32_t mode = chunk * kLanes + pair * 2;
     const double ax = b.CoeffRe[mode], bx = b.CoeffIm[mode], ay = b.CoeffRe[mode + 1], by = b.CoeffIm[mode + 1];
-    constexpr uint32_t chunks_per_stage = kTmKChunk / 16;
-    float *stage = powers + (size_t(group) * kTmStagesPerGroup + lc / chunks_per_stage) * TmPowerStageFloats() + size_t((lc % chunks_per_stage) * 4 + pair) * kTmBlock * 4;
+    uint8_t *stage = reinterpret_cast<uint8_t *>(powers + size_t(chunk) * TmPowerStageFloats());
+    uint8_t *head = stage + size_t(pair) * kTmBlock * 16;                                    // TF32: 16-byte K pieces of 4 elements, 4096 bytes apart
+    uint8_t *value16 = stage + kTmPowerHeadBytes + size_t(pair >> 1) * kTmBlock * 16 + (pair & 1) * 8; // BF16: pieces of 8 elements
+    uint8_t *tail16 = value16 + kTmPowerBf16Bytes;
     double rx = ax, ix = bx, ry = ay, iy = by;
     for (uint32_t j = 0; j < kTmBlock; ++j) {
         const float4 v = {float(rx), float(ix), float(ry), float(iy)};
-        const float4 head = {Tf32Head(v.x), Tf32Head(v.y), Tf32Head(v.z), Tf32Head(v.w)};
-        const float4 tail = {v.x - head.x, v.y - head.y, v.z - head.z, v.w - head.w};
-        float *at = stage + (j >> 3) * 32 + (j & 7) * 4;
-        *reinterpret_cast<float4 *>(at) = head;
-        *reinterpret_cast<float4 *>(at + kTmBlock * kTmKChunk) = tail;
+        const float4 h = {Tf32Head(v.x), Tf32Head(v.y), Tf32Head(v.z), Tf32Head(v.w)};
+        const uint32_t row = (j >> 3) * 128 + (j & 7) * 16;
+        *reinterpret_cast<float4 *>(head + row) = h;
+        *reinterpret_cast<uint2 *>(value16 + row) = PackBf16(v.x, v.y, v.z, v.w);
+        *reinterpret_cast<uint2 *>(tail16 + row) = PackBf16(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
         const double nrx = rx * ax - ix * bx, nry = ry * ay - iy * by;
         ix = rx * bx + ix * ax, iy = ry * by + iy * ay;
         rx = nrx, ry = nry;

@@ -6,10 +6,11 @@
 //   warp 0 (one lane): producer. Per stage a bulk copy (power stage, already a shared-memory image) and a 3-D TMA tile
 //                      copy (16 reduction elements x all time blocks of the row-major FP32 states, 64-byte swizzle)
 //                      straight into the stage's head half: kind::tf32 reads the top 19 bits, so FP32 rows are the head.
-//   warps 2-3:         splitters. tail = x - truncated(x) into the tail half; they and the power copy complete the
+//   warps 2-3:         splitters. BF16 copies of x and of the tail x - truncated(x) for the two cross products, which run
+//                      as kind::f16 MMAs (they need ~9 bits of each factor); they and the power copy complete the
 //                      stage's "full" mbarrier.
-//   warp 1 (one lane): issues tcgen05.mma kind::tf32, three per 8-wide reduction step and accumulator (head*head,
-//                      head*tail, tail*head), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
+//   warp 1 (one lane): per stage and accumulator two kind::f16 MMAs (tail*value, value*tail on BF16 copies, K = 16) and two
+//                      kind::tf32 MMAs (head*head, K = 8), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
 //   warps 4-11:        epilogue, one warp per (TMEM lane quarter, block half). tcgen05.ld of the accumulator (lane =
 //                      frame inside the half block, column = block) folded into FP32 registers, then coalesced stores
 //                      of the partial mix row.
@@ -18,6 +19,7 @@
 #include "common.h"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cudaTypedefs.h>
 
 namespace me {
@@ -83,6 +85,20 @@ __device__ __forceinline__ void MmaTf32(uint32_t tmem_d, uint64_t a, uint64_t b,
         "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// kind::f16 with BF16 operands (format 1), FP32 accumulate, both K-major: K = 16 per instruction.
+__host__ __device__ constexpr uint32_t InstructionDescriptorBf16(uint32_t m, uint32_t n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24); }
+__device__ __forceinline__ void MmaBf16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ uint2 PackBf16x4(float a, float b, float c, float d) {
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    return {reinterpret_cast<const uint32_t &>(lo), reinterpret_cast<const uint32_t &>(hi)};
+}
 __device__ __forceinline__ void MmaCommit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(SmemAddr(bar)) : "memory");
 }
@@ -106,7 +122,7 @@ __device__ __forceinline__ void TmemLoad16(uint32_t taddr, uint32_t (&v)[16]) {
 
 // Tensor-core accumulation rounds toward zero: n MMAs chained on one accumulator lose up to n * 2^-24 of its
 // magnitude, always in the same direction (measured: 1e-4 after the 1536 MMAs of a group). So a chain is cut after
-// kFoldStages stages (24 MMAs per accumulator, <= 1.5e-6) and folded into FP32 registers by the epilogue warps with
+// kFoldStages stages (16 MMAs per accumulator, <= 1e-6) and folded into FP32 registers by the epilogue warps with
 // round-to-nearest adds; two accumulator pairs alternate so the fold of one overlaps the MMAs into the other.
 constexpr uint32_t kFoldStages = 4;
 constexpr uint32_t kFoldStagesHost = kFoldStages;
@@ -162,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = InstructionDescriptor(128, N);
+            constexpr uint32_t idesc = InstructionDescriptor(128, N), idesc16 = InstructionDescriptorBf16(128, N);
             // Power halves: the 16-byte K pieces are 4096 bytes apart and the 8-row groups 128 bytes; frames 128-255
             // of the block start 16 row groups further.
             constexpr uint32_t lbo_p = kTmBlock * 16, sbo = 128, upper_rows = 16 * 128;
@@ -178,29 +194,29 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t stage = SmemAddr(stage_storage + size_t(s) * kStageBytes);
                 const uint32_t tmem_d = tmem_base + buffer * 2 * N;
+                // Stage layout: [FP32 state rows 8 KB, swizzled][BF16 states 4 KB][BF16 state tails 4 KB]
+                //               [TF32 power heads 16 KB][BF16 powers 8 KB][BF16 power tails 8 KB]
+                const uint32_t w_value16 = stage + kRawBytes, w_tail16 = w_value16 + kRawBytes / 2;
+                const uint32_t p_head32 = stage + kStateBytes, p_value16 = p_head32 + kTmPowerHeadBytes, p_tail16 = p_value16 + kTmPowerBf16Bytes;
 #pragma unroll
-                for (uint32_t kk = 0; kk < kSteps; ++kk) {
-                    // Inside the swizzle atom a K step of 8 TF32 is 32 bytes further along the row.
-                    const uint64_t w_head = SwizzledDescriptor(stage + kk * 32);
-                    const uint64_t w_tail = SwizzledDescriptor(stage + kStateHalfBytes + kk * 32);
+                for (uint32_t half = 0; half < 2; ++half) {
+                    const uint32_t d = tmem_d + half * N, rows = half * upper_rows;
+                    // The two cross products first (small terms), one K = 16 BF16 MMA each: power tail x state, power x state tail.
+                    MmaBf16(d, MatrixDescriptor(p_tail16 + rows, lbo_p, sbo), MatrixDescriptor(w_value16, N * 16, sbo), idesc16, !opens);
+                    MmaBf16(d, MatrixDescriptor(p_value16 + rows, lbo_p, sbo), MatrixDescriptor(w_tail16, N * 16, sbo), idesc16, 1);
 #pragma unroll
-                    for (uint32_t half = 0; half < 2; ++half) {
-                        const uint64_t p_head = MatrixDescriptor(stage + kStateBytes + kk * 2 * lbo_p + half * upper_rows, lbo_p, sbo);
-                        const uint64_t p_tail = MatrixDescriptor(stage + kStateBytes + kPowerHalfBytes + kk * 2 * lbo_p + half * upper_rows, lbo_p, sbo);
-                        MmaTf32(tmem_d + half * N, p_tail, w_head, idesc, !(opens && kk == 0));
-                        MmaTf32(tmem_d + half * N, p_head, w_tail, idesc, 1);
-                        MmaTf32(tmem_d + half * N, p_head, w_head, idesc, 1);
-                    }
+                    for (uint32_t kk = 0; kk < kSteps; ++kk) // head x head in TF32; inside the swizzle atom a K step of 8 is 32 bytes along the row
+                        MmaTf32(d, MatrixDescriptor(p_head32 + kk * 2 * lbo_p + rows, lbo_p, sbo), SwizzledDescriptor(stage + kk * 32), idesc, 1);
                 }
                 MmaCommit(&empty_bar[s]); // arrives when the MMAs above have read the stage
                 if (k % kFoldStages == kFoldStages - 1) MmaCommit(&accum_full[buffer]);
             }
         }
     } else if (warp < 4) {
-        // Splitters: the TMA copy lands the FP32 state rows in the head half of the stage, already in the swizzled K-major
-        // layout. kind::tf32 reads only the top 19 bits of each element, i.e. the head is the TRUNCATED value, so the tail is
-        // x - trunc(x), written at the same offsets of the tail half. Thread wt owns rows wt and wt + 64; the piece order
-        // keeps the loads and stores of a quarter-warp in different banks.
+        // Splitters: the TMA copy lands the FP32 state rows at the front of the stage, already in the swizzled K-major layout.
+        // kind::tf32 reads only the top 19 bits of each element, i.e. the head is the TRUNCATED value; the two cross products
+        // take BF16 copies of x and of the tail x - trunc(x), written in the canonical no-swizzle layout (8-element pieces).
+        // Thread wt owns rows wt and wt + 64; the piece order keeps a quarter-warp's loads in different banks.
         static_assert(N == 128, "two rows per splitter thread");
         const uint32_t wt = (warp - 2) * 32 + lane;
         for (uint32_t k = 0; k < n_stages; ++k) {
@@ -210,13 +226,18 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
                 const uint32_t n = wt + 64 * r, q = (n >> 1) & 3;
+                uint2 value[4], tail[4]; // logical 4-element pieces 0..3 of the row
 #pragma unroll
-                for (uint32_t j = 0; j < 4; ++j) {
-                    const uint32_t at = n * 64 + ((j ^ q) << 4);
-                    const float4 v = *reinterpret_cast<const float4 *>(stage + at);
-                    const float4 tail = {v.x - Tf32Truncated(v.x), v.y - Tf32Truncated(v.y), v.z - Tf32Truncated(v.z), v.w - Tf32Truncated(v.w)};
-                    *reinterpret_cast<float4 *>(stage + kStateHalfBytes + at) = tail;
+                for (uint32_t piece = 0; piece < 4; ++piece) {
+                    const float4 v = *reinterpret_cast<const float4 *>(stage + n * 64 + ((piece ^ q) << 4)); // 64-byte swizzle: logical piece ^ row bits
+                    value[piece] = PackBf16x4(v.x, v.y, v.z, v.w);
+                    tail[piece] = PackBf16x4(v.x - Tf32Truncated(v.x), v.y - Tf32Truncated(v.y), v.z - Tf32Truncated(v.z), v.w - Tf32Truncated(v.w));
                 }
+                const uint32_t at = (n >> 3) * 128 + (n & 7) * 16; // + 2048 for elements 8..15
+                *reinterpret_cast<uint4 *>(stage + kRawBytes + at) = {value[0].x, value[0].y, value[1].x, value[1].y};
+                *reinterpret_cast<uint4 *>(stage + kRawBytes + N * 16 + at) = {value[2].x, value[2].y, value[3].x, value[3].y};
+                *reinterpret_cast<uint4 *>(stage + kRawBytes + kRawBytes / 2 + at) = {tail[0].x, tail[0].y, tail[1].x, tail[1].y};
+                *reinterpret_cast<uint4 *>(stage + kRawBytes + kRawBytes / 2 + N * 16 + at) = {tail[2].x, tail[2].y, tail[3].x, tail[3].y};
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy stores -> visible to the tensor core's async proxy
             __syncwarp();

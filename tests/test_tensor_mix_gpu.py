@@ -3,7 +3,7 @@
 out[row][tile*N*256 + n*256 + r] = sum_k P_group[r, k] * W_tile,group[n, k] over the 4096 reduction elements of each of the
 row's groups (r = frame inside the 256-frame time block, n = time block inside the tile),
 operands split into a TF32 head and an FP32 tail (3xTF32): powers pre-split in the shared-memory stage layout, states plain
-row-major FP32 (split inside the kernel). Tolerance: 5e-6 of the row scale (measured 2.1e-6, FP32-level; a plain TF32
+row-major FP32 (split inside the kernel). Tolerance: 1.2e-5 of the row scale at the 4.5-sigma maximum over 65k outputs (the BF16 cross products leave ~2e-6 rms; a plain TF32
 product would miss it by 1e-3).
 """
 import ctypes as C
@@ -24,18 +24,32 @@ def split_tf32(x):
     return head, (x.astype(np.float32) - head).astype(np.float32)
 
 
+def bf16_bits(x):
+    """float32 -> bfloat16 bits, round to nearest even (__floats2bfloat162_rn)."""
+    bits = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    return (((bits + 0x7FFF + ((bits >> 16) & 1)) >> 16) & 0xFFFF).astype(np.uint16)
+
+
 def pack(mat):
-    """[rows, 4096] -> [stages][2 halves][rows*KC] in the stage layout of tensor_mix.cuh."""
+    """[256, 4096] -> [stages][8192 floats]: per stage the TF32 head (16 KB), BF16 value (8 KB) and BF16 tail (8 KB) images
+    of tensor_mix.cuh."""
     rows = mat.shape[0]
     head, tail = split_tf32(mat)
-    out = np.empty((STAGES, 2, rows * KC), np.float32)
+    out = np.zeros((STAGES, 32768), np.uint8)
     r = np.arange(rows)[:, None]
     k = np.arange(KC)[None, :]
-    idx = (k // 4) * rows * 4 + (r // 8) * 32 + (r % 8) * 4 + (k % 4)
+    at32 = (k // 4) * rows * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 4) * 4
+    at16 = (k // 8) * rows * 16 + (r // 8) * 128 + (r % 8) * 16 + (k % 8) * 2
     for s in range(STAGES):
-        out[s, 0, idx] = head[:, s * KC:(s + 1) * KC]
-        out[s, 1, idx] = tail[:, s * KC:(s + 1) * KC]
-    return out
+        block = slice(s * KC, (s + 1) * KC)
+        h = np.ascontiguousarray(head[:, block]).view(np.uint8).reshape(rows, KC, 4)
+        for byte in range(4):
+            out[s, at32 + byte] = h[:, :, byte]
+        for base, values in ((16384, mat[:, block]), (24576, tail[:, block])):
+            b = bf16_bits(values).view(np.uint8).reshape(rows, KC, 2)
+            for byte in range(2):
+                out[s, base + at16 + byte] = b[:, :, byte]
+    return out.view(np.float32)
 
 
 @pytest.mark.parametrize("n_blocks,groups,per_row,tiles,ragged", [(128, 2, 1, 2, 0), (128, 1, 1, 2, 777), (128, 4, 2, 1, 5000)])
@@ -62,4 +76,4 @@ def test_tensor_mix_matches_float64_product(n_blocks, groups, per_row, tiles, ra
         scale = np.sqrt(scale)
         err = np.abs(out[r] - want).max()
         assert np.isfinite(out[r]).all()
-        assert err <= 5e-6 * scale, f"row {r}: max error {err:.3e} vs scale {scale:.3e}"
+        assert err <= 1.2e-5 * scale, f"row {r}: max error {err:.3e} vs scale {scale:.3e}"
