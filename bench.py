@@ -301,17 +301,25 @@ def run_ours(args):
             chunks = -(-MODES // 8)
             groups = -(-(hi - lo) // (256 // chunks))
             tiles = -(-frames // 32768)
-            issued_flops = 3 * 2.0 * 256 * 128 * 4096 * groups * tiles
+            product_flops = 2.0 * 256 * 128 * 4096 * groups * tiles  # one of the three products of the 3xTF32 split
+            # head x head runs as kind::tf32, the two cross products as kind::f16 on BF16 copies at twice that rate: the
+            # tensor-pipe time at peak is (1 + 2/2) products at the TF32 rate, so "achieved" is quoted in TF32-equivalent flop/s.
+            issued_flops = 3 * product_flops
+            tf32_equivalent = 2 * product_flops
             walk_bytes = 4096 * 4.0 * groups * -(-frames // 256)
             m_ms, w_ms = sum(mix_ms) / len(mix_ms), sum(walk_ms) / len(walk_ms)
             tf32_peak = pk.get("bf16_tflops", 2250.0) / 2
+            stages = groups * 256 * tiles
+            smem_bytes = stages * 122880.0  # per 16-element stage: 40 KB of TMA writes, 16 KB of splitter traffic, 64 KB of MMA operand reads
             roofline = {
-                "bound": "tensor", "kernel": "TensorMixKernel<128,4> (tcgen05.mma kind::tf32, 3xTF32 split in the kernel, FP32 register folds)", "achieved": issued_flops / (m_ms * 1e-3) / 1e12, "peak": tf32_peak,
-                "unit": "TFLOP/s", "frac": issued_flops / (m_ms * 1e-3) / 1e12 / tf32_peak, "traffic": tensor_traffic("mix"), "kernel_ms_per_launch": m_ms, "launches_per_step": stats["tensor_windows"],
-                "issued_flops_per_step": issued_flops, "share_of_step": m_ms / ms_per_step,
+                "bound": "tensor", "kernel": "TensorMixKernel<128,4> (tcgen05.mma: head x head kind::tf32, cross products kind::f16 on BF16 copies; FP32 register folds)",
+                "achieved": tf32_equivalent / (m_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TF32-equivalent TFLOP/s", "frac": tf32_equivalent / (m_ms * 1e-3) / 1e12 / tf32_peak,
+                "traffic": tensor_traffic("mix"), "kernel_ms_per_launch": m_ms, "launches_per_step": stats["tensor_windows"],
+                "issued_flops_per_step": issued_flops, "issued_tflops": issued_flops / (m_ms * 1e-3) / 1e12, "share_of_step": m_ms / ms_per_step,
                 "peak_source": ("half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate; nominal 1125)" if "bf16_tflops" in pk else "nominal dense TF32 1125 TFLOP/s"),
                 "reference_fma_equivalent": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (m_ms * 1e-3) / 1e12,
-                "note": "the kernel streams 2 operand images (power stages from L2, state stages from HBM) at %.1f TB/s into shared memory; that ingest, not the MMA rate, bounds it" % ((issued_flops / (3 * 2.0 * 256 * 128 * 16)) * 40960 / (m_ms * 1e-3) / 1e12),
+                "shared_memory": {"bytes_per_launch": smem_bytes, "achieved_bytes_per_clk_per_sm": smem_bytes / (m_ms * 1e-3) / (148 * (pk.get("sm_max_mhz", 1965.0) * 1e6)), "peak_bytes_per_clk_per_sm": 128,
+                                  "note": "what actually bounds the kernel: SS-mode MMAs read both operands from shared memory (DESIGN.md 5.2, profiles/r01_resonator.md)"},
             }
             roofline_extra = {
                 "roofline_walk": {"bound": "hbm", "kernel": "ResonatorKernel<1,2,true> (state walk: c^256 steps, FP32 state rows)", "achieved": walk_bytes / (w_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
