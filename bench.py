@@ -310,7 +310,7 @@ def run_ours(args):
             m_ms, w_ms = sum(mix_ms) / len(mix_ms), sum(walk_ms) / len(walk_ms)
             tf32_peak = pk.get("bf16_tflops", 2250.0) / 2
             stages = groups * 256 * tiles
-            smem_bytes = stages * 122880.0  # per 16-element stage: 40 KB of TMA writes, 16 KB of splitter traffic, 64 KB of MMA operand reads
+            smem_bytes = stages * 106496.0  # per 16-element stage: 40 KB of TMA writes, 16 KB of splitter traffic, 48 KB of MMA operand reads
             roofline = {
                 "bound": "tensor", "kernel": "TensorMixKernel<128,4> (tcgen05.mma: head x head kind::tf32, cross products kind::f16 on BF16 copies; FP32 register folds)",
                 "achieved": tf32_equivalent / (m_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TF32-equivalent TFLOP/s", "frac": tf32_equivalent / (m_ms * 1e-3) / 1e12 / tf32_peak,

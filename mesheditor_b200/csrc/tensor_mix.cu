@@ -1,7 +1,7 @@
 // sm_100a tcgen05 kernel of the resonator bank's tensor-core form; see tensor_mix.cuh for the algebra.
 //
-// One CTA renders one time tile (BlocksPerTile x 256 frames) of a few chunk groups: two 128 x N accumulators (frames
-// 0-127 and 128-255 of every block) in tensor memory, fed stage by stage (16 reduction elements = 8 modes) through a
+// One CTA renders one time tile (BlocksPerTile x 256 frames) of a few chunk groups: a 128 x 256 accumulator (time blocks x
+// frames of a block) in tensor memory, double-buffered, fed stage by stage (16 reduction elements = 8 modes) through a
 // ring of shared-memory buffers.
 //   warp 0 (one lane): producer. Per stage a bulk copy (power stage, already a shared-memory image) and a 3-D TMA tile
 //                      copy (16 reduction elements x all time blocks of the row-major FP32 states, 64-byte swizzle)
@@ -9,9 +9,9 @@
 //   warps 2-3:         splitters. BF16 copies of x and of the tail x - truncated(x) for the two cross products, which run
 //                      as kind::f16 MMAs (they need ~9 bits of each factor); they and the power copy complete the
 //                      stage's "full" mbarrier.
-//   warp 1 (one lane): per stage and accumulator two kind::f16 MMAs (tail*value, value*tail on BF16 copies, K = 16) and two
-//                      kind::tf32 MMAs (head*head, K = 8), then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
-//   warps 4-11:        epilogue, one warp per (TMEM lane quarter, block half). tcgen05.ld of the accumulator (lane =
+//   warp 1 (one lane): per stage two kind::f16 MMAs (value*tail, tail*value on BF16 copies, K = 16) and two kind::tf32
+//                      MMAs (head*head, K = 8), M = 128 time blocks x N = 256 frames, then tcgen05.commit to the stage's "empty" mbarrier; owns the TMEM allocation.
+//   warps 4-11:        epilogue, one warp per (TMEM lane quarter, column half). tcgen05.ld of the accumulator (lane =
 //                      frame inside the half block, column = block) folded into FP32 registers, then coalesced stores
 //                      of the partial mix row.
 #include "tensor_mix.cuh"
@@ -178,10 +178,12 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = InstructionDescriptor(128, N), idesc16 = InstructionDescriptorBf16(128, N);
-            // Power halves: the 16-byte K pieces are 4096 bytes apart and the 8-row groups 128 bytes; frames 128-255
-            // of the block start 16 row groups further.
-            constexpr uint32_t lbo_p = kTmBlock * 16, sbo = 128, upper_rows = 16 * 128;
+            // The states are the A operand (M = N time blocks = TMEM lanes), the powers the B operand (N = 256 frames =
+            // accumulator columns): one MMA covers the whole time block, so neither operand is read twice per K step.
+            static_assert(N == 128 && kTmBlock == 256, "M = 128 time blocks, N = 256 frames");
+            constexpr uint32_t idesc = InstructionDescriptor(N, kTmBlock), idesc16 = InstructionDescriptorBf16(N, kTmBlock);
+            // Power images: the 16-byte K pieces are 4096 bytes apart and the 8-row groups 128 bytes.
+            constexpr uint32_t lbo_p = kTmBlock * 16, sbo = 128;
             for (uint32_t k = 0; k < n_stages; ++k) {
                 const uint32_t s = k % Stages, round = k / Stages;
                 const uint32_t fold = k / kFoldStages, buffer = fold & 1;
@@ -198,16 +200,12 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
                 //               [TF32 power heads 16 KB][BF16 powers 8 KB][BF16 power tails 8 KB]
                 const uint32_t w_value16 = stage + kRawBytes, w_tail16 = w_value16 + kRawBytes / 2;
                 const uint32_t p_head32 = stage + kStateBytes, p_value16 = p_head32 + kTmPowerHeadBytes, p_tail16 = p_value16 + kTmPowerBf16Bytes;
+                // The two cross products first (small terms), one K = 16 BF16 MMA each: state x power tail, state tail x power.
+                MmaBf16(tmem_d, MatrixDescriptor(w_value16, N * 16, sbo), MatrixDescriptor(p_tail16, lbo_p, sbo), idesc16, !opens);
+                MmaBf16(tmem_d, MatrixDescriptor(w_tail16, N * 16, sbo), MatrixDescriptor(p_value16, lbo_p, sbo), idesc16, 1);
 #pragma unroll
-                for (uint32_t half = 0; half < 2; ++half) {
-                    const uint32_t d = tmem_d + half * N, rows = half * upper_rows;
-                    // The two cross products first (small terms), one K = 16 BF16 MMA each: power tail x state, power x state tail.
-                    MmaBf16(d, MatrixDescriptor(p_tail16 + rows, lbo_p, sbo), MatrixDescriptor(w_value16, N * 16, sbo), idesc16, !opens);
-                    MmaBf16(d, MatrixDescriptor(p_value16 + rows, lbo_p, sbo), MatrixDescriptor(w_tail16, N * 16, sbo), idesc16, 1);
-#pragma unroll
-                    for (uint32_t kk = 0; kk < kSteps; ++kk) // head x head in TF32; inside the swizzle atom a K step of 8 is 32 bytes along the row
-                        MmaTf32(d, MatrixDescriptor(p_head32 + kk * 2 * lbo_p + rows, lbo_p, sbo), SwizzledDescriptor(stage + kk * 32), idesc, 1);
-                }
+                for (uint32_t kk = 0; kk < kSteps; ++kk) // head x head in TF32; inside the swizzle atom a K step of 8 is 32 bytes along the row
+                    MmaTf32(tmem_d, SwizzledDescriptor(stage + kk * 32), MatrixDescriptor(p_head32 + kk * 2 * lbo_p, lbo_p, sbo), idesc, 1);
                 MmaCommit(&empty_bar[s]); // arrives when the MMAs above have read the stage
                 if (k % kFoldStages == kFoldStages - 1) MmaCommit(&accum_full[buffer]);
             }
@@ -244,10 +242,10 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(&full_bar[s])) : "memory");
         }
     } else {
-        // TMEM lanes are reachable from the warp whose index mod 4 matches the lane quarter; warps 4-7 take frames
-        // 0-127 of every block, warps 8-11 frames 128-255.
+        // TMEM lanes (time blocks) are reachable from the warp whose index mod 4 matches the lane quarter; warps 4-7 take
+        // accumulator columns (frames of the block) 0-127, warps 8-11 columns 128-255.
         const uint32_t quarter = warp & 3, half = (warp - 4) >> 2;
-        const uint32_t row = half * 128 + quarter * 32 + lane; // frame inside the time block
+        const uint32_t block = quarter * 32 + lane; // time block inside the tile
         float acc[N];
 #pragma unroll
         for (uint32_t c = 0; c < N; ++c) acc[c] = 0.f;
@@ -267,12 +265,21 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(&accum_empty[buffer])) : "memory");
         }
+        // This thread holds 128 consecutive frames of its time block: 16-byte stores (the row is 16-byte aligned: every
+        // offset below is a multiple of four frames), scalar ones across the ragged end of the window.
         float *out = plan.Partial + size_t(row_index) * plan.Frames;
-        const uint32_t tile_frame = tile * N * kTmBlock;
+        const uint32_t frame0 = tile * N * kTmBlock + block * kTmBlock + half * 128;
+        const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
 #pragma unroll
-        for (uint32_t c = 0; c < N; ++c) {
-            const uint32_t frame = tile_frame + c * kTmBlock + row;
-            if (frame < plan.Frames) out[frame] = acc[c];
+        for (uint32_t c = 0; c < N; c += 4) {
+            const uint32_t frame = frame0 + c;
+            if (aligned && frame + 3 < plan.Frames) {
+                *reinterpret_cast<float4 *>(out + frame) = {acc[c], acc[c + 1], acc[c + 2], acc[c + 3]};
+            } else {
+#pragma unroll
+                for (uint32_t i = 0; i < 4; ++i)
+                    if (frame + i < plan.Frames) out[frame + i] = acc[c + i];
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
