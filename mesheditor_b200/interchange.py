@@ -114,3 +114,89 @@ def bank_modes(model: dict):
     rates = model["decayRates"]
     t60s = np.where(rates > 0, np.float32(LN1000) / np.where(rates > 0, rates, 1).astype(np.float32), np.float32(0)).astype(np.float32)
     return dict(freqs=model["frequencies"], t60s=t60s, shapes=np.ascontiguousarray(np.transpose(model["shapes"], (1, 0, 2))), positions=model["positions"], indices=model["indices"])
+
+
+# ---- KHR_audio_rigid_bodies glTF documents (glTF_PhysicalAudio/extensions/2.0/Khronos/KHR_audio_rigid_bodies) ------------------
+# The reference reads and writes these through fastgltf in its scene code (out of this path's scope); the generator of the
+# golden samples (glTF_PhysicalAudio/samples/generate.py:623-687) writes them from MeshEditorModalSolve's JSON. These two
+# functions are that last hop, so a solve on the GPU can be carried into a document the reference loads, and the reference's
+# committed golden models can be read back (tests/golden/make_golden.py reads the same fields).
+
+_COMPONENT = {5126: np.float32, 5123: np.uint16, 5125: np.uint32}
+_WIDTH = {"SCALAR": 1, "VEC3": 3}
+
+
+def _accessor(doc, index, buffers):
+    import base64
+
+    acc = doc["accessors"][index]
+    view = doc["bufferViews"][acc["bufferView"]]
+    b = view["buffer"]
+    if b not in buffers:
+        uri = doc["buffers"][b]["uri"]
+        if not uri.startswith("data:"):
+            raise ValueError("only embedded (data: URI) buffers are read")
+        buffers[b] = base64.b64decode(uri.split(",", 1)[1])
+    width = _WIDTH[acc["type"]]
+    a = np.frombuffer(buffers[b], _COMPONENT[acc["componentType"]], acc["count"] * width, view.get("byteOffset", 0) + acc.get("byteOffset", 0))
+    return a.reshape(-1, width).copy() if width > 1 else a.copy()
+
+
+def read_gltf_modal_models(doc) -> list:
+    """The modalModels of a glTF document (a dict, or a path to a .gltf with embedded buffers), each in the form
+    khr_modal_model() returns plus `name` and `material` (the acousticMaterials entry: density, youngsModulus, poissonRatio,
+    alpha, beta). Required fields per the schema: frequencies, decayRates, positions, shapes."""
+    if not isinstance(doc, dict):
+        with open(doc) as f:
+            doc = json.load(f)
+    ext = doc.get("extensions", {}).get("KHR_audio_rigid_bodies", {})
+    buffers, out = {}, []
+    for m in ext.get("modalModels", []):
+        freqs = _accessor(doc, m["frequencies"], buffers).astype(np.float32)
+        positions = _accessor(doc, m["positions"], buffers).astype(np.float32).reshape(-1, 3)
+        model = dict(name=m.get("name", ""), frequencies=freqs, decayRates=_accessor(doc, m["decayRates"], buffers).astype(np.float32), positions=positions,
+                     shapes=_accessor(doc, m["shapes"], buffers).astype(np.float32).reshape(len(freqs), len(positions), 3),
+                     indices=_accessor(doc, m["indices"], buffers).astype(np.uint32).reshape(-1) if "indices" in m else np.zeros(0, np.uint32))
+        if "material" in m:
+            model["material"] = dict(ext["acousticMaterials"][m["material"]])
+        mp = m.get("massProperties")
+        if mp:
+            model.update(mass=float(mp["mass"]), centerOfMass=np.asarray(mp.get("centerOfMass", (0, 0, 0)), np.float32), inertiaDiagonal=np.asarray(mp.get("inertiaDiagonal", (0, 0, 0)), np.float32))
+        out.append(model)
+    return out
+
+
+def write_gltf_modal_models(models, asset_generator="mesheditor_b200") -> dict:
+    """A minimal glTF 2.0 document carrying `models` (dicts as read_gltf_modal_models / khr_modal_model give them, each
+    optionally with `name` and a `material` dict) in extensions.KHR_audio_rigid_bodies, all arrays in one embedded buffer:
+    FLOAT SCALAR frequencies / decayRates, FLOAT VEC3 positions / mode-major shapes, UNSIGNED_INT SCALAR indices."""
+    import base64
+
+    blob, views, accessors, materials, out_models = bytearray(), [], [], [], []
+
+    def add(array, component, kind):
+        a = np.ascontiguousarray(array, _COMPONENT[component]).reshape(-1)
+        while len(blob) % 4:
+            blob.append(0)
+        views.append(dict(buffer=0, byteOffset=len(blob), byteLength=a.nbytes))
+        blob.extend(a.tobytes())
+        accessors.append(dict(bufferView=len(views) - 1, componentType=component, count=a.size // _WIDTH[kind], type=kind))
+        return len(accessors) - 1
+
+    for m in models:
+        entry = dict(name=m.get("name", ""), frequencies=add(m["frequencies"], 5126, "SCALAR"), decayRates=add(m["decayRates"], 5126, "SCALAR"), positions=add(m["positions"], 5126, "VEC3"),
+                     shapes=add(m["shapes"], 5126, "VEC3"))
+        if len(m.get("indices", ())):
+            entry["indices"] = add(m["indices"], 5125, "SCALAR")
+        if "material" in m:
+            if m["material"] not in materials:
+                materials.append(m["material"])
+            entry["material"] = materials.index(m["material"])
+        if "mass" in m:
+            entry["massProperties"] = dict(mass=float(m["mass"]), centerOfMass=[float(v) for v in m["centerOfMass"]], inertiaDiagonal=[float(v) for v in m["inertiaDiagonal"]])
+        out_models.append(entry)
+    ext = dict(modalModels=out_models)
+    if materials:
+        ext["acousticMaterials"] = materials
+    return dict(asset=dict(version="2.0", generator=asset_generator), extensionsUsed=["KHR_audio_rigid_bodies"], buffers=[dict(byteLength=len(blob), uri="data:application/octet-stream;base64," + base64.b64encode(bytes(blob)).decode())],
+                bufferViews=views, accessors=accessors, extensions=dict(KHR_audio_rigid_bodies=ext))

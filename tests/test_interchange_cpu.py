@@ -91,3 +91,44 @@ def test_modal_solve_json_matches_the_tool():
     bank = bank_modes(khr_modal_model(text))
     np.testing.assert_allclose(bank["t60s"], r.t60s, rtol=2e-7)
     np.testing.assert_array_equal(bank["shapes"], r.shapes)
+
+
+def test_khr_audio_rigid_bodies_document_round_trip():
+    """A modal model -> glTF document (extensions.KHR_audio_rigid_bodies) -> back: every array bit-identical."""
+    from mesheditor_b200.interchange import read_gltf_modal_models, write_gltf_modal_models
+
+    with open(os.path.join(GOLDEN, "model_21.modal"), "rb") as f:
+        model = khr_modal_model(ModalModel.from_bytes(f.read()).solve_json())
+    model.update(name="Bell", material=dict(name="Steel", density=8000.0, youngsModulus=2.0e11, poissonRatio=0.29, alpha=5.0, beta=3.0e-8), indices=np.array([0, 1, 2, 2, 3, 0], np.uint32))
+    second = dict(model, name="Bell2", indices=np.zeros(0, np.uint32))
+    doc = json.loads(json.dumps(write_gltf_modal_models([model, second])))  # through text, as a file would go
+    assert doc["asset"]["version"] == "2.0" and doc["extensionsUsed"] == ["KHR_audio_rigid_bodies"]
+    assert len(doc["extensions"]["KHR_audio_rigid_bodies"]["acousticMaterials"]) == 1
+    assert "indices" not in doc["extensions"]["KHR_audio_rigid_bodies"]["modalModels"][1]
+    back = read_gltf_modal_models(doc)
+    assert [m["name"] for m in back] == ["Bell", "Bell2"]
+    for key in ("frequencies", "decayRates", "positions", "shapes", "indices", "centerOfMass", "inertiaDiagonal"):
+        np.testing.assert_array_equal(back[0][key], model[key])
+    assert back[0]["mass"] == model["mass"] and back[0]["material"] == model["material"] and len(back[1]["indices"]) == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/glTF_PhysicalAudio/samples/Pile.gltf"), reason="the reference's sample documents are only in the build container")
+def test_reads_the_reference_golden_documents():
+    """The reader decodes the reference's committed samples to exactly the arrays tests/golden/*.npz were made from."""
+    import glob
+
+    from golden_util import golden_names, load_golden
+    from mesheditor_b200.interchange import read_gltf_modal_models
+
+    models = []
+    for path in glob.glob("/root/reference/glTF_PhysicalAudio/samples/**/*.gltf", recursive=True):
+        models += read_gltf_modal_models(path)
+    assert len(models) >= 7
+    for name in golden_names():
+        g = load_golden(name)
+        match = [m for m in models if len(m["frequencies"]) == len(g["golden_freqs"]) and np.array_equal(m["frequencies"], g["golden_freqs"])]
+        assert match, name
+        m = match[0]
+        np.testing.assert_array_equal(m["decayRates"], g["golden_decay"]), np.testing.assert_array_equal(m["positions"], g["golden_positions"])
+        np.testing.assert_array_equal(m["shapes"], g["golden_shapes"])
+        assert m["mass"] == float(g["golden_mass"])
