@@ -9,7 +9,7 @@ import numpy as np
 
 from ._lib import MeContactDynamics, MeImpactor, MeMassProperties, MeMaterial, MeModalEvent, MeStrike, MeStriker, check, lib
 
-STEEL = (8000.0, 2.0e11, 0.29, 5.0, 3.0e-8)  # materials::acoustic::Steel (AcousticMaterial.h:38)
+STEEL = (7850.0, 2.0e11, 0.29, 5.0, 3.0e-8)  # materials::acoustic::Steel (AcousticMaterial.h:38)
 CONSTANTS = {"inv_effective_modulus": 0, "combined_curvature": 1, "stiffness": 2, "patch_radius": 3, "static_penetration": 4, "saturation_penetration": 5, "punch_stiffness": 6}
 
 
