@@ -404,6 +404,30 @@ void me_bytes_free(void *);
  * Numbers are the shortest text that round-trips (std::format "{}"). *json is malloc'ed: release with me_bytes_free. */
 MeStatus me_modal_solve_json(const MeModalResult *, const uint32_t *triangle_indices, uint32_t n_triangle_indices, char **json);
 
+/* ------------------------------------------------------------------------------------------------
+ * Generation-job glue (first slice): what the reference's modal generation job does either side of
+ * mesh2modes apart from simplifying and tetrahedralizing the surface (src/audio/AudioSystem.cpp:838-862). Host-only.
+ * Every *out array is malloc'ed (one element at least, so never NULL on ME_OK): release with me_bytes_free.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* SampleSurfaceTriangles (AudioSystem.cpp:701-746): the mesh's triangulation collapsed onto the excitation vertices. Every
+ * mesh vertex takes the excitation vertex (its index in `excitation_vertices`) it reaches in the fewest edges; a triangle whose
+ * corners took three different ones contributes a triangle; one triangle per distinct point set, ordered by the sorted set, in
+ * the winding first seen (UniqueSampleTriangles, :675-695). Empty with fewer than 3 excitation vertices or no triangle. */
+MeStatus me_sample_surface_triangles(const uint32_t *triangle_indices, uint32_t n_triangle_indices, uint32_t vertex_count, const uint32_t *excitation_vertices, uint32_t n_excitation_vertices,
+                                     uint32_t **out, uint32_t *n_out);
+/* CompactExcitationVertices (AudioSystem.cpp:750-757): the first excitation vertex of every sample point, in sample point
+ * order, from me_modal_result_sample_point_of_excitation -> ModalModes::Vertices. */
+MeStatus me_compact_excitation_vertices(const uint32_t *vertices, uint32_t n_vertices, const uint32_t *sample_point_of, uint32_t n_sample_point_of, uint32_t **out, uint32_t *n_out);
+/* RelabelSampleTriangles (AudioSystem.cpp:761-769): the sample surface after the solve merged positions -> ModalModes::Indices.
+ * Empty when sample_point_of is empty; ME_BAD_ARG for a corner without a sample point. */
+MeStatus me_relabel_sample_triangles(const uint32_t *triangles, uint32_t n_triangle_indices, const uint32_t *sample_point_of, uint32_t n_sample_point_of, uint32_t **out, uint32_t *n_out);
+/* BuildTetMeshData (src/mesh/Tets.cpp:268-293): the TetMeshData a `.modal` file stores beside the modes (MeModalFileExtras
+ * tet_positions_xyz / tet_edge_indices): points divided by the node scale, as floats [n_points][3], and the distinct tet edges
+ * as (low, high) corner pairs in ascending order. */
+MeStatus me_build_tet_mesh_data(const double *points_xyz, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const float scale[3], float **positions_xyz, uint32_t **edge_indices,
+                                uint32_t *n_edge_indices);
+
 /* Unit-test entry of the tensor-core mix (tensor_mix.cuh): out[row][frame] = sum over the 4096 reduction elements of
  * each of the row's groups_per_row consecutive groups of power * state, operands given as host images of the stage layout documented in tensor_mix.cuh
  * (powers: groups*256 stages of 2*256*16 floats, stage layout; states: [tiles][groups][blocks_per_tile][4096] FP32, split in the kernel).

@@ -170,6 +170,10 @@ def lib():
         "me_striker_impactor": [C.POINTER(MeStriker), C.POINTER(MeImpactor)],
         "me_inverse_inertia_tensor": [C.POINTER(MeMassProperties), vp],
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
+        "me_sample_surface_triangles": [vp, u32, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
+        "me_compact_excitation_vertices": [vp, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
+        "me_relabel_sample_triangles": [vp, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
+        "me_build_tet_mesh_data": [vp, u32, vp, u32, vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u32)],
     })
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -1,6 +1,7 @@
 """Model interchange over the C ABI (include/me_modal.h, "Model interchange"): the reference's `.modal` files
 (src/audio/ModalModelFile.{h,cpp}) and the JSON of MeshEditorModalSolve (tests/ModalSolveTool.cpp:84-123) that
-glTF_PhysicalAudio embeds as KHR_audio_rigid_bodies modal models. Host-only."""
+glTF_PhysicalAudio embeds as KHR_audio_rigid_bodies modal models; and the generation-job glue either side of the solve
+(include/me_modal.h, "Generation-job glue": src/audio/AudioSystem.cpp:838-862, src/mesh/Tets.cpp:268-293). Host-only."""
 from __future__ import annotations
 
 import ctypes as C
@@ -16,6 +17,48 @@ LN1000 = float(np.float32(3) * np.float32(np.log(np.float32(10.0))))
 
 def _u32(a):
     return np.ascontiguousarray(a if a is not None else [], np.uint32).reshape(-1)
+
+
+def _take_u32(ptr, n):
+    try:
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint32)), (n,)).copy() if n else np.zeros(0, np.uint32)
+    finally:
+        lib().me_bytes_free(ptr)
+
+
+def sample_surface_triangles(triangle_indices, vertex_count, excitation_vertices) -> np.ndarray:
+    """SampleSurfaceTriangles (AudioSystem.cpp:701-746): triangles over the excitation vertices (as indices into
+    `excitation_vertices`), from the mesh's own triangulation collapsed onto them."""
+    tri, ex, out, n = _u32(triangle_indices), _u32(excitation_vertices), C.c_void_p(), C.c_uint32()
+    check(lib().me_sample_surface_triangles(tri.ctypes.data, len(tri), int(vertex_count), ex.ctypes.data, len(ex), C.byref(out), C.byref(n)))
+    return _take_u32(out, n.value)
+
+
+def compact_excitation_vertices(vertices, sample_point_of) -> np.ndarray:
+    """CompactExcitationVertices (AudioSystem.cpp:750-757): the first excitation vertex of every sample point."""
+    v, sp, out, n = _u32(vertices), _u32(sample_point_of), C.c_void_p(), C.c_uint32()
+    check(lib().me_compact_excitation_vertices(v.ctypes.data, len(v), sp.ctypes.data, len(sp), C.byref(out), C.byref(n)))
+    return _take_u32(out, n.value)
+
+
+def relabel_sample_triangles(triangles, sample_point_of) -> np.ndarray:
+    """RelabelSampleTriangles (AudioSystem.cpp:761-769): the sample surface over the sample points the solve merged."""
+    tri, sp, out, n = _u32(triangles), _u32(sample_point_of), C.c_void_p(), C.c_uint32()
+    check(lib().me_relabel_sample_triangles(tri.ctypes.data, len(tri), sp.ctypes.data, len(sp), C.byref(out), C.byref(n)))
+    return _take_u32(out, n.value)
+
+
+def build_tet_mesh_data(points, tets, scale=(1.0, 1.0, 1.0)):
+    """BuildTetMeshData (Tets.cpp:268-293) -> (positions float32 [V][3] in the node's local frame, edge index pairs uint32)."""
+    pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+    tt = np.ascontiguousarray(tets, np.uint32).reshape(-1, 4)
+    sc, pos, edges, n = (C.c_float * 3)(*scale), C.c_void_p(), C.c_void_p(), C.c_uint32()
+    check(lib().me_build_tet_mesh_data(pts.ctypes.data, len(pts), tt.ctypes.data, len(tt), sc, C.byref(pos), C.byref(edges), C.byref(n)))
+    try:
+        positions = np.ctypeslib.as_array(C.cast(pos, C.POINTER(C.c_float)), (3 * len(pts),)).reshape(-1, 3).copy() if len(pts) else np.zeros((0, 3), np.float32)
+    finally:
+        lib().me_bytes_free(pos)
+    return positions, _take_u32(edges, n.value)
 
 
 class ModalModel:
@@ -46,6 +89,26 @@ class ModalModel:
         """modal::mesh2modes on the GPU, keeping the result for serialisation (AudioSystem.cpp:850 -> SaveModalModelFile)."""
         h, status = solve_handle(points, tets, mat, excite_positions, baked_scale, config)
         return cls(h, status, baked_scale=baked_scale, solved_material=mat, **extras)
+
+    @classmethod
+    def generate(cls, tet_points, tets, mat, surface_positions, triangle_indices, vertices, node_scale=(1.0, 1.0, 1.0), config=None, tet_inputs_hash=0):
+        """The modal generation job after tetrahedralization (AudioSystem.cpp:830-862): solve at the excitation vertices'
+        positions, then fill everything SaveModalModelFile stores - ModalModes::Vertices / Indices / BakedScale, the eigen
+        summary's solve settings, the display TetMeshData - so that to_bytes() is the `.modal` file of the job."""
+        from .modal import solver_config
+
+        config = config if config is not None else solver_config()
+        surface = np.ascontiguousarray(surface_positions, np.float32).reshape(-1, 3)
+        vertices = _u32(vertices)
+        sample_triangles = sample_surface_triangles(triangle_indices, len(surface), vertices)
+        h, status = solve_handle(tet_points, tets, mat, surface[vertices], node_scale, config)
+        count = C.c_uint32()
+        sp = lib().me_modal_result_sample_point_of_excitation(h, C.byref(count))
+        sample_point_of = np.ctypeslib.as_array(sp, (count.value,)).astype(np.uint32) if count.value else np.zeros(0, np.uint32)
+        tet_positions, tet_edges = build_tet_mesh_data(tet_points, tets, node_scale)
+        return cls(h, status, vertices=compact_excitation_vertices(vertices, sample_point_of), indices=relabel_sample_triangles(sample_triangles, sample_point_of), baked_scale=node_scale,
+                   tet_positions=tet_positions, tet_edge_indices=tet_edges, solved_material=mat, solved_min_mode_freq=config.min_mode_freq, solved_max_mode_freq=config.max_mode_freq,
+                   solved_num_modes=config.num_modes, tet_inputs_hash=tet_inputs_hash, solved_vertices=vertices)
 
     @classmethod
     def from_bytes(cls, data: bytes):

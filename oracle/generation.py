@@ -1,0 +1,238 @@
+"""TEST INFRASTRUCTURE ONLY (oracle). The generation-job glue either side of modal::mesh2modes, two ways:
+  * a plain-Python restatement of the reference's algorithm (small cases only), each function citing what it follows;
+  * the UNMODIFIED reference functions where oracle/_ref is built: libme_ref_glue.so (the sample-surface helpers cut out of
+    src/audio/AudioSystem.cpp at build time, oracle/ref_glue_driver.cpp) and libme_ref_tet.so (src/mesh/Tets.cpp:
+    BuildTetMeshData, SimplifySurface; oracle/ref_tet_driver.cpp).
+Parity pinned: the restatement is checked against the reference functions live (tests/test_generation_cpu.py) and through
+tests/golden/generation/*.npz, which the reference functions wrote (tests/golden/make_generation_golden.py)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GLUE_SO = os.path.join(HERE, "_ref", "libme_ref_glue.so")
+TET_SO = os.path.join(HERE, "_ref", "libme_ref_tet.so")
+UNLABELLED = 0xFFFFFFFF
+
+
+def have_ref():
+    if not (os.path.exists(GLUE_SO) and os.path.exists(TET_SO)):
+        return False
+    return hasattr(C.CDLL(TET_SO), "ref_build_tet_mesh_data")
+
+
+# ---- restatement --------------------------------------------------------------------------------------------------------
+
+def unique_sample_triangles(windings):
+    """UniqueSampleTriangles (AudioSystem.cpp:675-695): drop triples that repeat a point; one winding per distinct point set,
+    ordered by the sorted set. The reference keeps whichever duplicate its (unstable) sort leaves first; its comment states the
+    intent - the winding first seen - which is what this returns. See windings_of() for what a test may demand of the rest."""
+    first = {}
+    for w in windings:
+        w = tuple(int(x) for x in w)
+        if w[0] == w[1] or w[1] == w[2] or w[0] == w[2]:
+            continue
+        first.setdefault(tuple(sorted(w)), w)
+    return np.array([c for key in sorted(first) for c in first[key]], np.uint32)
+
+
+def windings_of(windings):
+    """Point set -> every winding it was given with (any of them is a legitimate survivor of the reference's unstable sort)."""
+    out = {}
+    for w in windings:
+        w = tuple(int(x) for x in w)
+        if len(set(w)) == 3:
+            out.setdefault(tuple(sorted(w)), set()).add(w)
+    return out
+
+
+def surface_labels(triangle_indices, vertex_count, excitation_vertices):
+    """The breadth-first labelling inside SampleSurfaceTriangles (AudioSystem.cpp:704-736)."""
+    tri = np.asarray(triangle_indices, np.int64).reshape(-1)
+    tri = tri[: len(tri) // 3 * 3].reshape(-1, 3)
+    neighbours = [[] for _ in range(vertex_count)]
+    for t in tri:
+        for k in range(3):
+            neighbours[t[k]] += [int(t[(k + 1) % 3]), int(t[(k + 2) % 3])]
+    label = [UNLABELLED] * vertex_count
+    queue = []
+    for s, v in enumerate(excitation_vertices):
+        if v < vertex_count and label[v] == UNLABELLED:
+            label[v] = s
+            queue.append(int(v))
+    head = 0
+    while head < len(queue):
+        v = queue[head]
+        head += 1
+        for n in neighbours[v]:
+            if label[n] == UNLABELLED:
+                label[n] = label[v]
+                queue.append(n)
+    return label, tri
+
+
+def collapsed_windings(triangle_indices, vertex_count, excitation_vertices):
+    label, tri = surface_labels(triangle_indices, vertex_count, excitation_vertices)
+    return [tuple(label[c] for c in t) for t in tri if all(label[c] != UNLABELLED for c in t)]
+
+
+def sample_surface_triangles(triangle_indices, vertex_count, excitation_vertices):
+    """SampleSurfaceTriangles (AudioSystem.cpp:701-746)."""
+    if len(excitation_vertices) < 3 or len(triangle_indices) < 3:
+        return np.zeros(0, np.uint32)
+    return unique_sample_triangles(collapsed_windings(triangle_indices, vertex_count, excitation_vertices))
+
+
+def compact_excitation_vertices(vertices, sample_point_of):
+    """CompactExcitationVertices (AudioSystem.cpp:750-757)."""
+    out = []
+    for v, sp in zip(vertices, sample_point_of):
+        if sp == len(out):
+            out.append(int(v))
+    return np.array(out, np.uint32)
+
+
+def relabelled_windings(triangles, sample_point_of):
+    tri = np.asarray(triangles, np.int64).reshape(-1)
+    tri = tri[: len(tri) // 3 * 3].reshape(-1, 3)
+    return [tuple(int(sample_point_of[c]) for c in t) for t in tri]
+
+
+def relabel_sample_triangles(triangles, sample_point_of):
+    """RelabelSampleTriangles (AudioSystem.cpp:761-769)."""
+    if len(sample_point_of) == 0:
+        return np.zeros(0, np.uint32)
+    return unique_sample_triangles(relabelled_windings(triangles, sample_point_of))
+
+
+def build_tet_mesh_data(points, tets, scale):
+    """BuildTetMeshData (Tets.cpp:268-293): double points times the double reciprocal of the float scale, to float; the distinct
+    edges (low << 32 | high) ascending."""
+    inv = 1.0 / np.asarray(scale, np.float32).astype(np.float64)
+    positions = (np.asarray(points, np.float64).reshape(-1, 3) * inv).astype(np.float32)
+    t = np.asarray(tets, np.uint64).reshape(-1, 4)
+    pairs = [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]
+    keys = np.concatenate([(np.minimum(t[:, a], t[:, b]) << np.uint64(32)) | np.maximum(t[:, a], t[:, b]) for a, b in pairs]) if len(t) else np.zeros(0, np.uint64)
+    keys = np.unique(keys)
+    edges = np.stack([keys >> np.uint64(32), keys & np.uint64(0xFFFFFFFF)], 1).astype(np.uint32).reshape(-1)
+    return positions, edges
+
+
+# ---- the reference's own functions (oracle/_ref) ---------------------------------------------------------------------------
+
+def _u32(a):
+    return np.ascontiguousarray(a, np.uint32).reshape(-1)
+
+
+def _glue():
+    L = C.CDLL(GLUE_SO)
+    for name, args in {"ref_sample_surface_triangles": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32], "ref_compact_excitation_vertices": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32],
+                       "ref_relabel_sample_triangles": [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]}.items():
+        getattr(L, name).argtypes, getattr(L, name).restype = args, C.c_uint32
+    L.ref_glue_copy.argtypes, L.ref_glue_copy.restype = [C.c_void_p], None
+    return L
+
+
+def _glue_result(L, n):
+    out = np.zeros(n, np.uint32)
+    if n:
+        L.ref_glue_copy(out.ctypes.data)
+    return out
+
+
+def ref_sample_surface_triangles(triangle_indices, vertex_count, excitation_vertices):
+    L, tri, ex = _glue(), _u32(triangle_indices), _u32(excitation_vertices)
+    return _glue_result(L, L.ref_sample_surface_triangles(tri.ctypes.data, len(tri), vertex_count, ex.ctypes.data, len(ex)))
+
+
+def ref_compact_excitation_vertices(vertices, sample_point_of):
+    L, v, sp = _glue(), _u32(vertices), _u32(sample_point_of)
+    return _glue_result(L, L.ref_compact_excitation_vertices(v.ctypes.data, len(v), sp.ctypes.data, len(sp)))
+
+
+def ref_relabel_sample_triangles(triangles, sample_point_of):
+    L, tri, sp = _glue(), _u32(triangles), _u32(sample_point_of)
+    return _glue_result(L, L.ref_relabel_sample_triangles(tri.ctypes.data, len(tri), sp.ctypes.data, len(sp)))
+
+
+def ref_build_tet_mesh_data(points, tets, scale):
+    L = C.CDLL(TET_SO)
+    L.ref_build_tet_mesh_data.argtypes, L.ref_build_tet_mesh_data.restype = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p], C.c_uint32
+    L.ref_tet_data_copy.argtypes, L.ref_tet_data_copy.restype = [C.c_void_p, C.c_void_p], None
+    pts, tt, sc = np.ascontiguousarray(points, np.float64).reshape(-1, 3), np.ascontiguousarray(tets, np.uint32).reshape(-1, 4), np.ascontiguousarray(scale, np.float32)
+    n = L.ref_build_tet_mesh_data(pts.ctypes.data, len(pts), tt.ctypes.data, len(tt), sc.ctypes.data)
+    positions, edges = np.zeros((max(len(pts), 1), 3), np.float32), np.zeros(max(n, 1), np.uint32)
+    L.ref_tet_data_copy(positions.ctypes.data, edges.ctypes.data)
+    return positions[: len(pts)], edges[:n]
+
+
+def ref_simplify_surface(positions, triangle_indices, ratio):
+    """SimplifySurface (Tets.cpp:249-262): fixture generation only."""
+    L = C.CDLL(TET_SO)
+    L.ref_simplify_surface.argtypes, L.ref_simplify_surface.restype = [C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint32), C.c_float], C.c_uint32
+    pos, tri = np.ascontiguousarray(positions, np.float32).reshape(-1, 3).copy(), _u32(triangle_indices).copy()
+    n_tri = C.c_uint32(len(tri))
+    n_pos = L.ref_simplify_surface(pos.ctypes.data, len(pos), tri.ctypes.data, C.byref(n_tri), ratio)
+    return pos[:n_pos].copy(), tri[: n_tri.value].copy()
+
+
+# ---- seeded cases (shared by the golden generator and the tests) ---------------------------------------------------------------
+
+def case(seed):
+    """A closed triangulated surface with a random excitation set, and a plausible SamplePointOfExcitation that merges some of them."""
+    rng = np.random.default_rng(seed)
+    kind = seed % 3
+    if kind == 0:  # torus grid, consistently wound
+        nu, nv = int(rng.integers(5, 14)), int(rng.integers(4, 11))
+        idx = lambda i, j: (i % nu) * nv + (j % nv)  # noqa: E731
+        tri = [c for i in range(nu) for j in range(nv) for c in (idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j), idx(i + 1, j + 1), idx(i, j + 1))]
+        n_vertices = nu * nv
+    elif kind == 1:  # two disjoint shells (tetrahedron boundaries subdivided by a centre fan), one may hold no excitation vertex
+        def shell(base):
+            faces = [(0, 2, 1), (0, 1, 3), (1, 2, 3), (0, 3, 2)]
+            out = []
+            for f, (a, b, c) in enumerate(faces):
+                m = 4 + f
+                out += [a, b, m, b, c, m, c, a, m]
+            return [base + x for x in out]
+        tri, n_vertices = shell(0) + shell(8), 16 + int(rng.integers(0, 3))  # trailing vertices no triangle uses
+    else:  # random triangle soup with repeats and degenerate triangles
+        n_vertices = int(rng.integers(6, 40))
+        tri = rng.integers(0, n_vertices, 3 * int(rng.integers(4, 120))).tolist()
+    n_ex = int(rng.integers(2, max(4, n_vertices // 2)))
+    if kind == 1 and seed % 2:
+        vertices = rng.choice(8, size=min(n_ex, 6), replace=False)  # second shell left without excitation vertices
+    else:
+        vertices = rng.choice(n_vertices, size=min(n_ex, n_vertices), replace=False)
+    if seed % 5 == 0:
+        vertices = np.concatenate([vertices, vertices[:2], [n_vertices + 3]])  # repeats and one out of range
+    # sample points numbered by first appearance, some excitation positions merged into an earlier one
+    sp, count = [], 0
+    for i in range(len(vertices)):
+        if i and rng.random() < 0.25:
+            sp.append(int(rng.integers(0, count)))
+        else:
+            sp.append(count)
+            count += 1
+    return dict(triangles=np.asarray(tri, np.uint32), vertex_count=n_vertices, vertices=np.asarray(vertices, np.uint32), sample_point_of=np.asarray(sp, np.uint32))
+
+
+def tet_case(seed):
+    """A Kuhn block (6 tets per cell) with jittered points and an anisotropic node scale."""
+    rng = np.random.default_rng(1000 + seed)
+    n = [int(x) for x in rng.integers(1, 5, 3)]
+    grid = np.stack(np.meshgrid(*[np.arange(k + 1) for k in n], indexing="ij"), -1).reshape(-1, 3)
+    points = grid * rng.uniform(0.01, 0.3, 3) + rng.normal(0, 1e-3, grid.shape)
+    vid = lambda i, j, k: (i * (n[1] + 1) + j) * (n[2] + 1) + k  # noqa: E731
+    tets = []
+    for i in range(n[0]):
+        for j in range(n[1]):
+            for k in range(n[2]):
+                c = [vid(i + a, j + b, k + d) for a in (0, 1) for b in (0, 1) for d in (0, 1)]
+                for path in ((1, 3), (1, 5), (2, 3), (2, 6), (4, 5), (4, 6)):
+                    tets.append([c[0], c[path[0]], c[path[1]], c[7]])
+    scale = rng.uniform(0.3, 3.0, 3).astype(np.float32) if seed % 2 else np.ones(3, np.float32)
+    return dict(points=np.ascontiguousarray(points, np.float64), tets=np.asarray(tets, np.uint32), scale=scale)

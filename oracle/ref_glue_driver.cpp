@@ -1,0 +1,36 @@
+// TEST INFRASTRUCTURE ONLY (oracle). Never linked into the product library.
+//
+// extern "C" wrapper around the UNMODIFIED sample-surface helpers of the reference's modal generation job
+// (UniqueSampleTriangles, SampleSurfaceTriangles, CompactExcitationVertices, RelabelSampleTriangles:
+// /root/reference/src/audio/AudioSystem.cpp:673-769). AudioSystem.cpp as a whole needs the editor's dependencies, so
+// oracle/Makefile cuts exactly those definitions out of it at build time (glue_slice.inc, written to oracle/_ref/ and removed
+// after compiling) and this file includes them: the code that runs is the reference's, and none of it is stored in the repo.
+#include <algorithm>
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <span>
+#include <vector>
+
+#include "glue_slice.inc"
+
+namespace {
+std::vector<uint32_t> g_out;
+uint32_t Keep(std::vector<uint32_t> v) {
+    g_out = std::move(v);
+    return uint32_t(g_out.size());
+}
+} // namespace
+
+extern "C" {
+uint32_t ref_sample_surface_triangles(const uint32_t *triangle_indices, uint32_t n, uint32_t vertex_count, const uint32_t *excitation_vertices, uint32_t n_ex) {
+    return Keep(SampleSurfaceTriangles({triangle_indices, n}, vertex_count, {excitation_vertices, n_ex}));
+}
+uint32_t ref_compact_excitation_vertices(const uint32_t *vertices, uint32_t n, const uint32_t *sample_point_of, uint32_t n_sp) {
+    return Keep(CompactExcitationVertices({vertices, n}, {sample_point_of, n_sp}));
+}
+uint32_t ref_relabel_sample_triangles(const uint32_t *triangles, uint32_t n, const uint32_t *sample_point_of, uint32_t n_sp) {
+    return Keep(RelabelSampleTriangles({triangles, n}, {sample_point_of, n_sp}));
+}
+void ref_glue_copy(uint32_t *out) { std::memcpy(out, g_out.data(), g_out.size() * sizeof(uint32_t)); }
+}

@@ -1,0 +1,55 @@
+"""Generates tests/golden/generation/glue.npz: outputs of the UNMODIFIED reference functions of the modal generation job
+(SampleSurfaceTriangles / CompactExcitationVertices / RelabelSampleTriangles cut out of src/audio/AudioSystem.cpp, and
+BuildTetMeshData from src/mesh/Tets.cpp; oracle/_ref, `make -C oracle ref`) on the seeded cases of oracle/generation.py, the
+inputs stored beside them, and on BASELINE.json configs[0]'s IcoSphere (its surface, its tet mesh, the solver bench's ten
+excitation vertices), where the big arrays are kept as SHA-256 digests.
+Run: python tests/golden/make_generation_golden.py"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import generation as og  # noqa: E402
+
+SEEDS = list(range(24)) + [100, 101, 102, 205]
+TET_SEEDS = list(range(6))
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def icosphere():
+    z = np.load(os.path.join(ROOT, "tests", "meshes", "icosphere_c1.npz"))
+    n = len(z["surface"])
+    return z, (np.arange(10) * n // 10).astype(np.uint32)  # ModalSolverBench.cpp:220-221
+
+
+if __name__ == "__main__":
+    assert og.have_ref(), "build oracle/_ref first (make -C oracle ref; needs /root/reference)"
+    out = {}
+    for seed in SEEDS:
+        c = og.case(seed)
+        tri = og.ref_sample_surface_triangles(c["triangles"], c["vertex_count"], c["vertices"])
+        for k, v in c.items():
+            out[f"s{seed}_{k}"] = np.asarray(v)
+        out[f"s{seed}_sample_triangles"] = tri
+        out[f"s{seed}_compact"] = og.ref_compact_excitation_vertices(c["vertices"], c["sample_point_of"])
+        out[f"s{seed}_relabelled"] = og.ref_relabel_sample_triangles(tri, c["sample_point_of"])
+    for seed in TET_SEEDS:
+        t = og.tet_case(seed)
+        positions, edges = og.ref_build_tet_mesh_data(t["points"], t["tets"], t["scale"])
+        for k, v in t.items():
+            out[f"t{seed}_{k}"] = v
+        out[f"t{seed}_positions"], out[f"t{seed}_edges"] = positions, edges
+    z, vertices = icosphere()
+    tri = og.ref_sample_surface_triangles(z["triangles"], len(z["surface"]), vertices)
+    out["ico_sample_triangles"] = tri
+    scale = np.array([2.0, 0.5, 1.25], np.float32)
+    positions, edges = og.ref_build_tet_mesh_data(z["points"], z["tets"], scale)
+    out["ico_scale"], out["ico_tet_digests"], out["ico_edge_count"] = scale, np.array([digest(positions), digest(edges)]), np.array(len(edges))
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "generation", "glue.npz"), **out)
+    print(len(out), "arrays;", "icosphere sample triangles", len(tri) // 3, "tet edges", len(edges) // 2)

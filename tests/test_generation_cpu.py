@@ -1,0 +1,120 @@
+"""Generation-job glue (first slice) through the C ABI: the sample surface, ModalModes::Vertices and the display
+TetMeshData the reference's modal generation job builds either side of mesh2modes (AudioSystem.cpp:838-862, Tets.cpp:268-293),
+against outputs of the UNMODIFIED reference functions - committed (tests/golden/generation/glue.npz) and live where
+oracle/_ref is built - and against the restatement in oracle/generation.py. Host-only. Bar: bit-exact (index work; the float
+positions are one rounded product each)."""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from make_generation_golden import SEEDS, TET_SEEDS, icosphere  # noqa: E402
+
+from mesheditor_b200 import MeError  # noqa: E402
+from mesheditor_b200 import interchange as mi  # noqa: E402
+from oracle import generation as og  # noqa: E402
+
+pytestmark = pytest.mark.usefixtures("built_lib")
+
+GOLDEN = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "generation", "glue.npz"))
+
+
+def digest(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def triangle_sets(flat):
+    return np.sort(np.asarray(flat).reshape(-1, 3), axis=1)
+
+
+@pytest.mark.parametrize("seed", SEEDS)
+def test_sample_surface_against_the_reference_outputs(seed):
+    g = {k: GOLDEN[f"s{seed}_{k}"] for k in ("triangles", "vertex_count", "vertices", "sample_point_of", "sample_triangles", "compact", "relabelled")}
+    case = og.case(seed)  # the seeded inputs are reproducible: what is stored is what the generator saw
+    for k in ("triangles", "vertices", "sample_point_of"):
+        np.testing.assert_array_equal(case[k], g[k])
+    tri = mi.sample_surface_triangles(g["triangles"], int(g["vertex_count"]), g["vertices"])
+    np.testing.assert_array_equal(tri, g["sample_triangles"])
+    np.testing.assert_array_equal(mi.compact_excitation_vertices(g["vertices"], g["sample_point_of"]), g["compact"])
+    np.testing.assert_array_equal(mi.relabel_sample_triangles(tri, g["sample_point_of"]), g["relabelled"])
+    # the restatement: same point sets in the same order; a winding that the set was given with (the reference's survivor among
+    # repeated sets is its unstable sort's choice, the restatement returns the first seen); compaction exact
+    port = og.sample_surface_triangles(g["triangles"], int(g["vertex_count"]), g["vertices"])
+    np.testing.assert_array_equal(triangle_sets(port), triangle_sets(tri))
+    given = og.windings_of(og.collapsed_windings(g["triangles"], int(g["vertex_count"]), g["vertices"])) if len(g["vertices"]) >= 3 else {}
+    for w in tri.reshape(-1, 3):
+        assert tuple(int(x) for x in w) in given[tuple(sorted(int(x) for x in w))]
+    np.testing.assert_array_equal(og.compact_excitation_vertices(g["vertices"], g["sample_point_of"]), g["compact"])
+    np.testing.assert_array_equal(triangle_sets(og.relabel_sample_triangles(tri, g["sample_point_of"])), triangle_sets(g["relabelled"]))
+
+
+@pytest.mark.parametrize("seed", TET_SEEDS)
+def test_tet_mesh_data_against_the_reference_outputs(seed):
+    g = {k: GOLDEN[f"t{seed}_{k}"] for k in ("points", "tets", "scale", "positions", "edges")}
+    positions, edges = mi.build_tet_mesh_data(g["points"], g["tets"], g["scale"])
+    np.testing.assert_array_equal(positions, g["positions"]), np.testing.assert_array_equal(edges, g["edges"])
+    port_positions, port_edges = og.build_tet_mesh_data(g["points"], g["tets"], g["scale"])
+    np.testing.assert_array_equal(port_positions, g["positions"]), np.testing.assert_array_equal(port_edges, g["edges"])
+    pairs = edges.reshape(-1, 2).astype(np.int64)
+    assert np.all(pairs[:, 0] < pairs[:, 1]) and np.all(np.diff(pairs[:, 0] * 2**32 + pairs[:, 1]) > 0)  # (low, high), strictly ascending
+
+
+def test_icosphere_of_config1():
+    """BASELINE.json configs[0]: 2,562 surface vertices, ten excitation vertices i*V/10 -> a closed sample surface of 2*10-4
+    triangles; the tet mesh's 14,486 display edges."""
+    z, vertices = icosphere()
+    tri = mi.sample_surface_triangles(z["triangles"], len(z["surface"]), vertices)
+    np.testing.assert_array_equal(tri, GOLDEN["ico_sample_triangles"])
+    assert len(tri) == 3 * 16 and set(tri.tolist()) == set(range(10))
+    # closed and consistently wound: every directed edge once, its reverse once
+    edges = {(int(a), int(b)) for t in tri.reshape(-1, 3) for a, b in ((t[0], t[1]), (t[1], t[2]), (t[2], t[0]))}
+    assert len(edges) == 48 and all((b, a) in edges for a, b in edges)
+    positions, pairs = mi.build_tet_mesh_data(z["points"], z["tets"], GOLDEN["ico_scale"])
+    assert [digest(positions), digest(pairs)] == GOLDEN["ico_tet_digests"].tolist() and len(pairs) == int(GOLDEN["ico_edge_count"]) == 2 * 14486
+    # no merged excitation positions: vertices and triangles pass through the relabelling unchanged
+    identity = np.arange(10, dtype=np.uint32)
+    np.testing.assert_array_equal(mi.compact_excitation_vertices(vertices, identity), vertices)
+    np.testing.assert_array_equal(mi.relabel_sample_triangles(tri, identity), tri)
+
+
+@pytest.mark.skipif(not og.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+def test_against_the_reference_functions_live():
+    for seed in range(300, 420):
+        c = og.case(seed)
+        tri = mi.sample_surface_triangles(c["triangles"], c["vertex_count"], c["vertices"])
+        np.testing.assert_array_equal(tri, og.ref_sample_surface_triangles(c["triangles"], c["vertex_count"], c["vertices"]))
+        np.testing.assert_array_equal(mi.compact_excitation_vertices(c["vertices"], c["sample_point_of"]), og.ref_compact_excitation_vertices(c["vertices"], c["sample_point_of"]))
+        np.testing.assert_array_equal(mi.relabel_sample_triangles(tri, c["sample_point_of"]), og.ref_relabel_sample_triangles(tri, c["sample_point_of"]))
+    for seed in range(20, 40):
+        t = og.tet_case(seed)
+        ours, theirs = mi.build_tet_mesh_data(t["points"], t["tets"], t["scale"]), og.ref_build_tet_mesh_data(t["points"], t["tets"], t["scale"])
+        np.testing.assert_array_equal(ours[0], theirs[0]), np.testing.assert_array_equal(ours[1], theirs[1])
+
+
+def test_edge_cases():
+    tri = np.array([0, 1, 2, 2, 1, 3], np.uint32)
+    empty = np.zeros(0, np.uint32)
+    assert len(mi.sample_surface_triangles(tri, 4, [0, 1])) == 0  # fewer than three excitation vertices
+    assert len(mi.sample_surface_triangles(empty, 4, [0, 1, 2])) == 0  # no triangle
+    np.testing.assert_array_equal(mi.sample_surface_triangles(tri, 4, [0, 1, 2, 3]), [0, 1, 2, 2, 1, 3])  # every vertex its own label
+    np.testing.assert_array_equal(mi.sample_surface_triangles(tri, 4, [3, 2, 1]), [1, 2, 0])  # vertex 0 joins its first-listed neighbour 1: (2,1,1) collapses, (1,2,0) stays
+    with pytest.raises(MeError):
+        mi.sample_surface_triangles(tri, 3, [0, 1, 2])  # a triangle corner outside the vertices
+    assert len(mi.relabel_sample_triangles(tri, empty)) == 0
+    np.testing.assert_array_equal(mi.relabel_sample_triangles(tri, [0, 1, 1, 2]), [])  # (0,1,1) and (1,1,2) both collapse
+    np.testing.assert_array_equal(mi.relabel_sample_triangles([0, 1, 2, 1, 2, 0, 3, 1, 0], [0, 1, 2, 2]), [0, 1, 2])  # three windings of one set: the first survives
+    with pytest.raises(MeError):
+        mi.relabel_sample_triangles(tri, [0, 1, 2])  # corner 3 has no sample point
+    np.testing.assert_array_equal(mi.compact_excitation_vertices([7, 9, 4, 5], [0, 1, 0, 2]), [7, 9, 5])
+    np.testing.assert_array_equal(mi.compact_excitation_vertices([7, 9, 4, 5], [0, 1]), [7, 9])  # the shorter of the two lists bounds the scan
+    assert len(mi.compact_excitation_vertices(empty, empty)) == 0
+    positions, edges = mi.build_tet_mesh_data(np.zeros((0, 3)), np.zeros((0, 4), np.uint32))
+    assert positions.shape == (0, 3) and len(edges) == 0
+    positions, edges = mi.build_tet_mesh_data([[0, 0, 0], [2, 0, 0], [0, 3, 0], [0, 0, 4]], [[3, 1, 2, 0]], (2.0, 3.0, 4.0))
+    np.testing.assert_array_equal(positions, [[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]])
+    np.testing.assert_array_equal(edges, [0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3])
+    with pytest.raises(MeError):
+        mi.build_tet_mesh_data(np.zeros((3, 3)), [[0, 1, 2, 3]])

@@ -3,6 +3,7 @@ on the GPU (up to 30 modes under 16 kHz) -> MeshEditorModalSolve JSON -> KHR_aud
 the strike front-end from the solve's own mass properties -> 1 s of audio at 48 kHz, against the reference bank (oracle) driven by
 the same modes and the same event. Bar: 1e-5 of peak, both forms of the resonator bank."""
 import json
+import os
 
 import numpy as np
 import pytest
@@ -66,3 +67,45 @@ def test_icosphere_solve_to_struck_audio():
     assert peak > 0
     for path in (1, 2):
         assert float(np.abs(render(path) - ref).max()) <= 1e-5 * peak, path
+
+
+def test_generation_job_writes_the_reference_modal_file():
+    """The modal generation job after tetrahedralization (AudioSystem.cpp:830-862) over configs[0]: ten excitation vertices of the
+    IcoSphere's surface, two more that repeat earlier ones (their positions reach the same tet point and merge) -> solve ->
+    ModalModes::Vertices / Indices, eigen summary, TetMeshData -> `.modal` bytes. The reference's own archive (oracle/_ref) over the
+    same fields writes the same bytes, decodes ours to the same model, and the file parses back to it."""
+    from mesheditor_b200 import solver_config
+    from mesheditor_b200.interchange import ModalModel, relabel_sample_triangles, sample_surface_triangles
+    from oracle import generation as og
+    from oracle import interchange as oi
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "meshes", "icosphere_c1.npz"))
+    surface, triangles = z["surface"], z["triangles"]
+    vertices = np.concatenate([(np.arange(10) * len(surface) // 10), [0, 512]]).astype(np.uint32)  # 512 = 2 * 2562 // 10 again
+    scale = (1.0, 1.0, 1.0)
+    cfg = solver_config(num_modes=30, num_fem_modes=45)
+    model = ModalModel.generate(z["points"], z["tets"], "Steel", surface, triangles, vertices, scale, cfg, tet_inputs_hash=0x1234_5678_9ABC)
+    r = model.result
+    assert model.status == 0 and not r.empty and len(r.positions) == 10
+    np.testing.assert_array_equal(r.sample_point_of_excitation, list(range(10)) + [0, 2])
+    np.testing.assert_array_equal(model.vertices, vertices[:10]), np.testing.assert_array_equal(model.solved_vertices, vertices)
+    sample = sample_surface_triangles(triangles, len(surface), vertices)
+    np.testing.assert_array_equal(model.indices, relabel_sample_triangles(sample, r.sample_point_of_excitation))
+    np.testing.assert_array_equal(np.sort(model.indices.reshape(-1, 3), 1), np.sort(og.relabel_sample_triangles(og.sample_surface_triangles(triangles, len(surface), vertices), r.sample_point_of_excitation).reshape(-1, 3), 1))
+    assert len(model.indices) == 3 * 16 and model.indices.max() == 9  # a closed surface over the ten sample points
+    want_positions, want_edges = og.build_tet_mesh_data(z["points"], z["tets"], scale)
+    np.testing.assert_array_equal(model.tet_positions, want_positions), np.testing.assert_array_equal(model.tet_edge_indices, want_edges)
+    assert (model.solved_num_modes, model.solved_min_mode_freq, model.solved_max_mode_freq) == (30, 20.0, 16000.0)
+
+    data = model.to_bytes()
+    back = ModalModel.from_bytes(data)
+    assert back.to_bytes() == data and back.tet_inputs_hash == 0x1234_5678_9ABC
+    np.testing.assert_array_equal(back.indices, model.indices), np.testing.assert_array_equal(back.tet_edge_indices, model.tet_edge_indices)
+    if oi.have_ref():
+        mp, sm = r.mass_props, model.solved_material
+        fields = dict(freqs=r.freqs, t60s=r.t60s, shapes=r.shapes, positions=r.positions, vertices=model.vertices, indices=model.indices, original_fundamental=np.float32(r.original_fundamental),
+                      baked_scale=np.array(scale, np.float32), mass=mp["mass"], com=np.array(mp["center_of_mass"], np.float32), inertia=np.array(mp["inertia_diagonal"], np.float32),
+                      quat_wxyz=np.array(mp["inertia_orientation"], np.float32), tet_positions=model.tet_positions, tet_edges=model.tet_edge_indices, eigenvalues=r.eigenvalues,
+                      summary_shapes=r.summary_shapes, material=np.array([sm.density, sm.young_modulus, sm.poisson_ratio, sm.alpha, sm.beta]), min_freq=np.float32(20), max_freq=np.float32(16000),
+                      num_modes=30, tet_hash=0x1234_5678_9ABC, solved_vertices=model.solved_vertices)
+        assert oi.serialize(fields) == data and oi.parses_to(fields, data) == 1
