@@ -70,6 +70,29 @@ MeStatus me_bank_add_object(MeBank *, uint32_t n_modes, uint32_t n_points, const
 /* TuneModalObject (ModalAudio.cpp:340-393). Valid before and after install (live retune). */
 MeStatus me_bank_tune_object(MeBank *, uint32_t slot, const float *freqs, const float *t60s, uint32_t n,
                              float radius_scale);
+/* Tuning front-end: RetuneModalObject (src/audio/AudioSystem.cpp:263-311) after its scene lookups - what the reference computes
+ * between a stored modal model and TuneModalObject. Host-only float arithmetic, evaluated as the reference does. */
+typedef struct MeRetune {
+    float scale;        /* UniformScaleRatio (ContactScene.h:97-101): me_uniform_scale_ratio; > 0 */
+    float fundamental;  /* ModalTuning::FundamentalFreq; <= 0 keeps the model's own first frequency */
+    float t60_scale;    /* ModalTuning::T60Scale; 1 without a tuning */
+    int has_alpha;      /* the object carries an AcousticMaterial ... */
+    double alpha;       /* ... and this is its Rayleigh alpha: d' = alpha/2 + (d - alpha/2) / scale^2 */
+    float modal_level;  /* ModalControls::ModalLevel */
+    float gain;         /* ModalGain::Value; 1 without */
+} MeRetune;
+/* freqs * (fundamental / freqs[0]) / scale; T60 through the damping law above, times t60_scale; T60 <= 0 stays 0 (muted). */
+MeStatus me_retune_modes(const float *freqs, const float *t60s, uint32_t n, const MeRetune *, float *out_freqs, float *out_t60s);
+/* ModalOutGain (AudioSystem.cpp:221-224): modal_level * gain * scale^-2. */
+float me_modal_out_gain(const MeRetune *);
+/* UniformScaleRatio (ContactScene.h:97-101) over MeanScale (TransformMath.h:17-20): mean |world| / mean |baked| clamped to
+ * 0.001..1000; 1 without a world transform (NULL) or with a zero baked scale. */
+float me_uniform_scale_ratio(const float world_scale[3], const float baked_scale[3]);
+/* UpdateListenerGains (AudioSystem.cpp:232-243): 1/r from the object's node, held at the 1 m mix level inside 1 m. */
+float me_listener_gain(float distance);
+/* RetuneModalObject itself: me_retune_modes -> TuneModalObject(slot, ..., scale) -> OutGain[slot] = me_modal_out_gain
+ * (the listener gain is left as it is). No-op for n == 0. Valid before and after install. */
+MeStatus me_bank_retune_object(MeBank *, uint32_t slot, const float *freqs, const float *t60s, uint32_t n, const MeRetune *);
 /* SetModalObjectShapes (ModalAudio.cpp:395-410). ME_BAD_ARG when the mode/shape layout differs (reference: false). */
 MeStatus me_bank_set_object_shapes(MeBank *, uint32_t slot, uint32_t n_modes, uint32_t n_points,
                                    const float *shapes_xyz);

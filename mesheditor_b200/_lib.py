@@ -83,6 +83,12 @@ class MeSolveProfile(C.Structure):
         (n, C.c_uint32) for n in ("supernodes", "levels", "kernel_launches", "tets_kept")]
 
 
+class MeRetune(C.Structure):
+    """include/me_modal.h MeRetune: RetuneModalObject's inputs after its scene lookups (AudioSystem.cpp:263-311)."""
+
+    _fields_ = [("scale", C.c_float), ("fundamental", C.c_float), ("t60_scale", C.c_float), ("has_alpha", C.c_int), ("alpha", C.c_double), ("modal_level", C.c_float), ("gain", C.c_float)]
+
+
 class MeMassProperties(C.Structure):
     _fields_ = [("mass", C.c_double), ("center_of_mass", C.c_float * 3), ("inertia_diagonal", C.c_float * 3), ("inertia_orientation", C.c_float * 4)]
 
@@ -170,6 +176,8 @@ def lib():
         "me_striker_impactor": [C.POINTER(MeStriker), C.POINTER(MeImpactor)],
         "me_inverse_inertia_tensor": [C.POINTER(MeMassProperties), vp],
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
+        "me_retune_modes": [vp, vp, u32, C.POINTER(MeRetune), vp, vp],
+        "me_bank_retune_object": [vp, u32, vp, vp, u32, C.POINTER(MeRetune)],
         "me_sample_surface_triangles": [vp, u32, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
         "me_compact_excitation_vertices": [vp, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
         "me_relabel_sample_triangles": [vp, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
@@ -191,6 +199,9 @@ def lib():
     for name in ("me_modal_file_free", "me_bytes_free"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = None
+    for name, args in {"me_modal_out_gain": [C.POINTER(MeRetune)], "me_uniform_scale_ratio": [vp, vp], "me_listener_gain": [f32]}.items():
+        getattr(L, name).argtypes = args
+        getattr(L, name).restype = f32
     L.me_recoil_click_filter.argtypes = [f64, f64, f64, f64, vp]
     L.me_recoil_click_filter.restype = None
     for name in ("me_bank_free", "me_modal_result_free", "me_fem_free", "me_factor_free"):

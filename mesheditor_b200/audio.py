@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import ME_QUEUE_FULL, MeModalEvent, MeRenderStats, check, lib
+from ._lib import ME_QUEUE_FULL, MeModalEvent, MeRenderStats, MeRetune, check, lib
 
 MODE_COLUMNS = ["CoeffRe", "CoeffIm", "StateRe", "StateIm", "RadiationGain", "RadiationArea", "OutPhaseIm", "OutPhaseRe", "DeflectionGain", "QuadCompliance", "QuadDriveScale"]
 
@@ -23,6 +23,37 @@ def silence_event(obj):
 
 def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def uniform_scale_ratio(world_scale, baked_scale=(1.0, 1.0, 1.0)) -> float:
+    """UniformScaleRatio (ContactScene.h:97-101); world_scale None = no world transform."""
+    world = None if world_scale is None else (C.c_float * 3)(*world_scale)
+    return lib().me_uniform_scale_ratio(world, (C.c_float * 3)(*baked_scale))
+
+
+def listener_gain(distance) -> float:
+    """UpdateListenerGains (AudioSystem.cpp:232-243)."""
+    return lib().me_listener_gain(distance)
+
+
+def retuning(scale=1.0, fundamental=0.0, t60_scale=1.0, alpha=None, modal_level=1.0, gain=1.0) -> MeRetune:
+    """What RetuneModalObject (AudioSystem.cpp:263-311) looks up in the scene: size ratio, ModalTuning, the material's Rayleigh alpha
+    (None: no AcousticMaterial), ModalControls::ModalLevel, ModalGain::Value."""
+    return MeRetune(scale, fundamental, t60_scale, int(alpha is not None), 0.0 if alpha is None else float(alpha), modal_level, gain)
+
+
+def retune_modes(freqs, t60s, rt: MeRetune):
+    """The tuned (freqs, t60s) RetuneModalObject hands to TuneModalObject (AudioSystem.cpp:271, 299-308)."""
+    freqs, t60s = _f32(freqs), _f32(t60s)
+    n = min(len(freqs), len(t60s))
+    out_f, out_t = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    check(lib().me_retune_modes(freqs.ctypes.data, t60s.ctypes.data, n, C.byref(rt), out_f.ctypes.data, out_t.ctypes.data))
+    return out_f, out_t
+
+
+def modal_out_gain(rt: MeRetune) -> float:
+    """ModalOutGain (AudioSystem.cpp:221-224)."""
+    return lib().me_modal_out_gain(C.byref(rt))
 
 
 class ModalBank:
@@ -62,6 +93,11 @@ class ModalBank:
         check(lib().me_bank_tune_object(self._h, slot, freqs.ctypes.data, t60s.ctypes.data, min(len(freqs), len(t60s)), radius_scale))
 
     retune = tune
+
+    def retune_object(self, slot, freqs, t60s, rt: MeRetune):
+        """RetuneModalObject (AudioSystem.cpp:263-311): tuned modes -> TuneModalObject at the size ratio -> OutGain."""
+        freqs, t60s = _f32(freqs), _f32(t60s)
+        check(lib().me_bank_retune_object(self._h, slot, freqs.ctypes.data, t60s.ctypes.data, min(len(freqs), len(t60s)), C.byref(rt)))
 
     def set_shapes(self, slot, shapes):
         shapes = _f32(shapes)

@@ -194,6 +194,11 @@ void Bank::SetGain(uint32_t slot, float out_gain, float listener_gain) {
     ListenerGain[slot] = listener_gain;
 }
 
+void Bank::SetOutGain(uint32_t slot, float out_gain) {
+    CheckSlot(slot);
+    OutGain[slot] = out_gain;
+}
+
 // Pads every object to whole chunks, places objects so that none of at most 256 chunks straddles a CTA, and uploads
 // the per-mode columns. Also used for live retunes.
 void Bank::UploadTuning(cudaStream_t stream) {

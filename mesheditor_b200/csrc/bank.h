@@ -43,6 +43,7 @@ public:
     void TuneObject(uint32_t slot, const float *freqs, const float *t60s, uint32_t n, float radius_scale);
     void SetObjectShapes(uint32_t slot, uint32_t n_modes, uint32_t n_points, const float *shapes_xyz);
     void SetGain(uint32_t slot, float out_gain, float listener_gain);
+    void SetOutGain(uint32_t slot, float out_gain); // SetModalOutGain (AudioSystem.cpp:227-230): the listener gain stays
     void SetClickGain(float g) { ClickGain = g; }
     void SetMaxImpacts(uint32_t n) { MaxImpacts = n; }
     void SetTimeSegments(uint32_t n) { RequestedSegments = n; }

@@ -5,6 +5,7 @@
 
 #include <mutex>
 #include <new>
+#include <vector>
 
 namespace me {
 namespace {
@@ -83,6 +84,13 @@ struct MeBank {
 
 using me::Fail;
 using me::Guard;
+namespace me {
+// tuning.cpp
+void RetuneModes(const float *freqs, const float *t60s, uint32_t n, const MeRetune &rt, float *out_freqs, float *out_t60s);
+float ModalOutGain(const MeRetune &rt);
+} // namespace me
+using me::ModalOutGain;
+using me::RetuneModes;
 
 extern "C" {
 
@@ -126,6 +134,18 @@ MeStatus me_bank_set_object_shapes(MeBank *b, uint32_t slot, uint32_t n_modes, u
     });
 }
 MeStatus me_bank_set_gain(MeBank *b, uint32_t slot, float out_gain, float listener_gain) { return ME_BANK_CALL(b, b->Impl.SetGain(slot, out_gain, listener_gain)); }
+MeStatus me_bank_retune_object(MeBank *b, uint32_t slot, const float *freqs, const float *t60s, uint32_t n, const MeRetune *rt) {
+    return ME_BANK_CALL(b, {
+        if (!rt || (n && (!freqs || !t60s))) Fail(ME_BAD_ARG, "null argument");
+        if (!(rt->scale > 0)) Fail(ME_BAD_ARG, "scale must be positive");
+        if (!n) return; // RetuneModalObject returns before touching the slot when the model has no modes
+        std::vector<float> tuned_freqs(n);
+        std::vector<float> tuned_t60s(n);
+        RetuneModes(freqs, t60s, n, *rt, tuned_freqs.data(), tuned_t60s.data());
+        b->Impl.TuneObject(slot, tuned_freqs.data(), tuned_t60s.data(), n, rt->scale);
+        b->Impl.SetOutGain(slot, ModalOutGain(*rt));
+    });
+}
 MeStatus me_bank_set_click_gain(MeBank *b, float g) { return ME_BANK_CALL(b, b->Impl.SetClickGain(g)); }
 MeStatus me_bank_set_max_impacts(MeBank *b, uint32_t n) { return ME_BANK_CALL(b, b->Impl.SetMaxImpacts(n)); }
 MeStatus me_bank_set_time_segments(MeBank *b, uint32_t n) { return ME_BANK_CALL(b, b->Impl.SetTimeSegments(n)); }

@@ -1,0 +1,64 @@
+// Tuning front-end: what the reference computes between a stored modal model and TuneModalObject, after its scene lookups
+// (RetuneModalObject, src/audio/AudioSystem.cpp:263-311): the frequency ratio of a fundamental target and a size change, the
+// Rayleigh damping law under uniform scaling, the T60 scale; ModalOutGain (:221-224); UniformScaleRatio / MeanScale
+// (src/audio/ContactScene.h:97-101, src/TransformMath.h:17-20); the listener attenuation of UpdateListenerGains (:232-243).
+// Host code in float, operation for operation as the reference evaluates it, so that the tuned columns are bit-identical.
+#include "common.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numbers>
+
+namespace me {
+
+void RetuneModes(const float *freqs, const float *t60s, uint32_t n, const MeRetune &rt, float *out_freqs, float *out_t60s) {
+    if (!n) return;
+    constexpr float ln1000 = 3 * std::numbers::ln10_v<float>; // ModalAudio.h:46
+    const float scale = rt.scale;
+    // A fundamental target moves every mode by target / first mode; size moves them by 1 / scale.
+    const float ratio = (rt.fundamental > 0 && freqs[0] > 0 ? rt.fundamental / freqs[0] : 1.f) / scale;
+    const float half_alpha = float(rt.alpha / 2);
+    for (uint32_t k = 0; k < n; ++k) {
+        out_freqs[k] = freqs[k] * ratio;
+        if (t60s[k] <= 0) { // the undamped sentinel stays 0 and mutes the mode
+            out_t60s[k] = 0;
+            continue;
+        }
+        // d = (alpha + beta w^2) / 2 with w -> w / scale: the alpha half stays, the rest shrinks by scale^2.
+        float rate = ln1000 / t60s[k];
+        if (rt.has_alpha) rate = half_alpha + (rate - half_alpha) / (scale * scale);
+        out_t60s[k] = rt.t60_scale * ln1000 / std::max(rate, 1e-9f);
+    }
+}
+
+float ModalOutGain(const MeRetune &rt) { return rt.modal_level * rt.gain * std::pow(rt.scale, -2.f); }
+
+} // namespace me
+
+using namespace me;
+
+extern "C" {
+
+MeStatus me_retune_modes(const float *freqs, const float *t60s, uint32_t n, const MeRetune *rt, float *out_freqs, float *out_t60s) {
+    return Guard([&] {
+        if (!rt || (n && (!freqs || !t60s || !out_freqs || !out_t60s))) Fail(ME_BAD_ARG, "null argument");
+        if (!(rt->scale > 0)) Fail(ME_BAD_ARG, "scale must be positive (me_uniform_scale_ratio clamps it to 0.001..1000)");
+        RetuneModes(freqs, t60s, n, *rt, out_freqs, out_t60s);
+    });
+}
+
+float me_modal_out_gain(const MeRetune *rt) { return rt ? ModalOutGain(*rt) : 0.f; }
+
+float me_uniform_scale_ratio(const float *world_scale, const float *baked_scale) {
+    const auto mean = [](const float *s) { return (std::fabs(s[0]) + std::fabs(s[1]) + std::fabs(s[2])) / 3; };
+    if (!world_scale || !baked_scale) return 1.f;
+    const float baked = mean(baked_scale);
+    return baked > 0 ? std::clamp(mean(world_scale) / baked, 0.001f, 1000.f) : 1.f;
+}
+
+float me_listener_gain(float distance) {
+    constexpr float listener_distance = 1.f; // ModalAudio.h:43
+    return listener_distance / std::max(distance, listener_distance);
+}
+
+} // extern "C"

@@ -236,3 +236,46 @@ def tet_case(seed):
                     tets.append([c[0], c[path[0]], c[path[1]], c[7]])
     scale = rng.uniform(0.3, 3.0, 3).astype(np.float32) if seed % 2 else np.ones(3, np.float32)
     return dict(points=np.ascontiguousarray(points, np.float64), tets=np.asarray(tets, np.uint32), scale=scale)
+
+
+# ---- tuning front-end (RetuneModalObject's arithmetic, AudioSystem.cpp:263-311) ----------------------------------------------------
+
+def retune_modes(freqs, t60s, scale=1.0, fundamental=0.0, t60_scale=1.0, alpha=None):
+    """AudioSystem.cpp:271 and :299-308 in float32, one rounding per operation as the reference's float expressions have."""
+    f32 = np.float32
+    freqs, t60s, scale = np.asarray(freqs, f32), np.asarray(t60s, f32), f32(scale)
+    ln1000 = f32(3) * f32(np.log(10.0))
+    ratio = (f32(fundamental) / freqs[0] if fundamental > 0 and freqs[0] > 0 else f32(1)) / scale
+    out_f, out_t = freqs * ratio, np.zeros(len(t60s), f32)
+    half = f32(np.float64(alpha) / 2) if alpha is not None else None
+    for k, t60 in enumerate(t60s):
+        if t60 <= 0:
+            continue
+        d = ln1000 / t60
+        if alpha is not None:
+            d = half + (d - half) / (scale * scale)
+        out_t[k] = f32(t60_scale) * ln1000 / max(d, f32(1e-9))
+    return out_f, out_t
+
+
+def ref_retune_modes(freqs, t60s, scale=1.0, fundamental=0.0, t60_scale=1.0, alpha=None):
+    """The reference's own statements (cut out of RetuneModalObject at build time, oracle/ref_glue_driver.cpp)."""
+    L = C.CDLL(GLUE_SO)
+    L.ref_retune.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    L.ref_retune.restype = None
+    f, t = np.ascontiguousarray(freqs, np.float32), np.ascontiguousarray(t60s, np.float32)
+    out_f, out_t = np.zeros(len(f), np.float32), np.zeros(len(f), np.float32)
+    L.ref_retune(f.ctypes.data, t.ctypes.data, len(f), scale, fundamental, t60_scale, int(alpha is not None), 0.0 if alpha is None else alpha, out_f.ctypes.data, out_t.ctypes.data)
+    return out_f, out_t
+
+
+def retune_case(seed):
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.integers(1, 40))
+    freqs = np.sort(rng.uniform(30, 15000, n)).astype(np.float32)
+    t60s = rng.uniform(1e-3, 8.0, n).astype(np.float32)
+    t60s[rng.random(n) < 0.15] = 0.0  # undamped sentinel
+    if seed % 7 == 0:
+        freqs[0] = 0.0  # no usable fundamental to retarget
+    return dict(freqs=freqs, t60s=t60s, scale=float(np.float32(rng.choice([1.0, 0.001, 1000.0, rng.uniform(0.05, 20.0)]))), fundamental=float(np.float32(rng.choice([0.0, -1.0, rng.uniform(40, 2000)]))),
+                t60_scale=float(np.float32(rng.uniform(0.1, 3.0))), alpha=None if seed % 3 == 0 else float(rng.choice([0.0, 0.5, 5.0, 60.0])))

@@ -14,6 +14,27 @@
 
 #include "glue_slice.inc"
 
+// RetuneModalObject's arithmetic (AudioSystem.cpp:271,299-308): the statements themselves are cut out of the reference like
+// the functions above; this wrapper supplies the names they read (what the function looked up in the scene before them).
+#include <numbers>
+#include <optional>
+namespace {
+constexpr float Ln1000 = 3 * std::numbers::ln10_v<float>; // src/audio/ModalAudio.h:46
+struct {
+    std::vector<float> Freqs, T60s;
+} modes;
+} // namespace
+extern "C" void ref_retune(const float *in_freqs, const float *in_t60s, uint32_t n, float scale, float fundamental, float t60_scale, int has_alpha, double alpha_value, float *out_freqs,
+                           float *out_t60s) {
+    modes.Freqs.assign(in_freqs, in_freqs + n), modes.T60s.assign(in_t60s, in_t60s + n);
+    const size_t mode_count = n;
+    std::optional<double> alpha;
+    if (has_alpha) alpha = alpha_value;
+#include "retune_ratio.inc"
+#include "retune_loop.inc"
+    std::memcpy(out_freqs, freqs.data(), n * sizeof(float)), std::memcpy(out_t60s, t60s.data(), n * sizeof(float));
+}
+
 namespace {
 std::vector<uint32_t> g_out;
 uint32_t Keep(std::vector<uint32_t> v) {

@@ -1,5 +1,6 @@
 """Generation-job glue (first slice) through the C ABI: the sample surface, ModalModes::Vertices and the display
-TetMeshData the reference's modal generation job builds either side of mesh2modes (AudioSystem.cpp:838-862, Tets.cpp:268-293),
+TetMeshData the reference's modal generation job builds either side of mesh2modes (AudioSystem.cpp:838-862, Tets.cpp:268-293), and
+the tuning front-end between a stored model and TuneModalObject (RetuneModalObject, AudioSystem.cpp:263-311),
 against outputs of the UNMODIFIED reference functions - committed (tests/golden/generation/glue.npz) and live where
 oracle/_ref is built - and against the restatement in oracle/generation.py. Host-only. Bar: bit-exact (index work; the float
 positions are one rounded product each)."""
@@ -11,8 +12,9 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_generation_golden import SEEDS, TET_SEEDS, icosphere  # noqa: E402
+from make_generation_golden import RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere  # noqa: E402
 
+import mesheditor_b200 as me  # noqa: E402
 from mesheditor_b200 import MeError  # noqa: E402
 from mesheditor_b200 import interchange as mi  # noqa: E402
 from oracle import generation as og  # noqa: E402
@@ -92,6 +94,43 @@ def test_against_the_reference_functions_live():
         t = og.tet_case(seed)
         ours, theirs = mi.build_tet_mesh_data(t["points"], t["tets"], t["scale"]), og.ref_build_tet_mesh_data(t["points"], t["tets"], t["scale"])
         np.testing.assert_array_equal(ours[0], theirs[0]), np.testing.assert_array_equal(ours[1], theirs[1])
+
+
+@pytest.mark.parametrize("seed", RETUNE_SEEDS)
+def test_retune_against_the_reference_outputs(seed):
+    """RetuneModalObject's arithmetic (AudioSystem.cpp:271, 299-308): bit-exact against what the reference's own statements
+    computed (committed) and compute (live), and against the float32 restatement."""
+    c = og.retune_case(seed)
+    want = GOLDEN[f"r{seed}_freqs"], GOLDEN[f"r{seed}_t60s"]
+    got = me.retune_modes(c["freqs"], c["t60s"], me.retuning(c["scale"], c["fundamental"], c["t60_scale"], c["alpha"]))
+    np.testing.assert_array_equal(got[0], want[0]), np.testing.assert_array_equal(got[1], want[1])
+    port = og.retune_modes(**c)
+    np.testing.assert_array_equal(port[0], want[0]), np.testing.assert_array_equal(port[1], want[1])
+    assert np.all(got[1][c["t60s"] <= 0] == 0) and np.all(got[1][c["t60s"] > 0] > 0)  # the undamped sentinel survives, nothing else becomes it
+    if og.have_ref():
+        live = og.ref_retune_modes(**c)
+        np.testing.assert_array_equal(got[0], live[0]), np.testing.assert_array_equal(got[1], live[1])
+
+
+def test_retune_laws():
+    f32 = np.float32
+    freqs, t60s = np.array([200, 450, 900], f32), np.array([1.0, 0.5, 0.0], f32)
+    same = me.retune_modes(freqs, t60s, me.retuning())
+    np.testing.assert_array_equal(same[0], freqs)
+    np.testing.assert_allclose(same[1], t60s, rtol=3e-7)  # ln1000 / (ln1000 / t60): two roundings
+    up = me.retune_modes(freqs, t60s, me.retuning(fundamental=400.0))
+    np.testing.assert_array_equal(up[0], freqs * f32(2))  # every mode follows the fundamental
+    big = me.retune_modes(freqs, t60s, me.retuning(scale=2.0, alpha=0.0))
+    np.testing.assert_array_equal(big[0], freqs / f32(2))  # twice the size: an octave down ...
+    np.testing.assert_allclose(big[1][:2], t60s[:2] * 4, rtol=3e-7)  # ... and, without mass damping, four times the ring
+    held = me.retune_modes(freqs, t60s, me.retuning(scale=2.0, alpha=2 * 6.9077554))  # all of mode 0's damping is alpha: size leaves it alone
+    np.testing.assert_allclose(held[1][0], 1.0, rtol=1e-6)
+    assert me.modal_out_gain(me.retuning(scale=2.0, modal_level=0.5, gain=3.0)) == 0.375
+    assert me.uniform_scale_ratio((2, -2, 2)) == 2.0 and me.uniform_scale_ratio(None) == 1.0 and me.uniform_scale_ratio((1, 1, 1), (0, 0, 0)) == 1.0
+    assert me.uniform_scale_ratio((1e-9, 0, 0)) == f32(0.001) and me.uniform_scale_ratio((1e9, 0, 0)) == 1000.0 and me.uniform_scale_ratio((3, 3, 3), (1, 2, 3)) == 1.5
+    assert me.listener_gain(0.25) == 1.0 and me.listener_gain(4.0) == 0.25
+    with pytest.raises(MeError):
+        me.retune_modes(freqs, t60s, me.retuning(scale=0.0))
 
 
 def test_edge_cases():
