@@ -110,47 +110,3 @@ def test_generation_job_writes_the_reference_modal_file():
                       num_modes=30, tet_hash=0x1234_5678_9ABC, solved_vertices=model.solved_vertices)
         assert oi.serialize(fields) == data and oi.parses_to(fields, data) == 1
 
-
-def test_retuned_objects_match_the_reference_bank():
-    """RetuneModalObject (AudioSystem.cpp:263-311) through me_bank_retune_object - before install and live, on a ringing bank -
-    against the reference bank tuned with the reference's own retune statements (oracle/_ref; the float32 restatement without it):
-    tuned columns bit-identical, audio within 1e-5 of peak."""
-    from mesheditor_b200 import ModalBank, MeModalEvent, modal_out_gain, retuning
-    from oracle import generation as og
-
-    oracle_cls = orc.RefScene if orc.have_ref() else orc.PortBank
-    retune = og.ref_retune_modes if og.have_ref() else og.retune_modes
-    modes = orc.make_modes(96, 1.5)
-    cases = [dict(scale=1.0, fundamental=0.0, t60_scale=1.0, alpha=None), dict(scale=0.5, fundamental=110.0, t60_scale=0.8, alpha=5.0), dict(scale=2.5, fundamental=0.0, t60_scale=1.6, alpha=0.5)]
-    levels = [(1.0, 1.0), (0.7, 1.3), (0.5, 2.0)]
-    o, g = oracle_cls(48000.0, 1), ModalBank(48000.0, 0)
-
-    def apply(slot, case, level):
-        rt = retuning(case["scale"], case["fundamental"], case["t60_scale"], case["alpha"], modal_level=level[0], gain=level[1])
-        f, t = retune(modes["freqs"], modes["t60s"], **case)
-        o.retune(slot, f, t, case["scale"])
-        o.set_gain(slot, modal_out_gain(rt), 1.0)
-        g.retune_object(slot, modes["freqs"], modes["t60s"], rt)
-
-    for slot, (case, level) in enumerate(zip(cases, levels)):
-        assert o.add_modes(modes) == slot and g.add_modes(modes) == slot
-        apply(slot, case, level)
-    o.install(), g.install()
-
-    def compare_columns():
-        for col in ("CoeffRe", "CoeffIm", "RadiationGain", "OutPhaseRe", "OutPhaseIm"):
-            np.testing.assert_array_equal(g.mode_column(col), o.mode_column(col), err_msg=col)
-
-    compare_columns()
-    for slot in range(3):
-        ev = orc.impact_event(slot, 1.0 + 0.2 * slot, ex_pos=slot)
-        o.enqueue(ev), g.enqueue(MeModalEvent(ev.Kind, ev.Object, ev.ExPos, ev.Jx, ev.Jy, ev.Jz, ev.PulseStep, ev.PulseGamma, ev.AccelAmp, ev.ClickB0, ev.ClickA1, ev.ClickA2))
-    first = o.render_blocks(12), g.render_blocks(12)
-    # live: object 1 grows and loses its fundamental target while it rings, object 2's gain drops
-    apply(1, dict(scale=1.25, fundamental=0.0, t60_scale=1.0, alpha=5.0), (0.7, 1.3))
-    apply(2, cases[2], (0.25, 1.0))
-    compare_columns()
-    second = o.render_blocks(12), g.render_blocks(12)
-    for ref, got in (first, second):
-        peak = float(np.abs(ref).max())
-        assert peak > 0 and float(np.abs(got - ref).max()) <= 1e-5 * peak
