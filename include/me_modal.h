@@ -3,7 +3,8 @@
  * Drop-in boundary for MeshEditor's linear modal hot path. The reference has no FFI layer:
  * the boundary is two C++ free-function APIs, src/audio/ModalAudio.h:297-315 (synthesis) and
  * src/audio/mesh2modes.h:77-88 (analysis). Every entry point below names the reference function it replaces.
- * A header-only C++ shim (include/me_modal_shim.hpp) re-creates the reference's own signatures on top of this ABI.
+ * integration/mesh2modes_b200.cpp re-creates the reference's own analysis signatures on top of this ABI (a replacement
+ * translation unit for src/audio/mesh2modes.cpp); INTEGRATION.md shows the synthesis-side calls.
  *
  * Conventions
  *   - plain pointers and sizes only; inputs are borrowed for the duration of the call;
