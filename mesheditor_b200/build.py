@@ -47,7 +47,10 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, *ARCH, "-shared", "-o", OUT, *objs, "-lcudart"])
+    # Linked beside the target and renamed over it: a reader (or a gpurun snapshot) never sees a half-written library.
+    tmp = os.path.join(HERE, "build", os.path.basename(OUT) + ".link")
+    subprocess.check_call([NVCC, *ARCH, "-shared", "-o", tmp, *objs, "-lcudart"])
+    os.replace(tmp, OUT)
     return OUT
 
 
