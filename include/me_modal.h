@@ -91,6 +91,10 @@ float me_modal_out_gain(const MeRetune *);
 float me_uniform_scale_ratio(const float world_scale[3], const float baked_scale[3]);
 /* UpdateListenerGains (AudioSystem.cpp:232-243): 1/r from the object's node, held at the 1 m mix level inside 1 m. */
 float me_listener_gain(float distance);
+/* MonitorFrames (AudioSystem.cpp:1177-1189), the stage ProcessAudio applies after RenderModal on the device path: pressure in Pa
+ * to device units at 20 Pa full scale, in place, under a limiter whose gain follows the running peak envelope (instant attack,
+ * 100 ms release). *envelope is MonitorLimiter::Envelope (AudioTypes.h:20-22), carried across calls; start it at 0. */
+MeStatus me_monitor_frames(float *frames, uint64_t n, float sample_rate, float *envelope);
 /* RetuneModalObject itself: me_retune_modes -> TuneModalObject(slot, ..., scale) -> OutGain[slot] = me_modal_out_gain
  * (the listener gain is left as it is). No-op for n == 0. Valid before and after install. */
 MeStatus me_bank_retune_object(MeBank *, uint32_t slot, const float *freqs, const float *t60s, uint32_t n, const MeRetune *);

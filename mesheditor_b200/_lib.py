@@ -176,6 +176,7 @@ def lib():
         "me_striker_impactor": [C.POINTER(MeStriker), C.POINTER(MeImpactor)],
         "me_inverse_inertia_tensor": [C.POINTER(MeMassProperties), vp],
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
+        "me_monitor_frames": [vp, u64, f32, C.POINTER(f32)],
         "me_retune_modes": [vp, vp, u32, C.POINTER(MeRetune), vp, vp],
         "me_bank_retune_object": [vp, u32, vp, vp, u32, C.POINTER(MeRetune)],
         "me_sample_surface_triangles": [vp, u32, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],

@@ -36,6 +36,13 @@ def listener_gain(distance) -> float:
     return lib().me_listener_gain(distance)
 
 
+def monitor_frames(frames, sample_rate=48000.0, envelope=0.0):
+    """MonitorFrames (AudioSystem.cpp:1177-1189): pressure -> device units under the monitor limiter. Returns (frames, envelope)."""
+    out, env = np.array(frames, np.float32).reshape(-1), C.c_float(envelope)
+    check(lib().me_monitor_frames(out.ctypes.data, len(out), sample_rate, C.byref(env)))
+    return out, env.value
+
+
 def retuning(scale=1.0, fundamental=0.0, t60_scale=1.0, alpha=None, modal_level=1.0, gain=1.0) -> MeRetune:
     """What RetuneModalObject (AudioSystem.cpp:263-311) looks up in the scene: size ratio, ModalTuning, the material's Rayleigh alpha
     (None: no AcousticMaterial), ModalControls::ModalLevel, ModalGain::Value."""

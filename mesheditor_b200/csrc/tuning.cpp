@@ -1,7 +1,8 @@
 // Tuning front-end: what the reference computes between a stored modal model and TuneModalObject, after its scene lookups
 // (RetuneModalObject, src/audio/AudioSystem.cpp:263-311): the frequency ratio of a fundamental target and a size change, the
 // Rayleigh damping law under uniform scaling, the T60 scale; ModalOutGain (:221-224); UniformScaleRatio / MeanScale
-// (src/audio/ContactScene.h:97-101, src/TransformMath.h:17-20); the listener attenuation of UpdateListenerGains (:232-243).
+// (src/audio/ContactScene.h:97-101, src/TransformMath.h:17-20); the listener attenuation of UpdateListenerGains (:232-243);
+// and the monitor stage after the mix (MonitorFrames, :1177-1189): pressure to device units under a peak-envelope limiter.
 // Host code in float, operation for operation as the reference evaluates it, so that the tuned columns are bit-identical.
 #include "common.h"
 
@@ -54,6 +55,22 @@ float me_uniform_scale_ratio(const float *world_scale, const float *baked_scale)
     if (!world_scale || !baked_scale) return 1.f;
     const float baked = mean(baked_scale);
     return baked > 0 ? std::clamp(mean(world_scale) / baked, 0.001f, 1000.f) : 1.f;
+}
+
+MeStatus me_monitor_frames(float *frames, uint64_t n, float sample_rate, float *envelope) {
+    return Guard([&] {
+        if ((n && !frames) || !envelope) Fail(ME_BAD_ARG, "null argument");
+        if (!(sample_rate > 0)) Fail(ME_BAD_ARG, "sample_rate must be positive");
+        constexpr float full_scale_pressure = 20.f; // Pa: 120 dB SPL (AudioSystem.cpp:1177)
+        const float release = std::exp(-1.f / (0.1f * sample_rate)); // 100 ms
+        float peak = *envelope;
+        for (uint64_t i = 0; i < n; ++i) {
+            const float x = frames[i] / full_scale_pressure;
+            peak = std::max(std::abs(x), peak * release); // instant attack
+            frames[i] = peak > 1.f ? x / peak : x;
+        }
+        *envelope = peak;
+    });
 }
 
 float me_listener_gain(float distance) {

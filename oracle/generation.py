@@ -279,3 +279,38 @@ def retune_case(seed):
         freqs[0] = 0.0  # no usable fundamental to retarget
     return dict(freqs=freqs, t60s=t60s, scale=float(np.float32(rng.choice([1.0, 0.001, 1000.0, rng.uniform(0.05, 20.0)]))), fundamental=float(np.float32(rng.choice([0.0, -1.0, rng.uniform(40, 2000)]))),
                 t60_scale=float(np.float32(rng.uniform(0.1, 3.0))), alpha=None if seed % 3 == 0 else float(rng.choice([0.0, 0.5, 5.0, 60.0])))
+
+
+# ---- monitor stage (MonitorFrames, AudioSystem.cpp:1177-1189) ---------------------------------------------------------------------
+
+def monitor_frames(frames, sample_rate=48000.0, envelope=0.0):
+    """Float32 restatement: x = frame / 20 Pa; envelope = max(|x|, envelope * release); frame = x / envelope above the rail."""
+    f32 = np.float32
+    release = f32(np.exp(np.float64(f32(-1.0) / (f32(0.1) * f32(sample_rate)))))  # expf: the float argument's exponential, rounded once
+    out, env = np.array(frames, f32).reshape(-1), f32(envelope)
+    for i in range(len(out)):
+        x = out[i] / f32(20.0)
+        env = max(abs(x), f32(env * release))
+        out[i] = x / env if env > 1 else x
+    return out, float(env)
+
+
+def ref_monitor_frames(frames, sample_rate=48000.0, envelope=0.0):
+    """The reference's own loop (cut out of MonitorFrames at build time, oracle/ref_glue_driver.cpp)."""
+    L = C.CDLL(GLUE_SO)
+    L.ref_monitor_frames.argtypes, L.ref_monitor_frames.restype = [C.c_void_p, C.c_uint64, C.c_float, C.c_float], C.c_float
+    out = np.array(frames, np.float32).reshape(-1)
+    env = L.ref_monitor_frames(out.ctypes.data, len(out), sample_rate, envelope)
+    return out, float(env)
+
+
+def monitor_case(seed):
+    """Decaying bursts in Pa, some far above the 20 Pa rail, some silent stretches; rendered in two calls to carry the envelope."""
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(200, 3000))
+    t = np.arange(n)
+    x = np.zeros(n)
+    for _ in range(int(rng.integers(1, 6))):
+        start, amp = int(rng.integers(0, n)), float(rng.choice([0.5, 15.0, 25.0, 400.0]))
+        x[start:] += amp * np.exp(-(t[start:] - start) / rng.uniform(20, 800)) * np.sin(0.05 * rng.uniform(1, 40) * (t[start:] - start))
+    return dict(frames=x.astype(np.float32), sample_rate=float(rng.choice([44100.0, 48000.0, 96000.0])), split=int(rng.integers(1, n)))

@@ -55,3 +55,20 @@ uint32_t ref_relabel_sample_triangles(const uint32_t *triangles, uint32_t n, con
 }
 void ref_glue_copy(uint32_t *out) { std::memcpy(out, g_out.data(), g_out.size() * sizeof(uint32_t)); }
 }
+
+// MonitorFrames (AudioSystem.cpp:1177-1189): its constant and loop cut out of the reference; the release coefficient is the
+// function's first statement with the device sample rate passed in (the reference reads it from the registry).
+#include <cmath>
+#include "monitor_const.inc"
+namespace {
+struct MonitorLimiter {
+    float Envelope{0};
+}; // src/audio/AudioTypes.h:20-22
+} // namespace
+extern "C" float ref_monitor_frames(float *data, uint64_t n, float sample_rate, float envelope_in) {
+    MonitorLimiter limiter{envelope_in};
+    std::span<float> frames{data, n};
+    const float release = std::exp(-1.f / (0.1f * float(sample_rate)));
+#include "monitor_loop.inc"
+    return limiter.Envelope;
+}

@@ -1,6 +1,6 @@
 """Generates tests/golden/generation/glue.npz: outputs of the UNMODIFIED reference functions of the modal generation job
 (SampleSurfaceTriangles / CompactExcitationVertices / RelabelSampleTriangles cut out of src/audio/AudioSystem.cpp, and
-BuildTetMeshData from src/mesh/Tets.cpp, the statements of RetuneModalObject; oracle/_ref, `make -C oracle ref`) on the seeded cases of oracle/generation.py, the
+BuildTetMeshData from src/mesh/Tets.cpp, the statements of RetuneModalObject and MonitorFrames; oracle/_ref, `make -C oracle ref`) on the seeded cases of oracle/generation.py, the
 inputs stored beside them, and on BASELINE.json configs[0]'s IcoSphere (its surface, its tet mesh, the solver bench's ten
 excitation vertices), where the big arrays are kept as SHA-256 digests.
 Run: python tests/golden/make_generation_golden.py"""
@@ -17,6 +17,7 @@ from oracle import generation as og  # noqa: E402
 SEEDS = list(range(24)) + [100, 101, 102, 205]
 TET_SEEDS = list(range(6))
 RETUNE_SEEDS = list(range(28))
+MONITOR_SEEDS = list(range(10))
 
 
 def digest(a):
@@ -49,6 +50,11 @@ if __name__ == "__main__":
     for seed in RETUNE_SEEDS:
         c = og.retune_case(seed)
         out[f"r{seed}_freqs"], out[f"r{seed}_t60s"] = og.ref_retune_modes(**c)
+    for seed in MONITOR_SEEDS:
+        c = og.monitor_case(seed)
+        head, env = og.ref_monitor_frames(c["frames"][: c["split"]], c["sample_rate"], 0.0)
+        tail, env = og.ref_monitor_frames(c["frames"][c["split"]:], c["sample_rate"], env)
+        out[f"m{seed}_frames"], out[f"m{seed}_envelope"] = np.concatenate([head, tail]), np.float32(env)
     z, vertices = icosphere()
     tri = og.ref_sample_surface_triangles(z["triangles"], len(z["surface"]), vertices)
     out["ico_sample_triangles"] = tri

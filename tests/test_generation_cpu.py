@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_generation_golden import RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere  # noqa: E402
+from make_generation_golden import MONITOR_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere  # noqa: E402
 
 import mesheditor_b200 as me  # noqa: E402
 from mesheditor_b200 import MeError  # noqa: E402
@@ -133,6 +133,30 @@ def test_retune_laws():
         me.retune_modes(freqs, t60s, me.retuning(scale=0.0))
 
 
+@pytest.mark.parametrize("seed", MONITOR_SEEDS)
+def test_monitor_stage_against_the_reference_outputs(seed):
+    """MonitorFrames (AudioSystem.cpp:1177-1189) in two calls with the envelope carried across: bit-exact against the reference's
+    own loop (committed; live where oracle/_ref is built) and the float32 restatement."""
+    c = og.monitor_case(seed)
+    head, env = me.monitor_frames(c["frames"][: c["split"]], c["sample_rate"], 0.0)
+    tail, env = me.monitor_frames(c["frames"][c["split"]:], c["sample_rate"], env)
+    got = np.concatenate([head, tail])
+    np.testing.assert_array_equal(got, GOLDEN[f"m{seed}_frames"])
+    assert np.float32(env) == GOLDEN[f"m{seed}_envelope"]
+    whole, env_whole = me.monitor_frames(c["frames"], c["sample_rate"])  # splitting the stream changes nothing
+    np.testing.assert_array_equal(whole, got)
+    assert env_whole == env and np.abs(got).max() <= 1.0  # never past the rail
+    port, env_port = og.monitor_frames(c["frames"], c["sample_rate"])
+    np.testing.assert_array_equal(port, got)
+    assert np.float32(env_port) == np.float32(env)
+    quiet = np.abs(c["frames"]) < 1e-3
+    if og.have_ref():
+        live, env_live = og.ref_monitor_frames(c["frames"], c["sample_rate"])
+        np.testing.assert_array_equal(live, got)
+        assert env_live == env
+    assert quiet.sum() == 0 or np.all(np.abs(got[quiet]) <= 1e-3 / 20 + 1e-12)
+
+
 def test_edge_cases():
     tri = np.array([0, 1, 2, 2, 1, 3], np.uint32)
     empty = np.zeros(0, np.uint32)
@@ -157,3 +181,9 @@ def test_edge_cases():
     np.testing.assert_array_equal(edges, [0, 1, 0, 2, 0, 3, 1, 2, 1, 3, 2, 3])
     with pytest.raises(MeError):
         mi.build_tet_mesh_data(np.zeros((3, 3)), [[0, 1, 2, 3]])
+    out, env = me.monitor_frames([], 48000.0, 0.25)
+    assert len(out) == 0 and env == 0.25
+    out, env = me.monitor_frames([10.0, -40.0, 10.0], 48000.0)  # below the rail: plain scaling; above: held at it, and the release keeps the next sample down
+    assert out[0] == 0.5 and out[1] == -1.0 and 0.25 < out[2] < 0.2501 and 1.99 < env < 2.0
+    with pytest.raises(MeError):
+        me.monitor_frames([1.0], 0.0)
