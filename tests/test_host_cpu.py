@@ -104,3 +104,17 @@ def test_workload_generators(built_lib):
     owner = wl.lpt_assign([6.0 * d ** 3 for d in dims], 8)
     loads = np.bincount(owner, weights=[6.0 * d ** 3 for d in dims], minlength=8)
     assert loads.max() / loads.mean() < 1.15  # biggest-first greedy balances the batch
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/audio"), reason="the reference tree is not on this box")
+def test_reference_side_bank_binding_compiles_against_the_reference_headers():
+    """integration/modal_audio_b200.cpp is written against the reference's own ModalAudio.h / ModalModes.h and include/me_modal.h:
+    it must at least be valid C++ there (it cannot run without a GPU, and mesh2modes_b200.cpp needs Eigen, which is not vendored)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = "/root/reference"
+    cmd = ["g++", "-std=c++23", "-fsyntax-only", "-Wall", "-Werror", f"-I{ref}/src", f"-I{root}/include", "-isystem", f"{ref}/lib/glm", "-isystem", f"{ref}/lib/entt/src", "-DGLM_ENABLE_EXPERIMENTAL",
+           os.path.join(root, "integration", "modal_audio_b200.cpp")]
+    done = subprocess.run(cmd, capture_output=True, text=True)
+    assert done.returncode == 0, done.stderr
