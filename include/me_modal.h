@@ -270,6 +270,13 @@ MeStatus me_postprocess_modes(const double *eigenvalues, uint32_t n_eigen, const
  * `solved_material`) under `material`. ME_BAD_ARG when the edit is not exactly scalable (the reference returns nullopt). */
 MeStatus me_rescale_modes(const MeModalResult *solved, const MeMaterial *solved_material, const MeMaterial *material,
                           const MeSolverConfig *config, MeModalResult **out);
+/* What the edit loop hands to me_rescale_modes (src/audio/AudioSystem.cpp:595-616). EffectiveModalMaterial: `props` unless the
+ * object is an authoritative dynamic rigid body (body_mass > 0: its authored mass), in which case density = solved density *
+ * body_mass / solve_mass and Young's modulus scales with it (E / rho kept). RescaledModes' rule for SolverConfig::
+ * FundamentalFreq: a fundamental pinned at solve time (first frequency != OriginalFundamentalFreq > 0) stays pinned; returns
+ * 1 and writes it, else 0. */
+MeStatus me_effective_modal_material(const MeMaterial *props, const MeMaterial *solved, double solve_mass, double body_mass, MeMaterial *out);
+int me_pinned_fundamental(const float *freqs, uint32_t n, float original_fundamental, float *fundamental);
 
 /* --- Stages of the solve, exported for the parity tests and the roofline bench (inner operator concept of
  *     src/audio/CholeskyShiftInvert.h:18-23 and lib/spectra/.../SparseSymMatProd.h:83). ------------------------------ */

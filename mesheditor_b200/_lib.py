@@ -176,6 +176,8 @@ def lib():
         "me_striker_impactor": [C.POINTER(MeStriker), C.POINTER(MeImpactor)],
         "me_inverse_inertia_tensor": [C.POINTER(MeMassProperties), vp],
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
+        "me_effective_modal_material": [C.POINTER(MeMaterial), C.POINTER(MeMaterial), C.c_double, C.c_double, C.POINTER(MeMaterial)],
+        "me_pinned_fundamental": [vp, u32, f32, C.POINTER(f32)],
         "me_monitor_frames": [vp, u64, f32, C.POINTER(f32)],
         "me_retune_modes": [vp, vp, u32, C.POINTER(MeRetune), vp, vp],
         "me_bank_retune_object": [vp, u32, vp, vp, u32, C.POINTER(MeRetune)],

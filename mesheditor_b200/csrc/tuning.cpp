@@ -2,6 +2,8 @@
 // (RetuneModalObject, src/audio/AudioSystem.cpp:263-311): the frequency ratio of a fundamental target and a size change, the
 // Rayleigh damping law under uniform scaling, the T60 scale; ModalOutGain (:221-224); UniformScaleRatio / MeanScale
 // (src/audio/ContactScene.h:97-101, src/TransformMath.h:17-20); the listener attenuation of UpdateListenerGains (:232-243);
+// the material a model's modes re-derive at and the pinned fundamental of the edit loop (EffectiveModalMaterial :595-601,
+// RescaledModes :612-616), which feed me_rescale_modes;
 // and the monitor stage after the mix (MonitorFrames, :1177-1189): pressure to device units under a peak-envelope limiter.
 // Host code in float, operation for operation as the reference evaluates it, so that the tuned columns are bit-identical.
 #include "common.h"
@@ -71,6 +73,25 @@ MeStatus me_monitor_frames(float *frames, uint64_t n, float sample_rate, float *
         }
         *envelope = peak;
     });
+}
+
+MeStatus me_effective_modal_material(const MeMaterial *props, const MeMaterial *solved, double solve_mass, double body_mass, MeMaterial *out) {
+    return Guard([&] {
+        if (!props || !solved || !out) Fail(ME_BAD_ARG, "null argument");
+        *out = *props;
+        // The body's one mass: the modes derive at the density that makes the solve's mass meet it, and the stiffness follows so
+        // that E / rho - and with it every frequency - stays the named material's.
+        if (!(body_mass > 0) || solve_mass <= 0 || solved->density <= 0 || props->density <= 0) return;
+        const double density = solved->density * body_mass / solve_mass;
+        out->young_modulus *= density / props->density;
+        out->density = density;
+    });
+}
+
+int me_pinned_fundamental(const float *freqs, uint32_t n, float original_fundamental, float *fundamental) {
+    const bool pinned = n && freqs && original_fundamental > 0 && freqs[0] != original_fundamental;
+    if (pinned && fundamental) *fundamental = freqs[0];
+    return pinned;
 }
 
 float me_listener_gain(float distance) {

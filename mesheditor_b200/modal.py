@@ -225,3 +225,16 @@ def symbolic_analyse(rowptr, col, xyz):
     perm, info = np.zeros(n, np.uint32), MeSymbolicInfo()
     check(lib().me_symbolic_analyse(n, rowptr.ctypes.data, col.ctypes.data, xyz.ctypes.data, perm.ctypes.data, C.byref(info)))
     return perm, struct_dict(info)
+
+
+def effective_modal_material(props, solved, solve_mass, body_mass=0.0) -> MeMaterial:
+    """EffectiveModalMaterial (AudioSystem.cpp:595-601); body_mass <= 0: not an authoritative dynamic rigid body."""
+    p, s, out = material(props), material(solved), MeMaterial()
+    check(lib().me_effective_modal_material(C.byref(p), C.byref(s), solve_mass, body_mass, C.byref(out)))
+    return out
+
+
+def pinned_fundamental(freqs, original_fundamental):
+    """RescaledModes' rule (AudioSystem.cpp:612-616): the fundamental to keep pinned through a rescale, or None."""
+    f, out = np.ascontiguousarray(freqs, np.float32), C.c_float()
+    return out.value if lib().me_pinned_fundamental(f.ctypes.data, len(f), original_fundamental, C.byref(out)) else None

@@ -314,3 +314,26 @@ def monitor_case(seed):
         start, amp = int(rng.integers(0, n)), float(rng.choice([0.5, 15.0, 25.0, 400.0]))
         x[start:] += amp * np.exp(-(t[start:] - start) / rng.uniform(20, 800)) * np.sin(0.05 * rng.uniform(1, 40) * (t[start:] - start))
     return dict(frames=x.astype(np.float32), sample_rate=float(rng.choice([44100.0, 48000.0, 96000.0])), split=int(rng.integers(1, n)))
+
+
+# ---- edit-loop material glue (EffectiveModalMaterial / RescaledModes, AudioSystem.cpp:595-616) ----------------------------------------
+
+def effective_modal_material(props, solved, solve_mass, body_mass=None):
+    """AudioSystem.cpp:595-601. props / solved: (density, young, poisson, alpha, beta); body_mass None: no authoritative dynamic body."""
+    props = [float(x) for x in props]
+    if body_mass is None or not body_mass > 0 or solve_mass <= 0 or solved[0] <= 0 or props[0] <= 0:
+        return tuple(props)
+    rho = float(solved[0]) * float(np.float32(body_mass)) / solve_mass
+    props[1] *= rho / props[0]
+    props[0] = rho
+    return tuple(props)
+
+
+def ref_effective_modal_material(props, solved, solve_mass, body_mass):
+    """The reference's own statements past the guard (oracle/ref_glue_driver.cpp)."""
+    L = C.CDLL(GLUE_SO)
+    L.ref_effective_material.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_double, C.c_int, C.c_float]
+    L.ref_effective_material.restype = None
+    d, e = C.c_double(props[0]), C.c_double(props[1])
+    L.ref_effective_material(C.byref(d), C.byref(e), solved[0], solve_mass, 1, body_mass)
+    return (d.value, e.value) + tuple(float(x) for x in props[2:])

@@ -72,3 +72,26 @@ extern "C" float ref_monitor_frames(float *data, uint64_t n, float sample_rate, 
 #include "monitor_loop.inc"
     return limiter.Envelope;
 }
+
+// EffectiveModalMaterial (AudioSystem.cpp:595-601): its arithmetic cut out of the reference; the guard is the caller's
+// (oracle/generation.py: an authoritative dynamic body with positive masses and densities).
+namespace {
+struct Properties {
+    double Density, YoungModulus;
+};
+struct Motion {
+    std::optional<float> Mass;
+};
+constexpr float DefaultMass{1}; // src/physics/PhysicsTypes.h:132
+} // namespace
+extern "C" void ref_effective_material(double *density, double *young, double solved_density, double solve_mass, int has_mass, float body_mass) {
+    Properties props{*density, *young};
+    const struct {
+        Properties SolvedMaterial;
+    } summary{{solved_density, 0.0}};
+    Motion body;
+    if (has_mass) body.Mass = body_mass;
+    const Motion *motion = &body;
+#include "effective_material.inc"
+    *density = props.Density, *young = props.YoungModulus;
+}

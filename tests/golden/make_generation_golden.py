@@ -18,6 +18,14 @@ SEEDS = list(range(24)) + [100, 101, 102, 205]
 TET_SEEDS = list(range(6))
 RETUNE_SEEDS = list(range(28))
 MONITOR_SEEDS = list(range(10))
+MATERIAL_SEEDS = list(range(12))
+
+
+def material_case(seed):
+    rng = np.random.default_rng(7000 + seed)
+    props = (float(rng.uniform(500, 9000)), float(rng.uniform(1e9, 3e11)), 0.3, 5.0, 1e-7)
+    solved = (float(rng.uniform(500, 9000)), 2e11, 0.3, 5.0, 1e-7)
+    return props, solved, float(rng.uniform(0.01, 50)), float(np.float32(rng.uniform(0.01, 50)))
 
 
 def digest(a):
@@ -55,6 +63,8 @@ if __name__ == "__main__":
         head, env = og.ref_monitor_frames(c["frames"][: c["split"]], c["sample_rate"], 0.0)
         tail, env = og.ref_monitor_frames(c["frames"][c["split"]:], c["sample_rate"], env)
         out[f"m{seed}_frames"], out[f"m{seed}_envelope"] = np.concatenate([head, tail]), np.float32(env)
+    for seed in MATERIAL_SEEDS:
+        out[f"e{seed}_material"] = np.array(og.ref_effective_modal_material(*material_case(seed))[:2])
     z, vertices = icosphere()
     tri = og.ref_sample_surface_triangles(z["triangles"], len(z["surface"]), vertices)
     out["ico_sample_triangles"] = tri

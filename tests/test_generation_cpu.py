@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_generation_golden import MONITOR_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere  # noqa: E402
+from make_generation_golden import MATERIAL_SEEDS, MONITOR_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere, material_case  # noqa: E402
 
 import mesheditor_b200 as me  # noqa: E402
 from mesheditor_b200 import MeError  # noqa: E402
@@ -155,6 +155,27 @@ def test_monitor_stage_against_the_reference_outputs(seed):
         np.testing.assert_array_equal(live, got)
         assert env_live == env
     assert quiet.sum() == 0 or np.all(np.abs(got[quiet]) <= 1e-3 / 20 + 1e-12)
+
+
+def test_edit_loop_material_glue():
+    """EffectiveModalMaterial and RescaledModes' pinned fundamental (AudioSystem.cpp:595-616), which feed me_rescale_modes: FP64,
+    bit-exact against the reference's statements (committed and live) and the restatement."""
+    from mesheditor_b200 import modal as mm
+
+    for seed in MATERIAL_SEEDS:
+        props, solved, solve_mass, body_mass = material_case(seed)
+        got = mm.effective_modal_material(props, solved, solve_mass, body_mass)
+        assert [got.density, got.young_modulus] == GOLDEN[f"e{seed}_material"].tolist()
+        assert (got.density, got.young_modulus) == og.effective_modal_material(props, solved, solve_mass, body_mass)[:2]
+        assert (got.poisson_ratio, got.alpha, got.beta) == props[2:]
+        assert abs(got.young_modulus / got.density - props[1] / props[0]) <= 1e-15 * props[1] / props[0]  # E / rho kept: every frequency stays
+        assert abs(got.density * solve_mass - solved[0] * body_mass) <= 1e-12 * solved[0] * body_mass  # the solve's mass at that density is the body's
+        if og.have_ref():
+            assert (got.density, got.young_modulus) == og.ref_effective_modal_material(props, solved, solve_mass, body_mass)[:2]
+        for same in (mm.effective_modal_material(props, solved, solve_mass, 0.0), mm.effective_modal_material(props, solved, 0.0, body_mass), mm.effective_modal_material(props, (0.0,) + solved[1:], solve_mass, body_mass)):
+            assert (same.density, same.young_modulus) == props[:2]  # the guard: no authoritative body, no solve mass, no solved density
+    assert mm.pinned_fundamental([440.0, 900.0], 431.5) == 440.0  # matched to a recording at solve time: stays pinned
+    assert mm.pinned_fundamental([431.5, 900.0], 431.5) is None and mm.pinned_fundamental([], 10.0) is None and mm.pinned_fundamental([440.0], 0.0) is None
 
 
 def test_edge_cases():
