@@ -440,6 +440,22 @@ void me_bytes_free(void *);
 MeStatus me_modal_solve_json(const MeModalResult *, const uint32_t *triangle_indices, uint32_t n_triangle_indices, char **json);
 
 /* ------------------------------------------------------------------------------------------------
+ * Impact spectrum analysis (src/audio/AudioSystem.cpp:492-560): the fundamental of a recorded impact, which LaunchModalSolve
+ * passes to the solve as MeSolverConfig::fundamental_freq (:821-829). Host-only.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ComputeFft (:553-558): frames 30 .. sample_rate/16 under a Blackman-Harris window, transformed; complex_re_im receives
+ * n_real/2 + 1 (re, im) pairs in float. With complex_re_im NULL only *n_real is written (size query). ME_BAD_ARG when the
+ * recording is shorter than sample_rate/16 frames. */
+MeStatus me_impact_spectrum(const float *frames, uint64_t n_frames, uint32_t sample_rate, float *complex_re_im, uint64_t *n_real);
+/* EstimateFundamentalFrequency (:522-550): dB spectrum, noise threshold = median of the upper half + 15 dB, first local maximum
+ * from max(50 Hz, bin 15) that stands >= 10 dB above the mean of its +-15 bins; *hz = bin * sample_rate / n_real in whole hertz.
+ * Returns 1 and writes *hz, or 0 (the reference's nullopt). */
+int me_estimate_fundamental_from_spectrum(const float *complex_re_im, uint64_t n_real, uint32_t sample_rate, float *hz);
+/* Both steps: what the reference computes from a recorded impact before a solve. */
+int me_estimate_fundamental(const float *frames, uint64_t n_frames, uint32_t sample_rate, float *hz);
+
+/* ------------------------------------------------------------------------------------------------
  * Generation-job glue (first slice): what the reference's modal generation job does either side of
  * mesh2modes apart from simplifying and tetrahedralizing the surface (src/audio/AudioSystem.cpp:838-862). Host-only.
  * Every *out array is malloc'ed (one element at least, so never NULL on ME_OK): release with me_bytes_free.

@@ -178,6 +178,7 @@ def lib():
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
         "me_effective_modal_material": [C.POINTER(MeMaterial), C.POINTER(MeMaterial), C.c_double, C.c_double, C.POINTER(MeMaterial)],
         "me_pinned_fundamental": [vp, u32, f32, C.POINTER(f32)],
+        "me_impact_spectrum": [vp, u64, u32, vp, C.POINTER(u64)],
         "me_monitor_frames": [vp, u64, f32, C.POINTER(f32)],
         "me_retune_modes": [vp, vp, u32, C.POINTER(MeRetune), vp, vp],
         "me_bank_retune_object": [vp, u32, vp, vp, u32, C.POINTER(MeRetune)],
@@ -205,6 +206,8 @@ def lib():
     for name, args in {"me_modal_out_gain": [C.POINTER(MeRetune)], "me_uniform_scale_ratio": [vp, vp], "me_listener_gain": [f32]}.items():
         getattr(L, name).argtypes = args
         getattr(L, name).restype = f32
+    L.me_estimate_fundamental_from_spectrum.argtypes, L.me_estimate_fundamental_from_spectrum.restype = [vp, u64, u32, C.POINTER(f32)], i32
+    L.me_estimate_fundamental.argtypes, L.me_estimate_fundamental.restype = [vp, u64, u32, C.POINTER(f32)], i32
     L.me_recoil_click_filter.argtypes = [f64, f64, f64, f64, vp]
     L.me_recoil_click_filter.restype = None
     for name in ("me_bank_free", "me_modal_result_free", "me_fem_free", "me_factor_free"):

@@ -238,3 +238,24 @@ def pinned_fundamental(freqs, original_fundamental):
     """RescaledModes' rule (AudioSystem.cpp:612-616): the fundamental to keep pinned through a rescale, or None."""
     f, out = np.ascontiguousarray(freqs, np.float32), C.c_float()
     return out.value if lib().me_pinned_fundamental(f.ctypes.data, len(f), original_fundamental, C.byref(out)) else None
+
+
+def impact_spectrum(frames, sample_rate=48000):
+    """ComputeFft (AudioSystem.cpp:553-558) -> complex64 spectrum of the windowed segment (n_real/2 + 1 bins), n_real."""
+    f, n = np.ascontiguousarray(frames, np.float32), C.c_uint64()
+    check(lib().me_impact_spectrum(f.ctypes.data, len(f), int(sample_rate), None, C.byref(n)))
+    out = np.zeros((n.value // 2 + 1, 2), np.float32)
+    check(lib().me_impact_spectrum(f.ctypes.data, len(f), int(sample_rate), out.ctypes.data, C.byref(n)))
+    return out.view(np.complex64).reshape(-1), n.value
+
+
+def estimate_fundamental_from_spectrum(spectrum, n_real, sample_rate=48000):
+    """EstimateFundamentalFrequency (AudioSystem.cpp:522-550); None where the reference returns nullopt."""
+    s, hz = np.ascontiguousarray(spectrum, np.complex64), C.c_float()
+    return hz.value if lib().me_estimate_fundamental_from_spectrum(s.ctypes.data, int(n_real), int(sample_rate), C.byref(hz)) else None
+
+
+def estimate_fundamental(frames, sample_rate=48000):
+    """The fundamental LaunchModalSolve matches the model to (AudioSystem.cpp:821-829), or None."""
+    f, hz = np.ascontiguousarray(frames, np.float32), C.c_float()
+    return hz.value if lib().me_estimate_fundamental(f.ctypes.data, len(f), int(sample_rate), C.byref(hz)) else None

@@ -337,3 +337,60 @@ def ref_effective_modal_material(props, solved, solve_mass, body_mass):
     d, e = C.c_double(props[0]), C.c_double(props[1])
     L.ref_effective_material(C.byref(d), C.byref(e), solved[0], solve_mass, 1, body_mass)
     return (d.value, e.value) + tuple(float(x) for x in props[2:])
+
+
+# ---- impact spectrum analysis (AudioSystem.cpp:492-560) ------------------------------------------------------------------------------
+
+def impact_spectrum(frames, sample_rate=48000):
+    """ComputeFft (AudioSystem.cpp:553-558) with numpy's transform in place of FFTW: frames 30 .. sample_rate/16 under the float32
+    Blackman-Harris window (CreateBlackmanHarris, :494-513), spectrum rounded to complex64. Returns (spectrum, n_real)."""
+    f32 = np.float32
+    n = sample_rate // 16 - 30
+    i, coeff = np.arange(n, dtype=np.int64), [f32(0.35875), f32(-0.48829), f32(0.14128), f32(-0.01168)]
+    w = np.zeros(n, f32)
+    for j, c in enumerate(coeff):
+        w = (w + c * np.cos(np.pi * ((2 * i * j).astype(f32) / f32(n)).astype(np.float64)).astype(f32)).astype(f32)
+    x = (w * np.asarray(frames, f32)[30:30 + n]).astype(f32)
+    return np.fft.rfft(x.astype(np.float64)).astype(np.complex64), n
+
+
+def estimate_fundamental(spectrum, n_real, sample_rate=48000):
+    """EstimateFundamentalFrequency (AudioSystem.cpp:522-550) in float32."""
+    f32 = np.float32
+    s = np.asarray(spectrum, np.complex64)
+    power = (s.real * s.real + s.imag * s.imag).astype(f32)
+    db = (f32(10) * np.log10(np.maximum(power, f32(1e-20)).astype(np.float64))).astype(f32)
+    bins, reach = len(db), 15
+    upper = np.sort(db[bins // 2:])
+    threshold = f32(upper[len(upper) // 2] + f32(15))
+    for k in range(max(50 * n_real // sample_rate, reach), bins - reach):
+        if db[k] <= db[k - 1] or db[k] <= db[k + 1] or db[k] < threshold:
+            continue
+        total = f32(0)
+        for v in db[k - reach:k + reach + 1]:
+            total = f32(total + v)
+        if f32(db[k] - f32(total / f32(2 * reach + 1))) >= 10:
+            return float(k * sample_rate // n_real)
+    return None
+
+
+def ref_estimate_fundamental(spectrum, n_real, sample_rate=48000):
+    """The reference's own function (cut whole out of AudioSystem.cpp at build time) over the caller's spectrum."""
+    L = C.CDLL(GLUE_SO)
+    L.ref_estimate_fundamental.argtypes, L.ref_estimate_fundamental.restype = [C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(C.c_float)], C.c_int
+    s, hz = np.ascontiguousarray(spectrum, np.complex64), C.c_float()
+    return hz.value if L.ref_estimate_fundamental(s.ctypes.data, n_real, sample_rate, C.byref(hz)) else None
+
+
+def recording_case(seed):
+    """A struck object's recording: decaying partials over a noise floor; some cases hold nothing but noise."""
+    rng = np.random.default_rng(11000 + seed)
+    sample_rate = int(rng.choice([44100, 48000, 96000]))
+    n = sample_rate // 16 + int(rng.integers(0, 500))
+    t = np.arange(n) / sample_rate
+    x = rng.normal(0, 1e-4, n)
+    if seed % 5 != 4:
+        f0 = float(rng.uniform(80, 2500))
+        for h, amp in zip([1.0, 2.76, 5.4, 8.93][: int(rng.integers(1, 5))], [1.0, 0.5, 0.3, 0.2]):
+            x += amp * np.exp(-t * rng.uniform(3, 40)) * np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 6.28))
+    return dict(frames=x.astype(np.float32), sample_rate=sample_rate)

@@ -95,3 +95,26 @@ extern "C" void ref_effective_material(double *density, double *young, double so
 #include "effective_material.inc"
     *density = props.Density, *young = props.YoungModulus;
 }
+
+// EstimateFundamentalFrequency (AudioSystem.cpp:522-550), whole. FFTData (src/audio/FFTData.h) wraps an FFTW plan, which this
+// image does not have; the function reads only the spectrum and the real length, which this stand-in carries (the spectrum is
+// the caller's: numpy's transform of the windowed segment).
+namespace {
+struct FFTData {
+    const float (*Complex)[2];
+    size_t NumReal;
+};
+using std::ranges::nth_element; // AudioSystem.cpp:65
+} // namespace
+#if defined(__GLIBCXX__) && _GLIBCXX_RELEASE < 14
+namespace std {
+inline float log10f(float x) { return ::log10f(x); } // C++23's std::log10f, which this libstdc++ does not declare yet
+} // namespace std
+#endif
+#include "fundamental.inc"
+extern "C" int ref_estimate_fundamental(const float *complex_re_im, uint64_t n_real, uint32_t sample_rate, float *hz) {
+    const FFTData fft{reinterpret_cast<const float (*)[2]>(complex_re_im), size_t(n_real)};
+    const auto found = EstimateFundamentalFrequency(fft, sample_rate);
+    if (found) *hz = *found;
+    return found.has_value();
+}

@@ -1,6 +1,6 @@
 """Generates tests/golden/generation/glue.npz: outputs of the UNMODIFIED reference functions of the modal generation job
 (SampleSurfaceTriangles / CompactExcitationVertices / RelabelSampleTriangles cut out of src/audio/AudioSystem.cpp, and
-BuildTetMeshData from src/mesh/Tets.cpp, the statements of RetuneModalObject and MonitorFrames; oracle/_ref, `make -C oracle ref`) on the seeded cases of oracle/generation.py, the
+BuildTetMeshData from src/mesh/Tets.cpp, the statements of RetuneModalObject, MonitorFrames and EffectiveModalMaterial, EstimateFundamentalFrequency whole; oracle/_ref, `make -C oracle ref`) on the seeded cases of oracle/generation.py, the
 inputs stored beside them, and on BASELINE.json configs[0]'s IcoSphere (its surface, its tet mesh, the solver bench's ten
 excitation vertices), where the big arrays are kept as SHA-256 digests.
 Run: python tests/golden/make_generation_golden.py"""
@@ -19,6 +19,7 @@ TET_SEEDS = list(range(6))
 RETUNE_SEEDS = list(range(28))
 MONITOR_SEEDS = list(range(10))
 MATERIAL_SEEDS = list(range(12))
+RECORDING_SEEDS = list(range(20))
 
 
 def material_case(seed):
@@ -65,6 +66,11 @@ if __name__ == "__main__":
         out[f"m{seed}_frames"], out[f"m{seed}_envelope"] = np.concatenate([head, tail]), np.float32(env)
     for seed in MATERIAL_SEEDS:
         out[f"e{seed}_material"] = np.array(og.ref_effective_modal_material(*material_case(seed))[:2])
+    for seed in RECORDING_SEEDS:  # the reference's estimate over numpy's spectrum of the windowed segment; -1 = nullopt
+        c = og.recording_case(seed)
+        spectrum, n_real = og.impact_spectrum(**c)
+        hz = og.ref_estimate_fundamental(spectrum, n_real, c["sample_rate"])
+        out[f"f{seed}_hz"] = np.float32(-1 if hz is None else hz)
     z, vertices = icosphere()
     tri = og.ref_sample_surface_triangles(z["triangles"], len(z["surface"]), vertices)
     out["ico_sample_triangles"] = tri

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_generation_golden import MATERIAL_SEEDS, MONITOR_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere, material_case  # noqa: E402
+from make_generation_golden import MATERIAL_SEEDS, MONITOR_SEEDS, RECORDING_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere, material_case  # noqa: E402
 
 import mesheditor_b200 as me  # noqa: E402
 from mesheditor_b200 import MeError  # noqa: E402
@@ -178,6 +178,32 @@ def test_edit_loop_material_glue():
     assert mm.pinned_fundamental([431.5, 900.0], 431.5) is None and mm.pinned_fundamental([], 10.0) is None and mm.pinned_fundamental([440.0], 0.0) is None
 
 
+@pytest.mark.parametrize("seed", RECORDING_SEEDS)
+def test_fundamental_of_a_recorded_impact(seed):
+    """ComputeFft + EstimateFundamentalFrequency (AudioSystem.cpp:492-560), the SolverConfig::FundamentalFreq a solve is matched to:
+    the windowed segment's spectrum against numpy's transform (the reference uses FFTW; 1e-6 of the largest bin), the estimate
+    against the reference's own function - committed answers, and live on both spectra - and the float32 restatement."""
+    from mesheditor_b200 import modal as mm
+
+    c = og.recording_case(seed)
+    want = float(GOLDEN[f"f{seed}_hz"])
+    want = None if want < 0 else want
+    spectrum, n_real = mm.impact_spectrum(**c)
+    port_spectrum, port_n = og.impact_spectrum(**c)
+    assert n_real == port_n == c["sample_rate"] // 16 - 30 and len(spectrum) == n_real // 2 + 1
+    assert np.abs(spectrum - port_spectrum).max() <= 1e-6 * np.abs(port_spectrum).max()
+    assert mm.estimate_fundamental(**c) == want
+    assert mm.estimate_fundamental_from_spectrum(port_spectrum, n_real, c["sample_rate"]) == want
+    assert og.estimate_fundamental(port_spectrum, n_real, c["sample_rate"]) == want
+    if seed % 5 == 4:
+        assert want is None  # noise only: no prominent peak, the solve keeps its own fundamental
+    else:
+        assert want is not None and want >= 50
+    if og.have_ref():
+        assert og.ref_estimate_fundamental(port_spectrum, n_real, c["sample_rate"]) == want
+        assert og.ref_estimate_fundamental(spectrum, n_real, c["sample_rate"]) == want
+
+
 def test_edge_cases():
     tri = np.array([0, 1, 2, 2, 1, 3], np.uint32)
     empty = np.zeros(0, np.uint32)
@@ -208,3 +234,8 @@ def test_edge_cases():
     assert out[0] == 0.5 and out[1] == -1.0 and 0.25 < out[2] < 0.2501 and 1.99 < env < 2.0
     with pytest.raises(MeError):
         me.monitor_frames([1.0], 0.0)
+    from mesheditor_b200 import modal as mm
+
+    with pytest.raises(MeError):
+        mm.impact_spectrum(np.zeros(2999, np.float32), 48000)  # shorter than sample_rate / 16 frames
+    assert mm.estimate_fundamental(np.zeros(2999, np.float32), 48000) is None and mm.estimate_fundamental(np.zeros(3000, np.float32), 48000) is None
