@@ -402,6 +402,12 @@ typedef struct MeStrike {
     float sample_rate;            /* bank.SampleRate */
 } MeStrike;
 MeStatus me_make_strike_event(const MeStrike *, MeModalEvent *out);
+/* TiltAlongNormal (AudioSystem.cpp:359-371): the strike direction of a manual hit - the excited vertex's unit normal tilted toward
+ * the surface by a joystick position in the unit disk (centre: along the normal; rim: 90 degrees, in the tangent plane). */
+void me_tilt_along_normal(const float normal[3], const float joystick[2], float out[3]);
+/* SphereEquivalentCurvature (AudioSystem.cpp:379-380): mean curvature, 1/m, of the solid sphere with this mass and density (the
+ * colliding body's MeImpactor::curvature); 0 for an immovable body. */
+double me_sphere_equivalent_curvature(double density, double inv_mass);
 
 /* ------------------------------------------------------------------------------------------------
  * Model interchange: the data formats either side of a modal solve. Host-only.

@@ -197,6 +197,7 @@ def lib():
         "me_reduced_contact_mass": [C.POINTER(MeContactDynamics), u32, vp, C.POINTER(MeImpactor)],
         "me_estimate_contact_time": [C.POINTER(MeContactDynamics), u32, vp, f64, C.POINTER(MeMaterial), f64, f64, C.POINTER(MeImpactor), f64, f64],
         "me_contact_constant": [i32, C.POINTER(MeMaterial), C.POINTER(MeMaterial), f64, f64, f64],
+        "me_sphere_equivalent_curvature": [f64, f64],
     }.items():
         getattr(L, name).argtypes = args
         getattr(L, name).restype = f64
@@ -208,6 +209,7 @@ def lib():
         getattr(L, name).restype = f32
     L.me_estimate_fundamental_from_spectrum.argtypes, L.me_estimate_fundamental_from_spectrum.restype = [vp, u64, u32, C.POINTER(f32)], i32
     L.me_estimate_fundamental.argtypes, L.me_estimate_fundamental.restype = [vp, u64, u32, C.POINTER(f32)], i32
+    L.me_tilt_along_normal.argtypes, L.me_tilt_along_normal.restype = [vp, vp, vp], None
     L.me_recoil_click_filter.argtypes = [f64, f64, f64, f64, vp]
     L.me_recoil_click_filter.restype = None
     for name in ("me_bank_free", "me_modal_result_free", "me_fem_free", "me_factor_free"):

@@ -87,3 +87,15 @@ def make_strike_event(object_slot, excitable_index, force, contact_speed, direct
     out = MeModalEvent()
     check(lib().me_make_strike_event(C.byref(s), C.byref(out)))
     return out
+
+
+def tilt_along_normal(normal, joystick=(0.0, 0.0)) -> np.ndarray:
+    """TiltAlongNormal (AudioSystem.cpp:359-371): a manual strike's direction."""
+    n, j, out = np.ascontiguousarray(normal, np.float32), np.ascontiguousarray(joystick, np.float32), np.zeros(3, np.float32)
+    lib().me_tilt_along_normal(n.ctypes.data, j.ctypes.data, out.ctypes.data)
+    return out
+
+
+def sphere_equivalent_curvature(density, inv_mass) -> float:
+    """SphereEquivalentCurvature (AudioSystem.cpp:379-380)."""
+    return lib().me_sphere_equivalent_curvature(density, inv_mass)

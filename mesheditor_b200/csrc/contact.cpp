@@ -209,4 +209,25 @@ MeStatus me_make_strike_event(const MeStrike *s, MeModalEvent *out) {
     });
 }
 
+// Strike direction and the colliding body's curvature, as TriggerModalStrike's callers prepare them (AudioSystem.cpp:359-379).
+void me_tilt_along_normal(const float normal[3], const float joystick[2], float out[3]) {
+    const float nx = normal[0], ny = normal[1], nz = normal[2], jx = joystick[0], jy = joystick[1];
+    const float radius = std::sqrt(jx * jx + jy * jy);
+    if (radius < 1e-6f) { // the centre of the pad: straight along the normal
+        out[0] = nx, out[1] = ny, out[2] = nz;
+        return;
+    }
+    // Branchless orthonormal tangent frame of the normal (Duff et al. 2017), the one the reference builds.
+    const float sign = nz >= 0 ? 1.f : -1.f;
+    const float a = -1.f / (sign + nz);
+    const float b = nx * ny * a;
+    const float t[3] = {1.f + sign * nx * nx * a, sign * b, -sign * nx};
+    const float bt[3] = {b, sign + ny * ny * a, -ny};
+    const float theta = std::min(radius, 1.f) * 1.57079633f; // the rim lies in the tangent plane
+    const float c = std::cos(theta), s = std::sin(theta);
+    for (int k = 0; k < 3; ++k) out[k] = c * normal[k] + s * (jx * t[k] + jy * bt[k]) / radius;
+}
+
+double me_sphere_equivalent_curvature(double density, double inv_mass) { return std::cbrt(4.0 * std::numbers::pi / 3.0 * density * inv_mass); }
+
 } // extern "C"

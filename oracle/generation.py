@@ -394,3 +394,29 @@ def recording_case(seed):
         for h, amp in zip([1.0, 2.76, 5.4, 8.93][: int(rng.integers(1, 5))], [1.0, 0.5, 0.3, 0.2]):
             x += amp * np.exp(-t * rng.uniform(3, 40)) * np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 6.28))
     return dict(frames=x.astype(np.float32), sample_rate=sample_rate)
+
+
+# ---- strike direction (AudioSystem.cpp:359-380) ----------------------------------------------------------------------------------------
+
+def ref_tilt_along_normal(normal, joystick):
+    L = C.CDLL(GLUE_SO)
+    L.ref_tilt_along_normal.argtypes, L.ref_tilt_along_normal.restype = [C.c_void_p, C.c_void_p, C.c_void_p], None
+    n, j, out = np.ascontiguousarray(normal, np.float32), np.ascontiguousarray(joystick, np.float32), np.zeros(3, np.float32)
+    L.ref_tilt_along_normal(n.ctypes.data, j.ctypes.data, out.ctypes.data)
+    return out
+
+
+def ref_sphere_equivalent_curvature(density, inv_mass):
+    L = C.CDLL(GLUE_SO)
+    L.ref_sphere_equivalent_curvature.argtypes, L.ref_sphere_equivalent_curvature.restype = [C.c_double, C.c_double], C.c_double
+    return L.ref_sphere_equivalent_curvature(density, inv_mass)
+
+
+def direction_case(seed):
+    rng = np.random.default_rng(13000 + seed)
+    n = rng.normal(size=3)
+    if seed % 4 == 0:
+        n = np.array([0.0, 0.0, -1.0 if seed % 8 else 1.0]) + rng.normal(0, 1e-3, 3)  # near the poles of the tangent-frame construction
+    n = (n / np.linalg.norm(n)).astype(np.float32)
+    joy = (rng.uniform(-1.2, 1.2, 2) if seed % 5 else np.zeros(2)).astype(np.float32)  # past the rim clamps; the centre keeps the normal
+    return n, joy

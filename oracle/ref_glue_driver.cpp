@@ -118,3 +118,14 @@ extern "C" int ref_estimate_fundamental(const float *complex_re_im, uint64_t n_r
     if (found) *hz = *found;
     return found.has_value();
 }
+
+// TiltAlongNormal and SphereEquivalentCurvature (AudioSystem.cpp:359-380), whole, over the reference's glm vector types.
+#include "numeric/vec2.h"
+#include "numeric/vec3.h"
+#include <glm/geometric.hpp>
+#include "strike_direction.inc"
+extern "C" void ref_tilt_along_normal(const float *n, const float *joy, float *out) {
+    const vec3 d = TiltAlongNormal({n[0], n[1], n[2]}, {joy[0], joy[1]});
+    out[0] = d.x, out[1] = d.y, out[2] = d.z;
+}
+extern "C" double ref_sphere_equivalent_curvature(double density, double inv_mass) { return SphereEquivalentCurvature(density, inv_mass); }

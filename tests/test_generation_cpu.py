@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_generation_golden import MATERIAL_SEEDS, MONITOR_SEEDS, RECORDING_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere, material_case  # noqa: E402
+from make_generation_golden import DIRECTION_SEEDS, MATERIAL_SEEDS, MONITOR_SEEDS, RECORDING_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere, material_case  # noqa: E402
 
 import mesheditor_b200 as me  # noqa: E402
 from mesheditor_b200 import MeError  # noqa: E402
@@ -202,6 +202,26 @@ def test_fundamental_of_a_recorded_impact(seed):
     if og.have_ref():
         assert og.ref_estimate_fundamental(port_spectrum, n_real, c["sample_rate"]) == want
         assert og.ref_estimate_fundamental(spectrum, n_real, c["sample_rate"]) == want
+
+
+def test_strike_direction_and_colliding_curvature():
+    """TiltAlongNormal / SphereEquivalentCurvature (AudioSystem.cpp:359-380), what TriggerModalStrike's callers hand it: bit-exact
+    against the reference's own functions (committed and live)."""
+    from mesheditor_b200 import contact as mc
+
+    for seed in DIRECTION_SEEDS:
+        n, joy = og.direction_case(seed)
+        got = mc.tilt_along_normal(n, joy)
+        np.testing.assert_array_equal(got, GOLDEN["d_directions"][seed])
+        assert abs(float(np.linalg.norm(got.astype(np.float64))) - 1.0) < 2e-6  # a unit direction
+        reach = min(float(np.hypot(*joy.astype(np.float64))), 1.0)
+        assert abs(float(got.astype(np.float64) @ n.astype(np.float64)) - np.cos(reach * np.pi / 2)) < 2e-6  # tilted by radius * 90 degrees
+        if og.have_ref():
+            np.testing.assert_array_equal(got, og.ref_tilt_along_normal(n, joy))
+    cases = ((7850.0, 2.0), (1000.0, 0.0), (2700.0, 1e3), (750.0, 1e-4))
+    assert [mc.sphere_equivalent_curvature(rho, w) for rho, w in cases] == GOLDEN["d_curvatures"].tolist()
+    radius = 0.05  # a 5 cm steel ball: curvature 1 / radius
+    assert abs(mc.sphere_equivalent_curvature(7850.0, 1.0 / (7850.0 * 4.0 / 3.0 * np.pi * radius**3)) - 1.0 / radius) < 1e-12 / radius
 
 
 def test_edge_cases():
