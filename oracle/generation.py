@@ -1,10 +1,12 @@
-"""TEST INFRASTRUCTURE ONLY (oracle). The generation-job glue either side of modal::mesh2modes, two ways:
-  * a plain-Python restatement of the reference's algorithm (small cases only), each function citing what it follows;
-  * the UNMODIFIED reference functions where oracle/_ref is built: libme_ref_glue.so (the sample-surface helpers cut out of
-    src/audio/AudioSystem.cpp at build time, oracle/ref_glue_driver.cpp) and libme_ref_tet.so (src/mesh/Tets.cpp:
-    BuildTetMeshData, SimplifySurface; oracle/ref_tet_driver.cpp).
-Parity pinned: the restatement is checked against the reference functions live (tests/test_generation_cpu.py) and through
-tests/golden/generation/*.npz, which the reference functions wrote (tests/golden/make_generation_golden.py)."""
+"""TEST INFRASTRUCTURE ONLY (oracle). The host-side steps either side of modal::mesh2modes and RenderModal that
+src/audio/AudioSystem.cpp and src/mesh/Tets.cpp hold - the generation job's sample surface / excitation vertices / TetMeshData,
+RetuneModalObject's arithmetic, MonitorFrames, EffectiveModalMaterial, EstimateFundamentalFrequency, TiltAlongNormal - two ways:
+  * a plain-Python / numpy restatement of the reference's algorithm (small cases only), each function citing what it follows;
+  * the UNMODIFIED reference code where oracle/_ref is built: libme_ref_glue.so (functions and statements cut out of
+    src/audio/AudioSystem.cpp at build time - the file as a whole needs the editor's dependencies - oracle/ref_glue_driver.cpp)
+    and libme_ref_tet.so (src/mesh/Tets.cpp: BuildTetMeshData, SimplifySurface; oracle/ref_tet_driver.cpp).
+Parity pinned: the restatements are checked against the reference code live (tests/test_generation_cpu.py) and through
+tests/golden/generation/glue.npz, which the reference code wrote (tests/golden/make_generation_golden.py)."""
 from __future__ import annotations
 
 import ctypes as C
