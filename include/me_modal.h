@@ -446,6 +446,16 @@ void me_bytes_free(void *);
 MeStatus me_modal_solve_json(const MeModalResult *, const uint32_t *triangle_indices, uint32_t n_triangle_indices, char **json);
 
 /* ------------------------------------------------------------------------------------------------
+ * Rendered audio out: the file WriteWav produces (src/audio/AudioSystem.cpp:1244-1250 over src/audio/WavWriter.h). Host-only.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Mono 32-bit IEEE-float RIFF/WAVE ("fmt " format 3, "fact", "data"). normalize_max > 0 scales the frames by normalize_max /
+ * max(frames), WriteWav's rule. *bytes is malloc'ed: release with me_bytes_free. */
+MeStatus me_wav_encode(const float *frames, uint64_t n, uint32_t sample_rate, float normalize_max, uint8_t **bytes, uint64_t *size);
+/* Reads such a file back (also mono 16-bit PCM, as recorded impacts come); unknown chunks are skipped. *frames is malloc'ed. */
+MeStatus me_wav_decode(const uint8_t *bytes, uint64_t size, float **frames, uint64_t *n, uint32_t *sample_rate);
+
+/* ------------------------------------------------------------------------------------------------
  * Impact spectrum analysis (src/audio/AudioSystem.cpp:492-560): the fundamental of a recorded impact, which LaunchModalSolve
  * passes to the solve as MeSolverConfig::fundamental_freq (:821-829). Host-only.
  * ---------------------------------------------------------------------------------------------- */

@@ -178,6 +178,8 @@ def lib():
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
         "me_effective_modal_material": [C.POINTER(MeMaterial), C.POINTER(MeMaterial), C.c_double, C.c_double, C.POINTER(MeMaterial)],
         "me_pinned_fundamental": [vp, u32, f32, C.POINTER(f32)],
+        "me_wav_encode": [vp, u64, u32, f32, C.POINTER(vp), C.POINTER(u64)],
+        "me_wav_decode": [vp, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)],
         "me_impact_spectrum": [vp, u64, u32, vp, C.POINTER(u64)],
         "me_monitor_frames": [vp, u64, f32, C.POINTER(f32)],
         "me_retune_modes": [vp, vp, u32, C.POINTER(MeRetune), vp, vp],

@@ -43,6 +43,27 @@ def monitor_frames(frames, sample_rate=48000.0, envelope=0.0):
     return out, env.value
 
 
+def wav_bytes(frames, sample_rate=48000, normalize_max=None) -> bytes:
+    """WriteWav (AudioSystem.cpp:1244-1250): mono float32 RIFF/WAVE, optionally normalised to `normalize_max`."""
+    f, out, size = _f32(frames).reshape(-1), C.c_void_p(), C.c_uint64()
+    check(lib().me_wav_encode(f.ctypes.data, len(f), int(sample_rate), 0.0 if normalize_max is None else normalize_max, C.byref(out), C.byref(size)))
+    try:
+        return C.string_at(out, size.value)
+    finally:
+        lib().me_bytes_free(out)
+
+
+def wav_frames(data: bytes):
+    """The frames and sample rate of a mono float32 (or int16) RIFF/WAVE file."""
+    buf, out, n, rate = np.frombuffer(data, np.uint8), C.c_void_p(), C.c_uint64(), C.c_uint32()
+    check(lib().me_wav_decode(buf.ctypes.data, len(buf), C.byref(out), C.byref(n), C.byref(rate)))
+    try:
+        frames = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_float)), (n.value,)).copy() if n.value else np.zeros(0, np.float32)
+    finally:
+        lib().me_bytes_free(out)
+    return frames, rate.value
+
+
 def retuning(scale=1.0, fundamental=0.0, t60_scale=1.0, alpha=None, modal_level=1.0, gain=1.0) -> MeRetune:
     """What RetuneModalObject (AudioSystem.cpp:263-311) looks up in the scene: size ratio, ModalTuning, the material's Rayleigh alpha
     (None: no AcousticMaterial), ModalControls::ModalLevel, ModalGain::Value."""
