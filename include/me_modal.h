@@ -402,6 +402,12 @@ typedef struct MeStrike {
     float sample_rate;            /* bank.SampleRate */
 } MeStrike;
 MeStatus me_make_strike_event(const MeStrike *, MeModalEvent *out);
+/* UpdateContactDynamics (src/audio/ContactDynamics.cpp:19-46) past its registry lookups. `resolved`: the solve's mass properties, or
+ * the authoritative rigid body's (then mass_scale = 1); mass_scale: ModalDensityRatio (:13-17), material density / solved density.
+ * Outputs fill an MeContactDynamics: mass * mass_scale, InverseInertiaTensor / mass_scale, arms = (position - centre of mass) *
+ * MeanScale(baked_scale) for every sample point ([n_positions][3]). */
+MeStatus me_contact_dynamics(const MeMassProperties *resolved, double mass_scale, const float *positions_xyz, uint32_t n_positions, const float baked_scale[3], double *mass,
+                             float inverse_inertia[9], float *arms_xyz);
 /* TiltAlongNormal (AudioSystem.cpp:359-371): the strike direction of a manual hit - the excited vertex's unit normal tilted toward
  * the surface by a joystick position in the unit disk (centre: along the normal; rim: 90 degrees, in the tangent plane). */
 void me_tilt_along_normal(const float normal[3], const float joystick[2], float out[3]);

@@ -176,6 +176,7 @@ def lib():
         "me_striker_impactor": [C.POINTER(MeStriker), C.POINTER(MeImpactor)],
         "me_inverse_inertia_tensor": [C.POINTER(MeMassProperties), vp],
         "me_make_strike_event": [C.POINTER(MeStrike), C.POINTER(MeModalEvent)],
+        "me_contact_dynamics": [C.POINTER(MeMassProperties), C.c_double, vp, u32, vp, C.POINTER(C.c_double), vp, vp],
         "me_effective_modal_material": [C.POINTER(MeMaterial), C.POINTER(MeMaterial), C.c_double, C.c_double, C.POINTER(MeMaterial)],
         "me_pinned_fundamental": [vp, u32, f32, C.POINTER(f32)],
         "me_wav_encode": [vp, u64, u32, f32, C.POINTER(vp), C.POINTER(u64)],

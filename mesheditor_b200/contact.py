@@ -51,6 +51,15 @@ class ContactDynamics:
         self.c = MeContactDynamics(mass, (C.c_float * 9)(*np.asarray(inverse_inertia, np.float32).reshape(-1)), self.arms.ctypes.data, len(self.arms))
 
 
+def contact_dynamics(mass_props: dict, positions, baked_scale=(1.0, 1.0, 1.0), mass_scale=1.0) -> ContactDynamics:
+    """UpdateContactDynamics (ContactDynamics.cpp:19-46): from a solve's mass properties (ModalResult.mass_props) and sample points."""
+    mp = MeMassProperties(mass_props["mass"], (C.c_float * 3)(*mass_props["center_of_mass"]), (C.c_float * 3)(*mass_props["inertia_diagonal"]), (C.c_float * 4)(*mass_props["inertia_orientation"]))
+    pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+    mass, inverse, arms = C.c_double(), np.zeros(9, np.float32), np.zeros_like(pos)
+    check(lib().me_contact_dynamics(C.byref(mp), mass_scale, pos.ctypes.data, len(pos), (C.c_float * 3)(*baked_scale), C.byref(mass), inverse.ctypes.data, arms.ctypes.data))
+    return ContactDynamics(mass.value, inverse, arms)
+
+
 def _dir(d):
     return np.ascontiguousarray(d, np.float32)
 

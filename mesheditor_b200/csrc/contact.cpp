@@ -209,6 +209,23 @@ MeStatus me_make_strike_event(const MeStrike *s, MeModalEvent *out) {
     });
 }
 
+// UpdateContactDynamics (src/audio/ContactDynamics.cpp:19-46) past its registry lookups: the ContactDynamics a strike's contact time
+// is estimated with, from the mass properties the lookups resolved (the solve's, or an authoritative rigid body's) and the model.
+MeStatus me_contact_dynamics(const MeMassProperties *resolved, double mass_scale, const float *positions_xyz, uint32_t n_positions, const float baked_scale[3], double *mass,
+                             float inverse_inertia[9], float *arms_xyz) {
+    return Guard([&] {
+        if (!resolved || !baked_scale || !mass || !inverse_inertia || (n_positions && (!positions_xyz || !arms_xyz))) Fail(ME_BAD_ARG, "null argument");
+        const float size = std::max((std::fabs(baked_scale[0]) + std::fabs(baked_scale[1]) + std::fabs(baked_scale[2])) / 3, 1e-6f);
+        *mass = resolved->mass * mass_scale;
+        if (const MeStatus status = me_inverse_inertia_tensor(resolved, inverse_inertia); status != ME_OK) throw Failure{status};
+        const float lighten = float(1 / mass_scale); // a denser material is as much heavier as it is harder to turn
+        for (int k = 0; k < 9; ++k) inverse_inertia[k] *= lighten;
+        // Arms from the centre of mass to each sample point, node-local lengths brought to metres at the baked size.
+        for (uint32_t p = 0; p < n_positions; ++p)
+            for (int k = 0; k < 3; ++k) arms_xyz[3 * p + k] = (positions_xyz[3 * p + k] - resolved->center_of_mass[k]) * size;
+    });
+}
+
 // Strike direction and the colliding body's curvature, as TriggerModalStrike's callers prepare them (AudioSystem.cpp:359-379).
 void me_tilt_along_normal(const float normal[3], const float joystick[2], float out[3]) {
     const float nx = normal[0], ny = normal[1], nz = normal[2], jx = joystick[0], jy = joystick[1];

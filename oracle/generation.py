@@ -422,3 +422,28 @@ def direction_case(seed):
     n = (n / np.linalg.norm(n)).astype(np.float32)
     joy = (rng.uniform(-1.2, 1.2, 2) if seed % 5 else np.zeros(2)).astype(np.float32)  # past the rim clamps; the centre keeps the normal
     return n, joy
+
+
+# ---- contact dynamics (UpdateContactDynamics, src/audio/ContactDynamics.cpp:19-46) ----------------------------------------------------
+
+AUDIO_SO = os.path.join(HERE, "_ref", "libme_ref_audio.so")
+
+
+def ref_contact_dynamics(mass, com, inertia_diagonal, quat_wxyz, mass_scale, positions, baked_scale):
+    """The reference's own statements past the registry lookups (oracle/ref_audio_driver.cpp) -> (mass, inverse inertia[9], arms)."""
+    L = C.CDLL(AUDIO_SO)
+    L.ref_contact_dynamics.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+    L.ref_contact_dynamics.restype = C.c_uint32
+    f = lambda a: np.ascontiguousarray(a, np.float32)  # noqa: E731
+    com, diag, quat, pos, baked = f(com), f(inertia_diagonal), f(quat_wxyz), f(positions).reshape(-1, 3), f(baked_scale)
+    out_mass, inverse, arms = C.c_double(), np.zeros(9, np.float32), np.zeros_like(pos)
+    L.ref_contact_dynamics(mass, com.ctypes.data, diag.ctypes.data, quat.ctypes.data, mass_scale, pos.ctypes.data, len(pos), baked.ctypes.data, C.byref(out_mass), inverse.ctypes.data, arms.ctypes.data)
+    return out_mass.value, inverse, arms
+
+
+def dynamics_case(seed):
+    rng = np.random.default_rng(15000 + seed)
+    q = rng.normal(size=4)
+    return dict(mass=float(rng.uniform(0.01, 40)), com=rng.normal(0, 0.05, 3).astype(np.float32), inertia_diagonal=rng.uniform(1e-5, 2, 3).astype(np.float32),
+                quat_wxyz=(q / np.linalg.norm(q)).astype(np.float32), mass_scale=1.0 if seed % 3 == 0 else float(rng.uniform(0.2, 4)),
+                positions=rng.normal(0, 0.2, (int(rng.integers(1, 12)), 3)).astype(np.float32), baked_scale=(rng.uniform(-3, 3, 3) if seed % 4 else np.zeros(3)).astype(np.float32))

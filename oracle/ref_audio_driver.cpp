@@ -167,6 +167,27 @@ void ref_striker_impactor(const double *material, float tip_radius, float length
     const auto imp = StrikerImpactor(RefStriker(material, tip_radius, length));
     curvature_invmass[0] = imp.Curvature, curvature_invmass[1] = imp.InvMass;
 }
+// UpdateContactDynamics (src/audio/ContactDynamics.cpp:19-46) past its registry lookups: `resolved` and `mass_scale` are what the
+// lookups leave, `modes` the model; the statements between are the reference's own (cut out at build time, oracle/Makefile).
+#include "mean_scale.inc"
+uint32_t ref_contact_dynamics(double mass, const float *com, const float *inertia_diagonal, const float *quat_wxyz, double mass_scale, const float *positions, uint32_t n,
+                              const float *baked, double *out_mass, float *out_inverse_inertia9, float *out_arms) {
+    MassProperties resolved;
+    resolved.Mass = mass;
+    resolved.CenterOfMass = vec3{com[0], com[1], com[2]};
+    resolved.InertiaDiagonal = vec3{inertia_diagonal[0], inertia_diagonal[1], inertia_diagonal[2]};
+    resolved.InertiaOrientation = glm::quat{quat_wxyz[0], quat_wxyz[1], quat_wxyz[2], quat_wxyz[3]};
+    ModalModes model;
+    for (uint32_t i = 0; i < n; ++i) model.Positions.emplace_back(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]);
+    model.BakedScale = vec3{baked[0], baked[1], baked[2]};
+    const ModalModes *modes = &model;
+#include "contact_dynamics.inc"
+    *out_mass = cd.Mass;
+    for (int c = 0; c < 3; ++c)
+        for (int r = 0; r < 3; ++r) out_inverse_inertia9[3 * c + r] = cd.InverseInertia[c][r];
+    for (uint32_t i = 0; i < n; ++i) out_arms[3 * i] = cd.ContactArm[i].x, out_arms[3 * i + 1] = cd.ContactArm[i].y, out_arms[3 * i + 2] = cd.ContactArm[i].z;
+    return uint32_t(cd.ContactArm.size());
+}
 void ref_inverse_inertia(double mass, const float *inertia_diagonal, const float *quat_wxyz, float *out9) {
     MassProperties mp;
     mp.Mass = mass;

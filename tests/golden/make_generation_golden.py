@@ -21,6 +21,7 @@ MONITOR_SEEDS = list(range(10))
 MATERIAL_SEEDS = list(range(12))
 RECORDING_SEEDS = list(range(20))
 DIRECTION_SEEDS = list(range(40))
+DYNAMICS_SEEDS = list(range(16))
 
 
 def material_case(seed):
@@ -74,6 +75,9 @@ if __name__ == "__main__":
         out[f"f{seed}_hz"] = np.float32(-1 if hz is None else hz)
     out["d_directions"] = np.stack([og.ref_tilt_along_normal(*og.direction_case(seed)) for seed in DIRECTION_SEEDS])
     out["d_curvatures"] = np.array([og.ref_sphere_equivalent_curvature(rho, w) for rho, w in ((7850.0, 2.0), (1000.0, 0.0), (2700.0, 1e3), (750.0, 1e-4))])
+    for seed in DYNAMICS_SEEDS:
+        mass, inverse, arms = og.ref_contact_dynamics(**og.dynamics_case(seed))
+        out[f"c{seed}_mass"], out[f"c{seed}_inverse"], out[f"c{seed}_arms"] = np.float64(mass), inverse, arms
     z, vertices = icosphere()
     tri = og.ref_sample_surface_triangles(z["triangles"], len(z["surface"]), vertices)
     out["ico_sample_triangles"] = tri

@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
-from make_generation_golden import DIRECTION_SEEDS, MATERIAL_SEEDS, MONITOR_SEEDS, RECORDING_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere, material_case  # noqa: E402
+from make_generation_golden import DIRECTION_SEEDS, DYNAMICS_SEEDS, MATERIAL_SEEDS, MONITOR_SEEDS, RECORDING_SEEDS, RETUNE_SEEDS, SEEDS, TET_SEEDS, icosphere, material_case  # noqa: E402
 
 import mesheditor_b200 as me  # noqa: E402
 from mesheditor_b200 import MeError  # noqa: E402
@@ -222,6 +222,25 @@ def test_strike_direction_and_colliding_curvature():
     assert [mc.sphere_equivalent_curvature(rho, w) for rho, w in cases] == GOLDEN["d_curvatures"].tolist()
     radius = 0.05  # a 5 cm steel ball: curvature 1 / radius
     assert abs(mc.sphere_equivalent_curvature(7850.0, 1.0 / (7850.0 * 4.0 / 3.0 * np.pi * radius**3)) - 1.0 / radius) < 1e-12 / radius
+
+
+@pytest.mark.parametrize("seed", DYNAMICS_SEEDS)
+def test_contact_dynamics_against_the_reference_outputs(seed):
+    """UpdateContactDynamics (ContactDynamics.cpp:19-46) past its registry lookups - the ContactDynamics a strike's contact time is
+    estimated with, from a solve's mass properties and sample points: bit-exact against the reference's statements."""
+    from mesheditor_b200 import contact as mc
+
+    c = og.dynamics_case(seed)
+    d = mc.contact_dynamics(dict(mass=c["mass"], center_of_mass=c["com"], inertia_diagonal=c["inertia_diagonal"], inertia_orientation=c["quat_wxyz"]), c["positions"], c["baked_scale"], c["mass_scale"])
+    assert d.c.mass == float(GOLDEN[f"c{seed}_mass"]) == c["mass"] * c["mass_scale"]
+    np.testing.assert_array_equal(np.array(list(d.c.inverse_inertia), np.float32), GOLDEN[f"c{seed}_inverse"])
+    np.testing.assert_array_equal(d.arms, GOLDEN[f"c{seed}_arms"])
+    if not c["baked_scale"].any():
+        assert np.abs(d.arms).max() <= 1e-6 * np.abs(c["positions"] - c["com"]).max() * 1.01  # a zero baked scale is held at 1e-6
+    if og.have_ref():
+        mass, inverse, arms = og.ref_contact_dynamics(**c)
+        assert d.c.mass == mass
+        np.testing.assert_array_equal(np.array(list(d.c.inverse_inertia), np.float32), inverse), np.testing.assert_array_equal(d.arms, arms)
 
 
 def test_edge_cases():
