@@ -483,6 +483,9 @@ int me_estimate_fundamental(const float *frames, uint64_t n_frames, uint32_t sam
  * Every *out array is malloc'ed (one element at least, so never NULL on ME_OK): release with me_bytes_free.
  * ---------------------------------------------------------------------------------------------- */
 
+/* DesiredSolveVertices (AudioSystem.cpp:667-671) without copied sound vertices: clamp(requested, 1, num_vertices) excitation
+ * vertices, i * num_vertices / count. */
+MeStatus me_desired_solve_vertices(uint32_t requested, uint32_t num_vertices, uint32_t **out, uint32_t *n_out);
 /* SampleSurfaceTriangles (AudioSystem.cpp:701-746): the mesh's triangulation collapsed onto the excitation vertices. Every
  * mesh vertex takes the excitation vertex (its index in `excitation_vertices`) it reaches in the fewest edges; a triangle whose
  * corners took three different ones contributes a triangle; one triangle per distinct point set, ordered by the sorted set, in

@@ -185,6 +185,7 @@ def lib():
         "me_monitor_frames": [vp, u64, f32, C.POINTER(f32)],
         "me_retune_modes": [vp, vp, u32, C.POINTER(MeRetune), vp, vp],
         "me_bank_retune_object": [vp, u32, vp, vp, u32, C.POINTER(MeRetune)],
+        "me_desired_solve_vertices": [u32, u32, C.POINTER(vp), C.POINTER(u32)],
         "me_sample_surface_triangles": [vp, u32, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
         "me_compact_excitation_vertices": [vp, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],
         "me_relabel_sample_triangles": [vp, u32, vp, u32, C.POINTER(vp), C.POINTER(u32)],

@@ -143,6 +143,19 @@ MeStatus me_relabel_sample_triangles(const uint32_t *triangles, uint32_t n_trian
     });
 }
 
+MeStatus me_desired_solve_vertices(uint32_t requested, uint32_t num_vertices, uint32_t **out, uint32_t *n_out) {
+    return Guard([&] {
+        if (!out || !n_out) Fail(ME_BAD_ARG, "null argument");
+        if (!num_vertices) Fail(ME_BAD_ARG, "a mesh without vertices has nothing to excite");
+        // Evenly spaced over the mesh's vertex order, capped at the vertex count so that none is taken twice; the products stay in
+        // 32 bits, as the reference's do.
+        const uint32_t count = std::clamp(requested, 1u, num_vertices);
+        std::vector<uint32_t> picked(count);
+        for (uint32_t i = 0; i < count; ++i) picked[i] = i * num_vertices / count;
+        *out = Export(picked), *n_out = count;
+    });
+}
+
 MeStatus me_build_tet_mesh_data(const double *points_xyz, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const float scale[3], float **positions_xyz, uint32_t **edge_indices,
                                 uint32_t *n_edge_indices) {
     return Guard([&] {

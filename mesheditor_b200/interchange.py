@@ -26,6 +26,13 @@ def _take_u32(ptr, n):
         lib().me_bytes_free(ptr)
 
 
+def desired_solve_vertices(requested, num_vertices) -> np.ndarray:
+    """DesiredSolveVertices (AudioSystem.cpp:667-671): evenly spaced excitation vertices."""
+    out, n = C.c_void_p(), C.c_uint32()
+    check(lib().me_desired_solve_vertices(int(requested), int(num_vertices), C.byref(out), C.byref(n)))
+    return _take_u32(out, n.value)
+
+
 def sample_surface_triangles(triangle_indices, vertex_count, excitation_vertices) -> np.ndarray:
     """SampleSurfaceTriangles (AudioSystem.cpp:701-746): triangles over the excitation vertices (as indices into
     `excitation_vertices`), from the mesh's own triangulation collapsed onto them."""

@@ -447,3 +447,10 @@ def dynamics_case(seed):
     return dict(mass=float(rng.uniform(0.01, 40)), com=rng.normal(0, 0.05, 3).astype(np.float32), inertia_diagonal=rng.uniform(1e-5, 2, 3).astype(np.float32),
                 quat_wxyz=(q / np.linalg.norm(q)).astype(np.float32), mass_scale=1.0 if seed % 3 == 0 else float(rng.uniform(0.2, 4)),
                 positions=rng.normal(0, 0.2, (int(rng.integers(1, 12)), 3)).astype(np.float32), baked_scale=(rng.uniform(-3, 3, 3) if seed % 4 else np.zeros(3)).astype(np.float32))
+
+
+def ref_desired_solve_vertices(requested, num_vertices):
+    """DesiredSolveVertices (AudioSystem.cpp:667-671) past its copied-vertices branch, the reference's own statements."""
+    L = _glue()
+    L.ref_desired_solve_vertices.argtypes, L.ref_desired_solve_vertices.restype = [C.c_uint32, C.c_uint32], C.c_uint32
+    return _glue_result(L, L.ref_desired_solve_vertices(requested, num_vertices))

@@ -129,3 +129,32 @@ extern "C" void ref_tilt_along_normal(const float *n, const float *joy, float *o
     out[0] = d.x, out[1] = d.y, out[2] = d.z;
 }
 extern "C" double ref_sphere_equivalent_curvature(double density, double inv_mass) { return SphereEquivalentCurvature(density, inv_mass); }
+
+// DesiredSolveVertices (AudioSystem.cpp:667-671) past its copied-vertices branch.
+#include <ranges>
+namespace {
+using std::ranges::iota_view; // AudioSystem.cpp:65-66
+using std::views::transform;
+#if defined(__GLIBCXX__) && _GLIBCXX_RELEASE < 14
+// C++23's std::ranges::to, which this libstdc++ does not have yet: the one use below collects a view into a vector.
+template<typename Container>
+struct Collect {};
+template<typename Container>
+Collect<Container> to() { return {}; }
+template<std::ranges::input_range Range, typename Container>
+Container operator|(Range &&range, Collect<Container>) {
+    Container out;
+    for (auto &&v : range) out.push_back(v);
+    return out;
+}
+#else
+using std::ranges::to;
+#endif
+std::vector<uint32_t> EvenVertices(uint32_t requested, uint32_t num_vertices) {
+    const struct {
+        uint32_t NumVertices;
+    } settings{requested};
+#include "solve_vertices.inc"
+}
+} // namespace
+extern "C" uint32_t ref_desired_solve_vertices(uint32_t requested, uint32_t num_vertices) { return Keep(EvenVertices(requested, num_vertices)); }

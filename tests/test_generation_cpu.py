@@ -243,6 +243,22 @@ def test_contact_dynamics_against_the_reference_outputs(seed):
         np.testing.assert_array_equal(np.array(list(d.c.inverse_inertia), np.float32), inverse), np.testing.assert_array_equal(d.arms, arms)
 
 
+def test_desired_solve_vertices():
+    """DesiredSolveVertices (AudioSystem.cpp:667-671): i * V / count, count clamped to 1..V; the 32-bit products wrap as the reference's."""
+    cases = [(10, 2562), (1, 7), (0, 7), (50, 7), (7, 7), (3, 100000), (70000, 70000)]
+    for requested, n in cases:
+        got = mi.desired_solve_vertices(requested, n)
+        count = min(max(requested, 1), n)
+        want = ((np.arange(count, dtype=np.uint64) * n) % 2**32 // count).astype(np.uint32)
+        np.testing.assert_array_equal(got, want)
+        if og.have_ref():
+            np.testing.assert_array_equal(got, og.ref_desired_solve_vertices(requested, n))
+    np.testing.assert_array_equal(mi.desired_solve_vertices(10, 2562), icosphere()[1])  # the solver bench's rule on configs[0]
+    assert len(set(mi.desired_solve_vertices(50, 7).tolist())) == 7  # capped: no vertex twice
+    with pytest.raises(MeError):
+        mi.desired_solve_vertices(3, 0)
+
+
 def test_edge_cases():
     tri = np.array([0, 1, 2, 2, 1, 3], np.uint32)
     empty = np.zeros(0, np.uint32)
