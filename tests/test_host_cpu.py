@@ -118,3 +118,13 @@ def test_reference_side_bank_binding_compiles_against_the_reference_headers():
            os.path.join(root, "integration", "modal_audio_b200.cpp")]
     done = subprocess.run(cmd, capture_output=True, text=True)
     assert done.returncode == 0, done.stderr
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/me_modal.h must compile as C11 and as C++17 on its own, warnings as errors."""
+    import subprocess
+
+    header = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "me_modal.h")
+    for compiler, lang, std in (("gcc", "c", "-std=c11"), ("g++", "c++", "-std=c++17")):
+        done = subprocess.run([compiler, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", lang, header], capture_output=True, text=True)
+        assert done.returncode == 0, done.stderr
