@@ -235,8 +235,10 @@ typedef struct MeModalResult MeModalResult; /* modal::ModalResult (mesh2modes.h:
  *   warm path runs: subspace iteration over NumFemModes + 15 columns to config->warm_tolerance
  *   (SubspaceIterate, mesh2modes.cpp:339-428, selected at :459-472); any other seed falls back to the cold solve;
  *   keep_basis: fill the result's basis (SolveReuse::KeepBasis).
- * Status mirrors the reference's failure modes: ME_CANCELLED / ME_NOT_CONVERGED / ME_NO_MODES leave *out holding an
- * EMPTY result (the reference returns an empty ModalResult); ME_FACTOR_FAILED is the reference's std::runtime_error. */
+ * Status mirrors the reference's failure modes. A cancel seen right after assembly leaves *out EMPTY (mesh2modes.cpp:616
+ * returns `{}`). ME_NOT_CONVERGED, and a cancel seen later (inside ComputeModes, :462,479,490), leave *out with empty modes,
+ * eigen summary and basis but WITH the mass properties, the profile and the excitation remap, as :655-657 still build
+ * them. ME_NO_MODES keeps everything but the (empty) modes. ME_FACTOR_FAILED is the reference's std::runtime_error. */
 MeStatus me_modal_solve(const double *points_xyz, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const MeMaterial *material,
                         const float *excite_xyz, uint32_t n_excite, const float baked_scale[3], const MeSolverConfig *config,
                         const float *seed_basis, uint32_t seed_rows, uint32_t seed_cols, int keep_basis, MeJobMonitor *monitor,
@@ -267,7 +269,10 @@ const float *me_modal_result_basis(const MeModalResult *, uint32_t *rows, uint32
 MeStatus me_postprocess_modes(const double *eigenvalues, uint32_t n_eigen, const float *shapes, uint32_t n_points, float shape_scale,
                               const MeMaterial *material, const MeSolverConfig *config, const float *positions, MeModalResult **out);
 /* modal::RescaleModes (mesh2modes.h:88, mesh2modes.cpp:590-603), host-only: re-derives the modes of `solved` (solved with
- * `solved_material`) under `material`. ME_BAD_ARG when the edit is not exactly scalable (the reference returns nullopt). */
+ * `solved_material`) under `material`. ME_BAD_ARG when the edit is not exactly scalable (the reference returns nullopt).
+ * Like the reference, the eigen summary is left untouched: *out carries the SOLVED eigenvalues / summary shapes / mass
+ * properties / excitation remap next to the rescaled modes, so it can be rescaled again (always against `solved_material`)
+ * or archived with me_modal_file_serialize and the original solved material. */
 MeStatus me_rescale_modes(const MeModalResult *solved, const MeMaterial *solved_material, const MeMaterial *material,
                           const MeSolverConfig *config, MeModalResult **out);
 /* What the edit loop hands to me_rescale_modes (src/audio/AudioSystem.cpp:595-616). EffectiveModalMaterial: `props` unless the

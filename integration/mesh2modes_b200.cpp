@@ -54,28 +54,34 @@ modal::ModalResult modal::mesh2modes(const TetMesh &tets, const AcousticMaterial
     const MeSolverConfig c_config = ToC(config);
     const float scale[3]{baked_scale.x, baked_scale.y, baked_scale.z};
     // JobMonitor holds std::atomics; mirror it into the plain-C monitor from a watcher thread while the solve runs.
+    // The C monitor is a plain struct the library polls through volatile reads; this side touches it through atomic_ref only.
     MeJobMonitor c_monitor{0.f, 0};
     std::atomic<bool> done{false};
     std::thread watcher;
+    const auto mirror = [&] {
+        if (monitor->Cancelled()) std::atomic_ref<int>(c_monitor.cancelled).store(1, std::memory_order_relaxed);
+        monitor->Progress.store(std::atomic_ref<float>(c_monitor.progress).load(std::memory_order_relaxed), std::memory_order_relaxed);
+    };
     if (monitor) watcher = std::thread([&] {
-        while (!done.load(std::memory_order_relaxed)) {
-            if (monitor->Cancelled()) c_monitor.cancelled = 1;
-            monitor->Progress.store(c_monitor.progress, std::memory_order_relaxed);
+        while (!done.load(std::memory_order_acquire)) {
+            mirror();
             std::this_thread::sleep_for(std::chrono::milliseconds(2));
         }
     });
     ResultGuard guard;
     const float *seed = reuse.SeedBasis ? reuse.SeedBasis->data() : nullptr; // Eigen::MatrixXf is column-major
-    const MeStatus status = me_modal_solve(&tets.Points[0].x, uint32_t(tets.Points.size()), tets.Tets[0].data(), uint32_t(tets.Tets.size()), &c_material,
+    const MeStatus status = me_modal_solve(tets.Points.empty() ? nullptr : &tets.Points[0].x, uint32_t(tets.Points.size()), tets.Tets.empty() ? nullptr : tets.Tets[0].data(), uint32_t(tets.Tets.size()), &c_material,
                                            excite_positions.empty() ? nullptr : &excite_positions[0].x, uint32_t(excite_positions.size()), scale, &c_config, seed,
                                            seed ? uint32_t(reuse.SeedBasis->rows()) : 0, seed ? uint32_t(reuse.SeedBasis->cols()) : 0, reuse.KeepBasis, monitor ? &c_monitor : nullptr, &guard.R);
-    done = true;
+    done.store(true, std::memory_order_release);
     if (watcher.joinable()) watcher.join();
+    if (monitor) mirror(); // the watcher may have slept through the last store: the final progress (1.0) is copied here
     if (status == ME_FACTOR_FAILED) throw std::runtime_error(me_last_error()); // CholeskyShiftInvert.cpp:44
-    if (status != ME_OK && status != ME_NO_MODES) {
-        if (status == ME_CANCELLED || status == ME_NOT_CONVERGED) return {}; // the reference's empty result
-        throw std::runtime_error(me_last_error());
-    }
+    // ME_CANCELLED / ME_NOT_CONVERGED / ME_NO_MODES: the library hands back what the reference does — nothing at all for a cancel
+    // seen right after assembly (mesh2modes.cpp:616), and empty Modes / Summary / Basis around the mass properties, profile and
+    // excitation remap for a failure inside ComputeModes (:462,479,490 return from ComputeModes, :655-657 still build the result).
+    if (status != ME_OK && status != ME_NO_MODES && status != ME_CANCELLED && status != ME_NOT_CONVERGED) throw std::runtime_error(me_last_error());
+    if (!guard.R) return {};
     ModalResult out;
     const MeModalResult *r = guard.R;
     out.Modes = ModesOf(r);
@@ -92,7 +98,7 @@ modal::ModalResult modal::mesh2modes(const TetMesh &tets, const AcousticMaterial
     out.Summary.Shapes.assign(points, std::vector<vec3>(pairs));
     for (uint32_t q = 0; q < points; ++q)
         for (uint32_t k = 0; k < pairs; ++k) out.Summary.Shapes[q][k] = {ss[(size_t(q) * pairs + k) * 3], ss[(size_t(q) * pairs + k) * 3 + 1], ss[(size_t(q) * pairs + k) * 3 + 2]};
-    out.Summary.SolvedMaterial = material;
+    if (pairs) out.Summary.SolvedMaterial = material; // ComputeModes fills the summary only on success (:503-506)
     uint32_t rows = 0, cols = 0, count = 0;
     if (const float *basis = me_modal_result_basis(r, &rows, &cols)) out.Basis = Eigen::Map<const Eigen::MatrixXf>(basis, rows, cols);
     const uint32_t *remap = me_modal_result_sample_point_of_excitation(r, &count);

@@ -80,6 +80,7 @@ void Bank::CheckSlot(uint32_t slot) const {
 }
 void Bank::RequireInstalled() const {
     if (!Installed) Fail(ME_BAD_ARG, "the bank has not been installed (me_bank_install)");
+    if (NeedsReinstall) Fail(ME_BAD_ARG, "objects were added after me_bank_install: install the bank again before rendering (%u slots, %u installed)", ObjectCount(), InstalledObjects);
 }
 
 // AddModalObject, ModalAudio.cpp:291-338.
@@ -90,6 +91,10 @@ uint32_t Bank::AddObject(uint32_t count, uint32_t n_points, const float *shapes,
     const auto slot = ObjectCount();
     const size_t k0 = CoeffRe.size();
     ++TuningVersion;
+    // The reference never grows a live bank: RebuildModalBank builds the next one and InstallModalBank swaps it in
+    // (ModalAudio.cpp:277-289). A slot added after me_bank_install changes the padded layout the device buffers were sized
+    // for, so rendering is refused until the bank is installed again.
+    if (Installed) NeedsReinstall = true;
     ModeOffset.push_back(uint32_t(k0));
     ModeCount.push_back(count);
     TunedModeCount.push_back(count);
@@ -256,7 +261,8 @@ void Bank::UploadTuning(cudaStream_t stream) {
         log_rho[m] = rho > 0 ? std::log(rho) : -std::numeric_limits<double>::infinity();
         theta[m] = rho > 0 ? std::atan2(im, re) : 0.0;
     }
-    (void)layout_changed;
+    // A live retune (TuneModalObject on an installed bank) never changes the slot layout; only Install() may.
+    if (Installed && !Installing && layout_changed) Fail(ME_BAD_ARG, "the padded layout changed under an installed bank (%u chunks); install the bank again", chunks);
     DCoeffRe.Upload(cre, stream), DCoeffIm.Upload(cim, stream), DPhaseIm.Upload(pim, stream), DPhaseRe.Upload(pre, stream), DRadiationGain.Upload(rg, stream);
     DShapeX.Upload(sx, stream), DShapeY.Upload(sy, stream), DShapeZ.Upload(sz, stream);
     DChunkObject.Upload(chunk_obj, stream);
@@ -272,7 +278,14 @@ void Bank::UploadTuning(cudaStream_t stream) {
 // slot layout are dropped by the next render.
 void Bank::Install() {
     ME_CUDA(cudaSetDevice(Device));
-    UploadTuning(OwnStream);
+    Installing = true;
+    try {
+        UploadTuning(OwnStream);
+    } catch (...) {
+        Installing = false;
+        throw;
+    }
+    Installing = false;
     const size_t padded = std::max<size_t>(size_t(NChunks) * kLanes, 1);
     const uint32_t n_obj = ObjectCount();
     for (int side = 0; side < 2; ++side) {
@@ -287,8 +300,11 @@ void Bank::Install() {
     DSpeculation.Reserve(1);
     ME_CUDA(cudaStreamSynchronize(OwnStream));
     Impacts.clear();
+    RetunedObjects.clear();
     FlushEvents = true;
     Installed = true;
+    NeedsReinstall = false;
+    InstalledObjects = n_obj;
 }
 
 // EnqueueModalEvent, ModalAudio.cpp:417-425.
@@ -798,6 +814,11 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
             if (e.object >= n_obj) return; // DrainEvents :71
             if (e.kind == 0) {
                 if (!(e.pulse_step > 0)) return;
+                // TriggerModalStrike refuses a strike outside the object's excitable points before it becomes an event
+                // (AudioSystem.cpp: `excitable_index >= min(Vertices, Positions)` returns early); the C ABI takes raw events,
+                // so the same guard sits here: such an event is dropped like one aimed at a missing slot (DrainEvents :71), never turned
+                // into a shape read out of bounds.
+                if (e.ex_pos >= ShapePoints[e.object]) return;
                 for (; retire_cursor <= start / block_frames; ++retire_cursor) in_flight -= retire_in_block[retire_cursor]; // retired at or before `start`
                 if (in_flight >= MaxImpacts) return;
                 admit(MakeImpact(e), start);

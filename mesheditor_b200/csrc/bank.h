@@ -108,6 +108,9 @@ private:
 
     // Device residency.
     bool Installed{false};
+    bool Installing{false};
+    bool NeedsReinstall{false};  // AddObject after Install: the device layout is stale until the next Install
+    uint32_t InstalledObjects{0};
     bool TuningDirty{false};
     uint32_t NChunks{0};
     std::vector<uint32_t> ObjFirstChunk, ObjStride, ObjPaddedShapeOffset; // per object, padded layout

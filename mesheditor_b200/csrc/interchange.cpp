@@ -148,6 +148,7 @@ MeStatus me_modal_file_parse(const uint8_t *bytes, uint64_t size, MeModalResult 
         in.GetArray(r->Modes.Freqs), in.GetArray(r->Modes.T60s);
         uint32_t points = 0, columns = 0;
         nested(r->Modes.Shapes, points, columns);
+        if (r->Modes.T60s.size() != r->Modes.Freqs.size()) Fail(ME_BAD_ARG, "%zu T60s for %zu frequencies in .modal data", r->Modes.T60s.size(), r->Modes.Freqs.size());
         if (points && columns != r->Modes.Freqs.size()) Fail(ME_BAD_ARG, "mode shapes do not match the mode count in .modal data");
         r->PointCount = points;
         in.GetArray(f->Vertices);
@@ -165,7 +166,10 @@ MeStatus me_modal_file_parse(const uint8_t *bytes, uint64_t size, MeModalResult 
         in.GetArray(r->Eigenvalues);
         uint32_t summary_points = 0, eigen = 0;
         nested(r->SummaryShapes, summary_points, eigen);
-        if (summary_points && (summary_points != points || eigen != r->Eigenvalues.size())) Fail(ME_BAD_ARG, "eigen summary does not match in .modal data");
+        // The accessors and me_rescale_modes index SummaryShapes[p * eigen + k] for every sample point: an archive that carries
+        // eigenvalues must carry a summary row per point (the reference's nested vectors keep their own sizes; a flat table cannot).
+        const bool summary_expected = !r->Eigenvalues.empty() && points > 0;
+        if ((summary_points || summary_expected) && (summary_points != points || eigen != r->Eigenvalues.size())) Fail(ME_BAD_ARG, "eigen summary does not match in .modal data");
         auto &m = f->Extras.solved_material;
         m.density = in.Get<double>(), m.young_modulus = in.Get<double>(), m.poisson_ratio = in.Get<double>(), m.alpha = in.Get<double>(), m.beta = in.Get<double>();
         f->Extras.solved_min_mode_freq = in.Get<float>(), f->Extras.solved_max_mode_freq = in.Get<float>();

@@ -27,4 +27,5 @@ struct MeModalResult {
     std::vector<float> Basis;
     uint32_t BasisRows{0}, BasisCols{0};
     uint32_t PointCount{0};
+    bool ReachedComputeModes{false}; // a failure past this point keeps mass properties, profile and the excitation remap (mesh2modes.cpp:655-657)
 };

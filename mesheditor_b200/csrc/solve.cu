@@ -345,6 +345,7 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
     }
     profile.sample_excite = Seconds() - t0;
     res.PointCount = uint32_t(sample_points.size());
+    res.ReachedComputeModes = true;
 
     // ComputeModes (mesh2modes.cpp:441-512).
     const uint32_t n = fem.N;
@@ -469,10 +470,17 @@ MeStatus me_modal_solve(const double *points_xyz, uint32_t n_points, const uint3
         auto res = std::make_unique<MeModalResult>();
         inner = me::SolveImpl(points_xyz, n_points, tets, n_tets, material, excite_xyz, n_excite, baked_scale, config, seed_basis, seed_rows, seed_cols, keep_basis, monitor, *res);
         if (inner == ME_CANCELLED || inner == ME_NOT_CONVERGED) {
-            // The reference returns a default-constructed (empty) ModalResult here (mesh2modes.cpp:462,479,490,616).
-            const MeSolveProfile profile = res->Profile;
-            res = std::make_unique<MeModalResult>();
-            res->Profile = profile;
+            // A cancel seen right after assembly returns a default-constructed ModalResult (mesh2modes.cpp:616). Past that point the
+            // failure is ComputeModes returning empty ModalModes (:462,479,490): mesh2modes still hands back the mass properties, the
+            // profile and the excitation remap around them (:655-657), with an empty eigen summary and basis.
+            auto empty = std::make_unique<MeModalResult>();
+            empty->Profile = res->Profile;
+            if (res->ReachedComputeModes) {
+                empty->MassProps = res->MassProps;
+                empty->SamplePointOfExcitation = std::move(res->SamplePointOfExcitation);
+                empty->ReachedComputeModes = true;
+            }
+            res = std::move(empty);
             if (inner == ME_CANCELLED) me::SetLastError("cancelled");
         }
         *out = res.release();
@@ -533,12 +541,18 @@ MeStatus me_rescale_modes(const MeModalResult *solved, const MeMaterial *solved_
             Fail(ME_BAD_ARG, "material edit is not exactly scalable (Poisson ratio differs or no eigenpairs)");
         const double rho_ratio = material->density / solved_material->density;
         const double eigenvalue_scale = (material->young_modulus / solved_material->young_modulus) / rho_ratio;
+        if (solved->SummaryShapes.size() != size_t(solved->PointCount) * solved->Eigenvalues.size() * 3) Fail(ME_BAD_ARG, "inconsistent eigen summary (%zu shape floats for %u points x %zu eigenpairs)", solved->SummaryShapes.size(), solved->PointCount, solved->Eigenvalues.size());
+        // RescaleModes leaves the ModalEigenSummary untouched (it stays the SOLVED eigenpairs with their SolvedMaterial): only a local
+        // copy of the eigenvalues is scaled, so the result can be rescaled again or archived with the original solved material.
+        auto scaled = solved->Eigenvalues;
+        for (auto &v : scaled) v *= eigenvalue_scale;
         auto res = std::make_unique<MeModalResult>();
         res->Eigenvalues = solved->Eigenvalues;
-        for (auto &v : res->Eigenvalues) v *= eigenvalue_scale;
         res->SummaryShapes = solved->SummaryShapes;
         res->PointCount = solved->PointCount;
-        res->Modes = me::Postprocess(res->Eigenvalues, res->SummaryShapes, res->PointCount, float(1 / std::sqrt(rho_ratio)), me::FromC(material), me::FromC(config), solved->Modes.Positions);
+        res->MassProps = solved->MassProps;
+        res->SamplePointOfExcitation = solved->SamplePointOfExcitation;
+        res->Modes = me::Postprocess(scaled, res->SummaryShapes, res->PointCount, float(1 / std::sqrt(rho_ratio)), me::FromC(material), me::FromC(config), solved->Modes.Positions);
         *out = res.release();
     });
 }

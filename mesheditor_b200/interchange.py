@@ -157,6 +157,20 @@ class ModalModel:
         finally:
             lib().me_bytes_free(out)
 
+    def rescaled(self, mat, config=None):
+        """modal::RescaleModes (mesh2modes.h:88, AudioSystem.cpp:595-616): this model's solved eigenpairs re-derived under `mat`
+        (same Poisson ratio), as a new ModalModel that still carries the SOLVED summary and material, like the reference's
+        ModalModelData after a material edit. Raises MeError where the reference returns nullopt."""
+        from .modal import solver_config
+
+        cfg = config if config is not None else solver_config(num_modes=self.solved_num_modes, min_mode_freq=self.solved_min_mode_freq, max_mode_freq=self.solved_max_mode_freq)
+        m, h = material(mat), C.c_void_p()
+        check(lib().me_rescale_modes(self._h, C.byref(self.solved_material), C.byref(m), C.byref(cfg), C.byref(h)))
+        sm = self.solved_material
+        return ModalModel(h, ME_OK, vertices=self.vertices, indices=self.indices, baked_scale=self.baked_scale, tet_positions=self.tet_positions, tet_edge_indices=self.tet_edge_indices,
+                          solved_material=(sm.density, sm.young_modulus, sm.poisson_ratio, sm.alpha, sm.beta), solved_min_mode_freq=self.solved_min_mode_freq,
+                          solved_max_mode_freq=self.solved_max_mode_freq, solved_num_modes=self.solved_num_modes, tet_inputs_hash=self.tet_inputs_hash, solved_vertices=self.solved_vertices)
+
     def solve_json(self, triangle_indices=()) -> str:
         """What MeshEditorModalSolve prints for this model (tests/ModalSolveTool.cpp:84-123)."""
         tri, out = _u32(triangle_indices), C.c_void_p()

@@ -177,6 +177,7 @@ class PortBank(_Common):
         L.or_bank_enqueue.restype = C.c_int
         L.or_bank_enqueue.argtypes = [C.c_void_p, C.POINTER(Event)]
         L.or_bank_render.argtypes = [C.c_void_p, F32P, C.c_uint32]
+        L.or_bank_render_exact.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_uint32]
         for f in ("mode_total", "object_count", "active_impacts"):
             getattr(L, "or_bank_" + f).restype = C.c_uint32
             getattr(L, "or_bank_" + f).argtypes = [C.c_void_p]
@@ -226,6 +227,11 @@ class PortBank(_Common):
 
     def render(self, out):
         self.L.or_bank_render(self.h, out, out.size)
+
+    def render_exact(self, out):
+        """FP64 arbiter: the same recurrence over the same float32 parameters with states and sums in double. A bank is
+        rendered EITHER with render() OR with render_exact() for its whole life (the two keep separate states)."""
+        self.L.or_bank_render_exact(self.h, out, out.size)
 
     def mode_column(self, name):
         out = np.zeros(self.L.or_bank_mode_total(self.h), np.float32)

@@ -80,6 +80,9 @@ typedef struct OrBank {
     uint32_t *ObjImpacts;
     size_t ObjImpactsCap;
     int Cull; /* 1 = reference behaviour; 0 = render every tuned mode (diagnostic only) */
+    /* FP64 arbiter (or_bank_render_exact): the same bank, the same float parameters, states and sums in double. */
+    double *ExactRe, *ExactIm;
+    size_t ExactN;
 } OrBank;
 
 OrBank *or_bank_create(float sample_rate) {
@@ -98,6 +101,7 @@ void or_bank_free(OrBank *b) {
     free(b->ModeOffset), free(b->ModeCount), free(b->ShapeOffset), free(b->TunedModeCount), free(b->LiveModeCount);
     free(b->Ringing), free(b->OutGain), free(b->ListenerGain), free(b->RadiantRadius), free(b->DeflectionScale);
     free(b->Impacts), free(b->ForceScratch), free(b->Gains), free(b->ObjImpacts);
+    free(b->ExactRe), free(b->ExactIm);
     free(b);
 }
 
@@ -384,6 +388,138 @@ void or_bank_render(OrBank *b, float *out, uint32_t frame_count) {
     }
     for (uint32_t s = 0; s < frame_count; ++s) out[s] += mix[s];
     free(mix);
+    for (uint32_t i = b->NImpacts; i-- > 0;) {
+        const OrImpact *im = &b->Impacts[i];
+        if (im->SamplesLeft == 0 && fabsf(im->ClickZ1) + fabsf(im->ClickZ2) < 1e-12f) remove_impact(b, i);
+    }
+}
+
+/* ---- FP64 arbiter -------------------------------------------------------------------------------------------------
+ * The recurrence of RenderObjectFast (ModalAudio.cpp:115-131) evaluated in double over the SAME float32 parameters
+ * (coefficients, gains, output rotation, the float force samples of the stage above) and summed into a double mix.
+ * It answers one question only: when two float32 renderings of a long, undamped timeline differ by ~1e-5 of peak,
+ * which of them moved away from the recurrence's exact value. Not the reference's arithmetic, so never the parity oracle.
+ * Audibility culling follows the same rules on the double energies. */
+static void exact_states(OrBank *b) {
+    if (b->ExactN == b->CoeffRe.n) return;
+    b->ExactRe = (double *)realloc(b->ExactRe, b->CoeffRe.n * sizeof(double));
+    b->ExactIm = (double *)realloc(b->ExactIm, b->CoeffRe.n * sizeof(double));
+    for (size_t i = b->ExactN; i < b->CoeffRe.n; ++i) b->ExactRe[i] = b->ExactIm[i] = 0.0;
+    b->ExactN = b->CoeffRe.n;
+}
+
+static void silence_object_exact(OrBank *b, uint32_t o) {
+    const uint32_t k0 = b->ModeOffset[o], count = b->ModeCount[o];
+    for (uint32_t k = 0; k < count; ++k) b->ExactRe[k0 + k] = b->ExactIm[k0 + k] = 0.0;
+    silence_object(b, o);
+}
+
+static void render_object_exact(OrBank *b, uint32_t o, const uint32_t *impacts, uint32_t n_imp, double *out, uint32_t frame_count) {
+    const uint32_t k0 = b->ModeOffset[o], stride = b->ModeCount[o];
+    const uint32_t count = (n_imp == 0 && b->Cull) ? b->LiveModeCount[o] : b->TunedModeCount[o];
+    const uint32_t shape0 = b->ShapeOffset[o];
+    const double out_gain = b->OutGain[o];
+    const double mix_gain = (double)(b->OutGain[o] * b->ListenerGain[o]);
+    double energy = 0.0;
+    uint32_t live = 0;
+    float *gains = (float *)malloc((size_t)(n_imp ? n_imp : 1) * sizeof(float));
+    for (uint32_t k = 0; k < count; ++k) {
+        const size_t m = (size_t)k0 + k;
+        for (uint32_t t = 0; t < n_imp; ++t) {
+            const OrImpact *im = &b->Impacts[impacts[t]];
+            const uint32_t base = shape0 + im->ExPos * stride + k;
+            gains[t] = b->RadiationGain.p[m] * (b->ShapeX.p[base] * im->Jx + b->ShapeY.p[base] * im->Jy + b->ShapeZ.p[base] * im->Jz);
+        }
+        double zr = b->ExactRe[m], zi = b->ExactIm[m];
+        const double cr = b->CoeffRe.p[m], ci = b->CoeffIm.p[m], pi = b->OutPhaseIm.p[m], pr = b->OutPhaseRe.p[m];
+        for (uint32_t s = 0; s < frame_count; ++s) {
+            double e = 0.0;
+            for (uint32_t t = 0; t < n_imp; ++t) e += (double)b->ForceScratch[(size_t)impacts[t] * frame_count + s] * (double)gains[t];
+            const double re = zr * cr - zi * ci + e;
+            zi = zr * ci + zi * cr;
+            zr = re;
+            out[s] += (pi * zi + pr * zr) * mix_gain;
+        }
+        b->ExactRe[m] = zr, b->ExactIm[m] = zi;
+    }
+    free(gains);
+    for (uint32_t k = 0; k < count; k += OR_LANES) {
+        const uint32_t width = OR_LANES < count - k ? OR_LANES : count - k;
+        double chunk = 0.0;
+        for (uint32_t l = 0; l < width; ++l) chunk += b->ExactRe[k0 + k + l] * b->ExactRe[k0 + k + l] + b->ExactIm[k0 + k + l] * b->ExactIm[k0 + k + l];
+        energy += chunk;
+        if (chunk * out_gain * out_gain >= (double)kSilentEnergy) live = k + width;
+    }
+    if (!b->Cull) {
+        b->Ringing[o] = 1;
+        return;
+    }
+    if (n_imp == 0 && energy * out_gain * out_gain < (double)kSilentEnergy) {
+        silence_object_exact(b, o);
+        return;
+    }
+    b->Ringing[o] = 1;
+    b->LiveModeCount[o] = n_imp == 0 ? live : b->TunedModeCount[o];
+}
+
+/* Same block structure as or_bank_render; the force / click stage stays the reference's float recurrence (it IS the input). */
+void or_bank_render_exact(OrBank *b, double *out, uint32_t frame_count) {
+    if (frame_count == 0) return;
+    exact_states(b);
+    if (b->FlushEvents) {
+        b->FlushEvents = 0;
+        b->EventRead = b->EventWrite;
+    }
+    /* drain_events with the double states silenced alongside */
+    for (uint32_t read = b->EventRead; read != b->EventWrite; ++read) {
+        const OrEvent *e = &b->Events[read % OR_EVENT_CAPACITY];
+        if (e->Object < b->NObjects && e->Kind == 1) silence_object_exact(b, e->Object);
+    }
+    drain_events(b);
+    const uint32_t impact_count = b->NImpacts;
+    if ((size_t)impact_count * frame_count > b->ForceCap) {
+        b->ForceCap = (size_t)impact_count * frame_count;
+        b->ForceScratch = (float *)realloc(b->ForceScratch, b->ForceCap * sizeof(float));
+    }
+    for (uint32_t i = 0; i < impact_count; ++i) {
+        OrImpact *im = &b->Impacts[i];
+        float phase_re = im->PhaseRe, phase_im = im->PhaseIm;
+        const float rot_re = im->RotRe, rot_im = im->RotIm, gamma = im->Gamma, amp = im->AccelAmp;
+        const float b0 = im->ClickB0, a1 = im->ClickA1, a2 = im->ClickA2;
+        const float impact_click_gain = b->ClickGain * b->ListenerGain[im->Object];
+        float z1 = im->ClickZ1, z2 = im->ClickZ2;
+        uint32_t left = im->SamplesLeft;
+        float *force = b->ForceScratch + (size_t)i * frame_count;
+        for (uint32_t s = 0; s < frame_count; ++s) {
+            float cur = 0.f;
+            if (left > 0) {
+                const float re = phase_re * rot_re - phase_im * rot_im;
+                phase_im = phase_re * rot_im + phase_im * rot_re;
+                phase_re = re;
+                cur = gamma * 0.5f * (1.f - phase_re);
+                --left;
+            }
+            force[s] = cur;
+            const float u = amp * cur;
+            const float y = b0 * u + z1;
+            z1 = -a1 * y + z2;
+            z2 = -b0 * u - a2 * y;
+            out[s] += (double)(y * impact_click_gain);
+        }
+        im->PhaseRe = phase_re, im->PhaseIm = phase_im, im->SamplesLeft = left, im->ClickZ1 = z1, im->ClickZ2 = z2;
+    }
+    if (impact_count > b->ObjImpactsCap) {
+        b->ObjImpactsCap = impact_count;
+        b->ObjImpacts = (uint32_t *)realloc(b->ObjImpacts, impact_count * sizeof(uint32_t));
+    }
+    for (uint32_t o = 0; o < b->NObjects; ++o) {
+        if (!b->Ringing[o]) continue;
+        uint32_t n_imp = 0;
+        for (uint32_t i = 0; i < impact_count; ++i) {
+            if (b->Impacts[i].Object == o) b->ObjImpacts[n_imp++] = i;
+        }
+        render_object_exact(b, o, b->ObjImpacts, n_imp, out, frame_count);
+    }
     for (uint32_t i = b->NImpacts; i-- > 0;) {
         const OrImpact *im = &b->Impacts[i];
         if (im->SamplesLeft == 0 && fabsf(im->ClickZ1) + fabsf(im->ClickZ2) < 1e-12f) remove_impact(b, i);

@@ -132,3 +132,52 @@ def test_reads_the_reference_golden_documents():
         np.testing.assert_array_equal(m["decayRates"], g["golden_decay"]), np.testing.assert_array_equal(m["positions"], g["golden_positions"])
         np.testing.assert_array_equal(m["shapes"], g["golden_shapes"])
         assert m["mass"] == float(g["golden_mass"])
+
+
+def _physical_model(seed):
+    """A stored model whose eigenvalues are audible (the random golden models' are, too) with a realistic material."""
+    m = oi.random_model(seed, n_modes=9, n_points=6, n_eigen=24)
+    m["eigenvalues"] = np.sort(np.random.default_rng(seed).uniform((2 * np.pi * 90.0) ** 2, (2 * np.pi * 7000.0) ** 2, 24))
+    return m
+
+
+@pytest.mark.skipif(not oi.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed,density,young", [(5, 2700.0, 7.2e10), (6, 1350.0, 9.0e10), (7, 8000.0, 2.0e11)])
+def test_rescale_modes_matches_the_oracle_and_keeps_the_solved_summary(seed, density, young):
+    """modal::RescaleModes (mesh2modes.cpp:590-603) through me_rescale_modes: modes bit-equal to the restatement, and the eigen
+    summary stays the SOLVED one (the reference never touches ModalEigenSummary), so a second rescale does not compound."""
+    from mesheditor_b200 import solver_config
+    from oracle import modal as om
+
+    m = _physical_model(seed)
+    model = ModalModel.from_bytes(oi.serialize(m))
+    solved = om.Material(*m["material"])
+    edited = om.Material(density, young, solved.poisson, solved.alpha, solved.beta)
+    cfg = solver_config(num_modes=12, max_mode_freq=16000.0)
+    want = om.rescale_modes(m["eigenvalues"], m["summary_shapes"], solved, edited, om.SolverConfig(num_modes=12, num_fem_modes=27, max_mode_freq=16000.0), m["positions"])
+    got = model.rescaled((density, young, solved.poisson, solved.alpha, solved.beta), cfg)
+    np.testing.assert_array_equal(got.result.freqs, want.freqs), np.testing.assert_array_equal(got.result.t60s, want.t60s)
+    np.testing.assert_array_equal(got.result.shapes, want.shapes)
+    np.testing.assert_array_equal(got.result.eigenvalues, m["eigenvalues"])  # untouched
+    assert got.result.mass_props["mass"] == m["mass"]
+    again = got.rescaled((density, young, solved.poisson, solved.alpha, solved.beta), cfg)
+    np.testing.assert_array_equal(again.result.freqs, want.freqs)
+    # archived with the original solved material, the reference's loader reads the same summary back
+    stored = ModalModel.from_bytes(got.to_bytes())
+    np.testing.assert_array_equal(stored.result.eigenvalues, m["eigenvalues"])
+    with pytest.raises(MeError):
+        model.rescaled((density, young, solved.poisson + 0.01, solved.alpha, solved.beta), cfg)  # not exactly scalable -> nullopt
+
+
+def test_inconsistent_modal_data_is_rejected():
+    """Sizes the reference's nested vectors carry themselves but a flat table cannot: T60s vs Freqs, summary rows vs points."""
+    with open(os.path.join(GOLDEN, "model_3.modal"), "rb") as f:
+        data = bytearray(f.read())
+    n = int(np.frombuffer(bytes(data[:4]), np.uint32)[0])
+    t60_at = 4 + 4 * n
+    assert int(np.frombuffer(bytes(data[t60_at:t60_at + 4]), np.uint32)[0]) == n
+    short = bytearray(data)
+    short[t60_at:t60_at + 4] = np.uint32(n - 1).tobytes()
+    del short[t60_at + 4:t60_at + 8]  # one T60 fewer, everything after it intact
+    with pytest.raises(MeError, match="T60s"):
+        ModalModel.from_bytes(bytes(short))

@@ -223,3 +223,42 @@ def test_errors_are_reported_not_swallowed():
         g.tune(7, [1.0], [1.0])
     with pytest.raises(MeError):
         g.render_offline([to_me(orc.impact_event(0, 1.0))], [100], 1024, 512)  # not on a block boundary
+
+
+def test_objects_added_after_install_need_a_reinstall():
+    """The reference never grows a live bank (RebuildModalBank builds the next one, InstallModalBank swaps it in,
+    ModalAudio.cpp:277-289): a slot added after me_bank_install makes rendering fail loudly until the next install."""
+    from mesheditor_b200 import MeError
+
+    modes = orc.make_modes(40, 0.3)
+    g = gpu_bank()
+    g.add_modes(modes)
+    g.install()
+    g.enqueue(to_me(orc.impact_event(0, 1.0)))
+    first = g.render_blocks(2)
+    assert np.abs(first).max() > 0
+    g.add_modes(orc.make_modes(500, 0.3))  # would need more chunks than the device buffers were sized for
+    with pytest.raises(MeError):
+        g.render_blocks(1)
+    g.install()
+    o = orc.PortBank(48000.0, 1)
+    o.add_modes(modes), o.add_modes(orc.make_modes(500, 0.3))
+    o.install()
+    for bank, conv in ((o, lambda e: e), (g, to_me)):
+        bank.enqueue(conv(orc.impact_event(1, 0.7, ex_pos=2)))
+    assert rel_err(g.render_blocks(6), o.render_blocks(6)) <= TOL
+
+
+def test_strike_outside_the_excitable_points_is_dropped():
+    """TriggerModalStrike returns early for an excitable index past the object's points; the C ABI takes raw events, so the
+    guard sits in the bank: the event is ignored (never a shape read out of bounds), later events still render."""
+    modes = orc.make_modes(64, 0.2, sample_points=4)
+    o, g = build_pair(orc.PortBank, 2, modes)
+    bad = orc.impact_event(0, 1.0, ex_pos=4)      # one past the last point
+    worse = orc.impact_event(1, 1.0, ex_pos=10**6)
+    g.enqueue(to_me(bad)), g.enqueue(to_me(worse))
+    assert np.abs(g.render_blocks(2)).max() == 0.0 and g.active_impacts() == 0
+    good = orc.impact_event(1, 0.8, ex_pos=3)
+    o.render_blocks(2)
+    o.enqueue(good), g.enqueue(to_me(good))
+    assert rel_err(g.render_blocks(8), o.render_blocks(8)) <= TOL
