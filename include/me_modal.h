@@ -178,6 +178,14 @@ MeStatus me_bank_set_time_segments(MeBank *, uint32_t time_segments);
  * 1e-5-of-peak bar. */
 MeStatus me_bank_set_render_path(MeBank *, uint32_t path);
 
+/* DealObjects (ModalAudio.cpp:430-461), the reference's split of the ringing objects between its renderers, used here to
+ * split a bank's objects between GPUs (one renderer = one device): objects taken heaviest first, ties
+ * by object index, each onto the renderer carrying least so far (the first such renderer); with one renderer everything
+ * stays in bank order. costs[i] = modes x (1 + voices) of object i (`order.emplace_back(modes * (1 + voices), o)`, :444).
+ * Writes owner[i] in [0, n_renderers) and, when `local_slot` is not NULL, the object's slot inside its owner's bank (each
+ * renderer takes its objects in bank order, :459). Pure host function of its inputs: every rank computes the same deal. */
+MeStatus me_deal_objects(const uint64_t *costs, uint32_t n_objects, uint32_t n_renderers, uint32_t *owner, uint32_t *local_slot);
+
 /* ------------------------------------------------------------------------------------------------
  * Analysis: tet mesh + material -> modal model (reference: src/audio/mesh2modes.{h,cpp}).
  * ---------------------------------------------------------------------------------------------- */

@@ -6,3 +6,4 @@ This package is only the ctypes face of that ABI. Importing it never imports any
 from ._lib import LIB_PATH, MeError, MeModalEvent, MeRetune, lib  # noqa: F401
 from .audio import ModalBank, impact_event, listener_gain, measure_fp32_fma_rate, modal_out_gain, monitor_frames, retune_modes, retuning, silence_event, uniform_scale_ratio, wav_bytes, wav_frames  # noqa: F401
 from .modal import symbolic_analyse, Factor, FemSystem, ModalResult, material, measure_fp64_rate, mesh2modes, postprocess_modes, solver_config  # noqa: F401,E402
+from .sharded import ShardedModalBank, deal_objects  # noqa: F401,E402

@@ -156,6 +156,7 @@ def lib():
         "me_modal_result_mass_properties": [vp, C.POINTER(MeMassProperties)],
         "me_modal_result_profile": [vp, C.POINTER(MeSolveProfile)],
         "me_postprocess_modes": [vp, u32, vp, u32, f32, C.POINTER(MeMaterial), C.POINTER(MeSolverConfig), vp, C.POINTER(vp)],
+        "me_deal_objects": [vp, u32, u32, vp, vp],
         "me_rescale_modes": [vp, C.POINTER(MeMaterial), C.POINTER(MeMaterial), C.POINTER(MeSolverConfig), C.POINTER(vp)],
         "me_fem_assemble": [vp, u32, vp, u32, C.POINTER(MeMaterial), u32, i32, C.POINTER(vp)],
         "me_fem_info": [vp, C.POINTER(MeFemInfo)],

@@ -926,6 +926,30 @@ void Bank::GetObjectStatus(uint32_t slot, uint32_t *live_mode_count, uint32_t *r
     if (ringing) *ringing = ring;
 }
 
+// DealObjects, ModalAudio.cpp:430-461.
+void DealObjects(const uint64_t *costs, uint32_t n, uint32_t renderers, uint32_t *owner, uint32_t *local_slot) {
+    if (renderers == 0) Fail(ME_BAD_ARG, "no renderer to deal objects to");
+    if (n && (!costs || !owner)) Fail(ME_BAD_ARG, "null cost / owner array");
+    if (renderers == 1) {
+        std::fill_n(owner, n, 0u);
+    } else {
+        std::vector<uint32_t> order(n);
+        std::iota(order.begin(), order.end(), 0u);
+        // Heaviest first, and by object for equal weights, so the deal never depends on the sort's own tie-breaking (:452).
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return costs[a] != costs[b] ? costs[a] > costs[b] : a < b; });
+        std::vector<uint64_t> load(renderers, 0);
+        for (const uint32_t o : order) {
+            const auto least = uint32_t(std::min_element(load.begin(), load.end()) - load.begin());
+            load[least] += costs[o];
+            owner[o] = least;
+        }
+    }
+    if (local_slot) {
+        std::vector<uint32_t> next(renderers, 0);
+        for (uint32_t o = 0; o < n; ++o) local_slot[o] = next[owner[o]]++;
+    }
+}
+
 void Bank::GetObjectLayout(uint32_t slot, uint32_t *mode_offset, uint32_t *mode_count, uint32_t *tuned, float *radius) const {
     CheckSlot(slot);
     if (mode_offset) *mode_offset = ModeOffset[slot];

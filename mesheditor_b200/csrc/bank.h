@@ -151,4 +151,7 @@ private:
     friend struct BankAccess;
 };
 
+// DealObjects (ModalAudio.cpp:430-461): heaviest first onto the least-loaded renderer; see me_deal_objects.
+void DealObjects(const uint64_t *costs, uint32_t n_objects, uint32_t n_renderers, uint32_t *owner, uint32_t *local_slot);
+
 } // namespace me

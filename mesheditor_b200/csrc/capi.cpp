@@ -156,6 +156,9 @@ MeStatus me_bank_set_render_path(MeBank *b, uint32_t path) {
     });
 }
 MeStatus me_bank_install(MeBank *b) { return ME_BANK_CALL(b, b->Impl.Install()); }
+MeStatus me_deal_objects(const uint64_t *costs, uint32_t n_objects, uint32_t n_renderers, uint32_t *owner, uint32_t *local_slot) {
+    return Guard([&] { me::DealObjects(costs, n_objects, n_renderers, owner, local_slot); });
+}
 
 MeStatus me_bank_enqueue(MeBank *b, const MeModalEvent *e) {
     MeStatus queued = ME_OK;

@@ -27,56 +27,123 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _render_voices(lo, hi):
-    """Oracle render of voices [lo, hi) of the shared timeline, voices re-indexed from 0 as bench.py does per rank."""
-    from mesheditor_b200 import workloads as wl
-    from oracle import resonator as orc
+class OracleRank:
+    """The ModalBank calls ShardedModalBank makes, answered by the CPU oracle (this is a test: the product's rank is a
+    CUDA ModalBank). Events arrive as MeModalEvent and are handed to the oracle in its own struct."""
 
-    orc.build_port()
-    frames = BLOCKS * BLOCK
-    events, ev_frames, ev_voice = wl.c5_timeline(VOICES, frames, restrike_hz=20.0)
-    bank = (orc.RefScene if orc.have_ref() else orc.PortBank)(48000.0, 1)
-    modes = wl.make_modes(MODES, 0.5)
-    for _ in range(hi - lo):
-        bank.add_modes(modes)
+    def __init__(self, sample_rate, device):
+        from oracle import resonator as orc
+
+        orc.build_port()
+        self.orc, self.sample_rate = orc, sample_rate
+        self.bank = (orc.RefScene if orc.have_ref() else orc.PortBank)(sample_rate, 1)
+
+    def add_object(self, *a):
+        return self.bank.add_object(*a)
+
+    def install(self, discard_frames=512):
+        self.bank.install(discard_frames)
+
+    def _event(self, e):
+        return self.orc.Event(e.kind, e.object, e.ex_pos, e.jx, e.jy, e.jz, e.pulse_step, e.pulse_gamma, e.accel_amp, e.click_b0, e.click_a1, e.click_a2)
+
+    def enqueue(self, e):
+        self.bank.enqueue(self._event(e))
+        return True
+
+    def render(self, out):
+        self.bank.render(out)
+
+    def render_offline(self, packed, _frames, total, block):
+        arr, frames, n = packed
+        out, k = np.zeros(total, np.float32), 0
+        for begin in range(0, total, block):
+            while k < n and frames[k] == begin:
+                self.enqueue(arr[k])
+                k += 1
+            self.bank.render(out[begin:begin + block])
+        return out
+
+
+def _unequal_bank(rank, world, all_reduce=None):
+    """Six objects of unequal mode counts (the deal matters), the second one carrying a sustained voice in its cost."""
+    from mesheditor_b200 import ShardedModalBank
+    from mesheditor_b200 import workloads as wl
+
+    bank = ShardedModalBank(48000.0, 0, rank, world, bank_factory=OracleRank, all_reduce=all_reduce)
+    counts = [64, 8, 40, 64, 16, 24]
+    for i, n in enumerate(counts):
+        bank.add_modes(wl.make_modes(n, 0.5), voices=1 if i == 1 else 0)
     bank.install()
-    out = np.zeros(frames, np.float32)
-    for b in range(BLOCKS):
-        for (v, impulse, ex), f in zip(events, ev_frames):
-            if f == b * BLOCK and lo <= v < hi:
-                bank.enqueue(orc.impact_event(v - lo, impulse, ex))
-        bank.render(out[b * BLOCK:(b + 1) * BLOCK])
-    return out
+    frames = BLOCKS * BLOCK
+    events, ev_frames, _ = wl.c5_timeline(len(counts), frames, restrike_hz=20.0)
+    return bank, [wl.impact(v, impulse, ex) for v, impulse, ex in events], ev_frames, frames
 
 
 def _mix_worker(rank, world, port, result):
-    from mesheditor_b200 import workloads as wl
-
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    lo, hi = wl.shard_voices(VOICES, world, rank)
-    mix = torch.from_numpy(_render_voices(lo, hi))
-    dist.all_reduce(mix)  # the one collective of the synthesis path: sum of the per-rank mono mixes
-    spans = [None] * world
-    dist.all_gather_object(spans, (lo, hi))
+    bank, events, ev_frames, frames = _unequal_bank(rank, world)  # the default reduce: torch.distributed.all_reduce
+    mix = bank.render_offline(events, ev_frames, frames, BLOCK)
+    # streaming form: the same strikes enqueued block by block on every rank (SPMD), one all-reduce per block
+    stream_bank, _, _, _ = _unequal_bank(rank, world)
+    stream, k = np.zeros(frames, np.float32), 0
+    for b in range(BLOCKS):
+        while k < len(events) and ev_frames[k] == b * BLOCK:
+            stream_bank.enqueue(events[k])
+            k += 1
+        stream_bank.render(stream[b * BLOCK:(b + 1) * BLOCK])
+    owned = [None] * world
+    dist.all_gather_object(owned, bank.owned())
     if rank == 0:
-        result["mix"] = mix.numpy().copy()
-        result["spans"] = spans
+        result["mix"], result["stream"], result["owned"] = mix.copy(), stream.copy(), owned
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_sharded_mix_matches_single_rank_render(built_lib):
+    """ShardedModalBank over two gloo ranks == the same bank on one rank, at the reference's own gate for 1 vs N renderers
+    (tests/ModalRenderTest.cpp:40-49); the deal is the reference's (heaviest first, least-loaded renderer)."""
     world, port = 2, _free_port()
     with mp.Manager() as manager:
         result = manager.dict()
         mp.spawn(_mix_worker, args=(world, port, result), nprocs=world, join=True)
-        mix, spans = np.array(result["mix"]), list(result["spans"])
-    assert spans == [(0, 3), (3, 6)]  # contiguous, disjoint, covering
-    whole = _render_voices(0, VOICES)
+        mix, stream, owned = np.array(result["mix"]), np.array(result["stream"]), list(result["owned"])
+    # costs 64, 16, 40, 64, 16, 24 -> order 0, 3, 2, 5, 1, 4 -> loads (64, 64) (104, 64) (104, 88) (104, 104) (120, 104)
+    assert owned == [[0, 2, 4], [1, 3, 5]]
+    bank, events, ev_frames, frames = _unequal_bank(0, 1)
+    whole = bank.render_offline(events, ev_frames, frames, BLOCK)
     peak = float(np.abs(whole).max())
     assert peak > 0
     assert float(np.abs(mix - whole).max()) <= 1e-5 * peak
+    assert float(np.abs(stream - whole).max()) <= 1e-5 * peak
+
+
+def _deal_restated(costs, count):
+    """DealObjects, src/audio/ModalAudio.cpp:430-461, statement by statement (test-side restatement)."""
+    if count == 1:
+        return [0] * len(costs)
+    order = sorted(range(len(costs)), key=lambda o: (-costs[o], o))
+    load, owner = [0] * count, [0] * len(costs)
+    for o in order:
+        least = load.index(min(load))
+        load[least] += costs[o]
+        owner[o] = least
+    return owner
+
+
+@pytest.mark.parametrize("seed,n,world", [(0, 1, 1), (1, 7, 2), (2, 64, 8), (3, 1024, 8), (4, 33, 4), (5, 5, 8), (6, 0, 3)])
+def test_deal_objects_is_the_reference_deal(built_lib, seed, n, world):
+    from mesheditor_b200 import deal_objects
+
+    rng = np.random.default_rng(seed)
+    costs = (rng.integers(1, 60, n) * rng.integers(1, 4, n) * 8).astype(np.uint64) if seed != 3 else np.full(n, 500, np.uint64)
+    owner, local = deal_objects(costs, world)
+    assert list(owner) == _deal_restated([int(c) for c in costs], world)
+    for r in range(world):  # each renderer takes its objects in bank order (:459)
+        assert list(local[owner == r]) == list(range(int((owner == r).sum())))
+    if seed == 3:  # identical voices: an even split, 128 per GPU
+        assert np.bincount(owner, minlength=world).tolist() == [128] * 8
 
 
 def _batch_worker(rank, world, port, result):
