@@ -1,19 +1,28 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the modal hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload all|resonator|solve|batch]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[4], the polyphonic resonator bank — 1024 voices x 500 modes x 10 s at
-48 kHz, one strike per voice at frame 0 plus Poisson re-strikes — the one metric BASELINE.json quotes at 1/2/4/8 B200.
-A "step" is one offline render of the whole 10 s timeline. Voices are sharded over the ranks (strong scaling: the total
-stays 1024 voices) and the per-rank mono mixes are summed with one NCCL all-reduce over NVLink.
+BASELINE.json's metric has two halves; the default run (`--workload all`) measures both and prints ONE JSON line:
 
-`value`  = mode-samples/s with the bank resident in HBM, timed on the device (CUDA events, max over ranks).
-`e2e`    = the same metric through the C ABI with the strike timeline in HOST memory and the mix read back to HOST.
-`roofline` = FP32 issue ceiling (the resonator is FP32-ALU bound); `roofline_hbm` = mandatory bytes.
-`cpu_baseline` = the UNMODIFIED reference RenderModal (oracle/_ref) on the host cores, on a bounded sample.
-`--impl reference` runs only that CPU arm and prints it in the same format.
+  * the line itself = the half quoted at 1/2/4/8 B200: BASELINE.json configs[4], the polyphonic resonator bank — 1024 voices x
+    500 modes x 10 s at 48 kHz, one strike per voice at frame 0 plus Poisson re-strikes. A "step" is one offline render of the
+    whole 10 s timeline. Voices are dealt over the ranks by the reference's DealObjects rule (mesheditor_b200.ShardedModalBank;
+    strong scaling: the total stays 1024 voices) and the per-rank mono mixes are summed with one NCCL all-reduce over NVLink.
+      `value`    = mode-samples/s with the bank resident in HBM, timed on the device (CUDA events, max over ranks).
+      `e2e`      = the same metric through the C ABI with the strike timeline in HOST memory and the mix read back to HOST.
+      `roofline` = the dominant kernel of the step (tensor-core form: the tcgen05 mix; sample loop: FP32 issue).
+      `parity`   = the output of THIS configuration checked outside the timed region: the full 1024-voice mix against the
+                   reference's own render of the same timeline, and a 16-voice slice against the reference and the FP64 arbiter.
+      `cpu_baseline` = the UNMODIFIED reference RenderModal (oracle/_ref) on the host cores, one full-size step.
+  * `"solve"`  = the other half, "modal solve s/mesh @1M tets": BASELINE.json configs[2] through me_modal_solve (host mesh in,
+    host modal model out) with the reference bench's per-stage table (tests/ModalSolverBench.cpp:413-449) and the stage
+    rooflines (the 8-wide triangular-solve sweeps that carry the timed solve, SpMV, assembly, numeric factorisation).
+    A single eigensolve does not shard: with --gpus N every rank solves a replica ("replicas only") and the slowest is reported.
+  * `"batch"`  = BASELINE.json configs[3]: 64 meshes (10k..500k tets) dealt biggest-first over the ranks, no collective.
+
+`--impl reference` runs the CPU arm alone (the reference's RenderModal over the same full configuration) in the same format.
 """
 from __future__ import annotations
 
@@ -31,29 +40,31 @@ sys.path.insert(0, ROOT)
 
 VOICES, MODES, SECONDS, RATE, BLOCK = 1024, 500, 10.0, 48000.0, 512
 METRIC, UNIT = "resonator mode-samples/s", "mode-samples/s"
-OPS_PER_MODE_SAMPLE = 2.75  # FP32 lane-operations per mode-sample of the K=4 kernel: (2K+3)/K (DESIGN.md §4.1)
+OPS_PER_MODE_SAMPLE = 2.75  # FP32 lane-operations per mode-sample of the K=4 kernel: (2K+3)/K (DESIGN.md §5.1)
 REF_OPS_PER_MODE_SAMPLE = 7.0  # the reference's loop, SURVEY.md §8(d)
+PARITY_SLICE_VOICES = 16
 
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def tensor_traffic(which):
-    """DRAM bytes per launch of the tensor-form kernels from the committed ncu --set full capture, when there is one."""
+def profiled_traffic():
+    """DRAM bytes per launch of the tensor-form kernels from the committed `ncu --set full` capture of the N=1 step, with the
+    launch shape it was taken at (profiles/resonator_traffic.json), so that a rank's figure can be scaled to ITS launch."""
     try:
         with open(os.path.join(ROOT, "profiles", "resonator_traffic.json")) as f:
-            return json.load(f).get(f"{which}_dram_bytes_per_launch")
+            return json.load(f)
     except Exception:
-        return None
+        return {}
 
 
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return json.load(f), "measured"
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -94,50 +105,111 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "power_w_max": max(power), "samples": len(self.rows), "samples_under_load": len(loaded), "reasons": reasons}
 
 
-def cpu_reference(steps, warmup, voices=256, seconds=1.0, quiet=False):
-    """The reference's own RenderModal (oracle/_ref/libme_ref_audio.so, built from /root/reference sources) on the host
-    cores, RenderThreads = min(16, cores) (its cap, src/audio/AudioSystem.cpp:60), 512-frame blocks."""
-    from mesheditor_b200 import workloads as wl
-    from oracle import resonator as orc
-
-    kind = "reference" if orc.have_ref() else "port"
-    cores = os.cpu_count() or 1
-    threads = min(16, cores) if kind == "reference" else 1
-    modes = wl.c5_modes(MODES)
-    blocks = int(seconds * RATE) // BLOCK
-    events, ev_frames, _ = wl.c5_timeline(voices, blocks * BLOCK)
-    times, live = [], None
-    for it in range(warmup + steps):
-        scene = (orc.RefScene if kind == "reference" else orc.PortBank)(RATE, threads)
-        for _ in range(voices):
-            scene.add_modes(modes)
-        scene.install()
-        out = np.zeros(blocks * BLOCK, np.float32)
-        k = 0
-        t0 = time.perf_counter()
-        for b in range(blocks):
-            while k < len(events) and ev_frames[k] == b * BLOCK:
-                v, impulse, ex = events[k]
-                scene.enqueue(orc.impact_event(v, impulse, ex))
-                k += 1
-            scene.render(out[b * BLOCK:(b + 1) * BLOCK])
-        dt = time.perf_counter() - t0
-        live = scene.object_column("LiveModeCount")
-        if it >= warmup:
-            times.append(dt)
-    mode_samples = voices * MODES * blocks * BLOCK
-    ms = 1e3 * sum(times) / len(times)
+# ------------------------------------------------------------------------------------------------ synthesis: the CPU arm
+def workload_config(n_gpus):
+    """The same dict in both arms (the driver compares them): nothing run-dependent in here."""
     return {
-        "value": mode_samples / (ms * 1e-3), "unit": UNIT, "cores": threads, "kind": kind, "ms_per_step": ms,
-        "sample": f"{voices} voices x {MODES} modes x {blocks * BLOCK} frames ({blocks} blocks of {BLOCK}), same strike recipe; LiveModeCount {int(live.min())}..{int(live.max())} of {MODES} (no culling)",
+        "workload": f"BASELINE.json configs[4]: polyphonic resonator bank {VOICES} voices x {MODES} modes x {SECONDS:g} s at {RATE:g} Hz, strike per voice at frame 0 + 2 Hz Poisson re-strikes (MT19937 12345), 512-frame blocks",
+        "voices": VOICES, "modes_per_voice": MODES, "frames": int(SECONDS * RATE), "sample_rate": RATE, "block_frames": BLOCK,
+        "parallelism": f"voices dealt over {n_gpus} GPU(s) (DealObjects rule), one NCCL all-reduce of the mono mix" if n_gpus > 1 else "single GPU",
+        "l2_policy": "working set > L2: one step writes and reads 8 GB of block-start states (tensor-core form) or 3.9 GB of per-warp partial mixes (sample loop); nothing is reused across steps",
     }
 
 
+RING = 256  # ModalAudio::EventCapacity (ModalAudio.h:275): strikes the reference can take between two RenderModal calls
+
+
+class ReferenceScenes:
+    """The reference bank(s) of the CPU arm. The workload strikes all 1024 voices in the same block, and the reference's event
+    ring holds 256 events between two RenderModal calls (the rest are dropped and counted, ModalAudio.cpp:419-422), so the voices
+    live in ceil(voices / 256) ModalAudio instances of 256 voices each, rendered one after the other INTO THE SAME buffer
+    (RenderModal adds into `out`): the same code, the same total work, no strike lost."""
+
+    def __init__(self, voices, threads):
+        from mesheditor_b200 import workloads as wl
+        from oracle import resonator as orc
+
+        self.orc = orc
+        self.kind = "reference" if orc.have_ref() else "port"
+        cls = orc.RefScene if self.kind == "reference" else orc.PortBank
+        modes = wl.c5_modes(MODES)
+        self.scenes = []
+        for first in range(0, voices, RING):
+            scene = cls(RATE, threads if self.kind == "reference" else 1)
+            for _ in range(min(RING, voices - first)):
+                scene.add_modes(modes)
+            scene.install()
+            self.scenes.append(scene)
+
+    def step(self, events, ev_frames, frames):
+        """One step of the reference arm: RenderModal over the whole timeline in 512-frame blocks, the strikes of a block enqueued
+        before it (tests/ModalBench.h:76-80; the offline loop of src/audio/AudioSystem.cpp:1155-1159)."""
+        out, k = np.zeros(frames, np.float32), 0
+        t0 = time.perf_counter()
+        for begin in range(0, frames, BLOCK):
+            while k < len(events) and ev_frames[k] == begin:
+                v, impulse, ex = events[k]
+                self.scenes[v // RING].enqueue(self.orc.impact_event(v % RING, impulse, ex))
+                k += 1
+            for scene in self.scenes:
+                scene.render(out[begin:min(begin + BLOCK, frames)])
+        return time.perf_counter() - t0, out
+
+    def live_mode_counts(self):
+        return np.concatenate([s.object_column("LiveModeCount") for s in self.scenes])
+
+    def events_dropped(self):
+        return int(sum(s.events_dropped() for s in self.scenes))
+
+
+def reference_threads():
+    """The renderer count the CPU arm uses: the reference's pool takes up to the core count (ModalRenderPool::SetSize clamps to
+    hardware_concurrency, ModalAudio.cpp:238-243; its UI offers 1..16, AudioSystem.cpp:60). Both are timed on a 1 s prefix of the
+    workload and the faster one is used, so the baseline is the reference at its best on this host."""
+    from mesheditor_b200 import workloads as wl
+    from oracle import resonator as orc
+
+    cores = os.cpu_count() or 1
+    if not orc.have_ref():
+        return 1, {}
+    frames = int(RATE)
+    events, ev_frames, _ = wl.c5_timeline(VOICES, frames)
+    rates = {}
+    for threads in sorted({min(16, cores), cores}):
+        dt, _ = ReferenceScenes(VOICES, threads).step(events, ev_frames, frames)
+        rates[threads] = VOICES * MODES * frames / dt
+    return max(rates, key=rates.get), {str(k): float(f"{v:.4g}") for k, v in rates.items()}
+
+
+def cpu_reference(steps, warmup):
+    """The reference's own RenderModal (oracle/_ref/libme_ref_audio.so, built from /root/reference sources) on the host cores over
+    the FULL configuration: every step is 1024 voices x 480,000 frames. Returns the figures and the last step's mix."""
+    from mesheditor_b200 import workloads as wl
+
+    frames = int(SECONDS * RATE)
+    threads, calibration = reference_threads()
+    events, ev_frames, _ = wl.c5_timeline(VOICES, frames)
+    times, out, live, kind, dropped = [], None, None, "port", 0
+    for it in range(warmup + steps):
+        scenes = ReferenceScenes(VOICES, threads)
+        dt, out = scenes.step(events, ev_frames, frames)
+        live, kind, dropped = scenes.live_mode_counts(), scenes.kind, scenes.events_dropped()
+        if it >= warmup:
+            times.append(dt)
+    assert dropped == 0, f"the reference dropped {dropped} strikes"
+    ms = 1e3 * sum(times) / len(times)
+    return {
+        "value": VOICES * MODES * frames / (ms * 1e-3), "unit": UNIT, "cores": threads, "kind": kind, "ms_per_step": ms, "host_cores": os.cpu_count() or 1,
+        "sample": f"the full workload per step: {VOICES} voices x {MODES} modes x {frames} frames in {-(-frames // BLOCK)} blocks of {BLOCK}, same strike timeline, {steps} timed step(s) after {warmup} warm-up; "
+                  f"{-(-VOICES // RING)} ModalAudio banks of {RING} voices rendered into one buffer (the reference's event ring holds {RING} strikes per block; none dropped); "
+                  f"RenderPool of {threads} renderer(s) (faster of the UI's 16 and the pool's own ceiling = the core count, 1 s calibration in mode-samples/s: {calibration}); LiveModeCount {int(live.min())}..{int(live.max())} of {MODES} (no culling)",
+    }, out
+
+
 def run_reference(args):
-    rank = env_int("RANK", 0)
-    if rank != 0:
+    if env_int("RANK", 0) != 0:
         return
-    base = cpu_reference(args.steps, args.warmup)
+    base, _ = cpu_reference(args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -147,159 +219,193 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(n_gpus):
-    return {
-        "workload": f"BASELINE.json configs[4]: polyphonic resonator bank {VOICES} voices x {MODES} modes x {SECONDS:g} s at {RATE:g} Hz, strike per voice at frame 0 + 2 Hz Poisson re-strikes (MT19937 12345), 512-frame blocks",
-        "voices": VOICES, "modes_per_voice": MODES, "frames": int(SECONDS * RATE), "sample_rate": RATE, "block_frames": BLOCK,
-        "parallelism": f"voices sharded over {n_gpus} GPU(s), NCCL all-reduce of the mono mix" if n_gpus > 1 else "single GPU",
-        "l2_policy": "working set > L2: one step writes and reads 8 GB of block-start states (tensor-core form) or 3.9 GB of per-warp partial mixes (sample loop); nothing is reused across steps",
-    }
+# ------------------------------------------------------------------------------------------------ synthesis: the GPU arm
+class Ranks:
+    """torch.distributed plumbing shared by the three workloads (one process per GPU, NCCL)."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        from mesheditor_b200 import build
+
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+        build.build()
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op):
+        t = self.torch.tensor(values, dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op={"max": self.dist.ReduceOp.MAX, "min": self.dist.ReduceOp.MIN, "sum": self.dist.ReduceOp.SUM}[op])
+        return [float(x) for x in t]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
-
-    global VOICES
-    if args.voices:
-        VOICES = args.voices
-
-    from mesheditor_b200 import ModalBank, build, measure_fp32_fma_rate
+def sharded_bank(ranks, voices, render_path):
+    from mesheditor_b200 import ShardedModalBank
     from mesheditor_b200 import workloads as wl
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch with torch.distributed.run for --gpus > 1")
-    build.build()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    frames = int(SECONDS * RATE)
-    lo, hi = wl.shard_voices(VOICES, world, rank)
+    bank = ShardedModalBank(RATE, ranks.local, ranks.rank, ranks.world)
     modes = wl.c5_modes(MODES)
-    all_events, all_frames, all_voice = wl.c5_timeline(VOICES, frames)
-    mine = (all_voice >= lo) & (all_voice < hi)
-    events = [wl.impact(v - lo, impulse, ex) for (v, impulse, ex), keep in zip(all_events, mine) if keep]
-    ev_frames = all_frames[mine]
-    events = ModalBank.pack_events(events, ev_frames)  # contiguous MeModalEvent[] + frames, built once
-
-    bank = ModalBank(RATE, local)
-    for _ in range(hi - lo):
+    for _ in range(voices):
         bank.add_modes(modes)
     bank.install(0)
-    bank.set_render_path({"auto": 0, "loop": 1, "tensor": 2}[args.render_path])
+    bank.set_render_path({"auto": 0, "loop": 1, "tensor": 2}[render_path])
+    return bank
+
+
+def parity_report(ranks, full_mix, reference_mix, tensor_form, time_segments):
+    """Outside the timed region: is what was just timed the right audio? (a) the whole N-rank mix of configs[4] against the
+    reference's render of the same timeline; (b) a 16-voice slice of the same timeline, full length, dealt over the same ranks,
+    against the reference AND the FP64 arbiter (oracle/slices.py), which tells whose rounding moved."""
+    from mesheditor_b200 import workloads as wl
+    from oracle import slices
+
+    torch = ranks.torch
+    frames = int(SECONDS * RATE)
+    events, ev_frames = slices.c5_slice_timeline(PARITY_SLICE_VOICES, frames)
+    bank = sharded_bank(ranks, PARITY_SLICE_VOICES, "tensor" if tensor_form else "loop")
+    if time_segments == 1:
+        bank.set_time_segments(1)  # the walk the timed 1024-voice bank took
+    routed = bank.route_events([wl.impact(v, impulse, ex) for v, impulse, ex in events], ev_frames)
+    out = torch.zeros(frames, dtype=torch.float32, device="cuda")
+    stream = torch.cuda.Stream()  # an explicit stream: the library's kernels and the all-reduce must share one (NULL would mean the bank's own)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(stream):
+        bank.render_offline_device(routed, frames, BLOCK, out, stream.cuda_stream)
+    stream.synchronize()
+    if ranks.rank != 0:
+        return None
+    gpu_slice = out.cpu().numpy()
+    ref, kind = slices.reference_render(PARITY_SLICE_VOICES, frames, threads=min(16, os.cpu_count() or 1), events=events, ev_frames=ev_frames)
+    exact = slices.exact_render(PARITY_SLICE_VOICES, frames, events=events, ev_frames=ev_frames)
+    rep = {"gate": slices.GATE, "unit": "fraction of the reference render's peak amplitude", "oracle": kind,
+           "slice": dict(slices.compare(gpu_slice, ref, exact), voices=PARITY_SLICE_VOICES, frames=frames, ranks=ranks.world)}
+    if reference_mix is not None:
+        peak = float(np.abs(reference_mix).max())
+        rep["full_config"] = {"voices": VOICES, "frames": frames, "peak": peak, "gpu_vs_reference": float(np.abs(full_mix.astype(np.float64) - reference_mix).max() / peak),
+                              "note": "the N-rank mix of the timed configuration against the reference's float32 RenderModal of the same timeline (the cpu_baseline leg's own output)"}
+    s = rep["slice"]
+    rep["verdict"] = ("within the gate of the exact recurrence over all 10 s" if s["gpu_vs_exact"] <= slices.GATE else "OUTSIDE the gate of the exact recurrence") + \
+                     f"; the reference's own float32 recurrence is {s['reference_vs_exact']:.2e} of peak from the exact value by the end, so |gpu - reference| = {s['gpu_vs_reference']:.2e} is the reference's drift, not the GPU's"
+    return rep
+
+
+def run_resonator(args, ranks):
+    from mesheditor_b200 import ModalBank, measure_fp32_fma_rate  # noqa: F401
+    from mesheditor_b200 import workloads as wl
+
+    torch, dist = ranks.torch, ranks.dist
+    rank, world, local = ranks.rank, ranks.world, ranks.local
+    voices = args.voices or VOICES
+    frames = int(SECONDS * RATE)
+    bank = sharded_bank(ranks, voices, args.render_path)
+    mine = len(bank.owned())
+    all_events, all_frames, _ = wl.c5_timeline(voices, frames)
+    routed = bank.route_events([wl.impact(v, impulse, ex) for v, impulse, ex in all_events], all_frames)  # contiguous MeModalEvent[] + frames, built once
 
     out = torch.zeros(frames, dtype=torch.float32, device="cuda")
     host_out = torch.zeros(frames, dtype=torch.float32).pin_memory()
     # One explicit stream carries the library's kernels, the NCCL all-reduce and the timing events.
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    launches = [0]
 
     def step_device():
-        bank.render_offline_device(events, ev_frames, frames, BLOCK, out.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(out)
+        bank.render_offline_device(routed, frames, BLOCK, out, stream.cuda_stream)
 
     def step_e2e():
-        # Strike timeline from host memory in, final mix back in host memory (rank 0 keeps it).
-        bank.render_offline_device(events, ev_frames, frames, BLOCK, out.data_ptr(), stream.cuda_stream)
-        if world > 1:
-            dist.all_reduce(out)
+        # Strike timeline from host memory in, final mix back in host memory.
+        bank.render_offline_device(routed, frames, BLOCK, out, stream.cuda_stream)
         host_out.copy_(out, non_blocking=True)
         stream.synchronize()
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # Each step re-renders the same 10 s from a silent bank, so every step does identical work.
+    # Each step re-renders the same 10 s from a silent bank, so every step does identical work. (Tuning the bank — the power
+    # stages of the tensor-core form, 2.7 ms on the device — happens once at setup, like the reference's TuneModalObject.)
     def reset():
-        bank.install(0)
+        bank.local.install(0)
 
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         reset()
         step_device()
-    barrier()
+    ranks.barrier()
 
-    kernel_ms, walk_ms, mix_ms, stats = [], [], [], None
+    kernel_ms, walk_ms, mix_ms, pulse_ms, plan_ms, stats, launches = [], [], [], [], [], None, 0
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     elapsed_ms = 0.0
     with ClockSampler(local) as clocks:
         for _ in range(args.steps):
             reset()
-            barrier()
+            ranks.barrier()
             start.record(stream)
             step_device()
             stop.record(stream)
-            barrier()
+            ranks.barrier()
             elapsed_ms += start.elapsed_time(stop)
             stats = bank.stats()
             if os.environ.get("ME_BENCH_DEBUG"):
                 print(f"[bench] step {start.elapsed_time(stop):.2f} ms, library total {stats['total_device_ms']:.2f} ms, walk {stats['walk_kernel_ms']:.2f}, mix {stats['tensor_mix_kernel_ms']:.2f}, host plan {stats['host_plan_ms']:.2f}, pulses {stats['pulse_kernels_ms']:.2f}, stage {stats['resonator_kernel_ms']:.2f}", file=sys.stderr)
-            kernel_ms.append(stats["resonator_kernel_ms"])
-            walk_ms.append(stats["walk_kernel_ms"])
-            mix_ms.append(stats["tensor_mix_kernel_ms"])
-            launches[0] += stats["kernel_launches"]
+            kernel_ms.append(stats["resonator_kernel_ms"]), walk_ms.append(stats["walk_kernel_ms"]), mix_ms.append(stats["tensor_mix_kernel_ms"])
+            pulse_ms.append(stats["pulse_kernels_ms"]), plan_ms.append(stats["host_plan_ms"])
+            launches += stats["kernel_launches"]
     # e2e: wall clock around the host-buffer path.
     e2e_s = 0.0
     for _ in range(args.steps):
         reset()
-        barrier()
+        ranks.barrier()
         t0 = time.perf_counter()
         step_e2e()
         e2e_s += time.perf_counter() - t0
-        launches[0] += bank.stats()["kernel_launches"]
-    barrier()
+        launches += bank.stats()["kernel_launches"]
+    ranks.barrier()
+    full_mix = host_out.numpy().copy()
 
-    live = [bank.object_status(v)["LiveModeCount"] for v in range(hi - lo)]
+    live = [bank.local.object_status(v)["LiveModeCount"] for v in range(mine)] or [MODES]
     fallbacks = stats["scan_fallbacks"]
-    t = torch.tensor([elapsed_ms, e2e_s, float(launches[0]), float(min(live)) - 1e6 * fallbacks], dtype=torch.float64, device="cuda")
-    if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        tmin = t.clone()
-        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-        elapsed_ms, e2e_s, total_launches, min_live = float(tmax[0]), float(tmax[1]), int(tsum[2]), int(tmin[3])
-    else:
-        total_launches, min_live = launches[0], int(min(live))
+    elapsed_ms, e2e_s = ranks.reduce([elapsed_ms, e2e_s], "max")
+    total_launches = int(ranks.reduce([float(launches)], "sum")[0])
+    min_live = int(ranks.reduce([float(min(live)) - 1e6 * fallbacks], "min")[0])
+    tensor_form = stats["tensor_windows"] > 0
 
+    line = None
     if rank == 0:
-        total_mode_samples = VOICES * MODES * frames
+        avg = lambda xs: sum(xs) / len(xs)  # noqa: E731
+        total_mode_samples = voices * MODES * frames
         ms_per_step = elapsed_ms / args.steps
         value = total_mode_samples / (ms_per_step * 1e-3)
         e2e_value = total_mode_samples / (e2e_s / args.steps)
         pk, pk_kind = peaks()
         fma_peak = measure_fp32_fma_rate(local, 0, 10)       # scalar FFMA, the nominal FP32 issue ceiling
         fma_peak_fresh = measure_fp32_fma_rate(local, 5, 10)  # FFMA2 with three fresh register pairs (register-file bound)
-        k_ms = sum(kernel_ms) / len(kernel_ms)
-        rank_mode_samples = (hi - lo) * MODES * frames
+        k_ms = avg(kernel_ms)
+        rank_mode_samples = mine * MODES * frames
         achieved = OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3)
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "resonator_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-        # Mandatory bytes of one launch on this rank: 32 B per mode of state/coefficients + the per-warp
-        # partial rows written once (4 B per warp-sample) — the latter is this design's own traffic, counted as such.
-        mandatory = (hi - lo) * (32 * MODES) + 4 * frames
-        base = cpu_reference(1, 0) if not args.no_cpu_baseline else None
-        tensor_form = stats["tensor_windows"] > 0
+        # Mandatory bytes of one launch on this rank (SURVEY.md §8d): 32 B per mode of state/coefficients + the mix written once.
+        mandatory = mine * (32 * MODES) + 4 * frames
+        base, reference_mix = (None, None) if args.no_cpu_baseline else cpu_reference(1, 0)
         if tensor_form:
             # Tensor-core form (DESIGN.md §5.2). Dominant kernels: the tcgen05 mix (3xTF32 GEMM) and the state walk that
             # feeds it. Issued flops and written bytes follow from the padded layout: 4 voices of 63 chunks per 256-chunk
             # group, 4096 reduction elements per group, 128 time blocks of 256 frames per tile.
             chunks = -(-MODES // 8)
-            groups = -(-(hi - lo) // (256 // chunks))
+            groups = -(-mine // (256 // chunks))
             tiles = -(-frames // 32768)
             product_flops = 2.0 * 256 * 128 * 4096 * groups * tiles  # one of the three products of the 3xTF32 split
             # head x head runs as kind::tf32, the two cross products as kind::f16 on BF16 copies at twice that rate: the
@@ -307,54 +413,67 @@ def run_ours(args):
             issued_flops = 3 * product_flops
             tf32_equivalent = 2 * product_flops
             walk_bytes = 4096 * 4.0 * groups * -(-frames // 256)
-            m_ms, w_ms = sum(mix_ms) / len(mix_ms), sum(walk_ms) / len(walk_ms)
+            m_ms, w_ms = avg(mix_ms), avg(walk_ms)
             tf32_peak = pk.get("bf16_tflops", 2250.0) / 2
             stages = groups * 256 * tiles
             smem_bytes = stages * 106496.0  # per 16-element stage: 40 KB of TMA writes, 16 KB of splitter traffic, 48 KB of MMA operand reads
+            prof = profiled_traffic()
+            # The ncu figure belongs to the launch it was captured on; a rank's launch covers (its groups x tiles) of that.
+            scale = groups * tiles / max(1, prof.get("groups", 256) * prof.get("tiles", 15))
+            traffic = lambda which: (prof[f"{which}_dram_bytes_per_launch"] * scale if f"{which}_dram_bytes_per_launch" in prof else None)  # noqa: E731
             roofline = {
                 "bound": "tensor", "kernel": "TensorMixKernel<128,4> (tcgen05.mma: head x head kind::tf32, cross products kind::f16 on BF16 copies; FP32 register folds)",
                 "achieved": tf32_equivalent / (m_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TF32-equivalent TFLOP/s", "frac": tf32_equivalent / (m_ms * 1e-3) / 1e12 / tf32_peak,
-                "traffic": tensor_traffic("mix"), "kernel_ms_per_launch": m_ms, "launches_per_step": stats["tensor_windows"],
+                "traffic": traffic("mix"), "traffic_source": f"ncu --set full dram__bytes of the {prof.get('groups', 256)}-group x {prof.get('tiles', 15)}-tile launch (profiles/), scaled by this rank's groups x tiles = {groups} x {tiles}",
+                "kernel_ms_per_launch": m_ms, "launches_per_step": stats["tensor_windows"],
                 "issued_flops_per_step": issued_flops, "issued_tflops": issued_flops / (m_ms * 1e-3) / 1e12, "share_of_step": m_ms / ms_per_step,
                 "peak_source": ("half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate; nominal 1125)" if "bf16_tflops" in pk else "nominal dense TF32 1125 TFLOP/s"),
                 "reference_fma_equivalent": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (m_ms * 1e-3) / 1e12,
                 "shared_memory": {"bytes_per_launch": smem_bytes, "achieved_bytes_per_clk_per_sm": smem_bytes / (m_ms * 1e-3) / (148 * (pk.get("sm_max_mhz", 1965.0) * 1e6)), "peak_bytes_per_clk_per_sm": 128,
-                                  "note": "what actually bounds the kernel: SS-mode MMAs read both operands from shared memory (DESIGN.md 5.2, profiles/r01_resonator.md)"},
+                                  "note": "what actually bounds the kernel: SS-mode MMAs read both operands from shared memory (DESIGN.md 5.2)"},
             }
-            roofline_extra = {
+            extra = {
                 "roofline_walk": {"bound": "hbm", "kernel": "ResonatorKernel<1,2,true> (state walk: c^256 steps, FP32 state rows)", "achieved": walk_bytes / (w_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                  "frac": walk_bytes / (w_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": tensor_traffic("walk"), "kernel_ms_per_launch": w_ms, "algorithmic_bytes": walk_bytes, "share_of_step": w_ms / ms_per_step, "peak_source": pk_kind},
+                                  "frac": walk_bytes / (w_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic("walk"), "kernel_ms_per_launch": w_ms, "algorithmic_bytes": walk_bytes, "share_of_step": w_ms / ms_per_step, "peak_source": pk_kind},
                 "fp32_pipe_equivalent": {"note": "the same mode-samples per second on the FP32 pipe would need this multiple of the measured scalar-FFMA ceiling (reference loop: 7 lane-ops per mode-sample; this repo's sample loop: 2.75)",
                                          "reference_loop": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3) / fma_peak, "sample_loop": achieved / fma_peak, "ffma_peak_tlane_ops": fma_peak / 1e12},
             }
         else:
             roofline = {
                 "bound": "fp32_fma", "kernel": "ResonatorKernel<4,2>", "achieved": achieved / 1e12, "peak": fma_peak / 1e12, "unit": "TFMA-lane-op/s",
-                "frac": achieved / fma_peak, "traffic": traffic, "kernel_ms_per_launch": k_ms,
+                "frac": achieved / fma_peak, "traffic": None, "kernel_ms_per_launch": k_ms,
                 "ops_per_mode_sample": OPS_PER_MODE_SAMPLE, "peak_source": "FFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP32 figure)",
                 "peak_three_fresh_operands": fma_peak_fresh / 1e12, "frac_of_register_file_bound": achieved / fma_peak_fresh,
                 "reference_op_equivalent_frac": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3) / fma_peak,
             }
-            roofline_extra = {}
+            extra = {}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (3xTF32 products, FP32 accumulation)" if tensor_form else "f32", "data": "synthetic",
-            "config": dict(workload_config(world), live_mode_count_min=min_live, culling_triggered=min_live < MODES, time_segments=stats["time_segments"],
-                           render_path="tensor-core form: state walk + tcgen05 mix" if tensor_form else "FP32 sample loop", partial_rows=stats["partial_rows"]),
+            "config": workload_config(world) if voices == VOICES else dict(workload_config(world), voices=voices, workload=f"EXPERIMENT: {voices} voices (not the BASELINE.json configuration)"),
+            "run": {"live_mode_count_min": min_live, "culling_triggered": min_live < MODES, "time_segments": stats["time_segments"], "voices_on_rank0": mine,
+                    "render_path": "tensor-core form: state walk + tcgen05 mix" if tensor_form else "FP32 sample loop", "partial_rows": stats["partial_rows"],
+                    "step_breakdown_ms_rank0": {"walk": avg(walk_ms), "tensor_mix": avg(mix_ms), "force_and_pulse_kernels": avg(pulse_ms), "host_planning": avg(plan_ms), "whole_step": ms_per_step},
+                    "outside_the_timed_step": "bank tuning (TuneModalObject on the host, power stages of the tensor-core form: PowerTableKernel, once per tuning) and me_bank_install, as in the reference where tuning happens at setup"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": frames * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": total_launches,
             "roofline": roofline,
-            **roofline_extra,
+            **extra,
             "roofline_hbm": {"bound": "hbm", "achieved": mandatory / (k_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": mandatory / (k_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "peak_source": pk_kind,
                              "note": "mandatory bytes of the reference formulation only (SURVEY.md F9)"},
             "clocks": clocks.summary(),
         }
         if base:
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    else:
+        reference_mix = None
+    torch.cuda.synchronize()
+    torch.cuda.set_stream(torch.cuda.default_stream())
+    if not args.no_parity and voices == VOICES:
+        rep = parity_report(ranks, full_mix, reference_mix, tensor_form, stats["time_segments"])
+        if rank == 0:
+            line["parity"] = rep
+    return line
 
 
 # ------------------------------------------------------------------------------------------------ analysis workloads
@@ -385,7 +504,7 @@ def cpu_solve_reference(edge=CPU_SAMPLE_EDGE, modes=C3_MODES, order=C3_ORDER):
     dt = time.perf_counter() - t0
     return {"value": dt, "unit": SOLVE_UNIT, "cores": os.cpu_count() or 1, "kind": "port", "tets": len(tets), "dofs": r["dofs"],
             "sample": f"{edge}^3-cell Kuhn block = {len(tets):,} tets ({len(tets) / (6 * C3_EDGE ** 3):.1%} of the workload's tets), P{order}, {modes} modes, oracle/modal.py (numpy assembly + scipy ARPACK/SuperLU, BLAS threads on all host cores): "
-                      f"{dt:.1f} s for this sample; the full 998,250-tet mesh does not finish on the host in the bench's time budget"}
+                      f"{dt:.1f} s for this sample; the full 998,250-tet mesh does not finish on the host in the bench's time budget (SuperLU's fill grows ~n^(4/3): a stage-wise extrapolation would be a guess, so none is given)"}
 
 
 def solve_once(points, tets, ex, cfg):
@@ -396,104 +515,99 @@ def solve_once(points, tets, ex, cfg):
     return time.perf_counter() - t0, r
 
 
-def run_solve(args):
-    """`--workload solve`: one 1M-tet mesh on one GPU (a single eigensolve does not shard: with --gpus N every rank solves a
-    replica and the slowest is reported)."""
-    import torch
-    import torch.distributed as dist
+STAGES = ("mass_props", "assemble", "sample_excite", "factorize", "analyse", "iterate", "op_solve", "extract", "dofs", "stiffness_nonzeros", "op_applications", "restarts", "factor_nonzeros", "supernodes", "levels")
 
-    from mesheditor_b200 import Factor, FemSystem, build, measure_fp64_rate, solver_config
+
+def run_solve(args, ranks, steps, warmup, cpu_baseline=True):
+    """configs[2]: one 1M-tet mesh on one GPU (a single eigensolve does not shard: every rank solves a replica and the slowest
+    is reported). Returns the record (rank 0) with the reference bench's stage table (tests/ModalSolverBench.cpp:413-449)."""
+    from mesheditor_b200 import Factor, FemSystem, measure_fp64_rate, solver_config
     from mesheditor_b200 import workloads as wl
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    build.build()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch = ranks.torch
+    rank, world, local = ranks.rank, ranks.world, ranks.local
     points, tets = wl.kuhn_block(C3_EDGE, C3_EDGE, C3_EDGE, (0.3, 0.3, 0.3))
     ex = wl.bench_excitations(points)
     cfg = solver_config(num_modes=C3_MODES, element_order=C3_ORDER, max_mode_freq=1e9, device=local)
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(warmup):
         solve_once(points, tets, ex, cfg)
     times, profiles = [], []
     with ClockSampler(local) as clocks:
-        for _ in range(args.steps):
-            torch.cuda.synchronize()
+        for _ in range(steps):
+            ranks.barrier()
             dt, r = solve_once(points, tets, ex, cfg)  # host mesh in, host modal model out: this IS the end-to-end call
             assert r.status == 0 and len(r.freqs) == C3_MODES
             times.append(dt)
             profiles.append(r.profile)
-    t = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0:
-        sec = float(t[0])
-        prof = {k: (sum(p[k] for p in profiles) / len(profiles) if isinstance(profiles[0][k], float) else profiles[-1][k]) for k in profiles[0]}
-        device_s = sec - prof["mass_props"]  # everything but the (host) lumped mass properties runs on, or waits for, the device
-        pk, pk_kind = peaks()
-        # Stage rooflines, measured in this run through the stage entry points of the C ABI.
-        fem = FemSystem(points, tets, "Steel", C3_ORDER, local)
-        i = fem.info
-        x = np.random.default_rng(0).standard_normal(i["dofs"])
-        fem.spmv("K", x, 50)
-        spmv_bytes = 12 * 9 * i["node_blocks_full"] + 20 * i["dofs"] + 4
-        spmv = {"kernel": "SpmvBsr3Kernel (y = K x)", "bound": "hbm", "achieved": spmv_bytes / (fem.last_spmv_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "ms": fem.last_spmv_ms, "algorithmic_bytes": spmv_bytes}
-        spmv["frac"] = spmv["achieved"] / spmv["peak"]
-        asm_bytes = 16 * len(tets) + 24 * len(points) + 12 * (i["nnz_stiffness"] + i["nnz_mass"]) + 8 * (i["dofs"] + 1)
-        asm = {"kernel": "AssembleKernel", "bound": "hbm", "achieved": asm_bytes / (i["assemble_kernel_ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "ms": i["assemble_kernel_ms"], "algorithmic_bytes": asm_bytes}
-        asm["frac"] = asm["achieved"] / asm["peak"]
-        f = Factor(fem, -((2 * np.pi * 20.0) ** 2))
-        fi = f.info
-        dmma = measure_fp64_rate(local, 1, 3)
-        factor = {"kernel": "SyrkScatterKernel + PanelTrsmKernel + FactorDiagKernel (numeric Cholesky)", "bound": "tensor", "achieved": fi["factor_flops"] / (fi["factor_device_ms"] * 1e-3) / 1e12, "peak": dmma / 1e12,
-                  "unit": "TFLOP/s", "ms": fi["factor_device_ms"], "flops": fi["factor_flops"], "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) issue-rate probe measured in this run; MEASURED_PEAKS.json has no FP64 figure"}
-        factor["frac"] = factor["achieved"] / factor["peak"]
-        b = np.random.default_rng(1).standard_normal(i["dofs"])
-        for _ in range(3):
-            f.solve(b)
-        solve_ms = f.info["last_solve_device_ms"]
-        sweep_bytes = 16 * fi["factor_nonzeros"] + 16 * i["dofs"]
-        ops = prof["op_applications"]
-        line = {
-            "metric": SOLVE_METRIC, "value": sec, "unit": SOLVE_UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 * sec, "higher_is_better": False,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(solve_config(), parallelism="replicas only: one mesh's eigensolve runs on one GPU" if world > 1 else "single GPU"),
-            "e2e": {"value": sec, "unit": SOLVE_UNIT, "h2d_bytes_per_step": int(points.nbytes + tets.nbytes + ex.nbytes), "d2h_bytes_per_step": int(8 * (C3_MODES + 15) + 4 * 3 * 10 * (C3_MODES + 15) + 4 * 3 * 10),
-                    "note": "me_modal_solve takes the mesh from HOST memory and returns the modal model to HOST memory; value and e2e are the same call"},
-            "device_seconds": device_s, "gpu_launches": int(sum(p["kernel_launches"] for p in profiles)),
-            "profile": {k: prof[k] for k in ("mass_props", "assemble", "sample_excite", "factorize", "analyse", "iterate", "op_solve", "extract", "dofs", "stiffness_nonzeros", "op_applications", "restarts", "factor_nonzeros", "supernodes", "levels")},
-            "roofline": {"bound": "hbm", "kernel": "triangular-solve sweep of the shift-invert operator (DiagSolve/PanelForward/PanelBackward, one CUDA-graph replay per operator application)",
-                         "achieved": sweep_bytes / (solve_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": sweep_bytes / (solve_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
-                         "ms_per_launch": solve_ms, "algorithmic_bytes": sweep_bytes, "share_of_step": prof["op_solve"] / sec, "applications_per_step": ops, "peak_source": pk_kind},
-            "roofline_spmv": spmv, "roofline_assembly": asm, "roofline_factor": factor,
-            "clocks": clocks.summary(),
-        }
-        if not args.no_cpu_baseline:
-            base = cpu_solve_reference()
-            line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    sec = ranks.reduce([sum(times) / len(times)], "max")[0]
+    if rank != 0:
+        return None
+    prof = {k: (sum(p[k] for p in profiles) / len(profiles) if isinstance(profiles[0][k], float) else profiles[-1][k]) for k in profiles[0]}
+    pk, pk_kind = peaks()
+    # Stage rooflines, measured in this run through the stage entry points of the C ABI.
+    fem = FemSystem(points, tets, "Steel", C3_ORDER, local)
+    i = fem.info
+    x = np.random.default_rng(0).standard_normal(i["dofs"])
+    fem.spmv("K", x, 50)
+    spmv_bytes = 12 * 9 * i["node_blocks_full"] + 20 * i["dofs"] + 4
+    spmv = {"kernel": "SpmvBsr3Kernel (y = K x)", "bound": "hbm", "achieved": spmv_bytes / (fem.last_spmv_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "ms": fem.last_spmv_ms, "algorithmic_bytes": spmv_bytes}
+    spmv["frac"] = spmv["achieved"] / spmv["peak"]
+    asm_bytes = 16 * len(tets) + 24 * len(points) + 12 * (i["nnz_stiffness"] + i["nnz_mass"]) + 8 * (i["dofs"] + 1)
+    asm = {"kernel": "AssembleKernel", "bound": "hbm", "achieved": asm_bytes / (i["assemble_kernel_ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "ms": i["assemble_kernel_ms"], "algorithmic_bytes": asm_bytes}
+    asm["frac"] = asm["achieved"] / asm["peak"]
+    f = Factor(fem, -((2 * np.pi * 20.0) ** 2))
+    fi = f.info
+    dmma = measure_fp64_rate(local, 1, 3)
+    factor = {"kernel": "SyrkScatterKernel + PanelTrsmKernel + FactorDiagKernel (numeric Cholesky)", "bound": "tensor", "achieved": fi["factor_flops"] / (fi["factor_device_ms"] * 1e-3) / 1e12, "peak": dmma / 1e12,
+              "unit": "TFLOP/s", "ms": fi["factor_device_ms"], "flops": fi["factor_flops"], "peak_source": "FP64 DMMA (mma.sync.m8n8k4.f64) issue-rate probe measured in this run; MEASURED_PEAKS.json has no FP64 figure"}
+    factor["frac"] = factor["achieved"] / factor["peak"]
+    # The timed solve applies the operator to PANELS of 8 Krylov vectors: the kernels on its path are the 8-wide sweeps
+    # (solve_panel, CholeskyShiftInvert.cpp:55-62). Timed here with CUDA events around one panel application, 5 repetitions.
+    sweep_bytes = 16 * fi["factor_nonzeros"] + 16 * i["dofs"] * 8
+    b8 = np.asfortranarray(np.random.default_rng(1).standard_normal((i["dofs"], 8)))
+    panel_ms = []
+    for _ in range(6):
+        f.solve(b8)
+        panel_ms.append(f.info["last_solve_device_ms"])
+    panel_ms = sum(panel_ms[1:]) / 5
+    b1 = b8[:, 0].copy()
+    single_ms = []
+    for _ in range(4):
+        f.solve(b1)
+        single_ms.append(f.info["last_solve_device_ms"])
+    single_ms = sum(single_ms[1:]) / 3
+    ops = prof["op_applications"]
+    panels = -(-ops // 8)
+    rec = {
+        "metric": SOLVE_METRIC, "value": sec, "unit": SOLVE_UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sec, "higher_is_better": False,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": dict(solve_config(), parallelism="replicas only: one mesh's eigensolve runs on one GPU; every rank solves the same mesh, the slowest is reported" if world > 1 else "single GPU"),
+        "e2e": {"value": sec, "unit": SOLVE_UNIT, "h2d_bytes_per_step": int(points.nbytes + tets.nbytes + ex.nbytes), "d2h_bytes_per_step": int(8 * (C3_MODES + 15) + 4 * 3 * 10 * (C3_MODES + 15) + 4 * 3 * 10),
+                "note": "me_modal_solve takes the mesh from HOST memory and returns the modal model to HOST memory; value and e2e are the same call"},
+        "device_seconds": sec - prof["mass_props"], "gpu_launches": int(sum(p["kernel_launches"] for p in profiles)),
+        "profile": {k: prof[k] for k in STAGES},
+        "roofline": {"bound": "hbm", "kernel": "WideSweepKernel<0> + WideSweepKernel<1> (forward + backward triangular sweeps over the factor for a panel of 8 right-hand sides; WideBegin / MarkUnsolved / WidePermuteOut ride in the same event pair, ~1 % of it)",
+                     "achieved": sweep_bytes / (panel_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": sweep_bytes / (panel_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                     "ms_per_launch": panel_ms, "algorithmic_bytes": sweep_bytes, "share_of_step": prof["op_solve"] / sec, "panel_applications_per_step": panels, "operator_applications_per_step": ops,
+                     "op_solve_ms_per_panel_in_the_timed_solve": 1e3 * prof["op_solve"] / panels, "peak_source": pk_kind,
+                     "bytes": "16 * nnz(L) (the factor read once forward and once backward, 8 B each) + 16 * n * 8 (eight right-hand sides in and out)"},
+        "roofline_single_sweep": {"kernel": "SweepKernel<0/1> (one right-hand side; NOT on the timed path, kept for comparison)", "bound": "hbm", "ms_per_launch": single_ms, "achieved": (16 * fi["factor_nonzeros"] + 16 * i["dofs"]) / (single_ms * 1e-3) / 1e9,
+                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (16 * fi["factor_nonzeros"] + 16 * i["dofs"]) / (single_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "roofline_spmv": spmv, "roofline_assembly": asm, "roofline_factor": factor,
+        "clocks": clocks.summary(),
+    }
+    if cpu_baseline:
+        base = cpu_solve_reference()
+        rec["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    return rec
 
 
-def run_batch(args):
-    """`--workload batch`: BASELINE.json configs[3], 64 Kuhn blocks of 10k..500k tets, dealt biggest-first to the least-loaded
-    rank (the reference bench's biggest-file-first rule, tests/ModalSolverBench.cpp:475-478); no collective on the data path."""
-    import torch
-    import torch.distributed as dist
-
-    from mesheditor_b200 import build, solver_config
+def run_batch(args, ranks, steps, warmup):
+    """BASELINE.json configs[3], 64 Kuhn blocks of 10k..500k tets, dealt biggest-first to the least-loaded rank (the reference
+    bench's biggest-file-first rule, tests/ModalSolverBench.cpp:475-478); no collective on the data path."""
+    from mesheditor_b200 import solver_config
     from mesheditor_b200 import workloads as wl
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    build.build()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world, local = ranks.rank, ranks.world, ranks.local
     dims = wl.config4_dims()
     owner = wl.lpt_assign([(6.0 * d ** 3) ** (4.0 / 3.0) for d in dims], world)
     mine = [d for d, o in zip(dims, owner) if o == rank]
@@ -501,43 +615,39 @@ def run_batch(args):
     meshes = [wl.kuhn_block(d, d, d, (0.3, 0.3, 0.3)) for d in mine]
 
     def step():
-        n = 0
+        n, busy = 0, time.perf_counter()
         for points, tets in meshes:
             _, r = solve_once(points, tets, wl.bench_excitations(points), cfg)
-            assert r.status == 0
+            assert r.status == 0 and len(r.freqs) == 30
             n += r.profile["kernel_launches"]
-        return n
+        return n, time.perf_counter() - busy
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-
-    for _ in range(max(1, min(args.warmup, 3)) if args.warmup else 0):
+    for _ in range(warmup):
         step()
-    launches, total = 0, 0.0
+    launches, total, busy_s = 0, 0.0, 0.0
     with ClockSampler(local) as clocks:
-        for _ in range(args.steps):
-            barrier()
+        for _ in range(steps):
+            ranks.barrier()
             t0 = time.perf_counter()
-            launches += step()
-            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            total += float(dt[0])
-    lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(lt)
-    if rank == 0:
-        sec = total / args.steps
-        print(json.dumps({
-            "metric": "batch modal solve meshes/s", "value": len(dims) / sec, "unit": "meshes/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"BASELINE.json configs[3]: 64 Kuhn-block meshes, {6 * dims[0] ** 3:,}..{6 * dims[-1] ** 3:,} tets (log-spaced), P1, lowest 30 modes each", "parallelism": f"meshes dealt biggest-first over {world} GPU(s), no collective"},
-            "e2e": {"value": len(dims) / sec, "unit": "meshes/s", "h2d_bytes_per_step": int(sum(p.nbytes + t.nbytes for p, t in meshes)), "d2h_bytes_per_step": 0}, "gpu_launches": int(lt[0]), "clocks": clocks.summary()}))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+            n, busy = step()
+            launches += n
+            busy_s += busy
+            total += ranks.reduce([time.perf_counter() - t0], "max")[0]
+    n_launches = int(ranks.reduce([float(launches)], "sum")[0])
+    busy_all = ranks.reduce([busy_s / steps], "sum")[0]
+    if rank != 0:
+        return None
+    sec = total / steps
+    return {
+        "metric": "batch modal solve meshes/s", "value": len(dims) / sec, "unit": "meshes/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE.json configs[3]: 64 Kuhn-block meshes, {6 * dims[0] ** 3:,}..{6 * dims[-1] ** 3:,} tets (log-spaced), P1, lowest 30 modes each", "tets_total": int(sum(6 * d ** 3 for d in dims)),
+                   "parallelism": f"meshes dealt biggest-first over {world} GPU(s) by tets^(4/3), no collective on the data path"},
+        "seconds_per_batch": sec, "tets_per_second": float(sum(6 * d ** 3 for d in dims)) / sec, "load_balance": busy_all / (world * sec),
+        "e2e": {"value": len(dims) / sec, "unit": "meshes/s", "h2d_bytes_per_step": int(sum(p.nbytes + t.nbytes for p, t in meshes)), "d2h_bytes_per_step": 0,
+                "note": "each solve is an me_modal_solve call: host mesh in, host modal model out"},
+        "gpu_launches": n_launches, "clocks": clocks.summary(),
+    }
 
 
 def run_solve_reference(args):
@@ -558,26 +668,33 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity report of the resonator line (it renders a 16-voice slice on the host twice: ~10 s)")
     ap.add_argument("--voices", type=int, default=0, help="resonator: experiment with another voice count (the bench line then names it; default = BASELINE.json configs[4])")
     ap.add_argument("--render-path", default="auto", choices=["auto", "loop", "tensor"], help="resonator: kernels of the free-running bank (auto = tensor-core form for this workload)")
-    ap.add_argument("--workload", default="resonator", choices=["resonator", "solve", "batch"],
-                    help="resonator: configs[4] (default, the metric quoted at 1/2/4/8 GPUs); solve: configs[2], one 1M-tet mesh; batch: configs[3], 64 meshes sharded")
+    ap.add_argument("--workload", default="all", choices=["all", "resonator", "solve", "batch"],
+                    help="all (default): the resonator line (configs[4], the metric quoted at 1/2/4/8 GPUs) carrying the `solve` (configs[2]) and `batch` (configs[3]) records; or one of them alone")
+    ap.add_argument("--solve-steps", type=int, default=2, help="timed me_modal_solve calls of the solve record (after one warm-up call)")
     args = ap.parse_args()
-    if args.workload == "solve":
-        if args.steps == 5:
-            args.steps = 2
-        run_solve_reference(args) if args.impl == "reference" else run_solve(args)
-    elif args.workload == "batch":
-        if args.steps == 5:
-            args.steps = 1
-        if args.impl == "reference":
-            run_solve_reference(args)
+    if args.impl == "reference":
+        return run_solve_reference(args) if args.workload in ("solve", "batch") else run_reference(args)
+    ranks = Ranks(args)
+    try:
+        if args.workload == "solve":
+            line = run_solve(args, ranks, args.steps if args.steps != 5 else args.solve_steps, max(1, min(args.warmup, 3)), not args.no_cpu_baseline)
+        elif args.workload == "batch":
+            line = run_batch(args, ranks, args.steps if args.steps != 5 else 1, 1 if args.warmup else 0)
         else:
-            run_batch(args)
-    elif args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+            line = run_resonator(args, ranks)
+            if args.workload == "all":
+                # The other half of BASELINE.json's metric and its sharded batch, in the line the driver parses.
+                solve = run_solve(args, ranks, args.solve_steps, 1, not args.no_cpu_baseline)
+                batch = run_batch(args, ranks, 1, 0)
+                if ranks.rank == 0:
+                    line["solve"], line["batch"] = solve, batch
+        if ranks.rank == 0:
+            print(json.dumps(line))
+    finally:
+        ranks.close()
 
 
 if __name__ == "__main__":
