@@ -584,7 +584,7 @@ def run_solve(args, ranks, steps, warmup, cpu_baseline=True):
         "e2e": {"value": sec, "unit": SOLVE_UNIT, "h2d_bytes_per_step": int(points.nbytes + tets.nbytes + ex.nbytes), "d2h_bytes_per_step": int(8 * (C3_MODES + 15) + 4 * 3 * 10 * (C3_MODES + 15) + 4 * 3 * 10),
                 "note": "me_modal_solve takes the mesh from HOST memory and returns the modal model to HOST memory; value and e2e are the same call"},
         "device_seconds": sec - prof["mass_props"], "gpu_launches": int(sum(p["kernel_launches"] for p in profiles)),
-        "profile": {k: prof[k] for k in STAGES},
+        "seconds_each": times, "profile": {k: prof[k] for k in STAGES},
         "roofline": {"bound": "hbm", "kernel": "WideSweepKernel<0> + WideSweepKernel<1> (forward + backward triangular sweeps over the factor for a panel of 8 right-hand sides; WideBegin / MarkUnsolved / WidePermuteOut ride in the same event pair, ~1 % of it)",
                      "achieved": sweep_bytes / (panel_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": sweep_bytes / (panel_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
                      "ms_per_launch": panel_ms, "algorithmic_bytes": sweep_bytes, "share_of_step": prof["op_solve"] / sec, "panel_applications_per_step": panels, "operator_applications_per_step": ops,

@@ -485,6 +485,22 @@ __device__ __forceinline__ void AwaitSolved2(const double *p, int *fail, double 
     x = __longlong_as_double((long long)a), y = __longlong_as_double((long long)b);
 }
 
+// Handshakes of the panel sweeps (what the ncu capture of the first version showed the warps waiting on: polls issued one
+// after the other, a full fence per task that also waited for the task's own matrix loads, the ticket atomic):
+//   * arrivals are published with ONE release-increment per link by a warp that issues it right after the CTA barrier
+//     that follows the contributions (st/red.release.gpu after __syncthreads is cumulative over the CTA's writes: the
+//     split-K semaphore pattern), and awaited with ld.acquire.gpu polls: no __threadfence anywhere;
+//   * the k x 8 solved entries a forward panel slab needs are requested all at once and only the missing ones re-polled;
+//   * tickets are claimed two tasks ahead, so neither the atomic nor the descriptor load is ever waited for.
+__device__ __forceinline__ void ArriveRelease(uint32_t *counter) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+__device__ __forceinline__ uint32_t PeekAcquire(const uint32_t *counter) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    return v;
+}
+
 template<bool Backward>
 __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKernel(SweepArgs a) {
     __shared__ __align__(16) double vec[128 * kWide];      // the k x 8 (or 32 x 8) right-hand operand
@@ -492,35 +508,23 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
     __shared__ SweepTask s_task;
     __shared__ uint32_t s_id, s_node[kSolveRows];
     const uint32_t t = threadIdx.x, lane = t & 31, q = t >> 5, fr = lane >> 2, fk = lane & 3;
-    uint32_t next_id = 0;
-    uint64_t next_word = 0;
-    auto prefetch_next = [&] {
-        if (t < 32) {
-            if (t == 0) next_id = atomicAdd(a.Ticket, 1u);
-            next_id = __shfl_sync(0xffffffffu, next_id, 0);
-            if (t < 8 && next_id < a.NumTasks) next_word = reinterpret_cast<const uint64_t *>(a.Tasks + next_id)[t];
-        }
+    // Warp 0 keeps two claimed tickets: `id1` with its 64-byte descriptor already requested (8 lanes x 8 bytes), and `id2`
+    // whose atomic may still be in flight. Both are consumed one iteration after they were issued.
+    uint32_t id1 = 0, id2 = 0;
+    uint64_t word1 = 0;
+    auto claim = [&]() -> uint32_t {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(a.Ticket, 1u);
+        return id;
     };
-    bool tail_any = false, tail_mine = false;
-    uint32_t tail_target = 0;
-    auto publish_tail = [&] {
-        if (tail_any) {
-            __threadfence();
-            __syncthreads();
-            if (tail_mine) atomicAdd(a.Arrived + tail_target, 1u);
-            tail_any = tail_mine = false;
-        }
-    };
-    auto await_arrivals = [&](uint32_t super, uint32_t need) {
-        if (t == 0) {
-            for (uint32_t spin = 0; Peek(a.Arrived + super) < need; ++spin) {
-                if (GiveUp(spin, a.Fail)) break;
-                __nanosleep(20);
-            }
-            __threadfence();
-        }
-        __syncthreads();
-    };
+    if (q == 0) {
+        id1 = __shfl_sync(0xffffffffu, claim(), 0);
+        if (lane < 8 && id1 < a.NumTasks) word1 = reinterpret_cast<const uint64_t *>(a.Tasks + id1)[lane];
+        id2 = claim();
+    }
+    // Arrivals owed by the previous panel slab, held by warp 3 (one link per lane).
+    bool owed = false;
+    uint32_t owed_target = 0;
     // C[32 x 8] partial of this warp = A-fragments val[mi*8+ks] (rows 8mi.., k-steps of the warp's quarter) times vec.
     auto contract_quarter = [&](const double (&val)[32], double (&c)[4][2]) {
 #pragma unroll
@@ -536,19 +540,25 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             *reinterpret_cast<double2 *>(&part[(q * 32 + 8 * mi + fr) * kWide + 2 * fk]) = make_double2(c[mi][0], c[mi][1]);
     };
     auto reduced = [&](uint32_t idx) { return (part[idx] + part[256 + idx]) + (part[512 + idx] + part[768 + idx]); };
-    prefetch_next();
     for (;;) {
-        __syncthreads();
-        if (t < 8) reinterpret_cast<uint64_t *>(&s_task)[t] = next_word;
-        if (t == 0) s_id = next_id;
+        __syncthreads(); // every contribution of the previous task has been issued; its shared operands are free
+        if (owed) ArriveRelease(a.Arrived + owed_target);
+        owed = false;
+        if (q == 0) {
+            if (lane < 8) reinterpret_cast<uint64_t *>(&s_task)[lane] = word1;
+            if (lane == 0) s_id = id1;
+        }
         __syncthreads();
         const uint32_t id = s_id;
-        if (id >= a.NumTasks) {
-            publish_tail();
-            return;
-        }
+        if (id >= a.NumTasks) return;
         const SweepTask task = s_task;
         const uint32_t k = task.K;
+        if (q == 0) { // shift the ticket pipeline
+            id1 = __shfl_sync(0xffffffffu, id2, 0);
+            word1 = 0;
+            if (lane < 8 && id1 < a.NumTasks) word1 = reinterpret_cast<const uint64_t *>(a.Tasks + id1)[lane];
+            id2 = claim();
+        }
         double val[32];
         if (task.Kind == 0) {
             const double *mat = a.Diag + task.Base;
@@ -560,9 +570,13 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                     const bool in = row < k && col < k && (Backward ? col >= row : col <= row);
                     val[mi * 8 + ks] = in ? mat[row + size_t(col) * k] : 0.0;
                 }
-            prefetch_next();
-            publish_tail();
-            await_arrivals(task.Super, task.Need);
+            if (t == 96) { // (warp 3: warp 0 is busy with the tickets)
+                for (uint32_t spin = 0; PeekAcquire(a.Arrived + task.Super) < task.Need; ++spin) {
+                    if (GiveUp(spin, a.Fail)) break;
+                    __nanosleep(20);
+                }
+            }
+            __syncthreads();
             {
                 const double2 *src = reinterpret_cast<const double2 *>(a.Acc + (size_t(task.VecOffset) + t) * kWide);
                 double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
@@ -588,20 +602,40 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                     const uint32_t row = task.Row0 + 8 * mi + fr, col = 32 * q + 4 * ks + fk;
                     val[mi * 8 + ks] = (row < task.Limit && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
                 }
-            uint32_t link = 0;
             if (t < kSolveRows) s_node[t] = task.Row0 + t < task.Limit ? a.Rows[task.RowsBase + (task.Row0 + t) / 3] : 0;
-            if (t < task.LinkCount) link = a.Links[task.LinkBegin + t];
-            prefetch_next();
-            publish_tail();
+            if (q == 3) {
+                owed = lane < task.LinkCount;
+                if (owed) owed_target = a.Links[task.LinkBegin + lane];
+            }
             {
+                // out_S[t][0..8): four 16-byte pairs, all requested before any is examined.
                 const double *src = a.Out + (size_t(task.VecOffset) + t) * kWide;
+                unsigned long long x[kWide];
+#pragma unroll
+                for (int j = 0; j < kWide / 2; ++j) x[2 * j] = x[2 * j + 1] = 0;
+                if (t < k) {
+#pragma unroll
+                    for (int j = 0; j < kWide / 2; ++j) LoadL2x2(src + 2 * j, x[2 * j], x[2 * j + 1]);
+                    for (uint32_t spin = 0;; ++spin) {
+                        bool missing = false;
+#pragma unroll
+                        for (int j = 0; j < kWide / 2; ++j)
+                            if (x[2 * j] == kUnsolved || x[2 * j + 1] == kUnsolved) {
+                                missing = true;
+                                LoadL2x2(src + 2 * j, x[2 * j], x[2 * j + 1]);
+                            }
+                        if (!missing) break;
+                        if (GiveUp(spin, a.Fail)) {
+#pragma unroll
+                            for (int j = 0; j < kWide; ++j) x[j] = 0;
+                            break;
+                        }
+                        __nanosleep(20);
+                    }
+                }
                 double *dst = vec + t * kWide;
 #pragma unroll
-                for (int j = 0; j < kWide / 2; ++j) {
-                    double x = 0, y = 0;
-                    if (t < k) AwaitSolved2(src + 2 * j, a.Fail, x, y);
-                    dst[2 * j] = x, dst[2 * j + 1] = y;
-                }
+                for (int j = 0; j < kWide; ++j) dst[j] = __longlong_as_double((long long)x[j]);
             }
             __syncthreads();
             double c[4][2]{};
@@ -613,7 +647,6 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                 const uint32_t idx = t + 128 * h, lr = idx / kWide, row = task.Row0 + lr;
                 if (row < task.Limit) atomicAdd(a.Acc + (size_t(3) * s_node[lr] + row % 3) * kWide + idx % kWide, -reduced(idx));
             }
-            tail_any = true, tail_mine = t < task.LinkCount, tail_target = link;
         } else {
             // acc_S[k x 8] -= P_slab^T [k x 32] out[slab rows x 8]: warp q owns output columns 32q .. 32q+31 of the supernode.
             const double *pt = a.Panel + task.Base;
@@ -627,8 +660,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             uint32_t node = 0;
             const uint32_t vr = t >> 2, row = task.Row0 + vr;
             if (row < task.Limit) node = a.Rows[task.RowsBase + row / 3];
-            prefetch_next();
-            publish_tail();
+            if (q == 3) owed = lane == 0, owed_target = task.Super;
             {
                 double x = 0, y = 0;
                 if (row < task.Limit) AwaitSolved2(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3), a.Fail, x, y);
@@ -651,7 +683,6 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                     atomicAdd(dst + 1, -c[mi][1]);
                 }
             }
-            tail_any = true, tail_mine = t == 0, tail_target = task.Super;
         }
     }
 }

@@ -162,33 +162,60 @@ __global__ void __launch_bounds__(128) TallGemmNarrowKernel(const double *__rest
 }
 
 // partial[split][a_pad x 8] of X[:, :a]^T Y[:, :c (<= 8)]: CTA = 32 columns of X x one row range; its 4 warps take
-// alternate 4-row steps and are reduced in shared memory.
-// The row range is split so that (column groups x splits) fills the SMs several times over even when X is narrow.
-constexpr uint32_t kGramMinSplits = 64, kGramMaxSplits = 512;
-__global__ void __launch_bounds__(128) GramNarrowPartialKernel(const double *__restrict__ X, size_t n, uint32_t a, const double *__restrict__ Y, uint32_t c, double *__restrict__ partial, uint32_t a_pad, uint32_t splits) {
+// alternate 32-row steps and are reduced in shared memory. HBM-bound (X is read once: 8 n a bytes).
+//   * The sum over rows does not care in which order the tensor core sees them, so a thread's fragment elements are PAIRS of
+//     consecutive rows (rows 2 fk, 2 fk + 1 of each 8-row group feed DMMA steps 2g and 2g + 1): every load is 16 bytes and a
+//     quarter-warp covers 64 contiguous bytes of a column, half the load instructions of the one-row-per-step layout.
+//   * The grid is ONE wave: (column groups x splits) <= the CTAs resident at once (4 per SM by registers). The first version
+//     launched 64..512 splits whatever the width; at 320 columns that was 640 CTAs for 592 slots, i.e. a second, almost
+//     empty wave, and the kernel ran at 0.28 of HBM peak (profiles/r02_solve.md).
+constexpr uint32_t kGramCtasPerSm = 4;
+__global__ void __launch_bounds__(128, kGramCtasPerSm) GramNarrowPartialKernel(const double *__restrict__ X, size_t n, uint32_t a, const double *__restrict__ Y, uint32_t c, double *__restrict__ partial, uint32_t a_pad, uint32_t splits) {
     __shared__ double part[4 * 32 * kNarrow];
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, fr = lane >> 2, fk = lane & 3;
     const uint32_t col0 = blockIdx.x * 32, split = blockIdx.y;
     size_t chunk = (n + splits - 1) / splits;
-    chunk = (chunk + 127) & ~size_t(127); // whole CTA iterations (4 warps x 8 steps x 4 rows)
+    chunk = (chunk + 127) & ~size_t(127); // whole CTA iterations (4 warps x 4 groups of 8 rows)
     const size_t begin = split * chunk, end = min(n, begin + chunk);
+    const bool even = (n & 1) == 0; // 16-byte loads need every column to start 16-byte aligned
     double acc[4][2]{};
     for (size_t r0 = begin + 32 * w; r0 < end; r0 += 128) {
-        double val[32], b[8];
+        double2 val[16], b[4];
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            const size_t r = r0 + 4 * ks + fk;
+        for (int g = 0; g < 4; ++g) {
+            const size_t r = r0 + 8 * g + 2 * fk;
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
                 const uint32_t col = col0 + 8 * mi + fr;
-                val[ks * 4 + mi] = (r < end && col < a) ? X[r + size_t(col) * n] : 0.0;
+                const double *src = X + r + size_t(col) * n;
+                double2 v = make_double2(0.0, 0.0);
+                if (col < a) {
+                    if (even && r + 1 < end) v = *reinterpret_cast<const double2 *>(src);
+                    else {
+                        if (r < end) v.x = src[0];
+                        if (r + 1 < end) v.y = src[1];
+                    }
+                }
+                val[g * 4 + mi] = v;
             }
-            b[ks] = (r < end && fr < c) ? Y[r + size_t(fr) * n] : 0.0;
+            double2 y = make_double2(0.0, 0.0);
+            if (fr < c) {
+                const double *src = Y + r + size_t(fr) * n;
+                if (even && r + 1 < end) y = *reinterpret_cast<const double2 *>(src);
+                else {
+                    if (r < end) y.x = src[0];
+                    if (r + 1 < end) y.y = src[1];
+                }
+            }
+            b[g] = y;
         }
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
+        for (int g = 0; g < 4; ++g)
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi) Dmma(acc[mi][0], acc[mi][1], val[ks * 4 + mi], b[ks]);
+            for (int mi = 0; mi < 4; ++mi) {
+                Dmma(acc[mi][0], acc[mi][1], val[g * 4 + mi].x, b[g].x);
+                Dmma(acc[mi][0], acc[mi][1], val[g * 4 + mi].y, b[g].y);
+            }
     }
 #pragma unroll
     for (int mi = 0; mi < 4; ++mi) {
@@ -243,7 +270,13 @@ void Gram(DenseWorkspace &ws, const double *X, size_t n, uint32_t a, const doubl
     if (a == 0 || c == 0) return;
     const uint32_t a_pad = (a + 31) & ~31u;
     const uint32_t groups = a_pad / 32;
-    const uint32_t splits = std::min(kGramMaxSplits, std::max(kGramMinSplits, (6 * 148 + groups - 1) / groups));
+    static const uint32_t resident = [] {
+        int device = 0, sms = 148;
+        if (cudaGetDevice(&device) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        return uint32_t(sms) * kGramCtasPerSm;
+    }();
+    // one wave of CTAs, each with at least one iteration of 128 rows
+    const uint32_t splits = uint32_t(std::max<size_t>(1, std::min<size_t>(resident / groups, (n + 127) / 128)));
     ws.GramPartial.Reserve(size_t(splits) * a_pad * kNarrow);
     for (uint32_t c0 = 0; c0 < c; c0 += kNarrow) {
         const uint32_t cw = c - c0 < uint32_t(kNarrow) ? c - c0 : uint32_t(kNarrow);

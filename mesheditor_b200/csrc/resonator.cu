@@ -102,6 +102,48 @@ __device__ __forceinline__ void MakePowers(const float2 (&cre)[4], const float2 
     }
 }
 
+// The state jumps by p = float(c^K), not by c^K: every jump is off by the same factor c^K / p = 1 + e, |e| <= 2^-24. Unlike the
+// rounding of the arithmetic (random, a square-root walk) this error has a fixed sign per mode and adds up LINEARLY in the
+// number of jumps: 3.6e-4 per second of audio per mode at K = 4 - invisible on a decaying strike, far outside the 1e-5 gate on
+// a bank that rings for seconds (measured on BASELINE.json configs[4]: 2.9e-5 of peak inside one 15-block segment). So e is
+// kept (FP64 quotient, rounded once) and every kDriftJumps jumps the state is multiplied by 1 + n e, which leaves n^2 e^2.
+constexpr uint32_t kDriftJumps = 128;
+template<int K>
+__device__ __forceinline__ void MakeDrift(const float2 (&cre)[4], const float2 (&cim)[4], const Powers<K> &p, float *drift) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double a = h ? cre[i].y : cre[i].x, b = h ? cim[i].y : cim[i].x;
+            double r = a, q = b;
+#pragma unroll
+            for (int j = 1; j < K; ++j) { // the recurrence of MakePowers
+                const double nr = r * a - q * b;
+                q = r * b + q * a;
+                r = nr;
+            }
+            const double pr = h ? p.Re[K - 1][i].y : p.Re[K - 1][i].x, pi = h ? p.Im[K - 1][i].y : p.Im[K - 1][i].x;
+            const double d = pr * pr + pi * pi;
+            // e = (c^K - p) / p
+            const double er = d > 0 ? ((r - pr) * pr + (q - pi) * pi) / d : 0.0, ei = d > 0 ? ((q - pi) * pr - (r - pr) * pi) / d : 0.0;
+            drift[(4 * i + 2 * h) * kBlockThreads] = float(er);
+            drift[(4 * i + 2 * h + 1) * kBlockThreads] = float(ei);
+        }
+    }
+}
+// w <- w (1 + n e): e as MakeDrift left it ([component][thread], this thread's column).
+__device__ __forceinline__ void ApplyDrift(Chunk &w, const float *drift, uint32_t jumps) {
+    const float n = float(jumps);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float erx = n * drift[(4 * i) * kBlockThreads], eix = n * drift[(4 * i + 1) * kBlockThreads];
+        const float ery = n * drift[(4 * i + 2) * kBlockThreads], eiy = n * drift[(4 * i + 3) * kBlockThreads];
+        const float rx = w.Re[i].x, ix = w.Im[i].x, ry = w.Re[i].y, iy = w.Im[i].y;
+        w.Re[i] = {rx + fmaf(rx, erx, -ix * eix), ry + fmaf(ry, ery, -iy * eiy)};
+        w.Im[i] = {ix + fmaf(rx, eix, ix * erx), iy + fmaf(ry, eiy, iy * ery)};
+    }
+}
+
 // K samples: y[j] = sum Im(c^(j+1) w) for j < K-1 straight off the state, then w <- c^K w and y[K-1] = sum Im w.
 // Each sample is left as a float2 of two partial sums (the row sum adds them). Instructions that share a state
 // operand are kept adjacent so the operand-reuse cache can serve it: FFMA2 with three fresh register pairs is
@@ -209,9 +251,13 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
 
     Powers<K> p;
     Chunk w;
-    float2 jump_re[4], jump_im[4]; // Walk: c^kTmBlock
+    float2 jump_re[4], jump_im[4];       // Walk: float(c^kTmBlock)
+    float2 jump_lo_re[4], jump_lo_im[4]; // Walk: c^kTmBlock - float(c^kTmBlock): the jump is applied as hi + lo (see MakeDrift for why)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) jump_re[i] = jump_im[i] = float2{0.f, 0.f};
+    for (int i = 0; i < 4; ++i) jump_re[i] = jump_im[i] = jump_lo_re[i] = jump_lo_im[i] = float2{0.f, 0.f};
+    // Sample loop: this thread's drift terms e (16 floats), [component][thread], behind the transpose tiles.
+    float *drift = transposed_storage + kWarpsPerBlock * kTile * kRowPad + threadIdx.x;
+    uint32_t jumps = 0; // K-sample jumps since the drift was last taken out
     float gain = 1.f, out_scale = 0.f, energy_scale = 0.f;
     uint32_t my_chunk = 0, obj_chunks = 0, obj_first_local = 0, obj_tuned = 0;
     bool in_tuned = false, cull = false, live = true, ringing = true;
@@ -233,7 +279,11 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                     rx = nrx, ry = nry;
                 }
                 jump_re[i] = {float(rx), float(ry)}, jump_im[i] = {float(ix), float(iy)};
+                jump_lo_re[i] = {float(rx - double(jump_re[i].x)), float(ry - double(jump_re[i].y))};
+                jump_lo_im[i] = {float(ix - double(jump_im[i].x)), float(iy - double(jump_im[i].y))};
             }
+        } else {
+            MakeDrift<K>(cre, cim, p, drift);
         }
         const uint32_t first = b.ObjFirstChunk[object];
         my_chunk = chunk - first;
@@ -353,18 +403,25 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                 }
                 __syncwarp();
                 if (rendered) {
-                    float2 sr[4], si[4];
                     if (step == kTmBlock) {
+                        // w <- (hi + lo) w, the small products first
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) sr[i] = jump_re[i], si[i] = jump_im[i];
+                        for (int i = 0; i < 4; ++i) {
+                            const float lrx = fmaf(-w.Im[i].x, jump_lo_im[i].x, w.Re[i].x * jump_lo_re[i].x), lry = fmaf(-w.Im[i].y, jump_lo_im[i].y, w.Re[i].y * jump_lo_re[i].y);
+                            const float lix = fmaf(w.Re[i].x, jump_lo_im[i].x, w.Im[i].x * jump_lo_re[i].x), liy = fmaf(w.Re[i].y, jump_lo_im[i].y, w.Im[i].y * jump_lo_re[i].y);
+                            const float2 re = {fmaf(-w.Im[i].x, jump_im[i].x, fmaf(w.Re[i].x, jump_re[i].x, lrx)), fmaf(-w.Im[i].y, jump_im[i].y, fmaf(w.Re[i].y, jump_re[i].y, lry))};
+                            w.Im[i] = {fmaf(w.Re[i].x, jump_im[i].x, fmaf(w.Im[i].x, jump_re[i].x, lix)), fmaf(w.Re[i].y, jump_im[i].y, fmaf(w.Im[i].y, jump_re[i].y, liy))};
+                            w.Re[i] = re;
+                        }
                     } else {
-                        PolarPower(b, mode0, step, sr, si); // ragged end of the span
-                    }
+                        float2 sr[4], si[4];
+                        PolarPower(b, mode0, step, sr, si); // ragged end of the span: a single step
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 re = {fmaf(-w.Im[i].x, si[i].x, w.Re[i].x * sr[i].x), fmaf(-w.Im[i].y, si[i].y, w.Re[i].y * sr[i].y)};
-                        w.Im[i] = {fmaf(w.Re[i].x, si[i].x, w.Im[i].x * sr[i].x), fmaf(w.Re[i].y, si[i].y, w.Im[i].y * sr[i].y)};
-                        w.Re[i] = re;
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 re = {fmaf(-w.Im[i].x, si[i].x, w.Re[i].x * sr[i].x), fmaf(-w.Im[i].y, si[i].y, w.Re[i].y * sr[i].y)};
+                            w.Im[i] = {fmaf(w.Re[i].x, si[i].x, w.Im[i].x * sr[i].x), fmaf(w.Re[i].y, si[i].y, w.Im[i].y * sr[i].y)};
+                            w.Re[i] = re;
+                        }
                     }
                 }
                 t += step;
@@ -382,10 +439,14 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                     while (true) {
                         uint32_t lim = nv;
                         if (inj_frame - tile_abs < nv) lim = inj_frame - tile_abs; // inj_frame >= tile_abs + s
-                        for (; s + K <= lim; s += K) StepK<K>(w, p, column + s * (kRowPad / 2));
+                        for (; s + K <= lim; s += K, ++jumps) StepK<K>(w, p, column + s * (kRowPad / 2));
                         for (; s < lim; ++s) Step1<K>(w, p, column + s * (kRowPad / 2));
                         if (s == nv) break;
                         while (inj_frame == tile_abs + s) inject();
+                    }
+                    if (K > 1 && (jumps >= kDriftJumps || tile + kTile >= block_end)) {
+                        ApplyDrift(w, drift, jumps);
+                        jumps = 0;
                     }
                 }
                 // A chunk sitting the block out adds nothing; a muted object (mix gain 0) evolves but its samples are discarded.
@@ -770,7 +831,7 @@ void LaunchSegmentScan(const BankView &bank, const RenderPlan &plan, float *seg_
 void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int steps, cudaStream_t stream, LaunchCounter &counter) {
     if (bank.NChunks == 0 || plan.Frames == 0) return;
     const dim3 grid((bank.NChunks + kBlockThreads - 1) / kBlockThreads, plan.NSegments);
-    constexpr size_t smem = sizeof(float) * kWarpsPerBlock * kTile * kRowPad;
+    constexpr size_t smem = sizeof(float) * (kWarpsPerBlock * kTile * kRowPad + 16 * kBlockThreads); // transpose tiles + the drift terms
     static const bool wide = [] {
         const char *occ = std::getenv("ME_RESONATOR_OCC");
         return occ && occ[0] == '1';

@@ -143,12 +143,21 @@ def main():
         ("platform_ceramic", "Pile.gltf", "Platform", lambda: gen._grid_box(0.3, 0.03, 0.3, 0.05), 30, 16000.0),
         ("bracket_steel", "Pile.gltf", "Bracket", lambda: gen.union_surface(gen.BracketBoxes, 0.005), 30, 60000.0),
         ("marble_glass", "Pile.gltf", "Marble", lambda: sphere(gen.SphereR), 30, 60000.0),
+        # the remaining solved models of the sample tree: the glass bar, the machined ground plate, the ceramic sphere
+        ("bar_glass", "test/surface/PressedRing/a_NoGrip.gltf", "Solved box", lambda: gen._grid_box(*gen.BarHalf, 0.02), 30, 16000.0),
+        ("ground_ceramic", "test/surface/SurfaceRadiates/a_Scrape.gltf", "Ground Machined", lambda: gen._grid_box(*gen.GroundHalf, 0.04), 30, 16000.0),
+        # (its document links the model to acoustic material 0, Ceramic, but the generator solved it as the scene's STEEL probe,
+        #  generate.py:1048 `probe=solved_modes_sphere(SphereR, STEEL, max_freq=60000.0)`: the solve's material is what the fixture keeps)
+        ("sphere_steel", "test/AccelerationNoise/a_SteelBead.gltf", "Solved sphere", lambda: sphere(gen.SphereR), 30, 60000.0, gen.STEEL),
     ]
-    for fixture, gltf, name, build, modes, max_freq in cases:
+    for fixture, gltf, name, build, modes, max_freq, *solved_as in cases:
         if name is None:
             g = json.load(open(os.path.join(REF, gltf)))
             name = g["extensions"]["KHR_audio_rigid_bodies"]["modalModels"][0]["name"]
         gold = golden_model(gltf, name)
+        if solved_as:
+            m = solved_as[0]
+            gold["material"] = np.array([m["density"], m["youngsModulus"], m["poissonRatio"], m["alpha"], m["beta"]], np.float64)
         verts, tris = build()
         surf, tri = obj_roundtrip(verts, tris)
         points, tets = tetrahedralize(surf, tri)
