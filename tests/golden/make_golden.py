@@ -146,7 +146,8 @@ def main():
         # the remaining solved models of the sample tree: the glass bar, the machined ground plate, the ceramic sphere
         ("bar_glass", "test/surface/PressedRing/a_NoGrip.gltf", "Solved box", lambda: gen._grid_box(*gen.BarHalf, 0.02), 30, 16000.0),
         ("ground_ceramic", "test/surface/SurfaceRadiates/a_Scrape.gltf", "Ground Machined", lambda: gen._grid_box(*gen.GroundHalf, 0.04), 30, 16000.0),
-        # (its document links the model to acoustic material 0, Ceramic, but the generator solved it as the scene's STEEL probe,
+        ("sphere_ceramic", "test/PatchGrowth/a_SphereLight.gltf", "Solved sphere", lambda: sphere(gen.SphereR), 30, 60000.0),
+        # the steel bead (its document links the model to acoustic material 0, Ceramic, but the generator solved it as the scene's STEEL probe,
         #  generate.py:1048 `probe=solved_modes_sphere(SphereR, STEEL, max_freq=60000.0)`: the solve's material is what the fixture keeps)
         ("sphere_steel", "test/AccelerationNoise/a_SteelBead.gltf", "Solved sphere", lambda: sphere(gen.SphereR), 30, 60000.0, gen.STEEL),
     ]
