@@ -91,9 +91,8 @@ def test_thin_bar_bending_matches_closed_forms():
     check_family(fem.get("bending_z", []), bending_theory(length, mat, thickness, 1), 0.05)
 
 
-def test_full_size_solve_properties():
-    """BASELINE.json configs[2] (55^3-cell block, 998,250 tets, P1, 200 modes) is beyond the CPU oracle; what can be checked
-    at that size without one, through independent device operators (me_fem_spmv, me_factor_solve):
+def solve_properties(points, tets, material, order, modes, dofs=None, cols=None, warm=True):
+    """What can be checked beyond the CPU oracle's reach, through independent device operators (me_fem_spmv, me_factor_solve):
     (1) the six rigid-body modes are there (|lambda| tiny), the model starts above them, eigenvalues ascend;
     (2) Rayleigh quotients x^T K x / x^T M x of the returned (float32) basis reproduce the eigenvalues;
     (3) shift-invert residual ||A^-1 (K - lambda M) x||_2 / ||x||_2 with A = K - sigma M: the quantity the iteration
@@ -106,26 +105,38 @@ def test_full_size_solve_properties():
     from mesheditor_b200 import Factor, FemSystem, mesh2modes, solver_config
     from mesheditor_b200 import workloads as wl
 
-    points, tets = wl.kuhn_block(55, 55, 55, (0.3, 0.3, 0.3))
     ex = wl.bench_excitations(points)
-    cfg = solver_config(num_modes=200, element_order=1, max_mode_freq=1e9)
-    r = mesh2modes(points, tets, "Steel", ex, config=cfg, keep_basis=True)
-    assert r.status == 0 and len(r.freqs) == 200 and r.profile["dofs"] == 526848
+    cfg = solver_config(num_modes=modes, element_order=order, max_mode_freq=1e9)
+    r = mesh2modes(points, tets, material, ex, config=cfg, keep_basis=True)
+    assert r.status == 0 and len(r.freqs) == modes
+    if dofs is not None:
+        assert r.profile["dofs"] == dofs
+    nev = modes + 15
     lam = r.eigenvalues
-    assert len(lam) == 215 and np.all(np.diff(lam) >= -1e-9 * lam[-1])
+    assert len(lam) == nev and np.all(np.diff(lam) >= -1e-9 * lam[-1])
     assert np.abs(lam[:6]).max() < 1e-6 * lam[6] and lam[6] > 0  # rigid-body modes
-    assert abs(float(r.freqs[0]) - math.sqrt(lam[6]) / (2 * math.pi)) < 1e-3 * float(r.freqs[0])  # steel's damping shifts f by ~1e-9
-    fem = FemSystem(points, tets, "Steel", 1)
+    assert abs(float(r.freqs[0]) - math.sqrt(lam[6]) / (2 * math.pi)) < 1e-3 * float(r.freqs[0])  # material damping shifts f by ~1e-9
+    fem = FemSystem(points, tets, material, order)
+    n = fem.info["dofs"]
+    # Node coordinates for the analytic rigid-body modes: the corners, and for the 10-node element the edge midpoints
+    # (straight-sided tets; edge slots in the order 01, 02, 03, 12, 13, 23 of mesh2modes.cpp:200).
+    node_xyz = np.asarray(points, np.float64)
+    if order == 2:
+        nodes = fem.element_nodes()
+        node_xyz = np.zeros((n // 3, 3))
+        node_xyz[:len(points)] = points
+        for slot, (a, b) in enumerate([(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]):
+            node_xyz[nodes[:, 4 + slot]] = 0.5 * (node_xyz[nodes[:, a]] + node_xyz[nodes[:, b]])
     sigma = -((2 * math.pi * 20.0) ** 2)
     factor = Factor(fem, sigma)
-    cols = [6, 7, 8, 20, 57, 111, 180, 214]
-    rigid = np.zeros((3 * len(points), 6))
+    cols = cols or [6, 7, 8, nev // 10 + 6, nev // 4, nev // 2, nev - 35, nev - 1]
+    Mx = {}
+    rigid = np.zeros((n, 6))
     for a in range(3):
         rigid[a::3, a] = 1.0
-        rigid[:, 3 + a] = np.cross(np.eye(3)[a], points - points.mean(axis=0)).reshape(-1)
+        rigid[:, 3 + a] = np.cross(np.eye(3)[a], node_xyz - node_xyz.mean(axis=0)).reshape(-1)
     m_rigid = np.stack([fem.spmv("M", rigid[:, i]) for i in range(6)], axis=1)
     gram = rigid.T @ m_rigid
-    Mx = {}
     for j in cols:
         x = r.basis[:, j].astype(np.float64)
         kx, mx = fem.spmv("K", x), fem.spmv("M", x)
@@ -139,8 +150,55 @@ def test_full_size_solve_properties():
         for j in cols:
             assert abs(float(r.basis[:, i].astype(np.float64) @ Mx[j]) - (1.0 if i == j else 0.0)) < 1e-5, (i, j)
     del factor
-    warm = mesh2modes(points, tets, "Steel", ex, config=cfg, seed_basis=r.basis)
-    assert warm.status == 0 and len(warm.freqs) == 200
-    assert np.abs(warm.eigenvalues[6:206] / lam[6:206] - 1).max() < 1e-4
-    assert abs(float(warm.freqs[0]) - float(r.freqs[0])) < 0.05
-    assert warm.profile["restarts"] <= 5  # an exact seed re-locks in a few block iterations
+    if warm:
+        again = mesh2modes(points, tets, material, ex, config=cfg, seed_basis=r.basis)
+        assert again.status == 0 and len(again.freqs) == modes
+        assert np.abs(again.eigenvalues[6:6 + modes] / lam[6:6 + modes] - 1).max() < 1e-4
+        assert abs(float(again.freqs[0]) - float(r.freqs[0])) < 0.05
+        assert again.profile["restarts"] <= 5  # an exact seed re-locks in a few block iterations
+    return r
+
+
+def test_full_size_solve_properties():
+    """BASELINE.json configs[2] (55^3-cell block, 998,250 tets, P1, 200 modes) is beyond the CPU oracle: see solve_properties."""
+    from mesheditor_b200 import workloads as wl
+
+    points, tets = wl.kuhn_block(55, 55, 55, (0.3, 0.3, 0.3))
+    solve_properties(points, tets, "Steel", 1, 200, dofs=526848, cols=[6, 7, 8, 20, 57, 111, 180, 214])
+
+
+@pytest.mark.parametrize("order", [1, 2], ids=["P1", "P2"])
+def test_torus_config_solve_properties(order):
+    """BASELINE.json configs[1]: the synthetic ~200k-tet torus (210,912 Kuhn tets over a swept 13 x 13 x 208 grid, R = 0.10 m,
+    r = 0.03 m), Ceramic, lowest 100 modes, in the order BASELINE names (P1) and in the reference's own element (P2: 10-node
+    tets, 0.9 M DOFs, the only order with reference parity - SURVEY.md F1, section 8d "both orders for C2")."""
+    from mesheditor_b200 import workloads as wl
+
+    points, tets = wl.torus_mesh()
+    assert len(tets) == 210_912
+    r = solve_properties(points, tets, "Ceramic", order, 100, warm=(order == 1))
+    # a body of revolution: the elastic spectrum comes in degenerate pairs (cos / sin of the azimuth) next to a few singlets
+    lam = r.eigenvalues[6:]
+    pairs = int(np.sum(np.abs(np.diff(lam)) < 1e-6 * lam[1:]))
+    assert pairs >= 30
+
+
+@pytest.mark.parametrize("order", [1, 2], ids=["P1", "P2"])
+def test_coarse_torus_matches_oracle(order):
+    """The same torus recipe coarsened until the CPU oracle follows (24 x 3 x 3 cells, 1,296 tets): eigenvalues 1e-6 relative,
+    frequencies, and the cluster structure of a body of revolution."""
+    from mesheditor_b200 import mesh2modes, solver_config
+    from mesheditor_b200 import workloads as wl
+
+    points, tets = wl.torus_mesh(24, 3)
+    mat = om.MATERIALS["Ceramic"]
+    ex = wl.bench_excitations(points)
+    ocfg = om.SolverConfig(num_modes=40, num_fem_modes=55, max_mode_freq=1e9)
+    ref = om.mesh2modes(points, tets, mat, ex, config=ocfg, order=order)
+    r = mesh2modes(points, tets, mat, ex, config=solver_config(num_modes=40, max_mode_freq=1e9, element_order=order))
+    assert r.status == 0
+    lam, ref_lam = r.eigenvalues, ref["eigenvalues"]
+    elastic = ref_lam > 1e-3 * ref_lam[-1]
+    assert np.abs(lam[elastic] / ref_lam[elastic] - 1).max() <= 1e-6
+    assert np.abs(lam[~elastic]).max() <= 1e-6 * ref_lam[-1]
+    np.testing.assert_allclose(r.freqs, ref["modes"].freqs, rtol=1e-6)
