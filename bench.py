@@ -72,12 +72,15 @@ class ClockSampler:
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=None):
         self.index, self.proc, self.rows = index, None, []
+        self.period_ms = int(os.environ.get("ME_CLOCK_SAMPLE_MS", period_ms or 50))
 
     def __enter__(self):
+        if self.period_ms <= 0:
+            return self
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", str(self.period_ms)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             time.sleep(0.3)
         except Exception:
             self.proc = None

@@ -327,8 +327,10 @@ __device__ __forceinline__ double AwaitSolved(const double *p, int *fail) {
 struct SweepArgs {
     const SweepTask *Tasks;
     uint32_t NumTasks;
-    const uint32_t *Links;            // forward panel slabs: the ancestors they update
+    const uint32_t *Links;            // forward panel slabs: the ancestors they update; backward (panel sweeps): the ancestors they read
+    const uint32_t *LinkNeed;         // backward panel sweeps: diagonal slabs of each such ancestor
     uint32_t *Ticket, *Arrived;
+    uint32_t *Solved;                 // panel sweeps: diagonal slabs of each supernode whose results are published
     const uint32_t *Rows;             // below-diagonal node lists of all supernodes
     const double *Diag, *Panel;       // Linv + L (forward) or Linv^T + LT (backward)
     double *Acc, *Out;
@@ -490,7 +492,11 @@ __device__ __forceinline__ void AwaitSolved2(const double *p, int *fail, double 
 //   * arrivals are published with ONE release-increment per link by a warp that issues it right after the CTA barrier
 //     that follows the contributions (st/red.release.gpu after __syncthreads is cumulative over the CTA's writes: the
 //     split-K semaphore pattern), and awaited with ld.acquire.gpu polls: no __threadfence anywhere;
-//   * the k x 8 solved entries a forward panel slab needs are requested all at once and only the missing ones re-polled;
+//   * results are published the same way: a diagonal slab stores its rows of `out`, and after the CTA barrier ONE
+//     release-increment of Solved[supernode] announces them; a panel slab waits with ONE polling thread per counter it
+//     depends on and then loads the solved entries once. (The first version made every solved entry self-validating - a NaN
+//     sentinel polled by all 128 threads of every waiting CTA, 8 KB per CTA per poll round: with the 740 resident CTAs
+//     mostly waiting on the upper levels' dependency chains, the polls alone loaded L2 with terabytes per second.)
 //   * tickets are claimed two tasks ahead, so neither the atomic nor the descriptor load is ever waited for.
 __device__ __forceinline__ void ArriveRelease(uint32_t *counter) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
@@ -522,9 +528,9 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
         if (lane < 8 && id1 < a.NumTasks) word1 = reinterpret_cast<const uint64_t *>(a.Tasks + id1)[lane];
         id2 = claim();
     }
-    // Arrivals owed by the previous panel slab, held by warp 3 (one link per lane).
-    bool owed = false;
-    uint32_t owed_target = 0;
+    // Counter increments owed by the previous task, held by warp 3 (one counter per lane): arrivals of a panel slab's
+    // contributions, or the publication of a diagonal slab's results.
+    uint32_t *owed = nullptr;
     // C[32 x 8] partial of this warp = A-fragments val[mi*8+ks] (rows 8mi.., k-steps of the warp's quarter) times vec.
     auto contract_quarter = [&](const double (&val)[32], double (&c)[4][2]) {
 #pragma unroll
@@ -542,8 +548,8 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
     auto reduced = [&](uint32_t idx) { return (part[idx] + part[256 + idx]) + (part[512 + idx] + part[768 + idx]); };
     for (;;) {
         __syncthreads(); // every contribution of the previous task has been issued; its shared operands are free
-        if (owed) ArriveRelease(a.Arrived + owed_target);
-        owed = false;
+        if (owed) ArriveRelease(owed);
+        owed = nullptr;
         if (q == 0) {
             if (lane < 8) reinterpret_cast<uint64_t *>(&s_task)[lane] = word1;
             if (lane == 0) s_id = id1;
@@ -593,6 +599,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                 const uint32_t idx = t + 128 * h, row = task.Row0 + idx / kWide;
                 if (row < k) StoreL2(a.Out + (size_t(task.VecOffset) + row) * kWide + idx % kWide, reduced(idx));
             }
+            if (t == 96) owed = a.Solved + task.Super;
         } else if constexpr (!Backward) {
             const double *p0 = a.Panel + task.Base;
 #pragma unroll
@@ -603,39 +610,19 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                     val[mi * 8 + ks] = (row < task.Limit && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
                 }
             if (t < kSolveRows) s_node[t] = task.Row0 + t < task.Limit ? a.Rows[task.RowsBase + (task.Row0 + t) / 3] : 0;
-            if (q == 3) {
-                owed = lane < task.LinkCount;
-                if (owed) owed_target = a.Links[task.LinkBegin + lane];
-            }
-            {
-                // out_S[t][0..8): four 16-byte pairs, all requested before any is examined.
-                const double *src = a.Out + (size_t(task.VecOffset) + t) * kWide;
-                unsigned long long x[kWide];
-#pragma unroll
-                for (int j = 0; j < kWide / 2; ++j) x[2 * j] = x[2 * j + 1] = 0;
-                if (t < k) {
-#pragma unroll
-                    for (int j = 0; j < kWide / 2; ++j) LoadL2x2(src + 2 * j, x[2 * j], x[2 * j + 1]);
-                    for (uint32_t spin = 0;; ++spin) {
-                        bool missing = false;
-#pragma unroll
-                        for (int j = 0; j < kWide / 2; ++j)
-                            if (x[2 * j] == kUnsolved || x[2 * j + 1] == kUnsolved) {
-                                missing = true;
-                                LoadL2x2(src + 2 * j, x[2 * j], x[2 * j + 1]);
-                            }
-                        if (!missing) break;
-                        if (GiveUp(spin, a.Fail)) {
-#pragma unroll
-                            for (int j = 0; j < kWide; ++j) x[j] = 0;
-                            break;
-                        }
-                        __nanosleep(20);
-                    }
+            if (q == 3 && lane < task.LinkCount) owed = a.Arrived + a.Links[task.LinkBegin + lane];
+            if (t == 96) { // out_S is complete once its diagonal slabs have all published
+                for (uint32_t spin = 0; PeekAcquire(a.Solved + task.Super) < task.Need; ++spin) {
+                    if (GiveUp(spin, a.Fail)) break;
+                    __nanosleep(40);
                 }
-                double *dst = vec + t * kWide;
+            }
+            __syncthreads();
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(a.Out + (size_t(task.VecOffset) + t) * kWide);
+                double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
 #pragma unroll
-                for (int j = 0; j < kWide; ++j) dst[j] = __longlong_as_double((long long)x[j]);
+                for (int j = 0; j < kWide / 2; ++j) dst[j] = t < k ? __ldcg(src + j) : make_double2(0.0, 0.0);
             }
             __syncthreads();
             double c[4][2]{};
@@ -660,11 +647,20 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             uint32_t node = 0;
             const uint32_t vr = t >> 2, row = task.Row0 + vr;
             if (row < task.Limit) node = a.Rows[task.RowsBase + row / 3];
-            if (q == 3) owed = lane == 0, owed_target = task.Super;
+            if (t == 96) owed = a.Arrived + task.Super;
+            if (q == 3 && lane < task.LinkCount) { // the ancestors owning the slab's rows: one polling lane each
+                const uint32_t *solved = a.Solved + a.Links[task.LinkBegin + lane];
+                const uint32_t need = a.LinkNeed[task.LinkBegin + lane];
+                for (uint32_t spin = 0; PeekAcquire(solved) < need; ++spin) {
+                    if (GiveUp(spin, a.Fail)) break;
+                    __nanosleep(40);
+                }
+            }
+            __syncthreads();
             {
-                double x = 0, y = 0;
-                if (row < task.Limit) AwaitSolved2(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3), a.Fail, x, y);
-                vec[vr * kWide + 2 * (t & 3)] = x, vec[vr * kWide + 2 * (t & 3) + 1] = y;
+                double2 x = make_double2(0.0, 0.0);
+                if (row < task.Limit) x = __ldcg(reinterpret_cast<const double2 *>(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3)));
+                vec[vr * kWide + 2 * (t & 3)] = x.x, vec[vr * kWide + 2 * (t & 3) + 1] = x.y;
             }
             __syncthreads();
             double c[4][2]{};
@@ -688,15 +684,13 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
 }
 
 // Panel of up to kWide right-hand sides, column-major n x width in natural DOF order -> acc[permuted DOF][kWide]
-// (missing columns are zero); `out` is marked unsolved.
-__global__ void WideBeginKernel(const double *__restrict__ b, size_t n, uint32_t width, const uint32_t *__restrict__ inv_perm, double *__restrict__ acc, double *__restrict__ out) {
+// (missing columns are zero).
+__global__ void WideBeginKernel(const double *__restrict__ b, size_t n, uint32_t width, const uint32_t *__restrict__ inv_perm, double *__restrict__ acc) {
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; // natural DOF
     if (i >= n) return;
     const size_t dst = (size_t(3) * inv_perm[i / 3] + i % 3) * kWide;
 #pragma unroll
     for (int w = 0; w < kWide; ++w) acc[dst + w] = uint32_t(w) < width ? b[i + size_t(w) * n] : 0.0;
-#pragma unroll
-    for (int w = 0; w < kWide; ++w) out[i * kWide + w] = __longlong_as_double((long long)kUnsolved);
 }
 __global__ void WidePermuteOutKernel(const double *__restrict__ work, size_t n, uint32_t width, const uint32_t *__restrict__ inv_perm, double *__restrict__ x) {
     const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -803,7 +797,9 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     Work.Reserve(fem.N);
     Work2.Reserve(fem.N);
     DFail.Reserve(1);
-    DCounters.Reserve(size_t(2) * Sym.NumSuper + 2);
+    DCounters.Reserve(size_t(4) * Sym.NumSuper + 2);
+    DBwdLinks.Upload(Sym.BwdLinks, s);
+    DBwdLinkNeed.Upload(Sym.BwdLinkNeed, s);
     {
         int device = 0, sms = 0, fwd = 0, bwd = 0;
         ME_CUDA(cudaGetDevice(&device));
@@ -884,13 +880,15 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
         Work.Reserve(size_t(n) * kWide);
         Work2.Reserve(size_t(n) * kWide);
     }
-    uint32_t *counters = DCounters.Ptr; // [0, ns) forward arrivals, [ns, 2 ns) backward arrivals, then the two ticket counters
+    // [0, ns) forward arrivals, [ns, 2 ns) backward arrivals, the two ticket counters, then (panel sweeps) the published
+    // diagonal slabs: [2 ns + 2, 3 ns + 2) forward, [3 ns + 2, 4 ns + 2) backward.
+    uint32_t *counters = DCounters.Ptr;
     // Forward: Work accumulates the right-hand side, Work2 receives y. Backward: Work2 accumulates, Work receives x.
-    const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, counters + 2 * size_t(ns), counters, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr, DFail.Ptr};
-    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), nullptr, counters + 2 * size_t(ns) + 1, counters + ns, DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
+    const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, nullptr, counters + 2 * size_t(ns), counters, counters + 2 * size_t(ns) + 2, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr, DFail.Ptr};
+    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), DBwdLinks.Ptr, DBwdLinkNeed.Ptr, counters + 2 * size_t(ns) + 1, counters + ns, counters + 3 * size_t(ns) + 2, DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
     auto single = [&](const double *bi, double *xi) {
         SweepBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(bi, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr, Work2.Ptr);
-        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(2) * ns + 2) * sizeof(uint32_t), s));
+        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
         SweepKernel<false><<<FwdGrid, kSweepThreads, 0, s>>>(fwd);
         MarkUnsolvedKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n);
         SweepKernel<true><<<BwdGrid, kSweepThreads, 0, s>>>(bwd);
@@ -908,13 +906,12 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
             continue;
         }
         const uint32_t w = std::min<uint32_t>(left, kWide);
-        WideBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, n, w, DInvPerm.Ptr, Work.Ptr, Work2.Ptr);
-        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(2) * ns + 2) * sizeof(uint32_t), s));
+        WideBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, n, w, DInvPerm.Ptr, Work.Ptr);
+        ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
         WideSweepKernel<false><<<WideFwdGrid, kSweepThreads, 0, s>>>(fwd);
-        MarkUnsolvedKernel<<<Blocks(size_t(n) * kWide, 256), 256, 0, s>>>(Work.Ptr, n * kWide);
         WideSweepKernel<true><<<WideBwdGrid, kSweepThreads, 0, s>>>(bwd);
         WidePermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n, w, DInvPerm.Ptr, x + size_t(rhs) * n);
-        Stats.KernelLaunches += 5;
+        Stats.KernelLaunches += 4;
         rhs += w;
     }
     SolvesSinceCheck += width;

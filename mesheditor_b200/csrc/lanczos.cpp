@@ -463,6 +463,9 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
     const uint32_t launches0 = Fem.KernelLaunches, f_launches0 = Factor.Stats.KernelLaunches;
     const uint32_t tcap = mcap + b;
 
+    const bool prof = std::getenv("ME_PROFILE") != nullptr;
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_enter = now();
     DeviceBuffer<double> Va, Vb, W, Wb, MW, H1, H2, Small;
     Va.Reserve(n * tcap), Vb.Reserve(n * tcap), W.Reserve(n * b), Wb.Reserve(n * b), MW.Reserve(n * b);
     H1.Reserve(size_t(tcap) * b), H2.Reserve(size_t(tcap) * b), Small.Reserve(std::max<size_t>(size_t(tcap) * tcap, 4 * b * b));
@@ -507,6 +510,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         return true;
     };
 
+    const double t_alloc = now();
     // Start block: Op applied to the reference's pseudo-random residual (SimpleRandom, seed 0 -> 1), b columns of it.
     {
         std::vector<double> r0(n * b);
@@ -522,9 +526,11 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
     if (!orthonormalize(W.Ptr, Wb.Ptr, col(V, 0))) Fail(ME_NOT_CONVERGED, "block Lanczos: the start block is rank deficient");
 
     // ME_PROFILE=1: synchronising section timers printed to stderr (diagnostics only; perturbs the overlap of host and device).
-    const bool prof = std::getenv("ME_PROFILE") != nullptr;
     double sec[5]{};
-    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    if (prof) {
+        cudaStreamSynchronize(s);
+        fprintf(stderr, "[block lanczos] setup: allocations %.3f s, start block %.3f s\n", t_alloc - t_enter, now() - t_alloc);
+    }
     double mark_t = now();
     auto mark = [&](int which) {
         if (!prof) return;
@@ -630,6 +636,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         m = k;
     }
     mark(4);
+    const double t_loop_end = now();
     if (prof) fprintf(stderr, "[block lanczos] op %.3f s, reorth %.3f s, cholqr %.3f s, ritz (host) %.3f s, restart+other %.3f s, %u panel ops, %u restarts\n", sec[0], sec[1], sec[2], sec[3], sec[4], OpCalls, iter);
     out.Restarts = iter + 1;
     out.OpApplications = Ops;
@@ -662,6 +669,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
     OpCalls = 0;
     out.RankLost = broke;
     out.KernelLaunches = (Fem.KernelLaunches - launches0) + (Factor.Stats.KernelLaunches - f_launches0) + Ws.Launches;
+    if (prof) fprintf(stderr, "[block lanczos] extraction + checks %.3f s\n", now() - t_loop_end);
     return out;
 }
 

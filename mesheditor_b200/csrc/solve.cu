@@ -367,6 +367,7 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
     if (cancelled()) return ME_CANCELLED;
 
     t0 = Seconds();
+    const bool trace = std::getenv("ME_PROFILE") != nullptr;
     const volatile int *cancel_flag = monitor ? &monitor->cancelled : nullptr;
     // A basis solved over a different mesh cannot seed this solve: it falls back to the cold path (mesh2modes.cpp:459-464).
     const bool use_subspace = seed_basis != nullptr && seed_rows == n && seed_cols >= nev;
@@ -401,6 +402,7 @@ MeStatus SolveImpl(const double *points, uint32_t n_points, const uint32_t *tets
         if (use_block) outcome = lanczos.ComputeBlock(nev, config.Tolerance, config.MaxRestarts, cancel_flag);
         if (!use_block || outcome.RankLost) outcome = lanczos.Compute(nev, ncv, config.Tolerance, config.MaxRestarts, cancel_flag);
         profile.iterate = Seconds() - t0;
+        if (trace) fprintf(stderr, "[solve] iterate %.3f s (analyse %.3f, factorize %.3f, assemble %.3f)\n", profile.iterate, profile.analyse, profile.factorize, profile.assemble);
         profile.op_solve = outcome.OpSolveMs * 1e-3;
         profile.op_applications = outcome.OpApplications;
         profile.restarts = outcome.Restarts;
