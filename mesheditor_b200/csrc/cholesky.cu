@@ -601,14 +601,19 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             }
             if (t == 96) owed = a.Solved + task.Super;
         } else if constexpr (!Backward) {
+            // A run of task.Count consecutive 32-row slabs of one panel: acc[rows] -= P_slab out_S, slab after slab. The run
+            // shares the wait for out_S, the k x 8 operand in shared memory, the ticket and the arrivals it owes.
             const double *p0 = a.Panel + task.Base;
+            auto load_slab = [&](uint32_t row0) {
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t row = task.Row0 + 8 * mi + fr, col = 32 * q + 4 * ks + fk;
-                    val[mi * 8 + ks] = (row < task.Limit && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
-                }
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t row = row0 + 8 * mi + fr, col = 32 * q + 4 * ks + fk;
+                        val[mi * 8 + ks] = (row < task.Limit && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
+                    }
+            };
+            load_slab(task.Row0);
             if (t < kSolveRows) s_node[t] = task.Row0 + t < task.Limit ? a.Rows[task.RowsBase + (task.Row0 + t) / 3] : 0;
             if (q == 3 && lane < task.LinkCount) owed = a.Arrived + a.Links[task.LinkBegin + lane];
             if (t == 96) { // out_S is complete once its diagonal slabs have all published
@@ -624,51 +629,73 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
 #pragma unroll
                 for (int j = 0; j < kWide / 2; ++j) dst[j] = t < k ? __ldcg(src + j) : make_double2(0.0, 0.0);
             }
-            __syncthreads();
-            double c[4][2]{};
-            contract_quarter(val, c);
-            store_partials(c);
-            __syncthreads();
+            for (uint32_t slab = 0;; ++slab) {
+                const uint32_t row0 = task.Row0 + slab * kSolveRows;
+                __syncthreads(); // vec (first slab) / s_node and the previous slab's partials are settled
+                double c[4][2]{};
+                contract_quarter(val, c);
+                store_partials(c);
+                const bool more = slab + 1 < task.Count;
+                if (more) load_slab(row0 + kSolveRows); // in flight while this slab is reduced and scattered
+                __syncthreads();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t idx = t + 128 * h, lr = idx / kWide, row = task.Row0 + lr;
-                if (row < task.Limit) atomicAdd(a.Acc + (size_t(3) * s_node[lr] + row % 3) * kWide + idx % kWide, -reduced(idx));
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t idx = t + 128 * h, lr = idx / kWide, row = row0 + lr;
+                    if (row < task.Limit) atomicAdd(a.Acc + (size_t(3) * s_node[lr] + row % 3) * kWide + idx % kWide, -reduced(idx));
+                }
+                if (!more) break;
+                __syncthreads(); // every thread has read s_node / the partials of this slab
+                if (t < kSolveRows) s_node[t] = row0 + kSolveRows + t < task.Limit ? a.Rows[task.RowsBase + (row0 + kSolveRows + t) / 3] : 0;
             }
         } else {
-            // acc_S[k x 8] -= P_slab^T [k x 32] out[slab rows x 8]: warp q owns output columns 32q .. 32q+31 of the supernode.
+            // A run of task.Count consecutive 32-row slabs: acc_S[k x 8] -= sum over the slabs of P_slab^T [k x 32] out[slab rows
+            // x 8]. Warp q owns output columns 32q .. 32q+31 of the supernode and keeps their sums in its DMMA accumulators
+            // across the run: ONE set of FP64 atomics per run instead of one per slab (k x 8 atomics each, all slabs of a
+            // supernode onto the same k x 8 addresses: they were what the backward sweep waited for).
             const double *pt = a.Panel + task.Base;
+            auto load_slab = [&](uint32_t row0) {
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t col = 32 * q + 8 * mi + fr, row = row0 + 4 * ks + fk;
+                        val[mi * 8 + ks] = (row < task.Limit && col < k) ? pt[size_t(row) * k + col] : 0.0;
+                    }
+            };
+            load_slab(task.Row0);
+            if (t == 96) owed = a.Arrived + task.Super;
+            if (q == 3) { // the ancestors owning the run's rows: polled by the lanes of one warp
+                for (uint32_t i = lane; i < task.LinkCount; i += 32) {
+                    const uint32_t *solved = a.Solved + a.Links[task.LinkBegin + i];
+                    const uint32_t need = a.LinkNeed[task.LinkBegin + i];
+                    for (uint32_t spin = 0; PeekAcquire(solved) < need; ++spin) {
+                        if (GiveUp(spin, a.Fail)) break;
+                        __nanosleep(40);
+                    }
+                }
+            }
+            const uint32_t vr = t >> 2;
+            // this thread's row of the slab -> the node owning it (fetched one slab ahead: the solved entries hang off it)
+            auto node_of = [&](uint32_t row) { return row < task.Limit ? a.Rows[task.RowsBase + row / 3] : 0u; };
+            uint32_t node = node_of(task.Row0 + vr);
+            double c[4][2]{};
+            for (uint32_t slab = 0; slab < task.Count; ++slab) {
+                const uint32_t row0 = task.Row0 + slab * kSolveRows, row = row0 + vr;
+                __syncthreads(); // the links are solved (first slab); the previous slab's operand has been consumed
+                {
+                    double2 x = make_double2(0.0, 0.0);
+                    if (row < task.Limit) x = __ldcg(reinterpret_cast<const double2 *>(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3)));
+                    if (slab + 1 < task.Count) node = node_of(row + kSolveRows);
+                    vec[vr * kWide + 2 * (t & 3)] = x.x, vec[vr * kWide + 2 * (t & 3) + 1] = x.y;
+                }
+                __syncthreads();
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t col = 32 * q + 8 * mi + fr, row = task.Row0 + 4 * ks + fk;
-                    val[mi * 8 + ks] = (row < task.Limit && col < k) ? pt[size_t(row) * k + col] : 0.0;
-                }
-            uint32_t node = 0;
-            const uint32_t vr = t >> 2, row = task.Row0 + vr;
-            if (row < task.Limit) node = a.Rows[task.RowsBase + row / 3];
-            if (t == 96) owed = a.Arrived + task.Super;
-            if (q == 3 && lane < task.LinkCount) { // the ancestors owning the slab's rows: one polling lane each
-                const uint32_t *solved = a.Solved + a.Links[task.LinkBegin + lane];
-                const uint32_t need = a.LinkNeed[task.LinkBegin + lane];
-                for (uint32_t spin = 0; PeekAcquire(solved) < need; ++spin) {
-                    if (GiveUp(spin, a.Fail)) break;
-                    __nanosleep(40);
-                }
-            }
-            __syncthreads();
-            {
-                double2 x = make_double2(0.0, 0.0);
-                if (row < task.Limit) x = __ldcg(reinterpret_cast<const double2 *>(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3)));
-                vec[vr * kWide + 2 * (t & 3)] = x.x, vec[vr * kWide + 2 * (t & 3) + 1] = x.y;
-            }
-            __syncthreads();
-            double c[4][2]{};
+                    const double b = vec[(4 * ks + fk) * kWide + fr];
 #pragma unroll
-            for (int ks = 0; ks < 8; ++ks) {
-                const double b = vec[(4 * ks + fk) * kWide + fr];
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b);
+                    for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b);
+                }
+                if (slab + 1 < task.Count) load_slab(row0 + kSolveRows);
             }
 #pragma unroll
             for (int mi = 0; mi < 4; ++mi) {
@@ -798,8 +825,11 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     Work2.Reserve(fem.N);
     DFail.Reserve(1);
     DCounters.Reserve(size_t(4) * Sym.NumSuper + 2);
-    DBwdLinks.Upload(Sym.BwdLinks, s);
-    DBwdLinkNeed.Upload(Sym.BwdLinkNeed, s);
+    DWideFwdTasks.Upload(Sym.WideFwdTasks, s);
+    DWideBwdTasks.Upload(Sym.WideBwdTasks, s);
+    DWideFwdLinks.Upload(Sym.WideFwdLinks, s);
+    DWideBwdLinks.Upload(Sym.WideBwdLinks, s);
+    DWideBwdLinkNeed.Upload(Sym.WideBwdLinkNeed, s);
     {
         int device = 0, sms = 0, fwd = 0, bwd = 0;
         ME_CUDA(cudaGetDevice(&device));
@@ -885,7 +915,10 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     uint32_t *counters = DCounters.Ptr;
     // Forward: Work accumulates the right-hand side, Work2 receives y. Backward: Work2 accumulates, Work receives x.
     const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, nullptr, counters + 2 * size_t(ns), counters, counters + 2 * size_t(ns) + 2, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr, DFail.Ptr};
-    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), DBwdLinks.Ptr, DBwdLinkNeed.Ptr, counters + 2 * size_t(ns) + 1, counters + ns, counters + 3 * size_t(ns) + 2, DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
+    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), nullptr, nullptr, counters + 2 * size_t(ns) + 1, counters + ns, counters + 3 * size_t(ns) + 2, DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
+    SweepArgs wide_fwd = fwd, wide_bwd = bwd;
+    wide_fwd.Tasks = DWideFwdTasks.Ptr, wide_fwd.NumTasks = uint32_t(Sym.WideFwdTasks.size()), wide_fwd.Links = DWideFwdLinks.Ptr;
+    wide_bwd.Tasks = DWideBwdTasks.Ptr, wide_bwd.NumTasks = uint32_t(Sym.WideBwdTasks.size()), wide_bwd.Links = DWideBwdLinks.Ptr, wide_bwd.LinkNeed = DWideBwdLinkNeed.Ptr;
     auto single = [&](const double *bi, double *xi) {
         SweepBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(bi, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr, Work2.Ptr);
         ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
@@ -908,8 +941,8 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
         const uint32_t w = std::min<uint32_t>(left, kWide);
         WideBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, n, w, DInvPerm.Ptr, Work.Ptr);
         ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
-        WideSweepKernel<false><<<WideFwdGrid, kSweepThreads, 0, s>>>(fwd);
-        WideSweepKernel<true><<<WideBwdGrid, kSweepThreads, 0, s>>>(bwd);
+        WideSweepKernel<false><<<WideFwdGrid, kSweepThreads, 0, s>>>(wide_fwd);
+        WideSweepKernel<true><<<WideBwdGrid, kSweepThreads, 0, s>>>(wide_bwd);
         WidePermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n, w, DInvPerm.Ptr, x + size_t(rhs) * n);
         Stats.KernelLaunches += 4;
         rhs += w;

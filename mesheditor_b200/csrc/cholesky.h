@@ -48,7 +48,9 @@ private:
     DeviceBuffer<uint64_t> DRowPtr, DPanelOffset, DInvOffset;
     DeviceBuffer<PanelTile> DPanelTiles;
     DeviceBuffer<SweepTask> DFwdTasks, DBwdTasks;
-    DeviceBuffer<uint32_t> DFwdLinks, DBwdLinks, DBwdLinkNeed, DCounters;
+    DeviceBuffer<uint32_t> DFwdLinks, DCounters;
+    DeviceBuffer<SweepTask> DWideFwdTasks, DWideBwdTasks; // panel sweeps: runs of slabs (Symbolic::WideFwdTasks)
+    DeviceBuffer<uint32_t> DWideFwdLinks, DWideBwdLinks, DWideBwdLinkNeed;
     uint32_t FwdGrid{0}, BwdGrid{0}, WideFwdGrid{0}, WideBwdGrid{0};
     DeviceBuffer<UpdateTile> DUpdateTiles;
     DeviceBuffer<double> L, Linv, LinvT, LT, Work, Work2;

@@ -1,0 +1,193 @@
+// Dense symmetric eigensolver of the projected (Rayleigh-Ritz) problems, on the host: Householder tridiagonalisation and
+// implicit QL with accumulated vectors (the job Spectra hands to its TridiagEigen, lib/spectra/include/Spectra/LinAlg/
+// TridiagEigen.h, after HermEigsBase::retrieve_ritzpair). a: n x n row-major symmetric in, eigenvectors out (a[r * n + c] =
+// component r of vector c); d: eigenvalues, in the order the QL iteration leaves them.
+//
+// It sits on the critical path between two restarts of the block Lanczos iteration (m = 320 for the 1M-tet solve: 22 ms a
+// call, seven calls a solve, while the GPU idles). Two thirds of it is the accumulation of the QL rotations into the
+// eigenvector matrix, and the rotations themselves depend only on the tridiagonal entries: the QL iteration is run on d and
+// e alone, recording every rotation, and the whole history is then applied to the eigenvectors by a few threads, each on its
+// own column range, with a single fork and join. The arithmetic of each entry is the sequential algorithm's, operation for
+// operation (only disjoint ranges are handed out), so the result does not depend on the thread count.
+#include "lanczos.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace me {
+namespace {
+
+// [begin, end) of worker w's share of `count` items.
+inline void Share(uint32_t count, uint32_t w, uint32_t workers, uint32_t &begin, uint32_t &end) {
+    begin = uint32_t(uint64_t(count) * w / workers);
+    end = uint32_t(uint64_t(count) * (w + 1) / workers);
+}
+
+uint32_t TeamSize(uint32_t n) {
+    if (n < 96) return 1; // a sweep over a small matrix is shorter than a barrier
+    static const uint32_t configured = [] {
+        if (const char *env = std::getenv("ME_HOST_THREADS")) return uint32_t(std::max(1, std::atoi(env)));
+        return std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    }();
+    return configured;
+}
+} // namespace
+
+bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) {
+    d.assign(n, 0.0);
+    if (n == 0) return true;
+    std::vector<double> e(n, 0.0), scratch(n, 0.0);
+    auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
+    // Householder reduction to tridiagonal form, accumulating the transformation.
+    for (uint32_t i = n - 1; i >= 1; --i) {
+        const uint32_t l = i - 1;
+        double h = 0, scale = 0;
+        if (l > 0) {
+            for (uint32_t k = 0; k <= l; ++k) scale += std::abs(A(i, k));
+            if (scale == 0.0) e[i] = A(i, l);
+            else {
+                for (uint32_t k = 0; k <= l; ++k) {
+                    A(i, k) /= scale;
+                    h += A(i, k) * A(i, k);
+                }
+                double f = A(i, l);
+                double g = f >= 0 ? -std::sqrt(h) : std::sqrt(h);
+                e[i] = scale * g;
+                h -= f * g;
+                A(i, l) = f - g;
+                f = 0;
+                // e = A u / h with A symmetric and only its lower triangle stored: both sweeps run along contiguous rows.
+                for (uint32_t j = 0; j <= l; ++j) e[j] = 0;
+                const double *u = &a[size_t(i) * n];
+                for (uint32_t j = 0; j <= l; ++j) {
+                    const double *row = &a[size_t(j) * n];
+                    const double uj = u[j];
+                    double dot = 0;
+                    for (uint32_t k = 0; k < j; ++k) {
+                        dot += row[k] * u[k];
+                        e[k] += row[k] * uj;
+                    }
+                    e[j] += dot + row[j] * uj;
+                }
+                for (uint32_t j = 0; j <= l; ++j) {
+                    A(j, i) = A(i, j) / h;
+                    e[j] /= h;
+                    f += e[j] * A(i, j);
+                }
+                const double hh = f / (h + h);
+                for (uint32_t j = 0; j <= l; ++j) e[j] -= hh * A(i, j);
+                {
+                    const double *ui = &a[size_t(i) * n];
+                    for (uint32_t j = 0; j <= l; ++j) {
+                        const double fj = ui[j], gj = e[j];
+                        double *row = &a[size_t(j) * n];
+                        for (uint32_t k = 0; k <= j; ++k) row[k] -= fj * e[k] + gj * ui[k];
+                    }
+                }
+            }
+        } else e[i] = A(i, l);
+        d[i] = h;
+    }
+    d[0] = 0;
+    e[0] = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (d[i] != 0.0 && i > 0) {
+            // g = row_i * Q[0..i, 0..i), then Q[0..i, 0..i) -= Q[0..i, i] * g: contiguous row sweeps, columns shared out.
+            std::vector<double> &g = scratch;
+            std::fill(g.begin(), g.begin() + i, 0.0);
+            for (uint32_t k = 0; k < i; ++k) {
+                const double aik = A(i, k);
+                const double *row = &a[size_t(k) * n];
+                for (uint32_t j = 0; j < i; ++j) g[j] += aik * row[j];
+            }
+            for (uint32_t k = 0; k < i; ++k) {
+                const double aki = A(k, i);
+                double *row = &a[size_t(k) * n];
+                for (uint32_t j = 0; j < i; ++j) row[j] -= g[j] * aki;
+            }
+        }
+        d[i] = A(i, i);
+        A(i, i) = 1;
+        for (uint32_t j = 0; j < i; ++j) A(j, i) = A(i, j) = 0;
+    }
+    // Implicit QL on the tridiagonal matrix. The rotations mix two eigenvector columns at a time: work on the transpose
+    // so that they are contiguous rows (~3 n^3 flops). They depend only on d and e: recorded here, applied below.
+    for (uint32_t r = 0; r < n; ++r)
+        for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
+    for (uint32_t i = 1; i < n; ++i) e[i - 1] = e[i];
+    e[n - 1] = 0;
+    const double eps = std::numeric_limits<double>::epsilon();
+    struct Rotation {
+        double C, S;
+        uint32_t Row; // mixes rows Row and Row + 1 of the transposed eigenvector matrix
+    };
+    std::vector<Rotation> rotations;
+    rotations.reserve(size_t(n) * n);
+    for (uint32_t l = 0; l < n; ++l) {
+        uint32_t iter = 0, m;
+        do {
+            for (m = l; m + 1 < n; ++m) {
+                const double dd = std::abs(d[m]) + std::abs(d[m + 1]);
+                if (std::abs(e[m]) <= eps * dd) break;
+            }
+            if (m != l) {
+                if (++iter > 200) return false;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = std::hypot(g, 1.0);
+                g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
+                double s = 1, c = 1, p = 0;
+                int64_t i;
+                for (i = int64_t(m) - 1; i >= int64_t(l); --i) {
+                    double f = s * e[i];
+                    const double b = c * e[i];
+                    e[i + 1] = r = std::hypot(f, g);
+                    if (r == 0.0) {
+                        d[i + 1] -= p;
+                        e[m] = 0;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    d[i + 1] = g + (p = s * r);
+                    g = c * r - b;
+                    rotations.push_back({c, s, uint32_t(i)});
+                }
+                if (r == 0.0 && i >= int64_t(l)) continue;
+                d[l] -= p;
+                e[l] = g;
+                e[m] = 0;
+            }
+        } while (m != l);
+    }
+    // The rotation history, applied in order to every worker's own columns.
+    const auto apply = [&](uint32_t w, uint32_t workers) {
+        uint32_t k0, k1;
+        Share(n, w, workers, k0, k1);
+        if (k0 == k1) return;
+        for (const Rotation &q : rotations) {
+            double *zi = &a[size_t(q.Row) * n], *zi1 = zi + n;
+            for (uint32_t k = k0; k < k1; ++k) {
+                const double fk = zi1[k];
+                zi1[k] = q.S * zi[k] + q.C * fk;
+                zi[k] = q.C * zi[k] - q.S * fk;
+            }
+        }
+    };
+    const uint32_t workers = TeamSize(n);
+    std::vector<std::thread> threads;
+    for (uint32_t w = 1; w < workers; ++w) threads.emplace_back(apply, w, workers);
+    apply(0, workers);
+    for (auto &t : threads) t.join();
+    for (uint32_t r = 0; r < n; ++r)
+        for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
+    return true;
+}
+
+} // namespace me

@@ -19,134 +19,6 @@
 
 namespace me {
 
-bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) {
-    d.assign(n, 0.0);
-    if (n == 0) return true;
-    std::vector<double> e(n, 0.0), scratch(n, 0.0);
-    auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
-    // Householder reduction to tridiagonal form, accumulating the transformation.
-    for (uint32_t i = n - 1; i >= 1; --i) {
-        const uint32_t l = i - 1;
-        double h = 0, scale = 0;
-        if (l > 0) {
-            for (uint32_t k = 0; k <= l; ++k) scale += std::abs(A(i, k));
-            if (scale == 0.0) e[i] = A(i, l);
-            else {
-                for (uint32_t k = 0; k <= l; ++k) {
-                    A(i, k) /= scale;
-                    h += A(i, k) * A(i, k);
-                }
-                double f = A(i, l);
-                double g = f >= 0 ? -std::sqrt(h) : std::sqrt(h);
-                e[i] = scale * g;
-                h -= f * g;
-                A(i, l) = f - g;
-                f = 0;
-                // e = A u / h with A symmetric and only its lower triangle stored: both sweeps run along contiguous rows.
-                for (uint32_t j = 0; j <= l; ++j) e[j] = 0;
-                const double *u = &a[size_t(i) * n];
-                for (uint32_t j = 0; j <= l; ++j) {
-                    const double *row = &a[size_t(j) * n];
-                    const double uj = u[j];
-                    double dot = 0;
-                    for (uint32_t k = 0; k < j; ++k) {
-                        dot += row[k] * u[k];
-                        e[k] += row[k] * uj;
-                    }
-                    e[j] += dot + row[j] * uj;
-                }
-                for (uint32_t j = 0; j <= l; ++j) {
-                    A(j, i) = A(i, j) / h;
-                    e[j] /= h;
-                    f += e[j] * A(i, j);
-                }
-                const double hh = f / (h + h);
-                for (uint32_t j = 0; j <= l; ++j) {
-                    f = A(i, j);
-                    e[j] = g = e[j] - hh * f;
-                    for (uint32_t k = 0; k <= j; ++k) A(j, k) -= f * e[k] + g * A(i, k);
-                }
-            }
-        } else e[i] = A(i, l);
-        d[i] = h;
-    }
-    d[0] = 0;
-    e[0] = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        if (d[i] != 0.0 && i > 0) {
-            // g = row_i * Q[0..i, 0..i), then Q[0..i, 0..i) -= Q[0..i, i] * g: contiguous row sweeps.
-            std::vector<double> &g = scratch;
-            std::fill(g.begin(), g.begin() + i, 0.0);
-            for (uint32_t k = 0; k < i; ++k) {
-                const double aik = A(i, k);
-                const double *row = &a[size_t(k) * n];
-                for (uint32_t j = 0; j < i; ++j) g[j] += aik * row[j];
-            }
-            for (uint32_t k = 0; k < i; ++k) {
-                const double aki = A(k, i);
-                double *row = &a[size_t(k) * n];
-                for (uint32_t j = 0; j < i; ++j) row[j] -= g[j] * aki;
-            }
-        }
-        d[i] = A(i, i);
-        A(i, i) = 1;
-        for (uint32_t j = 0; j < i; ++j) A(j, i) = A(i, j) = 0;
-    }
-    // Implicit QL on the tridiagonal matrix. The rotations mix two eigenvector columns at a time: work on the transpose
-    // so that they are contiguous rows (this loop is ~3 n^3 flops and sits between every two restarts).
-    for (uint32_t r = 0; r < n; ++r)
-        for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
-    for (uint32_t i = 1; i < n; ++i) e[i - 1] = e[i];
-    e[n - 1] = 0;
-    const double eps = std::numeric_limits<double>::epsilon();
-    for (uint32_t l = 0; l < n; ++l) {
-        uint32_t iter = 0, m;
-        do {
-            for (m = l; m + 1 < n; ++m) {
-                const double dd = std::abs(d[m]) + std::abs(d[m + 1]);
-                if (std::abs(e[m]) <= eps * dd) break;
-            }
-            if (m != l) {
-                if (++iter > 200) return false;
-                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
-                double r = std::hypot(g, 1.0);
-                g = d[m] - d[l] + e[l] / (g + std::copysign(r, g));
-                double s = 1, c = 1, p = 0;
-                int64_t i;
-                for (i = int64_t(m) - 1; i >= int64_t(l); --i) {
-                    double f = s * e[i];
-                    const double b = c * e[i];
-                    e[i + 1] = r = std::hypot(f, g);
-                    if (r == 0.0) {
-                        d[i + 1] -= p;
-                        e[m] = 0;
-                        break;
-                    }
-                    s = f / r;
-                    c = g / r;
-                    g = d[i + 1] - p;
-                    r = (d[i] - g) * s + 2.0 * c * b;
-                    d[i + 1] = g + (p = s * r);
-                    g = c * r - b;
-                    double *zi = &a[size_t(i) * n], *zi1 = &a[size_t(i + 1) * n];
-                    for (uint32_t k = 0; k < n; ++k) {
-                        const double fk = zi1[k];
-                        zi1[k] = s * zi[k] + c * fk;
-                        zi[k] = c * zi[k] - s * fk;
-                    }
-                }
-                if (r == 0.0 && i >= int64_t(l)) continue;
-                d[l] -= p;
-                e[l] = g;
-                e[m] = 0;
-            }
-        } while (m != l);
-    }
-    for (uint32_t r = 0; r < n; ++r)
-        for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
-    return true;
-}
-
 void ShiftInvertLanczos::Op(const double *x, double *y) {
     auto s = Fem.Stream;
     if (OpEvents.size() < size_t(2) * (OpCalls + 1)) {
@@ -544,6 +416,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
     std::vector<uint32_t> order;
     uint32_t iter = 0, nconv = 0;
     bool broke = false;
+    bool op_ready = false; // W already holds Op applied to the residual block (issued ahead of the host eigensolve below)
     for (;; ++iter) {
         while (m < mcap) {
             if (cancelled && *cancelled) {
@@ -552,7 +425,8 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
             }
             const uint32_t cur = m + b;
             mark(4);
-            OpPanel(col(V, m), W.Ptr, b);
+            if (!op_ready) OpPanel(col(V, m), W.Ptr, b);
+            op_ready = false;
             mark(0);
             // Two Gram-Schmidt passes against the whole basis; the coefficients are the block column of T.
             mass_product(W.Ptr, MW.Ptr);
@@ -582,8 +456,14 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
             m += b;
         }
         if (out.Cancelled || broke) break;
-        // Rayleigh-Ritz on T[0:m, 0:m].
+        // Rayleigh-Ritz on T[0:m, 0:m]. The device would idle through the host eigensolve (tens of milliseconds), and what it has
+        // to do next if the iteration goes on is already known: a restart keeps the residual block as it is, and the first step
+        // after it applies the operator to exactly that block. So the application is issued now, ahead of the decision.
         mark(4);
+        if (iter < max_restarts) {
+            OpPanel(col(V, m), W.Ptr, b);
+            op_ready = true;
+        }
         evec.assign(size_t(m) * m, 0.0);
         for (uint32_t i = 0; i < m; ++i)
             for (uint32_t j = 0; j < m; ++j) evec[size_t(i) * m + j] = 0.5 * (Tm(i, j) + Tm(j, i));
@@ -655,11 +535,19 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         }
         Small.Reserve(q.size());
         ME_CUDA(cudaMemcpyAsync(Small.Ptr, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-        Vectors.Reserve(n * nev);
-        TallGemm(Ws, V, n, m, Small.Ptr, m, nev, Vectors.Ptr, s);
+        // The Ritz vectors are written into the spare basis buffer, which then becomes `Vectors`: no 0.9 GB allocation at the
+        // end of a solve whose 20 GB of buffers are all still alive (the stream-ordered pool sometimes took 0.2-0.7 s over it).
+        TallGemm(Ws, V, n, m, Small.Ptr, m, nev, V2, s);
+        DeviceBuffer<double> &spare = V2 == Va.Ptr ? Va : Vb;
+        std::swap(Vectors.Ptr, spare.Ptr);
+        std::swap(Vectors.Capacity, spare.Capacity);
     }
+    double t_tail[4]{};
+    t_tail[0] = now();
     ME_CUDA(cudaStreamSynchronize(s));
+    t_tail[1] = now();
     Factor.CheckSolves();
+    t_tail[2] = now();
     for (uint32_t i = 0; i < OpCalls; ++i) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, OpEvents[2 * i], OpEvents[2 * i + 1]) == cudaSuccess) out.OpSolveMs += ms;
@@ -667,6 +555,8 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
     for (auto e : OpEvents) cudaEventDestroy(e);
     OpEvents.clear();
     OpCalls = 0;
+    t_tail[3] = now();
+    if (prof) fprintf(stderr, "[block lanczos] tail: ritz vectors launch %.3f s, sync %.3f s, check %.3f s, events %.3f s\n", t_tail[0] - t_loop_end, t_tail[1] - t_tail[0], t_tail[2] - t_tail[1], t_tail[3] - t_tail[2]);
     out.RankLost = broke;
     out.KernelLaunches = (Fem.KernelLaunches - launches0) + (Factor.Stats.KernelLaunches - f_launches0) + Ws.Launches;
     if (prof) fprintf(stderr, "[block lanczos] extraction + checks %.3f s\n", now() - t_loop_end);

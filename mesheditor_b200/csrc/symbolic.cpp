@@ -330,34 +330,25 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
     // Dataflow schedules of the solves. Ticket order = level order (height above the leaves), NOT elimination order:
     // both are topological, but the post-order would walk one subtree's separator chains at a time, while the level
     // order keeps the chains of all subtrees of the same height in flight together.
-    std::vector<uint32_t> fwd_expected(ns, 0), bwd_expected(ns, 0);
-    {
-        size_t tasks = 0;
-        for (uint32_t s = 0; s < ns; ++s)
-            tasks += (3 * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]) + kSolveRows - 1) / kSolveRows + (3 * size_t(sym.RowPtr[s + 1] - sym.RowPtr[s]) + kSolveRows - 1) / kSolveRows;
-        sym.FwdTasks.reserve(tasks), sym.BwdTasks.reserve(tasks);
-        sym.FwdLinks.reserve(sym.Rows.size() / 2), sym.BwdLinks.reserve(sym.Rows.size() / 2), sym.BwdLinkNeed.reserve(sym.Rows.size() / 2);
-    }
-    auto targets_of = [&](uint32_t s, uint32_t slab, std::vector<uint32_t> &out) {
-        const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0;
-        const uint64_t first = (uint64_t(slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, (uint64_t(slab + 1) * kSolveRows + 2) / 3);
-        uint32_t prev = UINT32_MAX;
-        for (uint64_t j = first; j < last; ++j) {
-            const uint32_t target = sym.NodeSuper[sym.Rows[r0 + j]];
-            if (target != prev) {
-                out.push_back(target);
-                prev = target;
-            }
-        }
-    };
     auto columns = [&](uint32_t s) { return 3 * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]); };
     auto diag_slabs = [&](uint32_t s) { return (columns(s) + kSolveRows - 1) / kSolveRows; };
+    auto panel_slabs = [&](uint32_t s) { return uint32_t((3 * size_t(sym.RowPtr[s + 1] - sym.RowPtr[s]) + kSolveRows - 1) / kSolveRows); };
+    // The supernodes owning rows [first_slab, first_slab + count) slabs of s's panel, ascending (rows are), without repeats.
+    auto targets_of = [&](uint32_t s, uint32_t first_slab, uint32_t count, std::vector<uint32_t> &out, size_t from) {
+        const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0;
+        const uint64_t first = (uint64_t(first_slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, (uint64_t(first_slab + count) * kSolveRows + 2) / 3);
+        for (uint64_t j = first; j < last; ++j) {
+            const uint32_t target = sym.NodeSuper[sym.Rows[r0 + j]];
+            if (out.size() == from || out.back() != target) out.push_back(target);
+        }
+    };
     auto base_task = [&](uint32_t s) {
         SweepTask t{};
         t.Super = s;
         t.K = columns(s);
         t.VecOffset = 3 * sym.SuperFirst[s];
         t.RowsBase = uint32_t(sym.RowPtr[s]);
+        t.Count = 1;
         return t;
     };
     auto diag_task = [&](uint32_t s, uint32_t h) {
@@ -365,44 +356,79 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
         t.Kind = 0, t.Base = sym.InvOffset[s], t.Limit = t.K, t.Ld = t.K, t.Row0 = h * kSolveRows;
         return t;
     };
-    for (uint32_t l = 0; l < sym.NumLevels; ++l) {
-        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
-            for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) sym.FwdTasks.push_back(diag_task(sym.LevelOrder[i], h));
-        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-            const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
-            for (uint32_t h = 0; h * kSolveRows < m; ++h) {
-                SweepTask t = base_task(s);
-                t.Kind = 1, t.Base = sym.PanelOffset[s] + t.K, t.Limit = m, t.Ld = t.K + m, t.Row0 = h * kSolveRows, t.Need = diag_slabs(s);
-                t.LinkBegin = uint32_t(sym.FwdLinks.size());
-                targets_of(s, h, sym.FwdLinks);
-                t.LinkCount = uint32_t(sym.FwdLinks.size()) - t.LinkBegin;
-                for (uint32_t j = 0; j < t.LinkCount; ++j) ++fwd_expected[sym.FwdLinks[t.LinkBegin + j]];
-                sym.FwdTasks.push_back(t);
+    // run_of(level) = slabs per panel task on that level; max_links bounds the arrivals one forward task may owe.
+    auto make_schedules = [&](auto &&run_of, uint32_t max_links, std::vector<SweepTask> &fwd, std::vector<uint32_t> &fwd_links, std::vector<SweepTask> &bwd, std::vector<uint32_t> &bwd_links,
+                              std::vector<uint32_t> &bwd_link_need) {
+        std::vector<uint32_t> fwd_expected(ns, 0), bwd_expected(ns, 0);
+        size_t tasks = 0;
+        for (uint32_t s = 0; s < ns; ++s) tasks += diag_slabs(s) + panel_slabs(s);
+        fwd.reserve(tasks), bwd.reserve(tasks);
+        fwd_links.reserve(sym.Rows.size() / 2), bwd_links.reserve(sym.Rows.size() / 2), bwd_link_need.reserve(sym.Rows.size() / 2);
+        for (uint32_t l = 0; l < sym.NumLevels; ++l) {
+            const uint32_t run = std::max(1u, run_of(l));
+            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
+                for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) fwd.push_back(diag_task(sym.LevelOrder[i], h));
+            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
+                const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]), slabs = panel_slabs(s);
+                for (uint32_t h = 0; h < slabs;) {
+                    SweepTask t = base_task(s);
+                    t.Kind = 1, t.Base = sym.PanelOffset[s] + t.K, t.Limit = m, t.Ld = t.K + m, t.Row0 = h * kSolveRows, t.Need = diag_slabs(s);
+                    t.LinkBegin = uint32_t(fwd_links.size());
+                    // as many slabs as the run allows while the arrivals owed still fit the publishing warp
+                    uint32_t count = 0;
+                    while (count < run && h + count < slabs) {
+                        const size_t before = fwd_links.size();
+                        targets_of(s, h + count, 1, fwd_links, t.LinkBegin);
+                        if (count > 0 && fwd_links.size() - t.LinkBegin > max_links) {
+                            fwd_links.resize(before);
+                            break;
+                        }
+                        ++count;
+                    }
+                    t.Count = count;
+                    t.LinkCount = uint32_t(fwd_links.size()) - t.LinkBegin;
+                    for (uint32_t j = 0; j < t.LinkCount; ++j) ++fwd_expected[fwd_links[t.LinkBegin + j]];
+                    fwd.push_back(t);
+                    h += count;
+                }
             }
         }
-    }
-    for (auto &t : sym.FwdTasks)
-        if (t.Kind == 0) t.Need = fwd_expected[t.Super];
-    for (uint32_t l = sym.NumLevels; l-- > 0;) {
-        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-            const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
-            for (uint32_t h = 0; h * kSolveRows < m; ++h) {
-                SweepTask t = base_task(s);
-                t.Kind = 1, t.Base = sym.PanelOffset[s] - sym.InvOffset[s], t.Limit = m, t.Ld = t.K, t.Row0 = h * kSolveRows;
-                t.LinkBegin = uint32_t(sym.BwdLinks.size());
-                targets_of(s, h, sym.BwdLinks);
-                t.LinkCount = uint32_t(sym.BwdLinks.size()) - t.LinkBegin;
-                for (uint32_t j = 0; j < t.LinkCount; ++j) sym.BwdLinkNeed.push_back(diag_slabs(sym.BwdLinks[t.LinkBegin + j]));
-                ++bwd_expected[s];
-                sym.BwdTasks.push_back(t);
+        for (auto &t : fwd)
+            if (t.Kind == 0) t.Need = fwd_expected[t.Super];
+        for (uint32_t l = sym.NumLevels; l-- > 0;) {
+            const uint32_t run = std::max(1u, run_of(l));
+            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
+                const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]), slabs = panel_slabs(s);
+                for (uint32_t h = 0; h < slabs; h += run) {
+                    SweepTask t = base_task(s);
+                    t.Kind = 1, t.Base = sym.PanelOffset[s] - sym.InvOffset[s], t.Limit = m, t.Ld = t.K, t.Row0 = h * kSolveRows;
+                    t.Count = std::min(run, slabs - h);
+                    t.LinkBegin = uint32_t(bwd_links.size());
+                    targets_of(s, h, t.Count, bwd_links, t.LinkBegin);
+                    t.LinkCount = uint32_t(bwd_links.size()) - t.LinkBegin;
+                    for (uint32_t j = 0; j < t.LinkCount; ++j) bwd_link_need.push_back(diag_slabs(bwd_links[t.LinkBegin + j]));
+                    ++bwd_expected[s];
+                    bwd.push_back(t);
+                }
             }
+            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
+                for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) {
+                    SweepTask t = diag_task(sym.LevelOrder[i], h);
+                    t.Need = bwd_expected[t.Super];
+                    bwd.push_back(t);
+                }
         }
-        for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
-            for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) {
-                SweepTask t = diag_task(sym.LevelOrder[i], h);
-                t.Need = bwd_expected[t.Super];
-                sym.BwdTasks.push_back(t);
-            }
+    };
+    // Single-vector sweeps: one slab per task.
+    make_schedules([](uint32_t) { return 1u; }, UINT32_MAX, sym.FwdTasks, sym.FwdLinks, sym.BwdTasks, sym.BwdLinks, sym.BwdLinkNeed);
+    // Panel sweeps: runs on the levels wide enough to still hand every resident CTA (5 per SM x 148 SMs) a run of its own.
+    {
+        std::vector<uint32_t> level_slabs(sym.NumLevels, 0);
+        for (uint32_t l = 0; l < sym.NumLevels; ++l)
+            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) level_slabs[l] += panel_slabs(sym.LevelOrder[i]);
+        constexpr uint32_t resident = 5 * 148;
+        make_schedules([&](uint32_t l) { return std::min(kWideRun, level_slabs[l] / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
+                       sym.WideBwdLinkNeed);
     }
     lap("sweep tasks");
     sym.StructureSeconds = Now() - t1;

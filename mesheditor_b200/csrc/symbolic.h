@@ -26,6 +26,8 @@ struct PanelTile {
 // One task of a triangular-solve sweep: a slab of kSolveRows rows of a diagonal block's inverse (Kind 0) or of a panel
 // (Kind 1), with everything the kernel needs in one 64-byte record so that a task costs a single descriptor fetch.
 constexpr uint32_t kSolveRows = 32;
+constexpr uint32_t kWideRun = 8;     // longest run of slabs in one task of the panel sweeps
+constexpr uint32_t kWideRunLinks = 32; // a forward run owes at most this many arrivals (one per lane of the publishing warp)
 struct alignas(64) SweepTask {
     uint64_t Base;       // offset in doubles of the matrix block: into Linv / Linv^T (diag), L (forward panel), LT (backward panel)
     uint32_t Kind;       // 0 diagonal slab, 1 panel slab
@@ -37,7 +39,8 @@ struct alignas(64) SweepTask {
     uint32_t RowsBase;   // RowPtr[s]: the supernode's below-diagonal node list
     uint32_t LinkBegin, LinkCount; // ancestors updated (forward panel) / read (backward panel)
     uint32_t Need;       // arrivals to wait for: diagonal slab = contributions to the supernode; forward panel = its diagonal slabs
-    uint32_t Pad[3];
+    uint32_t Count;      // panel sweeps (WideTasks): consecutive kSolveRows-row slabs of the panel covered by this task (>= 1)
+    uint32_t Pad[2];
 };
 
 struct Symbolic {
@@ -64,6 +67,12 @@ struct Symbolic {
     std::vector<SweepTask> BwdTasks;          // levels descending: the level's panel slabs, then its diagonal slabs
     std::vector<uint32_t> FwdLinks;           // forward panel slabs: the ancestors they update
     std::vector<uint32_t> BwdLinks, BwdLinkNeed; // backward panel slabs: the ancestors they read, and how many diagonal slabs each has
+    // The same two schedules for the 8-wide panel sweeps (WideSweepKernel), where a panel task is a RUN of up to kWideRun
+    // consecutive slabs of one panel (SweepTask::Count): long runs on the wide lower levels of the tree, where a run amortises
+    // the handshakes and (backward) the atomics; single slabs on the narrow upper levels, where the slabs of one panel are all
+    // the parallelism there is.
+    std::vector<SweepTask> WideFwdTasks, WideBwdTasks;
+    std::vector<uint32_t> WideFwdLinks, WideBwdLinks, WideBwdLinkNeed;
     uint64_t FactorNonZeros{0};               // scalars stored in the panels
     double FactorFlops{0};
     uint32_t MaxPanelColumns{0}, MaxPanelRows{0};
