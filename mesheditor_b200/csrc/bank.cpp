@@ -611,6 +611,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 .SegStateRe = nullptr,
                 .SegStateIm = nullptr,
                 .Speculation = DSpeculation.Ptr,
+                .OnlyIf = 0u,
                 .Debug = std::getenv("ME_RESONATOR_DEBUG") ? 1u : 0u,
                 .WalkStates = nullptr,
                 .WalkBlocksPerTile = TensorBlocksPerTile,
@@ -644,6 +645,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
             cudaEvent_t k0 = NextEvent(), k1 = NextEvent();
             EventKind.push_back(0);
             ME_CUDA(cudaEventRecord(k0, stream));
+            bool mixed = false; // the window's MixKernel has been launched (tensor-core form launches it ahead of its flag check)
             bool tensor_window = tensor_span && !SpeculationFailed;
             uint32_t segments = 1;
             if (tensor_window) {
@@ -665,22 +667,35 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
                 seed_segments(segments);
                 Timed(1, stream, [&] { LaunchStateWalkKernel(view, plan, stream, Counter); });
-                if (segments > 1 && (speculation_failed() & 7u)) {
-                    SeededWalkFailed = true;
-                    ++Stats.scan_fallbacks;
-                    segments = plan.NSegments = 1;
-                    plan.SegmentFrames = blocks * block_frames;
-                    plan.SegStateRe = plan.SegStateIm = nullptr;
-                    ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
-                    Timed(1, stream, [&] { LaunchStateWalkKernel(view, plan, stream, Counter); });
+                const uint32_t seeded_segments = segments;
+                if (segments > 1) {
+                    // The sequential repeat, launched right behind the seeded walk and run only if that one raised a flag
+                    // (RenderPlan::OnlyIf): the device decides, the host does not wait to find out.
+                    RenderPlan repeat = plan;
+                    repeat.NSegments = 1;
+                    repeat.SegmentFrames = blocks * block_frames;
+                    repeat.SegStateRe = repeat.SegStateIm = nullptr;
+                    repeat.OnlyIf = 7u;
+                    Timed(1, stream, [&] { LaunchStateWalkKernel(view, repeat, stream, Counter); });
                 }
                 Timed(2, stream, [&] {
                     LaunchTensorMixKernel({.Groups = groups, .StagesPerRow = stages_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
                 });
                 ++Counter.Launches;
+                // The fixed-order mix goes out before the flags are read: one host round trip per window, behind its last launch.
+                ME_CUDA(cudaEventRecord(k1, stream));
+                LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, pulses, out_dev + begin, stream, Counter);
+                mixed = true;
+                const uint32_t flags = speculation_failed();
+                if (seeded_segments > 1 && (flags & 7u)) {
+                    SeededWalkFailed = true;
+                    ++Stats.scan_fallbacks;
+                    segments = 1;
+                }
                 // Only code 8 (an increment off the time-block grid) can invalidate a sequential walk.
-                if (speculation_failed() & 8u) {
+                if (flags & 8u) {
                     tensor_window = false;
+                    mixed = false;
                     render_sequentially();
                 } else {
                     ++Stats.tensor_windows;
@@ -709,11 +724,13 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                     LaunchResonatorKernel(view, plan, Steps, stream, Counter);
                 }
             }
-            ME_CUDA(cudaEventRecord(k1, stream));
+            if (!mixed) ME_CUDA(cudaEventRecord(k1, stream));
             Stats.time_segments = std::max(Stats.time_segments, segments);
             Stats.partial_rows = tensor_window ? mix_rows : rows;
-            if (tensor_window) LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, pulses, out_dev + begin, stream, Counter);
-            else LaunchMixKernel(DPartial.Ptr, rows, plan, pulses, out_dev + begin, stream, Counter);
+            if (!mixed) {
+                if (tensor_window) LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, pulses, out_dev + begin, stream, Counter);
+                else LaunchMixKernel(DPartial.Ptr, rows, plan, pulses, out_dev + begin, stream, Counter);
+            }
             Side ^= 1;
             view = View();
         }

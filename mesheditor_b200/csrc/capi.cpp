@@ -3,8 +3,12 @@
 #include "tensor_mix.cuh"
 #include "common.h"
 
+#include <algorithm>
+#include <cstdlib>
+#include <map>
 #include <mutex>
 #include <new>
+#include <unordered_map>
 #include <vector>
 
 namespace me {
@@ -46,34 +50,105 @@ cudaStream_t PoolStream() {
 }
 } // namespace
 
+// Device blocks released by the library are kept, by size, for the next request of (about) that size. A modal solve takes
+// and returns ~20 GB in a few dozen buffers, the same sizes every time the same mesh is solved again (the edit loop, a bench
+// step); handing those straight back to cudaFreeAsync / cudaMallocAsync left the stream-ordered pool re-carving its arena
+// on every solve, and one request in five or so stalled for 0.3 - 1.1 s (measured: profiles/r02_solve.md). With the cache a
+// steady-state solve makes no allocator call at all. At most ME_POOL_CACHE_GB (default 64) are held per device; beyond that
+// the largest idle blocks go back to the driver.
+namespace {
+struct BlockCache {
+    std::mutex Mutex;
+    std::unordered_map<void *, size_t> Sizes;   // every live block handed out by PoolAllocate
+    std::multimap<size_t, void *> Idle;         // released blocks, by size
+    size_t IdleBytes{0};
+};
+BlockCache &CacheOf(int device) {
+    static BlockCache caches[64];
+    if (device < 0 || device >= 64) Fail(ME_BAD_ARG, "device ordinal %d out of range", device);
+    return caches[device];
+}
+size_t CacheLimit() {
+    static const size_t limit = [] {
+        const char *env = std::getenv("ME_POOL_CACHE_GB");
+        return size_t(env ? std::max(0.0, std::atof(env)) : 64.0) << 30;
+    }();
+    return limit;
+}
+} // namespace
+
 void *PoolAllocate(size_t bytes) {
+    bytes = std::max<size_t>((bytes + 255) & ~size_t(255), 256);
+    int device = 0;
+    ME_CUDA(cudaGetDevice(&device));
+    BlockCache &cache = CacheOf(device);
+    {
+        std::lock_guard<std::mutex> lock(cache.Mutex);
+        // the smallest idle block that fits, if it is not wastefully larger (an eighth, or 1 MB for the small ones)
+        const auto it = cache.Idle.lower_bound(bytes);
+        if (it != cache.Idle.end() && it->first <= bytes + std::max<size_t>(bytes / 8, size_t(1) << 20)) {
+            void *ptr = it->second;
+            cache.IdleBytes -= it->first;
+            cache.Sizes[ptr] = it->first;
+            cache.Idle.erase(it);
+            return ptr;
+        }
+    }
     void *ptr = nullptr;
     const cudaStream_t s = PoolStream();
-    const cudaError_t err = cudaMallocAsync(&ptr, bytes ? bytes : 1, s);
+    cudaError_t err = cudaMallocAsync(&ptr, bytes, s);
+    if (err == cudaErrorMemoryAllocation) {
+        // make room: everything idle goes back to the driver, then once more
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lock(cache.Mutex);
+        for (auto &[size, idle] : cache.Idle) cudaFreeAsync(idle, s);
+        cache.Idle.clear();
+        cache.IdleBytes = 0;
+        cudaStreamSynchronize(s);
+        err = cudaMallocAsync(&ptr, bytes, s);
+    }
     if (err != cudaSuccess) Fail(err == cudaErrorMemoryAllocation ? ME_OUT_OF_MEMORY : ME_CUDA_ERROR, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(err));
     ME_CUDA(cudaStreamSynchronize(s)); // usable from any stream from here on
+    std::lock_guard<std::mutex> lock(cache.Mutex);
+    cache.Sizes[ptr] = bytes;
     return ptr;
 }
 void PoolFree(void *ptr) {
-    // Called from destructors: never throws. The device-wide wait is what cudaFree did implicitly.
-    cudaDeviceSynchronize();
+    // Called from destructors: never throws. The device-wide wait is what cudaFree did implicitly: nothing in flight uses the
+    // block any more, so whoever gets it next may use it on any stream.
     int device = 0;
     if (cudaGetDevice(&device) != cudaSuccess) return;
     cudaPointerAttributes attr{};
-    if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.device != device) {
-        cudaSetDevice(attr.device);
-        cudaDeviceSynchronize();
-        try {
-            cudaFreeAsync(ptr, PoolStream());
-        } catch (...) {
-        }
-        cudaSetDevice(device);
-        return;
-    }
+    const int owner = (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeDevice) ? attr.device : device;
+    if (owner != device) cudaSetDevice(owner);
+    cudaDeviceSynchronize();
     try {
-        cudaFreeAsync(ptr, PoolStream());
+        BlockCache &cache = CacheOf(owner);
+        std::vector<void *> evicted;
+        bool keep = false;
+        {
+            std::lock_guard<std::mutex> lock(cache.Mutex);
+            const auto known = cache.Sizes.find(ptr);
+            const size_t size = known != cache.Sizes.end() ? known->second : 0;
+            if (known != cache.Sizes.end()) cache.Sizes.erase(known);
+            if (size && size <= CacheLimit()) {
+                while (cache.IdleBytes + size > CacheLimit() && !cache.Idle.empty()) { // the largest idle blocks make room
+                    const auto last = std::prev(cache.Idle.end());
+                    cache.IdleBytes -= last->first;
+                    evicted.push_back(last->second);
+                    cache.Idle.erase(last);
+                }
+                cache.Idle.emplace(size, ptr);
+                cache.IdleBytes += size;
+                keep = true;
+            }
+        }
+        const cudaStream_t s = PoolStream();
+        for (void *e : evicted) cudaFreeAsync(e, s);
+        if (!keep) cudaFreeAsync(ptr, s);
     } catch (...) {
     }
+    if (owner != device) cudaSetDevice(device);
 }
 } // namespace me
 

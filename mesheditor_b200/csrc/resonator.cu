@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
     __shared__ float cull_energy[kBlockThreads];
     __shared__ uint8_t cull_audible[kBlockThreads];
 
+    if (plan.OnlyIf && (*reinterpret_cast<const volatile uint32_t *>(plan.Speculation) & plan.OnlyIf) == 0) return; // (grid-uniform: every CTA reads the same word, written by an earlier kernel)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t chunk = blockIdx.x * kBlockThreads + threadIdx.x;
     const uint32_t seg = blockIdx.y;

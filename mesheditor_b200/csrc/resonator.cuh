@@ -88,6 +88,10 @@ struct RenderPlan {
     // Set to 1 when a segment met a culling decision the scan along time could not foresee (a frozen chunk or a
     // silenced object with state left): the window is then rendered again sequentially in time.
     uint32_t *Speculation;
+    // Launch-time condition: when non-zero the kernel runs only if (*Speculation & OnlyIf) != 0 and returns at once otherwise.
+    // The sequential repeat of a seeded walk is launched this way right behind it, so that no host round trip sits between the
+    // walk and the tcgen05 mix: the device decides.
+    uint32_t OnlyIf;
     uint32_t Debug;
     // Tensor-core form (tensor_mix.cuh): the walk kernel (one segment: sequential in time, so culling is exact) writes
     // the block-start state of every 256-frame time block (kTmBlock) as rows of States[tile][chunk group][head,tail][block][4096].
