@@ -343,8 +343,8 @@ BankView Bank::View() const {
         .ObjStride = DObjStride.Ptr,
         .ObjFirstChunk = DObjFirstChunk.Ptr,
         .ObjTunedChunks = DObjTunedChunks.Ptr,
-        .ObjMixGain = DObjMixGain.Ptr,
-        .ObjEnergyScale = DObjEnergyScale.Ptr,
+        .ObjMixGain = PlanMixGain,
+        .ObjEnergyScale = PlanEnergyScale,
         .ObjCull = DObjCull.Ptr,
         .ChunkLive = DChunkLive[Side].Ptr,
         .ObjRinging = DObjRinging[Side].Ptr,
@@ -477,7 +477,12 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     }
     // The force and pulse kernels only need the impacts: they start now, and the per-object lists below are planned on the
     // host while they run.
-    DImpacts.Upload(CallImpacts, stream), DTails.Upload(CallTails, stream), DPulseWarps.Upload(CallPulseWarps, stream);
+    // Room for both halves of the plan: the impact half now, the per-object lists (bounded by the impact and object counts) later.
+    Plan.Begin(PlanArena::Room(n * sizeof(DevImpact)) + PlanArena::Room(n * sizeof(DevImpactTail)) + PlanArena::Room(CallPulseWarps.size() * sizeof(PulseWarp)) + 2 * PlanArena::Room(n_obj * sizeof(float)) +
+               2 * PlanArena::Room((size_t(n_obj) + 1) * 4) + 4 * PlanArena::Room(size_t(n) * 4) + 4096);
+    const DevImpact *d_impacts = Plan.Stage(CallImpacts);
+    const DevImpactTail *d_tails = Plan.Stage(CallTails);
+    const PulseWarp *d_pulse_warps = Plan.Stage(CallPulseWarps);
     DForce.Reserve(std::max<uint64_t>(force_total, 1)), DDeltaRe.Reserve(std::max<uint64_t>(delta_total, 1)), DDeltaIm.Reserve(std::max<uint64_t>(delta_total, 1)), DPulseRows.Reserve(std::max<uint64_t>(row_total, 1));
     // Slots of the delta buffers the pulse kernel does not write (chunks past the object in a warp's tail are skipped,
     // every chunk inside the object is written) need no clearing.
@@ -485,8 +490,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
     cudaEvent_t pulse_begin = NextEvent(), pulse_end = NextEvent();
     EventKind.push_back(3);
     ME_CUDA(cudaEventRecord(pulse_begin, stream));
-    LaunchForceKernel(DImpacts.Ptr, DTails.Ptr, n, DForce.Ptr, stream, Counter);
-    const PulsePlan pulses{.NPulseWarps = uint32_t(CallPulseWarps.size()), .Warps = DPulseWarps.Ptr, .Impacts = DImpacts.Ptr, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
+    const PulsePlan pulses{.NPulseWarps = uint32_t(CallPulseWarps.size()), .Warps = d_pulse_warps, .Impacts = d_impacts, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
     {
         // The mix gains are read by the pulse kernel too (and the view below must see their final addresses).
         MixGain.resize(n_obj), EnergyScale.resize(n_obj);
@@ -494,8 +498,10 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
             MixGain[o] = OutGain[o] * ListenerGain[o];
             EnergyScale[o] = MixGain[o] != 0.f ? (OutGain[o] * OutGain[o]) / (MixGain[o] * MixGain[o]) : 0.f;
         }
-        DObjMixGain.Upload(MixGain, stream), DObjEnergyScale.Upload(EnergyScale, stream);
+        PlanMixGain = Plan.Stage(MixGain), PlanEnergyScale = Plan.Stage(EnergyScale);
     }
+    Plan.Flush(stream); // first half: one copy
+    LaunchForceKernel(d_impacts, d_tails, n, DForce.Ptr, stream, Counter);
     BankView view = View();
     LaunchPulseKernel(view, pulses, stream, Counter);
     ME_CUDA(cudaEventRecord(pulse_end, stream));
@@ -546,8 +552,9 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         merged_ptr[o + 1] = uint32_t(CallExciteBegin.size());
     }
     CallExcitePtr = merged_ptr;
-    DInjectPtr.Upload(CallInjectPtr, stream), DInjectFrame.Upload(CallInjectFrame, stream), DInjectDelta.Upload(CallInjectDelta, stream);
-    DExcitePtr.Upload(CallExcitePtr, stream), DExciteBegin.Upload(CallExciteBegin, stream), DExciteEnd.Upload(CallExciteEnd, stream);
+    const uint32_t *d_inject_ptr = Plan.Stage(CallInjectPtr), *d_inject_frame = Plan.Stage(CallInjectFrame), *d_inject_delta = Plan.Stage(CallInjectDelta);
+    const uint32_t *d_excite_ptr = Plan.Stage(CallExcitePtr), *d_excite_begin = Plan.Stage(CallExciteBegin), *d_excite_end = Plan.Stage(CallExciteEnd);
+    Plan.Flush(stream); // second half
     Stats.h2d_bytes += n * (sizeof(DevImpact) + sizeof(DevImpactTail)) + CallPulseWarps.size() * sizeof(PulseWarp) + (CallInjectPtr.size() + CallExcitePtr.size() + 2 * CallInjectFrame.size() + 2 * CallExciteBegin.size() + 2 * n_obj) * 4;
 
     const uint32_t rows = ResonatorRows(NChunks);
@@ -599,12 +606,12 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 .Frames = wf,
                 .NSegments = 1,
                 .SegmentFrames = blocks * block_frames,
-                .ObjInjectPtr = DInjectPtr.Ptr,
-                .InjectFrame = DInjectFrame.Ptr,
-                .InjectDelta = DInjectDelta.Ptr,
-                .ObjExcitePtr = DExcitePtr.Ptr,
-                .ExciteBegin = DExciteBegin.Ptr,
-                .ExciteEnd = DExciteEnd.Ptr,
+                .ObjInjectPtr = d_inject_ptr,
+                .InjectFrame = d_inject_frame,
+                .InjectDelta = d_inject_delta,
+                .ObjExcitePtr = d_excite_ptr,
+                .ExciteBegin = d_excite_begin,
+                .ExciteEnd = d_excite_end,
                 .DeltaRe = DDeltaRe.Ptr,
                 .DeltaIm = DDeltaIm.Ptr,
                 .Partial = nullptr,
@@ -735,7 +742,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
             view = View();
         }
     }
-    if (any_click) LaunchClickKernel(DImpacts.Ptr, DTails.Ptr, n, out_dev, frames, stream, Counter);
+    if (any_click) LaunchClickKernel(d_impacts, d_tails, n, out_dev, frames, stream, Counter);
     for (uint32_t o = 0; o < n_obj; ++o) Stats.mode_samples += uint64_t(TunedModeCount[o]) * frames;
 }
 
