@@ -59,20 +59,29 @@ Bank::Bank(float sample_rate, int device) : SampleRate(sample_rate), Device(devi
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) Fail(ME_CUDA_ERROR, "no CUDA device is available (there is no CPU fallback)");
     if (device < 0 || device >= count) Fail(ME_BAD_ARG, "device %d out of range (%d visible)", device, count);
     ME_CUDA(cudaSetDevice(Device));
-    ME_CUDA(cudaStreamCreateWithFlags(&OwnStream, cudaStreamNonBlocking));
+    // The render stream outranks the pulse stream: when both have CTAs pending, the state walk (which the tcgen05 mix waits for) is
+    // placed first and the pulse kernels of the next sub-window fill what is left of the SMs. A caller's stream has the default
+    // (lowest) priority, so renders always run on the bank's own stream, forked from the caller's and joined back into it.
+    int least = 0, greatest = 0;
+    ME_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    ME_CUDA(cudaStreamCreateWithPriority(&OwnStream, cudaStreamNonBlocking, greatest));
+    ME_CUDA(cudaStreamCreateWithPriority(&PulseStream, cudaStreamNonBlocking, least));
     ME_CUDA(cudaEventCreate(&EvBegin));
     ME_CUDA(cudaEventCreate(&EvEnd));
     // Diagnostic overrides: samples advanced per state jump (1, 2 or 4) and segments of the scan along time.
     if (const char *steps = std::getenv("ME_RESONATOR_STEPS")) Steps = std::atoi(steps);
     if (const char *segments = std::getenv("ME_RESONATOR_SEGMENTS")) RequestedSegments = uint32_t(std::atoi(segments));
+    if (const char *tiles = std::getenv("ME_WALK_SUBWINDOW_TILES")) SubWindowTiles = uint32_t(std::max(0, std::atoi(tiles)));
 }
 
 Bank::~Bank() {
     cudaSetDevice(Device);
+    if (PulseStream) cudaStreamSynchronize(PulseStream), cudaStreamDestroy(PulseStream);
     if (OwnStream) cudaStreamSynchronize(OwnStream), cudaStreamDestroy(OwnStream);
     for (auto e : {EvBegin, EvEnd})
         if (e) cudaEventDestroy(e);
     for (auto e : EventPool) cudaEventDestroy(e);
+    for (auto e : JoinPool) cudaEventDestroy(e);
 }
 
 void Bank::CheckSlot(uint32_t slot) const {
@@ -297,7 +306,7 @@ void Bank::Install() {
     ME_CUDA(cudaMemsetAsync(DStateIm[0].Ptr, 0, padded * sizeof(float), OwnStream));
     ME_CUDA(cudaMemsetAsync(DChunkLive[0].Ptr, 1, std::max<uint32_t>(NChunks, 1), OwnStream));
     ME_CUDA(cudaMemsetAsync(DObjRinging[0].Ptr, 0, std::max<uint32_t>(n_obj, 1), OwnStream));
-    DSpeculation.Reserve(1);
+    DSpeculation.Reserve(64); // one word per sub-window of a launch window
     ME_CUDA(cudaStreamSynchronize(OwnStream));
     Impacts.clear();
     RetunedObjects.clear();
@@ -402,14 +411,19 @@ void Schedule(ScheduledImpact &s, uint32_t block_frames, uint32_t span_frames) {
     s.Survives = true;
 }
 
+// Samples of a contact pulse (ActivateImpact, ModalAudio.cpp:36).
+uint32_t PulseSamples(float pulse_step) {
+    const float steps = std::ceil(1.f / pulse_step);
+    return steps >= 4294967040.f ? 4294967040u : uint32_t(steps);
+}
+
 // ActivateImpact, ModalAudio.cpp:28-51.
 HostImpact MakeImpact(const MeModalEvent &e) {
     const auto theta = 2 * Pi * e.pulse_step;
-    const float steps = std::ceil(1.f / e.pulse_step);
     return {
         .Object = e.object,
         .ExPos = e.ex_pos,
-        .SamplesLeft = steps >= 4294967040.f ? 4294967040u : uint32_t(steps),
+        .SamplesLeft = PulseSamples(e.pulse_step),
         .Jx = e.jx,
         .Jy = e.jy,
         .Jz = e.jz,
@@ -428,69 +442,34 @@ HostImpact MakeImpact(const MeModalEvent &e) {
 }
 } // namespace
 
-void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<ScheduledImpact> &scheduled, float *out_dev, cudaStream_t stream) {
-    const auto plan_begin = std::chrono::steady_clock::now();
+void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<ScheduledImpact> &scheduled, const std::function<void(uint32_t)> &admit_before, const SpanBounds &bounds, float *out_dev, cudaStream_t stream) {
+    using Clock = std::chrono::steady_clock;
+    const auto since = [](Clock::time_point t0) { return std::chrono::duration<float, std::milli>(Clock::now() - t0).count(); };
     const uint32_t n_obj = ObjectCount();
-    const uint32_t n = uint32_t(scheduled.size());
-    // Impacts sorted by (start, object): the order of the pulse rows in the mix.
-    std::vector<uint32_t> order(n);
-    std::iota(order.begin(), order.end(), 0u);
-    const auto by_start_then_object = [&](uint32_t a, uint32_t b) {
-        const auto &x = scheduled[a], &y = scheduled[b];
-        return x.Start != y.Start ? x.Start < y.Start : x.AtStart.Object < y.AtStart.Object;
-    };
-    if (!std::is_sorted(order.begin(), order.end(), by_start_then_object)) std::stable_sort(order.begin(), order.end(), by_start_then_object);
-    CallImpacts.resize(n);
-    CallTails.resize(n);
-    CallPulseWarps.clear();
     // The tensor-core form needs RenderModal blocks made of whole 256-frame time blocks and tiles made of whole
     // RenderModal blocks, and pays off once (chunk groups x tiles) fills the SMs.
     const uint32_t groups = NChunks / kTmGroupChunks;
     const bool tensor_possible = groups > 0 && block_frames % kTmBlock == 0 && TensorTileFrames % block_frames == 0 && !SpeculationFailed;
     const uint64_t tensor_units = uint64_t(groups) * ((frames + TensorTileFrames - 1) / TensorTileFrames);
     const bool tensor_span = tensor_possible && (RenderPath == 2 || (RenderPath == 0 && tensor_units >= 128 && frames >= 2 * TensorTileFrames));
-    uint64_t force_total = 0, delta_total = 0, row_total = 0;
-    uint32_t max_len = 0;
-    bool any_click = false;
-    for (uint32_t i = 0; i < n; ++i) {
-        const auto &s = scheduled[order[i]];
-        const auto &im = s.AtStart;
-        const uint32_t len = uint32_t(std::min<uint64_t>(im.SamplesLeft, frames - s.Start));
-        // In a tensor span the pulse kernel keeps rendering the pulse's free ringing up to the next time-block boundary,
-        // where its state increment joins the bank (increments must land on block-start states).
-        uint32_t render_len = len;
-        if (tensor_span && len) render_len = uint32_t(std::min<uint64_t>((uint64_t(s.Start) + len + kTmBlock - 1) / kTmBlock * kTmBlock, frames)) - s.Start;
-        const uint32_t chunks = ObjStride[im.Object] / kLanes;
-        const uint32_t warps = len ? (chunks + 31) / 32 : 0;
-        if (force_total + len >= (uint64_t(1) << 32) || delta_total + ObjStride[im.Object] >= (uint64_t(1) << 32) || row_total + uint64_t(warps) * render_len >= (uint64_t(1) << 32))
-            Fail(ME_BAD_ARG, "impact buffers exceed 2^32 entries in one span");
-        CallImpacts[i] = {.Start = s.Start, .Len = len, .ForceOff = uint32_t(force_total), .ExPos = im.ExPos, .Jx = im.Jx, .Jy = im.Jy, .Jz = im.Jz, .Object = im.Object, .PhaseRe = im.PhaseRe, .PhaseIm = im.PhaseIm, .RotRe = im.RotRe, .RotIm = im.RotIm, .End = s.End, .DeltaOff = uint32_t(delta_total), .HasClick = HasClick(im) ? 1u : 0u, .RenderLen = render_len};
-        CallTails[i] = {.Gamma = im.Gamma, .AccelAmp = im.AccelAmp, .ClickB0 = im.ClickB0, .ClickA1 = im.ClickA1, .ClickA2 = im.ClickA2, .ClickZ1 = im.ClickZ1, .ClickZ2 = im.ClickZ2, .ClickGain = ClickGain * ListenerGain[im.Object]};
-        for (uint32_t w = 0; w < warps; ++w) {
-            CallPulseWarps.push_back({.Impact = i, .Chunk0 = w * 32, .RowOff = uint32_t(row_total), .Start = s.Start, .RenderLen = render_len, .Pad = 0});
-            row_total += render_len;
-        }
-        any_click |= HasClick(im);
-        max_len = std::max(max_len, render_len);
-        force_total += len;
-        if (len) delta_total += ObjStride[im.Object];
-    }
-    // The force and pulse kernels only need the impacts: they start now, and the per-object lists below are planned on the
-    // host while they run.
-    // Room for both halves of the plan: the impact half now, the per-object lists (bounded by the impact and object counts) later.
-    Plan.Begin(PlanArena::Room(n * sizeof(DevImpact)) + PlanArena::Room(n * sizeof(DevImpactTail)) + PlanArena::Room(CallPulseWarps.size() * sizeof(PulseWarp)) + 2 * PlanArena::Room(n_obj * sizeof(float)) +
-               2 * PlanArena::Room((size_t(n_obj) + 1) * 4) + 4 * PlanArena::Room(size_t(n) * 4) + 4096);
-    const DevImpact *d_impacts = Plan.Stage(CallImpacts);
-    const DevImpactTail *d_tails = Plan.Stage(CallTails);
-    const PulseWarp *d_pulse_warps = Plan.Stage(CallPulseWarps);
-    DForce.Reserve(std::max<uint64_t>(force_total, 1)), DDeltaRe.Reserve(std::max<uint64_t>(delta_total, 1)), DDeltaIm.Reserve(std::max<uint64_t>(delta_total, 1)), DPulseRows.Reserve(std::max<uint64_t>(row_total, 1));
+    // Tensor spans are rendered as a pipeline over sub-windows of a few tiles: while the walk kernel (HBM-write bound) steps the
+    // bank through sub-window k on the render stream, the force + pulse kernels (FP32-issue bound) of sub-window k + 1 run beside
+    // it on the pulse stream, and the host admits and plans sub-window k + 2. Only the first sub-window's planning is exposed.
+    // (A bank of few chunk groups walks in seeded segments and is launch-bound: it keeps one batch per launch window.)
+    const bool piped = tensor_span && SubWindowTiles > 0 && groups >= 128;
+    const cudaStream_t pulse_stream = piped ? PulseStream : stream;
+
+    auto host_begin = Clock::now();
+    const uint64_t window_bound = tensor_span ? (uint64_t(frames) + TensorTileFrames - 1) / TensorTileFrames + 1 : 2; // list sets staged at most
+    Plan.Begin(PlanArena::Room(bounds.Impacts * sizeof(DevImpact)) + PlanArena::Room(bounds.Impacts * sizeof(DevImpactTail)) + PlanArena::Room(bounds.Warps * sizeof(PulseWarp)) + 2 * PlanArena::Room(n_obj * sizeof(float)) +
+               window_bound * (2 * PlanArena::Room((size_t(n_obj) + 1) * 4) + 4 * PlanArena::Room(size_t(bounds.Impacts) * 4)) + 4096);
+    const auto impacts = Plan.Reserve<DevImpact>(bounds.Impacts);
+    const auto tails = Plan.Reserve<DevImpactTail>(bounds.Impacts);
+    const auto pulse_warps = Plan.Reserve<PulseWarp>(bounds.Warps);
+    Plan.SkipRegions();
+    DForce.Reserve(std::max<uint64_t>(bounds.Force, 1)), DDeltaRe.Reserve(std::max<uint64_t>(bounds.Delta, 1)), DDeltaIm.Reserve(std::max<uint64_t>(bounds.Delta, 1)), DPulseRows.Reserve(std::max<uint64_t>(bounds.Rows, 1));
     // Slots of the delta buffers the pulse kernel does not write (chunks past the object in a warp's tail are skipped,
     // every chunk inside the object is written) need no clearing.
-    Stats.host_plan_ms += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - plan_begin).count();
-    cudaEvent_t pulse_begin = NextEvent(), pulse_end = NextEvent();
-    EventKind.push_back(3);
-    ME_CUDA(cudaEventRecord(pulse_begin, stream));
-    const PulsePlan pulses{.NPulseWarps = uint32_t(CallPulseWarps.size()), .Warps = d_pulse_warps, .Impacts = d_impacts, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
     {
         // The mix gains are read by the pulse kernel too (and the view below must see their final addresses).
         MixGain.resize(n_obj), EnergyScale.resize(n_obj);
@@ -499,67 +478,200 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
             EnergyScale[o] = MixGain[o] != 0.f ? (OutGain[o] * OutGain[o]) / (MixGain[o] * MixGain[o]) : 0.f;
         }
         PlanMixGain = Plan.Stage(MixGain), PlanEnergyScale = Plan.Stage(EnergyScale);
+        Plan.Flush(stream);
+        Stats.h2d_bytes += 2 * n_obj * sizeof(float);
     }
-    Plan.Flush(stream); // first half: one copy
-    LaunchForceKernel(d_impacts, d_tails, n, DForce.Ptr, stream, Counter);
+    if (piped) {
+        // The pulse stream picks up behind everything the render stream has been given so far (the gains, earlier spans).
+        const cudaEvent_t fork = NextJoin();
+        ME_CUDA(cudaEventRecord(fork, stream));
+        ME_CUDA(cudaStreamWaitEvent(pulse_stream, fork, 0));
+    }
     BankView view = View();
-    LaunchPulseKernel(view, pulses, stream, Counter);
-    ME_CUDA(cudaEventRecord(pulse_end, stream));
 
-    // Per object: increments in frame order, and the merged intervals during which it holds a live impact.
-    // (impacts are in start order, so a counting sort by object leaves each object's lists in start order too)
-    CallInjectPtr.assign(n_obj + 1, 0), CallExcitePtr.assign(n_obj + 1, 0);
-    for (uint32_t i = 0; i < n; ++i) {
-        const auto &im = CallImpacts[i];
-        if (im.Len) ++CallInjectPtr[im.Object + 1];
-        if (im.End > im.Start) ++CallExcitePtr[im.Object + 1];
-    }
-    for (uint32_t o = 0; o < n_obj; ++o) CallInjectPtr[o + 1] += CallInjectPtr[o], CallExcitePtr[o + 1] += CallExcitePtr[o];
-    CallInjectFrame.resize(CallInjectPtr[n_obj]), CallInjectDelta.resize(CallInjectPtr[n_obj]);
-    std::vector<std::pair<uint32_t, uint32_t>> excite(CallExcitePtr[n_obj]);
-    {
-        std::vector<uint32_t> inject_at(CallInjectPtr.begin(), CallInjectPtr.end() - 1), excite_at(CallExcitePtr.begin(), CallExcitePtr.end() - 1);
-        for (uint32_t i = 0; i < n; ++i) {
-            const auto &im = CallImpacts[i];
-            if (im.Len) {
+    // ---- pulse batches: impacts in start order, planned and launched as they are admitted -------------------------------
+    uint32_t n = 0, n_warps = 0, max_len = 0;
+    uint64_t force_total = 0, delta_total = 0, row_total = 0;
+    bool any_click = false;
+    cudaEvent_t pulses_done = nullptr; // last batch's kernels have finished (pulse stream)
+    std::vector<uint32_t> order;
+    const auto current_pulses = [&] {
+        return PulsePlan{.NPulseWarps = n_warps, .Warps = pulse_warps.Dev, .Impacts = impacts.Dev, .Force = DForce.Ptr, .Rows = DPulseRows.Ptr, .DeltaRe = DDeltaRe.Ptr, .DeltaIm = DDeltaIm.Ptr, .MaxLen = max_len};
+    };
+    const auto plan_pulses_before = [&](uint32_t limit) {
+        admit_before(limit);
+        const uint32_t n0 = n, n1 = uint32_t(scheduled.size()), w0 = n_warps;
+        if (n1 == n0) return;
+        if (n1 > bounds.Impacts) Fail(ME_CUDA_ERROR, "internal: %u impacts admitted, %llu planned for", n1, (unsigned long long)bounds.Impacts);
+        // Sorted by (start, object): the order of the pulse rows in the mix. Batches are disjoint in start, so each is sorted on its own.
+        order.resize(n1 - n0);
+        std::iota(order.begin(), order.end(), n0);
+        const auto by_start_then_object = [&](uint32_t a, uint32_t b) {
+            const auto &x = scheduled[a], &y = scheduled[b];
+            return x.Start != y.Start ? x.Start < y.Start : x.AtStart.Object < y.AtStart.Object;
+        };
+        if (!std::is_sorted(order.begin(), order.end(), by_start_then_object)) std::stable_sort(order.begin(), order.end(), by_start_then_object);
+        for (uint32_t i = n0; i < n1; ++i) {
+            const auto &s = scheduled[order[i - n0]];
+            const auto &im = s.AtStart;
+            const uint32_t len = uint32_t(std::min<uint64_t>(im.SamplesLeft, frames - s.Start));
+            // In a tensor span the pulse kernel keeps rendering the pulse's free ringing up to the next time-block boundary,
+            // where its state increment joins the bank (increments must land on block-start states).
+            uint32_t render_len = len;
+            if (tensor_span && len) render_len = uint32_t(std::min<uint64_t>((uint64_t(s.Start) + len + kTmBlock - 1) / kTmBlock * kTmBlock, frames)) - s.Start;
+            const uint32_t stride = ObjStride[im.Object];
+            const uint32_t warps = len ? (stride / kLanes + 31) / 32 : 0;
+            if (force_total + len >= (uint64_t(1) << 32) || delta_total + stride >= (uint64_t(1) << 32) || row_total + uint64_t(warps) * render_len >= (uint64_t(1) << 32))
+                Fail(ME_BAD_ARG, "impact buffers exceed 2^32 entries in one span");
+            if (force_total + len > DForce.Capacity || delta_total + (len ? stride : 0) > DDeltaRe.Capacity || row_total + uint64_t(warps) * render_len > DPulseRows.Capacity || n_warps + warps > bounds.Warps)
+                Fail(ME_CUDA_ERROR, "internal: impact %u outgrows the span's pulse buffers", i);
+            impacts.Host[i] = {.Start = s.Start, .Len = len, .ForceOff = uint32_t(force_total), .ExPos = im.ExPos, .Jx = im.Jx, .Jy = im.Jy, .Jz = im.Jz, .Object = im.Object, .PhaseRe = im.PhaseRe, .PhaseIm = im.PhaseIm, .RotRe = im.RotRe, .RotIm = im.RotIm, .End = s.End, .DeltaOff = uint32_t(delta_total), .HasClick = HasClick(im) ? 1u : 0u, .RenderLen = render_len};
+            tails.Host[i] = {.Gamma = im.Gamma, .AccelAmp = im.AccelAmp, .ClickB0 = im.ClickB0, .ClickA1 = im.ClickA1, .ClickA2 = im.ClickA2, .ClickZ1 = im.ClickZ1, .ClickZ2 = im.ClickZ2, .ClickGain = ClickGain * ListenerGain[im.Object]};
+            for (uint32_t w = 0; w < warps; ++w) {
+                pulse_warps.Host[n_warps++] = {.Impact = i, .Chunk0 = w * 32, .RowOff = uint32_t(row_total), .Start = s.Start, .RenderLen = render_len, .Pad = 0};
+                row_total += render_len;
+            }
+            any_click |= HasClick(im);
+            max_len = std::max(max_len, render_len);
+            force_total += len;
+            if (len) delta_total += stride;
+        }
+        n = n1;
+        Plan.FlushRange(impacts, n0, n1 - n0, pulse_stream), Plan.FlushRange(tails, n0, n1 - n0, pulse_stream), Plan.FlushRange(pulse_warps, w0, n_warps - w0, pulse_stream);
+        Stats.h2d_bytes += (n1 - n0) * (sizeof(DevImpact) + sizeof(DevImpactTail)) + (n_warps - w0) * sizeof(PulseWarp);
+        Timed(3, pulse_stream, [&] {
+            LaunchForceKernel(impacts.Dev + n0, tails.Dev + n0, n1 - n0, DForce.Ptr, pulse_stream, Counter);
+            PulsePlan batch = current_pulses();
+            batch.NPulseWarps = n_warps - w0, batch.Warps = pulse_warps.Dev + w0;
+            LaunchPulseKernel(view, batch, pulse_stream, Counter);
+        });
+        if (piped) {
+            pulses_done = NextJoin();
+            ME_CUDA(cudaEventRecord(pulses_done, pulse_stream));
+        }
+    };
+    // The render stream may read what the pulse batches planned so far have written.
+    const auto join_pulses = [&] {
+        if (pulses_done) ME_CUDA(cudaStreamWaitEvent(stream, pulses_done, 0));
+        pulses_done = nullptr;
+    };
+
+    // ---- per-object lists of a stretch [begin, end) of the span ------------------------------------------------------------
+    // Per object: increments in landing order, and the merged intervals during which it holds a live impact. `candidates` (impact
+    // indices, ascending = start order) must hold every impact whose increment lands in [begin, end] or whose lifetime meets
+    // [begin, end); a counting sort by object leaves each object's lists in start order.
+    struct Lists {
+        const uint32_t *InjectPtr, *InjectFrame, *InjectDelta, *ExcitePtr, *ExciteBegin, *ExciteEnd;
+    };
+    std::vector<std::pair<uint32_t, uint32_t>> excite;
+    std::vector<uint32_t> inject_at, excite_at, merged_ptr;
+    const auto build_lists = [&](uint32_t begin, uint32_t end, const std::vector<uint32_t> &candidates) {
+        const auto lands_here = [&](const DevImpact &im) { return im.Len && im.Start + im.RenderLen >= begin && im.Start + im.RenderLen <= end; };
+        const auto lives_here = [&](const DevImpact &im) { return im.End > im.Start && im.End > begin && im.Start < end; };
+        CallInjectPtr.assign(n_obj + 1, 0), CallExcitePtr.assign(n_obj + 1, 0);
+        for (const uint32_t i : candidates) {
+            const auto &im = impacts.Host[i];
+            if (lands_here(im)) ++CallInjectPtr[im.Object + 1];
+            if (lives_here(im)) ++CallExcitePtr[im.Object + 1];
+        }
+        for (uint32_t o = 0; o < n_obj; ++o) CallInjectPtr[o + 1] += CallInjectPtr[o], CallExcitePtr[o + 1] += CallExcitePtr[o];
+        CallInjectFrame.resize(CallInjectPtr[n_obj]), CallInjectDelta.resize(CallInjectPtr[n_obj]);
+        excite.resize(CallExcitePtr[n_obj]);
+        inject_at.assign(CallInjectPtr.begin(), CallInjectPtr.end() - 1), excite_at.assign(CallExcitePtr.begin(), CallExcitePtr.end() - 1);
+        for (const uint32_t i : candidates) {
+            const auto &im = impacts.Host[i];
+            if (lands_here(im)) {
                 const uint32_t at = inject_at[im.Object]++;
                 CallInjectFrame[at] = im.Start + im.RenderLen, CallInjectDelta[at] = im.DeltaOff;
             }
-            if (im.End > im.Start) excite[excite_at[im.Object]++] = {im.Start, im.End};
+            if (lives_here(im)) excite[excite_at[im.Object]++] = {im.Start, im.End};
         }
+        CallExciteBegin.clear(), CallExciteEnd.clear();
+        merged_ptr.assign(n_obj + 1, 0);
+        for (uint32_t o = 0; o < n_obj; ++o) {
+            // Increments sorted by the frame they land on (pulse lengths differ, so start order is not landing order).
+            const uint32_t i0 = CallInjectPtr[o], i1 = CallInjectPtr[o + 1];
+            bool sorted = true;
+            for (uint32_t i = i0 + 1; i < i1 && sorted; ++i) sorted = CallInjectFrame[i - 1] <= CallInjectFrame[i];
+            if (!sorted) {
+                std::vector<std::pair<uint32_t, uint32_t>> tmp(i1 - i0);
+                for (uint32_t i = i0; i < i1; ++i) tmp[i - i0] = {CallInjectFrame[i], CallInjectDelta[i]};
+                std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
+                for (uint32_t i = i0; i < i1; ++i) CallInjectFrame[i] = tmp[i - i0].first, CallInjectDelta[i] = tmp[i - i0].second;
+            }
+            // Merged intervals during which the object holds a live impact.
+            const auto e0 = excite.begin() + CallExcitePtr[o], e1 = excite.begin() + CallExcitePtr[o + 1];
+            if (!std::is_sorted(e0, e1)) std::sort(e0, e1);
+            const size_t first = CallExciteBegin.size();
+            for (auto it = e0; it != e1; ++it) {
+                if (CallExciteBegin.size() > first && it->first <= CallExciteEnd.back()) CallExciteEnd.back() = std::max(CallExciteEnd.back(), it->second);
+                else CallExciteBegin.push_back(it->first), CallExciteEnd.push_back(it->second);
+            }
+            merged_ptr[o + 1] = uint32_t(CallExciteBegin.size());
+        }
+        CallExcitePtr = merged_ptr;
+        const Lists lists{Plan.Stage(CallInjectPtr), Plan.Stage(CallInjectFrame), Plan.Stage(CallInjectDelta), Plan.Stage(CallExcitePtr), Plan.Stage(CallExciteBegin), Plan.Stage(CallExciteEnd)};
+        Plan.Flush(stream);
+        Stats.h2d_bytes += (CallInjectPtr.size() + CallExcitePtr.size() + 2 * CallInjectFrame.size() + 2 * CallExciteBegin.size()) * 4;
+        return lists;
+    };
+    std::vector<uint32_t> candidates, carried; // impacts a stretch has to look at; those reaching past its end
+    const auto lists_for = [&](uint32_t begin, uint32_t end, uint32_t first_new) {
+        candidates = carried;
+        for (uint32_t i = first_new; i < n; ++i) candidates.push_back(i);
+        const Lists lists = build_lists(begin, end, candidates);
+        carried.clear();
+        for (const uint32_t i : candidates) {
+            const auto &im = impacts.Host[i];
+            if (std::max(im.Len ? im.Start + im.RenderLen : 0u, im.End) >= end) carried.push_back(i);
+        }
+        return lists;
+    };
+    const auto all_lists = [&](uint32_t begin, uint32_t end) { // after a fallback: every impact planned so far is looked at
+        candidates.resize(n);
+        std::iota(candidates.begin(), candidates.end(), 0u);
+        return build_lists(begin, end, candidates);
+    };
+    const auto plan_for = [&](const Lists &lists, uint32_t begin, uint32_t wf, uint32_t blocks) {
+        return RenderPlan{
+            .SpanFrames = frames,
+            .BlockFrames = block_frames,
+            .FrameBegin = begin,
+            .Frames = wf,
+            .NSegments = 1,
+            .SegmentFrames = blocks * block_frames,
+            .ObjInjectPtr = lists.InjectPtr,
+            .InjectFrame = lists.InjectFrame,
+            .InjectDelta = lists.InjectDelta,
+            .ObjExcitePtr = lists.ExcitePtr,
+            .ExciteBegin = lists.ExciteBegin,
+            .ExciteEnd = lists.ExciteEnd,
+            .DeltaRe = DDeltaRe.Ptr,
+            .DeltaIm = DDeltaIm.Ptr,
+            .Partial = nullptr,
+            .SegStateRe = nullptr,
+            .SegStateIm = nullptr,
+            .Speculation = DSpeculation.Ptr,
+            .OnlyIf = 0u,
+            .Debug = std::getenv("ME_RESONATOR_DEBUG") ? 1u : 0u,
+            .WalkStates = nullptr,
+            .WalkBlocksPerTile = TensorBlocksPerTile,
+        };
+    };
+
+    Lists span_lists{};
+    if (!tensor_span) {
+        // Sample loop: every impact of the span is planned at once; the per-object lists are built while the pulse kernels run.
+        plan_pulses_before(frames);
+        span_lists = all_lists(0, frames);
+        Stats.host_plan_ms += since(host_begin);
     }
-    CallExciteBegin.clear(), CallExciteEnd.clear();
-    std::vector<uint32_t> merged_ptr(n_obj + 1, 0);
-    for (uint32_t o = 0; o < n_obj; ++o) {
-        // Increments sorted by the frame they land on (pulse lengths differ, so start order is not landing order).
-        const uint32_t i0 = CallInjectPtr[o], i1 = CallInjectPtr[o + 1];
-        bool sorted = true;
-        for (uint32_t i = i0 + 1; i < i1 && sorted; ++i) sorted = CallInjectFrame[i - 1] <= CallInjectFrame[i];
-        if (!sorted) {
-            std::vector<std::pair<uint32_t, uint32_t>> tmp(i1 - i0);
-            for (uint32_t i = i0; i < i1; ++i) tmp[i - i0] = {CallInjectFrame[i], CallInjectDelta[i]};
-            std::stable_sort(tmp.begin(), tmp.end(), [](const auto &a, const auto &b) { return a.first < b.first; });
-            for (uint32_t i = i0; i < i1; ++i) CallInjectFrame[i] = tmp[i - i0].first, CallInjectDelta[i] = tmp[i - i0].second;
-        }
-        // Merged intervals during which the object holds a live impact.
-        const auto e0 = excite.begin() + CallExcitePtr[o], e1 = excite.begin() + CallExcitePtr[o + 1];
-        if (!std::is_sorted(e0, e1)) std::sort(e0, e1);
-        const size_t first = CallExciteBegin.size();
-        for (auto it = e0; it != e1; ++it) {
-            if (CallExciteBegin.size() > first && it->first <= CallExciteEnd.back()) CallExciteEnd.back() = std::max(CallExciteEnd.back(), it->second);
-            else CallExciteBegin.push_back(it->first), CallExciteEnd.push_back(it->second);
-        }
-        merged_ptr[o + 1] = uint32_t(CallExciteBegin.size());
-    }
-    CallExcitePtr = merged_ptr;
-    const uint32_t *d_inject_ptr = Plan.Stage(CallInjectPtr), *d_inject_frame = Plan.Stage(CallInjectFrame), *d_inject_delta = Plan.Stage(CallInjectDelta);
-    const uint32_t *d_excite_ptr = Plan.Stage(CallExcitePtr), *d_excite_begin = Plan.Stage(CallExciteBegin), *d_excite_end = Plan.Stage(CallExciteEnd);
-    Plan.Flush(stream); // second half
-    Stats.h2d_bytes += n * (sizeof(DevImpact) + sizeof(DevImpactTail)) + CallPulseWarps.size() * sizeof(PulseWarp) + (CallInjectPtr.size() + CallExcitePtr.size() + 2 * CallInjectFrame.size() + 2 * CallExciteBegin.size() + 2 * n_obj) * 4;
 
     const uint32_t rows = ResonatorRows(NChunks);
     Stats.time_segments = 1;
     if (rows == 0) {
+        plan_pulses_before(frames);
+        join_pulses();
         ME_CUDA(cudaMemsetAsync(out_dev, 0, size_t(frames) * sizeof(float), stream));
     } else {
         // Launch windows bound the partial-row buffer (or the state stages); they start on block boundaries.
@@ -596,46 +708,35 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
         }
         const uint32_t mix_rows = groups ? uint32_t(uint64_t(groups) * kTmStagesPerGroup / stages_per_row) : 0;
         const uint32_t ctas = NChunks / kBlockThreads;
+        bool lists_cover_span = !tensor_span; // span_lists hold every impact (sample loop, or after a fallback)
         for (uint32_t begin = 0; begin < frames; begin += window) {
             const uint32_t wf = std::min(window, frames - begin);
             const uint32_t blocks = (wf + block_frames - 1) / block_frames;
-            RenderPlan plan{
-                .SpanFrames = frames,
-                .BlockFrames = block_frames,
-                .FrameBegin = begin,
-                .Frames = wf,
-                .NSegments = 1,
-                .SegmentFrames = blocks * block_frames,
-                .ObjInjectPtr = d_inject_ptr,
-                .InjectFrame = d_inject_frame,
-                .InjectDelta = d_inject_delta,
-                .ObjExcitePtr = d_excite_ptr,
-                .ExciteBegin = d_excite_begin,
-                .ExciteEnd = d_excite_end,
-                .DeltaRe = DDeltaRe.Ptr,
-                .DeltaIm = DDeltaIm.Ptr,
-                .Partial = nullptr,
-                .SegStateRe = nullptr,
-                .SegStateIm = nullptr,
-                .Speculation = DSpeculation.Ptr,
-                .OnlyIf = 0u,
-                .Debug = std::getenv("ME_RESONATOR_DEBUG") ? 1u : 0u,
-                .WalkStates = nullptr,
-                .WalkBlocksPerTile = TensorBlocksPerTile,
-            };
-            const auto seed_segments = [&](uint32_t segments) {
+            if (!lists_cover_span && !(tensor_span && !SpeculationFailed)) {
+                // A tensor span that fell back to the sample loop: the remaining windows take lists over everything.
+                host_begin = Clock::now();
+                plan_pulses_before(frames);
+                span_lists = all_lists(begin, frames);
+                lists_cover_span = true;
+                Stats.host_plan_ms += since(host_begin);
+            }
+            RenderPlan plan = plan_for(span_lists, begin, wf, blocks);
+            const auto seed_segments = [&](RenderPlan &p, uint32_t segments) {
                 if (segments <= 1) return;
                 const size_t seg_floats = size_t(segments - 1) * NChunks * kLanes;
                 DSegRe.Reserve(seg_floats), DSegIm.Reserve(seg_floats);
-                plan.SegStateRe = DSegRe.Ptr, plan.SegStateIm = DSegIm.Ptr;
-                LaunchSegmentScan(view, plan, DSegRe.Ptr, DSegIm.Ptr, stream, Counter);
+                p.SegStateRe = DSegRe.Ptr, p.SegStateIm = DSegIm.Ptr;
+                LaunchSegmentScan(view, p, DSegRe.Ptr, DSegIm.Ptr, stream, Counter);
             };
-            const auto speculation_failed = [&]() -> uint32_t {
-                uint32_t failed = 0;
-                ME_CUDA(cudaMemcpyAsync(&failed, DSpeculation.Ptr, sizeof failed, cudaMemcpyDeviceToHost, stream));
+            // OR of the window's speculation words (one per sub-window).
+            const auto speculation_failed = [&](uint32_t words) -> uint32_t {
+                uint32_t failed[64] = {};
+                ME_CUDA(cudaMemcpyAsync(failed, DSpeculation.Ptr, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
                 ME_CUDA(cudaStreamSynchronize(stream));
-                if (failed && std::getenv("ME_RESONATOR_DEBUG")) fprintf(stderr, "[me] speculation failed: code %u (window %u+%u, %u segments)\n", failed, begin, wf, plan.NSegments);
-                return failed;
+                uint32_t any = 0;
+                for (uint32_t i = 0; i < words; ++i) any |= failed[i];
+                if (any && std::getenv("ME_RESONATOR_DEBUG")) fprintf(stderr, "[me] speculation failed: code %u (window %u+%u, %u segments)\n", any, begin, wf, plan.NSegments);
+                return any;
             };
             // A culling decision inside the window (or an increment off the time-block grid): the window is rendered
             // again sequentially in time by the sample loop (still on the GPU).
@@ -647,6 +748,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 plan.NSegments = 1;
                 plan.SegmentFrames = blocks * block_frames;
                 plan.SegStateRe = plan.SegStateIm = nullptr;
+                plan.Speculation = DSpeculation.Ptr;
                 LaunchResonatorKernel(view, plan, Steps, stream, Counter);
             };
             cudaEvent_t k0 = NextEvent(), k1 = NextEvent();
@@ -661,40 +763,83 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 const uint32_t tiles = (wf + TensorTileFrames - 1) / TensorTileFrames;
                 DWalkStates.Reserve(size_t(tiles) * groups * TmStateTileFloats(TensorBlocksPerTile));
                 DGroupMix.Reserve(size_t(mix_rows) * wf);
-                plan.WalkStates = DWalkStates.Ptr;
-                // A bank of few chunk groups cannot fill the SMs with one CTA per group: its walk is split into seeded
-                // segments along time (the scan of the sample loop). A culling decision inside the window invalidates
-                // the seeds; the walk is then repeated sequentially (it is cheap next to the mix).
-                segments = RequestedSegments ? RequestedSegments : (SeededWalkFailed || groups >= 148 ? 1u : std::min<uint32_t>(16, 296 / groups)); // two walk CTAs fit an SM: one wave
-                segments = std::max(1u, std::min(segments, blocks));
-                const uint32_t seg_blocks = (blocks + segments - 1) / segments;
-                segments = (blocks + seg_blocks - 1) / seg_blocks;
-                plan.NSegments = segments;
-                plan.SegmentFrames = seg_blocks * block_frames;
-                ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
-                seed_segments(segments);
-                Timed(1, stream, [&] { LaunchStateWalkKernel(view, plan, stream, Counter); });
-                const uint32_t seeded_segments = segments;
-                if (segments > 1) {
-                    // The sequential repeat, launched right behind the seeded walk and run only if that one raised a flag
-                    // (RenderPlan::OnlyIf): the device decides, the host does not wait to find out.
-                    RenderPlan repeat = plan;
-                    repeat.NSegments = 1;
-                    repeat.SegmentFrames = blocks * block_frames;
-                    repeat.SegStateRe = repeat.SegStateIm = nullptr;
-                    repeat.OnlyIf = 7u;
-                    Timed(1, stream, [&] { LaunchStateWalkKernel(view, repeat, stream, Counter); });
+                // Sub-windows of the pipeline, in tiles: the first ones are short (1, 2, .. tiles) so that the device has work after a
+                // fraction of the host's planning; the rest take SubWindowTiles each.
+                std::vector<uint32_t> sub_begin{0};
+                if (piped) {
+                    for (uint32_t at = 0, size = 1; at < tiles; size = std::min(size + 1, SubWindowTiles)) {
+                        at = std::min(tiles, at + size);
+                        if (at < tiles) sub_begin.push_back(at * TensorTileFrames);
+                    }
                 }
+                const uint32_t subs = uint32_t(sub_begin.size());
+                sub_begin.push_back(wf);
+                if (subs > 64) Fail(ME_BAD_ARG, "launch window of %u sub-windows (at most 64): raise ME_WALK_SUBWINDOW_TILES", subs);
+                ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, 64 * sizeof(uint32_t), stream));
+                const int side_at_begin = Side;
+                if (subs > 1) {
+                    // The window's start state, should the whole window have to be rendered again by the sample loop.
+                    const size_t modes = size_t(NChunks) * kLanes;
+                    DSnapRe.Reserve(modes), DSnapIm.Reserve(modes), DSnapLive.Reserve(NChunks), DSnapRinging.Reserve(std::max(n_obj, 1u));
+                    ME_CUDA(cudaMemcpyAsync(DSnapRe.Ptr, DStateRe[Side].Ptr, modes * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+                    ME_CUDA(cudaMemcpyAsync(DSnapIm.Ptr, DStateIm[Side].Ptr, modes * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+                    ME_CUDA(cudaMemcpyAsync(DSnapLive.Ptr, DChunkLive[Side].Ptr, NChunks, cudaMemcpyDeviceToDevice, stream));
+                    ME_CUDA(cudaMemcpyAsync(DSnapRinging.Ptr, DObjRinging[Side].Ptr, n_obj, cudaMemcpyDeviceToDevice, stream));
+                }
+                bool seeded = false;
+                uint32_t walked_segments = 1; // most segments any sub-window's walk was split into
+                for (uint32_t sub = 0; sub < subs; ++sub) {
+                    const uint32_t sb = begin + sub_begin[sub], sf = sub_begin[sub + 1] - sub_begin[sub];
+                    const uint32_t sub_blocks = (sf + block_frames - 1) / block_frames;
+                    host_begin = Clock::now();
+                    const uint32_t first_new = n;
+                    plan_pulses_before(sb + sf);
+                    const Lists lists = lists_for(sb, sb + sf, first_new);
+                    Stats.host_plan_ms += since(host_begin);
+                    join_pulses();
+                    RenderPlan walk = plan_for(lists, sb, sf, sub_blocks);
+                    walk.Speculation = DSpeculation.Ptr + sub;
+                    walk.WalkStates = DWalkStates.Ptr + size_t((sb - begin) / TensorTileFrames) * groups * TmStateTileFloats(TensorBlocksPerTile);
+                    // A bank of few chunk groups cannot fill the SMs with one CTA per group: its walk is split into seeded
+                    // segments along time (the scan of the sample loop). A culling decision inside the window invalidates
+                    // the seeds; the walk is then repeated sequentially (it is cheap next to the mix).
+                    segments = RequestedSegments ? RequestedSegments : (SeededWalkFailed || groups >= 148 ? 1u : std::min<uint32_t>(16, 296 / groups)); // two walk CTAs fit an SM: one wave
+                    segments = std::max(1u, std::min(segments, sub_blocks));
+                    const uint32_t seg_blocks = (sub_blocks + segments - 1) / segments;
+                    segments = (sub_blocks + seg_blocks - 1) / seg_blocks;
+                    walk.NSegments = segments;
+                    walk.SegmentFrames = seg_blocks * block_frames;
+                    seed_segments(walk, segments);
+                    Timed(1, stream, [&] { LaunchStateWalkKernel(view, walk, stream, Counter); });
+                    if (segments > 1) {
+                        // The sequential repeat, launched right behind the seeded walk and run only if that one raised a flag
+                        // (RenderPlan::OnlyIf): the device decides, the host does not wait to find out.
+                        seeded = true;
+                        RenderPlan repeat = walk;
+                        repeat.NSegments = 1;
+                        repeat.SegmentFrames = sub_blocks * block_frames;
+                        repeat.SegStateRe = repeat.SegStateIm = nullptr;
+                        repeat.OnlyIf = 7u;
+                        Timed(1, stream, [&] { LaunchStateWalkKernel(view, repeat, stream, Counter); });
+                    }
+                    walked_segments = std::max(walked_segments, segments);
+                    if (sub + 1 < subs) {
+                        Side ^= 1;
+                        view = View();
+                    }
+                }
+                plan.Speculation = DSpeculation.Ptr;
+                segments = walked_segments;
                 Timed(2, stream, [&] {
                     LaunchTensorMixKernel({.Groups = groups, .StagesPerRow = stages_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
                 });
                 ++Counter.Launches;
                 // The fixed-order mix goes out before the flags are read: one host round trip per window, behind its last launch.
                 ME_CUDA(cudaEventRecord(k1, stream));
-                LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, pulses, out_dev + begin, stream, Counter);
+                LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, current_pulses(), out_dev + begin, stream, Counter);
                 mixed = true;
-                const uint32_t flags = speculation_failed();
-                if (seeded_segments > 1 && (flags & 7u)) {
+                const uint32_t flags = speculation_failed(subs);
+                if (seeded && (flags & 7u)) {
                     SeededWalkFailed = true;
                     ++Stats.scan_fallbacks;
                     segments = 1;
@@ -703,11 +848,23 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 if (flags & 8u) {
                     tensor_window = false;
                     mixed = false;
+                    if (subs > 1) {
+                        const size_t modes = size_t(NChunks) * kLanes;
+                        Side = side_at_begin;
+                        ME_CUDA(cudaMemcpyAsync(DStateRe[Side].Ptr, DSnapRe.Ptr, modes * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+                        ME_CUDA(cudaMemcpyAsync(DStateIm[Side].Ptr, DSnapIm.Ptr, modes * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+                        ME_CUDA(cudaMemcpyAsync(DChunkLive[Side].Ptr, DSnapLive.Ptr, NChunks, cudaMemcpyDeviceToDevice, stream));
+                        ME_CUDA(cudaMemcpyAsync(DObjRinging[Side].Ptr, DSnapRinging.Ptr, n_obj, cudaMemcpyDeviceToDevice, stream));
+                        view = View();
+                    }
+                    const Lists lists = all_lists(begin, begin + wf);
+                    plan = plan_for(lists, begin, wf, blocks);
                     render_sequentially();
                 } else {
                     ++Stats.tensor_windows;
                 }
             } else {
+                join_pulses();
                 // Segments of the block-parallel scan along time: enough (chunk-CTA x segment) units to even out the
                 // 148 SMs, each a whole number of blocks.
                 segments = RequestedSegments;
@@ -720,10 +877,10 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
                 plan.NSegments = segments;
                 plan.SegmentFrames = seg_blocks * block_frames;
                 if (segments > 1) {
-                    ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, sizeof(uint32_t), stream));
-                    seed_segments(segments);
+                    ME_CUDA(cudaMemsetAsync(DSpeculation.Ptr, 0, 64 * sizeof(uint32_t), stream));
+                    seed_segments(plan, segments);
                     LaunchResonatorKernel(view, plan, Steps, stream, Counter);
-                    if (speculation_failed()) {
+                    if (speculation_failed(1)) {
                         render_sequentially();
                         segments = 1;
                     }
@@ -735,14 +892,18 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<
             Stats.time_segments = std::max(Stats.time_segments, segments);
             Stats.partial_rows = tensor_window ? mix_rows : rows;
             if (!mixed) {
-                if (tensor_window) LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, pulses, out_dev + begin, stream, Counter);
-                else LaunchMixKernel(DPartial.Ptr, rows, plan, pulses, out_dev + begin, stream, Counter);
+                if (tensor_window) LaunchMixKernel(DGroupMix.Ptr, mix_rows, plan, current_pulses(), out_dev + begin, stream, Counter);
+                else LaunchMixKernel(DPartial.Ptr, rows, plan, current_pulses(), out_dev + begin, stream, Counter);
             }
             Side ^= 1;
             view = View();
         }
     }
-    if (any_click) LaunchClickKernel(d_impacts, d_tails, n, out_dev, frames, stream, Counter);
+    // Whatever the windows did not reach (nothing, unless the span had no chunks to render).
+    plan_pulses_before(frames);
+    join_pulses();
+    if (any_click) LaunchClickKernel(impacts.Dev, tails.Dev, n, out_dev, frames, stream, Counter);
+    Plan.Seal(stream);
     for (uint32_t o = 0; o < n_obj; ++o) Stats.mode_samples += uint64_t(TunedModeCount[o]) * frames;
 }
 
@@ -755,6 +916,15 @@ cudaEvent_t Bank::NextEvent() {
     return EventPool[EventsUsed++];
 }
 
+cudaEvent_t Bank::NextJoin() {
+    if (JoinsUsed == JoinPool.size()) {
+        cudaEvent_t e;
+        ME_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        JoinPool.push_back(e);
+    }
+    return JoinPool[JoinsUsed++];
+}
+
 void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_frames, uint32_t n_events, uint64_t total_frames, uint32_t block_frames, float *out, bool out_is_device, cudaStream_t stream, bool use_own_stream) {
     RequireInstalled();
     if (total_frames == 0) return;
@@ -762,12 +932,15 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
     if (block_frames == 0) Fail(ME_BAD_ARG, "block_frames must be positive");
     if (total_frames >= (uint64_t(1) << 31)) Fail(ME_BAD_ARG, "total_frames must be below 2^31 per call");
     if (n_events && (!events || !event_frames)) Fail(ME_BAD_ARG, "null event arrays");
-    for (uint32_t i = 0; i < n_events; ++i) {
-        if (event_frames[i] % block_frames != 0 || event_frames[i] >= total_frames) Fail(ME_BAD_ARG, "event %u: frame %llu is not a block boundary inside the timeline", i, (unsigned long long)event_frames[i]);
-        if (i && event_frames[i] < event_frames[i - 1]) Fail(ME_BAD_ARG, "event frames must be ascending");
-    }
     ME_CUDA(cudaSetDevice(Device));
-    if (use_own_stream) stream = OwnStream;
+    const cudaStream_t caller = use_own_stream ? nullptr : stream;
+    JoinsUsed = 0;
+    if (!use_own_stream) {
+        const cudaEvent_t fork = NextJoin();
+        ME_CUDA(cudaEventRecord(fork, caller));
+        ME_CUDA(cudaStreamWaitEvent(OwnStream, fork, 0));
+    }
+    stream = OwnStream;
     if (TuningDirty) {
         UploadTuning(stream);
         for (const auto o : RetunedObjects) ResetObjectOnDevice(o, false, stream);
@@ -801,9 +974,30 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
         EventRead.store(read, std::memory_order_release);
     }
 
-    // A Silence event rewrites resonator state, so the timeline is rendered in spans cut at silences.
+    // What the impacts of any one span can need of the plan and the pulse buffers, from the events alone (a span's impacts are
+    // events of the timeline or remainders of earlier ones): the buffers are sized before the first impact is admitted, because
+    // the kernels of early impacts are already running while later ones are still being planned.
     const uint32_t total = uint32_t(total_frames);
     const uint32_t n_obj = ObjectCount();
+    SpanBounds bounds;
+    const auto bound = [&](uint32_t object, uint64_t samples_left) {
+        if (object >= n_obj) return;
+        const uint64_t len = std::min<uint64_t>(samples_left, total);
+        const uint32_t stride = ObjStride[object], warps = (stride / kLanes + 31) / 32;
+        ++bounds.Impacts, bounds.Force += len, bounds.Delta += stride, bounds.Warps += warps, bounds.Rows += warps * std::min<uint64_t>(len + kTmBlock, total);
+    };
+    for (const auto &im : Impacts) bound(im.Object, im.SamplesLeft);
+    for (const auto &e : ring)
+        if (e.kind == 0 && e.pulse_step > 0) bound(e.object, PulseSamples(e.pulse_step));
+    for (uint32_t i = 0; i < n_events; ++i) { // (one pass: the events' validity and their bounds)
+        if (event_frames[i] % block_frames != 0 || event_frames[i] >= total_frames) Fail(ME_BAD_ARG, "event %u: frame %llu is not a block boundary inside the timeline", i, (unsigned long long)event_frames[i]);
+        if (i && event_frames[i] < event_frames[i - 1]) Fail(ME_BAD_ARG, "event frames must be ascending");
+        if (events[i].kind == 0 && events[i].pulse_step > 0) bound(events[i].object, PulseSamples(events[i].pulse_step));
+    }
+
+    if (std::max({bounds.Force, bounds.Delta, bounds.Rows, bounds.Warps}) >= (uint64_t(1) << 32)) Fail(ME_BAD_ARG, "impact buffers exceed 2^32 entries in one call");
+
+    // A Silence event rewrites resonator state, so the timeline is rendered in spans cut at silences.
     uint32_t next_event = 0;
     uint32_t span_begin = 0;
     std::vector<ScheduledImpact> scheduled;
@@ -821,7 +1015,7 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
         // in frame order, so a count per retirement block and a cursor replace a heap of retirement frames.
         std::vector<uint32_t> retire_in_block(size_t(span_frames) / block_frames + 2, 0);
         uint32_t retire_cursor = 0, in_flight = 0;
-        scheduled.reserve(Impacts.size() + (n_events - next_event) + ring.size());
+        scheduled.reserve(bounds.Impacts);
         const auto note_retirement = [&](const ScheduledImpact &s) {
             ++in_flight;
             if (!s.Survives) ++retire_in_block[(uint64_t(s.End) + block_frames - 1) / block_frames];
@@ -832,8 +1026,6 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
             scheduled.push_back(s);
             note_retirement(s);
         };
-        for (const auto &im : Impacts) admit(im, 0);
-        Impacts.clear();
         const auto apply = [&](const MeModalEvent &e, uint32_t start) {
             if (e.object >= n_obj) return; // DrainEvents :71
             if (e.kind == 0) {
@@ -847,7 +1039,7 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
                 if (in_flight >= MaxImpacts) return;
                 admit(MakeImpact(e), start);
             } else if (e.kind == 1) {
-                // Only ever at the first frame of a span: nothing of this span has been rendered yet.
+                // Only ever at the first frame of a span: nothing of this span has been rendered (or planned) yet.
                 const size_t before = scheduled.size();
                 std::erase_if(scheduled, [&](const ScheduledImpact &s) { return s.AtStart.Object == e.object; });
                 if (scheduled.size() != before) {
@@ -858,17 +1050,29 @@ void Bank::RenderTimeline(const MeModalEvent *events, const uint64_t *event_fram
                 ResetObjectOnDevice(e.object, true, stream);
             }
         };
-        if (span_begin == 0)
-            for (const auto &e : ring) apply(e, 0);
-        for (; next_event < n_events && event_frames[next_event] < span_end; ++next_event) apply(events[next_event], uint32_t(event_frames[next_event]) - span_begin);
+        // The span's impacts are admitted on demand, in start order: RenderSpan asks for those starting before a frame when it is
+        // about to plan them, so the kernels of the first stretch run while the host is still admitting the next.
+        bool carried_in = false;
+        const auto admit_before = [&](uint32_t limit) {
+            if (!carried_in) {
+                carried_in = true;
+                for (const auto &im : Impacts) admit(im, 0);
+                Impacts.clear();
+                if (span_begin == 0)
+                    for (const auto &e : ring) apply(e, 0);
+            }
+            const uint64_t until = uint64_t(span_begin) + std::min(limit, span_frames);
+            for (; next_event < n_events && event_frames[next_event] < until; ++next_event) apply(events[next_event], uint32_t(event_frames[next_event]) - span_begin);
+        };
 
-        RenderSpan(span_frames, block_frames, scheduled, out_dev + span_begin, stream);
+        RenderSpan(span_frames, block_frames, scheduled, admit_before, bounds, out_dev + span_begin, stream);
         for (const auto &s : scheduled)
             if (s.Survives) Impacts.push_back(s.AtEnd);
         span_begin = span_end;
     }
     ME_CUDA(cudaEventRecord(EvEnd, stream));
     Stats.kernel_launches = Counter.Launches;
+    if (!use_own_stream) ME_CUDA(cudaStreamWaitEvent(caller, EvEnd, 0)); // the caller's stream continues behind the render
 
     if (!out_is_device) {
         POut.Reserve(total_frames);
@@ -886,9 +1090,17 @@ const MeRenderStats &Bank::LastStats() {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, EvBegin, EvEnd) == cudaSuccess) Stats.total_device_ms = ms;
             float kernel[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool trace = std::getenv("ME_RENDER_TRACE") != nullptr; // the call's timeline: every bracketed launch against the call's start
             for (uint32_t i = 0; i + 1 < EventsUsed; i += 2) {
                 if (cudaEventElapsedTime(&ms, EventPool[i], EventPool[i + 1]) == cudaSuccess) kernel[EventKind[i / 2]] += ms;
+                if (trace) {
+                    float t0 = 0.f, t1 = 0.f;
+                    cudaEventElapsedTime(&t0, EvBegin, EventPool[i]), cudaEventElapsedTime(&t1, EvBegin, EventPool[i + 1]);
+                    static const char *names[4] = {"window", "walk", "tensor mix", "force + pulses"};
+                    fprintf(stderr, "[me trace] %-14s %8.3f .. %8.3f ms\n", names[EventKind[i / 2]], t0, t1);
+                }
             }
+            if (trace) fprintf(stderr, "[me trace] call            0.000 .. %8.3f ms (host planning %.3f ms)\n", Stats.total_device_ms, Stats.host_plan_ms);
             Stats.resonator_kernel_ms = kernel[0];
             Stats.walk_kernel_ms = kernel[1];
             Stats.tensor_mix_kernel_ms = kernel[2];

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <atomic>
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 namespace me {
@@ -62,6 +63,29 @@ struct PlanArena {
     template<typename T>
     const T *Stage(const std::vector<T> &v) { return Stage(v.data(), v.size()); }
     static size_t Room(size_t bytes) { return bytes + 256; }
+    // A region filled in place, piece by piece, and copied with FlushRange (the arrays a span's pulse batches append to). Regions
+    // are reserved right after Begin, before anything is staged; SkipRegions then moves the flush cursor past them.
+    template<typename T>
+    struct Region {
+        T *Host;
+        const T *Dev;
+    };
+    template<typename T>
+    Region<T> Reserve(size_t count) {
+        const size_t at = (Cursor + 255) & ~size_t(255), bytes = count * sizeof(T);
+        if (at + bytes > Host.Capacity) Fail(ME_CUDA_ERROR, "internal: plan arena overflow (%zu + %zu of %zu bytes)", at, bytes, Host.Capacity);
+        Cursor = at + bytes;
+        return {reinterpret_cast<T *>(Host.Ptr + at), reinterpret_cast<const T *>(Dev.Ptr + at)};
+    }
+    void SkipRegions() { Flushed = Cursor; }
+    template<typename T>
+    void FlushRange(const Region<T> &region, size_t first, size_t count, cudaStream_t stream) {
+        if (count == 0) return;
+        const size_t at = size_t(reinterpret_cast<const uint8_t *>(region.Host + first) - Host.Ptr);
+        ME_CUDA(cudaMemcpyAsync(Dev.Ptr + at, Host.Ptr + at, count * sizeof(T), cudaMemcpyHostToDevice, stream));
+    }
+    // Every copy of this plan was issued on `stream` or on streams it has since waited for.
+    void Seal(cudaStream_t stream) { ME_CUDA(cudaEventRecord(Copied, stream)); }
     // Everything staged since the last flush, in one copy.
     void Flush(cudaStream_t stream) {
         if (Cursor > Flushed) ME_CUDA(cudaMemcpyAsync(Dev.Ptr + Flushed, Host.Ptr + Flushed, Cursor - Flushed, cudaMemcpyHostToDevice, stream));
@@ -106,8 +130,15 @@ private:
     void RequireInstalled() const;
     void UploadTuning(cudaStream_t);
     void ResetObjectOnDevice(uint32_t object, bool clear_state, cudaStream_t);
-    void RenderSpan(uint32_t frames, uint32_t block_frames, const std::vector<ScheduledImpact> &, float *out_dev, cudaStream_t);
+    // Upper bounds of what a span's impacts need in the plan and in the pulse buffers (sized before the first impact is admitted).
+    struct SpanBounds {
+        uint64_t Impacts{0}, Force{0}, Delta{0}, Rows{0}, Warps{0};
+    };
+    // `admit_before(limit)` appends to the schedule, in start order, every impact of the span that starts before frame `limit`
+    // (relative to the span) and has not been admitted yet.
+    void RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<ScheduledImpact> &, const std::function<void(uint32_t)> &admit_before, const SpanBounds &, float *out_dev, cudaStream_t);
     cudaEvent_t NextEvent();
+    cudaEvent_t NextJoin();
     // Brackets `launch` with an event pair of the given kind.
     template<typename F>
     void Timed(uint8_t kind, cudaStream_t stream, F &&launch) {
@@ -122,6 +153,10 @@ private:
     float SampleRate;
     int Device;
     cudaStream_t OwnStream{nullptr};
+    cudaStream_t PulseStream{nullptr}; // tensor-core form: the force + pulse kernels of a sub-window run beside the state walk of the one before
+    std::vector<cudaEvent_t> JoinPool; // untimed events ordering the two streams
+    uint32_t JoinsUsed{0};
+    uint32_t SubWindowTiles{2};        // tiles per sub-window of the pulse / walk pipeline (0: one batch per launch window, on the render stream)
     cudaEvent_t EvBegin{nullptr}, EvEnd{nullptr};
     std::vector<cudaEvent_t> EventPool; // begin/end pairs around every resonator kernel launch of the last call
     std::vector<uint8_t> EventKind;     // per pair: 0 the whole resonator stage of a window, 1 the walk kernel, 2 the tcgen05 mix kernel, 3 force + pulse kernels
@@ -161,13 +196,12 @@ private:
     DeviceBuffer<uint8_t> DObjCull, DChunkLive[2], DObjRinging[2];
     DeviceBuffer<uint32_t> DSpeculation;
     DeviceBuffer<float> DForce, DPartial, DOut, DSegRe, DSegIm, DDeltaRe, DDeltaIm, DPulseRows;
+    DeviceBuffer<float> DSnapRe, DSnapIm; // state at the start of a launch window walked in several sub-windows (for the sequential fallback)
+    DeviceBuffer<uint8_t> DSnapLive, DSnapRinging;
     DeviceBuffer<double> DLogRho, DTheta;
     PinnedBuffer<float> POut;
 
     // Per-call scratch.
-    std::vector<DevImpact> CallImpacts;
-    std::vector<DevImpactTail> CallTails;
-    std::vector<PulseWarp> CallPulseWarps;
     std::vector<uint32_t> CallInjectPtr, CallInjectFrame, CallInjectDelta, CallExcitePtr, CallExciteBegin, CallExciteEnd;
     std::vector<float> MixGain, EnergyScale;
 

@@ -254,8 +254,9 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
     Chunk w;
     float2 jump_re[4], jump_im[4];       // Walk: float(c^kTmBlock)
     float2 jump_lo_re[4], jump_lo_im[4]; // Walk: c^kTmBlock - float(c^kTmBlock): the jump is applied as hi + lo (see MakeDrift for why)
+    float2 jump_nim[4], jump_lo_nim[4];  // Walk: the imaginary parts negated, so that every product of the jump is a packed FFMA2
 #pragma unroll
-    for (int i = 0; i < 4; ++i) jump_re[i] = jump_im[i] = jump_lo_re[i] = jump_lo_im[i] = float2{0.f, 0.f};
+    for (int i = 0; i < 4; ++i) jump_re[i] = jump_im[i] = jump_lo_re[i] = jump_lo_im[i] = jump_nim[i] = jump_lo_nim[i] = float2{0.f, 0.f};
     // Sample loop: this thread's drift terms e (16 floats), [component][thread], behind the transpose tiles.
     float *drift = transposed_storage + kWarpsPerBlock * kTile * kRowPad + threadIdx.x;
     uint32_t jumps = 0; // K-sample jumps since the drift was last taken out
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                 jump_re[i] = {float(rx), float(ry)}, jump_im[i] = {float(ix), float(iy)};
                 jump_lo_re[i] = {float(rx - double(jump_re[i].x)), float(ry - double(jump_re[i].y))};
                 jump_lo_im[i] = {float(ix - double(jump_im[i].x)), float(iy - double(jump_im[i].y))};
+                jump_nim[i] = {-jump_im[i].x, -jump_im[i].y}, jump_lo_nim[i] = {-jump_lo_im[i].x, -jump_lo_im[i].y};
             }
         } else {
             MakeDrift<K>(cre, cim, p, drift);
@@ -344,6 +346,22 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
     float2 *column = reinterpret_cast<float2 *>(rows) + lane;
     float *partial = plan.Partial + size_t(blockIdx.x * kWarpsPerBlock + warp) * plan.Frames;
 
+    // Walk: row-major states (tensor_mix.cuh). This chunk owns 16 consecutive reduction elements of every time-block row, so the
+    // CTA's 256 chunk-threads fill one 16 KB row per step. A warp's 32 chunks own 2 KB of the row; they pass through a swizzled
+    // shared-memory transpose so that every store instruction covers 512 contiguous bytes. The row pointer is stepped, not
+    // recomputed: every step of the walk starts on a time-block boundary and fills exactly one row (the last one may be ragged).
+    float4 *walk_at = nullptr;
+    uint32_t walk_row = 0;
+    size_t walk_tile_skip = 0;
+    if constexpr (Walk) {
+        const uint32_t nb = plan.WalkBlocksPerTile;
+        const uint32_t block_index = seg_begin / kTmBlock;
+        const size_t tile_stride = size_t(gridDim.x) * TmStateTileFloats(nb) / 4;
+        walk_row = block_index % nb;
+        walk_at = reinterpret_cast<float4 *>(plan.WalkStates + size_t(blockIdx.x) * TmStateTileFloats(nb)) + warp * 128 + lane + size_t(block_index / nb) * tile_stride + size_t(walk_row) * (kTmGroupK / 4);
+        walk_tile_skip = tile_stride - size_t(nb) * (kTmGroupK / 4);
+    }
+
     uint32_t pos = seg_begin;
     while (pos < seg_end) {
         // One RenderModal block (or what is left of it inside this segment).
@@ -372,14 +390,8 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         const bool warp_renders = __ballot_sync(0xFFFFFFFFu, rendered) != 0;
 
         if constexpr (Walk) {
-            // Row-major states (tensor_mix.cuh): this chunk owns 16 consecutive reduction elements of every time-block row,
-            // so the CTA's 256 chunk-threads fill one 16 KB row per step, coalesced.
             // With one segment the walk is sequential in time over the whole window and culling needs no speculation; small
-            // banks (few chunk groups) are walked in several seeded segments like the sample loop. A warp's 32 chunks own 2 KB of the row; they pass through a swizzled shared-memory transpose so that every
-            // store instruction covers 512 contiguous bytes.
-            const uint32_t nb = plan.WalkBlocksPerTile;
-            float4 *rows = reinterpret_cast<float4 *>(plan.WalkStates + size_t(blockIdx.x) * TmStateTileFloats(nb)) + warp * 128 + lane;
-            const size_t tile_stride = size_t(gridDim.x) * TmStateTileFloats(nb) / 4;
+            // banks (few chunk groups) are walked in several seeded segments like the sample loop.
             float4 *exchange = reinterpret_cast<float4 *>(transposed_storage) + warp * 128;
             const uint32_t put = lane * 4, put_swizzle = (lane >> 1) & 3;
             const bool audible = rendered && out_scale != 0.f;
@@ -391,27 +403,34 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                     // Increments land on time-block boundaries in a span planned for this form (DevImpact::RenderLen).
                     if (inj_frame - t_abs < step) atomicOr(plan.Speculation, 8u);
                 }
-                const uint32_t block_index = t / kTmBlock;
-                float4 *at = rows + size_t(block_index / nb) * tile_stride + size_t(block_index % nb) * (kTmGroupK / 4);
+                // (Im, Im, Re, Re) of the chunk's mode pairs: reduction elements 4p .. 4p+3 (tensor_mix.cuh; PowerTableKernel
+                // writes the powers in the same order). The pairs are the registers the packed FP32 instructions work on.
+                if (audible) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) // (Im, Re) of the chunk's mode pairs: reduction elements 2m, 2m+1 (tensor_mix.cuh)
-                    exchange[put + (i ^ put_swizzle)] = audible ? float4{w.Im[i].x, w.Re[i].x, w.Im[i].y, w.Re[i].y} : float4{0.f, 0.f, 0.f, 0.f};
+                    for (int i = 0; i < 4; ++i) exchange[put + (i ^ put_swizzle)] = float4{w.Im[i].x, w.Im[i].y, w.Re[i].x, w.Re[i].y};
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) exchange[put + (i ^ put_swizzle)] = float4{0.f, 0.f, 0.f, 0.f};
+                }
                 __syncwarp();
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const uint32_t from = 8 * j + (lane >> 2); // the chunk-lane whose piece lands at position 32*j + lane
-                    at[32 * j] = exchange[from * 4 + ((lane & 3) ^ ((from >> 1) & 3))];
+                    walk_at[32 * j] = exchange[from * 4 + ((lane & 3) ^ ((from >> 1) & 3))];
                 }
                 __syncwarp();
+                // next row of the tile, or the first row of the next tile
+                walk_at += kTmGroupK / 4;
+                if (++walk_row == plan.WalkBlocksPerTile) walk_row = 0, walk_at += walk_tile_skip;
                 if (rendered) {
                     if (step == kTmBlock) {
                         // w <- (hi + lo) w, the small products first
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float lrx = fmaf(-w.Im[i].x, jump_lo_im[i].x, w.Re[i].x * jump_lo_re[i].x), lry = fmaf(-w.Im[i].y, jump_lo_im[i].y, w.Re[i].y * jump_lo_re[i].y);
-                            const float lix = fmaf(w.Re[i].x, jump_lo_im[i].x, w.Im[i].x * jump_lo_re[i].x), liy = fmaf(w.Re[i].y, jump_lo_im[i].y, w.Im[i].y * jump_lo_re[i].y);
-                            const float2 re = {fmaf(-w.Im[i].x, jump_im[i].x, fmaf(w.Re[i].x, jump_re[i].x, lrx)), fmaf(-w.Im[i].y, jump_im[i].y, fmaf(w.Re[i].y, jump_re[i].y, lry))};
-                            w.Im[i] = {fmaf(w.Re[i].x, jump_im[i].x, fmaf(w.Im[i].x, jump_re[i].x, lix)), fmaf(w.Re[i].y, jump_im[i].y, fmaf(w.Im[i].y, jump_re[i].y, liy))};
+                            const float2 lr = Fma2(w.Im[i], jump_lo_nim[i], Mul2(w.Re[i], jump_lo_re[i]));
+                            const float2 li = Fma2(w.Re[i], jump_lo_im[i], Mul2(w.Im[i], jump_lo_re[i]));
+                            const float2 re = Fma2(w.Im[i], jump_nim[i], Fma2(w.Re[i], jump_re[i], lr));
+                            w.Im[i] = Fma2(w.Re[i], jump_im[i], Fma2(w.Im[i], jump_re[i], li));
                             w.Re[i] = re;
                         }
                     } else {
@@ -764,7 +783,7 @@ __global__ void __launch_bounds__(128) PowerTableKernel(const BankView b, float 
     uint8_t *tail16 = value16 + kTmPowerBf16Bytes;
     double rx = ax, ix = bx, ry = ay, iy = by;
     for (uint32_t j = 0; j < kTmBlock; ++j) {
-        const float4 v = {float(rx), float(ix), float(ry), float(iy)};
+        const float4 v = {float(rx), float(ry), float(ix), float(iy)}; // against the state's (Im, Im, Re, Re) of the pair
         const float4 h = {Tf32Head(v.x), Tf32Head(v.y), Tf32Head(v.z), Tf32Head(v.w)};
         const uint32_t row = (j >> 3) * 128 + (j & 7) * 16;
         *reinterpret_cast<float4 *>(head + row) = h;
@@ -829,9 +848,24 @@ void LaunchForceKernel(const DevImpact *impacts, const DevImpactTail *tails, uin
     ++counter.Launches;
 }
 
+// Dynamic shared memory that leaves room for exactly `per_sm` CTAs of a kernel on an SM (0: no limit). The pulse kernels run
+// beside the state walk: how many CTAs of each an SM takes decides how much of one hides behind the other.
+static size_t OccupancyPad(const char *env, int fallback, size_t static_bytes) {
+    const char *v = std::getenv(env);
+    const int per_sm = v ? std::atoi(v) : fallback;
+    if (per_sm <= 0) return 0;
+    const size_t per_cta = (size_t(227) << 10) / size_t(per_sm + 1) + 1024; // more than a (per_sm + 1)-th of the SM's 227 KB
+    return per_cta > static_bytes ? std::min<size_t>(per_cta - static_bytes, (size_t(227) << 10) - static_bytes) : 0;
+}
+
 void LaunchPulseKernel(const BankView &bank, const PulsePlan &plan, cudaStream_t stream, LaunchCounter &counter) {
     if (plan.NPulseWarps == 0) return;
-    PulseKernel<<<(plan.NPulseWarps + kPulseWarps - 1) / kPulseWarps, kPulseWarps * 32, 0, stream>>>(bank, plan);
+    static const size_t pad = [] {
+        const size_t bytes = OccupancyPad("ME_PULSE_CTAS_PER_SM", 0, sizeof(float) * kPulseWarps * kTile * kRowPad);
+        if (bytes) ME_CUDA(cudaFuncSetAttribute(PulseKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+        return bytes;
+    }();
+    PulseKernel<<<(plan.NPulseWarps + kPulseWarps - 1) / kPulseWarps, kPulseWarps * 32, pad, stream>>>(bank, plan);
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
 }
@@ -874,7 +908,13 @@ void LaunchResonatorKernel(const BankView &bank, const RenderPlan &plan, int ste
 void LaunchStateWalkKernel(const BankView &bank, const RenderPlan &plan, cudaStream_t stream, LaunchCounter &counter) {
     if (bank.NChunks == 0 || plan.Frames == 0) return;
     const dim3 grid(bank.NChunks / kBlockThreads, plan.NSegments);
-    ResonatorKernel<1, 2, true><<<grid, kBlockThreads, kWarpsPerBlock * 128 * sizeof(float4), stream>>>(bank, plan);
+    static const size_t smem = [] {
+        const size_t used = kWarpsPerBlock * 128 * sizeof(float4), fixed = kBlockThreads * 5;
+        const size_t bytes = used + OccupancyPad("ME_WALK_CTAS_PER_SM", 0, used + fixed);
+        if (bytes > used) ME_CUDA(cudaFuncSetAttribute(ResonatorKernel<1, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+        return bytes;
+    }();
+    ResonatorKernel<1, 2, true><<<grid, kBlockThreads, smem, stream>>>(bank, plan);
     ME_CUDA(cudaGetLastError());
     ++counter.Launches;
 }
