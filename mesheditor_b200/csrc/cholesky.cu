@@ -796,7 +796,9 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     std::vector<float> xyz;
     fem.CopyFullPattern(rowptr, col);
     fem.CopyNodeCoords(xyz);
-    Sym = Analyse(fem.NodeCount, rowptr.data(), col.data(), xyz.data(), opt);
+    // The solve schedules keep being built on a host thread while the structures below are uploaded and (in the caller) the numeric
+    // factorisation runs: UploadSchedules, at the first solve, waits for them.
+    AnalyseInto(Sym, fem.NodeCount, rowptr.data(), col.data(), xyz.data(), opt, true);
     if (Sym.MaxPanelColumns > 128) Fail(ME_BAD_ARG, "internal: panel of %u columns", Sym.MaxPanelColumns);
     auto s = fem.Stream;
     DSuperFirst.Upload(Sym.SuperFirst, s);
@@ -813,9 +815,6 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     DInvOffset.Upload(Sym.InvOffset, s);
     DPanelTiles.Upload(Sym.PanelTiles, s);
     DUpdateTiles.Upload(Sym.UpdateTiles, s);
-    DFwdTasks.Upload(Sym.FwdTasks, s);
-    DFwdLinks.Upload(Sym.FwdLinks, s);
-    DBwdTasks.Upload(Sym.BwdTasks, s);
     if (Sym.Rows.size() >= (uint64_t(1) << 32)) Fail(ME_BAD_ARG, "mesh too large: supernodal row lists exceed 32-bit indexing");
     L.Reserve(Sym.FactorNonZeros);
     Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
@@ -825,11 +824,6 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     Work2.Reserve(fem.N);
     DFail.Reserve(1);
     DCounters.Reserve(size_t(4) * Sym.NumSuper + 2);
-    DWideFwdTasks.Upload(Sym.WideFwdTasks, s);
-    DWideBwdTasks.Upload(Sym.WideBwdTasks, s);
-    DWideFwdLinks.Upload(Sym.WideFwdLinks, s);
-    DWideBwdLinks.Upload(Sym.WideBwdLinks, s);
-    DWideBwdLinkNeed.Upload(Sym.WideBwdLinkNeed, s);
     {
         int device = 0, sms = 0, fwd = 0, bwd = 0;
         ME_CUDA(cudaGetDevice(&device));
@@ -852,6 +846,21 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     Stats.FactorFlops = Sym.FactorFlops;
     Stats.Supernodes = Sym.NumSuper;
     Stats.Levels = Sym.NumLevels;
+}
+
+void SparseCholesky::UploadSchedules() {
+    if (SchedulesUploaded) return;
+    Sym.WaitSchedules();
+    auto s = Fem.Stream;
+    DFwdTasks.Upload(Sym.FwdTasks, s);
+    DFwdLinks.Upload(Sym.FwdLinks, s);
+    DBwdTasks.Upload(Sym.BwdTasks, s);
+    DWideFwdTasks.Upload(Sym.WideFwdTasks, s);
+    DWideBwdTasks.Upload(Sym.WideBwdTasks, s);
+    DWideFwdLinks.Upload(Sym.WideFwdLinks, s);
+    DWideBwdLinks.Upload(Sym.WideBwdLinks, s);
+    DWideBwdLinkNeed.Upload(Sym.WideBwdLinkNeed, s);
+    SchedulesUploaded = true;
 }
 
 SparseCholesky::~SparseCholesky() {
@@ -902,6 +911,7 @@ void SparseCholesky::Factorize(double sigma) {
 void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     if (!Factored) Fail(ME_BAD_ARG, "Solve before Factorize");
     ME_CUDA(cudaSetDevice(Fem.Device));
+    UploadSchedules();
     auto s = Fem.Stream;
     const uint32_t n = Fem.N, ns = Sym.NumSuper;
     FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};

@@ -57,6 +57,8 @@ private:
     DeviceBuffer<int> DFail;
     cudaEvent_t Ev[4]{};
     bool Factored{false};
+    bool SchedulesUploaded{false};
+    void UploadSchedules(); // waits for the background construction of the solve schedules (symbolic.h) and uploads them
     uint32_t SolvesSinceCheck{0};
 };
 

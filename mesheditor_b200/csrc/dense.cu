@@ -238,6 +238,69 @@ __global__ void GramNarrowFinalKernel(const double *__restrict__ partial, uint32
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) out[col + size_t(w) * ldo] = v;
 }
+
+// The QL rotation history applied to one warp's 32 columns of the transposed eigenvector matrix (hosteig.cpp holds the host
+// form). The chain is sequential in the rotations (tens of thousands of them), so everything off the chain is taken out of it:
+// the records arrive in shared memory by bulk asynchronous copies two batches ahead (the lanes then read a record from one
+// address, a broadcast whose address does not depend on the arithmetic), and since a sweep of the QL iteration walks down the
+// rows - rotation (i, i+1) is followed by (i-1, i) - row i is carried in a register between the two: one row loaded and one
+// stored per rotation.
+constexpr uint32_t kRotationBatch = 512; // records per staged batch (12 KB)
+__global__ void __launch_bounds__(32) ApplyRotationsKernel(double *__restrict__ zt, uint32_t m, const QlRotation *__restrict__ rotations, size_t count) {
+    extern __shared__ __align__(16) double columns[]; // [m][32], then two batches of records
+    QlRotation *staged = reinterpret_cast<QlRotation *>(columns + size_t(m) * 32);
+    const uint32_t lane = threadIdx.x, col = blockIdx.x * 32 + lane;
+    const bool valid = col < m;
+    const size_t batches = (count + kRotationBatch - 1) / kRotationBatch;
+    // 16-byte pieces of batch `b` into buffer b & 1 (a record is 24 bytes: 3 pieces per 2 records; the list is padded to whole batches)
+    const auto stage = [&](size_t b) {
+        if (b < batches) {
+            const char *src = reinterpret_cast<const char *>(rotations + b * kRotationBatch);
+            const uint32_t dst = uint32_t(__cvta_generic_to_shared(staged + (b & 1) * kRotationBatch));
+            for (uint32_t piece = lane; piece < kRotationBatch * sizeof(QlRotation) / 16; piece += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + piece * 16), "l"(src + size_t(piece) * 16));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    stage(0);
+    stage(1);
+    for (uint32_t r = 0; r < m; ++r) columns[r * 32 + lane] = valid ? zt[size_t(r) * m + col] : 0.0;
+    uint32_t held_row = 0xFFFFFFFFu; // the row whose current value sits in `held` instead of shared memory
+    double held = 0.0;
+    for (size_t b = 0; b < batches; ++b) {
+        asm volatile("cp.async.wait_group 1;");
+        __syncwarp();
+        const QlRotation *batch = staged + (b & 1) * kRotationBatch;
+        const uint32_t in_batch = uint32_t(min(size_t(kRotationBatch), count - b * kRotationBatch));
+#pragma unroll 4
+        for (uint32_t i = 0; i < in_batch; ++i) {
+            const double c = batch[i].C, s = batch[i].S;
+            const uint32_t row = batch[i].Row;
+            double upper; // row + 1
+            if (held_row == row + 1) {
+                upper = held;
+            } else {
+                if (held_row != 0xFFFFFFFFu) columns[held_row * 32 + lane] = held;
+                upper = columns[(row + 1) * 32 + lane];
+            }
+            const double lower = columns[row * 32 + lane];
+            columns[(row + 1) * 32 + lane] = s * lower + c * upper;
+            held = c * lower - s * upper;
+            held_row = row;
+        }
+        __syncwarp();
+        stage(b + 2);
+    }
+    if (held_row != 0xFFFFFFFFu) columns[held_row * 32 + lane] = held;
+    if (valid)
+        for (uint32_t r = 0; r < m; ++r) zt[size_t(r) * m + col] = columns[r * 32 + lane];
+}
+
+__global__ void GatherRowsKernel(const double *__restrict__ zt, uint32_t m, const uint32_t *__restrict__ rows, uint32_t k, double *__restrict__ out) {
+    const uint32_t j = blockIdx.x;
+    const double *src = zt + size_t(rows[j]) * m;
+    for (uint32_t r = threadIdx.x; r < m; r += blockDim.x) out[r + size_t(j) * m] = src[r];
+}
 } // namespace
 
 void GemvT(DenseWorkspace &ws, const double *V, size_t n, uint32_t cols, const double *x, double *out, cudaStream_t s) {
@@ -284,6 +347,27 @@ void Gram(DenseWorkspace &ws, const double *X, size_t n, uint32_t a, const doubl
         GramNarrowFinalKernel<<<(a * kNarrow * 32 + 255) / 256, 256, 0, s>>>(ws.GramPartial.Ptr, a, cw, a_pad, out + size_t(c0) * ldo, ldo, splits);
         ws.Launches += 2;
     }
+}
+
+void ApplyRotations(double *zt, uint32_t m, const QlRotation *rotations, size_t count, cudaStream_t s, uint32_t &launches) {
+    if (m == 0 || count == 0) return;
+    if (m > kMaxDeviceRotationOrder) Fail(ME_BAD_ARG, "internal: ApplyRotations takes matrices up to order %u (got %u)", kMaxDeviceRotationOrder, m);
+    const size_t smem = size_t(m) * 32 * sizeof(double) + 2 * kRotationBatch * sizeof(QlRotation);
+    static size_t configured = 0;
+    if (smem > configured) {
+        ME_CUDA(cudaFuncSetAttribute(ApplyRotationsKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    ApplyRotationsKernel<<<(m + 31) / 32, 32, smem, s>>>(zt, m, rotations, count);
+    ME_CUDA(cudaGetLastError());
+    ++launches;
+}
+
+void GatherRows(const double *zt, uint32_t m, const uint32_t *rows, uint32_t k, double *out, cudaStream_t s, uint32_t &launches) {
+    if (k == 0 || m == 0) return;
+    GatherRowsKernel<<<k, 128, 0, s>>>(zt, m, rows, k, out);
+    ME_CUDA(cudaGetLastError());
+    ++launches;
 }
 
 } // namespace me

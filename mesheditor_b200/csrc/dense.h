@@ -30,4 +30,19 @@ void TallGemm(DenseWorkspace &, const double *V, size_t n, uint32_t m, const dou
 // X is read once per 8 columns of Y.
 void Gram(DenseWorkspace &, const double *X, size_t n, uint32_t a, const double *Y, uint32_t c, double *out, uint32_t ldo, cudaStream_t);
 
+// One plane rotation of the implicit QL iteration (hosteig.cpp): rows Row and Row + 1 of the transposed eigenvector matrix
+// become (C z_i - S z_i1, S z_i + C z_i1).
+struct QlRotation {
+    double C, S;
+    uint32_t Row, Pad;
+};
+// Largest matrix order ApplyRotations takes (one warp's 32 columns of all rows live in shared memory).
+constexpr uint32_t kMaxDeviceRotationOrder = 768;
+// zt (m x m, row-major, device): the whole rotation history applied in order, one thread per column, the column in shared
+// memory and the row shared by two consecutive rotations carried in a register. The arithmetic per entry is the host's.
+// `rotations` must be readable up to the next multiple of 512 records past `count` (staged in whole batches).
+void ApplyRotations(double *zt, uint32_t m, const QlRotation *rotations, size_t count, cudaStream_t, uint32_t &launches);
+// out (m x k, column-major, device): column j = row rows[j] of zt (m x m, row-major): the picked eigenvectors, as TallGemm takes them.
+void GatherRows(const double *zt, uint32_t m, const uint32_t *rows, uint32_t k, double *out, cudaStream_t, uint32_t &launches);
+
 } // namespace me

@@ -9,6 +9,10 @@
 // e alone, recording every rotation, and the whole history is then applied to the eigenvectors by a few threads, each on its
 // own column range, with a single fork and join. The arithmetic of each entry is the sequential algorithm's, operation for
 // operation (only disjoint ranges are handed out), so the result does not depend on the thread count.
+//
+// The block Lanczos iteration goes one step further (lanczos.cpp): it takes the two halves apart - SymmetricEigenReduce leaves
+// the transposed Householder basis and the rotation history - and applies the history on the device (dense.cu ApplyRotations),
+// where the eigenvector matrix is needed anyway for the restart GEMM.
 #include "lanczos.h"
 
 #include <algorithm>
@@ -38,8 +42,9 @@ uint32_t TeamSize(uint32_t n) {
 }
 } // namespace
 
-bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) {
+bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<QlRotation> &rotations) {
     d.assign(n, 0.0);
+    rotations.clear();
     if (n == 0) return true;
     std::vector<double> e(n, 0.0), scratch(n, 0.0);
     auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
@@ -122,12 +127,7 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
     for (uint32_t i = 1; i < n; ++i) e[i - 1] = e[i];
     e[n - 1] = 0;
     const double eps = std::numeric_limits<double>::epsilon();
-    struct Rotation {
-        double C, S;
-        uint32_t Row; // mixes rows Row and Row + 1 of the transposed eigenvector matrix
-    };
-    std::vector<Rotation> rotations;
-    rotations.reserve(size_t(n) * n);
+    rotations.reserve(size_t(n) * n + size_t(n) * n / 4);
     for (uint32_t l = 0; l < n; ++l) {
         uint32_t iter = 0, m;
         do {
@@ -157,7 +157,7 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
                     r = (d[i] - g) * s + 2.0 * c * b;
                     d[i + 1] = g + (p = s * r);
                     g = c * r - b;
-                    rotations.push_back({c, s, uint32_t(i)});
+                    rotations.push_back({c, s, uint32_t(i), 0u});
                 }
                 if (r == 0.0 && i >= int64_t(l)) continue;
                 d[l] -= p;
@@ -166,12 +166,17 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
             }
         } while (m != l);
     }
+    return true;
+}
+
+void SymmetricEigenApplyHost(uint32_t n, std::vector<double> &a, const std::vector<QlRotation> &rotations) {
+    if (n == 0) return;
     // The rotation history, applied in order to every worker's own columns.
     const auto apply = [&](uint32_t w, uint32_t workers) {
         uint32_t k0, k1;
         Share(n, w, workers, k0, k1);
         if (k0 == k1) return;
-        for (const Rotation &q : rotations) {
+        for (const QlRotation &q : rotations) {
             double *zi = &a[size_t(q.Row) * n], *zi1 = zi + n;
             for (uint32_t k = k0; k < k1; ++k) {
                 const double fk = zi1[k];
@@ -187,6 +192,12 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) 
     for (auto &t : threads) t.join();
     for (uint32_t r = 0; r < n; ++r)
         for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
+}
+
+bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d) {
+    std::vector<QlRotation> rotations;
+    if (!SymmetricEigenReduce(n, a, d, rotations)) return false;
+    SymmetricEigenApplyHost(n, a, rotations);
     return true;
 }
 

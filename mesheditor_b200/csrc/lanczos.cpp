@@ -11,6 +11,7 @@
 #include "lanczos.h"
 
 #include <algorithm>
+#include <functional>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -412,8 +413,14 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         mark_t = t;
     };
     uint32_t m = 0; // expanded columns: T is m x m, the residual block sits in columns [m, m + b)
-    std::vector<double> evec, theta, ritz_val, est;
+    std::vector<double> evec, theta, ritz_val, est, tail, q;
     std::vector<uint32_t> order;
+    std::vector<QlRotation> rotations;
+    DeviceBuffer<double> Zt;       // the Ritz vectors of the last decomposition, one per row (m x m)
+    DeviceBuffer<QlRotation> Rot;
+    DeviceBuffer<uint32_t> Pick;
+    bool ritz_on_device = false;
+    std::function<void(const std::vector<uint32_t> &)> pick_last; // Small <- picked vectors of the last decomposition
     uint32_t iter = 0, nconv = 0;
     bool broke = false;
     bool op_ready = false; // W already holds Op applied to the residual block (issued ahead of the host eigensolve below)
@@ -467,7 +474,41 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         evec.assign(size_t(m) * m, 0.0);
         for (uint32_t i = 0; i < m; ++i)
             for (uint32_t j = 0; j < m; ++j) evec[size_t(i) * m + j] = 0.5 * (Tm(i, j) + Tm(j, i));
-        if (!SymmetricEigen(m, evec, theta)) Fail(ME_NOT_CONVERGED, "block Lanczos: projected eigenproblem did not converge");
+        // Tridiagonalisation and the QL iteration on the host; the accumulation of the QL rotations into the eigenvector matrix
+        // (two thirds of the decomposition) on the device, where the matrix is wanted for the restart GEMM anyway. The host only
+        // takes back the last b components of every vector (residual estimates, the border of the restarted T).
+        const double t_ritz0 = now();
+        if (!SymmetricEigenReduce(m, evec, theta, rotations)) Fail(ME_NOT_CONVERGED, "block Lanczos: projected eigenproblem did not converge");
+        const double t_ritz1 = now();
+        ritz_on_device = m >= 96 && m <= kMaxDeviceRotationOrder && !std::getenv("ME_HOST_RITZ");
+        if (ritz_on_device) {
+            Zt.Reserve(size_t(m) * m), Rot.Reserve((rotations.size() / 512 + 1) * 512), Pick.Reserve(m);
+            ME_CUDA(cudaMemcpyAsync(Zt.Ptr, evec.data(), size_t(m) * m * sizeof(double), cudaMemcpyHostToDevice, s));
+            ME_CUDA(cudaMemcpyAsync(Rot.Ptr, rotations.data(), rotations.size() * sizeof(QlRotation), cudaMemcpyHostToDevice, s));
+            ApplyRotations(Zt.Ptr, m, Rot.Ptr, rotations.size(), s, Ws.Launches);
+            tail.resize(size_t(m) * b);
+            ME_CUDA(cudaMemcpy2DAsync(tail.data(), b * sizeof(double), Zt.Ptr + (m - b), m * sizeof(double), b * sizeof(double), m, cudaMemcpyDeviceToHost, s));
+            ME_CUDA(cudaStreamSynchronize(s));
+        } else {
+            SymmetricEigenApplyHost(m, evec, rotations);
+        }
+        if (prof) fprintf(stderr, "[block lanczos] ritz m = %u: reduce %.1f ms (%zu rotations), apply %.1f ms (%s)\n", m, 1e3 * (t_ritz1 - t_ritz0), rotations.size(), 1e3 * (now() - t_ritz1), ritz_on_device ? "device" : "host");
+        // component m - b + c of Ritz vector `vec`
+        const auto tail_of = [&](uint32_t vec, uint32_t c) { return ritz_on_device ? tail[size_t(vec) * b + c] : evec[size_t(m - b + c) * m + vec]; };
+        // Small <- the picked Ritz vectors as the columns of an m x count matrix
+        const auto pick_vectors = [&](const std::vector<uint32_t> &vectors) {
+            Small.Reserve(size_t(m) * vectors.size());
+            if (ritz_on_device) {
+                ME_CUDA(cudaMemcpyAsync(Pick.Ptr, vectors.data(), vectors.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+                GatherRows(Zt.Ptr, m, Pick.Ptr, uint32_t(vectors.size()), Small.Ptr, s, Ws.Launches);
+            } else {
+                q.resize(size_t(m) * vectors.size());
+                for (size_t j = 0; j < vectors.size(); ++j)
+                    for (uint32_t r = 0; r < m; ++r) q[r + j * m] = evec[size_t(r) * m + vectors[j]];
+                ME_CUDA(cudaMemcpyAsync(Small.Ptr, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+            }
+        };
+        pick_last = pick_vectors;
         order.resize(m);
         std::iota(order.begin(), order.end(), 0u);
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t c) { return std::abs(theta[a]) > std::abs(theta[c]); });
@@ -477,7 +518,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
             double sq = 0;
             for (uint32_t r = 0; r < b; ++r) {
                 double v = 0;
-                for (uint32_t c = 0; c < b; ++c) v += Tm(m + r, m - b + c) * evec[size_t(m - b + c) * m + order[i]];
+                for (uint32_t c = 0; c < b; ++c) v += Tm(m + r, m - b + c) * tail_of(order[i], c);
                 sq += v * v;
             }
             est[i] = std::sqrt(sq);
@@ -492,11 +533,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         uint32_t k = nev + std::min(nconv, (m - nev) / 2);
         k = std::min(k, m - b);
         k = mcap - (mcap - k) / b * b;
-        std::vector<double> q(size_t(m) * k);
-        for (uint32_t j = 0; j < k; ++j)
-            for (uint32_t r = 0; r < m; ++r) q[r + size_t(j) * m] = evec[size_t(r) * m + order[j]];
-        Small.Reserve(q.size());
-        ME_CUDA(cudaMemcpyAsync(Small.Ptr, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        pick_vectors(std::vector<uint32_t>(order.begin(), order.begin() + k));
         TallGemm(Ws, V, n, m, Small.Ptr, m, k, V2, s);
         ME_CUDA(cudaMemcpyAsync(col(V2, k), col(V, m), n * b * sizeof(double), cudaMemcpyDeviceToDevice, s));
         ME_CUDA(cudaStreamSynchronize(s));
@@ -505,7 +542,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         for (uint32_t r = 0; r < b; ++r)
             for (uint32_t j = 0; j < k; ++j) {
                 double v = 0;
-                for (uint32_t c = 0; c < b; ++c) v += Tm(m + r, m - b + c) * evec[size_t(m - b + c) * m + order[j]];
+                for (uint32_t c = 0; c < b; ++c) v += Tm(m + r, m - b + c) * tail_of(order[j], c);
                 border[size_t(r) * k + j] = v;
             }
         std::fill(T.begin(), T.end(), 0.0);
@@ -528,13 +565,12 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         for (uint32_t i = 0; i < nev; ++i) lambda[i] = 1.0 / ritz_val[i] + Sigma;
         std::stable_sort(pick.begin(), pick.end(), [&](uint32_t a, uint32_t c) { return lambda[a] < lambda[c]; });
         out.Eigenvalues.resize(nev);
-        std::vector<double> q(size_t(m) * nev);
+        std::vector<uint32_t> wanted(nev);
         for (uint32_t j = 0; j < nev; ++j) {
             out.Eigenvalues[j] = lambda[pick[j]];
-            for (uint32_t r = 0; r < m; ++r) q[r + size_t(j) * m] = evec[size_t(r) * m + order[pick[j]]];
+            wanted[j] = order[pick[j]];
         }
-        Small.Reserve(q.size());
-        ME_CUDA(cudaMemcpyAsync(Small.Ptr, q.data(), q.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+        pick_last(wanted);
         // The Ritz vectors are written into the spare basis buffer, which then becomes `Vectors`: no 0.9 GB allocation at the
         // end of a solve whose 20 GB of buffers are all still alive (the stream-ordered pool sometimes took 0.2-0.7 s over it).
         TallGemm(Ws, V, n, m, Small.Ptr, m, nev, V2, s);

@@ -26,6 +26,12 @@ struct LanczosOutcome {
 // Dense symmetric eigen-decomposition on the host (Householder tridiagonalisation + implicit QL), for the projected
 // matrix H (at most ncv x ncv). a: row-major n x n, overwritten with the eigenvectors (columns); d: eigenvalues, unsorted.
 bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d);
+// The same in two halves. Reduce: Householder tridiagonalisation + implicit QL on the tridiagonal entries; leaves in `a` the
+// TRANSPOSED orthogonal basis of the tridiagonal form (row-major: row j is what becomes eigenvector j), in `d` the eigenvalues
+// and in `rotations` the QL rotation history, each mixing rows Row and Row + 1 of `a`. Apply: the history applied to `a` and
+// `a` transposed back (a[r * n + c] = component r of vector c), on host threads; dense.h ApplyRotations is the device form.
+bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<QlRotation> &rotations);
+void SymmetricEigenApplyHost(uint32_t n, std::vector<double> &a, const std::vector<QlRotation> &rotations);
 
 class ShiftInvertLanczos {
 public:

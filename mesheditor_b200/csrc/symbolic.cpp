@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <new>
 #include <numeric>
 #include <thread>
 
@@ -138,8 +139,24 @@ struct Dissector {
 };
 } // namespace
 
+namespace {
+void BuildSchedules(Symbolic &sym);
+}
+
+void Symbolic::WaitSchedules() {
+    if (ScheduleThread.joinable()) ScheduleThread.join();
+    if (ScheduleFailed) throw std::bad_alloc(); // the only way building the schedules fails
+}
+
 Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const float *xyz, const SymbolicOptions &opt) {
     Symbolic sym;
+    AnalyseInto(sym, n, rowptr, col, xyz, opt, false);
+    return sym;
+}
+
+void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32_t *col, const float *xyz, const SymbolicOptions &opt, bool schedules_in_background) {
+    sym.WaitSchedules();
+    sym = Symbolic{};
     sym.NodeCount = n;
     const double t0 = Now();
     Dissector d{n, rowptr, col, xyz, opt};
@@ -295,6 +312,15 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
     }
     sym.FactorNonZeros = sym.PanelOffset[ns];
     lap("segments");
+    // The solve schedules read only what exists by now, and nothing below writes it: they are built on a thread of their own
+    // beside the tile lists, and (in the background form) on past this function's return.
+    sym.ScheduleThread = std::thread([&sym] {
+        try {
+            BuildSchedules(sym);
+        } catch (...) {
+            sym.ScheduleFailed = true;
+        }
+    });
 
     // Tile lists in (level, order inside the level) sequence: count per supernode, prefix, then fill on several threads.
     sym.PanelTilePtr.assign(size_t(sym.NumLevels) + 1, 0);
@@ -327,6 +353,16 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
         for (uint32_t l = 0; l < sym.NumLevels; ++l) sym.PanelTilePtr[l + 1] = panel_at[sym.LevelPtr[l + 1]], sym.UpdateTilePtr[l + 1] = update_at[sym.LevelPtr[l + 1]];
     }
     lap("tiles");
+    if (!schedules_in_background) {
+        sym.WaitSchedules();
+        lap("sweep tasks");
+    }
+    sym.StructureSeconds = Now() - t1;
+}
+
+namespace {
+void BuildSchedules(Symbolic &sym) {
+    const uint32_t ns = sym.NumSuper;
     // Dataflow schedules of the solves. Ticket order = level order (height above the leaves), NOT elimination order:
     // both are topological, but the post-order would walk one subtree's separator chains at a time, while the level
     // order keeps the chains of all subtrees of the same height in flight together.
@@ -419,8 +455,21 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
                 }
         }
     };
-    // Single-vector sweeps: one slab per task.
-    make_schedules([](uint32_t) { return 1u; }, UINT32_MAX, sym.FwdTasks, sym.FwdLinks, sym.BwdTasks, sym.BwdLinks, sym.BwdLinkNeed);
+    // Single-vector sweeps: one slab per task (on a thread of their own: the two pairs of schedules share nothing but their inputs).
+    bool single_failed = false;
+    std::thread single([&] {
+        try {
+            make_schedules([](uint32_t) { return 1u; }, UINT32_MAX, sym.FwdTasks, sym.FwdLinks, sym.BwdTasks, sym.BwdLinks, sym.BwdLinkNeed);
+        } catch (...) {
+            single_failed = true;
+        }
+    });
+    struct Join { // (an exception below must not leave the thread running)
+        std::thread &T;
+        ~Join() {
+            if (T.joinable()) T.join();
+        }
+    } join{single};
     // Panel sweeps: runs on the levels wide enough to still hand every resident CTA (5 per SM x 148 SMs) a run of its own.
     {
         std::vector<uint32_t> level_slabs(sym.NumLevels, 0);
@@ -430,9 +479,9 @@ Symbolic Analyse(uint32_t n, const uint32_t *rowptr, const uint32_t *col, const 
         make_schedules([&](uint32_t l) { return std::min(kWideRun, level_slabs[l] / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
                        sym.WideBwdLinkNeed);
     }
-    lap("sweep tasks");
-    sym.StructureSeconds = Now() - t1;
-    return sym;
+    single.join();
+    if (single_failed) throw std::bad_alloc();
 }
+} // namespace
 
 } // namespace me

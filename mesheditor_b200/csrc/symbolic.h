@@ -6,6 +6,7 @@
 #pragma once
 
 #include <cstdint>
+#include <thread>
 #include <vector>
 
 namespace me {
@@ -77,6 +78,18 @@ struct Symbolic {
     double FactorFlops{0};
     uint32_t MaxPanelColumns{0}, MaxPanelRows{0};
     double OrderingSeconds{0}, StructureSeconds{0};
+
+    // AnalyseInto may leave the four solve schedules above under construction on a background thread (they are first needed by
+    // the first triangular solve, a numeric factorisation later): WaitSchedules joins it. The object must not move meanwhile.
+    std::thread ScheduleThread;
+    bool ScheduleFailed{false};
+    void WaitSchedules();
+    Symbolic() = default;
+    Symbolic(Symbolic &&) = default;
+    Symbolic &operator=(Symbolic &&) = default;
+    ~Symbolic() {
+        if (ScheduleThread.joinable()) ScheduleThread.join();
+    }
 };
 
 constexpr uint32_t kTile = 64; // edge of the dense tiles the numeric kernels work on
@@ -84,5 +97,8 @@ constexpr uint32_t kTile = 64; // edge of the dense tiles the numeric kernels wo
 // rowptr/col: full symmetric node adjacency (CSR, diagonal included or not); xyz: node coordinates for the
 // geometric nested dissection.
 Symbolic Analyse(uint32_t node_count, const uint32_t *rowptr, const uint32_t *col, const float *xyz, const SymbolicOptions & = {});
+// The same into an object that stays where it is; with `schedules_in_background` the solve schedules are still being built when
+// it returns (Symbolic::WaitSchedules).
+void AnalyseInto(Symbolic &out, uint32_t node_count, const uint32_t *rowptr, const uint32_t *col, const float *xyz, const SymbolicOptions &, bool schedules_in_background);
 
 } // namespace me
