@@ -455,8 +455,9 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
     // Tensor spans are rendered as a pipeline over sub-windows of a few tiles: while the walk kernel (HBM-write bound) steps the
     // bank through sub-window k on the render stream, the force + pulse kernels (FP32-issue bound) of sub-window k + 1 run beside
     // it on the pulse stream, and the host admits and plans sub-window k + 2. Only the first sub-window's planning is exposed.
-    // (A bank of few chunk groups walks in seeded segments and is launch-bound: it keeps one batch per launch window.)
-    const bool piped = tensor_span && SubWindowTiles > 0 && groups >= 128;
+    const bool piped = tensor_span && SubWindowTiles > 0;
+    static const bool small_banks_piped = std::getenv("ME_SMALL_BANKS_PIPED") != nullptr; // measured: no gain (the chain pulses -> walk -> mix of a 128-voice bank is serial either way)
+    const bool small_bank = groups < 128;
     const cudaStream_t pulse_stream = piped ? PulseStream : stream;
 
     auto host_begin = Clock::now();
@@ -766,11 +767,15 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
                 // Sub-windows of the pipeline, in tiles: the first ones are short (1, 2, .. tiles) so that the device has work after a
                 // fraction of the host's planning; the rest take SubWindowTiles each.
                 std::vector<uint32_t> sub_begin{0};
-                if (piped) {
+                if (piped && !small_bank) {
                     for (uint32_t at = 0, size = 1; at < tiles; size = std::min(size + 1, SubWindowTiles)) {
                         at = std::min(tiles, at + size);
                         if (at < tiles) sub_begin.push_back(at * TensorTileFrames);
                     }
+                } else if (piped && small_banks_piped && tiles > 4) {
+                    // A small bank is launch-bound (every sub-window costs a seeded walk, its scan and its conditional repeat): two
+                    // sub-windows, so that all but a fraction of the host's planning runs beside the device.
+                    sub_begin.push_back(2 * TensorTileFrames);
                 }
                 const uint32_t subs = uint32_t(sub_begin.size());
                 sub_begin.push_back(wf);
