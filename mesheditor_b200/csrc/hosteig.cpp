@@ -40,15 +40,26 @@ uint32_t TeamSize(uint32_t n) {
     }();
     return configured;
 }
+
+// body(worker, workers) on `workers` threads (the caller is worker 0): one fork and one join.
+template<typename F>
+void RunTeam(uint32_t workers, F &&body) {
+    std::vector<std::thread> pool;
+    for (uint32_t w = 1; w < workers; ++w) pool.emplace_back([&body, w, workers] { body(w, workers); });
+    body(0u, workers);
+    for (auto &t : pool) t.join();
+}
 } // namespace
 
 bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<QlRotation> &rotations) {
     d.assign(n, 0.0);
     rotations.clear();
     if (n == 0) return true;
-    std::vector<double> e(n, 0.0), scratch(n, 0.0);
+    std::vector<double> e(n, 0.0);
     auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
-    // Householder reduction to tridiagonal form, accumulating the transformation.
+    const uint32_t workers = TeamSize(n);
+    // Householder reduction to tridiagonal form. (Its steps are tens of microseconds of O(n^2) work each: shared out over
+    // threads they gain less than the barriers between them cost, measured; it stays on one thread.)
     for (uint32_t i = n - 1; i >= 1; --i) {
         const uint32_t l = i - 1;
         double h = 0, scale = 0;
@@ -100,25 +111,35 @@ bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double
     }
     d[0] = 0;
     e[0] = 0;
-    for (uint32_t i = 0; i < n; ++i) {
-        if (d[i] != 0.0 && i > 0) {
-            // g = row_i * Q[0..i, 0..i), then Q[0..i, 0..i) -= Q[0..i, i] * g: contiguous row sweeps, columns shared out.
-            std::vector<double> &g = scratch;
-            std::fill(g.begin(), g.begin() + i, 0.0);
-            for (uint32_t k = 0; k < i; ++k) {
-                const double aik = A(i, k);
-                const double *row = &a[size_t(k) * n];
-                for (uint32_t j = 0; j < i; ++j) g[j] += aik * row[j];
+    {
+        // The orthogonal basis Q = H_1 H_2 .. accumulated in a matrix of its own, starting from the identity: step i reads the
+        // i-th Householder vector (row i of `a` left of the diagonal, and its scaled copy in column i) and updates Q's leading
+        // i x i block, g = u_i Q then Q -= (u_i / h) g. A worker owns a fixed range of Q's columns for the whole accumulation - its
+        // part of g and of the update involve nobody else's - so the workers never meet until the end.
+        std::vector<double> q(size_t(n) * n, 0.0);
+        for (uint32_t i = 0; i < n; ++i) q[size_t(i) * n + i] = 1.0;
+        RunTeam(workers, [&](uint32_t w, uint32_t count) {
+            uint32_t c0, c1;
+            Share(n, w, count, c0, c1);
+            std::vector<double> g(n, 0.0);
+            for (uint32_t i = 1; i < n; ++i) {
+                const uint32_t j1 = std::min(c1, i);
+                if (d[i] == 0.0 || c0 >= j1) continue;
+                std::fill(g.begin() + c0, g.begin() + j1, 0.0);
+                for (uint32_t k = 0; k < i; ++k) {
+                    const double aik = a[size_t(i) * n + k];
+                    const double *row = &q[size_t(k) * n];
+                    for (uint32_t j = c0; j < j1; ++j) g[j] += aik * row[j];
+                }
+                for (uint32_t k = 0; k < i; ++k) {
+                    const double aki = a[size_t(k) * n + i];
+                    double *row = &q[size_t(k) * n];
+                    for (uint32_t j = c0; j < j1; ++j) row[j] -= g[j] * aki;
+                }
             }
-            for (uint32_t k = 0; k < i; ++k) {
-                const double aki = A(k, i);
-                double *row = &a[size_t(k) * n];
-                for (uint32_t j = 0; j < i; ++j) row[j] -= g[j] * aki;
-            }
-        }
-        d[i] = A(i, i);
-        A(i, i) = 1;
-        for (uint32_t j = 0; j < i; ++j) A(j, i) = A(i, j) = 0;
+        });
+        for (uint32_t i = 0; i < n; ++i) d[i] = A(i, i);
+        a.swap(q);
     }
     // Implicit QL on the tridiagonal matrix. The rotations mix two eigenvector columns at a time: work on the transpose
     // so that they are contiguous rows (~3 n^3 flops). They depend only on d and e: recorded here, applied below.

@@ -301,7 +301,8 @@ std::vector<double> LowerInverse(uint32_t b, const std::vector<double> &l) {
 } // namespace
 
 uint32_t ShiftInvertLanczos::BlockBasisSize(uint32_t nev) {
-    const uint32_t extra = std::max(96u, nev / 2); // a deeper basis than the reference's nev + 20: restarts (host eigensolves) halve, the extra columns cost HBM only
+    uint32_t extra = std::max(96u, nev / 2); // a deeper basis than the reference's nev + 20: restarts (host eigensolves) halve, the extra columns cost HBM only
+    if (const char *env = std::getenv("ME_LANCZOS_EXTRA")) extra = uint32_t(std::max(8, std::atoi(env)));
     return (nev + extra + kLanczosBlock - 1) / kLanczosBlock * kLanczosBlock;
 }
 
