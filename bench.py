@@ -598,10 +598,37 @@ def run_solve(args, ranks, steps, warmup, cpu_baseline=True):
         "roofline_spmv": spmv, "roofline_assembly": asm, "roofline_factor": factor,
         "clocks": clocks.summary(),
     }
+    rec["other_configs"] = other_solve_configs(local)
     if cpu_baseline:
         base = cpu_solve_reference()
         rec["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     return rec
+
+
+def other_solve_configs(device):
+    """The analysis configurations of BASELINE.json next to configs[2], one warm call each after one warm-up call: configs[0]
+    (the reference's own CPU-runnable case, quadratic elements) and configs[1] (the ~200k-tet torus, lowest 100 modes) in the
+    linear elements BASELINE.json names AND in the reference's quadratic elements (both orders)."""
+    from mesheditor_b200 import mesh2modes, solver_config
+    from mesheditor_b200 import workloads as wl
+
+    out = []
+    for label, mesh, material, order, modes in (
+        ("configs[0]: tetrahedralised icosphere, steel, lowest 30 modes, quadratic (P2) elements", wl.config1_mesh()[:2], "Steel", 2, 30),
+        ("configs[1]: synthetic torus, lowest 100 modes, linear (P1) elements", wl.torus_mesh(), "Ceramic", 1, 100),
+        ("configs[1] in the reference's quadratic (P2) elements", wl.torus_mesh(), "Ceramic", 2, 100),
+    ):
+        points, tets = mesh
+        ex = wl.bench_excitations(points)
+        cfg = solver_config(num_modes=modes, element_order=order, max_mode_freq=1e9, device=device)
+        mesh2modes(points, tets, material, ex, config=cfg)
+        t0 = time.perf_counter()
+        r = mesh2modes(points, tets, material, ex, config=cfg)
+        dt = time.perf_counter() - t0
+        p = r.profile
+        out.append({"workload": label, "tets": int(len(tets)), "element_order": order, "num_modes": modes, "status": int(r.status), "kept_modes": int(len(r.freqs)), "value": dt, "unit": SOLVE_UNIT,
+                    "profile": {k: p[k] for k in ("assemble", "factorize", "analyse", "iterate", "op_solve", "dofs", "op_applications", "restarts", "factor_nonzeros", "supernodes", "levels")}})
+    return out
 
 
 def run_batch(args, ranks, steps, warmup):

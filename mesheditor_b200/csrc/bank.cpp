@@ -656,6 +656,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
             .OnlyIf = 0u,
             .Debug = std::getenv("ME_RESONATOR_DEBUG") ? 1u : 0u,
             .WalkStates = nullptr,
+            .WalkScales = nullptr,
             .WalkBlocksPerTile = TensorBlocksPerTile,
         };
     };
@@ -763,6 +764,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
                 // it goes) and writes the block-start states; the tcgen05 kernel turns them into per-group-set mixes.
                 const uint32_t tiles = (wf + TensorTileFrames - 1) / TensorTileFrames;
                 DWalkStates.Reserve(size_t(tiles) * groups * TmStateTileFloats(TensorBlocksPerTile));
+                DWalkScales.Reserve(size_t(tiles) * groups * TmScaleTileFloats(TensorBlocksPerTile));
                 DGroupMix.Reserve(size_t(mix_rows) * wf);
                 // Sub-windows of the pipeline, in tiles: the first ones are short (1, 2, .. tiles) so that the device has work after a
                 // fraction of the host's planning; the rest take SubWindowTiles each.
@@ -805,6 +807,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
                     RenderPlan walk = plan_for(lists, sb, sf, sub_blocks);
                     walk.Speculation = DSpeculation.Ptr + sub;
                     walk.WalkStates = DWalkStates.Ptr + size_t((sb - begin) / TensorTileFrames) * groups * TmStateTileFloats(TensorBlocksPerTile);
+                    walk.WalkScales = DWalkScales.Ptr + size_t((sb - begin) / TensorTileFrames) * groups * TmScaleTileFloats(TensorBlocksPerTile);
                     // A bank of few chunk groups cannot fill the SMs with one CTA per group: its walk is split into seeded
                     // segments along time (the scan of the sample loop). A culling decision inside the window invalidates
                     // the seeds; the walk is then repeated sequentially (it is cheap next to the mix).
@@ -836,7 +839,7 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
                 plan.Speculation = DSpeculation.Ptr;
                 segments = walked_segments;
                 Timed(2, stream, [&] {
-                    LaunchTensorMixKernel({.Groups = groups, .StagesPerRow = stages_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Partial = DGroupMix.Ptr}, stream);
+                    LaunchTensorMixKernel({.Groups = groups, .StagesPerRow = stages_per_row, .Tiles = tiles, .BlocksPerTile = TensorBlocksPerTile, .Frames = wf, .Powers = DPowers.Ptr, .States = DWalkStates.Ptr, .Scales = DWalkScales.Ptr, .Partial = DGroupMix.Ptr}, stream);
                 });
                 ++Counter.Launches;
                 // The fixed-order mix goes out before the flags are read: one host round trip per window, behind its last launch.

@@ -206,7 +206,7 @@ private:
     std::vector<float> MixGain, EnergyScale;
 
     // Tensor-core form (tensor_mix.cuh): power stages of the installed tuning, state stages and group mixes of a window.
-    DeviceBuffer<float> DPowers, DWalkStates, DGroupMix;
+    DeviceBuffer<float> DPowers, DWalkStates, DWalkScales, DGroupMix;
     uint64_t StateBudgetBytes{0}; // HBM the state stages of one launch window may take (half of what was free at first use, at most 40 GB)
     bool PowersDirty{true};
     uint64_t TuningVersion{1}, PowersVersion{0}; // the power stages follow the coefficients, not the install

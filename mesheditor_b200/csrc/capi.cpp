@@ -288,9 +288,13 @@ MeStatus me_debug_tensor_mix(int device, const float *powers, const float *state
         ME_CUDA(cudaSetDevice(device));
         const size_t np = size_t(groups) * me::kTmStagesPerGroup * me::TmPowerStageFloats();
         const size_t ns = size_t(tiles) * groups * me::TmStateTileFloats(blocks_per_tile);
-        me::DeviceBuffer<float> dp, ds, dout;
+        me::DeviceBuffer<float> dp, ds, dplanes, dscale, dout;
         dp.Upload(powers, np, nullptr), ds.Upload(states, ns, nullptr), dout.Reserve(size_t(groups / groups_per_row) * frames);
-        const me::TensorMixPlan plan{.Groups = groups, .StagesPerRow = groups_per_row * me::kTmStagesPerGroup, .Tiles = tiles, .BlocksPerTile = blocks_per_tile, .Frames = frames, .Powers = dp.Ptr, .States = ds.Ptr, .Partial = dout.Ptr};
+        dscale.Reserve(size_t(tiles) * groups * me::TmScaleTileFloats(blocks_per_tile));
+        dplanes.Reserve(ns);
+        me::LaunchStateScaleKernel(ds.Ptr, tiles * groups, blocks_per_tile, dscale.Ptr, nullptr); // (in the bank the walk kernel writes both as it goes)
+        me::LaunchStateSplitKernel(ds.Ptr, tiles * groups, blocks_per_tile, dscale.Ptr, dplanes.Ptr, nullptr);
+        const me::TensorMixPlan plan{.Groups = groups, .StagesPerRow = groups_per_row * me::kTmStagesPerGroup, .Tiles = tiles, .BlocksPerTile = blocks_per_tile, .Frames = frames, .Powers = dp.Ptr, .States = dplanes.Ptr, .Scales = dscale.Ptr, .Partial = dout.Ptr};
         cudaEvent_t a, b;
         ME_CUDA(cudaEventCreate(&a));
         ME_CUDA(cudaEventCreate(&b));

@@ -33,7 +33,7 @@
 
 #include "common.h"
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -200,18 +200,6 @@ __device__ __forceinline__ float SumRow(const float *rows, uint32_t lane) {
     return a + b;
 }
 
-// TF32 head of x (round to nearest); x - head is the FP32 tail: the two pieces of a 3xTF32 operand.
-__device__ __forceinline__ float Tf32Head(float x) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-    return __uint_as_float(u);
-}
-
-__device__ __forceinline__ uint2 PackBf16(float a, float b, float c, float d) {
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
-    return {reinterpret_cast<const uint32_t &>(lo), reinterpret_cast<const uint32_t &>(hi)};
-}
-
 // c^m for the chunk's eight modes from the FP64 polar form.
 __device__ __forceinline__ void PolarPower(const BankView &b, uint32_t mode0, uint32_t m, float2 (&re)[4], float2 (&im)[4]) {
 #pragma unroll
@@ -346,11 +334,12 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
     float2 *column = reinterpret_cast<float2 *>(rows) + lane;
     float *partial = plan.Partial + size_t(blockIdx.x * kWarpsPerBlock + warp) * plan.Frames;
 
-    // Walk: row-major states (tensor_mix.cuh). This chunk owns 16 consecutive reduction elements of every time-block row, so the
-    // CTA's 256 chunk-threads fill one 16 KB row per step. A warp's 32 chunks own 2 KB of the row; they pass through a swizzled
-    // shared-memory transpose so that every store instruction covers 512 contiguous bytes. The row pointer is stepped, not
-    // recomputed: every step of the walk starts on a time-block boundary and fills exactly one row (the last one may be ragged).
-    float4 *walk_at = nullptr;
+    // Walk: row-major states (tensor_mix.cuh). This chunk owns 16 consecutive reduction elements of every time-block row: 64 bytes,
+    // their FP16 hi values then their lo values; a warp's 32 chunks own 2 KB. They pass through a swizzled shared-memory transpose
+    // so that every store instruction covers 512 contiguous bytes. The row pointer is stepped, not recomputed: every step of the
+    // walk starts on a time-block boundary and fills exactly one row (the last one may be ragged).
+    uint4 *walk_at = nullptr; // this lane's 16 bytes of the first quarter of the warp's 2 KB of the row being written
+    float *scale_at = nullptr; // this warp's entry of the scale table for the row being written (tensor_mix.cuh)
     uint32_t walk_row = 0;
     size_t walk_tile_skip = 0;
     if constexpr (Walk) {
@@ -358,8 +347,9 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         const uint32_t block_index = seg_begin / kTmBlock;
         const size_t tile_stride = size_t(gridDim.x) * TmStateTileFloats(nb) / 4;
         walk_row = block_index % nb;
-        walk_at = reinterpret_cast<float4 *>(plan.WalkStates + size_t(blockIdx.x) * TmStateTileFloats(nb)) + warp * 128 + lane + size_t(block_index / nb) * tile_stride + size_t(walk_row) * (kTmGroupK / 4);
+        walk_at = reinterpret_cast<uint4 *>(plan.WalkStates + size_t(blockIdx.x) * TmStateTileFloats(nb)) + warp * 128 + lane + size_t(block_index / nb) * tile_stride + size_t(walk_row) * (kTmGroupK / 4);
         walk_tile_skip = tile_stride - size_t(nb) * (kTmGroupK / 4);
+        scale_at = plan.WalkScales + (size_t(block_index / nb) * gridDim.x + blockIdx.x) * TmScaleTileFloats(nb) + size_t(warp) * nb + walk_row;
     }
 
     uint32_t pos = seg_begin;
@@ -392,7 +382,7 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
         if constexpr (Walk) {
             // With one segment the walk is sequential in time over the whole window and culling needs no speculation; small
             // banks (few chunk groups) are walked in several seeded segments like the sample loop.
-            float4 *exchange = reinterpret_cast<float4 *>(transposed_storage) + warp * 128;
+            uint4 *exchange = reinterpret_cast<uint4 *>(transposed_storage) + warp * 128;
             const uint32_t put = lane * 4, put_swizzle = (lane >> 1) & 3;
             const bool audible = rendered && out_scale != 0.f;
             for (uint32_t t = pos; t < block_end;) {
@@ -403,14 +393,39 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                     // Increments land on time-block boundaries in a span planned for this form (DevImpact::RenderLen).
                     if (inj_frame - t_abs < step) atomicOr(plan.Speculation, 8u);
                 }
-                // (Im, Im, Re, Re) of the chunk's mode pairs: reduction elements 4p .. 4p+3 (tensor_mix.cuh; PowerTableKernel
-                // writes the powers in the same order). The pairs are the registers the packed FP32 instructions work on.
+                // The row as the mix kernel's tensor-core operand (tensor_mix.cuh): the warp's 512 entries scaled by the power of
+                // two that brings the largest into FP16 range, split into FP16 hi + lo. Reduction elements 4p .. 4p+3 of the chunk
+                // are (Im, Im, Re, Re) of its mode pair p - the register pairs the packed FP32 instructions work on; PowerTableKernel
+                // writes the powers in the same order.
+                float largest = 0.f;
                 if (audible) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) exchange[put + (i ^ put_swizzle)] = float4{w.Im[i].x, w.Im[i].y, w.Re[i].x, w.Re[i].y};
+                    for (int i = 0; i < 4; ++i) largest = fmaxf(fmaxf(largest, fmaxf(fabsf(w.Im[i].x), fabsf(w.Im[i].y))), fmaxf(fabsf(w.Re[i].x), fabsf(w.Re[i].y)));
+                }
+#pragma unroll
+                for (uint32_t d = 16; d; d >>= 1) largest = fmaxf(largest, __shfl_xor_sync(0xffffffffu, largest, d));
+                const float scale = TmStateScale(largest);
+                if (lane == 0) *scale_at = scale;
+                if (audible) {
+                    const float2 scale2 = {scale, scale};
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 im = Mul2(w.Im[i], scale2), re = Mul2(w.Re[i], scale2);
+                        const __half2 hi_im = __float22half2_rn(im), hi_re = __float22half2_rn(re);
+                        const float2 back_im = __half22float2(hi_im), back_re = __half22float2(hi_re);
+                        const __half2 lo_im = __floats2half2_rn(im.x - back_im.x, im.y - back_im.y), lo_re = __floats2half2_rn(re.x - back_re.x, re.y - back_re.y);
+                        hi[2 * i] = reinterpret_cast<const uint32_t &>(hi_im), hi[2 * i + 1] = reinterpret_cast<const uint32_t &>(hi_re);
+                        lo[2 * i] = reinterpret_cast<const uint32_t &>(lo_im), lo[2 * i + 1] = reinterpret_cast<const uint32_t &>(lo_re);
+                    }
+                    // the chunk's 64 bytes of the row: FP16 hi x 16, then lo x 16
+                    exchange[put + (0 ^ put_swizzle)] = uint4{hi[0], hi[1], hi[2], hi[3]};
+                    exchange[put + (1 ^ put_swizzle)] = uint4{hi[4], hi[5], hi[6], hi[7]};
+                    exchange[put + (2 ^ put_swizzle)] = uint4{lo[0], lo[1], lo[2], lo[3]};
+                    exchange[put + (3 ^ put_swizzle)] = uint4{lo[4], lo[5], lo[6], lo[7]};
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) exchange[put + (i ^ put_swizzle)] = float4{0.f, 0.f, 0.f, 0.f};
+                    for (int i = 0; i < 4; ++i) exchange[put + i] = uint4{0u, 0u, 0u, 0u};
                 }
                 __syncwarp();
 #pragma unroll
@@ -420,8 +435,11 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
                 }
                 __syncwarp();
                 // next row of the tile, or the first row of the next tile
-                walk_at += kTmGroupK / 4;
-                if (++walk_row == plan.WalkBlocksPerTile) walk_row = 0, walk_at += walk_tile_skip;
+                walk_at += kTmGroupK / 4, ++scale_at;
+                if (++walk_row == plan.WalkBlocksPerTile) {
+                    walk_row = 0, walk_at += walk_tile_skip;
+                    scale_at += size_t(gridDim.x) * TmScaleTileFloats(plan.WalkBlocksPerTile) - plan.WalkBlocksPerTile;
+                }
                 if (rendered) {
                     if (step == kTmBlock) {
                         // w <- (hi + lo) w, the small products first
@@ -768,8 +786,8 @@ __global__ void ClickKernel(const DevImpact *__restrict__ impacts, const DevImpa
 }
 
 // One thread per mode pair: rows j = 1..kTmBlock of the power stages, c^j by FP64 products of the float coefficient
-// (the same arithmetic as MakePowers). A stage (one chunk) holds three images of its 256 x 16 block (tensor_mix.cuh):
-// the TF32 head, and BF16 copies of the value and of the tail for the two cross products.
+// (the same arithmetic as MakePowers). A stage (one chunk) holds two FP16 images of its 256 x 16 block (tensor_mix.cuh):
+// hi = fp16(value) and lo = fp16(value - hi).
 __global__ void __launch_bounds__(128) PowerTableKernel(const BankView b, float *__restrict__ powers) {
     static_assert(kTmKChunk == 16, "one chunk per stage");
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; // chunk * 4 + pair
@@ -778,17 +796,17 @@ __global__ void __launch_bounds__(128) PowerTableKernel(const BankView b, float 
     const uint32_t mode = chunk * kLanes + pair * 2;
     const double ax = b.CoeffRe[mode], bx = b.CoeffIm[mode], ay = b.CoeffRe[mode + 1], by = b.CoeffIm[mode + 1];
     uint8_t *stage = reinterpret_cast<uint8_t *>(powers + size_t(chunk) * TmPowerStageFloats());
-    uint8_t *head = stage + size_t(pair) * kTmBlock * 16;                                    // TF32: 16-byte K pieces of 4 elements, 4096 bytes apart
-    uint8_t *value16 = stage + kTmPowerHeadBytes + size_t(pair >> 1) * kTmBlock * 16 + (pair & 1) * 8; // BF16: pieces of 8 elements
-    uint8_t *tail16 = value16 + kTmPowerBf16Bytes;
+    uint8_t *hi16 = stage + size_t(pair >> 1) * kTmBlock * 16 + (pair & 1) * 8; // pieces of 8 elements, 4096 bytes apart
+    uint8_t *lo16 = hi16 + kTmPowerImageBytes;
     double rx = ax, ix = bx, ry = ay, iy = by;
     for (uint32_t j = 0; j < kTmBlock; ++j) {
         const float4 v = {float(rx), float(ry), float(ix), float(iy)}; // against the state's (Im, Im, Re, Re) of the pair
-        const float4 h = {Tf32Head(v.x), Tf32Head(v.y), Tf32Head(v.z), Tf32Head(v.w)};
+        const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
         const uint32_t row = (j >> 3) * 128 + (j & 7) * 16;
-        *reinterpret_cast<float4 *>(head + row) = h;
-        *reinterpret_cast<uint2 *>(value16 + row) = PackBf16(v.x, v.y, v.z, v.w);
-        *reinterpret_cast<uint2 *>(tail16 + row) = PackBf16(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+        *reinterpret_cast<uint2 *>(hi16 + row) = {reinterpret_cast<const uint32_t &>(h0), reinterpret_cast<const uint32_t &>(h1)};
+        *reinterpret_cast<uint2 *>(lo16 + row) = {reinterpret_cast<const uint32_t &>(l0), reinterpret_cast<const uint32_t &>(l1)};
         const double nrx = rx * ax - ix * bx, nry = ry * ay - iy * by;
         ix = rx * bx + ix * ax, iy = ry * by + iy * ay;
         rx = nrx, ry = nry;

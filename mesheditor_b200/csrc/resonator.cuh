@@ -96,6 +96,7 @@ struct RenderPlan {
     // Tensor-core form (tensor_mix.cuh): the walk kernel (one segment: sequential in time, so culling is exact) writes
     // the block-start state of every 256-frame time block (kTmBlock) as rows of States[tile][chunk group][head,tail][block][4096].
     float *WalkStates;
+    float *WalkScales;         // [tile][chunk group][walk warp (8)][time block]: the FP16 scale of each warp's part of each row
     uint32_t WalkBlocksPerTile;
 };
 
