@@ -83,12 +83,22 @@ __device__ __forceinline__ uint64_t MatrixDescriptor(uint32_t smem_addr, uint32_
 // Instruction descriptor of kind::f16 (cute::UMMA::InstrDescriptor): FP32 accumulate, FP16 A and B (format 0), both K-major;
 // K = 16 per instruction.
 __host__ __device__ constexpr uint32_t InstructionDescriptorF16(uint32_t m, uint32_t n) { return (1u << 4) | (0u << 7) | (0u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24); }
+// Executed by a whole (converged) warp, issued by the one lane elect.sync picks: the operands are then warp-uniform values the
+// compiler keeps in uniform registers, instead of per-lane values it has to funnel there with a loop around every instruction.
 __device__ __forceinline__ void MmaF16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(a), "l"(b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void CommitElected(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
         : "memory");
 }
 // Four scaled states -> their FP16 hi and lo parts (two packed pairs each).
@@ -163,11 +173,12 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
 
-    // Producer and MMA issuer are ONE THREAD each, and a lone thread retires an instruction every ten cycles or so: at ~60
+    // Producer and MMA issuer are one warp each, and a lone warp retires an instruction every ten cycles or so: at ~60
     // instructions per stage the issue loop itself, not the tensor pipe (384 cycles per stage) or the copies, paced the kernel
     // (58 % tensor-pipe activity in the ncu capture). So both loops are unrolled over the ring (a ring round is one accumulator
-    // chain: Stages == kFoldStages), every address and descriptor of a slot is a constant offset from a base computed once, and a
-    // barrier that is already complete costs one try_wait.
+    // chain: Stages == kFoldStages), every address and descriptor of a slot is a constant offset from a base computed once, a
+    // barrier that is already complete costs one try_wait, and the whole warp runs the loop with elect.sync around the
+    // asynchronous instructions (operands stay in uniform registers).
     static_assert(Stages == kFoldStages, "one ring round = one accumulator chain");
     const uint32_t ring = SmemAddr(stage_storage), full0 = SmemAddr(&full_bar[0]), empty0 = SmemAddr(&empty_bar[0]);
     const auto wait = [](uint32_t bar, uint32_t parity) {
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
         }
     };
     if (warp == 0) {
-        if (lane == 0) {
+        {
             const uint8_t *powers = reinterpret_cast<const uint8_t *>(plan.Powers) + size_t(first_stage) * kPowerBytes;
             const uint64_t map = reinterpret_cast<uint64_t>(&states_map);
             asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -204,18 +215,19 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
                 for (uint32_t s = 0; s < Stages; ++s) {
                     if (round) wait(empty0 + s * 8, (round - 1) & 1);
                     const uint32_t stage = ring + s * kStageBytes, bar = full0 + s * 8;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(kStageBytes) : "memory");
-                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(stage), "l"(map), "r"(c0 + s * kTmKChunk), "r"(0),
-                                 "r"(c2), "r"(bar)
-                                 : "memory");
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage + kStateBytes), "l"(powers + size_t(k + s) * kPowerBytes), "n"(kPowerBytes),
-                                 "r"(bar)
-                                 : "memory");
+                    asm volatile(
+                        "{\n\t.reg .pred q;\n\t"
+                        "elect.sync _|q, 0xffffffff;\n\t"
+                        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+                        "@q cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%2], [%3, {%4, %5, %6}], [%0];\n\t"
+                        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%7], [%8], %9, [%0];\n\t}" ::"r"(bar),
+                        "n"(kStageBytes), "r"(stage), "l"(map), "r"(c0 + s * kTmKChunk), "r"(0), "r"(c2), "r"(stage + kStateBytes), "l"(powers + size_t(k + s) * kPowerBytes), "n"(kPowerBytes)
+                        : "memory");
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             // The states are the A operand (M = N time blocks = TMEM lanes), the powers the B operand (N = 256 frames =
             // accumulator columns): one MMA covers the whole time block, so neither operand is read twice per K step.
             static_assert(N == 128 && kTmBlock == 256, "M = 128 time blocks, N = 256 frames");
@@ -242,9 +254,9 @@ __global__ void __launch_bounds__(kThreads, 1) TensorMixKernel(const TensorMixPl
                     MmaF16(tmem_d, w_hi0 + s * step, p_lo0 + s * step, idesc, s != 0);
                     MmaF16(tmem_d, w_lo0 + s * step, p_hi0 + s * step, idesc, 1);
                     MmaF16(tmem_d, w_hi0 + s * step, p_hi0 + s * step, idesc, 1);
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + s * 8) : "memory"); // arrives when the MMAs above have read the stage
+                    CommitElected(empty0 + s * 8); // arrives when the MMAs above have read the stage
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(accum_full0 + buffer * 8) : "memory");
+                CommitElected(accum_full0 + buffer * 8);
             }
         }
     } else if (warp < 4) {
