@@ -404,40 +404,40 @@ def run_resonator(args, ranks):
         mandatory = mine * (32 * MODES) + 4 * frames
         base, reference_mix = (None, None) if args.no_cpu_baseline else cpu_reference(1, 0)
         if tensor_form:
-            # Tensor-core form. Dominant kernels: the tcgen05 mix (3xTF32 GEMM) and the state walk that
+            # Tensor-core form. Dominant kernels: the tcgen05 mix (FP16-split GEMM) and the state walk that
             # feeds it. Issued flops and written bytes follow from the padded layout: 4 voices of 63 chunks per 256-chunk
             # group, 4096 reduction elements per group, 128 time blocks of 256 frames per tile.
             chunks = -(-MODES // 8)
             groups = -(-mine // (256 // chunks))
             tiles = -(-frames // 32768)
-            product_flops = 2.0 * 256 * 128 * 4096 * groups * tiles  # one of the three products of the 3xTF32 split
-            # head x head runs as kind::tf32, the two cross products as kind::f16 on BF16 copies at twice that rate: the
-            # tensor-pipe time at peak is (1 + 2/2) products at the TF32 rate, so "achieved" is quoted in TF32-equivalent flop/s.
+            product_flops = 2.0 * 256 * 128 * 4096 * groups * tiles  # one of the three products of the split (hi*hi, hi*lo, lo*hi)
+            # All three products run as kind::f16 MMAs (FP16 operands, FP32 accumulation): "achieved" is issued FP16 flop/s
+            # against the measured dense 16-bit tensor peak.
             issued_flops = 3 * product_flops
-            tf32_equivalent = 2 * product_flops
             walk_bytes = 4096 * 4.0 * groups * -(-frames // 256)
             m_ms, w_ms = avg(mix_ms), avg(walk_ms)
-            tf32_peak = pk.get("bf16_tflops", 2250.0) / 2
+            f16_peak = pk.get("bf16_tflops", 2250.0)
             stages = groups * 256 * tiles
-            smem_bytes = stages * 106496.0  # per 16-element stage: 40 KB of TMA writes, 16 KB of splitter traffic, 48 KB of MMA operand reads
+            copy_bytes = stages * 24576.0  # per 16-element stage: 8 KB of states + 16 KB of power images through the SM's L2 port
             prof = profiled_traffic()
             # The ncu figure belongs to the launch it was captured on; a rank's launch covers (its groups x tiles) of that.
             scale = groups * tiles / max(1, prof.get("groups", 256) * prof.get("tiles", 15))
             traffic = lambda which: (prof[f"{which}_dram_bytes_per_launch"] * scale if f"{which}_dram_bytes_per_launch" in prof else None)  # noqa: E731
             roofline = {
-                "bound": "tensor", "kernel": "TensorMixKernel<128,4> (tcgen05.mma: head x head kind::tf32, cross products kind::f16 on BF16 copies; FP32 register folds)",
-                "achieved": tf32_equivalent / (m_ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TF32-equivalent TFLOP/s", "frac": tf32_equivalent / (m_ms * 1e-3) / 1e12 / tf32_peak,
+                "bound": "tensor", "kernel": "TensorMixKernel<128,8> (tcgen05.mma kind::f16: hi*hi + hi*lo + lo*hi of the two-term FP16 split, FP32 accumulation in TMEM, FP32 register folds)",
+                "achieved": issued_flops / (m_ms * 1e-3) / 1e12, "peak": f16_peak, "unit": "TFLOP/s (FP16 operands)", "frac": issued_flops / (m_ms * 1e-3) / 1e12 / f16_peak,
                 "traffic": traffic("mix"), "traffic_source": f"ncu --set full dram__bytes of the {prof.get('groups', 256)}-group x {prof.get('tiles', 15)}-tile launch (profiles/), scaled by this rank's groups x tiles = {groups} x {tiles}",
                 "kernel_ms_per_launch": m_ms, "launches_per_step": stats["tensor_windows"],
-                "issued_flops_per_step": issued_flops, "issued_tflops": issued_flops / (m_ms * 1e-3) / 1e12, "share_of_step": m_ms / ms_per_step,
-                "peak_source": ("half of MEASURED_PEAKS.json bf16_tflops (TF32 runs at half the bf16 rate; nominal 1125)" if "bf16_tflops" in pk else "nominal dense TF32 1125 TFLOP/s"),
+                "issued_flops_per_step": issued_flops, "algorithmic_flops_per_step": product_flops, "share_of_step": m_ms / ms_per_step,
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops (FP16 and BF16 share the tensor rate; nominal 2250)" if "bf16_tflops" in pk else "nominal dense FP16 2250 TFLOP/s"),
                 "reference_fma_equivalent": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (m_ms * 1e-3) / 1e12,
-                "shared_memory": {"bytes_per_launch": smem_bytes, "achieved_bytes_per_clk_per_sm": smem_bytes / (m_ms * 1e-3) / (148 * (pk.get("sm_max_mhz", 1965.0) * 1e6)), "peak_bytes_per_clk_per_sm": 128,
-                                  "note": "what actually bounds the kernel: SS-mode MMAs read both operands from shared memory (DESIGN.md 5.2)"},
+                "l2_to_sm": {"bytes_per_launch": copy_bytes, "achieved_bytes_per_clk_per_sm": copy_bytes / (m_ms * 1e-3) / (148 * (pk.get("sm_max_mhz", 1965.0) * 1e6)), "peak_bytes_per_clk_per_sm": 64,
+                             "note": "what the kernel runs into next to the tensor pipe: 24 KB per stage of 384 tensor cycles is the SM's whole 64 B/clk L2 read port (at the ~1.55 GHz the SM holds inside this kernel the figure is 1.27x higher; DESIGN.md 5.2)"},
             }
             extra = {
-                "roofline_walk": {"bound": "hbm", "kernel": "ResonatorKernel<1,2,true> (state walk: c^256 steps, FP32 state rows)", "achieved": walk_bytes / (w_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                  "frac": walk_bytes / (w_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic("walk"), "kernel_ms_per_launch": w_ms, "algorithmic_bytes": walk_bytes, "share_of_step": w_ms / ms_per_step, "peak_source": pk_kind},
+                "roofline_walk": {"bound": "hbm", "kernel": "ResonatorKernel<1,2,true> (state walk: c^256 steps, scaled FP16 hi/lo state rows)", "achieved": walk_bytes / (w_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                  "frac": walk_bytes / (w_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": traffic("walk"), "kernel_ms_per_launch": w_ms, "algorithmic_bytes": walk_bytes, "share_of_step": w_ms / ms_per_step, "peak_source": pk_kind,
+                                  "note": "its sub-window launches run beside the pulse kernels of the next sub-window (both slower for it): kernel_ms is the sum of the launches' own spans"},
                 "fp32_pipe_equivalent": {"note": "the same mode-samples per second on the FP32 pipe would need this multiple of the measured scalar-FFMA ceiling (reference loop: 7 lane-ops per mode-sample; this repo's sample loop: 2.75)",
                                          "reference_loop": REF_OPS_PER_MODE_SAMPLE * rank_mode_samples / (k_ms * 1e-3) / fma_peak, "sample_loop": achieved / fma_peak, "ffma_peak_tlane_ops": fma_peak / 1e12},
             }
@@ -452,7 +452,7 @@ def run_resonator(args, ranks):
             extra = {}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (3xTF32 products, FP32 accumulation)" if tensor_form else "f32", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (two-term FP16 split products on the tensor cores, FP32 accumulation; 22 significant bits per operand)" if tensor_form else "f32", "data": "synthetic",
             "config": workload_config(world) if voices == VOICES else dict(workload_config(world), voices=voices, workload=f"EXPERIMENT: {voices} voices (not the BASELINE.json configuration)"),
             "run": {"live_mode_count_min": min_live, "culling_triggered": min_live < MODES, "time_segments": stats["time_segments"], "voices_on_rank0": mine,
                     "render_path": "tensor-core form: state walk + tcgen05 mix" if tensor_form else "FP32 sample loop", "partial_rows": stats["partial_rows"],

@@ -353,11 +353,13 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
     }
 
     uint32_t pos = seg_begin;
+    uint32_t next_block_abs = ((plan.FrameBegin + seg_begin) / plan.BlockFrames + 1) * plan.BlockFrames; // end of the RenderModal block holding `pos` (stepped, not divided for, per block)
     while (pos < seg_end) {
         // One RenderModal block (or what is left of it inside this segment).
         const uint32_t pos_abs = plan.FrameBegin + pos;
-        const uint32_t block_end_abs = min(min((pos_abs / plan.BlockFrames + 1) * plan.BlockFrames, plan.SpanFrames), plan.FrameBegin + seg_end);
+        const uint32_t block_end_abs = min(min(next_block_abs, plan.SpanFrames), plan.FrameBegin + seg_end);
         const uint32_t block_end = block_end_abs - plan.FrameBegin;
+        if (block_end_abs == next_block_abs) next_block_abs += plan.BlockFrames;
         // Does the object hold a live impact in this block (:90 `impacts.empty()`)?
         while (exc < exc_hi && plan.ExciteEnd[exc] <= pos_abs) ++exc;
         const bool excited = exc < exc_hi && plan.ExciteBegin[exc] <= pos_abs;
@@ -402,9 +404,8 @@ __global__ void __launch_bounds__(kBlockThreads, MinBlocks) ResonatorKernel(cons
 #pragma unroll
                     for (int i = 0; i < 4; ++i) largest = fmaxf(fmaxf(largest, fmaxf(fabsf(w.Im[i].x), fabsf(w.Im[i].y))), fmaxf(fabsf(w.Re[i].x), fabsf(w.Re[i].y)));
                 }
-#pragma unroll
-                for (uint32_t d = 16; d; d >>= 1) largest = fmaxf(largest, __shfl_xor_sync(0xffffffffu, largest, d));
-                const float scale = TmStateScale(largest);
+                // (non-negative floats order like their bit patterns: one warp-wide integer max instead of five dependent shuffles)
+                const float scale = TmStateScale(__uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(largest))));
                 if (lane == 0) *scale_at = scale;
                 if (audible) {
                     const float2 scale2 = {scale, scale};
