@@ -519,7 +519,8 @@ MeStatus me_build_tet_mesh_data(const double *points_xyz, uint32_t n_points, con
 
 /* Unit-test entry of the tensor-core mix (tensor_mix.cuh): out[row][frame] = sum over the 4096 reduction elements of
  * each of the row's groups_per_row consecutive groups of power * state, operands given as host images of the stage layout documented in tensor_mix.cuh
- * (powers: groups*256 stages of 2*256*16 floats, stage layout; states: [tiles][groups][blocks_per_tile][4096] FP32, split in the kernel).
+ * (powers: groups*256 stages of two FP16 images of 256 x 16, stage layout; states: [tiles][groups][blocks_per_tile][4096] FP32 - the entry scales and
+ * splits them into the FP16 hi / lo rows the walk kernel writes, with the same helper kernels).
  * blocks_per_tile is 128; frames <= tiles*blocks_per_tile*256. `milliseconds` (may be NULL) receives the
  * kernel time of the last of `repeats` launches. */
 MeStatus me_debug_tensor_mix(int device, const float *powers, const float *states, uint32_t groups, uint32_t groups_per_row, uint32_t tiles, uint32_t blocks_per_tile, uint32_t frames,

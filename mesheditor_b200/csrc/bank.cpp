@@ -66,6 +66,7 @@ Bank::Bank(float sample_rate, int device) : SampleRate(sample_rate), Device(devi
     ME_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     ME_CUDA(cudaStreamCreateWithPriority(&OwnStream, cudaStreamNonBlocking, greatest));
     ME_CUDA(cudaStreamCreateWithPriority(&PulseStream, cudaStreamNonBlocking, least));
+    ME_CUDA(cudaStreamCreateWithPriority(&ForceStream, cudaStreamNonBlocking, greatest));
     ME_CUDA(cudaEventCreate(&EvBegin));
     ME_CUDA(cudaEventCreate(&EvEnd));
     // Diagnostic overrides: samples advanced per state jump (1, 2 or 4) and segments of the scan along time.
@@ -77,6 +78,7 @@ Bank::Bank(float sample_rate, int device) : SampleRate(sample_rate), Device(devi
 Bank::~Bank() {
     cudaSetDevice(Device);
     if (PulseStream) cudaStreamSynchronize(PulseStream), cudaStreamDestroy(PulseStream);
+    if (ForceStream) cudaStreamSynchronize(ForceStream), cudaStreamDestroy(ForceStream);
     if (OwnStream) cudaStreamSynchronize(OwnStream), cudaStreamDestroy(OwnStream);
     for (auto e : {EvBegin, EvEnd})
         if (e) cudaEventDestroy(e);
@@ -482,11 +484,13 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
         Plan.Flush(stream);
         Stats.h2d_bytes += 2 * n_obj * sizeof(float);
     }
+    const cudaStream_t force_stream = piped ? ForceStream : stream;
     if (piped) {
-        // The pulse stream picks up behind everything the render stream has been given so far (the gains, earlier spans).
+        // The pulse and force streams pick up behind everything the render stream has been given so far (the gains, earlier spans).
         const cudaEvent_t fork = NextJoin();
         ME_CUDA(cudaEventRecord(fork, stream));
         ME_CUDA(cudaStreamWaitEvent(pulse_stream, fork, 0));
+        ME_CUDA(cudaStreamWaitEvent(force_stream, fork, 0));
     }
     BankView view = View();
 
@@ -538,10 +542,18 @@ void Bank::RenderSpan(uint32_t frames, uint32_t block_frames, std::vector<Schedu
             if (len) delta_total += stride;
         }
         n = n1;
-        Plan.FlushRange(impacts, n0, n1 - n0, pulse_stream), Plan.FlushRange(tails, n0, n1 - n0, pulse_stream), Plan.FlushRange(pulse_warps, w0, n_warps - w0, pulse_stream);
+        // The batch's records and its force curves (one thread per impact walking its rotor sample by sample: ~30 us of latency,
+        // a handful of CTAs) go through the force stream, so that they run beside the pulse kernel of the batch before instead
+        // of behind it.
+        Plan.FlushRange(impacts, n0, n1 - n0, force_stream), Plan.FlushRange(tails, n0, n1 - n0, force_stream), Plan.FlushRange(pulse_warps, w0, n_warps - w0, force_stream);
         Stats.h2d_bytes += (n1 - n0) * (sizeof(DevImpact) + sizeof(DevImpactTail)) + (n_warps - w0) * sizeof(PulseWarp);
+        LaunchForceKernel(impacts.Dev + n0, tails.Dev + n0, n1 - n0, DForce.Ptr, force_stream, Counter);
+        if (force_stream != pulse_stream) {
+            const cudaEvent_t forces_done = NextJoin();
+            ME_CUDA(cudaEventRecord(forces_done, force_stream));
+            ME_CUDA(cudaStreamWaitEvent(pulse_stream, forces_done, 0));
+        }
         Timed(3, pulse_stream, [&] {
-            LaunchForceKernel(impacts.Dev + n0, tails.Dev + n0, n1 - n0, DForce.Ptr, pulse_stream, Counter);
             PulsePlan batch = current_pulses();
             batch.NPulseWarps = n_warps - w0, batch.Warps = pulse_warps.Dev + w0;
             LaunchPulseKernel(view, batch, pulse_stream, Counter);

@@ -154,7 +154,8 @@ private:
     int Device;
     cudaStream_t OwnStream{nullptr};
     cudaStream_t PulseStream{nullptr}; // tensor-core form: the force + pulse kernels of a sub-window run beside the state walk of the one before
-    std::vector<cudaEvent_t> JoinPool; // untimed events ordering the two streams
+    cudaStream_t ForceStream{nullptr}; // ... and the record copies + force kernel of a batch beside the pulse kernel of the batch before
+    std::vector<cudaEvent_t> JoinPool; // untimed events ordering the streams
     uint32_t JoinsUsed{0};
     uint32_t SubWindowTiles{2};        // tiles per sub-window of the pulse / walk pipeline (0: one batch per launch window, on the render stream)
     cudaEvent_t EvBegin{nullptr}, EvEnd{nullptr};

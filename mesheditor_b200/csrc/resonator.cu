@@ -612,13 +612,19 @@ __global__ void __launch_bounds__(kPulseWarps * 32) PulseKernel(const BankView b
     for (int i = 0; i < 4; ++i) ncim[i] = {-cim[i].x, -cim[i].y};
     const float2 scale2 = {out_scale, out_scale};
     // Past the pulse (tensor spans: up to the frame the increment is injected at) the response rings freely: those samples
-    // take the sample loop's K-step form, 2.75 lane-operations per mode-sample instead of 7.
+    // take the sample loop's K-step form, 2.75 lane-operations per mode-sample instead of 7. The kernel runs in two phases -
+    // tiles with force samples, then pure ringing - so that the powers of the K-step form (72 registers) are not alive while the
+    // forced recurrence runs: 5 CTAs fit an SM instead of 3, and two of them fit beside a CTA of the state walk.
     constexpr int K = 4;
-    Powers<K> p;
-    if (im.RenderLen > im.Len) MakePowers<K>(cre, cim, p);
-    for (uint32_t tile = 0; tile < im.RenderLen; tile += kTile) {
+    const auto flush = [&](uint32_t tile, uint32_t nv) { // the warp's nv samples of this tile: summed over its chunks, stored
+        __syncwarp();
+        if (lane < nv) plan.Rows[job.RowOff + tile + lane] = SumRow(rows, lane);
+        __syncwarp();
+    };
+    uint32_t tile = 0;
+    for (; tile < im.Len; tile += kTile) { // tiles holding force samples (the last one may already ring for part of its length)
         const uint32_t nv = min(kTile, im.RenderLen - tile);
-        const uint32_t forced = tile < im.Len ? min(nv, im.Len - tile) : 0;
+        const uint32_t forced = min(nv, im.Len - tile);
         for (uint32_t s = 0; s < forced; ++s) {
             const float f = __ldg(force + tile + s);
             const float2 f2 = {f, f};
@@ -632,17 +638,32 @@ __global__ void __launch_bounds__(kPulseWarps * 32) PulseKernel(const BankView b
             }
             reinterpret_cast<float2 *>(rows)[s * (kRowPad / 2) + lane] = Mul2(sum, scale2);
         }
-        if (forced < nv) {
+        for (uint32_t s = forced; s < nv; ++s) { // the rest of the transition tile rings freely, one sample at a time
+            float2 sum = {0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 re = Fma2(v.Re[i], cre[i], Mul2(v.Im[i], ncim[i]));
+                v.Im[i] = Fma2(v.Re[i], cim[i], Mul2(v.Im[i], cre[i]));
+                v.Re[i] = re;
+                sum = Add2(sum, v.Im[i]);
+            }
+            reinterpret_cast<float2 *>(rows)[s * (kRowPad / 2) + lane] = Mul2(sum, scale2);
+        }
+        flush(tile, nv);
+    }
+    if (tile < im.RenderLen) {
+        Powers<K> p;
+        MakePowers<K>(cre, cim, p);
+        for (; tile < im.RenderLen; tile += kTile) {
+            const uint32_t nv = min(kTile, im.RenderLen - tile);
             float2 *column = reinterpret_cast<float2 *>(rows) + lane;
-            uint32_t s = forced;
+            uint32_t s = 0;
             for (; s + K <= nv; s += K) StepK<K>(v, p, column + s * (kRowPad / 2));
             for (; s < nv; ++s) Step1<K>(v, p, column + s * (kRowPad / 2));
             if (out_scale == 0.f) // a muted object evolves but its samples are discarded
-                for (s = forced; s < nv; ++s) column[s * (kRowPad / 2)] = float2{0.f, 0.f};
+                for (s = 0; s < nv; ++s) column[s * (kRowPad / 2)] = float2{0.f, 0.f};
+            flush(tile, nv);
         }
-        __syncwarp();
-        if (lane < nv) plan.Rows[job.RowOff + tile + lane] = SumRow(rows, lane);
-        __syncwarp();
     }
     if (valid) {
         const uint32_t off = im.DeltaOff + my_chunk * kLanes;

@@ -127,7 +127,7 @@ uint32_t ResonatorRows(uint32_t n_chunks);
 // as the resonator kernel, but advancing one 256-frame time block per step with c^256 and writing the state stages instead of samples.
 void LaunchStateWalkKernel(const BankView &, const RenderPlan &, cudaStream_t, LaunchCounter &);
 // Power stages of the installed tuning: c^1..c^256 of every mode (FP64 products of the float coefficient), split into
-// TF32 head + FP32 tail, in the stage layout of tensor_mix.cuh. powers: [NChunks/256][256 stages][2][256*16] floats.
+// FP16 hi + lo, in the stage layout of tensor_mix.cuh. powers: [NChunks/256][256 stages][hi, lo][256 x 16] FP16.
 void LaunchPowerTableKernel(const BankView &, float *powers, cudaStream_t, LaunchCounter &);
 // out[n] = sum of the partial rows in fixed order (the reference sums renderer buffers in a fixed order, :553-555)
 // plus the pulse rows overlapping n.

@@ -11,11 +11,11 @@
 // FP32 accuracy comes from a two-term FP16 split of both operands, x = hi + lo with hi = fp16(x) and lo = fp16(x - hi): 22
 // significant bits, and hi*hi + hi*lo + lo*hi accumulate in FP32 (fp16 x fp16 products are exact there; the dropped lo*lo term
 // is 2^-22 relative). Three kind::f16 MMAs per 16 reduction elements - half the operand bytes and three quarters of the
-// tensor-pipe time of the 3xTF32 split this replaced, on a kernel bound by shared-memory operand traffic. FP16 has five
+// tensor-pipe time of the 3xTF32 split this replaced. FP16 has five
 // exponent bits, so the states are SCALED: the walk kernel records, per time block and per warp of chunk-threads (512
 // reduction elements = 32 stages), the power of two that brings the largest state of that range to [2^13, 2^14)
-// (TmStateScale); the mix kernel multiplies by it before splitting and divides it out again when it folds an accumulator chain
-// (4 stages, never across a range) into its FP32 registers. Entries far below a range's maximum lose relative precision
+// (TmStateScale) and stores the states multiplied by it, split; the mix kernel divides it out again when it folds an accumulator
+// chain (8 stages, never across a range) into its FP32 registers. Entries far below a range's maximum lose relative precision
 // against themselves, never against the sum they enter. The powers are at most 1 in magnitude and are split as they are.
 #pragma once
 
