@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 
 namespace me {
@@ -262,6 +263,107 @@ __global__ void __launch_bounds__(kSyrkThreads) SyrkScatterKernel(FactorView v, 
             }
 }
 
+// ------------------------------------------------------------------------------------------------ macro block inverses
+// The panel sweeps solve up to SymbolicOptions::MacroPanels consecutive panels of a separator chain in one step (symbolic.h):
+// W = inverse of the macro block's lower-triangular diagonal block, built here from the factor by block forward substitution,
+//   W_jj = Linv_j,   W_ij = -Linv_i * sum_{j <= l < i} L_il W_lj   (i > j),
+// one CTA per (block column j, 64-column slice): the columns of W are independent. Each W_ij goes to the forward row block of
+// panel i and, transposed, to the backward row block of panel j. All products are 128 x 64 DMMA tiles.
+struct MacroView {
+    const uint32_t *SuperFirst;
+    const uint64_t *RowPtr, *PanelOffset, *InvOffset, *MacroOffset, *MacroOffsetT;
+    const double *L, *Linv;
+    double *W, *WT;
+};
+constexpr int kMacroThreads = 256;
+
+// acc[128 x 64] += A[M x K] B[K x N], both column-major in global memory, M, K <= 128, N <= 64.
+__device__ __forceinline__ void MacroGemm(const double *__restrict__ A, uint32_t lda, uint32_t M, uint32_t K, const double *B, uint32_t ldb, uint32_t N, double *As, double *Bs,
+                                          double (&acc)[4][4][2]) {
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, wm = w & 3, wn = w >> 2;
+    for (uint32_t kc = 0; kc < K; kc += kChunk) {
+        __syncthreads();
+        for (uint32_t idx = t; idx < kChunk * 128; idx += kMacroThreads) {
+            const uint32_t r = idx & 127, c = idx >> 7;
+            As[c * kLdB128 + r] = (r < M && kc + c < K) ? A[r + size_t(kc + c) * lda] : 0.0;
+        }
+        for (uint32_t idx = t; idx < kChunk * kTile; idx += kMacroThreads) {
+            const uint32_t kk = idx & (kChunk - 1), n = idx / kChunk;
+            Bs[kk * kLdA + n] = (kc + kk < K && n < N) ? B[kc + kk + size_t(n) * ldb] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < kChunk / 4; ++ks) {
+            double a[4], b[4];
+            const uint32_t kk = 4 * ks + (lane & 3);
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) a[mi] = As[kk * kLdB128 + 32 * wm + 8 * mi + (lane >> 2)];
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni) b[ni] = Bs[kk * kLdA + 32 * wn + 8 * ni + (lane >> 2)];
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+                for (int ni = 0; ni < 4; ++ni) Dmma(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMacroThreads) MacroInverseKernel(MacroView v, const Symbolic::MacroJob *__restrict__ jobs) {
+    __shared__ double As[kChunk * kLdB128], Bs[kChunk * kLdA];
+    const Symbolic::MacroJob job = jobs[blockIdx.x];
+    const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, wm = w & 3, wn = w >> 2;
+    auto columns = [&](uint32_t s) { return 3 * (v.SuperFirst[s + 1] - v.SuperFirst[s]); };
+    auto start = [&](uint32_t s) { return 3 * (v.SuperFirst[s] - v.SuperFirst[job.First]); }; // a panel's first column inside the macro block
+    const uint32_t j = job.Column, kj = columns(j), off_j = start(j), n0 = job.Slice * kTile, nn = min(uint32_t(kTile), kj - n0);
+    double *wb = v.WT + v.MacroOffsetT[j]; // backward row block of panel j: element (r, c) = W(off_j + c, off_j + r), leading dimension k_j
+    {
+        const double *linv = v.Linv + v.InvOffset[j];
+        double *wf = v.W + v.MacroOffset[j] + size_t(off_j + n0) * kj;
+        for (uint32_t idx = t; idx < kj * nn; idx += kMacroThreads) {
+            const uint32_t r = idx % kj, c = idx / kj;
+            const double value = linv[r + size_t(n0 + c) * kj];
+            wf[r + size_t(c) * kj] = value;
+            wb[(n0 + c) + size_t(r) * kj] = value;
+        }
+    }
+    for (uint32_t i = j + 1; i <= job.Last; ++i) {
+        const uint32_t ki = columns(i), off_i = start(i);
+        double acc[4][4][2]{};
+        for (uint32_t l = j; l < i; ++l) {
+            const uint32_t kl = columns(l), off_l = start(l), ld_l = kl + 3 * uint32_t(v.RowPtr[l + 1] - v.RowPtr[l]);
+            // the rows of panel i inside panel l's rectangle: the chain's next panels are the first rows of its list, in order
+            const double *a = v.L + v.PanelOffset[l] + kl + (off_i - off_l - kl);
+            const double *b = v.W + v.MacroOffset[l] + size_t(off_j + n0) * kl;
+            MacroGemm(a, ld_l, ki, kl, b, kl, nn, As, Bs, acc);
+        }
+        double *wf = v.W + v.MacroOffset[i] + size_t(off_j + n0) * ki; // W_ij's slice: k_i x nn; holds the sum first
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t r = 32 * wm + 8 * mi + (lane >> 2), c = 32 * wn + 8 * ni + 2 * (lane & 3) + e;
+                    if (r < ki && c < nn) wf[r + size_t(c) * ki] = acc[mi][ni][e];
+                    acc[mi][ni][e] = 0.0;
+                }
+        MacroGemm(v.Linv + v.InvOffset[i], ki, ki, ki, wf, ki, nn, As, Bs, acc);
+        __syncthreads(); // every read of the sum is done
+#pragma unroll
+        for (int mi = 0; mi < 4; ++mi)
+#pragma unroll
+            for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const uint32_t r = 32 * wm + 8 * mi + (lane >> 2), c = 32 * wn + 8 * ni + 2 * (lane & 3) + e;
+                    if (r < ki && c < nn) {
+                        wf[r + size_t(c) * ki] = -acc[mi][ni][e];
+                        wb[(n0 + c) + size_t(off_i - off_j + r) * kj] = -acc[mi][ni][e];
+                    }
+                }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ triangular solves
 __global__ void PermuteOutKernel(const double *__restrict__ w, const uint32_t *__restrict__ inv_perm, uint32_t n_nodes, double *__restrict__ x) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -335,7 +437,15 @@ struct SweepArgs {
     const double *Diag, *Panel;       // Linv + L (forward) or Linv^T + LT (backward)
     double *Acc, *Out;
     int *Fail;
+    const double *Macro;              // panel sweeps: row blocks of the macro blocks' inverses (forward) / of their transposes (backward)
+    const uint32_t *ArriveNeed;       // panel sweeps: arrivals every supernode's entries wait for (what a macro slab polls for each panel it reads)
+    unsigned long long *Trace;        // ME_SWEEP_TRACE: per task, %globaltimer when it was taken up, when its inputs were complete, when it ended
 };
+__device__ __forceinline__ unsigned long long GlobalTimer() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
 constexpr int kSweepThreads = 128;
 constexpr int kSweepCtasPerSm = 5;
 
@@ -546,10 +656,15 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             *reinterpret_cast<double2 *>(&part[(q * 32 + 8 * mi + fr) * kWide + 2 * fk]) = make_double2(c[mi][0], c[mi][1]);
     };
     auto reduced = [&](uint32_t idx) { return (part[idx] + part[256 + idx]) + (part[512 + idx] + part[768 + idx]); };
+    uint32_t traced = 0xFFFFFFFFu;
+    auto stamp = [&](uint32_t id, uint32_t slot) {
+        if (a.Trace && t == 0 && id != 0xFFFFFFFFu) a.Trace[size_t(3) * id + slot] = GlobalTimer();
+    };
     for (;;) {
         __syncthreads(); // every contribution of the previous task has been issued; its shared operands are free
         if (owed) ArriveRelease(owed);
         owed = nullptr;
+        stamp(traced, 2);
         if (q == 0) {
             if (lane < 8) reinterpret_cast<uint64_t *>(&s_task)[lane] = word1;
             if (lane == 0) s_id = id1;
@@ -557,6 +672,8 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
         __syncthreads();
         const uint32_t id = s_id;
         if (id >= a.NumTasks) return;
+        traced = id;
+        stamp(id, 0);
         const SweepTask task = s_task;
         const uint32_t k = task.K;
         if (q == 0) { // shift the ticket pipeline
@@ -566,32 +683,57 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             id2 = claim();
         }
         double val[32];
-        if (task.Kind == 0) {
-            const double *mat = a.Diag + task.Base;
+        if (task.Kind != 1) {
+            // A 32-row slab of a diagonal block's inverse (Kind 0: k columns) or of a macro block's inverse (Kind 2: the row block of
+            // this panel, task.Limit columns over the entries of task.LinkCount consecutive panels, walked in chunks of 128 columns):
+            //   forward   out_S[rows] = sum over the block's panels up to S of  W[rows of S, their columns] acc[their entries]
+            //   backward  out_S[rows] = sum over the block's panels from S on of W^T[...]
+            // Forward the own diagonal block is the LAST of the row block (it starts at column DiagColumn), backward the first.
+            const bool macro = task.Kind == 2;
+            const double *mat = (macro ? a.Macro : a.Diag) + task.Base;
+            const uint32_t diag_col = Backward ? 0u : task.DiagColumn;
+            const uint32_t in_base = task.VecOffset - diag_col;
+            const uint32_t col_end = Backward ? task.Limit : min(task.Limit, diag_col + task.Row0 + kSolveRows);
+            auto load_chunk = [&](uint32_t c0) {
 #pragma unroll
-            for (int mi = 0; mi < 4; ++mi)
+                for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const uint32_t row = task.Row0 + 8 * mi + fr, col = 32 * q + 4 * ks + fk;
-                    const bool in = row < k && col < k && (Backward ? col >= row : col <= row);
-                    val[mi * 8 + ks] = in ? mat[row + size_t(col) * k] : 0.0;
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t row = task.Row0 + 8 * mi + fr, col = c0 + 32 * q + 4 * ks + fk;
+                        const bool in = row < k && col < col_end && (Backward ? col >= row : col <= diag_col + row);
+                        val[mi * 8 + ks] = in ? mat[row + size_t(col) * k] : 0.0;
+                    }
+            };
+            load_chunk(0);
+            if (!macro) {
+                if (t == 96) { // (warp 3: warp 0 is busy with the tickets)
+                    for (uint32_t spin = 0; PeekAcquire(a.Arrived + task.Super) < task.Need; ++spin) {
+                        if (GiveUp(spin, a.Fail)) break;
+                        __nanosleep(20);
+                    }
                 }
-            if (t == 96) { // (warp 3: warp 0 is busy with the tickets)
-                for (uint32_t spin = 0; PeekAcquire(a.Arrived + task.Super) < task.Need; ++spin) {
+            } else if (q == 3 && lane < task.LinkCount) { // one lane per panel of the block whose entries this slab reads
+                const uint32_t super = Backward ? task.Super + lane : task.Super - (task.LinkCount - 1) + lane;
+                const uint32_t need = a.ArriveNeed[super];
+                for (uint32_t spin = 0; PeekAcquire(a.Arrived + super) < need; ++spin) {
                     if (GiveUp(spin, a.Fail)) break;
                     __nanosleep(20);
                 }
             }
-            __syncthreads();
-            {
-                const double2 *src = reinterpret_cast<const double2 *>(a.Acc + (size_t(task.VecOffset) + t) * kWide);
-                double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
-#pragma unroll
-                for (int j = 0; j < kWide / 2; ++j) dst[j] = t < k ? __ldcg(src + j) : make_double2(0.0, 0.0);
-            }
-            __syncthreads();
             double c[4][2]{};
-            contract_quarter(val, c);
+            for (uint32_t c0 = 0; c0 < col_end; c0 += 128) {
+                __syncthreads(); // the entries are complete (first chunk) / the previous chunk's operand has been consumed
+                if (c0 == 0) stamp(id, 1);
+                {
+                    const double2 *src = reinterpret_cast<const double2 *>(a.Acc + (size_t(in_base) + c0 + t) * kWide);
+                    double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
+#pragma unroll
+                    for (int j = 0; j < kWide / 2; ++j) dst[j] = c0 + t < col_end ? __ldcg(src + j) : make_double2(0.0, 0.0);
+                }
+                __syncthreads();
+                contract_quarter(val, c);
+                if (c0 + 128 < col_end) load_chunk(c0 + 128);
+            }
             store_partials(c);
             __syncthreads();
 #pragma unroll
@@ -623,6 +765,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                 }
             }
             __syncthreads();
+            stamp(id, 1);
             {
                 const double2 *src = reinterpret_cast<const double2 *>(a.Out + (size_t(task.VecOffset) + t) * kWide);
                 double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
@@ -682,6 +825,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             for (uint32_t slab = 0; slab < task.Count; ++slab) {
                 const uint32_t row0 = task.Row0 + slab * kSolveRows, row = row0 + vr;
                 __syncthreads(); // the links are solved (first slab); the previous slab's operand has been consumed
+                if (slab == 0) stamp(id, 1);
                 {
                     double2 x = make_double2(0.0, 0.0);
                     if (row < task.Limit) x = __ldcg(reinterpret_cast<const double2 *>(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3)));
@@ -798,7 +942,9 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     fem.CopyNodeCoords(xyz);
     // The solve schedules keep being built on a host thread while the structures below are uploaded and (in the caller) the numeric
     // factorisation runs: UploadSchedules, at the first solve, waits for them.
-    AnalyseInto(Sym, fem.NodeCount, rowptr.data(), col.data(), xyz.data(), opt, true);
+    SymbolicOptions options = opt;
+    if (const char *env = std::getenv("ME_MACRO_PANELS")) options.MacroPanels = uint32_t(std::max(1, std::atoi(env))); // (tuning aid)
+    AnalyseInto(Sym, fem.NodeCount, rowptr.data(), col.data(), xyz.data(), options, true);
     if (Sym.MaxPanelColumns > 128) Fail(ME_BAD_ARG, "internal: panel of %u columns", Sym.MaxPanelColumns);
     auto s = fem.Stream;
     DSuperFirst.Upload(Sym.SuperFirst, s);
@@ -815,11 +961,16 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     DInvOffset.Upload(Sym.InvOffset, s);
     DPanelTiles.Upload(Sym.PanelTiles, s);
     DUpdateTiles.Upload(Sym.UpdateTiles, s);
+    DMacroOffset.Upload(Sym.MacroOffset, s);
+    DMacroOffsetT.Upload(Sym.MacroOffsetT, s);
+    DMacroJobs.Upload(Sym.MacroJobs, s);
     if (Sym.Rows.size() >= (uint64_t(1) << 32)) Fail(ME_BAD_ARG, "mesh too large: supernodal row lists exceed 32-bit indexing");
     L.Reserve(Sym.FactorNonZeros);
     Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
     LinvT.Reserve(Sym.InvOffset[Sym.NumSuper]);
     LT.Reserve(Sym.FactorNonZeros - Sym.InvOffset[Sym.NumSuper] + 1);
+    MacroW.Reserve(Sym.MacroOffset[Sym.NumSuper] + 1);
+    MacroWT.Reserve(Sym.MacroOffsetT[Sym.NumSuper] + 1);
     Work.Reserve(fem.N);
     Work2.Reserve(fem.N);
     DFail.Reserve(1);
@@ -860,6 +1011,9 @@ void SparseCholesky::UploadSchedules() {
     DWideFwdLinks.Upload(Sym.WideFwdLinks, s);
     DWideBwdLinks.Upload(Sym.WideBwdLinks, s);
     DWideBwdLinkNeed.Upload(Sym.WideBwdLinkNeed, s);
+    DWideFwdNeed.Upload(Sym.WideFwdNeed, s);
+    DWideBwdNeed.Upload(Sym.WideBwdNeed, s);
+    Stats.SweepLevels = Sym.SweepLevels;
     SchedulesUploaded = true;
 }
 
@@ -896,6 +1050,11 @@ void SparseCholesky::Factorize(double sigma) {
             ++launches;
         }
     }
+    if (!Sym.MacroJobs.empty()) {
+        const MacroView mv{DSuperFirst.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DMacroOffset.Ptr, DMacroOffsetT.Ptr, L.Ptr, Linv.Ptr, MacroW.Ptr, MacroWT.Ptr};
+        MacroInverseKernel<<<uint32_t(Sym.MacroJobs.size()), kMacroThreads, 0, s>>>(mv, DMacroJobs.Ptr);
+        ++launches;
+    }
     ME_CUDA(cudaEventRecord(Ev[1], s));
     int fail = 0;
     ME_CUDA(cudaMemcpyAsync(&fail, DFail.Ptr, sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -929,6 +1088,8 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     SweepArgs wide_fwd = fwd, wide_bwd = bwd;
     wide_fwd.Tasks = DWideFwdTasks.Ptr, wide_fwd.NumTasks = uint32_t(Sym.WideFwdTasks.size()), wide_fwd.Links = DWideFwdLinks.Ptr;
     wide_bwd.Tasks = DWideBwdTasks.Ptr, wide_bwd.NumTasks = uint32_t(Sym.WideBwdTasks.size()), wide_bwd.Links = DWideBwdLinks.Ptr, wide_bwd.LinkNeed = DWideBwdLinkNeed.Ptr;
+    wide_fwd.Macro = MacroW.Ptr, wide_fwd.ArriveNeed = DWideFwdNeed.Ptr;
+    wide_bwd.Macro = MacroWT.Ptr, wide_bwd.ArriveNeed = DWideBwdNeed.Ptr;
     auto single = [&](const double *bi, double *xi) {
         SweepBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(bi, DInvPerm.Ptr, Fem.NodeCount, Work.Ptr, Work2.Ptr);
         ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
@@ -949,11 +1110,35 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
             continue;
         }
         const uint32_t w = std::min<uint32_t>(left, kWide);
+        const char *trace_path = TraceDone ? nullptr : std::getenv("ME_SWEEP_TRACE");
+        DeviceBuffer<unsigned long long> trace;
+        if (trace_path) {
+            trace.Reserve(size_t(3) * (wide_fwd.NumTasks + wide_bwd.NumTasks));
+            ME_CUDA(cudaMemsetAsync(trace.Ptr, 0, trace.Capacity * sizeof(unsigned long long), s));
+            wide_fwd.Trace = trace.Ptr, wide_bwd.Trace = trace.Ptr + size_t(3) * wide_fwd.NumTasks;
+        }
         WideBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, n, w, DInvPerm.Ptr, Work.Ptr);
         ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
         WideSweepKernel<false><<<WideFwdGrid, kSweepThreads, 0, s>>>(wide_fwd);
         WideSweepKernel<true><<<WideBwdGrid, kSweepThreads, 0, s>>>(wide_bwd);
         WidePermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n, w, DInvPerm.Ptr, x + size_t(rhs) * n);
+        if (trace_path) { // one panel application's timeline: task records followed by their three time stamps
+            std::vector<unsigned long long> stamps(size_t(3) * (wide_fwd.NumTasks + wide_bwd.NumTasks));
+            ME_CUDA(cudaMemcpyAsync(stamps.data(), trace.Ptr, stamps.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            ME_CUDA(cudaStreamSynchronize(s));
+            if (FILE *f = std::fopen(trace_path, "wb")) {
+                const uint32_t header[4] = {wide_fwd.NumTasks, wide_bwd.NumTasks, ns, uint32_t(sizeof(SweepTask))};
+                std::fwrite(header, sizeof(header), 1, f);
+                std::fwrite(Sym.WideFwdTasks.data(), sizeof(SweepTask), Sym.WideFwdTasks.size(), f);
+                std::fwrite(Sym.WideBwdTasks.data(), sizeof(SweepTask), Sym.WideBwdTasks.size(), f);
+                std::fwrite(Sym.Level.data(), sizeof(uint32_t), ns, f);
+                std::fwrite(Sym.MacroFirst.data(), sizeof(uint32_t), ns, f);
+                std::fwrite(stamps.data(), sizeof(unsigned long long), stamps.size(), f);
+                std::fclose(f);
+            }
+            wide_fwd.Trace = wide_bwd.Trace = nullptr;
+            TraceDone = true;
+        }
         Stats.KernelLaunches += 4;
         rhs += w;
     }

@@ -17,6 +17,7 @@ struct CholeskyStats {
     uint64_t FactorNonZeros{0};
     double FactorFlops{0};
     uint32_t Supernodes{0}, Levels{0};
+    uint32_t SweepLevels{0};       // dependency levels of the panel sweeps (a macro block of chain panels counts once)
     uint32_t KernelLaunches{0};
 };
 
@@ -50,7 +51,10 @@ private:
     DeviceBuffer<SweepTask> DFwdTasks, DBwdTasks;
     DeviceBuffer<uint32_t> DFwdLinks, DCounters;
     DeviceBuffer<SweepTask> DWideFwdTasks, DWideBwdTasks; // panel sweeps: runs of slabs (Symbolic::WideFwdTasks)
-    DeviceBuffer<uint32_t> DWideFwdLinks, DWideBwdLinks, DWideBwdLinkNeed;
+    DeviceBuffer<uint32_t> DWideFwdLinks, DWideBwdLinks, DWideBwdLinkNeed, DWideFwdNeed, DWideBwdNeed;
+    DeviceBuffer<uint64_t> DMacroOffset, DMacroOffsetT;
+    DeviceBuffer<Symbolic::MacroJob> DMacroJobs;
+    DeviceBuffer<double> MacroW, MacroWT; // explicit inverses of the macro blocks' diagonal blocks (symbolic.h), forward and backward row blocks
     uint32_t FwdGrid{0}, BwdGrid{0}, WideFwdGrid{0}, WideBwdGrid{0};
     DeviceBuffer<UpdateTile> DUpdateTiles;
     DeviceBuffer<double> L, Linv, LinvT, LT, Work, Work2;
@@ -60,6 +64,7 @@ private:
     bool SchedulesUploaded{false};
     void UploadSchedules(); // waits for the background construction of the solve schedules (symbolic.h) and uploads them
     uint32_t SolvesSinceCheck{0};
+    bool TraceDone{false}; // ME_SWEEP_TRACE=<file>: the first panel application's task timeline is written once
 };
 
 // FP64 issue-rate micro-benchmark: mode 0 = DFMA, 1 = DMMA m8n8k4. Returns flop/s.

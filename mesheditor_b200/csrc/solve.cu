@@ -690,6 +690,44 @@ MeStatus me_symbolic_analyse(uint32_t node_count, const uint32_t *rowptr, const 
             }
             if (p < sym.NumSuper && sym.Level[p] <= sym.Level[s]) ++violations;
         }
+        // The dataflow schedules of the triangular solves, replayed in ticket order: every task must find its inputs published by
+        // tasks holding smaller tickets (the sweeps' spin-waits rely on it), with exactly the counts it waits for.
+        const auto replay = [&](const std::vector<me::SweepTask> &tasks, const std::vector<uint32_t> &links, const std::vector<uint32_t> *link_need, const std::vector<uint32_t> *need,
+                                bool backward) {
+            std::vector<uint32_t> arrived(sym.NumSuper, 0), solved(sym.NumSuper, 0), slabs(sym.NumSuper, 0);
+            for (uint32_t s = 0; s < sym.NumSuper; ++s) slabs[s] = (3 * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]) + me::kSolveRows - 1) / me::kSolveRows;
+            for (const me::SweepTask &t : tasks) {
+                if (t.Super >= sym.NumSuper) {
+                    ++violations;
+                    continue;
+                }
+                if (t.Kind == 0) {
+                    if (arrived[t.Super] != t.Need) ++violations;
+                    ++solved[t.Super];
+                } else if (t.Kind == 2) {
+                    for (uint32_t i = 0; i < t.LinkCount; ++i) {
+                        const uint32_t s = backward ? t.Super + i : t.Super - (t.LinkCount - 1) + i;
+                        if (!need || s >= sym.NumSuper || sym.MacroFirst[s] != sym.MacroFirst[t.Super] || arrived[s] != (*need)[s]) ++violations;
+                    }
+                    ++solved[t.Super];
+                } else if (!backward) {
+                    if (solved[t.Super] != slabs[t.Super] || t.Need != slabs[t.Super]) ++violations;
+                    for (uint32_t i = 0; i < t.LinkCount; ++i) ++arrived[links[t.LinkBegin + i]];
+                } else {
+                    for (uint32_t i = 0; i < t.LinkCount; ++i) {
+                        const uint32_t a = links[t.LinkBegin + i];
+                        if (solved[a] != slabs[a] || (link_need && (*link_need)[t.LinkBegin + i] != slabs[a])) ++violations;
+                    }
+                    ++arrived[t.Super];
+                }
+            }
+            for (uint32_t s = 0; s < sym.NumSuper; ++s)
+                if (solved[s] != slabs[s] || (need && arrived[s] != (*need)[s])) ++violations;
+        };
+        replay(sym.FwdTasks, sym.FwdLinks, nullptr, nullptr, false);
+        replay(sym.BwdTasks, sym.BwdLinks, &sym.BwdLinkNeed, nullptr, true);
+        replay(sym.WideFwdTasks, sym.WideFwdLinks, nullptr, &sym.WideFwdNeed, false);
+        replay(sym.WideBwdTasks, sym.WideBwdLinks, &sym.WideBwdLinkNeed, &sym.WideBwdNeed, true);
         if (perm_out) std::copy(sym.Perm.begin(), sym.Perm.end(), perm_out);
         *out = MeSymbolicInfo{sym.NumSuper, sym.NumLevels, sym.MaxPanelColumns, sym.MaxPanelRows, sym.FactorNonZeros, sym.UpdateTiles.size(), sym.PanelTiles.size(), violations,
                               sym.FactorFlops, sym.OrderingSeconds, sym.StructureSeconds};

@@ -181,6 +181,18 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
     sym.NodeSuper.assign(n, 0);
     for (uint32_t s = 0; s < ns; ++s)
         for (uint32_t v = sym.SuperFirst[s]; v < sym.SuperFirst[s + 1]; ++v) sym.NodeSuper[v] = s;
+    // Macro blocks of the panel sweeps: every chain of c > 1 panels is cut into ceil(c / MacroPanels) runs of near-equal length.
+    sym.MacroFirst.resize(ns), sym.MacroLast.resize(ns);
+    for (uint32_t s = 0; s < ns;) {
+        uint32_t e = s + 1;
+        while (e < ns && chain[e] == chain[s]) ++e;
+        const uint32_t panels = e - s, per = std::max(1u, opt.MacroPanels), blocks = (panels + per - 1) / per;
+        for (uint32_t b = 0; b < blocks; ++b) {
+            const uint32_t first = s + uint32_t(uint64_t(panels) * b / blocks), last = s + uint32_t(uint64_t(panels) * (b + 1) / blocks) - 1;
+            for (uint32_t i = first; i <= last; ++i) sym.MacroFirst[i] = first, sym.MacroLast[i] = last;
+        }
+        s = e;
+    }
     const double t1 = Now();
     sym.OrderingSeconds = t1 - t0;
 
@@ -311,6 +323,21 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
         sym.SegPtr[s + 1] = sym.SegTarget.size();
     }
     sym.FactorNonZeros = sym.PanelOffset[ns];
+    sym.MacroOffset.assign(size_t(ns) + 1, 0);
+    sym.MacroOffsetT.assign(size_t(ns) + 1, 0);
+    for (uint32_t s = 0; s < ns; ++s) {
+        uint64_t fwd = 0, bwd = 0;
+        if (sym.MacroFirst[s] != sym.MacroLast[s]) {
+            const uint64_t k = 3ull * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]);
+            fwd = k * 3ull * (sym.SuperFirst[s + 1] - sym.SuperFirst[sym.MacroFirst[s]]);
+            bwd = k * 3ull * (sym.SuperFirst[sym.MacroLast[s] + 1] - sym.SuperFirst[s]);
+            for (uint32_t slice = 0; slice * kTile < k; ++slice) sym.MacroJobs.push_back({sym.MacroFirst[s], sym.MacroLast[s], s, slice});
+        }
+        sym.MacroOffset[s + 1] = sym.MacroOffset[s] + fwd;
+        sym.MacroOffsetT[s + 1] = sym.MacroOffsetT[s] + bwd;
+    }
+    // (the first columns of a macro block carry the longest chains of products: they go first)
+    std::stable_sort(sym.MacroJobs.begin(), sym.MacroJobs.end(), [](const Symbolic::MacroJob &a, const Symbolic::MacroJob &b) { return a.Last - a.Column > b.Last - b.Column; });
     lap("segments");
     // The solve schedules read only what exists by now, and nothing below writes it: they are built on a thread of their own
     // beside the tile lists, and (in the background form) on past this function's return.
@@ -356,6 +383,7 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
     if (!schedules_in_background) {
         sym.WaitSchedules();
         lap("sweep tasks");
+        if (timing) fprintf(stderr, "[me] symbolic levels %u, panel-sweep levels %u, macro jobs %zu, macro inverse doubles %llu\n", sym.NumLevels, sym.SweepLevels, sym.MacroJobs.size(), (unsigned long long)sym.MacroOffset[ns]);
     }
     sym.StructureSeconds = Now() - t1;
 }
@@ -368,16 +396,6 @@ void BuildSchedules(Symbolic &sym) {
     // order keeps the chains of all subtrees of the same height in flight together.
     auto columns = [&](uint32_t s) { return 3 * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]); };
     auto diag_slabs = [&](uint32_t s) { return (columns(s) + kSolveRows - 1) / kSolveRows; };
-    auto panel_slabs = [&](uint32_t s) { return uint32_t((3 * size_t(sym.RowPtr[s + 1] - sym.RowPtr[s]) + kSolveRows - 1) / kSolveRows); };
-    // The supernodes owning rows [first_slab, first_slab + count) slabs of s's panel, ascending (rows are), without repeats.
-    auto targets_of = [&](uint32_t s, uint32_t first_slab, uint32_t count, std::vector<uint32_t> &out, size_t from) {
-        const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0;
-        const uint64_t first = (uint64_t(first_slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, (uint64_t(first_slab + count) * kSolveRows + 2) / 3);
-        for (uint64_t j = first; j < last; ++j) {
-            const uint32_t target = sym.NodeSuper[sym.Rows[r0 + j]];
-            if (out.size() == from || out.back() != target) out.push_back(target);
-        }
-    };
     auto base_task = [&](uint32_t s) {
         SweepTask t{};
         t.Super = s;
@@ -387,28 +405,65 @@ void BuildSchedules(Symbolic &sym) {
         t.Count = 1;
         return t;
     };
-    auto diag_task = [&](uint32_t s, uint32_t h) {
-        SweepTask t = base_task(s);
-        t.Kind = 0, t.Base = sym.InvOffset[s], t.Limit = t.K, t.Ld = t.K, t.Row0 = h * kSolveRows;
-        return t;
-    };
-    // run_of(level) = slabs per panel task on that level; max_links bounds the arrivals one forward task may owe.
-    auto make_schedules = [&](auto &&run_of, uint32_t max_links, std::vector<SweepTask> &fwd, std::vector<uint32_t> &fwd_links, std::vector<SweepTask> &bwd, std::vector<uint32_t> &bwd_links,
-                              std::vector<uint32_t> &bwd_link_need) {
-        std::vector<uint32_t> fwd_expected(ns, 0), bwd_expected(ns, 0);
+    // run_of(panel slabs of a level) = slabs per panel task on that level; max_links bounds the arrivals one forward task may owe.
+    // With `macros` the supernodes of a macro block (Symbolic::MacroFirst) share the level of the block's first panel: their diagonal
+    // slabs become slabs of the block's inverse, and their panel slabs cover only the rows outside the block.
+    auto make_schedules = [&](bool macros, auto &&run_of, uint32_t max_links, std::vector<SweepTask> &fwd, std::vector<uint32_t> &fwd_links, std::vector<SweepTask> &bwd,
+                              std::vector<uint32_t> &bwd_links, std::vector<uint32_t> &bwd_link_need, std::vector<uint32_t> &fwd_expected, std::vector<uint32_t> &bwd_expected, uint32_t *levels_used) {
+        auto first_of = [&](uint32_t s) { return macros ? sym.MacroFirst[s] : s; };
+        auto last_of = [&](uint32_t s) { return macros ? sym.MacroLast[s] : s; };
+        // rows at the top of s's panel that belong to its own macro block (the chain's next panels: the first rows of the list)
+        auto inside = [&](uint32_t s) { return 3 * (sym.SuperFirst[last_of(s) + 1] - sym.SuperFirst[s + 1]); };
+        auto panel_rows = [&](uint32_t s) { return 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]); };
+        auto panel_slabs = [&](uint32_t s) { return (panel_rows(s) - inside(s) + kSolveRows - 1) / kSolveRows; };
+        // The supernodes owning slabs [first_slab, first_slab + count) of s's panel (counted from the first row outside the macro
+        // block), ascending (rows are), without repeats.
+        auto targets_of = [&](uint32_t s, uint32_t first_slab, uint32_t count, std::vector<uint32_t> &out, size_t from) {
+            const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0, skip = inside(s);
+            const uint64_t first = (skip + uint64_t(first_slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, (skip + uint64_t(first_slab + count) * kSolveRows + 2) / 3);
+            for (uint64_t j = first; j < last; ++j) {
+                const uint32_t target = sym.NodeSuper[sym.Rows[r0 + j]];
+                if (out.size() == from || out.back() != target) out.push_back(target);
+            }
+        };
+        auto diag_task = [&](uint32_t s, uint32_t h, bool backward) {
+            SweepTask t = base_task(s);
+            t.Row0 = h * kSolveRows, t.Ld = t.K;
+            if (first_of(s) == last_of(s)) {
+                t.Kind = 0, t.Base = sym.InvOffset[s], t.Limit = t.K, t.LinkCount = 1;
+            } else if (!backward) {
+                t.Kind = 2, t.Base = sym.MacroOffset[s], t.DiagColumn = 3 * (sym.SuperFirst[s] - sym.SuperFirst[first_of(s)]), t.Limit = t.DiagColumn + t.K, t.LinkCount = s - first_of(s) + 1;
+            } else {
+                t.Kind = 2, t.Base = sym.MacroOffsetT[s], t.Limit = 3 * (sym.SuperFirst[last_of(s) + 1] - sym.SuperFirst[s]), t.LinkCount = last_of(s) - s + 1;
+            }
+            return t;
+        };
+        // Levels of this schedule: a supernode sits on the level of its macro block's first panel (ascending ids inside a level).
+        std::vector<uint32_t> level_ptr(size_t(sym.NumLevels) + 1, 0), order(ns), level_slabs(sym.NumLevels, 0);
+        for (uint32_t s = 0; s < ns; ++s) ++level_ptr[sym.Level[first_of(s)] + 1], level_slabs[sym.Level[first_of(s)]] += panel_slabs(s);
+        for (uint32_t l = 0; l < sym.NumLevels; ++l) level_ptr[l + 1] += level_ptr[l];
+        {
+            std::vector<uint32_t> at(level_ptr.begin(), level_ptr.end() - 1);
+            for (uint32_t s = 0; s < ns; ++s) order[at[sym.Level[first_of(s)]]++] = s;
+        }
+        if (levels_used) {
+            *levels_used = 0;
+            for (uint32_t l = 0; l < sym.NumLevels; ++l) *levels_used += level_ptr[l + 1] > level_ptr[l];
+        }
+        fwd_expected.assign(ns, 0), bwd_expected.assign(ns, 0);
         size_t tasks = 0;
         for (uint32_t s = 0; s < ns; ++s) tasks += diag_slabs(s) + panel_slabs(s);
         fwd.reserve(tasks), bwd.reserve(tasks);
         fwd_links.reserve(sym.Rows.size() / 2), bwd_links.reserve(sym.Rows.size() / 2), bwd_link_need.reserve(sym.Rows.size() / 2);
         for (uint32_t l = 0; l < sym.NumLevels; ++l) {
-            const uint32_t run = std::max(1u, run_of(l));
-            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
-                for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) fwd.push_back(diag_task(sym.LevelOrder[i], h));
-            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-                const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]), slabs = panel_slabs(s);
+            const uint32_t run = std::max(1u, run_of(level_slabs[l]));
+            for (uint32_t i = level_ptr[l]; i < level_ptr[l + 1]; ++i)
+                for (uint32_t h = 0; h < diag_slabs(order[i]); ++h) fwd.push_back(diag_task(order[i], h, false));
+            for (uint32_t i = level_ptr[l]; i < level_ptr[l + 1]; ++i) {
+                const uint32_t s = order[i], m = panel_rows(s), slabs = panel_slabs(s), skip = inside(s);
                 for (uint32_t h = 0; h < slabs;) {
                     SweepTask t = base_task(s);
-                    t.Kind = 1, t.Base = sym.PanelOffset[s] + t.K, t.Limit = m, t.Ld = t.K + m, t.Row0 = h * kSolveRows, t.Need = diag_slabs(s);
+                    t.Kind = 1, t.Base = sym.PanelOffset[s] + t.K, t.Limit = m, t.Ld = t.K + m, t.Row0 = skip + h * kSolveRows, t.Need = diag_slabs(s);
                     t.LinkBegin = uint32_t(fwd_links.size());
                     // as many slabs as the run allows while the arrivals owed still fit the publishing warp
                     uint32_t count = 0;
@@ -432,12 +487,12 @@ void BuildSchedules(Symbolic &sym) {
         for (auto &t : fwd)
             if (t.Kind == 0) t.Need = fwd_expected[t.Super];
         for (uint32_t l = sym.NumLevels; l-- > 0;) {
-            const uint32_t run = std::max(1u, run_of(l));
-            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) {
-                const uint32_t s = sym.LevelOrder[i], m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]), slabs = panel_slabs(s);
+            const uint32_t run = std::max(1u, run_of(level_slabs[l]));
+            for (uint32_t i = level_ptr[l]; i < level_ptr[l + 1]; ++i) {
+                const uint32_t s = order[i], m = panel_rows(s), slabs = panel_slabs(s), skip = inside(s);
                 for (uint32_t h = 0; h < slabs; h += run) {
                     SweepTask t = base_task(s);
-                    t.Kind = 1, t.Base = sym.PanelOffset[s] - sym.InvOffset[s], t.Limit = m, t.Ld = t.K, t.Row0 = h * kSolveRows;
+                    t.Kind = 1, t.Base = sym.PanelOffset[s] - sym.InvOffset[s], t.Limit = m, t.Ld = t.K, t.Row0 = skip + h * kSolveRows;
                     t.Count = std::min(run, slabs - h);
                     t.LinkBegin = uint32_t(bwd_links.size());
                     targets_of(s, h, t.Count, bwd_links, t.LinkBegin);
@@ -447,9 +502,9 @@ void BuildSchedules(Symbolic &sym) {
                     bwd.push_back(t);
                 }
             }
-            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i)
-                for (uint32_t h = 0; h < diag_slabs(sym.LevelOrder[i]); ++h) {
-                    SweepTask t = diag_task(sym.LevelOrder[i], h);
+            for (uint32_t i = level_ptr[l]; i < level_ptr[l + 1]; ++i)
+                for (uint32_t h = 0; h < diag_slabs(order[i]); ++h) {
+                    SweepTask t = diag_task(order[i], h, true);
                     t.Need = bwd_expected[t.Super];
                     bwd.push_back(t);
                 }
@@ -459,7 +514,8 @@ void BuildSchedules(Symbolic &sym) {
     bool single_failed = false;
     std::thread single([&] {
         try {
-            make_schedules([](uint32_t) { return 1u; }, UINT32_MAX, sym.FwdTasks, sym.FwdLinks, sym.BwdTasks, sym.BwdLinks, sym.BwdLinkNeed);
+            std::vector<uint32_t> fwd_need, bwd_need;
+            make_schedules(false, [](uint32_t) { return 1u; }, UINT32_MAX, sym.FwdTasks, sym.FwdLinks, sym.BwdTasks, sym.BwdLinks, sym.BwdLinkNeed, fwd_need, bwd_need, nullptr);
         } catch (...) {
             single_failed = true;
         }
@@ -470,14 +526,11 @@ void BuildSchedules(Symbolic &sym) {
             if (T.joinable()) T.join();
         }
     } join{single};
-    // Panel sweeps: runs on the levels wide enough to still hand every resident CTA (5 per SM x 148 SMs) a run of its own.
+    // Panel sweeps: macro blocks, and runs on the levels wide enough to still hand every resident CTA (5 per SM x 148 SMs) a run of its own.
     {
-        std::vector<uint32_t> level_slabs(sym.NumLevels, 0);
-        for (uint32_t l = 0; l < sym.NumLevels; ++l)
-            for (uint32_t i = sym.LevelPtr[l]; i < sym.LevelPtr[l + 1]; ++i) level_slabs[l] += panel_slabs(sym.LevelOrder[i]);
         constexpr uint32_t resident = 5 * 148;
-        make_schedules([&](uint32_t l) { return std::min(kWideRun, level_slabs[l] / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
-                       sym.WideBwdLinkNeed);
+        make_schedules(true, [&](uint32_t slabs) { return std::min(kWideRun, slabs / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
+                       sym.WideBwdLinkNeed, sym.WideFwdNeed, sym.WideBwdNeed, &sym.SweepLevels);
     }
     single.join();
     if (single_failed) throw std::bad_alloc();

@@ -14,6 +14,7 @@ namespace me {
 struct SymbolicOptions {
     uint32_t LeafNodes{40};   // dissection stops at subdomains of at most this many nodes (one dense leaf supernode)
     uint32_t PanelNodes{42};  // separators are split into chain panels of at most this many nodes (126 columns <= 128)
+    uint32_t MacroPanels{4};  // panel sweeps: consecutive panels of a chain solved as one block through its explicit inverse (1 = off)
 };
 
 // One tile of the trailing update of supernode S into the panel of an ancestor (see cholesky.cu SyrkScatterKernel).
@@ -31,17 +32,18 @@ constexpr uint32_t kWideRun = 8;     // longest run of slabs in one task of the 
 constexpr uint32_t kWideRunLinks = 32; // a forward run owes at most this many arrivals (one per lane of the publishing warp)
 struct alignas(64) SweepTask {
     uint64_t Base;       // offset in doubles of the matrix block: into Linv / Linv^T (diag), L (forward panel), LT (backward panel)
-    uint32_t Kind;       // 0 diagonal slab, 1 panel slab
+    uint32_t Kind;       // 0 diagonal slab, 1 panel slab, 2 slab of a macro block's inverse (panel sweeps only)
     uint32_t Super;
-    uint32_t K, Limit;   // columns of the supernode; row limit (k for diagonal slabs, m for panel slabs)
+    uint32_t K, Limit;   // columns of the supernode; row limit (k for diagonal slabs, m for panel slabs; macro slabs: columns of the inverse's row block)
     uint32_t Ld;         // leading dimension of the block
     uint32_t Row0;       // first row of the slab
     uint32_t VecOffset;  // 3 * SuperFirst[s]: where the supernode's own entries sit in the permuted vectors
     uint32_t RowsBase;   // RowPtr[s]: the supernode's below-diagonal node list
-    uint32_t LinkBegin, LinkCount; // ancestors updated (forward panel) / read (backward panel)
+    uint32_t LinkBegin, LinkCount; // ancestors updated (forward panel) / read (backward panel); macro slabs: LinkCount = panels of the macro block whose entries it reads
     uint32_t Need;       // arrivals to wait for: diagonal slab = contributions to the supernode; forward panel = its diagonal slabs
     uint32_t Count;      // panel sweeps (WideTasks): consecutive kSolveRows-row slabs of the panel covered by this task (>= 1)
-    uint32_t Pad[2];
+    uint32_t DiagColumn; // macro slabs, forward: column of the row block where the supernode's own diagonal block starts
+    uint32_t Pad;
 };
 
 struct Symbolic {
@@ -74,6 +76,21 @@ struct Symbolic {
     // the parallelism there is.
     std::vector<SweepTask> WideFwdTasks, WideBwdTasks;
     std::vector<uint32_t> WideFwdLinks, WideBwdLinks, WideBwdLinkNeed;
+    std::vector<uint32_t> WideFwdNeed, WideBwdNeed; // [NumSuper] contributions every supernode's entries wait for in the panel sweeps
+    // Macro blocks of the panel sweeps. The panels of a separator chain depend on each other one after the other (solve the diagonal
+    // block, update the rest of the chain, next panel): two dependent tasks per panel, which on the dense top separators IS the
+    // sweep's critical path. Up to MacroPanels consecutive panels of a chain therefore form a macro block whose lower-triangular
+    // diagonal block (the panels' diagonal blocks and the rows that couple them) is inverted explicitly after the numeric
+    // factorisation (cholesky.cu MacroInverseKernel): all its panels are then solved in ONE step from the block's entries, and
+    // their updates of the rows outside the block follow in one more.
+    std::vector<uint32_t> MacroFirst, MacroLast; // [NumSuper] first and last supernode of the macro block a supernode belongs to
+    std::vector<uint64_t> MacroOffset;        // [NumSuper+1] forward row block of each macro panel i: k_i x (k_0 + .. + k_i), column-major; empty for single supernodes
+    std::vector<uint64_t> MacroOffsetT;       // [NumSuper+1] backward row block: k_i x (k_i + .. + k_last), element (r, c) = inverse(c, r) counted from the panel's own start
+    struct MacroJob {
+        uint32_t First, Last, Column, Slice;  // macro block, which of its panels' columns, which 64-column slice of those
+    };
+    std::vector<MacroJob> MacroJobs;
+    uint32_t SweepLevels{0};                  // dependency levels of the panel sweeps (macro blocks count once)
     uint64_t FactorNonZeros{0};               // scalars stored in the panels
     double FactorFlops{0};
     uint32_t MaxPanelColumns{0}, MaxPanelRows{0};
