@@ -443,7 +443,7 @@ struct SweepArgs {
 };
 __device__ __forceinline__ unsigned long long GlobalTimer() {
     unsigned long long v;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v)::"memory"); // (the clobber keeps the read where it is written: between the barriers)
     return v;
 }
 constexpr int kSweepThreads = 128;
@@ -574,9 +574,9 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
 // over the factor serves all of them, so the bytes per right-hand side drop by kWide while the sweep stays HBM-bound.
 // Vectors are stored [permuted DOF][kWide] (one 64-byte row per DOF: a gathered/scattered row is one full sector pair).
 // Every slab product is a small dense contraction (32 x k times k x 8, or k x 32 times 32 x 8) and runs on the FP64
-// tensor cores: each warp owns a quarter of the contraction (forward/diagonal: a quarter of k, reduced across warps in
-// shared memory; backward: a quarter of the output columns), loads its 32 A-fragments straight from global memory in
-// the m8n8k4 fragment layout (all 32 loads in flight before anything waits), and takes B from the shared k x 8 panel.
+// tensor cores: each warp owns a quarter of it (forward/diagonal: 8 of the 32 rows; backward: a quarter of the output
+// columns), loads its 32 A-fragments straight from global memory in the m8n8k4 fragment layout (all 32 loads in flight
+// before anything waits), and takes B from the shared k x 8 panel (backward: from the solved entries themselves).
 constexpr int kWide = 8;
 
 __device__ __forceinline__ void LoadL2x2(const double *p, unsigned long long &a, unsigned long long &b) {
@@ -617,12 +617,20 @@ __device__ __forceinline__ uint32_t PeekAcquire(const uint32_t *counter) {
     return v;
 }
 
+// Work split inside a task (second form; the first one gave every warp a quarter of the contraction's K and reduced the four
+// partial products through shared memory: three CTA barriers per 32-row slab, and the next slab's loads only issued between
+// them - the task timelines (ME_SWEEP_TRACE) showed ~4 us per slab wherever a slab ran, 8 GB/s per CTA):
+//   * forward panel runs and diagonal slabs: a warp owns 8-ROW STRIPS (strip q, q + 4, ... of the run) over all k columns, so a
+//     strip's 8 x 8 product is complete in the warp's own DMMA accumulators and goes straight to the atomics / the store. After
+//     the run's operand is in shared memory the warps never meet again: each streams its strips, 32 loads in flight per lane.
+//   * backward panel runs: a warp owns 32 output columns (as before) and now gathers the solved entries of a slab's rows itself
+//     (64-byte rows from L2, the node ids from the read-only row lists) instead of through a shared copy with two barriers.
+constexpr int kWideCtasPerSm = 4; // (96 registers per thread at five CTAs per SM spilled the fragments)
 template<bool Backward>
-__global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKernel(SweepArgs a) {
-    __shared__ __align__(16) double vec[128 * kWide];      // the k x 8 (or 32 x 8) right-hand operand
-    __shared__ __align__(16) double part[4 * 32 * kWide];  // per-warp partial products of one slab
+__global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel(SweepArgs a) {
+    __shared__ __align__(16) double vec[128 * kWide]; // the k x 8 right-hand operand of the task
     __shared__ SweepTask s_task;
-    __shared__ uint32_t s_id, s_node[kSolveRows];
+    __shared__ uint32_t s_id;
     const uint32_t t = threadIdx.x, lane = t & 31, q = t >> 5, fr = lane >> 2, fk = lane & 3;
     // Warp 0 keeps two claimed tickets: `id1` with its 64-byte descriptor already requested (8 lanes x 8 bytes), and `id2`
     // whose atomic may still be in flight. Both are consumed one iteration after they were issued.
@@ -638,30 +646,24 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
         if (lane < 8 && id1 < a.NumTasks) word1 = reinterpret_cast<const uint64_t *>(a.Tasks + id1)[lane];
         id2 = claim();
     }
-    // Counter increments owed by the previous task, held by warp 3 (one counter per lane): arrivals of a panel slab's
+    // Counter increments owed by the previous task, held by warp 3 (one counter per lane): arrivals of a panel run's
     // contributions, or the publication of a diagonal slab's results.
     uint32_t *owed = nullptr;
-    // C[32 x 8] partial of this warp = A-fragments val[mi*8+ks] (rows 8mi.., k-steps of the warp's quarter) times vec.
-    auto contract_quarter = [&](const double (&val)[32], double (&c)[4][2]) {
+    // C[8 x 8] += A-fragments val[ks] (the strip's rows, k-steps 4 ks .. 4 ks + 3) times vec, on four accumulator chains.
+    auto contract_strip = [&](const double (&val)[32], uint32_t ksteps, double &c0, double &c1) {
+        double acc[4][2]{};
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-            const double b = vec[(32 * q + 4 * ks + fk) * kWide + fr];
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b);
-        }
+        for (int ks = 0; ks < 32; ++ks)
+            if (uint32_t(ks) < ksteps) Dmma(acc[ks & 3][0], acc[ks & 3][1], val[ks], vec[(4 * ks + fk) * kWide + fr]);
+        c0 += (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+        c1 += (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
     };
-    auto store_partials = [&](const double (&c)[4][2]) {
-#pragma unroll
-        for (int mi = 0; mi < 4; ++mi)
-            *reinterpret_cast<double2 *>(&part[(q * 32 + 8 * mi + fr) * kWide + 2 * fk]) = make_double2(c[mi][0], c[mi][1]);
-    };
-    auto reduced = [&](uint32_t idx) { return (part[idx] + part[256 + idx]) + (part[512 + idx] + part[768 + idx]); };
     uint32_t traced = 0xFFFFFFFFu;
     auto stamp = [&](uint32_t id, uint32_t slot) {
         if (a.Trace && t == 0 && id != 0xFFFFFFFFu) a.Trace[size_t(3) * id + slot] = GlobalTimer();
     };
     for (;;) {
-        __syncthreads(); // every contribution of the previous task has been issued; its shared operands are free
+        __syncthreads(); // every contribution of the previous task has been issued; its shared operand is free
         if (owed) ArriveRelease(owed);
         owed = nullptr;
         stamp(traced, 2);
@@ -689,20 +691,20 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
             //   forward   out_S[rows] = sum over the block's panels up to S of  W[rows of S, their columns] acc[their entries]
             //   backward  out_S[rows] = sum over the block's panels from S on of W^T[...]
             // Forward the own diagonal block is the LAST of the row block (it starts at column DiagColumn), backward the first.
+            // Warp q computes rows Row0 + 8 q .. + 7.
             const bool macro = task.Kind == 2;
             const double *mat = (macro ? a.Macro : a.Diag) + task.Base;
             const uint32_t diag_col = Backward ? 0u : task.DiagColumn;
             const uint32_t in_base = task.VecOffset - diag_col;
             const uint32_t col_end = Backward ? task.Limit : min(task.Limit, diag_col + task.Row0 + kSolveRows);
+            const uint32_t row = task.Row0 + 8 * q + fr;
             auto load_chunk = [&](uint32_t c0) {
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t row = task.Row0 + 8 * mi + fr, col = c0 + 32 * q + 4 * ks + fk;
-                        const bool in = row < k && col < col_end && (Backward ? col >= row : col <= diag_col + row);
-                        val[mi * 8 + ks] = in ? mat[row + size_t(col) * k] : 0.0;
-                    }
+                for (int ks = 0; ks < 32; ++ks) {
+                    const uint32_t col = c0 + 4 * ks + fk;
+                    const bool in = row < k && col < col_end && (Backward ? col >= row : col <= diag_col + row);
+                    val[ks] = in ? mat[row + size_t(col) * k] : 0.0;
+                }
             };
             load_chunk(0);
             if (!macro) {
@@ -720,43 +722,44 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                     __nanosleep(20);
                 }
             }
-            double c[4][2]{};
-            for (uint32_t c0 = 0; c0 < col_end; c0 += 128) {
+            double c0 = 0, c1 = 0;
+            for (uint32_t col0 = 0; col0 < col_end; col0 += 128) {
                 __syncthreads(); // the entries are complete (first chunk) / the previous chunk's operand has been consumed
-                if (c0 == 0) stamp(id, 1);
+                if (col0 == 0) stamp(id, 1);
                 {
-                    const double2 *src = reinterpret_cast<const double2 *>(a.Acc + (size_t(in_base) + c0 + t) * kWide);
+                    const double2 *src = reinterpret_cast<const double2 *>(a.Acc + (size_t(in_base) + col0 + t) * kWide);
                     double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
 #pragma unroll
-                    for (int j = 0; j < kWide / 2; ++j) dst[j] = c0 + t < col_end ? __ldcg(src + j) : make_double2(0.0, 0.0);
+                    for (int j = 0; j < kWide / 2; ++j) dst[j] = col0 + t < col_end ? __ldcg(src + j) : make_double2(0.0, 0.0);
                 }
                 __syncthreads();
-                contract_quarter(val, c);
-                if (c0 + 128 < col_end) load_chunk(c0 + 128);
+                contract_strip(val, (min(col_end - col0, 128u) + 3) >> 2, c0, c1);
+                if (col0 + 128 < col_end) load_chunk(col0 + 128);
             }
-            store_partials(c);
-            __syncthreads();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t idx = t + 128 * h, row = task.Row0 + idx / kWide;
-                if (row < k) StoreL2(a.Out + (size_t(task.VecOffset) + row) * kWide + idx % kWide, reduced(idx));
+            if (row < k) {
+                double *dst = a.Out + (size_t(task.VecOffset) + row) * kWide + 2 * fk;
+                StoreL2(dst, c0);
+                StoreL2(dst + 1, c1);
             }
             if (t == 96) owed = a.Solved + task.Super;
         } else if constexpr (!Backward) {
-            // A run of task.Count consecutive 32-row slabs of one panel: acc[rows] -= P_slab out_S, slab after slab. The run
-            // shares the wait for out_S, the k x 8 operand in shared memory, the ticket and the arrivals it owes.
+            // A run of task.Count consecutive 32-row slabs of one panel: acc[rows] -= P[rows, :] out_S. The run shares the wait for
+            // out_S, the k x 8 operand in shared memory, the ticket and the arrivals it owes; warp q takes the 8-row strips
+            // q, q + 4, ... of the run and never meets the other warps again.
             const double *p0 = a.Panel + task.Base;
-            auto load_slab = [&](uint32_t row0) {
+            const uint32_t row_end = min(task.Limit, task.Row0 + task.Count * kSolveRows), ksteps = (k + 3) >> 2;
+            auto load_strip = [&](uint32_t r0) {
+                const uint32_t row = r0 + fr;
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t row = row0 + 8 * mi + fr, col = 32 * q + 4 * ks + fk;
-                        val[mi * 8 + ks] = (row < task.Limit && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
-                    }
+                for (int ks = 0; ks < 32; ++ks) {
+                    const uint32_t col = 4 * ks + fk;
+                    val[ks] = (row < row_end && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
+                }
             };
-            load_slab(task.Row0);
-            if (t < kSolveRows) s_node[t] = task.Row0 + t < task.Limit ? a.Rows[task.RowsBase + (task.Row0 + t) / 3] : 0;
+            auto node_of = [&](uint32_t row) { return row < row_end ? __ldg(a.Rows + task.RowsBase + row / 3) : 0u; };
+            uint32_t r0 = task.Row0 + 8 * q;
+            load_strip(r0);
+            uint32_t node = node_of(r0 + fr);
             if (q == 3 && lane < task.LinkCount) owed = a.Arrived + a.Links[task.LinkBegin + lane];
             if (t == 96) { // out_S is complete once its diagonal slabs have all published
                 for (uint32_t spin = 0; PeekAcquire(a.Solved + task.Super) < task.Need; ++spin) {
@@ -772,40 +775,39 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
 #pragma unroll
                 for (int j = 0; j < kWide / 2; ++j) dst[j] = t < k ? __ldcg(src + j) : make_double2(0.0, 0.0);
             }
-            for (uint32_t slab = 0;; ++slab) {
-                const uint32_t row0 = task.Row0 + slab * kSolveRows;
-                __syncthreads(); // vec (first slab) / s_node and the previous slab's partials are settled
-                double c[4][2]{};
-                contract_quarter(val, c);
-                store_partials(c);
-                const bool more = slab + 1 < task.Count;
-                if (more) load_slab(row0 + kSolveRows); // in flight while this slab is reduced and scattered
-                __syncthreads();
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t idx = t + 128 * h, lr = idx / kWide, row = row0 + lr;
-                    if (row < task.Limit) atomicAdd(a.Acc + (size_t(3) * s_node[lr] + row % 3) * kWide + idx % kWide, -reduced(idx));
+            __syncthreads();
+            for (; r0 < row_end; r0 += kSolveRows) {
+                double c0 = 0, c1 = 0;
+                contract_strip(val, ksteps, c0, c1);
+                const uint32_t row = r0 + fr, mine = node;
+                if (r0 + kSolveRows < row_end) { // the next strip is in flight while this one is scattered
+                    load_strip(r0 + kSolveRows);
+                    node = node_of(r0 + kSolveRows + fr);
                 }
-                if (!more) break;
-                __syncthreads(); // every thread has read s_node / the partials of this slab
-                if (t < kSolveRows) s_node[t] = row0 + kSolveRows + t < task.Limit ? a.Rows[task.RowsBase + (row0 + kSolveRows + t) / 3] : 0;
+                if (row < row_end) {
+                    double *dst = a.Acc + (size_t(3) * mine + row % 3) * kWide + 2 * fk;
+                    atomicAdd(dst, -c0);
+                    atomicAdd(dst + 1, -c1);
+                }
             }
         } else {
             // A run of task.Count consecutive 32-row slabs: acc_S[k x 8] -= sum over the slabs of P_slab^T [k x 32] out[slab rows
             // x 8]. Warp q owns output columns 32q .. 32q+31 of the supernode and keeps their sums in its DMMA accumulators
-            // across the run: ONE set of FP64 atomics per run instead of one per slab (k x 8 atomics each, all slabs of a
-            // supernode onto the same k x 8 addresses: they were what the backward sweep waited for).
+            // across the run: ONE set of FP64 atomics per run. The solved entries of a slab's rows are gathered by every warp for
+            // itself (B fragment: row 4 ks + fk of the slab, right-hand side fr).
             const double *pt = a.Panel + task.Base;
+            const uint32_t row_end = min(task.Limit, task.Row0 + task.Count * kSolveRows);
+            const bool active = 32 * q < k; // (a narrow supernode leaves the upper warps without columns)
             auto load_slab = [&](uint32_t row0) {
 #pragma unroll
                 for (int mi = 0; mi < 4; ++mi)
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks) {
                         const uint32_t col = 32 * q + 8 * mi + fr, row = row0 + 4 * ks + fk;
-                        val[mi * 8 + ks] = (row < task.Limit && col < k) ? pt[size_t(row) * k + col] : 0.0;
+                        val[mi * 8 + ks] = (row < row_end && col < k) ? pt[size_t(row) * k + col] : 0.0;
                     }
             };
-            load_slab(task.Row0);
+            if (active) load_slab(task.Row0);
             if (t == 96) owed = a.Arrived + task.Super;
             if (q == 3) { // the ancestors owning the run's rows: polled by the lanes of one warp
                 for (uint32_t i = lane; i < task.LinkCount; i += 32) {
@@ -817,37 +819,32 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) WideSweepKerne
                     }
                 }
             }
-            const uint32_t vr = t >> 2;
-            // this thread's row of the slab -> the node owning it (fetched one slab ahead: the solved entries hang off it)
-            auto node_of = [&](uint32_t row) { return row < task.Limit ? a.Rows[task.RowsBase + row / 3] : 0u; };
-            uint32_t node = node_of(task.Row0 + vr);
-            double c[4][2]{};
-            for (uint32_t slab = 0; slab < task.Count; ++slab) {
-                const uint32_t row0 = task.Row0 + slab * kSolveRows, row = row0 + vr;
-                __syncthreads(); // the links are solved (first slab); the previous slab's operand has been consumed
-                if (slab == 0) stamp(id, 1);
-                {
-                    double2 x = make_double2(0.0, 0.0);
-                    if (row < task.Limit) x = __ldcg(reinterpret_cast<const double2 *>(a.Out + (size_t(3) * node + row % 3) * kWide + 2 * (t & 3)));
-                    if (slab + 1 < task.Count) node = node_of(row + kSolveRows);
-                    vec[vr * kWide + 2 * (t & 3)] = x.x, vec[vr * kWide + 2 * (t & 3) + 1] = x.y;
+            __syncthreads(); // the links are solved
+            stamp(id, 1);
+            if (active) {
+                double c[4][2]{};
+                for (uint32_t row0 = task.Row0; row0 < row_end; row0 += kSolveRows) {
+                    double b[8];
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        const uint32_t row = row0 + 4 * ks + fk;
+                        b[ks] = 0.0;
+                        if (row < row_end) b[ks] = __ldcg(a.Out + (size_t(3) * __ldg(a.Rows + task.RowsBase + row / 3) + row % 3) * kWide + fr);
+                    }
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                        for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b[ks]);
+                    if (row0 + kSolveRows < row_end) load_slab(row0 + kSolveRows);
                 }
-                __syncthreads();
 #pragma unroll
-                for (int ks = 0; ks < 8; ++ks) {
-                    const double b = vec[(4 * ks + fk) * kWide + fr];
-#pragma unroll
-                    for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b);
-                }
-                if (slab + 1 < task.Count) load_slab(row0 + kSolveRows);
-            }
-#pragma unroll
-            for (int mi = 0; mi < 4; ++mi) {
-                const uint32_t col = 32 * q + 8 * mi + fr;
-                if (col < k) {
-                    double *dst = a.Acc + (size_t(task.VecOffset) + col) * kWide + 2 * fk;
-                    atomicAdd(dst, -c[mi][0]);
-                    atomicAdd(dst + 1, -c[mi][1]);
+                for (int mi = 0; mi < 4; ++mi) {
+                    const uint32_t col = 32 * q + 8 * mi + fr;
+                    if (col < k) {
+                        double *dst = a.Acc + (size_t(task.VecOffset) + col) * kWide + 2 * fk;
+                        atomicAdd(dst, -c[mi][0]);
+                        atomicAdd(dst + 1, -c[mi][1]);
+                    }
                 }
             }
         }
@@ -1110,7 +1107,8 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
             continue;
         }
         const uint32_t w = std::min<uint32_t>(left, kWide);
-        const char *trace_path = TraceDone ? nullptr : std::getenv("ME_SWEEP_TRACE");
+        static bool trace_done = false; // one timeline per process: the first panel application of the first factor
+        const char *trace_path = trace_done ? nullptr : std::getenv("ME_SWEEP_TRACE");
         DeviceBuffer<unsigned long long> trace;
         if (trace_path) {
             trace.Reserve(size_t(3) * (wide_fwd.NumTasks + wide_bwd.NumTasks));
@@ -1137,7 +1135,7 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
                 std::fclose(f);
             }
             wide_fwd.Trace = wide_bwd.Trace = nullptr;
-            TraceDone = true;
+            trace_done = true;
         }
         Stats.KernelLaunches += 4;
         rhs += w;

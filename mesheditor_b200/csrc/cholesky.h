@@ -64,7 +64,6 @@ private:
     bool SchedulesUploaded{false};
     void UploadSchedules(); // waits for the background construction of the solve schedules (symbolic.h) and uploads them
     uint32_t SolvesSinceCheck{0};
-    bool TraceDone{false}; // ME_SWEEP_TRACE=<file>: the first panel application's task timeline is written once
 };
 
 // FP64 issue-rate micro-benchmark: mode 0 = DFMA, 1 = DMMA m8n8k4. Returns flop/s.

@@ -526,9 +526,9 @@ void BuildSchedules(Symbolic &sym) {
             if (T.joinable()) T.join();
         }
     } join{single};
-    // Panel sweeps: macro blocks, and runs on the levels wide enough to still hand every resident CTA (5 per SM x 148 SMs) a run of its own.
+    // Panel sweeps: macro blocks, and runs on the levels wide enough to still hand every resident CTA (4 per SM x 148 SMs) a run of its own.
     {
-        constexpr uint32_t resident = 5 * 148;
+        constexpr uint32_t resident = 4 * 148;
         make_schedules(true, [&](uint32_t slabs) { return std::min(kWideRun, slabs / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
                        sym.WideBwdLinkNeed, sym.WideFwdNeed, sym.WideBwdNeed, &sym.SweepLevels);
     }
