@@ -26,9 +26,15 @@ struct FactorView {
     const uint32_t *SuperFirst, *Rows, *NodeSuper;
     const uint64_t *RowPtr, *PanelOffset, *InvOffset;
     const uint32_t *SegTarget, *SegBegin, *SegEnd;
-    double *L, *Linv, *LinvT, *LT; // LT: the below-diagonal rectangles again, transposed ([row][column]), for the backward sweep
+    double *L, *Linv, *LinvT, *Slabs; // Slabs: the below-diagonal rectangles again, in 32-row slabs of 8 x 8 tiles (Symbolic::SlabOffset), for the sweeps
     int *Fail;
+    const uint64_t *SlabOffset;
 };
+
+// Position of element (row, col) of a supernode's rectangle inside its slab copy; kp = columns rounded up to 8.
+__device__ __forceinline__ size_t SlabIndex(uint32_t row, uint32_t col, uint32_t kp) {
+    return size_t(row >> 5) * (kSolveRows * kp) + (((row >> 3) & 3) * (kp >> 3) + (col >> 3)) * 64 + (row & 7) * 8 + (col & 7);
+}
 
 __device__ __forceinline__ uint32_t PanelColumns(const FactorView &v, uint32_t s) { return 3 * (v.SuperFirst[s + 1] - v.SuperFirst[s]); }
 __device__ __forceinline__ uint32_t PanelRows(const FactorView &v, uint32_t s) { return 3 * uint32_t(v.RowPtr[s + 1] - v.RowPtr[s]); }
@@ -146,7 +152,8 @@ __global__ void __launch_bounds__(kTrsmThreads) PanelTrsmKernel(FactorView v, co
     const uint32_t s = tile.Super, k = PanelColumns(v, s), m = PanelRows(v, s), ld = k + m;
     double *p0 = v.L + v.PanelOffset[s] + k;
     const double *linv = v.Linv + v.InvOffset[s];
-    double *pt = v.LT + (v.PanelOffset[s] - v.InvOffset[s]);
+    double *slabs = v.Slabs + v.SlabOffset[s];
+    const uint32_t kp = (k + 7) & ~7u;
     const uint32_t row0 = tile.RowTile * kTile, nrows = min(kTile, m - row0);
     const uint32_t t = threadIdx.x, lane = t & 31, w = t >> 5, wm = w & 1, wn = w >> 1;
     for (uint32_t idx = t; idx < 128 * 64; idx += kTrsmThreads) {
@@ -184,7 +191,7 @@ __global__ void __launch_bounds__(kTrsmThreads) PanelTrsmKernel(FactorView v, co
                 const uint32_t r = 32 * wm + 8 * mi + (lane >> 2), c = 32 * wn + 8 * ni + 2 * (lane & 3) + e;
                 if (r < nrows && c < k) {
                     p0[row0 + r + size_t(c) * ld] = acc[mi][ni][e];
-                    pt[size_t(row0 + r) * k + c] = acc[mi][ni][e];
+                    slabs[SlabIndex(row0 + r, c, kp)] = acc[mi][ni][e];
                 }
             }
 }
@@ -434,7 +441,7 @@ struct SweepArgs {
     uint32_t *Ticket, *Arrived;
     uint32_t *Solved;                 // panel sweeps: diagonal slabs of each supernode whose results are published
     const uint32_t *Rows;             // below-diagonal node lists of all supernodes
-    const double *Diag, *Panel;       // Linv + L (forward) or Linv^T + LT (backward)
+    const double *Diag, *Panel;       // Linv + L (forward) or Linv^T + the slab copy (backward; the panel sweeps: the slab copy both ways)
     double *Acc, *Out;
     int *Fail;
     const double *Macro;              // panel sweeps: row blocks of the macro blocks' inverses (forward) / of their transposes (backward)
@@ -551,9 +558,10 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepCtasPerSm) SweepKernel(Sw
         } else {
             // acc_S -= P_slab^T out[slab rows] once the ancestors owning those rows are solved. Read from the transposed
             // panel copy ([row][column]): thread = column, so the sum over the slab's rows stays in one register.
-            const double *pt = a.Panel + task.Base;
+            const double *pt = a.Panel + task.Base + (t >> 3) * 64 + (t & 7); // the task's slab of the slab copy: 8 x 8 tiles, [strip][column tile]
+            const uint32_t strip = ((k + 7) >> 3) * 64;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) val[j] = (task.Row0 + j < task.Limit && t < k) ? pt[size_t(task.Row0 + j) * k + t] : 0.0;
+            for (int j = 0; j < 32; ++j) val[j] = (task.Row0 + j < task.Limit && t < k) ? pt[(j >> 3) * strip + (j & 7) * 8] : 0.0;
             uint32_t node = 0;
             if (t < kSolveRows && task.Row0 + t < task.Limit) node = a.Rows[task.RowsBase + (task.Row0 + t) / 3];
             prefetch_next();
@@ -617,38 +625,112 @@ __device__ __forceinline__ uint32_t PeekAcquire(const uint32_t *counter) {
     return v;
 }
 
-// Work split inside a task (second form; the first one gave every warp a quarter of the contraction's K and reduced the four
-// partial products through shared memory: three CTA barriers per 32-row slab, and the next slab's loads only issued between
-// them - the task timelines (ME_SWEEP_TRACE) showed ~4 us per slab wherever a slab ran, 8 GB/s per CTA):
-//   * forward panel runs and diagonal slabs: a warp owns 8-ROW STRIPS (strip q, q + 4, ... of the run) over all k columns, so a
-//     strip's 8 x 8 product is complete in the warp's own DMMA accumulators and goes straight to the atomics / the store. After
-//     the run's operand is in shared memory the warps never meet again: each streams its strips, 32 loads in flight per lane.
-//   * backward panel runs: a warp owns 32 output columns (as before) and now gathers the solved entries of a slab's rows itself
-//     (64-byte rows from L2, the node ids from the read-only row lists) instead of through a shared copy with two barriers.
-constexpr int kWideCtasPerSm = 4; // (96 registers per thread at five CTAs per SM spilled the fragments)
+// Third form of the kernel (the timelines written by ME_SWEEP_TRACE decided it): with every warp loading its own fragments
+// from global memory, a CTA had its 32 KB of loads in flight for about half of its ~4 us per slab, and the 600-740 resident CTAs
+// together streamed the factor at 2.5-3.4 TB/s wherever the tree was wide, working 85 % of the time. A probe of the same access
+// shape without the arithmetic reaches 6 TB/s, and whole slabs copied by cp.async.bulk into a shared-memory ring reach 7.5 TB/s
+// (scripts/probes/stream_patterns.cu). So the matrix now travels on its own:
+//   * the below-diagonal rectangles are kept a second time as contiguous 32-row slabs of 8 x 8 tiles (FactorView::Slabs,
+//     written by PanelTrsmKernel); a slab is ONE bulk copy;
+//   * a PRODUCER warp claims the tickets, hands each task's descriptor to the consumers through a small queue in shared memory
+//     and streams the task's slabs into a ring of kWideStages buffers (mbarrier complete_tx / per-stage empty barriers). The
+//     matrix has no dependencies, so the producer runs ahead of the consumers, into the next tasks, as far as the ring allows:
+//     while the consumers wait for a task's inputs, its slabs and the next tasks' are already arriving;
+//   * four CONSUMER warps do what the warps of the second form did (forward: a warp owns the 8-row strip q of every slab and its
+//     8 x 8 product goes straight to the atomics; backward: a warp owns 32 output columns and gathers the solved entries of a
+//     slab's rows itself), reading fragments from shared memory: a forward tile is one conflict-free 16-byte load per lane
+//     feeding two DMMAs (columns {0,2,4,6} and {1,3,5,7} of the tile: the contraction does not care about the order), a backward
+//     half-tile is 256 contiguous bytes. They meet only at a task's handshakes (a named barrier of the 128 consumer threads).
+// Diagonal / macro slabs still load their fragments from global memory (4 % of the bytes).
+constexpr int kWideThreads = 160, kWideConsumers = 128;
+constexpr int kWideStages = 3, kWideQueue = 4;
+constexpr uint32_t kSlabDoubles = kSolveRows * 128;
+struct WideShared {
+    double Ring[kWideStages][kSlabDoubles]; // slabs in flight / being consumed
+    double Vec[128 * kWide];                // the task's k x 8 right-hand operand
+    SweepTask Queue[kWideQueue];
+    uint32_t QueueId[kWideQueue];           // the tasks' tickets (for the timeline)
+    uint64_t Full[kWideStages], Empty[kWideStages], QueueFull[kWideQueue], QueueEmpty[kWideQueue];
+};
+constexpr uint32_t kTerminator = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t SmemAddr(const void *p) { return uint32_t(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void MbarInit(uint64_t *bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count)); }
+__device__ __forceinline__ void MbarExpectTx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void MbarArrive(uint64_t *bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(SmemAddr(bar)) : "memory"); }
+__device__ __forceinline__ void MbarWait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MBAR_DONE;\n"
+        "bra MBAR_WAIT;\n"
+        "MBAR_DONE:\n"
+        "}" ::"r"(SmemAddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void BulkLoad(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(SmemAddr(dst)), "l"(src), "r"(bytes), "r"(SmemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ConsumerBarrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
 template<bool Backward>
-__global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel(SweepArgs a) {
-    __shared__ __align__(16) double vec[128 * kWide]; // the k x 8 right-hand operand of the task
-    __shared__ SweepTask s_task;
-    __shared__ uint32_t s_id;
+__global__ void __launch_bounds__(kWideThreads, 2) WideSweepKernel(SweepArgs a) {
+    extern __shared__ __align__(128) unsigned char wide_shared[];
+    WideShared &sh = *reinterpret_cast<WideShared *>(wide_shared);
     const uint32_t t = threadIdx.x, lane = t & 31, q = t >> 5, fr = lane >> 2, fk = lane & 3;
-    // Warp 0 keeps two claimed tickets: `id1` with its 64-byte descriptor already requested (8 lanes x 8 bytes), and `id2`
-    // whose atomic may still be in flight. Both are consumed one iteration after they were issued.
-    uint32_t id1 = 0, id2 = 0;
-    uint64_t word1 = 0;
-    auto claim = [&]() -> uint32_t {
-        uint32_t id = 0;
-        if (lane == 0) id = atomicAdd(a.Ticket, 1u);
-        return id;
-    };
-    if (q == 0) {
-        id1 = __shfl_sync(0xffffffffu, claim(), 0);
-        if (lane < 8 && id1 < a.NumTasks) word1 = reinterpret_cast<const uint64_t *>(a.Tasks + id1)[lane];
-        id2 = claim();
+    if (t == 0) {
+        for (int i = 0; i < kWideStages; ++i) MbarInit(sh.Full + i, 1), MbarInit(sh.Empty + i, 4);
+        for (int i = 0; i < kWideQueue; ++i) MbarInit(sh.QueueFull + i, 1), MbarInit(sh.QueueEmpty + i, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // Counter increments owed by the previous task, held by warp 3 (one counter per lane): arrivals of a panel run's
-    // contributions, or the publication of a diagonal slab's results.
-    uint32_t *owed = nullptr;
+    __syncthreads();
+    if (q == 4) {
+        // ---------------------------------------------------------------------------------------------------- producer
+        if (lane != 0) return;
+        uint32_t issued = 0; // slabs sent into the ring so far (the consumers count the same slabs)
+        // One ticket at a time, claimed when the previous task's slabs have all been sent: a version that kept three tickets in
+        // hand (atomic and descriptor never waited for) was 10-30 % SLOWER - a ticket claimed early and served late holds up every
+        // task that depends on it.
+        for (uint32_t n = 0;; ++n) {
+            const uint32_t id = atomicAdd(a.Ticket, 1u);
+            const bool done = id >= a.NumTasks;
+            uint4 w[4]{};
+            if (!done) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(a.Tasks + id);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) w[i] = __ldg(src + i);
+            } else {
+                w[0].z = kTerminator; // SweepTask::Kind
+            }
+            const uint32_t slot = n % kWideQueue, turn = n / kWideQueue;
+            if (turn > 0) MbarWait(sh.QueueEmpty + slot, (turn - 1) & 1);
+            uint4 *dst = reinterpret_cast<uint4 *>(sh.Queue + slot);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = w[i];
+            sh.QueueId[slot] = id;
+            MbarArrive(sh.QueueFull + slot); // (release: the descriptor is visible to whoever sees the phase)
+            if (done) return;
+            if (w[0].z == 1) { // SweepTask: Base (w0.x, w0.y), Kind w0.z, Super w0.w, K w1.x, ..., Count w3.y
+                const uint64_t base = uint64_t(w[0].x) | (uint64_t(w[0].y) << 32);
+                const uint32_t slab = kSolveRows * ((w[1].x + 7) & ~7u), count = w[3].y;
+                for (uint32_t i = 0; i < count; ++i, ++issued) {
+                    const uint32_t stage = issued % kWideStages, round = issued / kWideStages;
+                    if (round > 0) MbarWait(sh.Empty + stage, (round - 1) & 1);
+                    MbarExpectTx(sh.Full + stage, slab * 8);
+                    BulkLoad(sh.Ring[stage], a.Panel + base + size_t(i) * slab, slab * 8, sh.Full + stage);
+                }
+            }
+        }
+    }
+    // ------------------------------------------------------------------------------------------------------- consumers
+    double *vec = sh.Vec;
+    uint32_t consumed = 0; // slabs taken out of the ring so far
     // C[8 x 8] += A-fragments val[ks] (the strip's rows, k-steps 4 ks .. 4 ks + 3) times vec, on four accumulator chains.
     auto contract_strip = [&](const double (&val)[32], uint32_t ksteps, double &c0, double &c1) {
         double acc[4][2]{};
@@ -658,46 +740,36 @@ __global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel
         c0 += (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
         c1 += (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
     };
-    uint32_t traced = 0xFFFFFFFFu;
     auto stamp = [&](uint32_t id, uint32_t slot) {
-        if (a.Trace && t == 0 && id != 0xFFFFFFFFu) a.Trace[size_t(3) * id + slot] = GlobalTimer();
+        if (a.Trace && t == 0) a.Trace[size_t(3) * id + slot] = GlobalTimer();
     };
-    for (;;) {
-        __syncthreads(); // every contribution of the previous task has been issued; its shared operand is free
-        if (owed) ArriveRelease(owed);
-        owed = nullptr;
-        stamp(traced, 2);
-        if (q == 0) {
-            if (lane < 8) reinterpret_cast<uint64_t *>(&s_task)[lane] = word1;
-            if (lane == 0) s_id = id1;
-        }
-        __syncthreads();
-        const uint32_t id = s_id;
-        if (id >= a.NumTasks) return;
-        traced = id;
+    for (uint32_t n = 0;; ++n) {
+        const uint32_t slot = n % kWideQueue;
+        MbarWait(sh.QueueFull + slot, (n / kWideQueue) & 1);
+        const SweepTask task = sh.Queue[slot];
+        const uint32_t id = sh.QueueId[slot];
+        __syncwarp();
+        if (lane == 0) MbarArrive(sh.QueueEmpty + slot);
+        if (task.Kind == kTerminator) return;
         stamp(id, 0);
-        const SweepTask task = s_task;
         const uint32_t k = task.K;
-        if (q == 0) { // shift the ticket pipeline
-            id1 = __shfl_sync(0xffffffffu, id2, 0);
-            word1 = 0;
-            if (lane < 8 && id1 < a.NumTasks) word1 = reinterpret_cast<const uint64_t *>(a.Tasks + id1)[lane];
-            id2 = claim();
-        }
-        double val[32];
+        // Counter increments owed by this task, held by warp 3 (one counter per lane): arrivals of a panel run's contributions, or
+        // the publication of a diagonal slab's results. Released after the consumers' barrier that ends the task.
+        uint32_t *owed = nullptr;
         if (task.Kind != 1) {
             // A 32-row slab of a diagonal block's inverse (Kind 0: k columns) or of a macro block's inverse (Kind 2: the row block of
             // this panel, task.Limit columns over the entries of task.LinkCount consecutive panels, walked in chunks of 128 columns):
             //   forward   out_S[rows] = sum over the block's panels up to S of  W[rows of S, their columns] acc[their entries]
             //   backward  out_S[rows] = sum over the block's panels from S on of W^T[...]
             // Forward the own diagonal block is the LAST of the row block (it starts at column DiagColumn), backward the first.
-            // Warp q computes rows Row0 + 8 q .. + 7.
+            // Warp q computes rows Row0 + 8 q .. + 7 from fragments it loads itself.
             const bool macro = task.Kind == 2;
             const double *mat = (macro ? a.Macro : a.Diag) + task.Base;
             const uint32_t diag_col = Backward ? 0u : task.DiagColumn;
             const uint32_t in_base = task.VecOffset - diag_col;
             const uint32_t col_end = Backward ? task.Limit : min(task.Limit, diag_col + task.Row0 + kSolveRows);
             const uint32_t row = task.Row0 + 8 * q + fr;
+            double val[32];
             auto load_chunk = [&](uint32_t c0) {
 #pragma unroll
                 for (int ks = 0; ks < 32; ++ks) {
@@ -708,7 +780,7 @@ __global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel
             };
             load_chunk(0);
             if (!macro) {
-                if (t == 96) { // (warp 3: warp 0 is busy with the tickets)
+                if (t == 96) {
                     for (uint32_t spin = 0; PeekAcquire(a.Arrived + task.Super) < task.Need; ++spin) {
                         if (GiveUp(spin, a.Fail)) break;
                         __nanosleep(20);
@@ -724,7 +796,7 @@ __global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel
             }
             double c0 = 0, c1 = 0;
             for (uint32_t col0 = 0; col0 < col_end; col0 += 128) {
-                __syncthreads(); // the entries are complete (first chunk) / the previous chunk's operand has been consumed
+                ConsumerBarrier(); // the entries are complete (first chunk) / the previous chunk's operand has been consumed
                 if (col0 == 0) stamp(id, 1);
                 {
                     const double2 *src = reinterpret_cast<const double2 *>(a.Acc + (size_t(in_base) + col0 + t) * kWide);
@@ -732,7 +804,7 @@ __global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel
 #pragma unroll
                     for (int j = 0; j < kWide / 2; ++j) dst[j] = col0 + t < col_end ? __ldcg(src + j) : make_double2(0.0, 0.0);
                 }
-                __syncthreads();
+                ConsumerBarrier();
                 contract_strip(val, (min(col_end - col0, 128u) + 3) >> 2, c0, c1);
                 if (col0 + 128 < col_end) load_chunk(col0 + 128);
             }
@@ -743,23 +815,11 @@ __global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel
             }
             if (t == 96) owed = a.Solved + task.Super;
         } else if constexpr (!Backward) {
-            // A run of task.Count consecutive 32-row slabs of one panel: acc[rows] -= P[rows, :] out_S. The run shares the wait for
-            // out_S, the k x 8 operand in shared memory, the ticket and the arrivals it owes; warp q takes the 8-row strips
-            // q, q + 4, ... of the run and never meets the other warps again.
-            const double *p0 = a.Panel + task.Base;
-            const uint32_t row_end = min(task.Limit, task.Row0 + task.Count * kSolveRows), ksteps = (k + 3) >> 2;
-            auto load_strip = [&](uint32_t r0) {
-                const uint32_t row = r0 + fr;
-#pragma unroll
-                for (int ks = 0; ks < 32; ++ks) {
-                    const uint32_t col = 4 * ks + fk;
-                    val[ks] = (row < row_end && col < k) ? p0[row + size_t(col) * task.Ld] : 0.0;
-                }
-            };
-            auto node_of = [&](uint32_t row) { return row < row_end ? __ldg(a.Rows + task.RowsBase + row / 3) : 0u; };
-            uint32_t r0 = task.Row0 + 8 * q;
-            load_strip(r0);
-            uint32_t node = node_of(r0 + fr);
+            // A run of task.Count consecutive slabs of one panel: acc[rows] -= P[rows, :] out_S. The run shares the wait for out_S,
+            // the k x 8 operand in shared memory and the arrivals it owes; warp q takes the 8-row strip q of every slab.
+            const uint32_t tiles = (k + 7) >> 3, row_end = min(task.Limit, task.Row0 + task.Count * kSolveRows);
+            auto node_of = [&](uint32_t row) { return row >= task.RowMin && row < row_end ? __ldg(a.Rows + task.RowsBase + row / 3) : 0u; };
+            uint32_t row = task.Row0 + 8 * q + fr, node = node_of(row);
             if (q == 3 && lane < task.LinkCount) owed = a.Arrived + a.Links[task.LinkBegin + lane];
             if (t == 96) { // out_S is complete once its diagonal slabs have all published
                 for (uint32_t spin = 0; PeekAcquire(a.Solved + task.Super) < task.Need; ++spin) {
@@ -767,47 +827,52 @@ __global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel
                     __nanosleep(40);
                 }
             }
-            __syncthreads();
+            ConsumerBarrier();
             stamp(id, 1);
-            {
+            {   // operand in two planes, even and odd columns: the tile loads pair column 2 fk with 2 fk + 1
                 const double2 *src = reinterpret_cast<const double2 *>(a.Out + (size_t(task.VecOffset) + t) * kWide);
-                double2 *dst = reinterpret_cast<double2 *>(vec + t * kWide);
+                double2 *dst = reinterpret_cast<double2 *>(vec + (t & 1) * (64 * kWide) + (t >> 1) * kWide);
 #pragma unroll
                 for (int j = 0; j < kWide / 2; ++j) dst[j] = t < k ? __ldcg(src + j) : make_double2(0.0, 0.0);
             }
-            __syncthreads();
-            for (; r0 < row_end; r0 += kSolveRows) {
-                double c0 = 0, c1 = 0;
-                contract_strip(val, ksteps, c0, c1);
-                const uint32_t row = r0 + fr, mine = node;
-                if (r0 + kSolveRows < row_end) { // the next strip is in flight while this one is scattered
-                    load_strip(r0 + kSolveRows);
-                    node = node_of(r0 + kSolveRows + fr);
+            ConsumerBarrier();
+            for (uint32_t i = 0; i < task.Count; ++i, ++consumed, row += kSolveRows) {
+                const uint32_t stage = consumed % kWideStages;
+                MbarWait(sh.Full + stage, (consumed / kWideStages) & 1);
+                const double2 *tile = reinterpret_cast<const double2 *>(sh.Ring[stage] + size_t(q) * tiles * 64) + lane;
+                double acc[4][2]{};
+#pragma unroll 2
+                for (uint32_t j = 0; j < tiles; j += 2) { // two tiles per step, four accumulator chains
+                    const bool two = j + 1 < tiles;
+                    const double2 a0 = tile[32 * j], a1 = two ? tile[32 * j + 32] : make_double2(0.0, 0.0);
+                    const double *b = vec + (4 * j + fk) * kWide + fr;
+                    Dmma(acc[0][0], acc[0][1], a0.x, b[0]);
+                    Dmma(acc[1][0], acc[1][1], a0.y, b[64 * kWide]);
+                    Dmma(acc[2][0], acc[2][1], a1.x, b[4 * kWide]);
+                    Dmma(acc[3][0], acc[3][1], a1.y, b[(64 + 4) * kWide]);
                 }
-                if (row < row_end) {
-                    double *dst = a.Acc + (size_t(3) * mine + row % 3) * kWide + 2 * fk;
-                    atomicAdd(dst, -c0);
-                    atomicAdd(dst + 1, -c1);
+                __syncwarp();
+                if (lane == 0) MbarArrive(sh.Empty + stage);
+                const uint32_t mine = node, at = row;
+                if (i + 1 < task.Count) node = node_of(row + kSolveRows);
+                if (at >= task.RowMin && at < row_end) {
+                    double *dst = a.Acc + (size_t(3) * mine + at % 3) * kWide + 2 * fk;
+                    atomicAdd(dst, -((acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0])));
+                    atomicAdd(dst + 1, -((acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1])));
                 }
             }
         } else {
-            // A run of task.Count consecutive 32-row slabs: acc_S[k x 8] -= sum over the slabs of P_slab^T [k x 32] out[slab rows
-            // x 8]. Warp q owns output columns 32q .. 32q+31 of the supernode and keeps their sums in its DMMA accumulators
-            // across the run: ONE set of FP64 atomics per run. The solved entries of a slab's rows are gathered by every warp for
-            // itself (B fragment: row 4 ks + fk of the slab, right-hand side fr).
-            const double *pt = a.Panel + task.Base;
-            const uint32_t row_end = min(task.Limit, task.Row0 + task.Count * kSolveRows);
-            const bool active = 32 * q < k; // (a narrow supernode leaves the upper warps without columns)
-            auto load_slab = [&](uint32_t row0) {
-#pragma unroll
-                for (int mi = 0; mi < 4; ++mi)
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t col = 32 * q + 8 * mi + fr, row = row0 + 4 * ks + fk;
-                        val[mi * 8 + ks] = (row < row_end && col < k) ? pt[size_t(row) * k + col] : 0.0;
-                    }
+            // A run of task.Count consecutive slabs: acc_S[k x 8] -= sum over the slabs of P_slab^T [k x 32] out[slab rows x 8].
+            // Warp q owns output columns 32q .. 32q+31 of the supernode and keeps their sums in its DMMA accumulators across the
+            // run: ONE set of FP64 atomics per run. The solved entries of a slab's rows are gathered by every warp for itself
+            // (B fragment: row 4 ks + fk of the slab, right-hand side fr).
+            const uint32_t tiles = (k + 7) >> 3, row_end = min(task.Limit, task.Row0 + task.Count * kSolveRows);
+            auto entry_of = [&](uint32_t row) -> const double * {
+                return row >= task.RowMin && row < row_end ? a.Out + (size_t(3) * __ldg(a.Rows + task.RowsBase + row / 3) + row % 3) * kWide + fr : nullptr;
             };
-            if (active) load_slab(task.Row0);
+            const double *entry[8];
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) entry[ks] = entry_of(task.Row0 + 4 * ks + fk);
             if (t == 96) owed = a.Arrived + task.Super;
             if (q == 3) { // the ancestors owning the run's rows: polled by the lanes of one warp
                 for (uint32_t i = lane; i < task.LinkCount; i += 32) {
@@ -819,35 +884,41 @@ __global__ void __launch_bounds__(kSweepThreads, kWideCtasPerSm) WideSweepKernel
                     }
                 }
             }
-            __syncthreads(); // the links are solved
+            ConsumerBarrier(); // the links are solved
             stamp(id, 1);
-            if (active) {
-                double c[4][2]{};
-                for (uint32_t row0 = task.Row0; row0 < row_end; row0 += kSolveRows) {
-                    double b[8];
+            double c[4][2]{};
+            for (uint32_t i = 0; i < task.Count; ++i, ++consumed) {
+                double b[8];
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks) {
-                        const uint32_t row = row0 + 4 * ks + fk;
-                        b[ks] = 0.0;
-                        if (row < row_end) b[ks] = __ldcg(a.Out + (size_t(3) * __ldg(a.Rows + task.RowsBase + row / 3) + row % 3) * kWide + fr);
-                    }
+                for (int ks = 0; ks < 8; ++ks) b[ks] = entry[ks] ? __ldcg(entry[ks]) : 0.0;
+                if (i + 1 < task.Count) {
 #pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-#pragma unroll
-                        for (int mi = 0; mi < 4; ++mi) Dmma(c[mi][0], c[mi][1], val[mi * 8 + ks], b[ks]);
-                    if (row0 + kSolveRows < row_end) load_slab(row0 + kSolveRows);
+                    for (int ks = 0; ks < 8; ++ks) entry[ks] = entry_of(task.Row0 + (i + 1) * kSolveRows + 4 * ks + fk);
                 }
+                const uint32_t stage = consumed % kWideStages;
+                MbarWait(sh.Full + stage, (consumed / kWideStages) & 1);
+                const double *slab = sh.Ring[stage] + (4 * q) * 64 + fk * 8 + fr;
 #pragma unroll
-                for (int mi = 0; mi < 4; ++mi) {
-                    const uint32_t col = 32 * q + 8 * mi + fr;
-                    if (col < k) {
-                        double *dst = a.Acc + (size_t(task.VecOffset) + col) * kWide + 2 * fk;
-                        atomicAdd(dst, -c[mi][0]);
-                        atomicAdd(dst + 1, -c[mi][1]);
-                    }
+                for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                    for (int mi = 0; mi < 4; ++mi)
+                        if (4 * q + mi < tiles) Dmma(c[mi][0], c[mi][1], slab[((ks >> 1) * tiles + mi) * 64 + (ks & 1) * 32], b[ks]);
+                __syncwarp();
+                if (lane == 0) MbarArrive(sh.Empty + stage);
+            }
+#pragma unroll
+            for (int mi = 0; mi < 4; ++mi) {
+                const uint32_t col = 32 * q + 8 * mi + fr;
+                if (col < k) {
+                    double *dst = a.Acc + (size_t(task.VecOffset) + col) * kWide + 2 * fk;
+                    atomicAdd(dst, -c[mi][0]);
+                    atomicAdd(dst + 1, -c[mi][1]);
                 }
             }
         }
+        ConsumerBarrier(); // every contribution of the task has been issued; the shared operand is free
+        if (owed) ArriveRelease(owed);
+        stamp(id, 2);
     }
 }
 
@@ -956,6 +1027,7 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     DRowPtr.Upload(Sym.RowPtr, s);
     DPanelOffset.Upload(Sym.PanelOffset, s);
     DInvOffset.Upload(Sym.InvOffset, s);
+    DSlabOffset.Upload(Sym.SlabOffset, s);
     DPanelTiles.Upload(Sym.PanelTiles, s);
     DUpdateTiles.Upload(Sym.UpdateTiles, s);
     DMacroOffset.Upload(Sym.MacroOffset, s);
@@ -965,7 +1037,8 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     L.Reserve(Sym.FactorNonZeros);
     Linv.Reserve(Sym.InvOffset[Sym.NumSuper]);
     LinvT.Reserve(Sym.InvOffset[Sym.NumSuper]);
-    LT.Reserve(Sym.FactorNonZeros - Sym.InvOffset[Sym.NumSuper] + 1);
+    Slabs.Reserve(Sym.SlabOffset[Sym.NumSuper] + 1);
+    ME_CUDA(cudaMemsetAsync(Slabs.Ptr, 0, Slabs.Capacity * sizeof(double), s)); // (the padding rows and columns are never written again)
     MacroW.Reserve(Sym.MacroOffset[Sym.NumSuper] + 1);
     MacroWT.Reserve(Sym.MacroOffsetT[Sym.NumSuper] + 1);
     Work.Reserve(fem.N);
@@ -980,8 +1053,10 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
         ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, SweepKernel<true>, kSweepThreads, 0));
         if (fwd < 1 || bwd < 1) Fail(ME_CUDA_ERROR, "sweep kernels do not fit an SM");
         FwdGrid = uint32_t(sms * fwd), BwdGrid = uint32_t(sms * bwd); // every CTA resident: the spin-waits rely on it
-        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd, WideSweepKernel<false>, kSweepThreads, 0));
-        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, WideSweepKernel<true>, kSweepThreads, 0));
+        ME_CUDA(cudaFuncSetAttribute(WideSweepKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(WideShared))));
+        ME_CUDA(cudaFuncSetAttribute(WideSweepKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(WideShared))));
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd, WideSweepKernel<false>, kWideThreads, sizeof(WideShared)));
+        ME_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd, WideSweepKernel<true>, kWideThreads, sizeof(WideShared)));
         if (fwd < 1 || bwd < 1) Fail(ME_CUDA_ERROR, "panel sweep kernels do not fit an SM");
         WideFwdGrid = uint32_t(sms * fwd), WideBwdGrid = uint32_t(sms * bwd);
     }
@@ -1023,7 +1098,7 @@ SparseCholesky::~SparseCholesky() {
 void SparseCholesky::Factorize(double sigma) {
     ME_CUDA(cudaSetDevice(Fem.Device));
     auto s = Fem.Stream;
-    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, Slabs.Ptr, DFail.Ptr, DSlabOffset.Ptr};
     ME_CUDA(cudaEventRecord(Ev[0], s));
     ME_CUDA(cudaMemsetAsync(DFail.Ptr, 0, sizeof(int), s));
     ME_CUDA(cudaMemsetAsync(L.Ptr, 0, Sym.FactorNonZeros * sizeof(double), s));
@@ -1070,7 +1145,7 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     UploadSchedules();
     auto s = Fem.Stream;
     const uint32_t n = Fem.N, ns = Sym.NumSuper;
-    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, LT.Ptr, DFail.Ptr};
+    FactorView v{DSuperFirst.Ptr, DRows.Ptr, DNodeSuper.Ptr, DRowPtr.Ptr, DPanelOffset.Ptr, DInvOffset.Ptr, DSegTarget.Ptr, DSegBegin.Ptr, DSegEnd.Ptr, L.Ptr, Linv.Ptr, LinvT.Ptr, Slabs.Ptr, DFail.Ptr, DSlabOffset.Ptr};
     if (width > 2 && Work.Capacity < size_t(n) * kWide) {
         ME_CUDA(cudaStreamSynchronize(s)); // growing a buffer releases the old block
         Work.Reserve(size_t(n) * kWide);
@@ -1081,9 +1156,9 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
     uint32_t *counters = DCounters.Ptr;
     // Forward: Work accumulates the right-hand side, Work2 receives y. Backward: Work2 accumulates, Work receives x.
     const SweepArgs fwd{DFwdTasks.Ptr, uint32_t(Sym.FwdTasks.size()), DFwdLinks.Ptr, nullptr, counters + 2 * size_t(ns), counters, counters + 2 * size_t(ns) + 2, DRows.Ptr, Linv.Ptr, L.Ptr, Work.Ptr, Work2.Ptr, DFail.Ptr};
-    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), nullptr, nullptr, counters + 2 * size_t(ns) + 1, counters + ns, counters + 3 * size_t(ns) + 2, DRows.Ptr, LinvT.Ptr, LT.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
+    const SweepArgs bwd{DBwdTasks.Ptr, uint32_t(Sym.BwdTasks.size()), nullptr, nullptr, counters + 2 * size_t(ns) + 1, counters + ns, counters + 3 * size_t(ns) + 2, DRows.Ptr, LinvT.Ptr, Slabs.Ptr, Work2.Ptr, Work.Ptr, DFail.Ptr};
     SweepArgs wide_fwd = fwd, wide_bwd = bwd;
-    wide_fwd.Tasks = DWideFwdTasks.Ptr, wide_fwd.NumTasks = uint32_t(Sym.WideFwdTasks.size()), wide_fwd.Links = DWideFwdLinks.Ptr;
+    wide_fwd.Tasks = DWideFwdTasks.Ptr, wide_fwd.NumTasks = uint32_t(Sym.WideFwdTasks.size()), wide_fwd.Links = DWideFwdLinks.Ptr, wide_fwd.Panel = Slabs.Ptr;
     wide_bwd.Tasks = DWideBwdTasks.Ptr, wide_bwd.NumTasks = uint32_t(Sym.WideBwdTasks.size()), wide_bwd.Links = DWideBwdLinks.Ptr, wide_bwd.LinkNeed = DWideBwdLinkNeed.Ptr;
     wide_fwd.Macro = MacroW.Ptr, wide_fwd.ArriveNeed = DWideFwdNeed.Ptr;
     wide_bwd.Macro = MacroWT.Ptr, wide_bwd.ArriveNeed = DWideBwdNeed.Ptr;
@@ -1117,8 +1192,8 @@ void SparseCholesky::Solve(const double *b, double *x, uint32_t width) {
         }
         WideBeginKernel<<<Blocks(n, 256), 256, 0, s>>>(b + size_t(rhs) * n, n, w, DInvPerm.Ptr, Work.Ptr);
         ME_CUDA(cudaMemsetAsync(counters, 0, (size_t(4) * ns + 2) * sizeof(uint32_t), s));
-        WideSweepKernel<false><<<WideFwdGrid, kSweepThreads, 0, s>>>(wide_fwd);
-        WideSweepKernel<true><<<WideBwdGrid, kSweepThreads, 0, s>>>(wide_bwd);
+        WideSweepKernel<false><<<WideFwdGrid, kWideThreads, sizeof(WideShared), s>>>(wide_fwd);
+        WideSweepKernel<true><<<WideBwdGrid, kWideThreads, sizeof(WideShared), s>>>(wide_bwd);
         WidePermuteOutKernel<<<Blocks(n, 256), 256, 0, s>>>(Work.Ptr, n, w, DInvPerm.Ptr, x + size_t(rhs) * n);
         if (trace_path) { // one panel application's timeline: task records followed by their three time stamps
             std::vector<unsigned long long> stamps(size_t(3) * (wide_fwd.NumTasks + wide_bwd.NumTasks));

@@ -46,7 +46,7 @@ private:
     FemSystem &Fem;
     Symbolic Sym;
     DeviceBuffer<uint32_t> DSuperFirst, DRows, DNodeSuper, DInvPerm, DPerm, DSegTarget, DSegBegin, DSegEnd, DLevelOrder;
-    DeviceBuffer<uint64_t> DRowPtr, DPanelOffset, DInvOffset;
+    DeviceBuffer<uint64_t> DRowPtr, DPanelOffset, DInvOffset, DSlabOffset;
     DeviceBuffer<PanelTile> DPanelTiles;
     DeviceBuffer<SweepTask> DFwdTasks, DBwdTasks;
     DeviceBuffer<uint32_t> DFwdLinks, DCounters;
@@ -57,7 +57,7 @@ private:
     DeviceBuffer<double> MacroW, MacroWT; // explicit inverses of the macro blocks' diagonal blocks (symbolic.h), forward and backward row blocks
     uint32_t FwdGrid{0}, BwdGrid{0}, WideFwdGrid{0}, WideBwdGrid{0};
     DeviceBuffer<UpdateTile> DUpdateTiles;
-    DeviceBuffer<double> L, Linv, LinvT, LT, Work, Work2;
+    DeviceBuffer<double> L, Linv, LinvT, Slabs, Work, Work2;
     DeviceBuffer<int> DFail;
     cudaEvent_t Ev[4]{};
     bool Factored{false};

@@ -302,11 +302,13 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
     // Panel offsets, segments, work lists.
     sym.PanelOffset.assign(size_t(ns) + 1, 0);
     sym.InvOffset.assign(size_t(ns) + 1, 0);
+    sym.SlabOffset.assign(size_t(ns) + 1, 0);
     sym.SegPtr.assign(size_t(ns) + 1, 0);
     for (uint32_t s = 0; s < ns; ++s) {
         const uint64_t k = 3ull * (sym.SuperFirst[s + 1] - sym.SuperFirst[s]), m = 3ull * (sym.RowPtr[s + 1] - sym.RowPtr[s]);
         sym.PanelOffset[s + 1] = sym.PanelOffset[s] + (k + m) * k;
         sym.InvOffset[s + 1] = sym.InvOffset[s] + k * k;
+        sym.SlabOffset[s + 1] = sym.SlabOffset[s] + ((m + kSolveRows - 1) / kSolveRows) * kSolveRows * ((k + 7) / 8 * 8);
         sym.FactorFlops += double(k) * k * k / 3.0 + double(m) * k * k + double(m) * m * k;
         sym.MaxPanelColumns = std::max<uint32_t>(sym.MaxPanelColumns, uint32_t(k));
         sym.MaxPanelRows = std::max<uint32_t>(sym.MaxPanelRows, uint32_t(m));
@@ -408,19 +410,22 @@ void BuildSchedules(Symbolic &sym) {
     // run_of(panel slabs of a level) = slabs per panel task on that level; max_links bounds the arrivals one forward task may owe.
     // With `macros` the supernodes of a macro block (Symbolic::MacroFirst) share the level of the block's first panel: their diagonal
     // slabs become slabs of the block's inverse, and their panel slabs cover only the rows outside the block.
-    auto make_schedules = [&](bool macros, auto &&run_of, uint32_t max_links, std::vector<SweepTask> &fwd, std::vector<uint32_t> &fwd_links, std::vector<SweepTask> &bwd,
+    auto make_schedules = [&](bool macros, bool forward_slabs, auto &&run_of, uint32_t max_links, std::vector<SweepTask> &fwd, std::vector<uint32_t> &fwd_links, std::vector<SweepTask> &bwd,
                               std::vector<uint32_t> &bwd_links, std::vector<uint32_t> &bwd_link_need, std::vector<uint32_t> &fwd_expected, std::vector<uint32_t> &bwd_expected, uint32_t *levels_used) {
         auto first_of = [&](uint32_t s) { return macros ? sym.MacroFirst[s] : s; };
         auto last_of = [&](uint32_t s) { return macros ? sym.MacroLast[s] : s; };
         // rows at the top of s's panel that belong to its own macro block (the chain's next panels: the first rows of the list)
         auto inside = [&](uint32_t s) { return 3 * (sym.SuperFirst[last_of(s) + 1] - sym.SuperFirst[s + 1]); };
         auto panel_rows = [&](uint32_t s) { return 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]); };
-        auto panel_slabs = [&](uint32_t s) { return (panel_rows(s) - inside(s) + kSolveRows - 1) / kSolveRows; };
-        // The supernodes owning slabs [first_slab, first_slab + count) of s's panel (counted from the first row outside the macro
-        // block), ascending (rows are), without repeats.
+        // Panel tasks cover whole 32-row slabs of the slab copy; the first one of a macro panel starts inside the block's rows.
+        auto first_slab_of = [&](uint32_t s) { return inside(s) / kSolveRows; };
+        auto panel_slabs = [&](uint32_t s) { return (panel_rows(s) + kSolveRows - 1) / kSolveRows - (panel_rows(s) > inside(s) ? first_slab_of(s) : (panel_rows(s) + kSolveRows - 1) / kSolveRows); };
+        auto slab_doubles = [&](uint32_t s) { return uint64_t(kSolveRows) * ((columns(s) + 7) / 8 * 8); };
+        // The supernodes owning slabs [first_slab, first_slab + count) of s's panel (counted from the slab holding the first row
+        // outside the macro block; rows inside it are left out), ascending (rows are), without repeats.
         auto targets_of = [&](uint32_t s, uint32_t first_slab, uint32_t count, std::vector<uint32_t> &out, size_t from) {
-            const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0, skip = inside(s);
-            const uint64_t first = (skip + uint64_t(first_slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, (skip + uint64_t(first_slab + count) * kSolveRows + 2) / 3);
+            const uint64_t r0 = sym.RowPtr[s], nodes = sym.RowPtr[s + 1] - r0, skip = inside(s), slab0 = first_slab_of(s);
+            const uint64_t first = std::max<uint64_t>(skip, (slab0 + first_slab) * kSolveRows) / 3, last = std::min<uint64_t>(nodes, ((slab0 + first_slab + count) * kSolveRows + 2) / 3);
             for (uint64_t j = first; j < last; ++j) {
                 const uint32_t target = sym.NodeSuper[sym.Rows[r0 + j]];
                 if (out.size() == from || out.back() != target) out.push_back(target);
@@ -460,10 +465,12 @@ void BuildSchedules(Symbolic &sym) {
             for (uint32_t i = level_ptr[l]; i < level_ptr[l + 1]; ++i)
                 for (uint32_t h = 0; h < diag_slabs(order[i]); ++h) fwd.push_back(diag_task(order[i], h, false));
             for (uint32_t i = level_ptr[l]; i < level_ptr[l + 1]; ++i) {
-                const uint32_t s = order[i], m = panel_rows(s), slabs = panel_slabs(s), skip = inside(s);
+                const uint32_t s = order[i], m = panel_rows(s), slabs = panel_slabs(s), skip = inside(s), slab0 = first_slab_of(s);
                 for (uint32_t h = 0; h < slabs;) {
                     SweepTask t = base_task(s);
-                    t.Kind = 1, t.Base = sym.PanelOffset[s] + t.K, t.Limit = m, t.Ld = t.K + m, t.Row0 = skip + h * kSolveRows, t.Need = diag_slabs(s);
+                    t.Kind = 1, t.Limit = m, t.Row0 = (slab0 + h) * kSolveRows, t.RowMin = skip, t.Need = diag_slabs(s);
+                    if (forward_slabs) t.Base = sym.SlabOffset[s] + (slab0 + h) * slab_doubles(s), t.Ld = t.K;
+                    else t.Base = sym.PanelOffset[s] + t.K, t.Ld = t.K + m;
                     t.LinkBegin = uint32_t(fwd_links.size());
                     // as many slabs as the run allows while the arrivals owed still fit the publishing warp
                     uint32_t count = 0;
@@ -489,10 +496,10 @@ void BuildSchedules(Symbolic &sym) {
         for (uint32_t l = sym.NumLevels; l-- > 0;) {
             const uint32_t run = std::max(1u, run_of(level_slabs[l]));
             for (uint32_t i = level_ptr[l]; i < level_ptr[l + 1]; ++i) {
-                const uint32_t s = order[i], m = panel_rows(s), slabs = panel_slabs(s), skip = inside(s);
+                const uint32_t s = order[i], m = panel_rows(s), slabs = panel_slabs(s), skip = inside(s), slab0 = first_slab_of(s);
                 for (uint32_t h = 0; h < slabs; h += run) {
                     SweepTask t = base_task(s);
-                    t.Kind = 1, t.Base = sym.PanelOffset[s] - sym.InvOffset[s], t.Limit = m, t.Ld = t.K, t.Row0 = skip + h * kSolveRows;
+                    t.Kind = 1, t.Base = sym.SlabOffset[s] + (slab0 + h) * slab_doubles(s), t.Limit = m, t.Ld = t.K, t.Row0 = (slab0 + h) * kSolveRows, t.RowMin = skip;
                     t.Count = std::min(run, slabs - h);
                     t.LinkBegin = uint32_t(bwd_links.size());
                     targets_of(s, h, t.Count, bwd_links, t.LinkBegin);
@@ -515,7 +522,7 @@ void BuildSchedules(Symbolic &sym) {
     std::thread single([&] {
         try {
             std::vector<uint32_t> fwd_need, bwd_need;
-            make_schedules(false, [](uint32_t) { return 1u; }, UINT32_MAX, sym.FwdTasks, sym.FwdLinks, sym.BwdTasks, sym.BwdLinks, sym.BwdLinkNeed, fwd_need, bwd_need, nullptr);
+            make_schedules(false, false, [](uint32_t) { return 1u; }, UINT32_MAX, sym.FwdTasks, sym.FwdLinks, sym.BwdTasks, sym.BwdLinks, sym.BwdLinkNeed, fwd_need, bwd_need, nullptr);
         } catch (...) {
             single_failed = true;
         }
@@ -526,10 +533,10 @@ void BuildSchedules(Symbolic &sym) {
             if (T.joinable()) T.join();
         }
     } join{single};
-    // Panel sweeps: macro blocks, and runs on the levels wide enough to still hand every resident CTA (4 per SM x 148 SMs) a run of its own.
+    // Panel sweeps: macro blocks, and runs on the levels wide enough to still hand every resident CTA (2 per SM x 148 SMs) a run of its own.
     {
-        constexpr uint32_t resident = 4 * 148;
-        make_schedules(true, [&](uint32_t slabs) { return std::min(kWideRun, slabs / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
+        constexpr uint32_t resident = 2 * 148;
+        make_schedules(true, true, [&](uint32_t slabs) { return std::min(kWideRun, slabs / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
                        sym.WideBwdLinkNeed, sym.WideFwdNeed, sym.WideBwdNeed, &sym.SweepLevels);
     }
     single.join();

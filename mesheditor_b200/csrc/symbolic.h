@@ -14,7 +14,8 @@ namespace me {
 struct SymbolicOptions {
     uint32_t LeafNodes{40};   // dissection stops at subdomains of at most this many nodes (one dense leaf supernode)
     uint32_t PanelNodes{42};  // separators are split into chain panels of at most this many nodes (126 columns <= 128)
-    uint32_t MacroPanels{4};  // panel sweeps: consecutive panels of a chain solved as one block through its explicit inverse (1 = off)
+    uint32_t MacroPanels{1};  // panel sweeps: consecutive panels of a chain solved as one block through its explicit inverse (1 = off, the default:
+                              // with the slab ring the sweeps are as fast without; ME_MACRO_PANELS turns it on)
 };
 
 // One tile of the trailing update of supernode S into the panel of an ancestor (see cholesky.cu SyrkScatterKernel).
@@ -31,7 +32,8 @@ constexpr uint32_t kSolveRows = 32;
 constexpr uint32_t kWideRun = 8;     // longest run of slabs in one task of the panel sweeps
 constexpr uint32_t kWideRunLinks = 32; // a forward run owes at most this many arrivals (one per lane of the publishing warp)
 struct alignas(64) SweepTask {
-    uint64_t Base;       // offset in doubles of the matrix block: into Linv / Linv^T (diag), L (forward panel), LT (backward panel)
+    uint64_t Base;       // offset in doubles of the matrix block: into Linv / Linv^T (diag), L (forward panel of the single-vector sweeps), or of the
+                         // task's first 32-row slab in the slab copy of the rectangles (Symbolic::SlabOffset; every other panel task)
     uint32_t Kind;       // 0 diagonal slab, 1 panel slab, 2 slab of a macro block's inverse (panel sweeps only)
     uint32_t Super;
     uint32_t K, Limit;   // columns of the supernode; row limit (k for diagonal slabs, m for panel slabs; macro slabs: columns of the inverse's row block)
@@ -43,7 +45,7 @@ struct alignas(64) SweepTask {
     uint32_t Need;       // arrivals to wait for: diagonal slab = contributions to the supernode; forward panel = its diagonal slabs
     uint32_t Count;      // panel sweeps (WideTasks): consecutive kSolveRows-row slabs of the panel covered by this task (>= 1)
     uint32_t DiagColumn; // macro slabs, forward: column of the row block where the supernode's own diagonal block starts
-    uint32_t Pad;
+    uint32_t RowMin;     // panel tasks: rows below this one belong to the supernode's own macro block and are left out (Row0 is slab-aligned)
 };
 
 struct Symbolic {
@@ -57,6 +59,11 @@ struct Symbolic {
     std::vector<uint32_t> LevelPtr, LevelOrder; // supernodes grouped by level
     std::vector<uint64_t> PanelOffset;        // [NumSuper+1] offset in doubles of each dense panel, (3k + 3m) x 3k column-major
     std::vector<uint64_t> InvOffset;          // [NumSuper+1] offset in doubles of each inverted diagonal block (3k x 3k)
+    // The below-diagonal rectangles once more in the layout the sweeps stream: per supernode ceil(rows / 32) slabs of 32 rows, each
+    // ONE contiguous block of 32 x kp doubles (kp = columns rounded up to 8) made of 8 x 8 row-major tiles, [strip of 8 rows][tile of
+    // 8 columns]: a slab is a single bulk copy into shared memory, and both sweeps read DMMA fragments from it without bank conflicts
+    // (forward: an 8 x 8 tile is one 16-byte load per lane; backward: half a tile, 4 rows, is 256 contiguous bytes).
+    std::vector<uint64_t> SlabOffset;         // [NumSuper+1] offset in doubles of each supernode's slabs
     std::vector<uint64_t> SegPtr;             // [NumSuper+1] into Seg*
     std::vector<uint32_t> SegTarget, SegBegin, SegEnd; // runs of Rows that are columns of one ancestor supernode
     // Work lists per level.
