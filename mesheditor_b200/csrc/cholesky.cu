@@ -642,6 +642,12 @@ __device__ __forceinline__ uint32_t PeekAcquire(const uint32_t *counter) {
 //     feeding two DMMAs (columns {0,2,4,6} and {1,3,5,7} of the tile: the contraction does not care about the order), a backward
 //     half-tile is 256 contiguous bytes. They meet only at a task's handshakes (a named barrier of the 128 consumer threads).
 // Diagonal / macro slabs still load their fragments from global memory (4 % of the bytes).
+// Measured on the 1M-tet factor (scripts/gpu_sweep_ab.py, one process): 4.7 ms per panel application against 5.3-5.8 (first form) and
+// 6.4 (second form). Tried on top of it and dropped: two stages with three CTAs per SM (5.1 ms), the producer holding three tickets
+// (5.2-6.1 ms: see the producer loop), eight copies of the backward accumulator to spread the runs' atomics (7.3 ms: the diagonal
+// slabs, which are every level's critical path, had eight times the entries to load); with the atomics skipped altogether a panel
+// application is 4.6 ms, so they are not what is left. What is: the ~90 narrow upper levels, where a level is one diagonal slab
+// and one round of single-slab tasks of ~2.5 us each (1.4 of the 4.7 ms for 8 % of the bytes).
 constexpr int kWideThreads = 160, kWideConsumers = 128;
 constexpr int kWideStages = 3, kWideQueue = 4;
 constexpr uint32_t kSlabDoubles = kSolveRows * 128;
