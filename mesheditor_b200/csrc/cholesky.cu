@@ -86,51 +86,161 @@ __global__ void ScatterMatrixKernel(FactorView v, const uint32_t *__restrict__ b
         }
 }
 
-// Cholesky of one diagonal block (k <= 128) in shared memory, fused with the inverse of its factor.
-// 512 threads: four per matrix row. The lower triangle of the k x LDS array holds A (then L); the strict upper
-// triangle holds E^T, where E (unit lower) accumulates the same row operations applied to the identity, so that
-// L^-1 = diag(L)^-1 E.
+// Cholesky of one diagonal block (k <= 128) and the inverse of its factor, in shared memory, one CTA per supernode. On the
+// separator chains of the upper levels this kernel runs alone, a level at a time: it is all latency, and the first version (a
+// column at a time over the whole block, the inverse accumulated alongside: 126 steps of ~2 us) was 44 ms of a 300 ms
+// factorisation. This one is blocked by 16 columns:
+//   Cholesky   per block: the 16 x 16 diagonal block a column at a time on 256 threads (two named barriers per column), the rows
+//              below solved against it (a thread per row), then the rank-16 update of the trailing triangle in 4 x 4 register tiles;
+//   inverse    in place, last block column first (the dtrtri order): the 16 x 16 diagonal blocks are inverted by a warp each,
+//              then block column j becomes -X22 * L21 * X_jj, X22 the already inverted trailing triangle: two barriers per block column.
 constexpr int kFactorThreads = 512;
+constexpr uint32_t kFactorBlock = 16;
 __global__ void __launch_bounds__(kFactorThreads) FactorDiagKernel(FactorView v, const uint32_t *__restrict__ level_supers) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const uint32_t s = level_supers[blockIdx.x];
-    const uint32_t k = PanelColumns(v, s), ld = k + PanelRows(v, s), lds = k | 1;
+    const uint32_t k = PanelColumns(v, s), ld = k + PanelRows(v, s), lds = (k + 1) & ~1u; // (even: the tiles are read 16 bytes at a time)
     double *panel = v.L + v.PanelOffset[s];
-    const uint32_t t = threadIdx.x, i = t & 127, h = t >> 7;
-    for (uint32_t idx = t; idx < k * k; idx += kFactorThreads) {
-        const uint32_t r = idx % k, c = idx / k;
-        sm[r + c * lds] = r >= c ? panel[r + size_t(c) * ld] : 0.0;
+    double *scratch = sm + size_t(lds) * k;       // [112 x 16]: a block column's intermediate product
+    double *rdiag = scratch + 112 * kFactorBlock; // [k]: reciprocals of the factor's diagonal
+    const uint32_t t = threadIdx.x;
+    auto A = [&](uint32_t r, uint32_t c) -> double & { return sm[r + size_t(c) * lds]; };
+    for (uint32_t idx = t; idx < lds * k; idx += kFactorThreads) {
+        const uint32_t r = idx % lds, c = idx / lds;
+        sm[idx] = (r >= c && r < k) ? panel[r + size_t(c) * ld] : 0.0;
     }
-    double pending = 0;
     bool bad = false;
-    for (uint32_t j = 0; j < k; ++j) {
+    for (uint32_t jb = 0; jb < k; jb += kFactorBlock) {
+        const uint32_t nb = min(kFactorBlock, k - jb), below = jb + nb, rest = k - below;
         __syncthreads();
-        if (h == 0 && j > 0 && i >= j - 1 && i < k) sm[i + (j - 1) * lds] = pending;
-        double d = sm[j + j * lds];
-        if (!(d > 0.0) || !isfinite(d)) {
-            bad = true;
-            d = 1.0;
+        if (t < 256) { // the diagonal block: thread (i, c) owns entry (jb + i, jb + c)
+            const uint32_t i = t & 15, c = t >> 4;
+            for (uint32_t j = 0; j < nb; ++j) {
+                asm volatile("bar.sync 2, 256;" ::: "memory"); // the previous column's writes are visible
+                double d = A(jb + j, jb + j);
+                if (!(d > 0.0) || !isfinite(d)) {
+                    bad = true;
+                    d = 1.0;
+                }
+                const double sq = sqrt(d), inv = 1.0 / sq;
+                const double li = (i < nb) ? A(jb + i, jb + j) * inv : 0.0, lc = (c < nb) ? A(jb + c, jb + j) * inv : 0.0;
+                asm volatile("bar.sync 2, 256;" ::: "memory"); // every thread has read column j
+                if (i < nb && c < nb) {
+                    if (c == j) {
+                        if (i == j) A(jb + j, jb + j) = sq, rdiag[jb + j] = inv;
+                        else if (i > j) A(jb + i, jb + j) = li;
+                    } else if (c > j && i >= c) {
+                        A(jb + i, jb + c) -= li * lc;
+                    }
+                }
+            }
         }
-        const double sq = sqrt(d), inv = 1.0 / sq;
-        if (i == j) pending = sq;
-        if (i > j && i < k) {
-            const double l = sm[i + j * lds] * inv, f = l * inv;
-            for (uint32_t c = j + 1 + h; c <= i; c += 4) sm[i + c * lds] -= l * (sm[c + j * lds] * inv);
-            for (uint32_t c = h; c < j; c += 4) sm[c + i * lds] -= f * sm[c + j * lds];
-            if (h == (j & 3)) sm[j + i * lds] = -f;
-            pending = l;
+        __syncthreads();
+        if (t < rest) { // rows below: x D^T = a, a thread per row
+            const uint32_t r = below + t;
+            double x[kFactorBlock];
+#pragma unroll
+            for (uint32_t c = 0; c < kFactorBlock; ++c) {
+                if (c < nb) {
+                    double sum = A(r, jb + c);
+#pragma unroll
+                    for (uint32_t u = 0; u < kFactorBlock; ++u)
+                        if (u < c) sum -= x[u] * A(jb + c, jb + u);
+                    x[c] = sum * rdiag[jb + c];
+                }
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < kFactorBlock; ++c)
+                if (c < nb) A(r, jb + c) = x[c];
+        }
+        __syncthreads();
+        // trailing triangle -= P P^T over the block's columns, 4 x 4 tiles of (row, column) >= below
+        const uint32_t tiles = (rest + 3) / 4;
+        for (uint32_t tile = t; tile < tiles * tiles; tile += kFactorThreads) {
+            const uint32_t ti = tile / tiles, tc = tile % tiles;
+            if (tc > ti) continue;
+            const uint32_t r0 = below + 4 * ti, c0 = below + 4 * tc;
+            double acc[4][4]{};
+            for (uint32_t u = 0; u < nb; ++u) {
+                double a[4], b[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) a[e] = r0 + e < k ? A(r0 + e, jb + u) : 0.0, b[e] = c0 + e < k ? A(c0 + e, jb + u) : 0.0;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) acc[e][f] += a[e] * b[f];
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+                    if (r0 + e < k && c0 + f <= r0 + e) A(r0 + e, c0 + f) -= acc[e][f];
         }
     }
-    __syncthreads();
-    if (h == 0 && i >= k - 1 && i < k) sm[i + (k - 1) * lds] = pending;
     __syncthreads();
     if (bad && t == 0) atomicExch(v.Fail, 1);
+    for (uint32_t idx = t; idx < k * k; idx += kFactorThreads) {
+        const uint32_t r = idx % k, c = idx / k;
+        if (r >= c) panel[r + size_t(c) * ld] = A(r, c);
+    }
+    __syncthreads(); // the factor has been read out: it is overwritten from here on
+    // Inverse in place. Diagonal blocks first: warp w inverts block w, lane c its column c by forward substitution.
+    const uint32_t blocks = (k + kFactorBlock - 1) / kFactorBlock, warp = t >> 5, lane = t & 31;
+    if (warp < blocks) {
+        const uint32_t jb = warp * kFactorBlock, nb = min(kFactorBlock, k - jb), c = lane;
+        double x[kFactorBlock];
+#pragma unroll
+        for (uint32_t i = 0; i < kFactorBlock; ++i) {
+            x[i] = 0.0;
+            if (c < nb && i < nb && i >= c) {
+                double sum = i == c ? 1.0 : 0.0;
+#pragma unroll
+                for (uint32_t u = 0; u < kFactorBlock; ++u)
+                    if (u < i && u >= c) sum -= A(jb + i, jb + u) * x[u];
+                x[i] = sum * rdiag[jb + i];
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (uint32_t i = 0; i < kFactorBlock; ++i)
+            if (c < nb && i < nb && i >= c) A(jb + i, jb + c) = x[i];
+    }
+    for (uint32_t j = blocks - 1; j-- > 0;) {
+        const uint32_t jb = j * kFactorBlock, below = jb + kFactorBlock, rest = k - below; // (every block but the last is full)
+        __syncthreads();
+        // scratch[row][0..15] = X22[row, :] L21: thread (row, four columns)
+        for (uint32_t item = t; item < rest * 4; item += kFactorThreads) {
+            const uint32_t row = item % rest, quad = item / rest;
+            double sum[4]{};
+            for (uint32_t l = 0; l <= row; ++l) {
+                const double xv = A(below + row, below + l);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) sum[e] += xv * A(below + l, jb + 4 * quad + e);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) scratch[row * kFactorBlock + 4 * quad + e] = sum[e];
+        }
+        __syncthreads();
+        // block column j <- -scratch X_jj (X_jj lower triangular)
+        for (uint32_t item = t; item < rest * 4; item += kFactorThreads) {
+            const uint32_t row = item % rest, quad = item / rest;
+            double sum[4]{};
+#pragma unroll
+            for (uint32_t u = 0; u < kFactorBlock; ++u) {
+                const double tv = scratch[row * kFactorBlock + u];
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (u >= 4 * quad + e) sum[e] += tv * A(jb + u, jb + 4 * quad + e);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) A(below + row, jb + 4 * quad + e) = -sum[e];
+        }
+    }
+    __syncthreads();
     double *linv = v.Linv + v.InvOffset[s], *linvt = v.LinvT + v.InvOffset[s];
     for (uint32_t idx = t; idx < k * k; idx += kFactorThreads) {
         const uint32_t r = idx % k, c = idx / k;
-        if (r >= c) panel[r + size_t(c) * ld] = sm[r + c * lds];
-        const double dr = sm[r + r * lds];
-        const double value = r == c ? 1.0 / dr : (r > c ? sm[c + r * lds] / dr : 0.0);
+        const double value = r >= c ? A(r, c) : 0.0;
         linv[r + size_t(c) * k] = value;
         linvt[c + size_t(r) * k] = value;
     }
@@ -1067,7 +1177,7 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
         WideFwdGrid = uint32_t(sms * fwd), WideBwdGrid = uint32_t(sms * bwd);
     }
     for (auto &e : Ev) ME_CUDA(cudaEventCreate(&e));
-    ME_CUDA(cudaFuncSetAttribute(FactorDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 129 * 8));
+    ME_CUDA(cudaFuncSetAttribute(FactorDiagKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * 128 + 112 * 16 + 128) * 8));
     ME_CUDA(cudaFuncSetAttribute(PanelTrsmKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 * kLdA + kChunk * kLdB128) * 8));
     ME_CUDA(cudaStreamSynchronize(s));
     Stats.AnalyseSeconds = Seconds() - t0;
@@ -1111,7 +1221,7 @@ void SparseCholesky::Factorize(double sigma) {
     ScatterMatrixKernel<<<Blocks(Fem.NumBlocks, 256), 256, 0, s>>>(v, Fem.BlkRow.Ptr, Fem.BlkCol.Ptr, Fem.KBlk.Ptr, Fem.MBlk.Ptr, DInvPerm.Ptr, Fem.NumBlocks, sigma);
     uint32_t launches = 1;
     const uint32_t kmax = Sym.MaxPanelColumns;
-    const size_t diag_smem = size_t(kmax) * (kmax | 1) * 8;
+    const size_t diag_smem = (size_t((kmax + 1) & ~1u) * kmax + 112 * 16 + 128) * 8;
     const size_t trsm_smem = (128 * kLdA + kChunk * kLdB128) * 8;
     for (uint32_t l = 0; l < Sym.NumLevels; ++l) {
         const uint32_t n_super = Sym.LevelPtr[l + 1] - Sym.LevelPtr[l];
