@@ -370,4 +370,32 @@ void GatherRows(const double *zt, uint32_t m, const uint32_t *rows, uint32_t k, 
     ++launches;
 }
 
+namespace {
+constexpr uint32_t kRandomStretch = 64; // consecutive values per thread
+__global__ void SimpleRandomKernel(double *__restrict__ out, size_t count) {
+    const size_t first = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * kRandomStretch;
+    if (first >= count) return;
+    constexpr unsigned long long m = 2147483647ull;
+    unsigned long long x = 1, base = 16807ull, e = first + 1; // value i is 16807^(i + 1) mod m
+    while (e) {
+        if (e & 1) x = x * base % m;
+        base = base * base % m;
+        e >>= 1;
+    }
+    const size_t last = min(count, first + kRandomStretch);
+    for (size_t i = first; i < last; ++i) {
+        out[i] = double(x) / 2147483647.0 - 0.5;
+        x = x * 16807ull % m;
+    }
+}
+} // namespace
+
+void FillSimpleRandom(double *out, size_t count, cudaStream_t s, uint32_t &launches) {
+    if (count == 0) return;
+    const size_t threads = (count + kRandomStretch - 1) / kRandomStretch;
+    SimpleRandomKernel<<<uint32_t((threads + 127) / 128), 128, 0, s>>>(out, count);
+    ME_CUDA(cudaGetLastError());
+    ++launches;
+}
+
 } // namespace me

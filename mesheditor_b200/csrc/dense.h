@@ -45,4 +45,10 @@ void ApplyRotations(double *zt, uint32_t m, const QlRotation *rotations, size_t 
 // out (m x k, column-major, device): column j = row rows[j] of zt (m x m, row-major): the picked eigenvectors, as TallGemm takes them.
 void GatherRows(const double *zt, uint32_t m, const uint32_t *rows, uint32_t k, double *out, cudaStream_t, uint32_t &launches);
 
+// out[i] = the (i + 1)-th value of Spectra's SimpleRandom (Park-Miller LCG x <- 16807 x mod 2^31 - 1 from seed 1) mapped to
+// (-0.5, 0.5): the reference's start residual (lib/spectra/include/Spectra/Util/SimpleRandom.h), value for value. The generator
+// is a power map, so every thread jumps to its own stretch by modular exponentiation (the 4.2M values of the 1M-tet start block
+// took 37 ms of host loop, allocation and pageable copy per solve).
+void FillSimpleRandom(double *out, size_t count, cudaStream_t, uint32_t &launches);
+
 } // namespace me

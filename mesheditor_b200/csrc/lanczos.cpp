@@ -67,16 +67,7 @@ LanczosOutcome ShiftInvertLanczos::Compute(uint32_t nev, uint32_t ncv, double to
     };
 
     // Initial residual: the reference's SimpleRandom (Park-Miller LCG, seed 0 -> 1), uniform in (-0.5, 0.5).
-    {
-        std::vector<double> r0(n);
-        uint64_t x = 1;
-        for (size_t i = 0; i < n; ++i) {
-            x = (x * 16807ull) % 2147483647ull;
-            r0[i] = double(x) / 2147483647.0 - 0.5;
-        }
-        ME_CUDA(cudaMemcpyAsync(W.Ptr, r0.data(), n * sizeof(double), cudaMemcpyHostToDevice, s));
-        ME_CUDA(cudaStreamSynchronize(s));
-    }
+    FillSimpleRandom(W.Ptr, n, s, Ws.Launches);
     // v0 <- Op(r) / ||.||_M ; w = Op(v0); H00 = <v0, w>; f = w - H00 v0   (Arnoldi::init)
     Op(W.Ptr, col(V, 0));
     double vnorm = std::sqrt(std::max(0.0, mdot(col(V, 0), col(V, 0))));
@@ -386,16 +377,7 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
 
     const double t_alloc = now();
     // Start block: Op applied to the reference's pseudo-random residual (SimpleRandom, seed 0 -> 1), b columns of it.
-    {
-        std::vector<double> r0(n * b);
-        uint64_t x = 1;
-        for (auto &v : r0) {
-            x = (x * 16807ull) % 2147483647ull;
-            v = double(x) / 2147483647.0 - 0.5;
-        }
-        ME_CUDA(cudaMemcpyAsync(Wb.Ptr, r0.data(), r0.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-        ME_CUDA(cudaStreamSynchronize(s));
-    }
+    FillSimpleRandom(Wb.Ptr, size_t(n) * b, s, Ws.Launches);
     OpPanel(Wb.Ptr, W.Ptr, b);
     if (!orthonormalize(W.Ptr, Wb.Ptr, col(V, 0))) Fail(ME_NOT_CONVERGED, "block Lanczos: the start block is rank deficient");
 
