@@ -1127,7 +1127,8 @@ SparseCholesky::SparseCholesky(FemSystem &fem, const SymbolicOptions &opt) : Fem
     // The solve schedules keep being built on a host thread while the structures below are uploaded and (in the caller) the numeric
     // factorisation runs: UploadSchedules, at the first solve, waits for them.
     SymbolicOptions options = opt;
-    if (const char *env = std::getenv("ME_MACRO_PANELS")) options.MacroPanels = uint32_t(std::max(1, std::atoi(env))); // (tuning aid)
+    if (const char *env = std::getenv("ME_MACRO_PANELS")) options.MacroPanels = uint32_t(std::max(1, std::atoi(env))); // (tuning aids)
+    if (std::getenv("ME_MACRO_BACKWARD")) options.MacroBackward = true;
     AnalyseInto(Sym, fem.NodeCount, rowptr.data(), col.data(), xyz.data(), options, true);
     if (Sym.MaxPanelColumns > 128) Fail(ME_BAD_ARG, "internal: panel of %u columns", Sym.MaxPanelColumns);
     auto s = fem.Stream;

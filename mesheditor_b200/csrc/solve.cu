@@ -707,7 +707,7 @@ MeStatus me_symbolic_analyse(uint32_t node_count, const uint32_t *rowptr, const 
                 } else if (t.Kind == 2) {
                     for (uint32_t i = 0; i < t.LinkCount; ++i) {
                         const uint32_t s = backward ? t.Super + i : t.Super - (t.LinkCount - 1) + i;
-                        if (!need || s >= sym.NumSuper || sym.MacroFirst[s] != sym.MacroFirst[t.Super] || arrived[s] != (*need)[s]) ++violations;
+                        if (!need || s >= sym.NumSuper || sym.MacroFirst[s] != sym.MacroFirst[t.Super] || arrived[s] != (*need)[s] || (backward && !sym.MacroBackward)) ++violations;
                     }
                     ++solved[t.Super];
                 } else if (!backward) {

@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <future>
+#include <memory>
 #include <new>
 #include <numeric>
 #include <thread>
@@ -43,38 +45,56 @@ struct Dissector {
     const uint32_t *RowPtr, *Col;
     const float *Xyz;
     SymbolicOptions Opt;
-    std::vector<uint32_t> Dom;  // current subdomain stamp of each node
-    uint32_t NextStamp{1};
-    // Output, in elimination order.
-    std::vector<uint32_t> Perm;       // new -> old
-    std::vector<uint32_t> SuperFirst; // first new index of each supernode
-    std::vector<uint32_t> Parent;
-    std::vector<uint32_t> Chain;      // panels of one separator (or one leaf) share a chain id
-    uint32_t NextChain{0};
+    // Current subdomain stamp of each node. The two halves of a cut are dissected on different threads (down to kForkDepth): they
+    // write disjoint nodes, but a boundary scan reads the stamps of neighbours in the other half, hence relaxed atomics (a stamp
+    // is unique to one call, so a neighbour's stamp changing under the scan never compares equal to the one looked for).
+    std::unique_ptr<std::atomic<uint32_t>[]> Dom;
+    std::atomic<uint32_t> NextStamp{1};
+    static constexpr int kForkDepth = 4;
 
-    // Emits `nodes` as a chain of panels; `children` are the tops of the subtrees below. Returns the chain's top.
-    uint32_t EmitChain(const std::vector<uint32_t> &nodes, uint32_t panel, const std::vector<uint32_t> &children) {
-        uint32_t first_panel = uint32_t(SuperFirst.size());
-        for (size_t at = 0; at < nodes.size(); at += panel) {
-            const size_t end = std::min(nodes.size(), at + panel);
-            const uint32_t id = uint32_t(SuperFirst.size());
-            SuperFirst.push_back(uint32_t(Perm.size()));
-            Parent.push_back(UINT32_MAX);
-            Chain.push_back(NextChain);
-            if (id > first_panel) Parent[id - 1] = id;
-            Perm.insert(Perm.end(), nodes.begin() + at, nodes.begin() + end);
-        }
-        ++NextChain;
-        for (uint32_t c : children) Parent[c] = first_panel;
-        return uint32_t(SuperFirst.size()) - 1;
+    // The supernodes of one subtree in elimination order, numbered from 0 inside it (the whole tree once the recursion returns).
+    struct Sub {
+        std::vector<uint32_t> Perm;       // new -> old
+        std::vector<uint32_t> SuperFirst; // first index into Perm of each supernode
+        std::vector<uint32_t> Parent;     // UINT32_MAX: none (yet)
+        std::vector<uint32_t> Chain;      // panels of one separator (or one leaf) share a chain id
+        uint32_t Chains{0};
+        std::vector<uint32_t> Tops;       // tops of the subtrees emitted so far
+    };
+    static void Append(Sub &into, Sub &&part) {
+        const uint32_t node0 = uint32_t(into.Perm.size()), super0 = uint32_t(into.SuperFirst.size());
+        into.Perm.insert(into.Perm.end(), part.Perm.begin(), part.Perm.end());
+        for (const uint32_t f : part.SuperFirst) into.SuperFirst.push_back(f + node0);
+        for (const uint32_t p : part.Parent) into.Parent.push_back(p == UINT32_MAX ? UINT32_MAX : p + super0);
+        for (const uint32_t c : part.Chain) into.Chain.push_back(c + into.Chains);
+        into.Chains += part.Chains;
+        for (const uint32_t t : part.Tops) into.Tops.push_back(t + super0);
     }
 
-    // Orders the subdomain `nodes`; appends the tops of the emitted subtrees to `tops`.
-    void Dissect(std::vector<uint32_t> &nodes, std::vector<uint32_t> &tops) {
-        if (nodes.empty()) return;
+    // Emits `nodes` as a chain of panels on top of the subtrees whose tops `sub` holds; the chain's top becomes the only top.
+    static void EmitChain(Sub &sub, const std::vector<uint32_t> &nodes, uint32_t panel) {
+        const uint32_t first_panel = uint32_t(sub.SuperFirst.size());
+        for (size_t at = 0; at < nodes.size(); at += panel) {
+            const size_t end = std::min(nodes.size(), at + panel);
+            const uint32_t id = uint32_t(sub.SuperFirst.size());
+            sub.SuperFirst.push_back(uint32_t(sub.Perm.size()));
+            sub.Parent.push_back(UINT32_MAX);
+            sub.Chain.push_back(sub.Chains);
+            if (id > first_panel) sub.Parent[id - 1] = id;
+            sub.Perm.insert(sub.Perm.end(), nodes.begin() + at, nodes.begin() + end);
+        }
+        ++sub.Chains;
+        for (const uint32_t c : sub.Tops) sub.Parent[c] = first_panel;
+        sub.Tops.assign(1, uint32_t(sub.SuperFirst.size()) - 1);
+    }
+
+    // Orders the subdomain `nodes`.
+    Sub Dissect(std::vector<uint32_t> &nodes, int depth) {
+        Sub out;
+        if (nodes.empty()) return out;
         if (nodes.size() <= Opt.LeafNodes) {
-            tops.push_back(EmitChain(nodes, std::max(Opt.LeafNodes, Opt.PanelNodes), {}));
-            return;
+            EmitChain(out, nodes, std::max(Opt.LeafNodes, Opt.PanelNodes));
+            return out;
         }
         float lo[3]{1e30f, 1e30f, 1e30f}, hi[3]{-1e30f, -1e30f, -1e30f};
         for (uint32_t v : nodes)
@@ -101,40 +121,42 @@ struct Dissector {
             left.assign(nodes.begin(), nodes.begin() + nodes.size() / 2);
             right.assign(nodes.begin() + nodes.size() / 2, nodes.end());
         }
-        const uint32_t stamp_l = NextStamp++, stamp_r = NextStamp++;
-        for (uint32_t v : left) Dom[v] = stamp_l;
-        for (uint32_t v : right) Dom[v] = stamp_r;
+        const uint32_t stamp_l = NextStamp.fetch_add(3, std::memory_order_relaxed), stamp_r = stamp_l + 1, stamp_s = stamp_l + 2;
+        for (uint32_t v : left) Dom[v].store(stamp_l, std::memory_order_relaxed);
+        for (uint32_t v : right) Dom[v].store(stamp_r, std::memory_order_relaxed);
         auto boundary = [&](const std::vector<uint32_t> &side, uint32_t other) {
-            std::vector<uint32_t> out;
+            std::vector<uint32_t> found;
             for (uint32_t v : side)
                 for (uint32_t j = RowPtr[v]; j < RowPtr[v + 1]; ++j)
-                    if (Dom[Col[j]] == other) {
-                        out.push_back(v);
+                    if (Dom[Col[j]].load(std::memory_order_relaxed) == other) {
+                        found.push_back(v);
                         break;
                     }
-            return out;
+            return found;
         };
         std::vector<uint32_t> sep_l = boundary(left, stamp_r), sep_r = boundary(right, stamp_l);
         const bool take_left = sep_l.size() < sep_r.size();
         std::vector<uint32_t> &sep = take_left ? sep_l : sep_r;
         std::vector<uint32_t> &cut_side = take_left ? left : right;
-        const uint32_t stamp_s = NextStamp++;
-        for (uint32_t v : sep) Dom[v] = stamp_s;
+        for (uint32_t v : sep) Dom[v].store(stamp_s, std::memory_order_relaxed);
         std::vector<uint32_t> rest;
         rest.reserve(cut_side.size() - sep.size());
         for (uint32_t v : cut_side)
-            if (Dom[v] != stamp_s) rest.push_back(v);
+            if (Dom[v].load(std::memory_order_relaxed) != stamp_s) rest.push_back(v);
         cut_side.swap(rest);
         nodes.clear();
         nodes.shrink_to_fit();
-        std::vector<uint32_t> children;
-        Dissect(left, children);
-        Dissect(right, children);
-        if (sep.empty()) {
-            tops.insert(tops.end(), children.begin(), children.end());
-            return;
+        if (depth < kForkDepth && std::min(left.size(), right.size()) >= 4096) {
+            auto other = std::async(std::launch::async, [&] { return Dissect(left, depth + 1); });
+            Sub r = Dissect(right, depth + 1);
+            out = other.get();
+            Append(out, std::move(r));
+        } else {
+            out = Dissect(left, depth + 1);
+            Append(out, Dissect(right, depth + 1));
         }
-        tops.push_back(EmitChain(sep, Opt.PanelNodes, children));
+        if (!sep.empty()) EmitChain(out, sep, Opt.PanelNodes);
+        return out;
     }
 };
 } // namespace
@@ -160,28 +182,30 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
     sym.NodeCount = n;
     const double t0 = Now();
     Dissector d{n, rowptr, col, xyz, opt};
-    d.Dom.assign(n, 0);
-    d.Perm.reserve(n);
+    d.Dom.reset(new std::atomic<uint32_t>[n]);
+    for (uint32_t i = 0; i < n; ++i) d.Dom[i].store(0, std::memory_order_relaxed);
+    Dissector::Sub tree;
     {
-        std::vector<uint32_t> all(n), tops;
+        std::vector<uint32_t> all(n);
         std::iota(all.begin(), all.end(), 0u);
-        d.Dissect(all, tops);
+        tree = d.Dissect(all, 0);
     }
-    sym.Perm = std::move(d.Perm);
+    sym.Perm = std::move(tree.Perm);
     sym.InvPerm.assign(n, 0);
     for (uint32_t i = 0; i < n; ++i) sym.InvPerm[sym.Perm[i]] = i;
-    const uint32_t ns = uint32_t(d.SuperFirst.size());
+    const uint32_t ns = uint32_t(tree.SuperFirst.size());
     sym.NumSuper = ns;
-    sym.SuperFirst = std::move(d.SuperFirst);
+    sym.SuperFirst = std::move(tree.SuperFirst);
     sym.SuperFirst.push_back(n);
-    sym.Parent = std::move(d.Parent);
-    const std::vector<uint32_t> chain = std::move(d.Chain);
+    sym.Parent = std::move(tree.Parent);
+    const std::vector<uint32_t> chain = std::move(tree.Chain);
     for (auto &p : sym.Parent)
         if (p == UINT32_MAX) p = ns;
     sym.NodeSuper.assign(n, 0);
     for (uint32_t s = 0; s < ns; ++s)
         for (uint32_t v = sym.SuperFirst[s]; v < sym.SuperFirst[s + 1]; ++v) sym.NodeSuper[v] = s;
     // Macro blocks of the panel sweeps: every chain of c > 1 panels is cut into ceil(c / MacroPanels) runs of near-equal length.
+    sym.MacroBackward = opt.MacroBackward;
     sym.MacroFirst.resize(ns), sym.MacroLast.resize(ns);
     for (uint32_t s = 0; s < ns;) {
         uint32_t e = s + 1;
@@ -534,10 +558,19 @@ void BuildSchedules(Symbolic &sym) {
         }
     } join{single};
     // Panel sweeps: macro blocks, and runs on the levels wide enough to still hand every resident CTA (2 per SM x 148 SMs) a run of its own.
+    // The two directions are scheduled separately when only the forward sweep takes macro blocks (SymbolicOptions::MacroBackward).
     {
         constexpr uint32_t resident = 2 * 148;
-        make_schedules(true, true, [&](uint32_t slabs) { return std::min(kWideRun, slabs / resident); }, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks,
-                       sym.WideBwdLinkNeed, sym.WideFwdNeed, sym.WideBwdNeed, &sym.SweepLevels);
+        const auto run_of = [&](uint32_t slabs) { return std::min(kWideRun, slabs / resident); };
+        if (sym.MacroBackward) {
+            make_schedules(true, true, run_of, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, sym.WideBwdTasks, sym.WideBwdLinks, sym.WideBwdLinkNeed, sym.WideFwdNeed, sym.WideBwdNeed, &sym.SweepLevels);
+        } else {
+            std::vector<SweepTask> unused_tasks;
+            std::vector<uint32_t> unused_links, unused_link_need, unused_need, unused_fwd_links;
+            make_schedules(true, true, run_of, kWideRunLinks, sym.WideFwdTasks, sym.WideFwdLinks, unused_tasks, unused_links, unused_link_need, sym.WideFwdNeed, unused_need, &sym.SweepLevels);
+            unused_tasks.clear(), unused_need.clear();
+            make_schedules(false, true, run_of, kWideRunLinks, unused_tasks, unused_fwd_links, sym.WideBwdTasks, sym.WideBwdLinks, sym.WideBwdLinkNeed, unused_need, sym.WideBwdNeed, nullptr);
+        }
     }
     single.join();
     if (single_failed) throw std::bad_alloc();

@@ -14,8 +14,10 @@ namespace me {
 struct SymbolicOptions {
     uint32_t LeafNodes{40};   // dissection stops at subdomains of at most this many nodes (one dense leaf supernode)
     uint32_t PanelNodes{42};  // separators are split into chain panels of at most this many nodes (126 columns <= 128)
-    uint32_t MacroPanels{1};  // panel sweeps: consecutive panels of a chain solved as one block through its explicit inverse (1 = off, the default:
-                              // with the slab ring the sweeps are as fast without; ME_MACRO_PANELS turns it on)
+    uint32_t MacroPanels{4};  // panel sweeps: consecutive panels of a chain solved as one block through its explicit inverse (1 = off;
+                              // ME_MACRO_PANELS). Measured with the slab ring at 1M tets, 8 panels: forward 2.09 -> 1.90 ms, backward 2.67 -> 2.91 ms,
+    bool MacroBackward{false}; // so the backward sweep keeps its panels one by one unless ME_MACRO_BACKWARD is set (forward only, same box: 4.72 ms per
+                               // panel application without, 4.57 with 8 panels, 4.48 with 4)
 };
 
 // One tile of the trailing update of supernode S into the panel of an ancestor (see cholesky.cu SyrkScatterKernel).
@@ -97,7 +99,8 @@ struct Symbolic {
         uint32_t First, Last, Column, Slice;  // macro block, which of its panels' columns, which 64-column slice of those
     };
     std::vector<MacroJob> MacroJobs;
-    uint32_t SweepLevels{0};                  // dependency levels of the panel sweeps (macro blocks count once)
+    uint32_t SweepLevels{0};                  // dependency levels of the forward panel sweep (macro blocks count once)
+    bool MacroBackward{false};                // the backward panel sweep takes the macro blocks too (SymbolicOptions::MacroBackward)
     uint64_t FactorNonZeros{0};               // scalars stored in the panels
     double FactorFlops{0};
     uint32_t MaxPanelColumns{0}, MaxPanelRows{0};

@@ -62,14 +62,15 @@ def test_panel_solve_and_unstructured_mesh():
         assert _backward_error(A, X[:, k], B[:, k]) <= 1e-14
 
 
-@pytest.mark.parametrize("width,macro_panels", [(8, None), (11, None), (20, None), (8, 4), (11, 3)])
+@pytest.mark.parametrize("width,macro_panels", [(8, None), (11, None), (20, None), (8, 4), (11, 3), (8, 1)])
 def test_wide_panel_solve_matches_single_solves(width, macro_panels, monkeypatch):
     """solve_panel through the 8-wide panel sweeps (one pass over the factor per 8 columns) against column-by-column solves; also
     with runs of chain panels solved through explicit inverses of their diagonal blocks (ME_MACRO_PANELS, symbolic.h)."""
     from mesheditor_b200 import Factor, FemSystem
 
-    if macro_panels:
+    if macro_panels:  # (default: macro blocks of 8 panels in the forward sweep only)
         monkeypatch.setenv("ME_MACRO_PANELS", str(macro_panels))
+        monkeypatch.setenv("ME_MACRO_BACKWARD", "1")
 
     points, tets = om.kuhn_block(9, 8, 7, size=(0.5, 0.4, 0.3))
     mat = om.MATERIALS["Ceramic"]
