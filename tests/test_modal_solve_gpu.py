@@ -194,3 +194,30 @@ def test_solved_model_round_trips_through_the_interchange_formats():
             want += [a, b, c]
     assert d["indices"] == want and len(want) == 6
     np.testing.assert_array_equal(np.asarray(d["frequencies"], np.float32), r.freqs)
+
+
+def test_concurrent_solves_match_sequential():
+    """Several me_modal_solve calls in flight on one device (host threads, every solve on its own stream: how bench.py runs
+    BASELINE.json configs[3]) give what the same calls give one after the other."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from mesheditor_b200 import mesh2modes, solver_config
+
+    mat = om.MATERIALS["Steel"]
+    jobs = [om.kuhn_block(*dims, size=(0.3, 0.25, 0.2)) for dims in ((12, 10, 9), (7, 6, 5), (16, 12, 11), (9, 9, 8), (5, 4, 4), (14, 13, 10))]
+    cfg = solver_config(num_modes=24, max_mode_freq=1e9, element_order=1)
+
+    def solve(job):
+        points, tets = job
+        r = mesh2modes(points, tets, mat, points[:6].astype(np.float32), config=cfg)
+        assert r.status == 0
+        return r.eigenvalues.copy(), r.freqs.copy()
+
+    sequential = [solve(j) for j in jobs]
+    for _ in range(2):
+        with ThreadPoolExecutor(max_workers=3) as pool:
+            concurrent = list(pool.map(solve, jobs))
+        for (lam, freqs), (ref_lam, ref_freqs) in zip(concurrent, sequential):
+            elastic = ref_lam > 1e-3 * ref_lam[-1]
+            assert np.abs(lam[elastic] / ref_lam[elastic] - 1).max() <= 1e-9  # (the factor's atomics reorder sums at rounding level)
+            np.testing.assert_allclose(freqs, ref_freqs, rtol=1e-6)
