@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round 2, visit X (8 GPUs): the default bench line at N = 8.
+# Round 2, 8-GPU visit: the default bench line at N = 8.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name --format=csv,noheader | sort | uniq -c
 (time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 8 --steps 5 --warmup 3) > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err; echo "exit $?"; tail -3 gpurun_out/bench_n8.err
