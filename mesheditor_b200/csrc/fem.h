@@ -67,7 +67,7 @@ public:
     Material Mat{};
 
     DeviceBuffer<double> Points, Basis, KBlk, MBlk, KFull, MFull;
-    DeviceBuffer<uint32_t> Tets, ElemNodes, BlkColPtr, BlkRow, BlkCol, ContribPtr, Contrib, FullRowPtr, FullCol, FullSrc;
+    DeviceBuffer<uint32_t> Tets, ElemNodes, BlkColPtr, BlkRow, BlkCol, ContribPtr, Contrib, AssembleOrder, FullRowPtr, FullCol, FullSrc;
     DeviceBuffer<double> TabMass;   // [Npe][Npe]
     DeviceBuffer<double> TabTermW;  // per ordered local pair (a, c): up to 4 gradient terms w * Phig[k] (x) Phig[l]
     DeviceBuffer<uint8_t> TabTermKL, TabTermCount, TabPairA, TabPairC;
