@@ -13,7 +13,10 @@ fem = FemSystem(points, tets, MATERIALS["Steel"], 1)
 dofs = fem.info["dofs"]
 b8 = np.asfortranarray(np.random.default_rng(1).standard_normal((dofs, 8)))
 for setting in sys.argv[2:] or ["1", "4", "1", "4"]:
-    os.environ["ME_MACRO_PANELS"] = setting
+    os.environ["ME_MACRO_PANELS"] = setting.rstrip("b")  # "4": four panels per macro block, forward sweep only; "4b": both sweeps
+    os.environ.pop("ME_MACRO_BACKWARD", None)
+    if setting.endswith("b"):
+        os.environ["ME_MACRO_BACKWARD"] = "1"
     f = Factor(fem, -((2 * math.pi * 20.0) ** 2))
     ms = []
     for _ in range(13):
