@@ -521,6 +521,16 @@ def solve_once(points, tets, ex, cfg):
 STAGES = ("mass_props", "assemble", "sample_excite", "factorize", "analyse", "iterate", "op_solve", "extract", "dofs", "stiffness_nonzeros", "op_applications", "restarts", "factor_nonzeros", "supernodes", "levels")
 
 
+def sweep_traffic(factor_nonzeros):
+    """DRAM bytes of one panel application from the committed ncu capture, if it was taken on a factor of this size."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "solve_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_panel_application"]) if int(t["factor_nonzeros"]) == int(factor_nonzeros) else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def run_solve(args, ranks, steps, warmup, cpu_baseline=True):
     """configs[2]: one 1M-tet mesh on one GPU (a single eigensolve does not shard: every rank solves a replica and the slowest
     is reported). Returns the record (rank 0) with the reference bench's stage table (tests/ModalSolverBench.cpp:413-449)."""
@@ -589,7 +599,8 @@ def run_solve(args, ranks, steps, warmup, cpu_baseline=True):
         "device_seconds": sec - prof["mass_props"], "gpu_launches": int(sum(p["kernel_launches"] for p in profiles)),
         "seconds_each": times, "profile": {k: prof[k] for k in STAGES},
         "roofline": {"bound": "hbm", "kernel": "WideSweepKernel<0> + WideSweepKernel<1> (forward + backward triangular sweeps over the factor for a panel of 8 right-hand sides; WideBegin / MarkUnsolved / WidePermuteOut ride in the same event pair, ~1 % of it)",
-                     "achieved": sweep_bytes / (panel_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": sweep_bytes / (panel_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": None,
+                     "achieved": sweep_bytes / (panel_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": sweep_bytes / (panel_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "traffic": sweep_traffic(fi["factor_nonzeros"]),
+                     "traffic_source": "ncu --set full dram__bytes of one forward + one backward panel sweep of this factor (profiles/solve_traffic.json); null for any other factor",
                      "ms_per_launch": panel_ms, "algorithmic_bytes": sweep_bytes, "share_of_step": prof["op_solve"] / sec, "panel_applications_per_step": panels, "operator_applications_per_step": ops,
                      "op_solve_ms_per_panel_in_the_timed_solve": 1e3 * prof["op_solve"] / panels, "peak_source": pk_kind,
                      "bytes": "16 * nnz(L) (the factor read once forward and once backward, 8 B each) + 16 * n * 8 (eight right-hand sides in and out)"},
