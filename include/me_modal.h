@@ -246,7 +246,10 @@ typedef struct MeModalResult MeModalResult; /* modal::ModalResult (mesh2modes.h:
  * Status mirrors the reference's failure modes. A cancel seen right after assembly leaves *out EMPTY (mesh2modes.cpp:616
  * returns `{}`). ME_NOT_CONVERGED, and a cancel seen later (inside ComputeModes, :462,479,490), leave *out with empty modes,
  * eigen summary and basis but WITH the mass properties, the profile and the excitation remap, as :655-657 still build
- * them. ME_NO_MODES keeps everything but the (empty) modes. ME_FACTOR_FAILED is the reference's std::runtime_error. */
+ * them. ME_NO_MODES keeps everything but the (empty) modes. ME_FACTOR_FAILED is the reference's std::runtime_error.
+ * Calls may run concurrently from several host threads, on one device or on several (the reference's generation jobs are one
+ * worker thread each, AudioSystem.cpp:830-862): every call works on a CUDA stream of its own, so one call's host stages overlap
+ * the others' kernels; the results are those of the same calls made one after the other. */
 MeStatus me_modal_solve(const double *points_xyz, uint32_t n_points, const uint32_t *tets, uint32_t n_tets, const MeMaterial *material,
                         const float *excite_xyz, uint32_t n_excite, const float baked_scale[3], const MeSolverConfig *config,
                         const float *seed_basis, uint32_t seed_rows, uint32_t seed_cols, int keep_basis, MeJobMonitor *monitor,
