@@ -17,7 +17,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <limits>
 #include <thread>
@@ -49,6 +51,117 @@ void RunTeam(uint32_t workers, F &&body) {
     body(0u, workers);
     for (auto &t : pool) t.join();
 }
+// Barrier of a team that meets every few microseconds: the waiters spin (a futex round trip costs more than the work between two
+// of these barriers).
+struct SpinBarrier {
+    explicit SpinBarrier(uint32_t team) : Team(team) {}
+    void Wait() {
+        const uint32_t phase = Phase.load(std::memory_order_acquire);
+        if (Arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == Team) {
+            Arrived.store(0, std::memory_order_relaxed);
+            Phase.store(phase + 1, std::memory_order_release);
+        } else {
+            while (Phase.load(std::memory_order_acquire) == phase) {
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+            }
+        }
+    }
+    const uint32_t Team;
+    alignas(64) std::atomic<uint32_t> Arrived{0};
+    alignas(64) std::atomic<uint32_t> Phase{0};
+};
+
+// The Householder reduction of SymmetricEigenReduce on a team in lockstep: the two O(l^2) sweeps of a step (e = A u over the stored
+// lower triangle, and the rank-2 update) are shared out by rows in stretches of equal area, the O(l) parts stay with worker 0,
+// five spin barriers a step. The partial products of e are summed in worker order, so the result is a function of the team size
+// (fixed per machine: TeamSize), not of the timing.
+void HouseholderReduceTeam(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<double> &e, uint32_t workers) {
+    auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
+    SpinBarrier barrier(workers);
+    std::vector<std::vector<double>> partial(workers, std::vector<double>(n, 0.0));
+    struct Shared {
+        bool Active{false};
+        double H{0};
+    } shared;
+    RunTeam(workers, [&](uint32_t w, uint32_t count) {
+        double *mine = partial[w].data();
+        for (uint32_t i = n - 1; i >= 1; --i) {
+            const uint32_t l = i - 1, rows = l + 1;
+            if (w == 0) {
+                double h = 0, scale = 0;
+                shared.Active = false;
+                if (l > 0) {
+                    for (uint32_t k = 0; k <= l; ++k) scale += std::abs(A(i, k));
+                    if (scale == 0.0) e[i] = A(i, l);
+                    else {
+                        for (uint32_t k = 0; k <= l; ++k) {
+                            A(i, k) /= scale;
+                            h += A(i, k) * A(i, k);
+                        }
+                        const double f = A(i, l);
+                        const double g = f >= 0 ? -std::sqrt(h) : std::sqrt(h);
+                        e[i] = scale * g;
+                        h -= f * g;
+                        A(i, l) = f - g;
+                        shared.Active = true;
+                    }
+                } else e[i] = A(i, l);
+                shared.H = h;
+                d[i] = h;
+            }
+            barrier.Wait();
+            if (!shared.Active) {
+                barrier.Wait(); // (worker 0 must not rewrite `shared` before everyone has read it)
+                continue;
+            }
+            const double h = shared.H;
+            const double *u = &a[size_t(i) * n];
+            // rows [j0, j1) of equal area: row j costs j
+            const uint32_t j0 = uint32_t(std::sqrt(double(w) / count) * rows), j1 = w + 1 == count ? rows : uint32_t(std::sqrt(double(w + 1) / count) * rows);
+            std::fill(mine, mine + rows, 0.0);
+            for (uint32_t j = j0; j < j1; ++j) {
+                const double *row = &a[size_t(j) * n];
+                const double uj = u[j];
+                double dot = 0;
+                for (uint32_t k = 0; k < j; ++k) {
+                    dot += row[k] * u[k];
+                    mine[k] += row[k] * uj;
+                }
+                mine[j] += dot + row[j] * uj;
+            }
+            barrier.Wait();
+            {   // e[k] = sum of the partial products, worker by worker, over this worker's share of k
+                uint32_t k0, k1;
+                Share(rows, w, count, k0, k1);
+                for (uint32_t k = k0; k < k1; ++k) {
+                    double sum = 0;
+                    for (uint32_t t = 0; t < count; ++t) sum += partial[t][k];
+                    e[k] = sum;
+                }
+            }
+            barrier.Wait();
+            if (w == 0) {
+                double f = 0;
+                for (uint32_t j = 0; j <= l; ++j) {
+                    A(j, i) = A(i, j) / h;
+                    e[j] /= h;
+                    f += e[j] * A(i, j);
+                }
+                const double hh = f / (h + h);
+                for (uint32_t j = 0; j <= l; ++j) e[j] -= hh * A(i, j);
+            }
+            barrier.Wait();
+            for (uint32_t j = j0; j < j1; ++j) {
+                const double fj = u[j], gj = e[j];
+                double *row = &a[size_t(j) * n];
+                for (uint32_t k = 0; k <= j; ++k) row[k] -= fj * e[k] + gj * u[k];
+            }
+            barrier.Wait();
+        }
+    });
+}
 } // namespace
 
 bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<QlRotation> &rotations) {
@@ -58,9 +171,15 @@ bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double
     std::vector<double> e(n, 0.0);
     auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
     const uint32_t workers = TeamSize(n);
-    // Householder reduction to tridiagonal form. (Its steps are tens of microseconds of O(n^2) work each: shared out over
-    // threads they gain less than the barriers between them cost, measured; it stays on one thread.)
-    for (uint32_t i = n - 1; i >= 1; --i) {
+    // Householder reduction to tridiagonal form. Its steps are tens of microseconds of O(n^2) work each: a team shares them out only
+    // behind spin barriers (HouseholderReduceTeam; with fork-join or futex barriers the threads gained less than the barriers cost).
+    static const bool team_reduce = std::getenv("ME_HOST_TRIDIAG_SERIAL") == nullptr;
+    static const bool timing = std::getenv("ME_EIG_TIMING") != nullptr;
+    const auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    const bool on_team = team_reduce && workers > 1 && n >= 128;
+    if (on_team) HouseholderReduceTeam(n, a, d, e, workers);
+    for (uint32_t i = n - 1; i >= 1 && !on_team; --i) {
         const uint32_t l = i - 1;
         double h = 0, scale = 0;
         if (l > 0) {
@@ -111,6 +230,7 @@ bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double
     }
     d[0] = 0;
     e[0] = 0;
+    const double t_reduced = now();
     {
         // The orthogonal basis Q = H_1 H_2 .. accumulated in a matrix of its own, starting from the identity: step i reads the
         // i-th Householder vector (row i of `a` left of the diagonal, and its scaled copy in column i) and updates Q's leading
@@ -147,6 +267,17 @@ bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double
         for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
     for (uint32_t i = 1; i < n; ++i) e[i - 1] = e[i];
     e[n - 1] = 0;
+    const double t_basis = now();
+    struct Report {
+        bool On;
+        double Begin, Reduced, Basis;
+        uint32_t N;
+        std::vector<QlRotation> &Rotations;
+        ~Report() {
+            if (On) fprintf(stderr, "[me] host eigensolver n = %u: tridiagonalisation %.2f ms, basis %.2f ms, QL %.2f ms (%zu rotations)\n", N, Reduced - Begin, Basis - Reduced,
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - Basis, Rotations.size());
+        }
+    } report{timing, t_begin, t_reduced, t_basis, n, rotations};
     const double eps = std::numeric_limits<double>::epsilon();
     rotations.reserve(size_t(n) * n + size_t(n) * n / 4);
     for (uint32_t l = 0; l < n; ++l) {
