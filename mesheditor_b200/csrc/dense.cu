@@ -371,6 +371,38 @@ void GatherRows(const double *zt, uint32_t m, const uint32_t *rows, uint32_t k, 
 }
 
 namespace {
+__global__ void __launch_bounds__(32) HouseholderBasisKernel(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ h, uint32_t m, double *__restrict__ zt) {
+    extern __shared__ double column[]; // [m][32]: entry k of this lane's column of Q
+    const uint32_t lane = threadIdx.x, j = blockIdx.x * 32 + lane;
+    for (uint32_t k = 0; k < m; ++k) column[k * 32 + lane] = k == j ? 1.0 : 0.0;
+    // Reflector i changes the leading i entries of the columns j < i; for j >= i those entries are still zero, the dot product with
+    // them too, and the update a no-op: the warp's lanes need no predicate, only a common first step.
+    for (uint32_t i = blockIdx.x * 32 + 1; i < m; ++i) {
+        if (h[i] == 0.0) continue;
+        const double *ui = u + size_t(i) * m, *vi = v + size_t(i) * m;
+        double g0 = 0, g1 = 0;
+        uint32_t k = 0;
+        for (; k + 1 < i; k += 2) g0 += ui[k] * column[k * 32 + lane], g1 += ui[k + 1] * column[(k + 1) * 32 + lane];
+        if (k < i) g0 += ui[k] * column[k * 32 + lane];
+        const double g = g0 + g1;
+        for (k = 0; k < i; ++k) column[k * 32 + lane] -= g * vi[k];
+    }
+    if (j < m)
+        for (uint32_t k = 0; k < m; ++k) zt[size_t(j) * m + k] = column[k * 32 + lane];
+}
+} // namespace
+
+void HouseholderBasis(const double *u, const double *v, const double *h, uint32_t m, double *zt, cudaStream_t s, uint32_t &launches) {
+    if (m == 0) return;
+    if (m > kMaxDeviceRotationOrder) Fail(ME_BAD_ARG, "internal: HouseholderBasis takes matrices up to order %u (got %u)", kMaxDeviceRotationOrder, m);
+    const size_t bytes = size_t(m) * 32 * sizeof(double);
+    ME_CUDA(cudaFuncSetAttribute(HouseholderBasisKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
+    HouseholderBasisKernel<<<(m + 31) / 32, 32, bytes, s>>>(u, v, h, m, zt);
+    ME_CUDA(cudaGetLastError());
+    ++launches;
+}
+
+namespace {
 constexpr uint32_t kRandomStretch = 64; // consecutive values per thread
 __global__ void SimpleRandomKernel(double *__restrict__ out, size_t count) {
     const size_t first = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * kRandomStretch;

@@ -42,6 +42,12 @@ constexpr uint32_t kMaxDeviceRotationOrder = 768;
 // memory and the row shared by two consecutive rotations carried in a register. The arithmetic per entry is the host's.
 // `rotations` must be readable up to the next multiple of 512 records past `count` (staged in whole batches).
 void ApplyRotations(double *zt, uint32_t m, const QlRotation *rotations, size_t count, cudaStream_t, uint32_t &launches);
+// zt (m x m, row-major, device) <- the transposed orthogonal basis Q^T of a Householder tridiagonalisation, Q = H_1 H_2 .. H_{m-1},
+// H_i = I - u_i u_i^T / h[i] over the leading i entries (lanczos.h HouseholderTridiagonal): `u` row-major with u_i[k] at [i * m + k],
+// `v` row-major with u_i[k] / h[i] at [i * m + k] (k < i), `h` of length m (0: no reflection). One thread per column of Q, the column in
+// shared memory, every reflector a dot product and an update of its leading entries: the 5 ms this accumulation takes on the host
+// become ~1 ms beside the host's QL iteration. m <= kMaxDeviceRotationOrder.
+void HouseholderBasis(const double *u, const double *v, const double *h, uint32_t m, double *zt, cudaStream_t, uint32_t &launches);
 // out (m x k, column-major, device): column j = row rows[j] of zt (m x m, row-major): the picked eigenvectors, as TallGemm takes them.
 void GatherRows(const double *zt, uint32_t m, const uint32_t *rows, uint32_t k, double *out, cudaStream_t, uint32_t &launches);
 

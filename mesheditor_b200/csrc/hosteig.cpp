@@ -164,11 +164,11 @@ void HouseholderReduceTeam(uint32_t n, std::vector<double> &a, std::vector<doubl
 }
 } // namespace
 
-bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<QlRotation> &rotations) {
+void HouseholderTridiagonal(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<double> &e, std::vector<double> &h_out) {
     d.assign(n, 0.0);
-    rotations.clear();
-    if (n == 0) return true;
-    std::vector<double> e(n, 0.0);
+    e.assign(n, 0.0);
+    h_out.assign(n, 0.0);
+    if (n == 0) return;
     auto A = [&](uint32_t r, uint32_t c) -> double & { return a[size_t(r) * n + c]; };
     const uint32_t workers = TeamSize(n);
     // Householder reduction to tridiagonal form. Its steps are tens of microseconds of O(n^2) work each: a team shares them out only
@@ -230,7 +230,17 @@ bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double
     }
     d[0] = 0;
     e[0] = 0;
-    const double t_reduced = now();
+    // Step i reflects with I - u_i u_i^T / h_i (h_i = 0: no reflection): u_i is row i of `a` left of the diagonal, u_i / h_i column i above it.
+    h_out = d;
+    for (uint32_t i = 0; i < n; ++i) d[i] = A(i, i);
+    for (uint32_t i = 1; i < n; ++i) e[i - 1] = e[i];
+    e[n - 1] = 0;
+    if (timing) fprintf(stderr, "[me] host eigensolver n = %u: tridiagonalisation %.2f ms\n", n, now() - t_begin);
+}
+
+void HouseholderBasisHost(uint32_t n, std::vector<double> &a, const std::vector<double> &h) {
+    if (n == 0) return;
+    const uint32_t workers = TeamSize(n);
     {
         // The orthogonal basis Q = H_1 H_2 .. accumulated in a matrix of its own, starting from the identity: step i reads the
         // i-th Householder vector (row i of `a` left of the diagonal, and its scaled copy in column i) and updates Q's leading
@@ -244,7 +254,7 @@ bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double
             std::vector<double> g(n, 0.0);
             for (uint32_t i = 1; i < n; ++i) {
                 const uint32_t j1 = std::min(c1, i);
-                if (d[i] == 0.0 || c0 >= j1) continue;
+                if (h[i] == 0.0 || c0 >= j1) continue;
                 std::fill(g.begin() + c0, g.begin() + j1, 0.0);
                 for (uint32_t k = 0; k < i; ++k) {
                     const double aik = a[size_t(i) * n + k];
@@ -258,26 +268,26 @@ bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double
                 }
             }
         });
-        for (uint32_t i = 0; i < n; ++i) d[i] = A(i, i);
         a.swap(q);
     }
-    // Implicit QL on the tridiagonal matrix. The rotations mix two eigenvector columns at a time: work on the transpose
-    // so that they are contiguous rows (~3 n^3 flops). They depend only on d and e: recorded here, applied below.
+    // The rotations of the QL iteration mix two eigenvector columns at a time: work on the transpose so that they are contiguous rows.
     for (uint32_t r = 0; r < n; ++r)
         for (uint32_t c = r + 1; c < n; ++c) std::swap(a[size_t(r) * n + c], a[size_t(c) * n + r]);
-    for (uint32_t i = 1; i < n; ++i) e[i - 1] = e[i];
-    e[n - 1] = 0;
-    const double t_basis = now();
-    struct Report {
-        bool On;
-        double Begin, Reduced, Basis;
-        uint32_t N;
-        std::vector<QlRotation> &Rotations;
-        ~Report() {
-            if (On) fprintf(stderr, "[me] host eigensolver n = %u: tridiagonalisation %.2f ms, basis %.2f ms, QL %.2f ms (%zu rotations)\n", N, Reduced - Begin, Basis - Reduced,
-                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count() - Basis, Rotations.size());
-        }
-    } report{timing, t_begin, t_reduced, t_basis, n, rotations};
+}
+
+bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<QlRotation> &rotations) {
+    std::vector<double> e, h;
+    HouseholderTridiagonal(n, a, d, e, h);
+    HouseholderBasisHost(n, a, h);
+    return TridiagonalQl(n, d, e, rotations);
+}
+
+// Implicit QL on the tridiagonal matrix with diagonal d and off-diagonal e (e[i] couples i and i + 1, e[n - 1] = 0). The rotations
+// depend only on d and e: every one is recorded ({C, S, Row} mixes rows Row and Row + 1 of the transposed eigenvector matrix) and
+// applied elsewhere (SymmetricEigenApplyHost, dense.h ApplyRotations: ~3 n^3 flops).
+bool TridiagonalQl(uint32_t n, std::vector<double> &d, std::vector<double> &e, std::vector<QlRotation> &rotations) {
+    rotations.clear();
+    if (n == 0) return true;
     const double eps = std::numeric_limits<double>::epsilon();
     rotations.reserve(size_t(n) * n + size_t(n) * n / 4);
     for (uint32_t l = 0; l < n; ++l) {

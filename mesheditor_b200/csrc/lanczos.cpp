@@ -402,6 +402,8 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
     DeviceBuffer<double> Zt;       // the Ritz vectors of the last decomposition, one per row (m x m)
     DeviceBuffer<QlRotation> Rot;
     DeviceBuffer<uint32_t> Pick;
+    DeviceBuffer<double> TriU, TriV, TriH; // the reflectors of the tridiagonalisation (dense.h HouseholderBasis)
+    std::vector<double> offdiag, reflector_h, evec_t;
     bool ritz_on_device = false;
     std::function<void(const std::vector<uint32_t> &)> pick_last; // Small <- picked vectors of the last decomposition
     uint32_t iter = 0, nconv = 0;
@@ -461,12 +463,30 @@ LanczosOutcome ShiftInvertLanczos::ComputeBlock(uint32_t nev, double tol, uint32
         // (two thirds of the decomposition) on the device, where the matrix is wanted for the restart GEMM anyway. The host only
         // takes back the last b components of every vector (residual estimates, the border of the restarted T).
         const double t_ritz0 = now();
-        if (!SymmetricEigenReduce(m, evec, theta, rotations)) Fail(ME_NOT_CONVERGED, "block Lanczos: projected eigenproblem did not converge");
-        const double t_ritz1 = now();
         ritz_on_device = m >= 96 && m <= kMaxDeviceRotationOrder && !std::getenv("ME_HOST_RITZ");
+        // The orthogonal basis of the tridiagonal form is accumulated from the reflectors on the device as well (behind the operator
+        // application already in the stream), while the host runs the QL iteration on the two diagonals.
+        static const bool host_basis = std::getenv("ME_HOST_BASIS") != nullptr; // (A/B switch: the basis accumulated on host threads)
+        const bool basis_on_device = ritz_on_device && !host_basis;
+        if (basis_on_device) {
+            HouseholderTridiagonal(m, evec, theta, offdiag, reflector_h);
+            evec_t.resize(size_t(m) * m);
+            for (uint32_t i = 1; i < m; ++i) // row i of the transposed copy: u_i / h_i, contiguous
+                for (uint32_t k = 0; k < i; ++k) evec_t[size_t(i) * m + k] = evec[size_t(k) * m + i];
+            const size_t mm = size_t(m) * m;
+            TriU.Reserve(size_t(mcap) * mcap), TriV.Reserve(size_t(mcap) * mcap), TriH.Reserve(mcap), Zt.Reserve(size_t(mcap) * mcap);
+            ME_CUDA(cudaMemcpyAsync(TriU.Ptr, evec.data(), mm * sizeof(double), cudaMemcpyHostToDevice, s));
+            ME_CUDA(cudaMemcpyAsync(TriV.Ptr, evec_t.data(), mm * sizeof(double), cudaMemcpyHostToDevice, s));
+            ME_CUDA(cudaMemcpyAsync(TriH.Ptr, reflector_h.data(), m * sizeof(double), cudaMemcpyHostToDevice, s));
+            HouseholderBasis(TriU.Ptr, TriV.Ptr, TriH.Ptr, m, Zt.Ptr, s, Ws.Launches);
+            if (!TridiagonalQl(m, theta, offdiag, rotations)) Fail(ME_NOT_CONVERGED, "block Lanczos: projected eigenproblem did not converge");
+        } else if (!SymmetricEigenReduce(m, evec, theta, rotations)) {
+            Fail(ME_NOT_CONVERGED, "block Lanczos: projected eigenproblem did not converge");
+        }
+        const double t_ritz1 = now();
         if (ritz_on_device) {
             Zt.Reserve(size_t(m) * m), Rot.Reserve((rotations.size() / 512 + 1) * 512), Pick.Reserve(m);
-            ME_CUDA(cudaMemcpyAsync(Zt.Ptr, evec.data(), size_t(m) * m * sizeof(double), cudaMemcpyHostToDevice, s));
+            if (!basis_on_device) ME_CUDA(cudaMemcpyAsync(Zt.Ptr, evec.data(), size_t(m) * m * sizeof(double), cudaMemcpyHostToDevice, s));
             ME_CUDA(cudaMemcpyAsync(Rot.Ptr, rotations.data(), rotations.size() * sizeof(QlRotation), cudaMemcpyHostToDevice, s));
             ApplyRotations(Zt.Ptr, m, Rot.Ptr, rotations.size(), s, Ws.Launches);
             tail.resize(size_t(m) * b);

@@ -32,6 +32,13 @@ bool SymmetricEigen(uint32_t n, std::vector<double> &a, std::vector<double> &d);
 // `a` transposed back (a[r * n + c] = component r of vector c), on host threads; dense.h ApplyRotations is the device form.
 bool SymmetricEigenReduce(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<QlRotation> &rotations);
 void SymmetricEigenApplyHost(uint32_t n, std::vector<double> &a, const std::vector<QlRotation> &rotations);
+// The three stages of SymmetricEigenReduce on their own. Tridiagonal: leaves the diagonal in d, the off-diagonal in e (e[i] couples
+// i and i + 1, e[n - 1] = 0) and the reflectors in `a` (step i reflects with I - u_i u_i^T / h[i], h[i] = 0 meaning none: u_i in
+// row i left of the diagonal, u_i / h[i] in column i above it). BasisHost: `a` <- the transposed orthogonal basis accumulated from
+// those reflectors (dense.h HouseholderBasis is the device form). Ql: the rotation history from d and e alone.
+void HouseholderTridiagonal(uint32_t n, std::vector<double> &a, std::vector<double> &d, std::vector<double> &e, std::vector<double> &h);
+void HouseholderBasisHost(uint32_t n, std::vector<double> &a, const std::vector<double> &h);
+bool TridiagonalQl(uint32_t n, std::vector<double> &d, std::vector<double> &e, std::vector<QlRotation> &rotations);
 
 class ShiftInvertLanczos {
 public:
