@@ -272,10 +272,9 @@ __global__ void __launch_bounds__(32) ApplyRotationsKernel(double *__restrict__ 
         __syncwarp();
         const QlRotation *batch = staged + (b & 1) * kRotationBatch;
         const uint32_t in_batch = uint32_t(min(size_t(kRotationBatch), count - b * kRotationBatch));
-#pragma unroll 4
-        for (uint32_t i = 0; i < in_batch; ++i) {
-            const double c = batch[i].C, s = batch[i].S;
-            const uint32_t row = batch[i].Row;
+        const auto rotate = [&](const QlRotation &q) {
+            const double c = q.C, s = q.S;
+            const uint32_t row = q.Row;
             double upper; // row + 1
             if (held_row == row + 1) {
                 upper = held;
@@ -287,7 +286,15 @@ __global__ void __launch_bounds__(32) ApplyRotationsKernel(double *__restrict__ 
             columns[(row + 1) * 32 + lane] = s * lower + c * upper;
             held = c * lower - s * upper;
             held_row = row;
+        };
+        // Four records at a time into registers before any of their stores: the compiler cannot tell that the staged records and the
+        // columns never overlap, and would otherwise load every record behind the store of the rotation before it.
+        uint32_t i = 0;
+        for (; i + 4 <= in_batch; i += 4) {
+            const QlRotation q0 = batch[i], q1 = batch[i + 1], q2 = batch[i + 2], q3 = batch[i + 3];
+            rotate(q0), rotate(q1), rotate(q2), rotate(q3);
         }
+        for (; i < in_batch; ++i) rotate(batch[i]);
         __syncwarp();
         stage(b + 2);
     }
