@@ -292,7 +292,23 @@ __global__ void __launch_bounds__(32) ApplyRotationsKernel(double *__restrict__ 
         uint32_t i = 0;
         for (; i + 4 <= in_batch; i += 4) {
             const QlRotation q0 = batch[i], q1 = batch[i + 1], q2 = batch[i + 2], q3 = batch[i + 3];
-            rotate(q0), rotate(q1), rotate(q2), rotate(q3);
+            // A sweep of the QL iteration walks down the rows one at a time. On such a stretch the three lower rows are not touched
+            // by the stores of the rotations before them (nor held in the register), so they are read ahead of the whole group, and
+            // what is left on the chain of a rotation is its two multiply-adds on the carried row.
+            const bool descending = q1.Row + 1 == q0.Row && q2.Row + 1 == q1.Row && q3.Row + 1 == q2.Row && held_row != q1.Row && held_row != q2.Row && held_row != q3.Row;
+            if (descending) {
+                const double l1 = columns[q1.Row * 32 + lane], l2 = columns[q2.Row * 32 + lane], l3 = columns[q3.Row * 32 + lane];
+                rotate(q0); // leaves row q0.Row = q1.Row + 1 in `held`
+                columns[(q1.Row + 1) * 32 + lane] = q1.S * l1 + q1.C * held;
+                held = q1.C * l1 - q1.S * held;
+                columns[(q2.Row + 1) * 32 + lane] = q2.S * l2 + q2.C * held;
+                held = q2.C * l2 - q2.S * held;
+                columns[(q3.Row + 1) * 32 + lane] = q3.S * l3 + q3.C * held;
+                held = q3.C * l3 - q3.S * held;
+                held_row = q3.Row;
+            } else {
+                rotate(q0), rotate(q1), rotate(q2), rotate(q3);
+            }
         }
         for (; i < in_batch; ++i) rotate(batch[i]);
         __syncwarp();
