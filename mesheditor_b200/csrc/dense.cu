@@ -394,33 +394,44 @@ void GatherRows(const double *zt, uint32_t m, const uint32_t *rows, uint32_t k, 
 }
 
 namespace {
-__global__ void __launch_bounds__(32) HouseholderBasisKernel(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ h, uint32_t m, double *__restrict__ zt) {
-    extern __shared__ double column[]; // [m][32]: entry k of this lane's column of Q
-    const uint32_t lane = threadIdx.x, j = blockIdx.x * 32 + lane;
-    for (uint32_t k = 0; k < m; ++k) column[k * 32 + lane] = k == j ? 1.0 : 0.0;
+// 32 columns of Q per CTA (a lane each), the rows shared out over kBasisWarps warps (row k belongs to warp k mod kBasisWarps): every
+// reflector is a partial dot product per warp, a sum of the partials, an update of the warp's own rows - two CTA barriers. (One
+// warp per CTA, as in ApplyRotationsKernel, is bound by its own instruction stream: ~4 cycles an instruction, 2.3 ms at order 328.)
+constexpr uint32_t kBasisWarps = 8;
+__global__ void __launch_bounds__(32 * kBasisWarps) HouseholderBasisKernel(const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ h, uint32_t m, double *__restrict__ zt) {
+    extern __shared__ double column[]; // [m][32]: entry k of a lane's column of Q; then [kBasisWarps][32] partial dot products
+    double *partial = column + size_t(m) * 32;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, j = blockIdx.x * 32 + lane;
+    for (uint32_t k = warp; k < m; k += kBasisWarps) column[k * 32 + lane] = k == j ? 1.0 : 0.0;
+    __syncthreads();
     // Reflector i changes the leading i entries of the columns j < i; for j >= i those entries are still zero, the dot product with
-    // them too, and the update a no-op: the warp's lanes need no predicate, only a common first step.
+    // them too, and the update a no-op: the lanes need no predicate, only a common first step.
     for (uint32_t i = blockIdx.x * 32 + 1; i < m; ++i) {
-        if (h[i] == 0.0) continue;
+        if (h[i] == 0.0) continue; // (the same decision in every thread)
         const double *ui = u + size_t(i) * m, *vi = v + size_t(i) * m;
         double g0 = 0, g1 = 0;
-        uint32_t k = 0;
-        for (; k + 1 < i; k += 2) g0 += ui[k] * column[k * 32 + lane], g1 += ui[k + 1] * column[(k + 1) * 32 + lane];
+        uint32_t k = warp;
+        for (; k + kBasisWarps < i; k += 2 * kBasisWarps) g0 += ui[k] * column[k * 32 + lane], g1 += ui[k + kBasisWarps] * column[(k + kBasisWarps) * 32 + lane];
         if (k < i) g0 += ui[k] * column[k * 32 + lane];
-        const double g = g0 + g1;
-        for (k = 0; k < i; ++k) column[k * 32 + lane] -= g * vi[k];
+        partial[warp * 32 + lane] = g0 + g1;
+        __syncthreads();
+        double g = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < kBasisWarps; ++w) g += partial[w * 32 + lane];
+        for (k = warp; k < i; k += kBasisWarps) column[k * 32 + lane] -= g * vi[k];
+        __syncthreads();
     }
     if (j < m)
-        for (uint32_t k = 0; k < m; ++k) zt[size_t(j) * m + k] = column[k * 32 + lane];
+        for (uint32_t k = warp; k < m; k += kBasisWarps) zt[size_t(j) * m + k] = column[k * 32 + lane];
 }
 } // namespace
 
 void HouseholderBasis(const double *u, const double *v, const double *h, uint32_t m, double *zt, cudaStream_t s, uint32_t &launches) {
     if (m == 0) return;
     if (m > kMaxDeviceRotationOrder) Fail(ME_BAD_ARG, "internal: HouseholderBasis takes matrices up to order %u (got %u)", kMaxDeviceRotationOrder, m);
-    const size_t bytes = size_t(m) * 32 * sizeof(double);
+    const size_t bytes = (size_t(m) + kBasisWarps) * 32 * sizeof(double);
     ME_CUDA(cudaFuncSetAttribute(HouseholderBasisKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
-    HouseholderBasisKernel<<<(m + 31) / 32, 32, bytes, s>>>(u, v, h, m, zt);
+    HouseholderBasisKernel<<<(m + 31) / 32, 32 * kBasisWarps, bytes, s>>>(u, v, h, m, zt);
     ME_CUDA(cudaGetLastError());
     ++launches;
 }
