@@ -241,9 +241,33 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
     std::vector<std::vector<uint32_t>> rows_of(ns);
     {
         std::vector<std::vector<uint32_t>> marks(16);
+        static const bool check_followers = std::getenv("ME_SYMBOLIC_CHECK") != nullptr; // (debug: every shortcut structure against the general rule)
         const auto structure = [&](uint32_t s, std::vector<uint32_t> &mark) {
             const uint32_t first = sym.SuperFirst[s], last = sym.SuperFirst[s + 1];
             std::vector<uint32_t> &r = rows_of[s];
+            if (s > 0 && chain[s - 1] == chain[s] && !check_followers) {
+                // A later panel of a chain has one child, the panel before it, whose sorted structure already holds the rest of the
+                // chain and everything inherited from below: this panel's structure is that list past its own nodes, plus whatever
+                // its own adjacency adds (rarely anything). No marks, no sort: on the big separators this was most of the analysis.
+                const std::vector<uint32_t> &below = rows_of[s - 1];
+                r.assign(std::lower_bound(below.begin(), below.end(), last), below.end());
+                std::vector<uint32_t> extra;
+                for (uint32_t v = first; v < last; ++v) {
+                    const uint32_t old = sym.Perm[v];
+                    for (uint32_t j = rowptr[old]; j < rowptr[old + 1]; ++j) {
+                        const uint32_t u = sym.InvPerm[col[j]];
+                        if (u >= last && !std::binary_search(r.begin(), r.end(), u)) extra.push_back(u);
+                    }
+                }
+                if (!extra.empty()) {
+                    std::sort(extra.begin(), extra.end());
+                    extra.erase(std::unique(extra.begin(), extra.end()), extra.end());
+                    std::vector<uint32_t> merged(r.size() + extra.size());
+                    std::merge(r.begin(), r.end(), extra.begin(), extra.end(), merged.begin());
+                    r.swap(merged);
+                }
+                return;
+            }
             for (uint32_t v = first; v < last; ++v) {
                 const uint32_t old = sym.Perm[v];
                 for (uint32_t j = rowptr[old]; j < rowptr[old + 1]; ++j) {
@@ -306,7 +330,9 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
             for (auto &t : pool) t.join();
         }
         if (marks[0].empty()) marks[0].assign(n, UINT32_MAX);
+        const double t_subtrees = Now();
         for (const uint32_t s : top) structure(s, marks[0]);
+        if (std::getenv("ME_SYMBOLIC_TIMING")) fprintf(stderr, "[me] symbolic rows: subtrees %.1f ms on %zu threads, %zu top supernodes %.1f ms\n", 1e3 * (t_subtrees - t1), workers, top.size(), 1e3 * (Now() - t_subtrees));
     }
     sym.RowPtr.assign(size_t(ns) + 1, 0);
     for (uint32_t s = 0; s < ns; ++s) sym.RowPtr[s + 1] = sym.RowPtr[s] + rows_of[s].size();
