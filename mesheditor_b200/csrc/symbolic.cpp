@@ -409,14 +409,19 @@ void AnalyseInto(Symbolic &sym, uint32_t n, const uint32_t *rowptr, const uint32
         const auto tiles_of = [&](uint32_t s, PanelTile *panel_out, UpdateTile *update_out, uint64_t &panels, uint64_t &updates) {
             const uint32_t m = 3 * uint32_t(sym.RowPtr[s + 1] - sym.RowPtr[s]);
             panels = updates = 0;
-            for (uint32_t t = 0; t * kTile < m; ++t, ++panels)
-                if (panel_out) panel_out[panels] = {s, t};
+            if (!panel_out) panels = (m + kTile - 1) / kTile;
+            else
+                for (uint32_t t = 0; t * kTile < m; ++t, ++panels) panel_out[panels] = {s, t};
             for (uint64_t g = sym.SegPtr[s]; g < sym.SegPtr[s + 1]; ++g) {
                 const uint32_t c0 = 3 * sym.SegBegin[g], c1 = 3 * sym.SegEnd[g];
                 const uint32_t col_tiles = (c1 - c0 + kTile - 1) / kTile, row_tiles = (m - c0 + kTile - 1) / kTile;
-                for (uint32_t ct = 0; ct < col_tiles; ++ct)
-                    for (uint32_t rt = ct; rt < row_tiles; ++rt, ++updates)
-                        if (update_out) update_out[updates] = {s, uint32_t(g), uint16_t(rt), uint16_t(ct)};
+                for (uint32_t ct = 0; ct < col_tiles; ++ct) {
+                    if (!update_out) { // (the counting pass needs no walk over the tiles)
+                        updates += row_tiles > ct ? row_tiles - ct : 0;
+                        continue;
+                    }
+                    for (uint32_t rt = ct; rt < row_tiles; ++rt, ++updates) update_out[updates] = {s, uint32_t(g), uint16_t(rt), uint16_t(ct)};
+                }
             }
         };
         ParallelChunks(ns, 256, [&](size_t a, size_t b, size_t) {
